@@ -1,0 +1,322 @@
+// uaisa_capi.cu -- the C ABI of libuaisa_b200.so (declared in include/uaisa_b200.h).
+// Host-side only: handle management, scenario upload, launch geometry, error reporting.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/uaisa_b200.h"
+#include "uaisa_kernels.cuh"
+
+using namespace uaisa;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string &msg) { g_err = msg; return code; }
+int cuda_fail(cudaError_t e, const char *what) {
+    g_err = std::string(what) + ": " + cudaGetErrorString(e);
+    return UAISA_ECUDA;
+}
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return cuda_fail(e_, #call); } while (0)
+
+using KernelFn = void (*)(const Params, const Launch);
+
+}  // namespace
+
+struct UaisaHandle {
+    UaisaConfig cfg{};
+    Params P{};
+    int device = 0;
+    int A = 0;
+    int grid = 0, threads = 0;
+    size_t smem = 0;
+    KernelFn kernel = nullptr;
+    bool scenarios_set = false;
+    int64_t launches = 0;
+    std::vector<void *> allocs;
+    // lazily allocated device I/O buffers for uaisa_step_host
+    float *h_action = nullptr, *h_obs = nullptr, *h_reward = nullptr;
+    uint8_t *h_count = nullptr, *h_flags = nullptr;   // flags: done | info | finish, A each
+    int32_t *h_nbr = nullptr;
+    cudaStream_t h_stream = nullptr;
+};
+
+namespace {
+
+template <typename T>
+int dalloc(UaisaHandle *h, T **p, size_t n) {
+    void *q = nullptr;
+    cudaError_t e = cudaMalloc(&q, sizeof(T) * (n ? n : 1));
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc");
+    h->allocs.push_back(q);
+    *p = static_cast<T *>(q);
+    return UAISA_OK;
+}
+
+int launch(UaisaHandle *h, const Launch &L, void *stream) {
+    if (!h->scenarios_set) return fail(UAISA_ESTATE, "uaisa_set_scenarios has not been called");
+    h->kernel<<<h->grid, h->threads, h->smem, static_cast<cudaStream_t>(stream)>>>(h->P, L);
+    h->launches++;
+    CK(cudaGetLastError());
+    return UAISA_OK;
+}
+
+struct DeviceGuard {
+    int prev = -1; bool ok = true;
+    explicit DeviceGuard(int dev) { if (cudaGetDevice(&prev) != cudaSuccess) ok = false; else if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false; }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+}  // namespace
+
+extern "C" {
+
+const char *uaisa_last_error(void) { return g_err.c_str(); }
+int uaisa_version(void) { return 100; }
+
+int uaisa_default_config(UaisaConfig *c) {
+    if (!c) return fail(UAISA_EINVAL, "cfg is NULL");
+    std::memset(c, 0, sizeof(*c));
+    c->n_envs = 1; c->n_drones = 1; c->max_waypoints = 2; c->max_buildings = 1; c->n_scenarios = 1; c->nm = 10;
+    c->env_train = 1; c->threads_per_block = 0; c->count_pairs = 0;
+    c->goal_threshold = 0.4; c->max_acc = 1.0; c->max_angle_change = 90.0; c->dt = 1.0; c->vel_max = 1.0;
+    c->neighbor_range = 10.0; c->building_range = 5.0; c->building_zgate = 2.0; c->ctime_threshold = 2.0;
+    c->delta_t = 1.0; c->exp_radius = 0.2;
+    return UAISA_OK;
+}
+
+int uaisa_create(const UaisaConfig *cfg, UaisaHandle **out) {
+    if (!cfg || !out) return fail(UAISA_EINVAL, "NULL argument");
+    *out = nullptr;
+    if (cfg->n_envs < 1 || cfg->n_drones < 1 || cfg->n_drones > UAISA_MAX_DRONES) return fail(UAISA_EINVAL, "n_envs >= 1 and 1 <= n_drones <= 1024 required");
+    if (cfg->max_waypoints < 2 || cfg->max_waypoints > 0xFFFF) return fail(UAISA_EINVAL, "2 <= max_waypoints <= 65535 required");
+    if (cfg->max_buildings < 1 || cfg->n_scenarios < 1) return fail(UAISA_EINVAL, "max_buildings >= 1 and n_scenarios >= 1 required");
+    if (cfg->nm < 0 || cfg->nm > UAISA_MAX_NM) return fail(UAISA_EINVAL, "0 <= nm <= 16 required");
+    if ((long long)cfg->n_envs * cfg->n_drones > 0x7fffffffLL / 128) return fail(UAISA_EINVAL, "too many agents");
+    int ndev = 0;
+    CK(cudaGetDeviceCount(&ndev));
+    if (ndev < 1) return fail(UAISA_ECUDA, "no CUDA device");
+    UaisaHandle *h = new (std::nothrow) UaisaHandle();
+    if (!h) return fail(UAISA_ENOMEM, "out of host memory");
+    h->cfg = *cfg;
+    CK(cudaGetDevice(&h->device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, h->device));
+    if (prop.major != 10) { delete h; return fail(UAISA_ECUDA, "libuaisa_b200 is built for sm_100a (B200) only"); }
+    const int E = cfg->n_envs, N = cfg->n_drones;
+    h->A = E * N;
+    Params &P = h->P;
+    P.E = E; P.N = N; P.W = cfg->max_waypoints; P.M = cfg->max_buildings; P.nm = cfg->nm;
+    P.obs_dim = UAISA_OBS_SELF + UAISA_ROW * cfg->nm;
+    P.obs_pitch = P.obs_dim + cfg->nm; if ((P.obs_pitch & 1) == 0) P.obs_pitch += 1;   // odd pitch: conflict-free row writes
+    P.env_train = cfg->env_train; P.count_pairs = cfg->count_pairs;
+    P.goal_thr = cfg->goal_threshold; P.max_acc = cfg->max_acc; P.max_ang = cfg->max_angle_change; P.dt = cfg->dt;
+    P.vel_max = cfg->vel_max; P.nbr_range = cfg->neighbor_range; P.bld_range = cfg->building_range;
+    P.bld_zgate = cfg->building_zgate; P.ctime = cfg->ctime_threshold; P.delta_t = cfg->delta_t; P.exp_radius = cfg->exp_radius;
+    // launch geometry: whole envs per CTA; shrink the CTA until the grid covers the 148 SMs twice
+    int threads = cfg->threads_per_block;
+    const int minthreads = ((N + 31) / 32) * 32;
+    if (threads <= 0) {
+        threads = minthreads > 128 ? minthreads : 128;
+        while (threads / 2 >= minthreads && threads / 2 >= 32 && (E + (threads / N) - 1) / (threads / N) < 2 * prop.multiProcessorCount) threads /= 2;
+    }
+    if (threads < N || threads > 1024 || threads % 32) { delete h; return fail(UAISA_EINVAL, "threads_per_block must be a multiple of 32 in [n_drones, 1024]"); }
+    h->threads = threads; P.threads = threads; P.envs_per_cta = threads / N;
+    h->grid = (E + P.envs_per_cta - 1) / P.envs_per_cta;
+    h->smem = sizeof(double) * 8 * threads + sizeof(float) * (size_t)threads * P.obs_pitch + sizeof(int) * 2 * P.envs_per_cta;
+    const int need = cfg->nm < N - 1 ? cfg->nm : N - 1;
+    if (threads > 256) h->kernel = uaisa_env_kernel<16, 1024>;
+    else if (need <= 4) h->kernel = uaisa_env_kernel<4, 256>;
+    else if (need <= 10) h->kernel = uaisa_env_kernel<10, 256>;
+    else h->kernel = uaisa_env_kernel<16, 256>;
+    if (h->smem > (size_t)prop.sharedMemPerBlockOptin) { delete h; return fail(UAISA_EINVAL, "shared memory per CTA exceeds the device limit; lower threads_per_block"); }
+    cudaError_t e = cudaFuncSetAttribute(reinterpret_cast<const void *>(h->kernel), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem);
+    if (e != cudaSuccess) { delete h; return cuda_fail(e, "cudaFuncSetAttribute"); }
+    const size_t A = h->A, S = cfg->n_scenarios, SN = S * N;
+    int rc = UAISA_OK;
+    double *wp, *rl, *rad, *pr, *bld, *map; int *npts, *nbld, *e2s;
+    if ((rc = dalloc(h, &wp, SN * P.W * 3)) || (rc = dalloc(h, &npts, SN)) || (rc = dalloc(h, &rl, SN)) || (rc = dalloc(h, &rad, SN)) ||
+        (rc = dalloc(h, &pr, SN)) || (rc = dalloc(h, &bld, S * P.M * 4)) || (rc = dalloc(h, &nbld, S)) || (rc = dalloc(h, &map, S * 3)) ||
+        (rc = dalloc(h, &e2s, (size_t)E)) || (rc = dalloc(h, &P.pos_yaw, A)) || (rc = dalloc(h, &P.vel_pitch, A)) ||
+        (rc = dalloc(h, &P.real_len, A)) || (rc = dalloc(h, &P.max_dev, A)) || (rc = dalloc(h, &P.extra_len, A)) ||
+        (rc = dalloc(h, &P.wpf, A)) || (rc = dalloc(h, &P.ep_len, A)) || (rc = dalloc(h, &P.counters, 4))) {
+        uaisa_destroy(h);
+        return rc;
+    }
+    P.wp = wp; P.npts = npts; P.route_len = rl; P.radius = rad; P.prio = pr; P.bld = bld; P.nbld = nbld; P.map = map; P.env2scn = e2s;
+    cudaMemset(P.extra_len, 0, sizeof(float) * A); cudaMemset(P.ep_len, 0, sizeof(int) * A); cudaMemset(P.counters, 0, 32);
+    *out = h;
+    return UAISA_OK;
+}
+
+int uaisa_destroy(UaisaHandle *h) {
+    if (!h) return UAISA_OK;
+    DeviceGuard g(h->device);
+    cudaDeviceSynchronize();
+    for (void *p : h->allocs) cudaFree(p);
+    if (h->h_stream) cudaStreamDestroy(h->h_stream);
+    delete h;
+    return UAISA_OK;
+}
+
+int uaisa_set_scenarios(UaisaHandle *h, const double *waypoints, const int32_t *n_points, const double *radius, const double *priority,
+                        const double *buildings, const int32_t *n_buildings, const double *map_size, const int32_t *env2scenario) {
+    if (!h || !waypoints || !n_points || !radius || !priority || !buildings || !n_buildings || !map_size || !env2scenario)
+        return fail(UAISA_EINVAL, "NULL argument");
+    const Params &P = h->P;
+    const size_t S = h->cfg.n_scenarios, N = P.N, SN = S * N, W = P.W;
+    std::vector<double> rl(SN);
+    for (size_t q = 0; q < SN; q++) {
+        if (n_points[q] < 2 || n_points[q] > (int)W) return fail(UAISA_EINVAL, "n_points must be in [2, max_waypoints] (drone.py:46-48 reads waypoints[1])");
+        double tot = 0.0;   // drone.calculate_total_length (drone.py:409-429)
+        const double *w = waypoints + q * W * 3;
+        for (int i = 0; i + 1 < n_points[q]; i++) {
+            double dx = w[3 * (i + 1)] - w[3 * i], dy = w[3 * (i + 1) + 1] - w[3 * i + 1], dz = w[3 * (i + 1) + 2] - w[3 * i + 2];
+            tot += std::sqrt(dx * dx + dy * dy + dz * dz);
+        }
+        rl[q] = tot;
+    }
+    for (size_t s = 0; s < S; s++) if (n_buildings[s] < 0 || n_buildings[s] > P.M) return fail(UAISA_EINVAL, "n_buildings out of range");
+    for (int e = 0; e < P.E; e++) if (env2scenario[e] < 0 || env2scenario[e] >= (int)S) return fail(UAISA_EINVAL, "env2scenario out of range");
+    DeviceGuard g(h->device);
+    CK(cudaMemcpy(const_cast<double *>(P.wp), waypoints, sizeof(double) * SN * W * 3, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(const_cast<int *>(P.npts), n_points, sizeof(int) * SN, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(const_cast<double *>(P.route_len), rl.data(), sizeof(double) * SN, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(const_cast<double *>(P.radius), radius, sizeof(double) * SN, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(const_cast<double *>(P.prio), priority, sizeof(double) * SN, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(const_cast<double *>(P.bld), buildings, sizeof(double) * S * P.M * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(const_cast<int *>(P.nbld), n_buildings, sizeof(int) * S, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(const_cast<double *>(P.map), map_size, sizeof(double) * S * 3, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(const_cast<int *>(P.env2scn), env2scenario, sizeof(int) * P.E, cudaMemcpyHostToDevice));
+    // a defined (if meaningless) state for the first MODE_RESET load
+    CK(cudaMemset(P.pos_yaw, 0, sizeof(float4) * h->A)); CK(cudaMemset(P.vel_pitch, 0, sizeof(float4) * h->A));
+    CK(cudaMemset(P.real_len, 0, sizeof(float) * h->A)); CK(cudaMemset(P.max_dev, 0, sizeof(float) * h->A));
+    { std::vector<int> one((size_t)h->A, 1); CK(cudaMemcpy(P.wpf, one.data(), sizeof(int) * h->A, cudaMemcpyHostToDevice)); }
+    h->scenarios_set = true;
+    int rc = uaisa_reset(h, nullptr, nullptr, nullptr, nullptr, nullptr);
+    if (rc) return rc;
+    CK(cudaDeviceSynchronize());
+    return UAISA_OK;
+}
+
+int uaisa_step(UaisaHandle *h, const float *action, float *obs, uint8_t *count, int32_t *nbr, float *reward, uint8_t *done,
+               uint8_t *info, uint8_t *finish, void *stream) {
+    return uaisa_rollout(h, 1, action, obs, count, nbr, reward, done, info, finish, 0, 0, stream);
+}
+
+int uaisa_rollout(UaisaHandle *h, int32_t T, const float *action, float *obs, uint8_t *count, int32_t *nbr, float *reward,
+                  uint8_t *done, uint8_t *info, uint8_t *finish, int32_t auto_reset, int32_t max_ep_len, void *stream) {
+    if (!h || !action) return fail(UAISA_EINVAL, "NULL handle or action");
+    if (T < 1) return fail(UAISA_EINVAL, "T must be >= 1");
+    Launch L{};
+    L.mode = MODE_STEP; L.T = T; L.auto_reset = auto_reset ? 1 : 0; L.max_ep_len = max_ep_len; L.epoch_ended = 0;
+    L.action = action; L.obs = obs; L.count = count; L.nbr = nbr; L.reward = reward; L.done = done; L.info = info; L.finish = finish;
+    return launch(h, L, stream);
+}
+
+int uaisa_reset(UaisaHandle *h, const uint8_t *agent_mask, float *obs, uint8_t *count, int32_t *nbr, void *stream) {
+    if (!h) return fail(UAISA_EINVAL, "NULL handle");
+    Launch L{};
+    L.mode = MODE_RESET; L.T = 1; L.mask = agent_mask; L.obs = obs; L.count = count; L.nbr = nbr;
+    return launch(h, L, stream);
+}
+
+int uaisa_observe(UaisaHandle *h, const uint8_t *env_mask, float *obs, uint8_t *count, int32_t *nbr, void *stream) {
+    if (!h) return fail(UAISA_EINVAL, "NULL handle");
+    Launch L{};
+    L.mode = MODE_OBSERVE; L.T = 1; L.mask = env_mask; L.obs = obs; L.count = count; L.nbr = nbr;
+    return launch(h, L, stream);
+}
+
+int uaisa_autoreset(UaisaHandle *h, const uint8_t *done, const uint8_t *finish, int32_t max_ep_len, int32_t epoch_ended, float *obs,
+                    uint8_t *count, int32_t *nbr, uint8_t *reset_mask, uint8_t *path_cut, void *stream) {
+    if (!h || !done || !finish) return fail(UAISA_EINVAL, "NULL handle / done / finish");
+    Launch L{};
+    L.mode = MODE_AUTORESET; L.T = 1; L.max_ep_len = max_ep_len; L.epoch_ended = epoch_ended ? 1 : 0;
+    L.done_in = done; L.finish_in = finish; L.obs = obs; L.count = count; L.nbr = nbr; L.reset_mask = reset_mask; L.path_cut = path_cut;
+    return launch(h, L, stream);
+}
+
+static int copy_state(UaisaHandle *h, const UaisaStateView *v, bool to_handle, void *stream) {
+    if (!h || !v) return fail(UAISA_EINVAL, "NULL argument");
+    const Params &P = h->P;
+    const size_t A = h->A;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+#define CP(field, hp, bytes) do { if (v->field) { if (to_handle) CK(cudaMemcpyAsync(hp, v->field, bytes, cudaMemcpyDefault, s)); else CK(cudaMemcpyAsync(v->field, hp, bytes, cudaMemcpyDefault, s)); } } while (0)
+    CP(pos_yaw, P.pos_yaw, sizeof(float4) * A); CP(vel_pitch, P.vel_pitch, sizeof(float4) * A);
+    CP(real_len, P.real_len, sizeof(float) * A); CP(max_dev, P.max_dev, sizeof(float) * A);
+    CP(extra_len, P.extra_len, sizeof(float) * A); CP(wp_flags, P.wpf, sizeof(int) * A);
+#undef CP
+    return UAISA_OK;
+}
+int uaisa_get_state(UaisaHandle *h, const UaisaStateView *dst, void *stream) { return copy_state(h, dst, false, stream); }
+int uaisa_set_state(UaisaHandle *h, const UaisaStateView *src, void *stream) { return copy_state(h, src, true, stream); }
+
+int uaisa_cal_des(UaisaHandle *h, float *des, void *stream) {
+    if (!h || !des) return fail(UAISA_EINVAL, "NULL argument");
+    if (!h->scenarios_set) return fail(UAISA_ESTATE, "uaisa_set_scenarios has not been called");
+    uaisa_cal_des_kernel<<<(h->A + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(h->P, des);
+    h->launches++;
+    CK(cudaGetLastError());
+    return UAISA_OK;
+}
+
+int uaisa_indicators(UaisaHandle *h, float *max_dev, float *extra_len, void *stream) {
+    if (!h) return fail(UAISA_EINVAL, "NULL handle");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (max_dev) CK(cudaMemcpyAsync(max_dev, h->P.max_dev, sizeof(float) * h->A, cudaMemcpyDefault, s));
+    if (extra_len) CK(cudaMemcpyAsync(extra_len, h->P.extra_len, sizeof(float) * h->A, cudaMemcpyDefault, s));
+    return UAISA_OK;
+}
+
+int uaisa_get_counters(UaisaHandle *h, int64_t *in_range_pairs, int64_t *cone_evals, int64_t *nonfinite_obs, void *stream) {
+    if (!h) return fail(UAISA_EINVAL, "NULL handle");
+    unsigned long long c[4] = {0, 0, 0, 0};
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    CK(cudaMemcpyAsync(c, h->P.counters, sizeof(c), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemsetAsync(h->P.counters, 0, sizeof(c), s));
+    CK(cudaStreamSynchronize(s));
+    if (in_range_pairs) *in_range_pairs = (int64_t)c[0];
+    if (cone_evals) *cone_evals = (int64_t)c[1];
+    if (nonfinite_obs) *nonfinite_obs = (int64_t)c[2];
+    return UAISA_OK;
+}
+
+int64_t uaisa_launch_count(const UaisaHandle *h) { return h ? h->launches : 0; }
+
+int uaisa_step_host(UaisaHandle *h, const float *action, float *obs, uint8_t *count, int32_t *nbr, float *reward, uint8_t *done,
+                    uint8_t *info, uint8_t *finish) {
+    if (!h || !action) return fail(UAISA_EINVAL, "NULL handle or action");
+    DeviceGuard g(h->device);
+    const size_t A = h->A; const Params &P = h->P;
+    if (!h->h_action) {
+        int rc;
+        if ((rc = dalloc(h, &h->h_action, A * 3)) || (rc = dalloc(h, &h->h_obs, A * P.obs_dim)) || (rc = dalloc(h, &h->h_reward, A)) ||
+            (rc = dalloc(h, &h->h_count, A)) || (rc = dalloc(h, &h->h_flags, A * 3)) || (rc = dalloc(h, &h->h_nbr, A * (P.nm ? P.nm : 1))))
+            return rc;
+        CK(cudaStreamCreateWithFlags(&h->h_stream, cudaStreamNonBlocking));
+    }
+    cudaStream_t s = h->h_stream;
+    CK(cudaMemcpyAsync(h->h_action, action, sizeof(float) * A * 3, cudaMemcpyHostToDevice, s));
+    int rc = uaisa_step(h, h->h_action, obs ? h->h_obs : nullptr, count ? h->h_count : nullptr, nbr ? h->h_nbr : nullptr,
+                        reward ? h->h_reward : nullptr, done ? h->h_flags : nullptr, info ? h->h_flags + A : nullptr,
+                        finish ? h->h_flags + 2 * A : nullptr, s);
+    if (rc) return rc;
+    if (obs) CK(cudaMemcpyAsync(obs, h->h_obs, sizeof(float) * A * P.obs_dim, cudaMemcpyDeviceToHost, s));
+    if (count) CK(cudaMemcpyAsync(count, h->h_count, A, cudaMemcpyDeviceToHost, s));
+    if (nbr) CK(cudaMemcpyAsync(nbr, h->h_nbr, sizeof(int32_t) * A * P.nm, cudaMemcpyDeviceToHost, s));
+    if (reward) CK(cudaMemcpyAsync(reward, h->h_reward, sizeof(float) * A, cudaMemcpyDeviceToHost, s));
+    if (done) CK(cudaMemcpyAsync(done, h->h_flags, A, cudaMemcpyDeviceToHost, s));
+    if (info) CK(cudaMemcpyAsync(info, h->h_flags + A, A, cudaMemcpyDeviceToHost, s));
+    if (finish) CK(cudaMemcpyAsync(finish, h->h_flags + 2 * A, A, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return UAISA_OK;
+}
+
+}  // extern "C"

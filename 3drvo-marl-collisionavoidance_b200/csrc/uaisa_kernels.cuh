@@ -1,0 +1,229 @@
+// uaisa_kernels.cuh -- device side of libuaisa_b200.so (sm_100a only).
+//
+// One kernel template runs every mode of the env hot path; one thread owns one drone, one CTA owns a
+// block of whole environments, so all coupling (the pairwise RVO passes) stays inside the CTA:
+//
+//   PASS A  (pre-move states)   rvo reward            ir_gym.py:50-133, rvo_inter.py:63-83
+//   MOVE                        kinematics + FSM      drone.py:96-129,431-490 (env_base.py:135-144)
+//   PASS B  (post-move states)  collision / obs / reward   ir_gym.py:136-311, rvo_inter.py:20-61
+//   [AUTO-RESET + OBSERVE]      trainer reset policy  multi_ppo.py:221-281, ir_gym.py:372-383
+//
+// Numerics: mutable state lives in HBM as fp32 SoA (float4 pos+yaw, float4 vel+pitch, ...).  Inside a
+// step everything is evaluated in fp64 from those fp32 values -- every discrete output of the reference
+// (flags, neighbour order, the 2-dp/3-dp rounded observations and rewards) hangs off comparisons and
+// decimal roundings of fp64 quantities, and an fp32 evaluation flips them at 1e-5..1e-3 per value
+// (SURVEY.md section 7).  The post-move state is exchanged between the threads of an env in fp64 through
+// shared memory and only rounded to fp32 when it is written back, so one step started from the same
+// fp32 state reproduces the fp64 reference to the last ulp of libm.  The file is compiled with
+// -fmad=false: the only fused operations are the explicit fma() chains that mirror numpy's dot/norm.
+#pragma once
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <stdint.h>
+
+namespace uaisa {
+
+enum Mode : int { MODE_STEP = 0, MODE_OBSERVE = 1, MODE_RESET = 2, MODE_AUTORESET = 3 };
+
+constexpr int OBS_SELF = 12;
+constexpr int ROW = 9;
+constexpr int FLAG_ARRIVE = 1 << 16;
+constexpr int FLAG_DEST = 1 << 17;
+constexpr int WP_MASK = 0xFFFF;
+
+struct Params {
+    // geometry
+    int E, N, W, M, nm, obs_dim, obs_pitch;
+    int envs_per_cta, threads;
+    int env_train, count_pairs;
+    // hyper-parameters (reference constructor defaults, see include/uaisa_b200.h)
+    double goal_thr, max_acc, max_ang, dt, vel_max, nbr_range, bld_range, bld_zgate, ctime, delta_t, exp_radius;
+    // scenario constants (device, fp64, shared by envs -> L2/L1 resident)
+    const double *wp; const int *npts; const double *route_len; const double *radius; const double *prio;
+    const double *bld; const int *nbld; const double *map; const int *env2scn;
+    // mutable state (device, fp32 SoA)
+    float4 *pos_yaw; float4 *vel_pitch; float *real_len; float *max_dev; float *extra_len; int *wpf; int *ep_len;
+    unsigned long long *counters;  // [0] in-range pairs, [1] cone evaluations, [2] non-finite observations
+};
+
+struct Launch {
+    int mode, T, auto_reset, max_ep_len, epoch_ended;
+    const float *action;         // [T][A][3]
+    const uint8_t *mask;         // MODE_RESET: agent mask; MODE_OBSERVE: env mask; (NULL = all)
+    const uint8_t *done_in, *finish_in;  // MODE_AUTORESET
+    float *obs; uint8_t *count; int *nbr; float *reward; uint8_t *done, *info, *finish;
+    uint8_t *reset_mask, *path_cut;
+};
+
+// ---- numpy / python arithmetic primitives (see oracle/uaisa_oracle.c for the derivation) ----------
+__device__ __forceinline__ double np_dot3(double a0, double a1, double a2, double b0, double b1, double b2) {
+    return fma(a2, b2, fma(a1, b1, a0 * b0));
+}
+__device__ __forceinline__ double np_norm3(double a0, double a1, double a2) { return sqrt(np_dot3(a0, a1, a2, a0, a1, a2)); }
+__device__ __forceinline__ double np_norm2(double a0, double a1) { return sqrt(fma(a1, a1, a0 * a0)); }
+__device__ __forceinline__ double np_clip(double x, double lo, double hi) { return fmin(fmax(x, lo), hi); }
+__device__ __forceinline__ double np_round2(double x) { return rint(x * 100.0) / 100.0; }
+__device__ __forceinline__ double np_round3(double x) { return rint(x * 1000.0) / 1000.0; }
+// builtin round(x, 2) of a Python float, returned in hundredths (exact decimal rounding, ties to even)
+__device__ __forceinline__ double py_round2_hundredths(double x) {
+    double hi = x * 100.0, lo = fma(x, 100.0, -hi), r = rint(hi), d = hi - r;
+    if (d == 0.5 && lo > 0.0) r += 1.0; else if (d == -0.5 && lo < 0.0) r -= 1.0;
+    return r;
+}
+__device__ __forceinline__ double py_mod360(double x) {  // drone.py:457, Python float %
+    if (x > 0.0 && x < 360.0) return x;
+    double m = fmod(x, 360.0);
+    if (m != 0.0) { if (m < 0.0) m += 360.0; } else m = 0.0;
+    return m;
+}
+
+// ---- per-thread drone ---------------------------------------------------------------------------
+struct Drone {
+    double px, py, pz, vx, vy, vz, yaw, pitch, real_len, max_dev;
+    int i, flags;   // waypoint index, FLAG_ARRIVE | FLAG_DEST
+};
+
+struct Consts {   // per-drone scenario constants
+    const double *wp;   // this drone's waypoint list [W][3]
+    double radius, prio, route_len;
+    int n;              // n_points
+};
+
+__device__ __forceinline__ void load3(const double *p, double &x, double &y, double &z) { x = __ldg(p); y = __ldg(p + 1); z = __ldg(p + 2); }
+
+__device__ __forceinline__ bool within_goal(const Params &P, double px, double py, double pz, const double *q) {
+    double qx, qy, qz; load3(q, qx, qy, qz);
+    return np_norm3(px - qx, py - qy, pz - qz) <= P.goal_thr;   // drone.py:172-192
+}
+
+// drone.calculate_deviation (drone.py:366-406)
+__device__ __forceinline__ double deviation(const double *st, const double *en, double x0, double y0, double z0) {
+    double x1, y1, z1, x2, y2, z2; load3(st, x1, y1, z1); load3(en, x2, y2, z2);
+    double dx = x2 - x1, dy = y2 - y1, dz = z2 - z1;
+    double mag = sqrt(dx * dx + dy * dy + dz * dz);
+    if (mag == 0.0) return 0.0;
+    double dxh = dx / mag, dyh = dy / mag, dzh = dz / mag;
+    double px = x0 - x1, py = y0 - y1, pz = z0 - z1;
+    double t = px * dxh + py * dyh + pz * dzh;
+    double qx = x1 + t * dxh, qy = y1 + t * dyh, qz = z1 + t * dzh;
+    double ex = x0 - qx, ey = y0 - qy, ez = z0 - qz;
+    return sqrt(ex * ex + ey * ey + ez * ez);
+}
+
+// drone.cal_des_vel (drone.py:199-210, 319-352)
+__device__ __forceinline__ void cal_des_vel(const Params &P, double px, double py, double pz, const double *cur,
+                                            double &d0, double &d1, double &d2) {
+    double cx, cy, cz; load3(cur, cx, cy, cz);
+    double fx = cx - px, fy = cy - py, fz = cz - pz;
+    double dis = np_norm3(fx, fy, fz);
+    if (dis > P.goal_thr) {
+#ifdef UAISA_LIBM_DES
+        double az = atan2(fy, fx), el = atan2(fz, np_norm2(fx, fy));
+        double sa, ca, se, ce; sincos(az, &sa, &ca); sincos(el, &se, &ce);
+        d0 = np_round3(P.vel_max * (ca * ce)); d1 = np_round3(P.vel_max * (sa * ce)); d2 = np_round3(P.vel_max * se);
+#else
+        // cos(atan2(fy,fx))*cos(atan2(fz,h)) == fx/dis etc. up to a few ulp (<<1e-3 rounding quantum);
+        // h == 0 gives (0,0,+-1) on both routes.
+        d0 = np_round3(P.vel_max * (fx / dis)); d1 = np_round3(P.vel_max * (fy / dis)); d2 = np_round3(P.vel_max * (fz / dis));
+#endif
+    } else {
+        d0 = d1 = d2 = 0.0;
+    }
+}
+
+// vel_obs3D.cal_vo_exp_tim (vel_obs3D.py:145-182)
+__device__ __forceinline__ double cal_vo_exp_tim(double rx, double ry, double rz, double ovx, double ovy, double ovz, double ra, double rb) {
+    double r = ra + rb;
+    double vx = -ovx, vy = -ovy, vz = -ovz;
+    double a = vx * vx + vy * vy + vz * vz;
+    double b = 2.0 * rx * vx + 2.0 * ry * vy + 2.0 * rz * vz;
+    double c = rx * rx + ry * ry + rz * rz - r * r;
+    if (c <= 0.0) return 0.0;
+    double temp = b * b - 4.0 * a * c;
+    if (temp <= 0.0) return CUDART_INF;
+    double sq = sqrt(temp);
+    double t1 = (-b + sq) / (2.0 * a), t2 = (-b - sq) / (2.0 * a);
+    if (t1 < 0.0 && t2 < 0.0) return -1.0;
+    double t3 = t1 >= 0.0 ? t1 : CUDART_INF, t4 = t2 >= 0.0 ? t2 : CUDART_INF;
+    return t4 < t3 ? t4 : t3;
+}
+
+enum PairBits : int { PB_EVAL = 1, PB_COL = 2, PB_FULL = 4, PB_VO = 8 };
+
+// rvo_inter.preprocess neighbour test (rvo_inter.py:89-97) + config_vo_circle2 (rvo_inter.py:116-196).
+// (ax,ay,az) is the action with the |a|<1e-5 -> 0 substitution already applied.
+__device__ __forceinline__ int vo_pair(const Params &P, double x, double y, double z, double vx, double vy, double vz,
+                                       double r, double pra, double mx, double my, double mz, double mvx, double mvy,
+                                       double mvz, double mr, double prb, double ax, double ay, double az,
+                                       double &t_out, double &alpha_h, double &md, double &iet) {
+    if (x == mx && y == my && z == mz) return 0;
+    if (!(np_norm3(x - mx, y - my, z - mz) <= P.nbr_range)) return 0;
+    double rel_x = mx - x, rel_y = my - y, rel_z = mz - z;
+    double dis = sqrt(rel_y * rel_y + rel_x * rel_x + rel_z * rel_z);
+    double R = r + mr;
+    bool col = P.env_train ? (dis <= R) : (dis <= r - P.exp_radius + mr);
+    if (col) return PB_EVAL | PB_COL;
+    double dotp = vx * rel_x + vy * rel_y + vz * rel_z;
+    if (dotp <= 0.0) return PB_EVAL;
+    alpha_h = py_round2_hundredths(asin(R / np_norm3(rel_x, rel_y, rel_z)));   // get_alpha, vel_obs3D.py:8-17
+    double pr = pra / (pra + prb);                                             // get_PAA, vel_obs3D.py:19-32
+    double PAAx = pr * (2.0 * x + (vx + mvx) * 1.0), PAAy = pr * (2.0 * y + (vy + mvy) * 1.0), PAAz = pr * (2.0 * z + (vz + mvz) * 1.0);
+    double Bx = x + 2.0 * ax * P.delta_t - PAAx, By = y + 2.0 * ay * P.delta_t - PAAy, Bz = z + 2.0 * az * P.delta_t - PAAz;
+    double AB = np_norm3(rel_x, rel_y, rel_z) * np_norm3(Bx, By, Bz);
+    double cosang = (AB != 0.0) ? np_dot3(rel_x, rel_y, rel_z, Bx, By, Bz) / AB : 0.0;
+    double beta_h = rint(acos(cosang) * 100.0);            // get_beta: unclamped arccos, numpy rounding
+    int bits = PB_EVAL | PB_FULL;
+    double exp_time = CUDART_INF;
+    if (alpha_h > beta_h) {                                 // alpha > beta on the rounded values; NaN beta -> outside
+        double rel_vx = 2.0 * ax - mvx - vx, rel_vy = 2.0 * ay - mvy - vy, rel_vz = 2.0 * az - mvz - vz;
+        exp_time = cal_vo_exp_tim(rel_x, rel_y, rel_z, rel_vx, rel_vy, rel_vz, r, mr);
+        if (exp_time < P.ctime) bits |= PB_VO; else exp_time = CUDART_INF;
+    }
+    t_out = exp_time;
+    md = dis - mr;
+    iet = 1.0 / (exp_time + 0.2);
+    return bits;
+}
+
+// ---- top-nm neighbour list (rvo_inter.py:50-59) ------------------------------------------------------
+// Kept sorted most-urgent-first; "more urgent" = later in the reference's stable descending sort by
+// (-iet, md): larger iet, then smaller md, then larger drone index.
+template <int MAXR>
+struct TopList {
+    double iet[MAXR], md[MAXR];
+    int j[MAXR], ah[MAXR];
+    int cnt;
+    __device__ __forceinline__ void clear() { cnt = 0; }
+    __device__ __forceinline__ void insert(int cap, double c_iet, double c_md, int c_j, int c_ah) {
+        bool placed = false;
+#pragma unroll
+        for (int s = 0; s < MAXR; s++) {
+            bool valid = s < cnt;
+            bool sw = valid && ((c_iet > iet[s]) || (c_iet == iet[s] && (c_md < md[s] || (c_md == md[s] && c_j > j[s]))));
+            if (sw) {
+                double t0 = iet[s]; iet[s] = c_iet; c_iet = t0;
+                double t1 = md[s]; md[s] = c_md; c_md = t1;
+                int t2 = j[s]; j[s] = c_j; c_j = t2;
+                int t3 = ah[s]; ah[s] = c_ah; c_ah = t3;
+            }
+            if (!valid && !placed && s < cap) { iet[s] = c_iet; md[s] = c_md; j[s] = c_j; ah[s] = c_ah; placed = true; }
+        }
+        if (placed) cnt++;
+    }
+};
+
+// ir_gym.calculate_angle_between_vectors, 2nd definition (ir_gym.py:447-473)
+__device__ __forceinline__ double angle_between(double A0, double A1, double A2, double B0, double B1, double B2) {
+    const double eps = 1e-8;
+    double magA = sqrt(A0 * A0 + A1 * A1 + A2 * A2 + eps), magB = sqrt(B0 * B0 + B1 * B1 + B2 * B2 + eps);
+    double dp = A0 * B0 + A1 * B1 + A2 * B2;
+    if (magA < 1e-6 || magB < 1e-6) return 0.0;
+    double c = np_clip(dp / (magA * magB), -1.0 + eps, 1.0 - eps);
+    return acos(c);
+}
+
+template <int MAXR, int MAXT>
+__global__ void uaisa_env_kernel(const __grid_constant__ Params P, const __grid_constant__ Launch L);
+__global__ void uaisa_cal_des_kernel(const __grid_constant__ Params P, float *des);
+
+}  // namespace uaisa

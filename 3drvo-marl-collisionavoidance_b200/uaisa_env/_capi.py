@@ -1,0 +1,81 @@
+"""ctypes binding of libuaisa_b200.so (include/uaisa_b200.h).  No CPU fallback: if the library is
+missing or the device is not a B200 the calls raise."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libuaisa_b200.so")
+
+SYMBOLS = (
+    "uaisa_last_error", "uaisa_version", "uaisa_default_config", "uaisa_create", "uaisa_destroy",
+    "uaisa_set_scenarios", "uaisa_step", "uaisa_reset", "uaisa_observe", "uaisa_autoreset", "uaisa_rollout",
+    "uaisa_get_state", "uaisa_set_state", "uaisa_cal_des", "uaisa_indicators", "uaisa_get_counters",
+    "uaisa_launch_count", "uaisa_step_host",
+)
+
+
+class UaisaConfig(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in (
+        "n_envs", "n_drones", "max_waypoints", "max_buildings", "n_scenarios", "nm", "env_train",
+        "threads_per_block", "count_pairs", "reserved")] + [(n, C.c_double) for n in (
+        "goal_threshold", "max_acc", "max_angle_change", "dt", "vel_max", "neighbor_range", "building_range",
+        "building_zgate", "ctime_threshold", "delta_t", "exp_radius")]
+
+
+class UaisaStateView(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("pos_yaw", "vel_pitch", "real_len", "max_dev", "extra_len", "wp_flags")]
+
+
+class UaisaError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib():
+    """Load the shared library (build it first with __graft_entry__.build() / make -C csrc)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise UaisaError("libuaisa_b200.so not built (%s); run `make -C %s`" % (LIB_PATH, os.path.join(os.path.dirname(_HERE), "csrc")))
+        L = C.CDLL(LIB_PATH)
+        vp, i32 = C.c_void_p, C.c_int32
+        L.uaisa_last_error.restype = C.c_char_p
+        L.uaisa_version.restype = C.c_int
+        L.uaisa_default_config.argtypes = [C.POINTER(UaisaConfig)]
+        L.uaisa_create.argtypes = [C.POINTER(UaisaConfig), C.POINTER(vp)]
+        L.uaisa_destroy.argtypes = [vp]
+        L.uaisa_set_scenarios.argtypes = [vp] * 9
+        L.uaisa_step.argtypes = [vp] * 10
+        L.uaisa_reset.argtypes = [vp] * 6
+        L.uaisa_observe.argtypes = [vp] * 6
+        L.uaisa_autoreset.argtypes = [vp, vp, vp, i32, i32, vp, vp, vp, vp, vp, vp]
+        L.uaisa_rollout.argtypes = [vp, i32] + [vp] * 8 + [i32, i32, vp]
+        L.uaisa_get_state.argtypes = [vp, C.POINTER(UaisaStateView), vp]
+        L.uaisa_set_state.argtypes = [vp, C.POINTER(UaisaStateView), vp]
+        L.uaisa_cal_des.argtypes = [vp, vp, vp]
+        L.uaisa_indicators.argtypes = [vp, vp, vp, vp]
+        L.uaisa_get_counters.argtypes = [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64), vp]
+        L.uaisa_launch_count.argtypes = [vp]
+        L.uaisa_launch_count.restype = C.c_int64
+        L.uaisa_step_host.argtypes = [vp] * 9
+        for name in SYMBOLS:
+            fn = getattr(L, name)
+            if fn.restype is C.c_int and name not in ("uaisa_version",):
+                fn.restype = C.c_int
+        _lib = L
+    return _lib
+
+
+def check(rc: int):
+    if rc != 0:
+        raise UaisaError("libuaisa_b200 error %d: %s" % (rc, lib().uaisa_last_error().decode("utf-8", "replace")))
+
+
+def default_config() -> UaisaConfig:
+    c = UaisaConfig()
+    check(lib().uaisa_default_config(C.byref(c)))
+    return c

@@ -176,7 +176,7 @@ def scenario_world3() -> ScenarioSet:
 
 def scenario_c3(seed: int = 0, n_scenarios: int = 1, n_drones: int = 16, n_buildings: int = 8) -> ScenarioSet:
     """configs[2]: N=16 on a ring of radius 4 about (5,5), z 5 -> antipodal goals at z 2, one or two
-    intermediate waypoints, M cylinders (x,y~U(2,8), h~U(3,5), r~U(0.5,1.0)) at least 1.0 from any waypoint."""
+    intermediate waypoints, M cylinders (x,y~U(2,8), h~U(3,5), r~U(0.5,1.0)) clear of every waypoint."""
     rng = np.random.default_rng(seed)
     out = []
     for _ in range(n_scenarios):
@@ -197,11 +197,14 @@ def scenario_c3(seed: int = 0, n_scenarios: int = 1, n_drones: int = 16, n_build
         allw = np.concatenate([np.asarray(w) for w in wl], axis=0)
         bl = []
         tries = 0
-        while len(bl) < n_buildings and tries < 10000:
+        margin = 0.3   # clearance between a cylinder's surface and every waypoint; relaxed if the map is too crowded
+        while len(bl) < n_buildings:
             tries += 1
+            if tries % 2000 == 0:
+                margin *= 0.5
             x, y = rng.uniform(2, 8, 2)
             h, r = rng.uniform(3, 5), rng.uniform(0.5, 1.0)
-            if np.min(np.hypot(allw[:, 0] - x, allw[:, 1] - y)) < r + 1.0:
+            if np.min(np.hypot(allw[:, 0] - x, allw[:, 1] - y)) < r + margin:
                 continue
             bl.append([round(float(x), 2), round(float(y), 2), round(float(h), 2), round(float(r), 2)])
         out.append(ScenarioSet.from_dict({"drone_num": n_drones, "map_size": [10, 10, 5], "waypoints_list": wl,

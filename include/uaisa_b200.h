@@ -1,0 +1,150 @@
+/*
+ * uaisa_b200.h -- C ABI of libuaisa_b200.so: the batched 3-D RVO multi-drone environment step on
+ * NVIDIA B200 (sm_100a).  This is the drop-in boundary for the hot path of
+ * ZSHCRWY25/3DRVO-MARL-CollisionAvoidance.
+ *
+ * The reference has no FFI: its boundary is the duck-typed Python object `mdin`
+ * (uaisa_env/drone_envs/mdin.py:6-49) that train/policy/multi_ppo.py drives.  Each entry point below
+ * names the reference method it replaces; the Python side that binds these symbols with ctypes is
+ * `3drvo-marl-collisionavoidance_b200/uaisa_env/_capi.py`.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative UAISA_E* code; nothing throws or aborts
+ *     across the boundary; uaisa_last_error() returns a thread-local message for the last failure.
+ *   - the handle is opaque and library-owned, bound to the CUDA device current at uaisa_create().
+ *   - unless a parameter is marked HOST, I/O buffers are caller-owned DEVICE pointers (e.g. torch CUDA
+ *     tensors); the library never frees or retains them past the call.
+ *   - calls are asynchronous on the caller's `stream` (a cudaStream_t passed as void*, NULL = legacy
+ *     default stream); no hidden synchronisation or allocation in step/observe/reset/autoreset.
+ *   - a handle is not re-entrant; independent handles may be used from different threads
+ *     (the reference runs a train env and a test env concurrently: multi_ppo.py:291-292).
+ *   - agents are numbered a = env * N + drone;  A = E * N.
+ *   - observation layout per agent (ir_gym.py:203-229): 12 self values [p(3) v(3) r prio des_vel(3) dev]
+ *     then nm rows of 9 [apex(3) rel_pos(3) alpha min_dis 1/(t+0.2)], most urgent LAST, zero padded;
+ *     `count` = number of valid rows; `nbr` = in-env drone index of each row (-1 = empty).
+ */
+#ifndef UAISA_B200_H
+#define UAISA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define UAISA_OK 0
+#define UAISA_EINVAL (-1)  /* bad argument / configuration */
+#define UAISA_ECUDA (-2)   /* a CUDA runtime call failed (message has the cudaError string) */
+#define UAISA_ENOMEM (-3)
+#define UAISA_ESTATE (-4)  /* call order: scenarios not set */
+
+#define UAISA_OBS_SELF 12
+#define UAISA_ROW 9
+#define UAISA_MAX_NM 16
+#define UAISA_MAX_DRONES 1024
+
+/* Hyper-parameters the reference hard-codes in constructors (citations: SURVEY.md section 5). */
+typedef struct UaisaConfig {
+    int32_t n_envs;          /* E */
+    int32_t n_drones;        /* N  (data_1.json drone_num)            <= UAISA_MAX_DRONES */
+    int32_t max_waypoints;   /* W                                      >= 2 */
+    int32_t max_buildings;   /* M                                      >= 1 */
+    int32_t n_scenarios;     /* S  distinct scenarios shared by the envs */
+    int32_t nm;              /* neighbour slots, mdin.py:7 neighbors_num=10   <= UAISA_MAX_NM */
+    int32_t env_train;       /* ir_gym.py:18 env_train=True */
+    int32_t threads_per_block; /* 0 = auto */
+    int32_t count_pairs;     /* 1 = maintain the pair counters of uaisa_get_counters (costs atomics) */
+    int32_t reserved;
+    double goal_threshold;   /* drone.py:15      0.4 */
+    double max_acc;          /* drone.py:72      1.0 */
+    double max_angle_change; /* drone.py:73      90  */
+    double dt;               /* drone.py:14      1   */
+    double vel_max;          /* drone.py:15      1   */
+    double neighbor_range;   /* rvo_inter.py:96  10  */
+    double building_range;   /* rvo_inter.py:104 5   */
+    double building_zgate;   /* rvo_inter.py:101 2   */
+    double ctime_threshold;  /* rvo_inter.py:11  2   */
+    double delta_t;          /* rvo_inter.py:11  1   */
+    double exp_radius;       /* rvo_inter.py:11  0.2 */
+} UaisaConfig;
+
+/* Mutable per-agent state, structure-of-arrays, fp32 (drone.py:19-76).  Used by get/set_state:
+ * each non-NULL pointer is a caller buffer (device or host, any cudaMemcpyDefault-able address). */
+typedef struct UaisaStateView {
+    float *pos_yaw;     /* [A][4]  x, y, z, yaw (deg)     drone.state, drone.yaw   */
+    float *vel_pitch;   /* [A][4]  vx, vy, vz, pitch (deg) drone.vel, drone.pitch   */
+    float *real_len;    /* [A]     drone.real_route_len */
+    float *max_dev;     /* [A]     drone.max_deviation  */
+    float *extra_len;   /* [A]     drone.extra_len      */
+    int32_t *wp_flags;  /* [A]     bits 0-15 drone.i, bit 16 arrive_flag, bit 17 destination_arrive_flag */
+} UaisaStateView;
+
+typedef struct UaisaHandle UaisaHandle;
+
+const char *uaisa_last_error(void);
+int uaisa_version(void);
+int uaisa_default_config(UaisaConfig *cfg);
+
+/* mdin.__init__ -> ir_gym.__init__ -> env_base.__init__ (mdin.py:7-16, env_base.py:15-24) */
+int uaisa_create(const UaisaConfig *cfg, UaisaHandle **out);
+int uaisa_destroy(UaisaHandle *h);
+
+/* env_base.load_data (env_base.py:26-47): scenario constants, HOST pointers, copied to the device.
+ * waypoints[S][N][W][3], n_points[S][N], radius[S][N], priority[S][N], buildings[S][M][4]=(x,y,h,r),
+ * n_buildings[S], map_size[S][3], env2scenario[E].  Doubles: a json scenario is kept exactly.
+ * Also resets every agent (drone.__init__ state).  Synchronous. */
+int uaisa_set_scenarios(UaisaHandle *h, const double *waypoints, const int32_t *n_points, const double *radius,
+                        const double *priority, const double *buildings, const int32_t *n_buildings,
+                        const double *map_size, const int32_t *env2scenario);
+
+/* mdin.drone_step (mdin.py:19-30): action[A][3] -> obs[A][12+9nm], count[A], nbr[A][nm], reward[A],
+ * done[A] (collision), info[A] (arrive_flag), finish[A] (destination_arrive_flag).
+ * Any output pointer may be NULL (not written). */
+int uaisa_step(UaisaHandle *h, const float *action, float *obs, uint8_t *count, int32_t *nbr, float *reward,
+               uint8_t *done, uint8_t *info, uint8_t *finish, void *stream);
+
+/* mdin.drone_reset / drone_reset_one (mdin.py:38-46) + ir_gym.env_observation (ir_gym.py:372-383):
+ * resets agents with agent_mask[a]!=0 (NULL = all agents) as drone.reset (drone.py:270-291), then, when
+ * obs != NULL, writes the observations of every agent of each env that had a reset. */
+int uaisa_reset(UaisaHandle *h, const uint8_t *agent_mask, float *obs, uint8_t *count, int32_t *nbr, void *stream);
+
+/* ir_gym.env_observation (ir_gym.py:372-383) for envs with env_mask[e]!=0 (NULL = all). */
+int uaisa_observe(UaisaHandle *h, const uint8_t *env_mask, float *obs, uint8_t *count, int32_t *nbr, void *stream);
+
+/* Trainer-side reset policy of multi_ppo.training_loop (multi_ppo.py:221-281), per env, on device:
+ * ep_len += 1; done_i -> reset i; all finish or epoch_ended -> reset env; any finish or
+ * ep_len > max_ep_len -> reset those; then env_observation for every touched env (obs/count/nbr are
+ * overwritten for those envs only).  reset_mask[A] / path_cut[A] (finish_path would be called) may be NULL. */
+int uaisa_autoreset(UaisaHandle *h, const uint8_t *done, const uint8_t *finish, int32_t max_ep_len, int32_t epoch_ended,
+                    float *obs, uint8_t *count, int32_t *nbr, uint8_t *reset_mask, uint8_t *path_cut, void *stream);
+
+/* T open-loop steps in ONE launch (state stays on chip between steps): action[T][A][3]; outputs are
+ * [T][...] with the same per-step layouts as uaisa_step (NULL = skip).  auto_reset!=0 applies the
+ * uaisa_autoreset policy after every step (max_ep_len as given, epoch_ended = 0). */
+int uaisa_rollout(UaisaHandle *h, int32_t T, const float *action, float *obs, uint8_t *count, int32_t *nbr,
+                  float *reward, uint8_t *done, uint8_t *info, uint8_t *finish, int32_t auto_reset,
+                  int32_t max_ep_len, void *stream);
+
+/* state access (teacher forcing, drone_list[i].vel): copies between the handle and caller buffers */
+int uaisa_get_state(UaisaHandle *h, const UaisaStateView *dst, void *stream);
+int uaisa_set_state(UaisaHandle *h, const UaisaStateView *src, void *stream);
+/* ir_gym.cal_des_list (ir_gym.py:44-46): des[A][3] */
+int uaisa_cal_des(UaisaHandle *h, float *des, void *stream);
+/* ir_gym.indicators_deviation / indicators_extra_len (ir_gym.py:414-420): max_dev[A], extra_len[A] */
+int uaisa_indicators(UaisaHandle *h, float *max_dev, float *extra_len, void *stream);
+/* HOST outputs; synchronises `stream`.  in_range_pairs / cone_evals: pair evaluations and full cone
+ * evaluations since the last call (only with cfg.count_pairs); nonfinite_obs: observations that
+ * contained NaN/Inf (the reference raises ValueError there, ir_gym.py:232-239). */
+int uaisa_get_counters(UaisaHandle *h, int64_t *in_range_pairs, int64_t *cone_evals, int64_t *nonfinite_obs, void *stream);
+/* kernel launches issued through this handle so far (bench.py's gpu_launches) */
+int64_t uaisa_launch_count(const UaisaHandle *h);
+
+/* Host-buffer convenience used for the end-to-end number: H2D(action) -> step -> D2H(outputs), all
+ * pointers HOST (pinned for full speed), synchronous on return. */
+int uaisa_step_host(UaisaHandle *h, const float *action, float *obs, uint8_t *count, int32_t *nbr, float *reward,
+                    uint8_t *done, uint8_t *info, uint8_t *finish);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UAISA_B200_H */

@@ -1,0 +1,196 @@
+"""-m gpu: the CUDA path (through the C ABI) against the oracle on identical seeded inputs.
+Contract (BASELINE.json north_star): done/info/finish flags, counts and neighbour indices bit-exact;
+positions, velocities, rewards and observations within 1e-5 relative (fp32 state vs fp64 reference)."""
+import glob
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import _util  # noqa: F401
+import oracle
+from gpu_harness import Stats, lockstep, f32
+from uaisa_env.scenario import ScenarioSet, scenario_c1, scenario_c3, scenario_c4, scenario_world3
+from uaisa_env.vec_env import VecMdin, pack_state, unpack_state
+
+pytestmark = pytest.mark.gpu
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+
+
+def swarm(n=12, rad=1.0, seed=0):
+    rng = np.random.default_rng(seed)
+    ang = 2 * np.pi * np.arange(n) / n
+    st = np.stack([5 + rad * np.cos(ang), 5 + rad * np.sin(ang), 2.5 + 0.3 * rng.uniform(-1, 1, n)], 1)
+    en = np.stack([5 - rad * np.cos(ang), 5 - rad * np.sin(ang), 2.5 + 0.3 * rng.uniform(-1, 1, n)], 1)
+    return ScenarioSet.from_start_end(np.round(st, 2), np.round(en, 2), (10, 10, 5), buildings=[[5, 5, 1.5, 0.3]])
+
+
+def golden_scn(name):
+    z = np.load([p for p in GOLDEN if os.path.basename(p) == name + ".npz"][0])
+    return ScenarioSet.from_dict(json.loads(str(z["scenario_json"])))
+
+
+@pytest.mark.parametrize("name,E,nm,steps", [
+    ("c1", 64, 10, 150), ("world3", 85, 10, 150), ("world_8", 32, 10, 150), ("world_8", 16, 2, 100),
+    ("swarm12", 24, 3, 120), ("swarm12", 24, 10, 120), ("c3", 16, 10, 120), ("swarm20", 8, 16, 80)])
+def test_lockstep_teacher_forced(name, E, nm, steps):
+    scn = {"c1": scenario_c1, "world3": scenario_world3, "world_8": lambda: golden_scn("world_8"),
+           "swarm12": lambda: swarm(12, 1.0, 3), "swarm20": lambda: swarm(20, 1.3, 4),
+           "c3": lambda: scenario_c3(seed=2, n_scenarios=4)}[name]()
+    st = lockstep(scn, E, nm, steps, seed=hash((name, nm)) % 1000, epoch_len=70, block=20)
+    st.assert_parity()
+    assert st.dones > 0 and st.resets > 0
+    if name.startswith("swarm"):
+        assert st.rows > 200
+    # in practice the fp32 images are bit-identical; keep a hard ceiling on the inexact fraction
+    assert st.obs_inexact <= 1e-4 * st.obs_vals and st.rew_inexact <= 1e-3 * st.rew_vals, st.summary()
+
+
+def test_dense_256():
+    """configs[3] shape: one CTA per 256-drone env, neighbour lists truncated to nm."""
+    scn = scenario_c4(seed=1, n_scenarios=2, n_drones=256)
+    st = lockstep(scn, 3, 10, 12, seed=5, block=3)
+    st.assert_parity()
+    assert st.rows > 0
+
+
+def test_edge_shapes():
+    # single drone, no neighbours; nm = 0; N=3 (CTA not a multiple of N); explicit CTA sizes
+    one = ScenarioSet.from_start_end([[1, 1, 1]], [[3, 3, 2]], (5, 5, 3))
+    lockstep(one, 5, 10, 40, seed=1).assert_parity()
+    lockstep(scenario_world3(), 7, 0, 40, seed=2).assert_parity()
+    lockstep(scenario_world3(), 50, 10, 40, seed=3, threads_per_block=32).assert_parity()
+    lockstep(swarm(12, 1.0, 7), 30, 10, 40, seed=4, threads_per_block=256).assert_parity()
+    lockstep(scenario_c1(), 9, 10, 40, seed=5, env_train=0).assert_parity()
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
+def test_against_reference_golden(path):
+    """CUDA path vs outputs RECORDED FROM THE REFERENCE itself: the device is loaded with the fp32
+    image of each recorded pre-state, so differences are bounded by that input rounding (a 2-dp
+    rounded observation may move by one quantum when the rounding of the state crosses a tie)."""
+    z = np.load(path)
+    scn = ScenarioSet.from_dict(json.loads(str(z["scenario_json"])))
+    nm = int(z["nm"])
+    env = VecMdin(scn, 1, neighbors_num=nm)
+    T = z["action"].shape[0]
+    flag_bad = 0; obs_bad = 0; rew_bad = 0; nvals = 0
+    for t in range(T):
+        pre = {k: z["pre_" + k][t] for k in ("pos", "vel", "yaw", "pitch", "wp_idx", "arrive_flag", "dest_flag", "real_len", "max_dev", "extra_len")}
+        env.set_state(pack_state(pre))
+        env.step(torch.from_numpy(z["action"][t].astype(np.float32)).cuda())
+        o = env.obs.cpu().numpy().astype(np.float64); r = env.reward.cpu().numpy().astype(np.float64)
+        flag_bad += int((env.done.cpu().numpy() != z["done"][t]).sum() + (env.finish.cpu().numpy() != z["finish"][t]).sum()
+                        + (env.info.cpu().numpy() != z["info"][t]).sum() + (env.count.cpu().numpy() != z["count"][t]).sum())
+        same_cnt = env.count.cpu().numpy() == z["count"][t]
+        d = np.abs(o - z["obs"][t])[same_cnt]
+        assert d.size == 0 or d.max() <= 0.0100001 + 1e-5 * np.abs(z["obs"][t]).max(), (t, d.max())
+        obs_bad += int((d > 1e-5 * np.maximum(1, np.abs(z["obs"][t][same_cnt]))).sum()); nvals += d.size
+        ref_r = z["reward"][t]
+        fin = np.isfinite(ref_r)
+        rew_bad += int((np.abs(r[fin] - ref_r[fin]) > 2e-3 + 1e-5 * np.abs(ref_r[fin])).sum()) + int((np.isfinite(r) != fin).sum())
+    env.close()
+    n = T * scn.N
+    assert flag_bad <= max(1, n // 500), flag_bad
+    assert obs_bad <= max(2, nvals // 2000), (obs_bad, nvals)
+    assert rew_bad <= max(1, n // 200), rew_bad
+
+
+def test_rollout_equals_repeated_step_and_fused_autoreset():
+    scn = swarm(12, 1.2, 9)
+    E, nm, T = 40, 10, 30
+    rng = np.random.default_rng(0)
+    A = E * scn.N
+    acts = torch.from_numpy(np.round(rng.uniform(-1, 1, (T, A, 3)), 2).astype(np.float32)).cuda()
+    a = VecMdin(scn, E, neighbors_num=nm); b = VecMdin(scn, E, neighbors_num=nm)
+    a.reset(); b.reset()
+    names = ("obs", "count", "nbr", "reward", "done", "info", "finish")
+    out = {"obs": torch.zeros((T, A, a.obs_dim), device="cuda"), "count": torch.zeros((T, A), dtype=torch.uint8, device="cuda"),
+           "nbr": torch.zeros((T, A, nm), dtype=torch.int32, device="cuda"), "reward": torch.zeros((T, A), device="cuda"),
+           "done": torch.zeros((T, A), dtype=torch.uint8, device="cuda"), "info": torch.zeros((T, A), dtype=torch.uint8, device="cuda"),
+           "finish": torch.zeros((T, A), dtype=torch.uint8, device="cuda")}
+    a.rollout(acts, out, auto_reset=True, max_ep_len=12)
+    for t in range(T):
+        b.step(acts[t])
+        for k in ("reward", "done", "info", "finish"):
+            assert torch.equal(getattr(b, k).view(-1), out[k][t].view(-1)) or (k == "reward" and torch.equal(torch.nan_to_num(b.reward, 7.0), torch.nan_to_num(out[k][t], 7.0))), (t, k)
+        b.autoreset(max_ep_len=12)
+        for k in ("obs", "count", "nbr"):
+            assert torch.equal(getattr(b, k), out[k][t]), (t, k)
+    sa, sb = a.get_state(), b.get_state()
+    for k in sa:
+        assert torch.equal(sa[k], sb[k]), k
+    a.close(); b.close()
+
+
+def test_env_sharding_is_bitwise_deterministic():
+    """a shard of envs computes exactly what the same env ids compute in the full batch."""
+    scn = scenario_c3(seed=3, n_scenarios=3, n_drones=8, n_buildings=4)
+    E, nm, T = 48, 10, 25
+    e2s = (np.arange(E) % 3).astype(np.int32)
+    rng = np.random.default_rng(1)
+    acts = np.round(rng.uniform(-1, 1, (T, E, scn.N, 3)), 2).astype(np.float32)
+    full = VecMdin(scn, E, env2scenario=e2s, neighbors_num=nm); full.reset()
+    lo = VecMdin(scn, 16, env2scenario=e2s[:16], neighbors_num=nm); lo.reset()
+    hi = VecMdin(scn, 32, env2scenario=e2s[16:], neighbors_num=nm, threads_per_block=64); hi.reset()
+    for t in range(T):
+        full.step(torch.from_numpy(acts[t].reshape(-1, 3)).cuda()); full.autoreset(max_ep_len=10)
+        lo.step(torch.from_numpy(acts[t, :16].reshape(-1, 3).copy()).cuda()); lo.autoreset(max_ep_len=10)
+        hi.step(torch.from_numpy(acts[t, 16:].reshape(-1, 3).copy()).cuda()); hi.autoreset(max_ep_len=10)
+        for k in ("obs", "reward", "done", "finish", "count", "nbr"):
+            cat = torch.cat([getattr(lo, k), getattr(hi, k)], 0)
+            f = getattr(full, k)
+            assert torch.equal(torch.nan_to_num(cat.float(), 7.0), torch.nan_to_num(f.float(), 7.0)), (t, k)
+    for e in (full, lo, hi):
+        e.close()
+
+
+def test_masks_and_api_errors():
+    scn = scenario_world3()
+    env = VecMdin(scn, 10, neighbors_num=10, count_pairs=True)
+    env.reset()
+    act = torch.full((env.A, 3), 0.3, device="cuda")
+    env.step(act)
+    before = env.obs.clone()
+    # observe only env 3: other rows untouched
+    m = torch.zeros(env.E, dtype=torch.uint8, device="cuda"); m[3] = 1
+    env.obs.fill_(-7.0)
+    env.observe(m)
+    assert (env.obs[9:12] != -7.0).all() and (env.obs[:9] == -7.0).all() and (env.obs[12:] == -7.0).all()
+    # reset one drone of env 5: state back at its start, env 5 re-observed
+    am = torch.zeros(env.A, dtype=torch.uint8, device="cuda"); am[16] = 1
+    env.obs.fill_(-7.0)
+    env.reset(am)
+    st = unpack_state(env.get_state())
+    assert np.array_equal(st["pos"][16], scn.waypoints[0, 1, 0]) and np.all(st["vel"][16] == 0) and st["wp_idx"][16] == 1
+    assert (env.obs[15:18] != -7.0).all() and (env.obs[:15] == -7.0).all()
+    c = env.counters()
+    assert c["in_range_pairs"] > 0 and c["nonfinite_obs"] == 0
+    assert env.launch_count >= 4
+    with pytest.raises(ValueError):
+        env.step(torch.zeros((env.A, 3), dtype=torch.float64, device="cuda"))
+    with pytest.raises(ValueError):
+        env.step(torch.zeros((env.A, 3)))
+    env.close()
+    bad = scenario_world3(); bad.n_points[0, 0] = 1
+    with pytest.raises(Exception):
+        VecMdin(bad, 2)
+    del before
+
+
+def test_step_host_matches_device_step():
+    scn = scenario_c1()
+    a = VecMdin(scn, 33, neighbors_num=10); b = VecMdin(scn, 33, neighbors_num=10)
+    a.reset(); b.reset()
+    rng = np.random.default_rng(3)
+    out = {"obs": np.zeros((a.A, a.obs_dim), np.float32), "count": np.zeros(a.A, np.uint8), "nbr": np.zeros((a.A, 10), np.int32),
+           "reward": np.zeros(a.A, np.float32), "done": np.zeros(a.A, np.uint8), "info": np.zeros(a.A, np.uint8), "finish": np.zeros(a.A, np.uint8)}
+    for t in range(10):
+        act = np.round(rng.uniform(-1, 1, (a.A, 3)), 2).astype(np.float32)
+        a.step_host(act, out)
+        b.step(torch.from_numpy(act).cuda())
+        for k in out:
+            assert np.array_equal(out[k], getattr(b, k).cpu().numpy(), equal_nan=(k == "reward")), (t, k)
+    a.close(); b.close()

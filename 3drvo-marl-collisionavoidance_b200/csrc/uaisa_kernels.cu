@@ -3,14 +3,15 @@
 
 namespace uaisa {
 
+// fp32 round trip: what a store to HBM followed by the next step's load would do
+__device__ __forceinline__ double rt(double x) { return (double)(float)x; }
+
 __device__ __forceinline__ void reset_drone(Drone &d, const Consts &C) {   // drone.reset, drone.py:270-291
     load3(C.wp, d.px, d.py, d.pz);
+    d.px = rt(d.px); d.py = rt(d.py); d.pz = rt(d.pz);   // the state is fp32: a start point is stored rounded
     d.vx = d.vy = d.vz = 0.0; d.yaw = d.pitch = 0.0; d.real_len = 0.0; d.max_dev = 0.0;
     d.i = 1; d.flags = 0;   // extra_len is deliberately not cleared
 }
-
-// fp32 round trip: what a store to HBM followed by the next step's load would do
-__device__ __forceinline__ double rt(double x) { return (double)(float)x; }
 
 __device__ __forceinline__ void publish(double *sx, int threads, int tid, const Drone &d, const Consts &C) {
     sx[0 * threads + tid] = d.px; sx[1 * threads + tid] = d.py; sx[2 * threads + tid] = d.pz;

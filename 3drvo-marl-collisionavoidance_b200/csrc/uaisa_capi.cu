@@ -114,7 +114,6 @@ int uaisa_create(const UaisaConfig *cfg, UaisaHandle **out) {
     Params &P = h->P;
     P.E = E; P.N = N; P.W = cfg->max_waypoints; P.M = cfg->max_buildings; P.nm = cfg->nm;
     P.obs_dim = UAISA_OBS_SELF + UAISA_ROW * cfg->nm;
-    P.obs_pitch = P.obs_dim + cfg->nm; if ((P.obs_pitch & 1) == 0) P.obs_pitch += 1;   // odd pitch: conflict-free row writes
     P.env_train = cfg->env_train; P.count_pairs = cfg->count_pairs;
     P.goal_thr = cfg->goal_threshold; P.max_acc = cfg->max_acc; P.max_ang = cfg->max_angle_change; P.dt = cfg->dt;
     P.vel_max = cfg->vel_max; P.nbr_range = cfg->neighbor_range; P.bld_range = cfg->building_range;
@@ -129,7 +128,7 @@ int uaisa_create(const UaisaConfig *cfg, UaisaHandle **out) {
     if (threads < N || threads > 1024 || threads % 32) { delete h; return fail(UAISA_EINVAL, "threads_per_block must be a multiple of 32 in [n_drones, 1024]"); }
     h->threads = threads; P.threads = threads; P.envs_per_cta = threads / N;
     h->grid = (E + P.envs_per_cta - 1) / P.envs_per_cta;
-    h->smem = sizeof(double) * 8 * threads + sizeof(float) * (size_t)threads * P.obs_pitch + sizeof(int) * 2 * P.envs_per_cta;
+    h->smem = sizeof(double) * 8 * threads + 4 * (size_t)(((threads * P.obs_dim + 3) & ~3) + ((threads * P.nm + 3) & ~3)) + sizeof(int) * 2 * P.envs_per_cta;
     const int need = cfg->nm < N - 1 ? cfg->nm : N - 1;
     if (threads > 256) h->kernel = uaisa_env_kernel<16, 1024>;
     else if (need <= 4) h->kernel = uaisa_env_kernel<4, 256>;
@@ -291,7 +290,7 @@ int uaisa_get_counters(UaisaHandle *h, int64_t *in_range_pairs, int64_t *cone_ev
 int64_t uaisa_launch_count(const UaisaHandle *h) { return h ? h->launches : 0; }
 
 int uaisa_step_host(UaisaHandle *h, const float *action, float *obs, uint8_t *count, int32_t *nbr, float *reward, uint8_t *done,
-                    uint8_t *info, uint8_t *finish) {
+                    uint8_t *info, uint8_t *finish, int32_t auto_reset, int32_t max_ep_len) {
     if (!h || !action) return fail(UAISA_EINVAL, "NULL handle or action");
     DeviceGuard g(h->device);
     const size_t A = h->A; const Params &P = h->P;
@@ -304,9 +303,9 @@ int uaisa_step_host(UaisaHandle *h, const float *action, float *obs, uint8_t *co
     }
     cudaStream_t s = h->h_stream;
     CK(cudaMemcpyAsync(h->h_action, action, sizeof(float) * A * 3, cudaMemcpyHostToDevice, s));
-    int rc = uaisa_step(h, h->h_action, obs ? h->h_obs : nullptr, count ? h->h_count : nullptr, nbr ? h->h_nbr : nullptr,
-                        reward ? h->h_reward : nullptr, done ? h->h_flags : nullptr, info ? h->h_flags + A : nullptr,
-                        finish ? h->h_flags + 2 * A : nullptr, s);
+    int rc = uaisa_rollout(h, 1, h->h_action, obs ? h->h_obs : nullptr, count ? h->h_count : nullptr, nbr ? h->h_nbr : nullptr,
+                           reward ? h->h_reward : nullptr, done ? h->h_flags : nullptr, info ? h->h_flags + A : nullptr,
+                           finish ? h->h_flags + 2 * A : nullptr, auto_reset, max_ep_len, s);
     if (rc) return rc;
     if (obs) CK(cudaMemcpyAsync(obs, h->h_obs, sizeof(float) * A * P.obs_dim, cudaMemcpyDeviceToHost, s));
     if (count) CK(cudaMemcpyAsync(count, h->h_count, A, cudaMemcpyDeviceToHost, s));

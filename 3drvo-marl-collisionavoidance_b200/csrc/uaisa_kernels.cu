@@ -52,50 +52,71 @@ __device__ __forceinline__ void pair_pass(const Params &P, const double *sx, int
     }
 }
 
-// Observation assembly into the staging row (ir_gym.py:203-229): 12 self values + rows, np.round(., 2)
+// Observation assembly into the staging row (ir_gym.py:203-229): 12 self values + rows, np.round(., 2).
+// The staging area is zeroed (nbr: -1) cooperatively at the top of a step; `staged` = rows this thread has
+// written since, so a re-observe after an auto-reset only clears what is stale.
 template <int MAXR>
-__device__ __forceinline__ bool stage_obs(const Params &P, float *row, const double *sx, int threads, int lbase,
+__device__ __forceinline__ bool stage_obs(const Params &P, float *row, int *nbr, const double *sx, int threads, int lbase,
                                           const Drone &d, const Consts &C, double d0, double d1, double d2, double dev,
-                                          const TopList<MAXR> &top) {
-    double self[OBS_SELF] = {d.px, d.py, d.pz, d.vx, d.vy, d.vz, C.radius, C.prio, d0, d1, d2, dev};
+                                          const TopList<MAXR> &top, int &staged) {
+    const double self[OBS_SELF] = {d.px, d.py, d.pz, d.vx, d.vy, d.vz, C.radius, C.prio, d0, d1, d2, dev};
     bool bad = false;
 #pragma unroll
-    for (int q = 0; q < OBS_SELF; q++) { double v = np_round2(self[q]); bad |= !isfinite(v); row[q] = (float)v; }
-    const int nm = P.nm;
-    int *nbr = reinterpret_cast<int *>(row + P.obs_dim);
+    for (int q = 0; q < OBS_SELF; q++) row[q] = np_round2_f32(self[q], bad);
     // slot r (least urgent first, most urgent last) = top[cnt-1-r]
 #pragma unroll
     for (int s = 0; s < MAXR; s++) {
         if (s < top.cnt) {
             const int r = top.cnt - 1 - s, o = lbase + top.j[s];
-            double mx = sx[0 * threads + o], my = sx[1 * threads + o], mz = sx[2 * threads + o];
-            double mvx = sx[3 * threads + o], mvy = sx[4 * threads + o], mvz = sx[5 * threads + o], prb = sx[7 * threads + o];
-            double pr = C.prio / (C.prio + prb);
-            double v[ROW] = {pr * (2.0 * d.px + (d.vx + mvx) * 1.0), pr * (2.0 * d.py + (d.vy + mvy) * 1.0),
-                             pr * (2.0 * d.pz + (d.vz + mvz) * 1.0), mx - d.px, my - d.py, mz - d.pz,
-                             (double)top.ah[s] / 100.0, top.md[s], top.iet[s]};
+            const double mx = sx[0 * threads + o], my = sx[1 * threads + o], mz = sx[2 * threads + o];
+            const double mvx = sx[3 * threads + o], mvy = sx[4 * threads + o], mvz = sx[5 * threads + o], prb = sx[7 * threads + o];
+            const double pr = fast_div(C.prio, C.prio + prb);
+            const double v[ROW] = {pr * (2.0 * d.px + (d.vx + mvx) * 1.0), pr * (2.0 * d.py + (d.vy + mvy) * 1.0),
+                                   pr * (2.0 * d.pz + (d.vz + mvz) * 1.0), mx - d.px, my - d.py, mz - d.pz,
+                                   (double)top.ah[s] * 0.01, top.md[s], top.iet[s]};
             float *rr = row + OBS_SELF + ROW * r;
 #pragma unroll
-            for (int q = 0; q < ROW; q++) { double w = np_round2(v[q]); bad |= !isfinite(w); rr[q] = (float)w; }
+            for (int q = 0; q < ROW; q++) rr[q] = np_round2_f32(v[q], bad);
             nbr[r] = top.j[s];
         }
     }
-    for (int r = top.cnt; r < nm; r++) {
+    for (int r = top.cnt; r < staged; r++) {
         float *rr = row + OBS_SELF + ROW * r;
 #pragma unroll
         for (int q = 0; q < ROW; q++) rr[q] = 0.0f;
         nbr[r] = -1;
     }
+    staged = top.cnt;
     return bad;
+}
+
+// n 32-bit words smem -> global, widest vectors the destination alignment allows (src is 16-byte aligned)
+__device__ __forceinline__ void copy_out(uint32_t *__restrict__ dst, const uint32_t *__restrict__ src, int n, int tid, int nthreads) {
+    const uintptr_t da = reinterpret_cast<uintptr_t>(dst);
+    if ((da & 15) == 0) {
+        const int n4 = n >> 2;
+        const uint4 *s4 = reinterpret_cast<const uint4 *>(src); uint4 *d4 = reinterpret_cast<uint4 *>(dst);
+        for (int i = tid; i < n4; i += nthreads) d4[i] = s4[i];
+        for (int i = (n4 << 2) + tid; i < n; i += nthreads) dst[i] = src[i];
+    } else if ((da & 7) == 0) {
+        const int n2 = n >> 1;
+        const uint2 *s2 = reinterpret_cast<const uint2 *>(src); uint2 *d2 = reinterpret_cast<uint2 *>(dst);
+        for (int i = tid; i < n2; i += nthreads) d2[i] = s2[i];
+        for (int i = (n2 << 1) + tid; i < n; i += nthreads) dst[i] = src[i];
+    } else {
+        for (int i = tid; i < n; i += nthreads) dst[i] = src[i];
+    }
 }
 
 template <int MAXR, int MAXT>
 __global__ void __launch_bounds__(MAXT) uaisa_env_kernel(const __grid_constant__ Params P, const __grid_constant__ Launch L) {
     extern __shared__ double smem_d[];
     const int threads = P.threads;
-    double *sx = smem_d;
-    float *sobs = reinterpret_cast<float *>(sx + 8 * threads);
-    int *senv = reinterpret_cast<int *>(sobs + (size_t)threads * P.obs_pitch);   // [envs_per_cta] reduction bits
+    double *sx = smem_d;                                                         // [8][threads] exchange
+    const int obs_words = (threads * P.obs_dim + 3) & ~3, nbr_words = (threads * P.nm + 3) & ~3;
+    float *sobs = reinterpret_cast<float *>(sx + 8 * threads);                   // [threads][obs_dim] dense rows
+    int *snbr = reinterpret_cast<int *>(sobs + obs_words);                       // [threads][nm]
+    int *senv = snbr + nbr_words;                                                // [envs_per_cta] reduction bits
     int *ssel = senv + P.envs_per_cta;                                           // [envs_per_cta] obs selected
 
     const int tid = threadIdx.x, N = P.N;
@@ -109,7 +130,8 @@ __global__ void __launch_bounds__(MAXT) uaisa_env_kernel(const __grid_constant__
     const int nenv_here = min(P.envs_per_cta, P.E - env0);
     const int nag_here = nenv_here * N;          // agents of this CTA: contiguous range starting at env0*N
     const int cap = min(P.nm, MAXR);
-    float *myrow = sobs + (size_t)tid * P.obs_pitch;
+    float *myrow = sobs + (size_t)tid * P.obs_dim;
+    int *mynbr = snbr + (size_t)tid * P.nm;
 
     Consts C; Drone d; int ep_len = 0;
     const double *bld = nullptr; int nb = 0; double mapx = 0, mapy = 0, mapz = 0;
@@ -132,6 +154,13 @@ __global__ void __launch_bounds__(MAXT) uaisa_env_kernel(const __grid_constant__
     for (int t = 0; t < T; t++) {
         bool st_done = false, st_fin = false;
         if (tid < P.envs_per_cta) { senv[tid] = 0; ssel[tid] = (L.mode == MODE_STEP) ? 1 : 0; }
+        {   // clear the staging area: rows are mostly zero padding (nm slots), neighbour ids default to -1
+            uint4 *z = reinterpret_cast<uint4 *>(sobs);
+            for (int i = tid; i < (obs_words >> 2); i += blockDim.x) z[i] = make_uint4(0u, 0u, 0u, 0u);
+            uint4 *m = reinterpret_cast<uint4 *>(snbr);
+            for (int i = tid; i < (nbr_words >> 2); i += blockDim.x) m[i] = make_uint4(~0u, ~0u, ~0u, ~0u);
+        }
+        int staged = 0;
         __syncthreads();
         if (L.mode == MODE_STEP) {
             // ---------------------------------------------------------------- PASS A (pre-move)
@@ -202,7 +231,7 @@ __global__ void __launch_bounds__(MAXT) uaisa_env_kernel(const __grid_constant__
                 bool vo; double tmin; TopList<MAXR> top; top.clear();
                 pair_pass<MAXR, true>(P, sx, threads, lbase, N, k, d, C, ax, ay, az, vo, tmin, col, top, cap, n_rng, n_cone);
                 if (d.px < 0 || d.px > mapx || d.py < 0 || d.py > mapy || d.pz < 0 || d.pz > mapz) col = true;   // drone.py:213-225
-                n_bad += stage_obs<MAXR>(P, myrow, sx, threads, lbase, d, C, d0, d1, d2, dev, top) ? 1u : 0u;
+                n_bad += stage_obs<MAXR>(P, myrow, mynbr, sx, threads, lbase, d, C, d0, d1, d2, dev, top, staged) ? 1u : 0u;
                 // ir_gym.mov_reward (ir_gym.py:256-311)
                 double rB;
                 if (col) rB = -50.0;
@@ -269,7 +298,7 @@ __global__ void __launch_bounds__(MAXT) uaisa_env_kernel(const __grid_constant__
                 double d0, d1, d2, dev; dronestate(P, d, C, d0, d1, d2, dev);
                 bool vo, col = false; double tmin; TopList<MAXR> top; top.clear();
                 pair_pass<MAXR, true>(P, sx, threads, lbase, N, k, d, C, 0.0, 0.0, 0.0, vo, tmin, col, top, cap, n_rng, n_cone);
-                n_bad += stage_obs<MAXR>(P, myrow, sx, threads, lbase, d, C, d0, d1, d2, dev, top) ? 1u : 0u;
+                n_bad += stage_obs<MAXR>(P, myrow, mynbr, sx, threads, lbase, d, C, d0, d1, d2, dev, top, staged) ? 1u : 0u;
                 if (L.count) L.count[(size_t)t * A + a] = (uint8_t)top.cnt;
                 d.max_dev = rt(d.max_dev);
             }
@@ -279,20 +308,15 @@ __global__ void __launch_bounds__(MAXT) uaisa_env_kernel(const __grid_constant__
         __syncthreads();
         {
             const size_t abase = (size_t)t * A + (size_t)env0 * N;
-            if (L.obs) {
-                float *g = L.obs + abase * P.obs_dim;
-                const int tot = nag_here * P.obs_dim;
-                for (int idx = tid; idx < tot; idx += blockDim.x) {
-                    const int la = idx / P.obs_dim, q = idx - la * P.obs_dim;
-                    if (ssel[la / N]) g[idx] = sobs[(size_t)la * P.obs_pitch + q];
-                }
-            }
-            if (L.nbr) {
-                int *g = L.nbr + abase * P.nm;
-                const int tot = nag_here * P.nm;
-                for (int idx = tid; idx < tot; idx += blockDim.x) {
-                    const int la = idx / P.nm, q = idx - la * P.nm;
-                    if (ssel[la / N]) g[idx] = reinterpret_cast<const int *>(sobs + (size_t)la * P.obs_pitch + P.obs_dim)[q];
+            if (L.mode == MODE_STEP) {   // every env of the CTA is written: one flat, vectorised copy
+                if (L.obs) copy_out(reinterpret_cast<uint32_t *>(L.obs + abase * P.obs_dim), reinterpret_cast<const uint32_t *>(sobs), nag_here * P.obs_dim, tid, blockDim.x);
+                if (L.nbr) copy_out(reinterpret_cast<uint32_t *>(L.nbr + abase * P.nm), reinterpret_cast<const uint32_t *>(snbr), nag_here * P.nm, tid, blockDim.x);
+            } else {                     // only the selected envs: one warp per row
+                const int warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
+                for (int la = warp; la < nag_here; la += nwarps) {
+                    if (!ssel[la / N]) continue;
+                    if (L.obs) for (int q = lane; q < P.obs_dim; q += 32) L.obs[(abase + la) * P.obs_dim + q] = sobs[(size_t)la * P.obs_dim + q];
+                    if (L.nbr) for (int q = lane; q < P.nm; q += 32) L.nbr[(abase + la) * P.nm + q] = snbr[(size_t)la * P.nm + q];
                 }
             }
         }

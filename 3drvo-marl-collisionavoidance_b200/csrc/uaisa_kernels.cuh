@@ -33,7 +33,7 @@ constexpr int WP_MASK = 0xFFFF;
 
 struct Params {
     // geometry
-    int E, N, W, M, nm, obs_dim, obs_pitch;
+    int E, N, W, M, nm, obs_dim;
     int envs_per_cta, threads;
     int env_train, count_pairs;
     // hyper-parameters (reference constructor defaults, see include/uaisa_b200.h)
@@ -62,8 +62,43 @@ __device__ __forceinline__ double np_dot3(double a0, double a1, double a2, doubl
 __device__ __forceinline__ double np_norm3(double a0, double a1, double a2) { return sqrt(np_dot3(a0, a1, a2, a0, a1, a2)); }
 __device__ __forceinline__ double np_norm2(double a0, double a1) { return sqrt(fma(a1, a1, a0 * a0)); }
 __device__ __forceinline__ double np_clip(double x, double lo, double hi) { return fmin(fmax(x, lo), hi); }
-__device__ __forceinline__ double np_round2(double x) { return rint(x * 100.0) / 100.0; }
-__device__ __forceinline__ double np_round3(double x) { return rint(x * 1000.0) / 1000.0; }
+
+// ---- division without the libdevice slow path ---------------------------------------------------------
+// a / c for a compile-time constant c with y = RN(1/c): q0 = a*y, r = a - c*q0 (exact in the FMA),
+// q = q0 + r*y is the correctly rounded quotient (Markstein); verified exhaustively on the host against
+// IEEE division for every integer |a| <= 2^26 and 2e8 random numerators for c = 100 and c = 1000
+// (DESIGN.md "exact rounding").  a must be finite.
+__device__ __forceinline__ double div_const(double a, double c, double y) {
+    double q0 = a * y, r = fma(-c, q0, a);
+    return fma(r, y, q0);
+}
+// General a / b for finite, normal, non-zero b: MUFU.RCP64H seed, two Newton steps, Markstein correction.
+// Correctly rounded except in rare last-bit cases; used only where an ulp cannot matter (the value is later
+// rounded to 2-3 decimals or compared with a threshold; a flip needs a 1e-16-wide coincidence).
+__device__ __forceinline__ double fast_rcp(double b) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(b));
+    double e = fma(-b, y, 1.0); y = fma(y, e, y);
+    e = fma(-b, y, 1.0); y = fma(y, e, y);
+    return y;
+}
+__device__ __forceinline__ double fast_div(double a, double b) {
+    double y = fast_rcp(b), q = a * y, r = fma(-b, q, a);
+    return fma(r, y, q);
+}
+// np.round(x, 2) / np.round(x, 3) = rint(x*10^k)/10^k, bit-exact for finite x
+__device__ __forceinline__ double np_round2(double x) { double k = rint(x * 100.0); return isfinite(k) ? div_const(k, 100.0, 0.01) : k; }
+__device__ __forceinline__ double np_round3(double x) { double k = rint(x * 1000.0); return isfinite(k) ? div_const(k, 1000.0, 0.001) : k; }
+// (float)np.round(x, 2): the fp32 image of rint(x*100)/100 equals the fp32 image of rint(x*100)*0.01
+// (k/100 is never within 2^-30 of an fp32 rounding tie unless it is exact; checked exhaustively, ibid.)
+__device__ __forceinline__ float np_round2_f32(double x, bool &bad) { double k = rint(x * 100.0); bad |= !isfinite(k); return (float)(k * 0.01); }
+// sqrt(x) <= T without the square root unless x is within 1e-14 of T^2 (NaN -> false)
+__device__ __forceinline__ bool sqrt_le(double x, double T) {
+    const double T2 = T * T;
+    if (x < T2 * (1.0 - 1e-14)) return true;
+    if (x > T2 * (1.0 + 1e-14)) return false;
+    return sqrt(x) <= T;
+}
 // builtin round(x, 2) of a Python float, returned in hundredths (exact decimal rounding, ties to even)
 __device__ __forceinline__ double py_round2_hundredths(double x) {
     double hi = x * 100.0, lo = fma(x, 100.0, -hi), r = rint(hi), d = hi - r;
@@ -93,7 +128,8 @@ __device__ __forceinline__ void load3(const double *p, double &x, double &y, dou
 
 __device__ __forceinline__ bool within_goal(const Params &P, double px, double py, double pz, const double *q) {
     double qx, qy, qz; load3(q, qx, qy, qz);
-    return np_norm3(px - qx, py - qy, pz - qz) <= P.goal_thr;   // drone.py:172-192
+    const double fx = px - qx, fy = py - qy, fz = pz - qz;
+    return sqrt_le(np_dot3(fx, fy, fz, fx, fy, fz), P.goal_thr);   // norm(p - q) <= 0.4, drone.py:172-192
 }
 
 // drone.calculate_deviation (drone.py:366-406)
@@ -102,7 +138,8 @@ __device__ __forceinline__ double deviation(const double *st, const double *en, 
     double dx = x2 - x1, dy = y2 - y1, dz = z2 - z1;
     double mag = sqrt(dx * dx + dy * dy + dz * dz);
     if (mag == 0.0) return 0.0;
-    double dxh = dx / mag, dyh = dy / mag, dzh = dz / mag;
+    const double im = fast_rcp(mag);
+    double dxh = dx * im, dyh = dy * im, dzh = dz * im;
     double px = x0 - x1, py = y0 - y1, pz = z0 - z1;
     double t = px * dxh + py * dyh + pz * dzh;
     double qx = x1 + t * dxh, qy = y1 + t * dyh, qz = z1 + t * dzh;
@@ -124,7 +161,8 @@ __device__ __forceinline__ void cal_des_vel(const Params &P, double px, double p
 #else
         // cos(atan2(fy,fx))*cos(atan2(fz,h)) == fx/dis etc. up to a few ulp (<<1e-3 rounding quantum);
         // h == 0 gives (0,0,+-1) on both routes.
-        d0 = np_round3(P.vel_max * (fx / dis)); d1 = np_round3(P.vel_max * (fy / dis)); d2 = np_round3(P.vel_max * (fz / dis));
+        const double id = fast_rcp(dis);
+        d0 = np_round3(P.vel_max * (fx * id)); d1 = np_round3(P.vel_max * (fy * id)); d2 = np_round3(P.vel_max * (fz * id));
 #endif
     } else {
         d0 = d1 = d2 = 0.0;
@@ -141,8 +179,8 @@ __device__ __forceinline__ double cal_vo_exp_tim(double rx, double ry, double rz
     if (c <= 0.0) return 0.0;
     double temp = b * b - 4.0 * a * c;
     if (temp <= 0.0) return CUDART_INF;
-    double sq = sqrt(temp);
-    double t1 = (-b + sq) / (2.0 * a), t2 = (-b - sq) / (2.0 * a);
+    double sq = sqrt(temp), ia = fast_rcp(2.0 * a);
+    double t1 = (-b + sq) * ia, t2 = (-b - sq) * ia;
     if (t1 < 0.0 && t2 < 0.0) return -1.0;
     double t3 = t1 >= 0.0 ? t1 : CUDART_INF, t4 = t2 >= 0.0 ? t2 : CUDART_INF;
     return t4 < t3 ? t4 : t3;
@@ -152,36 +190,41 @@ enum PairBits : int { PB_EVAL = 1, PB_COL = 2, PB_FULL = 4, PB_VO = 8 };
 
 // rvo_inter.preprocess neighbour test (rvo_inter.py:89-97) + config_vo_circle2 (rvo_inter.py:116-196).
 // (ax,ay,az) is the action with the |a|<1e-5 -> 0 substitution already applied.
+// t_out / alpha_h are valid when PB_FULL is set; md / iet only when PB_VO is set.
 __device__ __forceinline__ int vo_pair(const Params &P, double x, double y, double z, double vx, double vy, double vz,
                                        double r, double pra, double mx, double my, double mz, double mvx, double mvy,
                                        double mvz, double mr, double prb, double ax, double ay, double az,
                                        double &t_out, double &alpha_h, double &md, double &iet) {
     if (x == mx && y == my && z == mz) return 0;
-    if (!(np_norm3(x - mx, y - my, z - mz) <= P.nbr_range)) return 0;
-    double rel_x = mx - x, rel_y = my - y, rel_z = mz - z;
-    double dis = sqrt(rel_y * rel_y + rel_x * rel_x + rel_z * rel_z);
-    double R = r + mr;
-    bool col = P.env_train ? (dis <= R) : (dis <= r - P.exp_radius + mr);
+    const double rel_x = mx - x, rel_y = my - y, rel_z = mz - z;      // == -(self - other), squares identical
+    const double s2 = np_dot3(rel_x, rel_y, rel_z, rel_x, rel_y, rel_z);   // np.linalg.norm argument
+    if (!sqrt_le(s2, P.nbr_range)) return 0;
+    const double d2 = rel_y * rel_y + rel_x * rel_x + rel_z * rel_z;      // dis_mr^2, rvo_inter.py:135
+    const double R = r + mr;
+    const bool col = P.env_train ? sqrt_le(d2, R) : sqrt_le(d2, r - P.exp_radius + mr);
     if (col) return PB_EVAL | PB_COL;
-    double dotp = vx * rel_x + vy * rel_y + vz * rel_z;
+    const double dotp = vx * rel_x + vy * rel_y + vz * rel_z;
     if (dotp <= 0.0) return PB_EVAL;
-    alpha_h = py_round2_hundredths(asin(R / np_norm3(rel_x, rel_y, rel_z)));   // get_alpha, vel_obs3D.py:8-17
-    double pr = pra / (pra + prb);                                             // get_PAA, vel_obs3D.py:19-32
-    double PAAx = pr * (2.0 * x + (vx + mvx) * 1.0), PAAy = pr * (2.0 * y + (vy + mvy) * 1.0), PAAz = pr * (2.0 * z + (vz + mvz) * 1.0);
-    double Bx = x + 2.0 * ax * P.delta_t - PAAx, By = y + 2.0 * ay * P.delta_t - PAAy, Bz = z + 2.0 * az * P.delta_t - PAAz;
-    double AB = np_norm3(rel_x, rel_y, rel_z) * np_norm3(Bx, By, Bz);
-    double cosang = (AB != 0.0) ? np_dot3(rel_x, rel_y, rel_z, Bx, By, Bz) / AB : 0.0;
-    double beta_h = rint(acos(cosang) * 100.0);            // get_beta: unclamped arccos, numpy rounding
+    const double nab = sqrt(s2);
+    alpha_h = py_round2_hundredths(asin(fast_div(R, nab)));                // get_alpha, vel_obs3D.py:8-17
+    const double pr = fast_div(pra, pra + prb);                            // get_PAA, vel_obs3D.py:19-32
+    const double PAAx = pr * (2.0 * x + (vx + mvx) * 1.0), PAAy = pr * (2.0 * y + (vy + mvy) * 1.0), PAAz = pr * (2.0 * z + (vz + mvz) * 1.0);
+    const double Bx = x + 2.0 * ax * P.delta_t - PAAx, By = y + 2.0 * ay * P.delta_t - PAAy, Bz = z + 2.0 * az * P.delta_t - PAAz;
+    const double AB = nab * np_norm3(Bx, By, Bz);
+    const double cosang = (AB != 0.0) ? fast_div(np_dot3(rel_x, rel_y, rel_z, Bx, By, Bz), AB) : 0.0;
+    const double beta_h = rint(acos(cosang) * 100.0);      // get_beta: unclamped arccos, numpy rounding
     int bits = PB_EVAL | PB_FULL;
     double exp_time = CUDART_INF;
     if (alpha_h > beta_h) {                                 // alpha > beta on the rounded values; NaN beta -> outside
-        double rel_vx = 2.0 * ax - mvx - vx, rel_vy = 2.0 * ay - mvy - vy, rel_vz = 2.0 * az - mvz - vz;
+        const double rel_vx = 2.0 * ax - mvx - vx, rel_vy = 2.0 * ay - mvy - vy, rel_vz = 2.0 * az - mvz - vz;
         exp_time = cal_vo_exp_tim(rel_x, rel_y, rel_z, rel_vx, rel_vy, rel_vz, r, mr);
-        if (exp_time < P.ctime) bits |= PB_VO; else exp_time = CUDART_INF;
+        if (exp_time < P.ctime) {
+            bits |= PB_VO;
+            md = sqrt(d2) - mr;
+            iet = fast_div(1.0, exp_time + 0.2);
+        } else exp_time = CUDART_INF;
     }
     t_out = exp_time;
-    md = dis - mr;
-    iet = 1.0 / (exp_time + 0.2);
     return bits;
 }
 
@@ -218,7 +261,7 @@ __device__ __forceinline__ double angle_between(double A0, double A1, double A2,
     double magA = sqrt(A0 * A0 + A1 * A1 + A2 * A2 + eps), magB = sqrt(B0 * B0 + B1 * B1 + B2 * B2 + eps);
     double dp = A0 * B0 + A1 * B1 + A2 * B2;
     if (magA < 1e-6 || magB < 1e-6) return 0.0;
-    double c = np_clip(dp / (magA * magB), -1.0 + eps, 1.0 - eps);
+    double c = np_clip(fast_div(dp, magA * magB), -1.0 + eps, 1.0 - eps);
     return acos(c);
 }
 

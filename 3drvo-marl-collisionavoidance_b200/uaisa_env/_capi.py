@@ -61,7 +61,7 @@ def lib():
         L.uaisa_get_counters.argtypes = [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64), vp]
         L.uaisa_launch_count.argtypes = [vp]
         L.uaisa_launch_count.restype = C.c_int64
-        L.uaisa_step_host.argtypes = [vp] * 9
+        L.uaisa_step_host.argtypes = [vp] * 9 + [i32, i32]
         for name in SYMBOLS:
             fn = getattr(L, name)
             if fn.restype is C.c_int and name not in ("uaisa_version",):

@@ -174,12 +174,12 @@ class VecMdin:
     def launch_count(self) -> int:
         return int(self.L.uaisa_launch_count(self.h))
 
-    def step_host(self, action: np.ndarray, out: dict):
+    def step_host(self, action: np.ndarray, out: dict, auto_reset: bool = False, max_ep_len: int = 300):
         """End-to-end call with HOST buffers (numpy, ideally pinned): H2D action, step, D2H outputs."""
         p = lambda k: None if out.get(k) is None else out[k].ctypes.data_as(C.c_void_p)  # noqa: E731
         with torch.cuda.device(self.device):
             _capi.check(self.L.uaisa_step_host(self.h, action.ctypes.data_as(C.c_void_p), p("obs"), p("count"), p("nbr"), p("reward"),
-                                               p("done"), p("info"), p("finish")))
+                                               p("done"), p("info"), p("finish"), int(auto_reset), int(max_ep_len)))
         return out
 
 

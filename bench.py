@@ -1,0 +1,330 @@
+#!/usr/bin/env python
+"""bench.py -- agent-steps/s of the batched 3-D RVO env step (BASELINE.json metric) on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload c2|c3|c4|c5|sat]
+
+A "step" is one env step (PASS A -> move -> PASS B -> trainer auto-reset + re-observe) of every env of
+the workload; `value` = agent-steps/s over all ranks with actions and state resident in HBM, `e2e` = the
+same through uaisa_step_host with pinned HOST buffers (H2D actions + D2H outputs every step).
+Default workload = BASELINE.json configs[1]: 1024 envs x 4 drones (train/drone_paths.yaml scenario).
+Envs are independent, so ranks shard them with no data-path collective ("weak": E per GPU is fixed).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "3drvo-marl-collisionavoidance_b200")
+for p in (ROOT, PKG):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+from uaisa_env.scenario import scenario_c1, scenario_c3, scenario_c4  # noqa: E402
+
+NM = 10
+MAX_EP_LEN = 300             # train_process.py default max_ep_len
+BYTES_PER_AGENT_STEP = 156 + 40 * NM   # 556 B at nm=10
+
+
+def workload(name):
+    """-> (description, ScenarioSet, envs per GPU)"""
+    if name == "c2":
+        return "configs[1]: 1024 envs x 4 drones (train/drone_paths.yaml, 50x50x10, straight routes), nm=10", scenario_c1(), 1024
+    if name == "c3":
+        return "configs[2]: 4096 envs x 16 drones, 8 cylinders, 3-4 waypoint routes, nm=10", scenario_c3(seed=0, n_scenarios=8), 4096
+    if name == "c4":
+        return "configs[3]: 64 envs x 256 drones dense airspace 50x50x10, nm=10", scenario_c4(seed=0, n_scenarios=2), 64
+    if name == "c5":
+        return "configs[4] env part: 65536 envs x 4 drones per GPU, nm=10", scenario_c1(), 65536
+    if name == "sat":
+        return "saturating size: 262144 envs x 4 drones per GPU (configs[1] scenario), nm=10", scenario_c1(), 262144
+    raise SystemExit("unknown workload %r" % name)
+
+
+def synth_actions(rng, T, A):
+    """i.i.d. U(-1,1)^3 rounded to 2 dp (the trainer rounds its actions to 2 dp, multi_ppo.py:197-205)."""
+    return np.round(rng.uniform(-1.0, 1.0, size=(T, A, 3)), 2).astype(np.float32)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_baseline(scn, E, seconds=12.0, threads=0, seed=0):
+    """The oracle port (oracle/uaisa_oracle.c, OpenMP over envs) timed on the host cores on a bounded
+    sample of the same workload: same scenario, E envs, same action distribution, same reset policy."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle
+
+    ob = oracle.OracleBatch(scn, E, nm=NM)
+    cores = threads or oracle.max_threads()
+    oracle.set_threads(cores)
+    rng = np.random.default_rng(seed)
+    A = ob.A
+    ep_len = np.zeros(A, np.int32)
+    ob.reset(); ob.observe()
+    chunk = 8
+    acts = synth_actions(rng, chunk, A).astype(np.float64)
+
+    def one(t):
+        _, _, done, _, fin = ob.step(acts[t % chunk])
+        _, eobs, _ = ob.autoreset(done, fin, ep_len, MAX_EP_LEN, False)
+        if eobs.any():
+            ob.observe(eobs)
+
+    for t in range(2):
+        one(t)
+    n = 0
+    t0 = time.perf_counter()
+    while True:
+        one(n); n += 1
+        el = time.perf_counter() - t0
+        if el >= seconds or n >= 100000:
+            break
+    return {"value": A * n / el, "unit": "agent-steps/s", "cores": int(cores), "kind": "port",
+            "sample": "%d steps of %d envs x %d drones in %.1f s (oracle/uaisa_oracle.c, fp64, OpenMP over envs)" % (n, E, scn.N, el)}, n, el
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path = the oracle port (the reference is
+    pure Python and /root/reference does not travel to the GPU box).  Rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    desc, scn, E = workload(args.workload)
+    E_total = E * args.gpus
+    # bounded sample: each "step" is one env step of the full E_total-env workload on the host
+    E_run = min(E_total, 16384)
+    budget = 20.0
+    cb, n, el = cpu_baseline(scn, E_run, seconds=budget)
+    K = max(args.steps, 1)
+    line = {
+        "impl": "reference", "metric": "agent-steps/sec (batched 3D RVO env step)", "value": cb["value"], "unit": "agent-steps/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * E_total * scn.N / cb["value"],
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": desc, "envs_total": E_total, "drones_per_env": scn.N, "nm": NM,
+                   "sampled_envs": E_run, "sampled_steps": n, "note": "steps/warmup flags bound nothing here: the sample is time-bounded (%.0f s)" % budget},
+        "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": "agent-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    del K
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c2")
+    ap.add_argument("--chunk", type=int, default=0, help="env steps per rollout launch (0 = auto)")
+    ap.add_argument("--e2e-steps", type=int, default=0)
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--threads-per-block", type=int, default=0)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+
+    from uaisa_env.vec_env import VecMdin
+
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    desc, scn, E = workload(args.workload)
+    N = scn.N
+    A = E * N
+    K, W = max(args.steps, 1), max(args.warmup, 3)
+    env = VecMdin(scn, E, neighbors_num=NM, device=dev, threads_per_block=args.threads_per_block)
+    env.reset()
+    # ---- inputs resident in HBM: K steps of actions, outputs for one chunk of steps
+    per_step_out = A * (env.obs_dim * 4 + 1 + NM * 4 + 4 + 3)
+    chunk = args.chunk or max(1, min(K, int(6e9 // per_step_out), 512))
+    rng = np.random.default_rng(1234 + rank)
+    n_act = min(K, max(chunk, 64))
+    acts = torch.from_numpy(synth_actions(rng, n_act, A)).to(dev)           # reused cyclically when K > n_act
+    out = {"obs": torch.empty((chunk, A, env.obs_dim), dtype=torch.float32, device=dev), "count": torch.empty((chunk, A), dtype=torch.uint8, device=dev),
+           "nbr": torch.empty((chunk, A, NM), dtype=torch.int32, device=dev), "reward": torch.empty((chunk, A), dtype=torch.float32, device=dev),
+           "done": torch.empty((chunk, A), dtype=torch.uint8, device=dev), "info": torch.empty((chunk, A), dtype=torch.uint8, device=dev),
+           "finish": torch.empty((chunk, A), dtype=torch.uint8, device=dev)}
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)          # > 126 MB L2
+
+    def run_steps(nsteps, events=None):
+        done_steps = 0
+        while done_steps < nsteps:
+            T = min(chunk, nsteps - done_steps, n_act)
+            a0 = done_steps % n_act
+            if a0 + T > n_act:
+                T = n_act - a0
+            o = {k: v[:T] for k, v in out.items()}
+            if events is not None:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+            env.rollout(acts[a0:a0 + T], o, auto_reset=True, max_ep_len=MAX_EP_LEN)
+            if events is not None:
+                e1.record(); events.append((e0, e1, T))
+            done_steps += T
+
+    run_steps(W)
+    torch.cuda.synchronize()
+    flush.fill_(1)
+    clocks = ClockSampler(local) if rank == 0 else None
+    l0 = env.launch_count
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    evs = []
+    t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_start.record()
+    run_steps(K, evs)
+    t_end.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms = t_start.elapsed_time(t_end)
+    launches = env.launch_count - l0
+    kern_ms = sum(e0.elapsed_time(e1) for e0, e1, _ in evs)
+    clk = clocks.stop() if clocks else None
+    tms = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    ms_max = float(tms.item())
+    value = world * A * K / (ms_max * 1e-3)
+
+    # ---- single-launch-per-step variant (what a closed-loop policy would see), device timed
+    Ks = min(K, 200)
+    o1 = {k: v[:1] for k, v in out.items()}
+    for t in range(3):
+        env.rollout(acts[t % n_act:t % n_act + 1], o1, auto_reset=True, max_ep_len=MAX_EP_LEN)
+    torch.cuda.synchronize()
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s0.record()
+    for t in range(Ks):
+        env.rollout(acts[t % n_act:t % n_act + 1], o1, auto_reset=True, max_ep_len=MAX_EP_LEN)
+    s1.record(); torch.cuda.synchronize()
+    single_ms = s0.elapsed_time(s1) / Ks
+
+    # ---- end to end through the host-buffer C-ABI call: pinned host action in, all outputs back, every step
+    Ke = args.e2e_steps or min(K, 200 if A <= 65536 else 20)
+    pin = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory()  # noqa: E731
+    h_act = pin((A, 3), torch.float32)
+    h_out_t = {"obs": pin((A, env.obs_dim), torch.float32), "count": pin((A,), torch.uint8), "nbr": pin((A, NM), torch.int32),
+               "reward": pin((A,), torch.float32), "done": pin((A,), torch.uint8), "info": pin((A,), torch.uint8), "finish": pin((A,), torch.uint8)}
+    h_out = {k: v.numpy() for k, v in h_out_t.items()}
+    h_acts = synth_actions(rng, 8, A)
+    for t in range(3):
+        h_act.numpy()[...] = h_acts[t % 8]
+        env.step_host(h_act.numpy(), h_out, auto_reset=True, max_ep_len=MAX_EP_LEN)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    te0 = time.perf_counter()
+    for t in range(Ke):
+        h_act.numpy()[...] = h_acts[t % 8]          # the step's input is produced on the host
+        env.step_host(h_act.numpy(), h_out, auto_reset=True, max_ep_len=MAX_EP_LEN)
+        _ = float(h_out["reward"][0])               # the result is read on the host
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - te0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * A * Ke / float(te.item())
+    h2d = A * 3 * 4
+    d2h = A * (env.obs_dim * 4 + 1 + NM * 4 + 4 + 3)
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md 6.65 TB/s)"
+        avg_launch_ms = kern_ms / max(len(evs), 1)
+        steps_per_launch = K / max(len(evs), 1)
+        achieved = BYTES_PER_AGENT_STEP * A * steps_per_launch / (avg_launch_ms * 1e-3) / 1e9
+        cb = None
+        if not args.no_cpu:
+            cb, _, _ = cpu_baseline(scn, min(E, 16384), seconds=12.0)
+        line = {
+            "metric": "agent-steps/sec (batched 3D RVO env step)", "value": value, "unit": "agent-steps/s", "n_gpus": world,
+            "steps": K, "warmup": W, "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": desc, "envs_per_gpu": E, "drones_per_env": N, "nm": NM, "auto_reset": "trainer policy (multi_ppo.py:221-281), max_ep_len=300",
+                       "actions": "U(-1,1)^3 rounded to 2 dp, resident in HBM", "steps_per_launch": steps_per_launch, "threads_per_cta": env.cfg.threads_per_block or "auto",
+                       "l2": "flushed (256 MiB write) before the timed region; per-launch outputs %.0f MB" % (per_step_out * steps_per_launch / 1e6),
+                       "state": "fp32 SoA in HBM, fp64 arithmetic"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "kernel": "uaisa_env_kernel", "bytes_per_agent_step": BYTES_PER_AGENT_STEP, "avg_launch_ms": avg_launch_ms,
+                         "peak_source": peak_src},
+            "single_step_launch": {"value": world * A / (single_ms * 1e-3), "unit": "agent-steps/s", "ms_per_step": single_ms,
+                                   "note": "one launch per env step (closed-loop use), device-timed over %d steps" % Ks},
+            "e2e": {"value": e2e_value, "unit": "agent-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke},
+            "gpu_launches": int(launches), "clocks": clk,
+        }
+        if cb:
+            line["cpu_baseline"] = cb
+        print(json.dumps(line))
+    env.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -139,10 +139,11 @@ int uaisa_get_counters(UaisaHandle *h, int64_t *in_range_pairs, int64_t *cone_ev
 /* kernel launches issued through this handle so far (bench.py's gpu_launches) */
 int64_t uaisa_launch_count(const UaisaHandle *h);
 
-/* Host-buffer convenience used for the end-to-end number: H2D(action) -> step -> D2H(outputs), all
- * pointers HOST (pinned for full speed), synchronous on return. */
+/* Host-buffer convenience used for the end-to-end number: H2D(action) -> step [-> trainer auto-reset
+ * + re-observe, as uaisa_rollout's auto_reset] -> D2H(outputs); all pointers HOST (pinned for full
+ * speed); synchronous on return. */
 int uaisa_step_host(UaisaHandle *h, const float *action, float *obs, uint8_t *count, int32_t *nbr, float *reward,
-                    uint8_t *done, uint8_t *info, uint8_t *finish);
+                    uint8_t *done, uint8_t *info, uint8_t *finish, int32_t auto_reset, int32_t max_ep_len);
 
 #ifdef __cplusplus
 }

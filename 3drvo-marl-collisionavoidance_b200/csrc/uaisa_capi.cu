@@ -118,6 +118,8 @@ int uaisa_create(const UaisaConfig *cfg, UaisaHandle **out) {
     P.goal_thr = cfg->goal_threshold; P.max_acc = cfg->max_acc; P.max_ang = cfg->max_angle_change; P.dt = cfg->dt;
     P.vel_max = cfg->vel_max; P.nbr_range = cfg->neighbor_range; P.bld_range = cfg->building_range;
     P.bld_zgate = cfg->building_zgate; P.ctime = cfg->ctime_threshold; P.delta_t = cfg->delta_t; P.exp_radius = cfg->exp_radius;
+    P.goal2_lo = P.goal_thr * P.goal_thr * (1.0 - 1e-14); P.goal2_hi = P.goal_thr * P.goal_thr * (1.0 + 1e-14);
+    P.nbr2_lo = P.nbr_range * P.nbr_range * (1.0 - 1e-14); P.nbr2_hi = P.nbr_range * P.nbr_range * (1.0 + 1e-14);
     // launch geometry: whole envs per CTA; shrink the CTA until the grid covers the 148 SMs twice
     int threads = cfg->threads_per_block;
     const int minthreads = ((N + 31) / 32) * 32;
@@ -128,12 +130,11 @@ int uaisa_create(const UaisaConfig *cfg, UaisaHandle **out) {
     if (threads < N || threads > 1024 || threads % 32) { delete h; return fail(UAISA_EINVAL, "threads_per_block must be a multiple of 32 in [n_drones, 1024]"); }
     h->threads = threads; P.threads = threads; P.envs_per_cta = threads / N;
     h->grid = (E + P.envs_per_cta - 1) / P.envs_per_cta;
-    h->smem = sizeof(double) * 8 * threads + 4 * (size_t)(((threads * P.obs_dim + 3) & ~3) + ((threads * P.nm + 3) & ~3)) + sizeof(int) * 2 * P.envs_per_cta;
+    h->smem = sizeof(double) * 8 * threads + sizeof(int) * 2 * P.envs_per_cta;
     const int need = cfg->nm < N - 1 ? cfg->nm : N - 1;
     if (threads > 256) h->kernel = uaisa_env_kernel<16, 1024>;
-    else if (need <= 4) h->kernel = uaisa_env_kernel<4, 256>;
-    else if (need <= 10) h->kernel = uaisa_env_kernel<10, 256>;
-    else h->kernel = uaisa_env_kernel<16, 256>;
+    else if (threads > 128) h->kernel = need <= 4 ? uaisa_env_kernel<4, 256> : need <= 10 ? uaisa_env_kernel<10, 256> : uaisa_env_kernel<16, 256>;
+    else h->kernel = need <= 4 ? uaisa_env_kernel<4, 128> : need <= 10 ? uaisa_env_kernel<10, 128> : uaisa_env_kernel<16, 128>;
     if (h->smem > (size_t)prop.sharedMemPerBlockOptin) { delete h; return fail(UAISA_EINVAL, "shared memory per CTA exceeds the device limit; lower threads_per_block"); }
     cudaError_t e = cudaFuncSetAttribute(reinterpret_cast<const void *>(h->kernel), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem);
     if (e != cudaSuccess) { delete h; return cuda_fail(e, "cudaFuncSetAttribute"); }

@@ -38,6 +38,7 @@ struct Params {
     int env_train, count_pairs;
     // hyper-parameters (reference constructor defaults, see include/uaisa_b200.h)
     double goal_thr, max_acc, max_ang, dt, vel_max, nbr_range, bld_range, bld_zgate, ctime, delta_t, exp_radius;
+    double goal2_lo, goal2_hi, nbr2_lo, nbr2_hi;   // T^2*(1 -+ 1e-14) guard bands for sqrt(x) <= T (host-computed)
     // scenario constants (device, fp64, shared by envs -> L2/L1 resident)
     const double *wp; const int *npts; const double *route_len; const double *radius; const double *prio;
     const double *bld; const int *nbld; const double *map; const int *env2scn;
@@ -91,13 +92,36 @@ __device__ __forceinline__ double np_round2(double x) { double k = rint(x * 100.
 __device__ __forceinline__ double np_round3(double x) { double k = rint(x * 1000.0); return isfinite(k) ? div_const(k, 1000.0, 0.001) : k; }
 // (float)np.round(x, 2): the fp32 image of rint(x*100)/100 equals the fp32 image of rint(x*100)*0.01
 // (k/100 is never within 2^-30 of an fp32 rounding tie unless it is exact; checked exhaustively, ibid.)
-__device__ __forceinline__ float np_round2_f32(double x, bool &bad) { double k = rint(x * 100.0); bad |= !isfinite(k); return (float)(k * 0.01); }
+__device__ __forceinline__ float np_round2_f32(double x) { return (float)(rint(x * 100.0) * 0.01); }
 // sqrt(x) <= T without the square root unless x is within 1e-14 of T^2 (NaN -> false)
+__device__ __forceinline__ bool sqrt_le_band(double x, double T, double lo, double hi) {
+    const bool below = x < lo;
+    if (below || x > hi) return below;
+    return sqrt(x) <= T;
+}
 __device__ __forceinline__ bool sqrt_le(double x, double T) {
     const double T2 = T * T;
-    if (x < T2 * (1.0 - 1e-14)) return true;
-    if (x > T2 * (1.0 + 1e-14)) return false;
-    return sqrt(x) <= T;
+    return sqrt_le_band(x, T, T2 * (1.0 - 1e-14), T2 * (1.0 + 1e-14));
+}
+// sin/cos of t = deg * (pi/180) for |t| <~ 8 (yaw in [0,360], pitch in [-90,90]): two-term Cody-Waite
+// reduction by pi/2 and the fdlibm __kernel_sin/__kernel_cos minimax polynomials (< 1 ulp), no slow path.
+__device__ __forceinline__ void sincos_small(double t, double &s, double &c) {
+    const double k = rint(t * 6.36619772367581382433e-01);          // 2/pi
+    double r = fma(-k, 1.57079632679489655800e+00, t);             // pi/2 hi
+    r = fma(-k, 6.12323399573676603587e-17, r);                    // pi/2 lo
+    const double z = r * r;
+    double ps = fma(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
+    ps = fma(z, ps, 2.75573137070700676789e-06); ps = fma(z, ps, -1.98412698298579493134e-04);
+    ps = fma(z, ps, 8.33333333332248946124e-03); ps = fma(z, ps, -1.66666666666666324348e-01);
+    const double sr = fma(z * r, ps, r);
+    double pc = fma(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
+    pc = fma(z, pc, -2.75573143513906633035e-07); pc = fma(z, pc, 2.48015872894767294178e-05);
+    pc = fma(z, pc, -1.38888888888741095749e-03); pc = fma(z, pc, 4.16666666666666019037e-02);
+    const double cr = fma(z * z, pc, fma(-0.5, z, 1.0));
+    const int q = (int)k & 3;
+    const double ss = (q & 1) ? cr : sr, cc = (q & 1) ? sr : cr;
+    s = (q & 2) ? -ss : ss;
+    c = ((q + 1) & 2) ? -cc : cc;
 }
 // builtin round(x, 2) of a Python float, returned in hundredths (exact decimal rounding, ties to even)
 __device__ __forceinline__ double py_round2_hundredths(double x) {
@@ -129,7 +153,7 @@ __device__ __forceinline__ void load3(const double *p, double &x, double &y, dou
 __device__ __forceinline__ bool within_goal(const Params &P, double px, double py, double pz, const double *q) {
     double qx, qy, qz; load3(q, qx, qy, qz);
     const double fx = px - qx, fy = py - qy, fz = pz - qz;
-    return sqrt_le(np_dot3(fx, fy, fz, fx, fy, fz), P.goal_thr);   // norm(p - q) <= 0.4, drone.py:172-192
+    return sqrt_le_band(np_dot3(fx, fy, fz, fx, fy, fz), P.goal_thr, P.goal2_lo, P.goal2_hi);   // norm(p - q) <= 0.4, drone.py:172-192
 }
 
 // drone.calculate_deviation (drone.py:366-406)
@@ -189,22 +213,26 @@ __device__ __forceinline__ double cal_vo_exp_tim(double rx, double ry, double rz
 enum PairBits : int { PB_EVAL = 1, PB_COL = 2, PB_FULL = 4, PB_VO = 8 };
 
 // rvo_inter.preprocess neighbour test (rvo_inter.py:89-97) + config_vo_circle2 (rvo_inter.py:116-196).
+// `so` points at the other drone's column of the exchange array (stride `st` doubles between the 8 fields
+// px py pz vx vy vz r prio); fields are loaded only once they are needed.
 // (ax,ay,az) is the action with the |a|<1e-5 -> 0 substitution already applied.
 // t_out / alpha_h are valid when PB_FULL is set; md / iet only when PB_VO is set.
 __device__ __forceinline__ int vo_pair(const Params &P, double x, double y, double z, double vx, double vy, double vz,
-                                       double r, double pra, double mx, double my, double mz, double mvx, double mvy,
-                                       double mvz, double mr, double prb, double ax, double ay, double az,
+                                       double r, double pra, const double *so, int st, double ax, double ay, double az,
                                        double &t_out, double &alpha_h, double &md, double &iet) {
+    const double mx = so[0], my = so[st], mz = so[2 * st];
     if (x == mx && y == my && z == mz) return 0;
     const double rel_x = mx - x, rel_y = my - y, rel_z = mz - z;      // == -(self - other), squares identical
     const double s2 = np_dot3(rel_x, rel_y, rel_z, rel_x, rel_y, rel_z);   // np.linalg.norm argument
-    if (!sqrt_le(s2, P.nbr_range)) return 0;
+    if (!sqrt_le_band(s2, P.nbr_range, P.nbr2_lo, P.nbr2_hi)) return 0;
     const double d2 = rel_y * rel_y + rel_x * rel_x + rel_z * rel_z;      // dis_mr^2, rvo_inter.py:135
+    const double mr = so[6 * st];
     const double R = r + mr;
     const bool col = P.env_train ? sqrt_le(d2, R) : sqrt_le(d2, r - P.exp_radius + mr);
     if (col) return PB_EVAL | PB_COL;
     const double dotp = vx * rel_x + vy * rel_y + vz * rel_z;
     if (dotp <= 0.0) return PB_EVAL;
+    const double mvx = so[3 * st], mvy = so[4 * st], mvz = so[5 * st], prb = so[7 * st];
     const double nab = sqrt(s2);
     alpha_h = py_round2_hundredths(asin(fast_div(R, nab)));                // get_alpha, vel_obs3D.py:8-17
     const double pr = fast_div(pra, pra + prb);                            // get_PAA, vel_obs3D.py:19-32
@@ -255,14 +283,21 @@ struct TopList {
     }
 };
 
-// ir_gym.calculate_angle_between_vectors, 2nd definition (ir_gym.py:447-473)
-__device__ __forceinline__ double angle_between(double A0, double A1, double A2, double B0, double B1, double B2) {
+// ir_gym.calculate_angle_between_vectors, 2nd definition (ir_gym.py:447-473), folded with the angle
+// buckets of rvo_reward_cal (ir_gym.py:90-100): theta = acos(c) is only compared with pi/18, pi/6, pi/3,
+// pi/2, and acos is monotone, so the bucket is read off c against the cosines of those angles
+// (thresholds found by bisection against the libm the reference calls).  NaN -> -4 like the reference's else-branch.
+__device__ __forceinline__ double angle_punish(double A0, double A1, double A2, double B0, double B1, double B2) {
     const double eps = 1e-8;
-    double magA = sqrt(A0 * A0 + A1 * A1 + A2 * A2 + eps), magB = sqrt(B0 * B0 + B1 * B1 + B2 * B2 + eps);
-    double dp = A0 * B0 + A1 * B1 + A2 * B2;
-    if (magA < 1e-6 || magB < 1e-6) return 0.0;
-    double c = np_clip(fast_div(dp, magA * magB), -1.0 + eps, 1.0 - eps);
-    return acos(c);
+    const double magA = sqrt(A0 * A0 + A1 * A1 + A2 * A2 + eps), magB = sqrt(B0 * B0 + B1 * B1 + B2 * B2 + eps);
+    const double dp = A0 * B0 + A1 * B1 + A2 * B2;
+    const double c = np_clip(fast_div(dp, magA * magB), -1.0 + eps, 1.0 - eps);
+    // smallest doubles c with glibc acos(c) < pi/18, pi/6, pi/3, pi/2 (bisection over doubles)
+    if (c >= 0x1.f838b8c811c18p-1) return 3.0;
+    if (c >= 0x1.bb67ae8584cabp-1) return 1.0;
+    if (c >= 0x1.0000000000002p-1) return 0.5;
+    if (c >= 0x1.8d313198a2e04p-53) return 0.0;
+    return -4.0;
 }
 
 template <int MAXR, int MAXT>

@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libuaisa_b200.so")
+LIB_PATH = os.environ.get("UAISA_B200_LIB") or os.path.join(os.path.dirname(_HERE), "lib", "libuaisa_b200.so")
 
 SYMBOLS = (
     "uaisa_last_error", "uaisa_version", "uaisa_default_config", "uaisa_create", "uaisa_destroy",

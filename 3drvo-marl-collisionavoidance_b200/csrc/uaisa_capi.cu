@@ -130,27 +130,29 @@ int uaisa_create(const UaisaConfig *cfg, UaisaHandle **out) {
     if (threads < N || threads > 1024 || threads % 32) { delete h; return fail(UAISA_EINVAL, "threads_per_block must be a multiple of 32 in [n_drones, 1024]"); }
     h->threads = threads; P.threads = threads; P.envs_per_cta = threads / N;
     h->grid = (E + P.envs_per_cta - 1) / P.envs_per_cta;
-    h->smem = sizeof(double) * 8 * threads + sizeof(int) * 2 * P.envs_per_cta;
+    h->smem = sizeof(double) * 8 * threads + sizeof(int) * 2 * P.envs_per_cta + 16 + 2 * 4096;   // + TMA fill tiles
     const int need = cfg->nm < N - 1 ? cfg->nm : N - 1;
-    if (threads > 256) h->kernel = uaisa_env_kernel<16, 1024>;
-    else if (threads > 128) h->kernel = need <= 4 ? uaisa_env_kernel<4, 256> : need <= 10 ? uaisa_env_kernel<10, 256> : uaisa_env_kernel<16, 256>;
-    else h->kernel = need <= 4 ? uaisa_env_kernel<4, 128> : need <= 10 ? uaisa_env_kernel<10, 128> : uaisa_env_kernel<16, 128>;
+    const bool wl = (N <= 32) && (32 % N == 0) && threads <= 128;   // every env inside one warp
+    if (threads > 256) h->kernel = uaisa_env_kernel<16, 1024, false>;
+    else if (threads > 128) h->kernel = need <= 4 ? uaisa_env_kernel<4, 256, false> : need <= 10 ? uaisa_env_kernel<10, 256, false> : uaisa_env_kernel<16, 256, false>;
+    else if (wl) h->kernel = need <= 4 ? uaisa_env_kernel<4, 128, true> : need <= 10 ? uaisa_env_kernel<10, 128, true> : uaisa_env_kernel<16, 128, true>;
+    else h->kernel = need <= 4 ? uaisa_env_kernel<4, 128, false> : need <= 10 ? uaisa_env_kernel<10, 128, false> : uaisa_env_kernel<16, 128, false>;
     if (h->smem > (size_t)prop.sharedMemPerBlockOptin) { delete h; return fail(UAISA_EINVAL, "shared memory per CTA exceeds the device limit; lower threads_per_block"); }
     cudaError_t e = cudaFuncSetAttribute(reinterpret_cast<const void *>(h->kernel), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem);
     if (e != cudaSuccess) { delete h; return cuda_fail(e, "cudaFuncSetAttribute"); }
     const size_t A = h->A, S = cfg->n_scenarios, SN = S * N;
     int rc = UAISA_OK;
-    double *wp, *rl, *rad, *pr, *bld, *map; int *npts, *nbld, *e2s;
-    if ((rc = dalloc(h, &wp, SN * P.W * 3)) || (rc = dalloc(h, &npts, SN)) || (rc = dalloc(h, &rl, SN)) || (rc = dalloc(h, &rad, SN)) ||
+    double *wp, *sg, *rl, *rad, *pr, *bld, *map; int *npts, *nbld, *e2s;
+    if ((rc = dalloc(h, &wp, SN * P.W * 3)) || (rc = dalloc(h, &sg, SN * P.W * 4)) || (rc = dalloc(h, &npts, SN)) || (rc = dalloc(h, &rl, SN)) || (rc = dalloc(h, &rad, SN)) ||
         (rc = dalloc(h, &pr, SN)) || (rc = dalloc(h, &bld, S * P.M * 4)) || (rc = dalloc(h, &nbld, S)) || (rc = dalloc(h, &map, S * 3)) ||
         (rc = dalloc(h, &e2s, (size_t)E)) || (rc = dalloc(h, &P.pos_yaw, A)) || (rc = dalloc(h, &P.vel_pitch, A)) ||
         (rc = dalloc(h, &P.real_len, A)) || (rc = dalloc(h, &P.max_dev, A)) || (rc = dalloc(h, &P.extra_len, A)) ||
-        (rc = dalloc(h, &P.wpf, A)) || (rc = dalloc(h, &P.ep_len, A)) || (rc = dalloc(h, &P.counters, 4))) {
+        (rc = dalloc(h, &P.wpf, A)) || (rc = dalloc(h, &P.ep_len, A)) || (rc = dalloc(h, &P.counters, 32))) {
         uaisa_destroy(h);
         return rc;
     }
-    P.wp = wp; P.npts = npts; P.route_len = rl; P.radius = rad; P.prio = pr; P.bld = bld; P.nbld = nbld; P.map = map; P.env2scn = e2s;
-    cudaMemset(P.extra_len, 0, sizeof(float) * A); cudaMemset(P.ep_len, 0, sizeof(int) * A); cudaMemset(P.counters, 0, 32);
+    P.wp = wp; P.seg = sg; P.npts = npts; P.route_len = rl; P.radius = rad; P.prio = pr; P.bld = bld; P.nbld = nbld; P.map = map; P.env2scn = e2s;
+    cudaMemset(P.extra_len, 0, sizeof(float) * A); cudaMemset(P.ep_len, 0, sizeof(int) * A); cudaMemset(P.counters, 0, 32 * 8);
     *out = h;
     return UAISA_OK;
 }
@@ -171,7 +173,7 @@ int uaisa_set_scenarios(UaisaHandle *h, const double *waypoints, const int32_t *
         return fail(UAISA_EINVAL, "NULL argument");
     const Params &P = h->P;
     const size_t S = h->cfg.n_scenarios, N = P.N, SN = S * N, W = P.W;
-    std::vector<double> rl(SN);
+    std::vector<double> rl(SN), sg(SN * W * 4, 0.0);
     for (size_t q = 0; q < SN; q++) {
         if (n_points[q] < 2 || n_points[q] > (int)W) return fail(UAISA_EINVAL, "n_points must be in [2, max_waypoints] (drone.py:46-48 reads waypoints[1])");
         double tot = 0.0;   // drone.calculate_total_length (drone.py:409-429)
@@ -181,11 +183,19 @@ int uaisa_set_scenarios(UaisaHandle *h, const double *waypoints, const int32_t *
             tot += std::sqrt(dx * dx + dy * dy + dz * dz);
         }
         rl[q] = tot;
+        for (size_t i = 1; i < W; i++) {   // segment wp[i-1] -> wp[i] as drone.calculate_deviation normalises it (drone.py:374-388)
+            double dx = w[3 * i] - w[3 * (i - 1)], dy = w[3 * i + 1] - w[3 * (i - 1) + 1], dz = w[3 * i + 2] - w[3 * (i - 1) + 2];
+            double mag = std::sqrt(dx * dx + dy * dy + dz * dz);
+            double *g = sg.data() + (q * W + i) * 4;
+            g[3] = mag;
+            if (mag != 0.0) { g[0] = dx / mag; g[1] = dy / mag; g[2] = dz / mag; }
+        }
     }
     for (size_t s = 0; s < S; s++) if (n_buildings[s] < 0 || n_buildings[s] > P.M) return fail(UAISA_EINVAL, "n_buildings out of range");
     for (int e = 0; e < P.E; e++) if (env2scenario[e] < 0 || env2scenario[e] >= (int)S) return fail(UAISA_EINVAL, "env2scenario out of range");
     DeviceGuard g(h->device);
     CK(cudaMemcpy(const_cast<double *>(P.wp), waypoints, sizeof(double) * SN * W * 3, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(const_cast<double *>(P.seg), sg.data(), sizeof(double) * SN * W * 4, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(const_cast<int *>(P.npts), n_points, sizeof(int) * SN, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(const_cast<double *>(P.route_len), rl.data(), sizeof(double) * SN, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(const_cast<double *>(P.radius), radius, sizeof(double) * SN, cudaMemcpyHostToDevice));
@@ -289,6 +299,15 @@ int uaisa_get_counters(UaisaHandle *h, int64_t *in_range_pairs, int64_t *cone_ev
 }
 
 int64_t uaisa_launch_count(const UaisaHandle *h) { return h ? h->launches : 0; }
+
+int uaisa_get_region_clocks(UaisaHandle *h, int64_t *out16, void *stream) {
+    if (!h || !out16) return fail(UAISA_EINVAL, "NULL argument");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    CK(cudaMemcpyAsync(out16, h->P.counters + 8, 16 * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemsetAsync(h->P.counters + 8, 0, 16 * sizeof(int64_t), s));
+    CK(cudaStreamSynchronize(s));
+    return UAISA_OK;
+}
 
 int uaisa_step_host(UaisaHandle *h, const float *action, float *obs, uint8_t *count, int32_t *nbr, float *reward, uint8_t *done,
                     uint8_t *info, uint8_t *finish, int32_t auto_reset, int32_t max_ep_len) {

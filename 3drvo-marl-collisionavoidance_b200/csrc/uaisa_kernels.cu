@@ -38,20 +38,59 @@ __device__ __forceinline__ void fill_out(uint32_t *__restrict__ dst, int n, uint
     for (int i = head + (n4 << 2) + tid; i < n; i += nthreads) dst[i] = v;
 }
 
+// ---- TMA bulk stores (cp.async.bulk shared::cta -> global): the zero padding that makes up most of every
+// observation row is streamed to HBM by the copy engine from a constant shared-memory tile, off the warps'
+// critical path and out of the LSU store queue.
+constexpr int FILL_TILE = 4096;   // bytes of each constant tile (zeros / 0xFF)
+__device__ __forceinline__ void bulk_store(void *gdst, const void *ssrc, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"((uint32_t)__cvta_generic_to_shared(ssrc)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// called by ONE lane: fill [dst, dst+bytes) from the constant tile (dst 16-byte aligned, bytes % 16 == 0)
+__device__ __forceinline__ void bulk_fill(char *dst, const void *tile, int bytes) {
+    for (int off = 0; off < bytes; off += FILL_TILE) bulk_store(dst + off, tile, (uint32_t)min(FILL_TILE, bytes - off));
+}
+
 enum Phase : int { PH_A = 0, PH_B = 1, PH_OBS = 2 };
+
+// Optional per-region cycle accounting (build with -DUAISA_REGION_CLOCKS; lane 0 of every warp accumulates
+// clock64() deltas into counters[8+region]).  A profiling aid only; compiled out of the product build.
+enum Region : int { RG_PROLOGUE = 0, RG_FILL, RG_SYNC, RG_DRONESTATE, RG_PAIRS, RG_REWARD_A, RG_MOVE, RG_OBSROW, RG_TAIL_B, RG_AUTORESET, RG_EPILOGUE, RG_B_FLAGS, RG_B_COL, RG_B_REWARD, RG_B_OUT, RG_ACT, RG_COUNT };
+#ifdef UAISA_REGION_CLOCKS
+#define RG_DECL long long rg_acc[RG_COUNT]; for (int q_ = 0; q_ < RG_COUNT; q_++) rg_acc[q_] = 0; long long rg_t = clock64();
+#define RG_MARK(r) do { const long long n_ = clock64(); rg_acc[r] += n_ - rg_t; rg_t = n_; } while (0)
+#define RG_FLUSH() do { if ((threadIdx.x & 31) == 0) for (int q_ = 0; q_ < RG_COUNT; q_++) atomicAdd(P.counters + 8 + q_, (unsigned long long)rg_acc[q_]); } while (0)
+#else
+#define RG_DECL
+#define RG_MARK(r) do { } while (0)
+#define RG_FLUSH() do { } while (0)
+#endif
 
 #ifndef UAISA_MINB128
 #define UAISA_MINB128 3   // CTAs of 128 threads per SM the register allocator must leave room for
 #endif
-template <int MAXR, int MAXT>
+// WL ("warp local"): N divides 32, so every env lives inside one warp -- all CTA barriers become __syncwarp(),
+// the per-env reductions of the reset policy become ballots, and each warp clears its own 32 output rows.
+template <int MAXR, int MAXT, bool WL>
 __global__ void __launch_bounds__(MAXT, (MAXT <= 128 ? UAISA_MINB128 : 1)) uaisa_env_kernel(const __grid_constant__ Params P, const __grid_constant__ Launch L) {
+#define ENV_SYNC() do { if (WL) __syncwarp(); else __syncthreads(); } while (0)
     extern __shared__ double smem_d[];
     const int threads = P.threads;
     double *sx = smem_d;                                                         // [8][threads] exchange
     int *senv = reinterpret_cast<int *>(sx + 8 * threads);                       // [envs_per_cta] reduction bits
     int *ssel = senv + P.envs_per_cta;                                           // [envs_per_cta] obs selected
+    // constant tiles for the TMA fills (WL only), 16-byte aligned after the arrays above
+    uint4 *tile0 = reinterpret_cast<uint4 *>((reinterpret_cast<uintptr_t>(ssel + P.envs_per_cta) + 15) & ~uintptr_t(15));
+    uint4 *tile1 = tile0 + FILL_TILE / 16;
+    if (WL) {
+        for (int i = threadIdx.x; i < FILL_TILE / 16; i += blockDim.x) { tile0[i] = make_uint4(0u, 0u, 0u, 0u); tile1[i] = make_uint4(~0u, ~0u, ~0u, ~0u); }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the copy engine
+        __syncthreads();
+    }
 
-    const int tid = threadIdx.x, N = P.N;
+    const int tid = threadIdx.x, N = P.N, lane = tid & 31;
+    const unsigned env_lanes = WL ? (N >= 32 ? 0xffffffffu : (((1u << N) - 1u) << (lane - lane % N))) : 0u;
     const int le = tid / N, k = tid - le * N;
     const int env0 = blockIdx.x * P.envs_per_cta;
     const int env = env0 + le;
@@ -64,6 +103,7 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 128 ? UAISA_MINB128 : 1)) uaisa
     const bool is_step = L.mode == MODE_STEP;
     const bool do_auto = (L.mode == MODE_AUTORESET) || (is_step && L.auto_reset);
 
+    RG_DECL
     Consts C; Drone d; int ep_len = 0;
     const double *bld = nullptr; int nb = 0, scn = 0;
     double extra_len_new = 0.0; bool extra_len_dirty = false;
@@ -71,7 +111,7 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 128 ? UAISA_MINB128 : 1)) uaisa
         scn = __ldg(P.env2scn + env);
         const int sn = scn * N + k;
         C.wp = P.wp + (size_t)sn * P.W * 3; C.radius = __ldg(P.radius + sn); C.prio = __ldg(P.prio + sn);
-        C.route_len = __ldg(P.route_len + sn); C.n = __ldg(P.npts + sn);
+        C.route_len = __ldg(P.route_len + sn); C.n = __ldg(P.npts + sn); C.seg = P.seg + (size_t)sn * P.W * 4;
         bld = P.bld + (size_t)scn * P.M * 4; nb = __ldg(P.nbld + scn);
         const float4 py = P.pos_yaw[a], vp = P.vel_pitch[a];
         d.px = py.x; d.py = py.y; d.pz = py.z; d.yaw = py.w; d.vx = vp.x; d.vy = vp.y; d.vz = vp.z; d.pitch = vp.w;
@@ -82,67 +122,105 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 128 ? UAISA_MINB128 : 1)) uaisa
     }
     unsigned n_rng = 0, n_cone = 0, n_bad = 0;
     const int T = is_step ? L.T : 1;
+    RG_MARK(RG_PROLOGUE);
 
     for (int t = 0; t < T; t++) {
         const size_t o = (size_t)t * A + a;              // this thread's slot in the [T][A] outputs
         float *const myobs = L.obs ? L.obs + o * P.obs_dim : nullptr;
         int *const mynbr = L.nbr ? L.nbr + o * P.nm : nullptr;
-        if (tid < P.envs_per_cta) { senv[tid] = 0; ssel[tid] = 0; }
-        if (is_step) {   // every row of the CTA is written this step: clear the whole region once, coalesced
-            const size_t abase = (size_t)t * A + (size_t)env0 * N;
-            if (L.obs) fill_out(reinterpret_cast<uint32_t *>(L.obs + abase * P.obs_dim), nag_here * P.obs_dim, 0u, tid, blockDim.x);
-            if (L.nbr) fill_out(reinterpret_cast<uint32_t *>(L.nbr + abase * P.nm), nag_here * P.nm, ~0u, tid, blockDim.x);
+        float a32x = 0.f, a32y = 0.f, a32z = 0.f;        // issue the action loads ahead of the burst of clearing stores
+        if (is_step && valid) {
+            const float *ap = L.action + o * 3; a32x = ap[0]; a32y = ap[1]; a32z = ap[2];
+            if (t + 1 < T) asm volatile("prefetch.global.L2 [%0];" ::"l"(ap + (size_t)A * 3));   // next step's action
         }
-        double ax = 0, ay = 0, az = 0, rA = 0;
-        if (is_step && valid) { const float *ap = L.action + o * 3; ax = ap[0]; ay = ap[1]; az = ap[2]; }
+        if (!WL && tid < P.envs_per_cta) { senv[tid] = 0; ssel[tid] = 0; }
+        if (is_step) {   // every row is written this step: clear the output region once, coalesced 16-byte stores
+            if (WL) {    // my warp's 32 rows
+                const int w0 = tid - lane, nw = min(32, nag_here - w0);
+                if (nw > 0) {
+                    const size_t abase = (size_t)t * A + (size_t)env0 * N + w0;
+                    if (L.obs) {
+                        char *dst = reinterpret_cast<char *>(L.obs + abase * P.obs_dim); const int bytes = nw * P.obs_dim * 4;
+                        if (((reinterpret_cast<uintptr_t>(dst) | (uintptr_t)bytes) & 15) == 0) { if (lane == 0) bulk_fill(dst, tile0, bytes); }
+                        else fill_out(reinterpret_cast<uint32_t *>(dst), bytes >> 2, 0u, lane, 32);
+                    }
+                    if (L.nbr) {
+                        char *dst = reinterpret_cast<char *>(L.nbr + abase * P.nm); const int bytes = nw * P.nm * 4;
+                        if (((reinterpret_cast<uintptr_t>(dst) | (uintptr_t)bytes) & 15) == 0) { if (lane == 0) bulk_fill(dst, tile1, bytes); }
+                        else fill_out(reinterpret_cast<uint32_t *>(dst), bytes >> 2, ~0u, lane, 32);
+                    }
+                    if (lane == 0) bulk_commit();
+                }
+            } else {
+                const size_t abase = (size_t)t * A + (size_t)env0 * N;
+                if (L.obs) fill_out(reinterpret_cast<uint32_t *>(L.obs + abase * P.obs_dim), nag_here * P.obs_dim, 0u, tid, blockDim.x);
+                if (L.nbr) fill_out(reinterpret_cast<uint32_t *>(L.nbr + abase * P.nm), nag_here * P.nm, ~0u, tid, blockDim.x);
+            }
+        }
+        RG_MARK(RG_FILL);
+        const double ax = a32x, ay = a32y, az = a32z; double rA = 0;
+#ifdef UAISA_REGION_CLOCKS
+        if (ax + ay + az == 123456.0) n_bad++;   // force the loads to complete here
+#endif
+        RG_MARK(RG_ACT);
         bool st_done = false, st_fin = false;
         int staged = -1;                                 // rows of mine already in HBM this step (-1: none, row not cleared)
 
         for (int ph = is_step ? PH_A : PH_OBS; ph <= PH_OBS; ph++) {
             bool active = valid;
+            RG_MARK(RG_TAIL_B);
             if (ph == PH_OBS) {
                 // ------------------------------------------------ who gets (re-)observed
+                bool sel = false;      // my env is (re-)observed
+                bool rs = false;       // I am reset
                 if (L.mode == MODE_RESET) {
-                    __syncthreads();
-                    if (valid && (L.mask == nullptr || L.mask[a])) { reset_drone(d, C); ssel[le] = 1; }   // benign race: all write 1
+                    rs = valid && (L.mask == nullptr || L.mask[a]);
+                    if (WL) sel = (__ballot_sync(0xffffffffu, rs) & env_lanes) != 0;
+                    else { __syncthreads(); if (rs) ssel[le] = 1; __syncthreads(); sel = valid && ssel[le]; }   // benign race: all write 1
                 } else if (L.mode == MODE_OBSERVE) {
-                    __syncthreads();
-                    if (valid && k == 0) ssel[le] = (L.mask == nullptr || L.mask[env]) ? 1 : 0;
+                    sel = valid && (L.mask == nullptr || L.mask[env]);
                 } else if (L.mode == MODE_AUTORESET) {
                     if (valid) { st_done = L.done_in[a] != 0; st_fin = L.finish_in[a] != 0; }
                 }
                 if (do_auto) {   // trainer reset policy, multi_ppo.py:221-281
-                    __syncthreads();
-                    if (valid) {
-                        ep_len += 1;
-                        atomicOr(&senv[le], (st_done ? 1 : 0) | (st_fin ? 2 : 4) | (ep_len > L.max_ep_len ? 8 : 0));
+                    if (valid) ep_len += 1;
+                    const bool over = valid && ep_len > L.max_ep_len;
+                    int bits;
+                    if (WL) {
+                        const unsigned bd = __ballot_sync(0xffffffffu, valid && st_done), bf = __ballot_sync(0xffffffffu, valid && st_fin);
+                        const unsigned bn = __ballot_sync(0xffffffffu, valid && !st_fin), bo = __ballot_sync(0xffffffffu, over);
+                        bits = ((bd & env_lanes) ? 1 : 0) | ((bf & env_lanes) ? 2 : 0) | ((bn & env_lanes) ? 4 : 0) | ((bo & env_lanes) ? 8 : 0);
+                    } else {
+                        __syncthreads();
+                        if (valid) atomicOr(&senv[le], (st_done ? 1 : 0) | (st_fin ? 2 : 4) | (over ? 8 : 0));
+                        __syncthreads();
+                        bits = valid ? senv[le] : 0;
                     }
-                    __syncthreads();
                     if (valid) {
-                        const int bits = senv[le];
                         const bool all_fin = !(bits & 4), terminal = (bits & 2) || (bits & 8);
-                        bool rs = false, cut = false, ob = false;
-                        if (bits & 1) { if (st_done) { rs = true; ep_len = 0; } ob = true; }                   // :230-242
-                        if (L.epoch_ended || all_fin) { rs = true; ep_len = 0; cut = true; ob = true; }        // :244-264
-                        else if (terminal) { if (st_fin || ep_len > L.max_ep_len) { rs = true; ep_len = 0; } cut = true; ob = true; }   // :266-281
-                        if (rs) reset_drone(d, C);
-                        if (ob) ssel[le] = 1;
+                        bool cut = false;
+                        if (bits & 1) { if (st_done) { rs = true; ep_len = 0; } sel = true; }                   // :230-242
+                        if (L.epoch_ended || all_fin) { rs = true; ep_len = 0; cut = true; sel = true; }        // :244-264
+                        else if (terminal) { if (st_fin || ep_len > L.max_ep_len) { rs = true; ep_len = 0; } cut = true; sel = true; }   // :266-281
                         if (L.reset_mask) L.reset_mask[o] = rs;
                         if (L.path_cut) L.path_cut[o] = cut;
                     }
                 } else if (is_step) {
                     break;       // plain step: nothing to re-observe (uniform over the CTA)
                 }
-                __syncthreads();
-                active = valid && ssel[le] && (L.obs || L.count || L.nbr);
+                if (rs) reset_drone(d, C);
+                active = valid && sel && (L.obs || L.count || L.nbr);
+                RG_MARK(RG_AUTORESET);
             }
             // -------------------------------------------------------- publish my state, then read the others'
-            if (ph != PH_OBS) __syncthreads();   // (PH_OBS: the barrier above already separates it from phase B's reads)
+            if (WL && is_step && ph == PH_B && lane == 0) bulk_wait_all();   // my warp's cleared rows have landed: rows may now be scattered
+            ENV_SYNC();   // everybody is done reading the previous phase's columns
             if (valid) {
                 sx[0 * threads + tid] = d.px; sx[1 * threads + tid] = d.py; sx[2 * threads + tid] = d.pz;
                 sx[3 * threads + tid] = d.vx; sx[4 * threads + tid] = d.vy; sx[5 * threads + tid] = d.vz;
             }
-            __syncthreads();
+            ENV_SYNC();
+            RG_MARK(RG_SYNC);
             if (!active) continue;
 
             // drone.dronestate (drone.py:254-263): desired velocity + deviation, side effect on max_deviation
@@ -150,39 +228,53 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 128 ? UAISA_MINB128 : 1)) uaisa
             {
                 const double *cur = C.wp + 3 * d.i;
                 cal_des_vel(P, d.px, d.py, d.pz, cur, d0, d1, d2);
-                dev = deviation(cur - 3, cur, d.px, d.py, d.pz);
+                dev = deviation(cur - 3, C.seg + 4 * d.i, d.px, d.py, d.pz);
                 if (dev > d.max_dev) d.max_dev = dev;
             }
+            RG_MARK(RG_DRONESTATE);
             // pairwise pass over the drones of my env (rvo_inter.py:20-83)
             bool vo_any = false, col = false; double tmin = CUDART_INF;
             TopList<MAXR> top; top.clear();
             {
                 double bx = (ph == PH_OBS) ? 0.0 : ax, by = (ph == PH_OBS) ? 0.0 : ay, bz = (ph == PH_OBS) ? 0.0 : az;
-                if (np_norm3(bx, by, bz) < 1e-5) { bx = by = bz = 0.0; }   // rvo_inter.py:118-119
-                for (int j = 0; j < N; j++) {
-                    if (j == k) continue;
-                    double tt, ah, md, iet;
-                    const int bits = vo_pair(P, d.px, d.py, d.pz, d.vx, d.vy, d.vz, C.radius, C.prio, sx + lbase + j, threads,
-                                             bx, by, bz, tt, ah, md, iet);
-                    n_rng += (bits & PB_EVAL) ? 1u : 0u; n_cone += (bits & PB_FULL) ? 1u : 0u;
-                    if (bits & PB_VO) {
-                        vo_any = true; if (tt < tmin) tmin = tt;
-                        if (ph != PH_A) top.insert(cap, iet, md, j, (int)ah);
+                if (np_dot3(bx, by, bz, bx, by, bz) < 1e-10 * (1.0 - 1e-14)) { bx = by = bz = 0.0; }   // norm(a) < 1e-5, rvo_inter.py:118-119
+                // Stage 1 runs over a chunk of up to 32 neighbours with no divergent work and yields a mask of the
+                // pairs whose cone must be evaluated; stage 2 walks that mask (rvo_inter.py:29,67 map both).
+                for (int jb = 0; jb < N; jb += 32) {
+                    unsigned cand = 0;
+                    const int jn = min(32, N - jb);
+#pragma unroll 4
+                    for (int jj = 0; jj < jn; jj++) {
+                        const int j = jb + jj;
+                        const int bits = (j == k) ? 0 : pair_gate(P, d.px, d.py, d.pz, d.vx, d.vy, d.vz, C.radius, sx + lbase + j, threads);
+                        n_rng += (bits & PB_EVAL) ? 1u : 0u;
+                        col |= (bits & PB_COL) != 0;
+                        cand |= (bits & PB_FULL) ? (1u << jj) : 0u;
                     }
-                    if (bits & PB_COL) col = true;
+                    n_cone += __popc(cand);
+                    while (cand) {
+                        const int jj = __ffs(cand) - 1; cand &= cand - 1;
+                        const int j = jb + jj;
+                        double tt, ah, md, iet;
+                        if (pair_cone(P, d.px, d.py, d.pz, d.vx, d.vy, d.vz, C.radius, C.prio, sx + lbase + j, threads, bx, by, bz, tt, ah, md, iet)) {
+                            vo_any = true; if (tt < tmin) tmin = tt;
+                            if (ph != PH_A) top.insert(cap, iet, md, j, (int)ah);
+                        }
+                    }
                 }
             }
-
+            RG_MARK(RG_PAIRS);
             if (ph == PH_A) {
                 // ---------------------------------------------------- ir_gym.rvo_reward_cal (ir_gym.py:64-133)
-                const double vnum = 0.2 * np_norm3(ax, ay, az), vden = np_norm3(d0, d1, d2);
+                const double vnum = 0.2 * fast_sqrt(np_dot3(ax, ay, az, ax, ay, az)), vden = fast_sqrt(np_dot3(d0, d1, d2, d0, d1, d2));
                 const double vel_pen = (vden != 0.0) ? fast_div(vnum, vden) : vnum / vden;   // IEEE inf/nan when des = 0 (ir_gym.py:88)
                 const double ap_ = angle_punish(d0, d1, d2, ax, ay, az);
                 double safety = 0;
                 if (vo_any) { double urg = 0; if (tmin < 2) urg = -8.0 * exp(-tmin / 0.5); safety = -2.5 + urg; }
                 rA = np_round3(ap_ + vel_pen + safety);
+                RG_MARK(RG_REWARD_A);
                 // ---------------------------------------------------- MOVE: drone.move_forward (drone.py:96-129,431-490)
-                const double speed = np_norm3(d.vx, d.vy, d.vz);
+                const double speed = fast_sqrt(np_dot3(d.vx, d.vy, d.vz, d.vx, d.vy, d.vz));
                 const double acc = np_clip(ax * P.max_acc, -P.max_acc, P.max_acc);
                 const double dyaw = np_clip(ay * P.max_ang, -P.max_ang, P.max_ang), dpitch = np_clip(az * P.max_ang, -P.max_ang, P.max_ang);
                 double nv = speed + acc * 1.0; nv = (0.0 > nv) ? 0.0 : nv;
@@ -192,13 +284,14 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 128 ? UAISA_MINB128 : 1)) uaisa
                 double nvx = nv * cp * cy, nvy = nv * cp * sy, nvz = nv * sp;
                 if (d.flags & FLAG_DEST) { nvx = nvy = nvz = 0.0; }   // stop is always on (env_base.py:142)
                 const double nx = d.px + nvx * P.dt, ny = d.py + nvy * P.dt, nz = d.pz + nvz * P.dt;
-                d.real_len = d.real_len + np_norm3(nx - d.px, ny - d.py, nz - d.pz);
+                { const double ux = nx - d.px, uy = ny - d.py, uz = nz - d.pz; d.real_len = d.real_len + fast_sqrt(np_dot3(ux, uy, uz, ux, uy, uz)); }
                 d.px = nx; d.py = ny; d.pz = nz; d.vx = nvx; d.vy = nvy; d.vz = nvz;
                 if (within_goal(P, d.px, d.py, d.pz, C.wp + 3 * d.i)) {           // drone.py:116-129
                     const bool at_dest = within_goal(P, d.px, d.py, d.pz, C.wp + 3 * (C.n - 1));
                     if (at_dest) { extra_len_new = d.real_len - C.route_len; extra_len_dirty = true; }
                     if (!at_dest && d.i < C.n - 1) { d.i += 1; d.flags &= ~FLAG_ARRIVE; }
                 }
+                RG_MARK(RG_MOVE);
                 continue;
             }
 
@@ -255,6 +348,7 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 128 ? UAISA_MINB128 : 1)) uaisa
                 n_bad += bad ? 1u : 0u;
                 if (L.count) L.count[o] = (uint8_t)top.cnt;
             }
+            RG_MARK(RG_OBSROW);
             if (ph == PH_OBS) { d.max_dev = rt(d.max_dev); continue; }
 
             // ------------------------------------------------------------ phase B only: flags, collisions, reward
@@ -265,6 +359,7 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 128 ? UAISA_MINB128 : 1)) uaisa
                 if (at_dest) { extra_len_new = d.real_len - C.route_len; extra_len_dirty = true; }
                 if (at_dest && !(d.flags & FLAG_DEST)) { d.flags |= FLAG_DEST; dest_now = true; }
             }
+            RG_MARK(RG_B_FLAGS);
             for (int m = 0; m < nb; m++) {   // rvo_inter.py:99-105 filter, :198-209 check
                 const double bx = __ldg(bld + 4 * m), by = __ldg(bld + 4 * m + 1), bh = __ldg(bld + 4 * m + 2), br = __ldg(bld + 4 * m + 3);
                 if (bh > d.pz - P.bld_zgate && d.pz <= bh) {
@@ -276,6 +371,7 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 128 ? UAISA_MINB128 : 1)) uaisa
                 const double mapx = __ldg(P.map + 3 * scn), mapy = __ldg(P.map + 3 * scn + 1), mapz = __ldg(P.map + 3 * scn + 2);
                 if (d.px < 0 || d.px > mapx || d.py < 0 || d.py > mapy || d.pz < 0 || d.pz > mapz) col = true;
             }
+            RG_MARK(RG_B_COL);
             double rB;   // ir_gym.mov_reward (ir_gym.py:256-311)
             if (col) rB = -50.0;
             else {
@@ -288,6 +384,7 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 128 ? UAISA_MINB128 : 1)) uaisa
                 if (exlen > 0) { ex_pen = -0.3 * log(exlen + 1.0 + 1e-6); if (ex_pen < -6.0 || ex_pen != ex_pen) ex_pen = -6.0; }
                 rB = np_round3(rew + dev_pen + ex_pen);
             }
+            RG_MARK(RG_B_REWARD);
             st_done = col; st_fin = (d.flags & FLAG_DEST) != 0;
             if (L.reward) L.reward[o] = (float)(rA + rB);
             if (L.done) L.done[o] = col;
@@ -296,8 +393,11 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 128 ? UAISA_MINB128 : 1)) uaisa
             // what the next step will load from HBM
             d.px = rt(d.px); d.py = rt(d.py); d.pz = rt(d.pz); d.vx = rt(d.vx); d.vy = rt(d.vy); d.vz = rt(d.vz);
             d.yaw = rt(d.yaw); d.pitch = rt(d.pitch); d.real_len = rt(d.real_len); d.max_dev = rt(d.max_dev);
+            RG_MARK(RG_B_OUT);
         }
-        __syncthreads();   // the next step republishes sx and re-arms senv/ssel
+        RG_MARK(RG_TAIL_B);
+        ENV_SYNC();   // the next step republishes sx and re-arms senv/ssel
+        RG_MARK(RG_SYNC);
     }
 
     if (valid) {
@@ -308,6 +408,8 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 128 ? UAISA_MINB128 : 1)) uaisa
         if (extra_len_dirty) P.extra_len[a] = (float)extra_len_new;
         if (do_auto) P.ep_len[a] = ep_len;
     }
+    RG_MARK(RG_EPILOGUE);
+    RG_FLUSH();
     const bool any_bad = __any_sync(0xffffffffu, n_bad != 0);
     if (P.count_pairs || any_bad) {
         for (int off = 16; off > 0; off >>= 1) {
@@ -334,12 +436,10 @@ __global__ void uaisa_cal_des_kernel(const __grid_constant__ Params P, float *de
     des[3 * a] = (float)d0; des[3 * a + 1] = (float)d1; des[3 * a + 2] = (float)d2;
 }
 
-template __global__ void uaisa_env_kernel<4, 128>(const __grid_constant__ Params, const __grid_constant__ Launch);
-template __global__ void uaisa_env_kernel<10, 128>(const __grid_constant__ Params, const __grid_constant__ Launch);
-template __global__ void uaisa_env_kernel<16, 128>(const __grid_constant__ Params, const __grid_constant__ Launch);
-template __global__ void uaisa_env_kernel<4, 256>(const __grid_constant__ Params, const __grid_constant__ Launch);
-template __global__ void uaisa_env_kernel<10, 256>(const __grid_constant__ Params, const __grid_constant__ Launch);
-template __global__ void uaisa_env_kernel<16, 256>(const __grid_constant__ Params, const __grid_constant__ Launch);
-template __global__ void uaisa_env_kernel<16, 1024>(const __grid_constant__ Params, const __grid_constant__ Launch);
+#define UAISA_INST(R, T, W) template __global__ void uaisa_env_kernel<R, T, W>(const __grid_constant__ Params, const __grid_constant__ Launch);
+UAISA_INST(4, 128, true) UAISA_INST(10, 128, true) UAISA_INST(16, 128, true)
+UAISA_INST(4, 128, false) UAISA_INST(10, 128, false) UAISA_INST(16, 128, false)
+UAISA_INST(4, 256, false) UAISA_INST(10, 256, false) UAISA_INST(16, 256, false) UAISA_INST(16, 1024, false)
+#undef UAISA_INST
 
 }  // namespace uaisa

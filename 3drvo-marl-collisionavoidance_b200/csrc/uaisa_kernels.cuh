@@ -40,7 +40,7 @@ struct Params {
     double goal_thr, max_acc, max_ang, dt, vel_max, nbr_range, bld_range, bld_zgate, ctime, delta_t, exp_radius;
     double goal2_lo, goal2_hi, nbr2_lo, nbr2_hi;   // T^2*(1 -+ 1e-14) guard bands for sqrt(x) <= T (host-computed)
     // scenario constants (device, fp64, shared by envs -> L2/L1 resident)
-    const double *wp; const int *npts; const double *route_len; const double *radius; const double *prio;
+    const double *wp; const double *seg; const int *npts; const double *route_len; const double *radius; const double *prio;
     const double *bld; const int *nbld; const double *map; const int *env2scn;
     // mutable state (device, fp32 SoA)
     float4 *pos_yaw; float4 *vel_pitch; float *real_len; float *max_dev; float *extra_len; int *wpf; int *ep_len;
@@ -86,6 +86,21 @@ __device__ __forceinline__ double fast_rcp(double b) {
 __device__ __forceinline__ double fast_div(double a, double b) {
     double y = fast_rcp(b), q = a * y, r = fma(-b, q, a);
     return fma(r, y, q);
+}
+// 1/sqrt(x) and sqrt(x) for normal x > 0 without libdevice's special-case path: MUFU.RSQ64H seed (2^-22),
+// two Newton steps; sqrt adds a Markstein correction (correctly rounded except rare last-bit cases).
+__device__ __forceinline__ double fast_rsqrt(double x) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double e = fma(-(x * y), y, 1.0); y = fma(0.5 * y, e, y);
+    e = fma(-(x * y), y, 1.0); y = fma(0.5 * y, e, y);
+    return y;
+}
+__device__ __forceinline__ double fast_sqrt(double x) {   // x >= 0 (0 -> 0)
+    const double y = fast_rsqrt(x);
+    double s = x * y;
+    s = fma(fma(-s, s, x), 0.5 * y, s);
+    return x > 0.0 ? s : 0.0;
 }
 // np.round(x, 2) / np.round(x, 3) = rint(x*10^k)/10^k, bit-exact for finite x
 __device__ __forceinline__ double np_round2(double x) { double k = rint(x * 100.0); return isfinite(k) ? div_const(k, 100.0, 0.01) : k; }
@@ -144,6 +159,7 @@ struct Drone {
 
 struct Consts {   // per-drone scenario constants
     const double *wp;   // this drone's waypoint list [W][3]
+    const double *seg;  // [W][4]: unit direction and length of the segment wp[i-1] -> wp[i]
     double radius, prio, route_len;
     int n;              // n_points
 };
@@ -156,38 +172,29 @@ __device__ __forceinline__ bool within_goal(const Params &P, double px, double p
     return sqrt_le_band(np_dot3(fx, fy, fz, fx, fy, fz), P.goal_thr, P.goal2_lo, P.goal2_hi);   // norm(p - q) <= 0.4, drone.py:172-192
 }
 
-// drone.calculate_deviation (drone.py:366-406)
-__device__ __forceinline__ double deviation(const double *st, const double *en, double x0, double y0, double z0) {
-    double x1, y1, z1, x2, y2, z2; load3(st, x1, y1, z1); load3(en, x2, y2, z2);
-    double dx = x2 - x1, dy = y2 - y1, dz = z2 - z1;
-    double mag = sqrt(dx * dx + dy * dy + dz * dz);
+// drone.calculate_deviation (drone.py:366-406).  `st` = previous waypoint; `sg` = (dx/|d|, dy/|d|, dz/|d|, |d|) of
+// the segment previous -> current, computed once on the host with the reference's own operations.
+__device__ __forceinline__ double deviation(const double *st, const double *sg, double x0, double y0, double z0) {
+    const double mag = __ldg(sg + 3);
     if (mag == 0.0) return 0.0;
-    const double im = fast_rcp(mag);
-    double dxh = dx * im, dyh = dy * im, dzh = dz * im;
-    double px = x0 - x1, py = y0 - y1, pz = z0 - z1;
-    double t = px * dxh + py * dyh + pz * dzh;
-    double qx = x1 + t * dxh, qy = y1 + t * dyh, qz = z1 + t * dzh;
-    double ex = x0 - qx, ey = y0 - qy, ez = z0 - qz;
-    return sqrt(ex * ex + ey * ey + ez * ez);
+    double x1, y1, z1, dxh, dyh, dzh; load3(st, x1, y1, z1); load3(sg, dxh, dyh, dzh);
+    const double px = x0 - x1, py = y0 - y1, pz = z0 - z1;
+    const double t = px * dxh + py * dyh + pz * dzh;
+    const double qx = x1 + t * dxh, qy = y1 + t * dyh, qz = z1 + t * dzh;
+    const double ex = x0 - qx, ey = y0 - qy, ez = z0 - qz;
+    return fast_sqrt(ex * ex + ey * ey + ez * ez);
 }
 
-// drone.cal_des_vel (drone.py:199-210, 319-352)
+// drone.cal_des_vel (drone.py:199-210, 319-352).  cos(atan2(fy,fx))*cos(atan2(fz,h)) == fx/|f| etc. up to a few
+// ulp (<< the 1e-3 rounding quantum); h == 0 gives (0,0,+-1) on both routes.
 __device__ __forceinline__ void cal_des_vel(const Params &P, double px, double py, double pz, const double *cur,
                                             double &d0, double &d1, double &d2) {
     double cx, cy, cz; load3(cur, cx, cy, cz);
-    double fx = cx - px, fy = cy - py, fz = cz - pz;
-    double dis = np_norm3(fx, fy, fz);
-    if (dis > P.goal_thr) {
-#ifdef UAISA_LIBM_DES
-        double az = atan2(fy, fx), el = atan2(fz, np_norm2(fx, fy));
-        double sa, ca, se, ce; sincos(az, &sa, &ca); sincos(el, &se, &ce);
-        d0 = np_round3(P.vel_max * (ca * ce)); d1 = np_round3(P.vel_max * (sa * ce)); d2 = np_round3(P.vel_max * se);
-#else
-        // cos(atan2(fy,fx))*cos(atan2(fz,h)) == fx/dis etc. up to a few ulp (<<1e-3 rounding quantum);
-        // h == 0 gives (0,0,+-1) on both routes.
-        const double id = fast_rcp(dis);
-        d0 = np_round3(P.vel_max * (fx * id)); d1 = np_round3(P.vel_max * (fy * id)); d2 = np_round3(P.vel_max * (fz * id));
-#endif
+    const double fx = cx - px, fy = cy - py, fz = cz - pz;
+    const double s2 = np_dot3(fx, fy, fz, fx, fy, fz);
+    if (!sqrt_le_band(s2, P.goal_thr, P.goal2_lo, P.goal2_hi) && s2 == s2) {      // dis > goal_threshold
+        const double id = P.vel_max * fast_rsqrt(s2);
+        d0 = np_round3(fx * id); d1 = np_round3(fy * id); d2 = np_round3(fz * id);
     } else {
         d0 = d1 = d2 = 0.0;
     }
@@ -212,27 +219,36 @@ __device__ __forceinline__ double cal_vo_exp_tim(double rx, double ry, double rz
 
 enum PairBits : int { PB_EVAL = 1, PB_COL = 2, PB_FULL = 4, PB_VO = 8 };
 
-// rvo_inter.preprocess neighbour test (rvo_inter.py:89-97) + config_vo_circle2 (rvo_inter.py:116-196).
-// `so` points at the other drone's column of the exchange array (stride `st` doubles between the 8 fields
-// px py pz vx vy vz r prio); fields are loaded only once they are needed.
-// (ax,ay,az) is the action with the |a|<1e-5 -> 0 substitution already applied.
-// t_out / alpha_h are valid when PB_FULL is set; md / iet only when PB_VO is set.
-__device__ __forceinline__ int vo_pair(const Params &P, double x, double y, double z, double vx, double vy, double vz,
-                                       double r, double pra, const double *so, int st, double ax, double ay, double az,
-                                       double &t_out, double &alpha_h, double &md, double &iet) {
-    const double mx = so[0], my = so[st], mz = so[2 * st];
-    if (x == mx && y == my && z == mz) return 0;
+// Stage 1 of a pair (branch-free up to the rare exact-sqrt fallbacks): rvo_inter.preprocess neighbour test
+// (rvo_inter.py:89-97), the collision test and the "moving away" gate of config_vo_circle2
+// (rvo_inter.py:131-161).  `so` = the other drone's column of the exchange array (stride `st` doubles
+// between the fields px py pz vx vy vz r prio).  Returns PB_EVAL if in range, |PB_COL on collision,
+// |PB_FULL if the cone has to be evaluated (stage 2).
+__device__ __forceinline__ int pair_gate(const Params &P, double x, double y, double z, double vx, double vy, double vz,
+                                         double r, const double *so, int st) {
+    const double mx = so[0], my = so[st], mz = so[2 * st], mr = so[6 * st];
     const double rel_x = mx - x, rel_y = my - y, rel_z = mz - z;      // == -(self - other), squares identical
     const double s2 = np_dot3(rel_x, rel_y, rel_z, rel_x, rel_y, rel_z);   // np.linalg.norm argument
-    if (!sqrt_le_band(s2, P.nbr_range, P.nbr2_lo, P.nbr2_hi)) return 0;
+    const bool same = (x == mx) & (y == my) & (z == mz);              // how the reference excludes "self"
+    if (same || !sqrt_le_band(s2, P.nbr_range, P.nbr2_lo, P.nbr2_hi)) return 0;
     const double d2 = rel_y * rel_y + rel_x * rel_x + rel_z * rel_z;      // dis_mr^2, rvo_inter.py:135
-    const double mr = so[6 * st];
-    const double R = r + mr;
-    const bool col = P.env_train ? sqrt_le(d2, R) : sqrt_le(d2, r - P.exp_radius + mr);
-    if (col) return PB_EVAL | PB_COL;
+    const double Rc = P.env_train ? r + mr : r - P.exp_radius + mr;
+    if (sqrt_le(d2, Rc)) return PB_EVAL | PB_COL;
     const double dotp = vx * rel_x + vy * rel_y + vz * rel_z;
-    if (dotp <= 0.0) return PB_EVAL;
+    return (dotp <= 0.0) ? PB_EVAL : (PB_EVAL | PB_FULL);
+}
+
+// Stage 2: the cone itself (rvo_inter.py:165-196, vel_obs3D.py:8-66,145-182).  (ax,ay,az) is the action with
+// the |a|<1e-5 -> 0 substitution already applied.  Returns PB_VO if the chosen velocity is inside the cone
+// with an expected collision time below the threshold; then t_out, alpha_h, md, iet are valid.
+__device__ __forceinline__ int pair_cone(const Params &P, double x, double y, double z, double vx, double vy, double vz,
+                                         double r, double pra, const double *so, int st, double ax, double ay, double az,
+                                         double &t_out, double &alpha_h, double &md, double &iet) {
+    const double mx = so[0], my = so[st], mz = so[2 * st], mr = so[6 * st];
     const double mvx = so[3 * st], mvy = so[4 * st], mvz = so[5 * st], prb = so[7 * st];
+    const double rel_x = mx - x, rel_y = my - y, rel_z = mz - z;
+    const double s2 = np_dot3(rel_x, rel_y, rel_z, rel_x, rel_y, rel_z);
+    const double R = r + mr;
     const double nab = sqrt(s2);
     alpha_h = py_round2_hundredths(asin(fast_div(R, nab)));                // get_alpha, vel_obs3D.py:8-17
     const double pr = fast_div(pra, pra + prb);                            // get_PAA, vel_obs3D.py:19-32
@@ -241,19 +257,15 @@ __device__ __forceinline__ int vo_pair(const Params &P, double x, double y, doub
     const double AB = nab * np_norm3(Bx, By, Bz);
     const double cosang = (AB != 0.0) ? fast_div(np_dot3(rel_x, rel_y, rel_z, Bx, By, Bz), AB) : 0.0;
     const double beta_h = rint(acos(cosang) * 100.0);      // get_beta: unclamped arccos, numpy rounding
-    int bits = PB_EVAL | PB_FULL;
-    double exp_time = CUDART_INF;
-    if (alpha_h > beta_h) {                                 // alpha > beta on the rounded values; NaN beta -> outside
-        const double rel_vx = 2.0 * ax - mvx - vx, rel_vy = 2.0 * ay - mvy - vy, rel_vz = 2.0 * az - mvz - vz;
-        exp_time = cal_vo_exp_tim(rel_x, rel_y, rel_z, rel_vx, rel_vy, rel_vz, r, mr);
-        if (exp_time < P.ctime) {
-            bits |= PB_VO;
-            md = sqrt(d2) - mr;
-            iet = fast_div(1.0, exp_time + 0.2);
-        } else exp_time = CUDART_INF;
-    }
+    if (!(alpha_h > beta_h)) return 0;                     // alpha > beta on the rounded values; NaN beta -> outside
+    const double rel_vx = 2.0 * ax - mvx - vx, rel_vy = 2.0 * ay - mvy - vy, rel_vz = 2.0 * az - mvz - vz;
+    const double exp_time = cal_vo_exp_tim(rel_x, rel_y, rel_z, rel_vx, rel_vy, rel_vz, r, mr);
+    if (!(exp_time < P.ctime)) return 0;
+    const double d2 = rel_y * rel_y + rel_x * rel_x + rel_z * rel_z;
     t_out = exp_time;
-    return bits;
+    md = sqrt(d2) - mr;
+    iet = fast_div(1.0, exp_time + 0.2);
+    return PB_VO;
 }
 
 // ---- top-nm neighbour list (rvo_inter.py:50-59) ------------------------------------------------------
@@ -289,9 +301,9 @@ struct TopList {
 // (thresholds found by bisection against the libm the reference calls).  NaN -> -4 like the reference's else-branch.
 __device__ __forceinline__ double angle_punish(double A0, double A1, double A2, double B0, double B1, double B2) {
     const double eps = 1e-8;
-    const double magA = sqrt(A0 * A0 + A1 * A1 + A2 * A2 + eps), magB = sqrt(B0 * B0 + B1 * B1 + B2 * B2 + eps);
+    const double mA2 = A0 * A0 + A1 * A1 + A2 * A2 + eps, mB2 = B0 * B0 + B1 * B1 + B2 * B2 + eps;
     const double dp = A0 * B0 + A1 * B1 + A2 * B2;
-    const double c = np_clip(fast_div(dp, magA * magB), -1.0 + eps, 1.0 - eps);
+    const double c = np_clip(dp * fast_rsqrt(mA2 * mB2), -1.0 + eps, 1.0 - eps);   // dp / (|A| |B|) to ~2 ulp
     // smallest doubles c with glibc acos(c) < pi/18, pi/6, pi/3, pi/2 (bisection over doubles)
     if (c >= 0x1.f838b8c811c18p-1) return 3.0;
     if (c >= 0x1.bb67ae8584cabp-1) return 1.0;
@@ -300,7 +312,7 @@ __device__ __forceinline__ double angle_punish(double A0, double A1, double A2, 
     return -4.0;
 }
 
-template <int MAXR, int MAXT>
+template <int MAXR, int MAXT, bool WL>
 __global__ void uaisa_env_kernel(const __grid_constant__ Params P, const __grid_constant__ Launch L);
 __global__ void uaisa_cal_des_kernel(const __grid_constant__ Params P, float *des);
 

@@ -170,6 +170,14 @@ class VecMdin:
         _capi.check(self.L.uaisa_get_counters(self.h, C.byref(a), C.byref(b), C.byref(c), self._stream()))
         return {"in_range_pairs": a.value, "cone_evals": b.value, "nonfinite_obs": c.value}
 
+    REGIONS = ("prologue", "fill", "sync", "dronestate", "pairs", "reward_a", "move", "obsrow", "tail_b", "autoreset", "epilogue", "b_flags", "b_col", "b_reward", "b_out", "act")
+
+    def region_clocks(self) -> dict:
+        """Per-region SM-cycle sums (profiling builds only: -DUAISA_REGION_CLOCKS)."""
+        buf = (C.c_int64 * 16)()
+        _capi.check(self.L.uaisa_get_region_clocks(self.h, buf, self._stream()))
+        return {n: int(buf[i]) for i, n in enumerate(self.REGIONS)}
+
     @property
     def launch_count(self) -> int:
         return int(self.L.uaisa_launch_count(self.h))

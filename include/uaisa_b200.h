@@ -138,6 +138,9 @@ int uaisa_indicators(UaisaHandle *h, float *max_dev, float *extra_len, void *str
 int uaisa_get_counters(UaisaHandle *h, int64_t *in_range_pairs, int64_t *cone_evals, int64_t *nonfinite_obs, void *stream);
 /* kernel launches issued through this handle so far (bench.py's gpu_launches) */
 int64_t uaisa_launch_count(const UaisaHandle *h);
+/* Profiling aid: per-region SM-cycle sums (summed over warps) since the last call; all zero unless the
+ * library was built with -DUAISA_REGION_CLOCKS.  out16 is HOST; synchronises `stream`. */
+int uaisa_get_region_clocks(UaisaHandle *h, int64_t *out16, void *stream);
 
 /* Host-buffer convenience used for the end-to-end number: H2D(action) -> step [-> trainer auto-reset
  * + re-observe, as uaisa_rollout's auto_reset] -> D2H(outputs); all pointers HOST (pinned for full

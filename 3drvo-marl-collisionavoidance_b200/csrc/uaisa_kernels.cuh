@@ -109,10 +109,11 @@ __device__ __forceinline__ double np_round3(double x) { double k = rint(x * 1000
 // (k/100 is never within 2^-30 of an fp32 rounding tie unless it is exact; checked exhaustively, ibid.)
 __device__ __forceinline__ float np_round2_f32(double x) { return (float)(rint(x * 100.0) * 0.01); }
 // sqrt(x) <= T without the square root unless x is within 1e-14 of T^2 (NaN -> false)
+static __device__ __noinline__ bool sqrt_le_exact(double x, double T) { return sqrt(x) <= T; }   // rare: kept out of line (i-cache)
 __device__ __forceinline__ bool sqrt_le_band(double x, double T, double lo, double hi) {
     const bool below = x < lo;
     if (below || x > hi) return below;
-    return sqrt(x) <= T;
+    return sqrt_le_exact(x, T);
 }
 __device__ __forceinline__ bool sqrt_le(double x, double T) {
     const double T2 = T * T;

@@ -62,7 +62,7 @@ __device__ __forceinline__ double np_dot3(double a0, double a1, double a2, doubl
 }
 __device__ __forceinline__ double np_norm3(double a0, double a1, double a2) { return sqrt(np_dot3(a0, a1, a2, a0, a1, a2)); }
 __device__ __forceinline__ double np_norm2(double a0, double a1) { return sqrt(fma(a1, a1, a0 * a0)); }
-__device__ __forceinline__ double np_clip(double x, double lo, double hi) { return fmin(fmax(x, lo), hi); }
+__device__ __forceinline__ double np_clip(double x, double lo, double hi) { return (x != x) ? x : fmin(fmax(x, lo), hi); }   // np.clip propagates NaN
 
 // ---- division without the libdevice slow path ---------------------------------------------------------
 // a / c for a compile-time constant c with y = RN(1/c): q0 = a*y, r = a - c*q0 (exact in the FMA),

@@ -71,7 +71,7 @@ void uo_default_config(UoConfig *c) {
 static inline double np_dot3(const double *a, const double *b) { return fma(a[2], b[2], fma(a[1], b[1], a[0] * b[0])); }
 static inline double np_norm3(const double *a) { return sqrt(np_dot3(a, a)); }
 static inline double np_norm2(const double *a) { return sqrt(fma(a[1], a[1], a[0] * a[0])); }
-static inline double np_clip(double x, double lo, double hi) { return fmin(fmax(x, lo), hi); }
+static inline double np_clip(double x, double lo, double hi) { return (x != x) ? x : fmin(fmax(x, lo), hi); } /* np.clip propagates NaN */
 
 double uo_npround(double x, int nd) {
     static const double p10[4] = {1.0, 10.0, 100.0, 1000.0};

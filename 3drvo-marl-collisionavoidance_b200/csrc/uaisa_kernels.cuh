@@ -250,19 +250,38 @@ __device__ __forceinline__ int pair_cone(const Params &P, double x, double y, do
     const double rel_x = mx - x, rel_y = my - y, rel_z = mz - z;
     const double s2 = np_dot3(rel_x, rel_y, rel_z, rel_x, rel_y, rel_z);
     const double R = r + mr;
-    const double nab = sqrt(s2);
-    alpha_h = py_round2_hundredths(asin(fast_div(R, nab)));                // get_alpha, vel_obs3D.py:8-17
     const double pr = fast_div(pra, pra + prb);                            // get_PAA, vel_obs3D.py:19-32
     const double PAAx = pr * (2.0 * x + (vx + mvx) * 1.0), PAAy = pr * (2.0 * y + (vy + mvy) * 1.0), PAAz = pr * (2.0 * z + (vz + mvz) * 1.0);
     const double Bx = x + 2.0 * ax * P.delta_t - PAAx, By = y + 2.0 * ay * P.delta_t - PAAy, Bz = z + 2.0 * az * P.delta_t - PAAz;
-    const double AB = nab * np_norm3(Bx, By, Bz);
-    const double cosang = (AB != 0.0) ? fast_div(np_dot3(rel_x, rel_y, rel_z, Bx, By, Bz), AB) : 0.0;
-    const double beta_h = rint(acos(cosang) * 100.0);      // get_beta: unclamped arccos, numpy rounding
-    if (!(alpha_h > beta_h)) return 0;                     // alpha > beta on the rounded values; NaN beta -> outside
+    const double b2 = np_dot3(Bx, By, Bz, Bx, By, Bz), dab = np_dot3(rel_x, rel_y, rel_z, Bx, By, Bz);
+    // Trig-free screen.  inside <=> round(100 alpha) > round(100 beta) with alpha = asin(R/|rel|), beta = acos(c):
+    // beta > alpha + 0.02 rad is certainly outside and beta < alpha - 0.02 certainly inside (each rounding moves a
+    // value by <= 0.005 rad), and both are decided on cosines: cos(alpha -+ 0.02) = cos a cos .02 +- sin a sin .02.
+    // Only the +-0.02 band around alpha (and the degenerate / near-collinear cases, where the reference's
+    // unclamped arccos may return NaN) go through asin/acos.
+    bool need_exact = true, inside = false;
+    alpha_h = CUDART_NAN;
+    if (b2 > 0.0) {
+        const double inab = fast_rsqrt(s2), sin_a = R * inab, c_f = dab * inab * fast_rsqrt(b2);
+        const double cos_a = fast_sqrt(fma(-sin_a, sin_a, 1.0));
+        const double C02 = 0.99980000666657776, S02 = 0.019998666693333084;   // cos(0.02), sin(0.02)
+        if (c_f < cos_a * C02 - sin_a * S02 - 1e-9) return 0;                                   // beta > alpha + 0.02
+        if (sin_a > 0.03 && c_f > cos_a * C02 + sin_a * S02 + 1e-9 && c_f < 1.0 - 1e-9) { need_exact = false; inside = true; }
+    }
+    if (need_exact) {
+        const double nab = sqrt(s2);
+        alpha_h = py_round2_hundredths(asin(R / nab));                     // get_alpha, vel_obs3D.py:8-17 (IEEE ops: rare path)
+        const double AB = nab * sqrt(b2);
+        const double cosang = (AB != 0.0) ? dab / AB : 0.0;
+        const double beta_h = rint(acos(cosang) * 100.0);  // get_beta: unclamped arccos, numpy rounding
+        inside = alpha_h > beta_h;                         // NaN beta -> outside, as in the reference
+    }
+    if (!inside) return 0;
     const double rel_vx = 2.0 * ax - mvx - vx, rel_vy = 2.0 * ay - mvy - vy, rel_vz = 2.0 * az - mvz - vz;
     const double exp_time = cal_vo_exp_tim(rel_x, rel_y, rel_z, rel_vx, rel_vy, rel_vz, r, mr);
     if (!(exp_time < P.ctime)) return 0;
     const double d2 = rel_y * rel_y + rel_x * rel_x + rel_z * rel_z;
+    if (alpha_h != alpha_h) alpha_h = py_round2_hundredths(asin(R / sqrt(s2)));   // the row needs the rounded alpha
     t_out = exp_time;
     md = sqrt(d2) - mr;
     iet = fast_div(1.0, exp_time + 0.2);

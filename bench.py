@@ -106,7 +106,11 @@ def cpu_baseline(scn, E, seconds=12.0, threads=0, seed=0):
     import oracle
 
     ob = oracle.OracleBatch(scn, E, nm=NM)
-    cores = threads or oracle.max_threads()
+    try:
+        avail = len(os.sched_getaffinity(0))      # torchrun exports OMP_NUM_THREADS=1: ask the OS, not OpenMP
+    except AttributeError:
+        avail = os.cpu_count() or 1
+    cores = threads or avail
     oracle.set_threads(cores)
     rng = np.random.default_rng(seed)
     A = ob.A

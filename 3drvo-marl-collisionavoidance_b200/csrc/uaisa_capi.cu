@@ -130,8 +130,10 @@ int uaisa_create(const UaisaConfig *cfg, UaisaHandle **out) {
     if (threads < N || threads > 1024 || threads % 32) { delete h; return fail(UAISA_EINVAL, "threads_per_block must be a multiple of 32 in [n_drones, 1024]"); }
     h->threads = threads; P.threads = threads; P.envs_per_cta = threads / N;
     h->grid = (E + P.envs_per_cta - 1) / P.envs_per_cta;
-    h->smem = sizeof(double) * 8 * threads + sizeof(int) * 2 * P.envs_per_cta + 16 + 2 * 4096;   // + TMA fill tiles
     const int need = cfg->nm < N - 1 ? cfg->nm : N - 1;
+    const int maxr = threads > 256 ? 16 : (need <= 4 ? 4 : need <= 10 ? 10 : 16);
+    h->smem = sizeof(double) * 8 * threads + sizeof(int) * 2 * P.envs_per_cta + 16 + 2 * 4096   // + TMA fill tiles
+              + (maxr > 4 ? (size_t)threads * maxr * 24 : 0);                                     // + shared top-nm lists
     const bool wl = (N <= 32) && (32 % N == 0) && threads <= 128;   // every env inside one warp
     if (threads > 256) h->kernel = uaisa_env_kernel<16, 1024, false>;
     else if (threads > 128) h->kernel = need <= 4 ? uaisa_env_kernel<4, 256, false> : need <= 10 ? uaisa_env_kernel<10, 256, false> : uaisa_env_kernel<16, 256, false>;

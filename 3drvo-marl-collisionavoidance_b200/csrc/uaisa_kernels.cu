@@ -83,6 +83,7 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 128 ? UAISA_MINB128 : 1)) uaisa
     // constant tiles for the TMA fills (WL only), 16-byte aligned after the arrays above
     uint4 *tile0 = reinterpret_cast<uint4 *>((reinterpret_cast<uintptr_t>(ssel + P.envs_per_cta) + 15) & ~uintptr_t(15));
     uint4 *tile1 = tile0 + FILL_TILE / 16;
+    void *stop = tile1 + FILL_TILE / 16;               // top-nm lists of the MAXR > 4 instantiations
     if (WL) {
         for (int i = threadIdx.x; i < FILL_TILE / 16; i += blockDim.x) { tile0[i] = make_uint4(0u, 0u, 0u, 0u); tile1[i] = make_uint4(~0u, ~0u, ~0u, ~0u); }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the copy engine
@@ -234,7 +235,7 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 128 ? UAISA_MINB128 : 1)) uaisa
             RG_MARK(RG_DRONESTATE);
             // pairwise pass over the drones of my env (rvo_inter.py:20-83)
             bool vo_any = false, col = false; double tmin = CUDART_INF;
-            TopList<MAXR> top; top.clear();
+            TopList<MAXR> top; top.init(stop, threads, tid); top.clear();
             {
                 double bx = (ph == PH_OBS) ? 0.0 : ax, by = (ph == PH_OBS) ? 0.0 : ay, bz = (ph == PH_OBS) ? 0.0 : az;
                 if (np_dot3(bx, by, bz, bx, by, bz) < 1e-10 * (1.0 - 1e-14)) { bx = by = bz = 0.0; }   // norm(a) < 1e-5, rvo_inter.py:118-119
@@ -252,13 +253,33 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 128 ? UAISA_MINB128 : 1)) uaisa
                         cand |= (bits & PB_FULL) ? (1u << jj) : 0u;
                     }
                     n_cone += __popc(cand);
-                    while (cand) {
-                        const int jj = __ffs(cand) - 1; cand &= cand - 1;
-                        const int j = jb + jj;
-                        double tt, ah, md, iet;
-                        if (pair_cone(P, d.px, d.py, d.pz, d.vx, d.vy, d.vz, C.radius, C.prio, sx + lbase + j, threads, bx, by, bz, tt, ah, md, iet)) {
+                    // stage 2a: trig-free screen of every candidate (uniform work) -> inside / ambiguous masks
+                    unsigned ins = 0, amb = 0;
+                    for (unsigned m = cand; m; m &= m - 1) {
+                        const int jj = __ffs(m) - 1;
+                        PairGeom g; pair_geom(P, d.px, d.py, d.pz, d.vx, d.vy, d.vz, C.radius, C.prio, sx + lbase + jb + jj, threads, bx, by, bz, g);
+                        const int c = cone_screen(g);
+                        ins |= (c == 1) ? (1u << jj) : 0u; amb |= (c == 2) ? (1u << jj) : 0u;
+                    }
+                    // stage 2b: the few ambiguous pairs go through asin/acos with the reference's roundings
+                    for (unsigned m = amb; m; m &= m - 1) {
+                        const int jj = __ffs(m) - 1;
+                        PairGeom g; pair_geom(P, d.px, d.py, d.pz, d.vx, d.vy, d.vz, C.radius, C.prio, sx + lbase + jb + jj, threads, bx, by, bz, g);
+                        double ah;
+                        if (cone_exact(g, ah)) ins |= 1u << jj;
+                    }
+                    // stage 2c: pairs inside the cone -> expected collision time, vo_flag, row keys
+                    for (unsigned m = ins; m; m &= m - 1) {
+                        const int jj = __ffs(m) - 1, j = jb + jj;
+                        const double *so = sx + lbase + j;
+                        PairGeom g; pair_geom(P, d.px, d.py, d.pz, d.vx, d.vy, d.vz, C.radius, C.prio, so, threads, bx, by, bz, g);
+                        double tt, md, iet;
+                        if (cone_time(P, d.vx, d.vy, d.vz, C.radius, so, threads, bx, by, bz, g, tt, md, iet)) {
                             vo_any = true; if (tt < tmin) tmin = tt;
-                            if (ph != PH_A) top.insert(cap, iet, md, j, (int)ah);
+                            if (ph != PH_A) {
+                                const double ah = py_round2_hundredths(asin(g.R / sqrt(g.s2)));   // get_alpha, vel_obs3D.py:8-17
+                                top.insert(cap, iet, md, j, (int)ah);
+                            }
                         }
                     }
                 }
@@ -316,25 +337,22 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 128 ? UAISA_MINB128 : 1)) uaisa
                     }
                 }
                 // slot r (least urgent first, most urgent last) = top[cnt-1-r]
+                top.for_each([&](int sl, double t_iet, double t_md, int t_j, int t_ah) {
+                    const int r = top.cnt - 1 - sl;
+                    const double *so = sx + lbase + t_j;
+                    if (myobs) {
+                        const double mx = so[0], my = so[threads], mz = so[2 * threads];
+                        const double mvx = so[3 * threads], mvy = so[4 * threads], mvz = so[5 * threads], prb = so[7 * threads];
+                        const double pr = (C.prio == prb) ? 0.5 : fast_div(C.prio, C.prio + prb);
+                        const double v[ROW] = {pr * (2.0 * d.px + (d.vx + mvx) * 1.0), pr * (2.0 * d.py + (d.vy + mvy) * 1.0),
+                                               pr * (2.0 * d.pz + (d.vz + mvz) * 1.0), mx - d.px, my - d.py, mz - d.pz,
+                                               (double)t_ah * 0.01, t_md, t_iet};
+                        float *rr = myobs + OBS_SELF + ROW * r;
 #pragma unroll
-                for (int s = 0; s < MAXR; s++) {
-                    if (s < top.cnt) {
-                        const int r = top.cnt - 1 - s;
-                        const double *so = sx + lbase + top.j[s];
-                        if (myobs) {
-                            const double mx = so[0], my = so[threads], mz = so[2 * threads];
-                            const double mvx = so[3 * threads], mvy = so[4 * threads], mvz = so[5 * threads], prb = so[7 * threads];
-                            const double pr = fast_div(C.prio, C.prio + prb);
-                            const double v[ROW] = {pr * (2.0 * d.px + (d.vx + mvx) * 1.0), pr * (2.0 * d.py + (d.vy + mvy) * 1.0),
-                                                   pr * (2.0 * d.pz + (d.vz + mvz) * 1.0), mx - d.px, my - d.py, mz - d.pz,
-                                                   (double)top.ah[s] * 0.01, top.md[s], top.iet[s]};
-                            float *rr = myobs + OBS_SELF + ROW * r;
-#pragma unroll
-                            for (int q = 0; q < ROW; q++) { const float w = np_round2_f32(v[q]); bad |= (w * 0.f != 0.f); rr[q] = w; }
-                        }
-                        if (mynbr) mynbr[r] = top.j[s];
+                        for (int q = 0; q < ROW; q++) { const float w = np_round2_f32(v[q]); bad |= (w * 0.f != 0.f); rr[q] = w; }
                     }
-                }
+                    if (mynbr) mynbr[r] = t_j;
+                });
                 // rows beyond cnt: untouched zero fill after a step's clear, stale after a re-observe, or
                 // never cleared in the stand-alone observe/reset/autoreset modes
                 const int stale_end = (staged < 0) ? (is_step ? 0 : P.nm) : staged;

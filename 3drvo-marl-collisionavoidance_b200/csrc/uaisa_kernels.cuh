@@ -239,70 +239,91 @@ __device__ __forceinline__ int pair_gate(const Params &P, double x, double y, do
     return (dotp <= 0.0) ? PB_EVAL : (PB_EVAL | PB_FULL);
 }
 
-// Stage 2: the cone itself (rvo_inter.py:165-196, vel_obs3D.py:8-66,145-182).  (ax,ay,az) is the action with
-// the |a|<1e-5 -> 0 substitution already applied.  Returns PB_VO if the chosen velocity is inside the cone
-// with an expected collision time below the threshold; then t_out, alpha_h, md, iet are valid.
-__device__ __forceinline__ int pair_cone(const Params &P, double x, double y, double z, double vx, double vy, double vz,
-                                         double r, double pra, const double *so, int st, double ax, double ay, double az,
-                                         double &t_out, double &alpha_h, double &md, double &iet) {
+// Stage 2 of a pair: the cone (rvo_inter.py:165-196, vel_obs3D.py:8-66,145-182), itself split in three so that the
+// lanes of a warp never wait on each other's rare paths:
+//   cone_screen  trig-free classification: certainly outside / certainly inside / ambiguous
+//   cone_exact   asin / acos with the reference's roundings, only for ambiguous pairs
+//   cone_time    expected collision time + the row's sort keys, only for pairs inside the cone
+// (ax,ay,az) is the action with the |a|<1e-5 -> 0 substitution already applied.
+struct PairGeom {
+    double rel_x, rel_y, rel_z, s2, b2, dab, R;
+};
+__device__ __forceinline__ void pair_geom(const Params &P, double x, double y, double z, double vx, double vy, double vz,
+                                          double r, double pra, const double *so, int st, double ax, double ay, double az, PairGeom &g) {
     const double mx = so[0], my = so[st], mz = so[2 * st], mr = so[6 * st];
     const double mvx = so[3 * st], mvy = so[4 * st], mvz = so[5 * st], prb = so[7 * st];
-    const double rel_x = mx - x, rel_y = my - y, rel_z = mz - z;
-    const double s2 = np_dot3(rel_x, rel_y, rel_z, rel_x, rel_y, rel_z);
-    const double R = r + mr;
-    const double pr = fast_div(pra, pra + prb);                            // get_PAA, vel_obs3D.py:19-32
+    g.rel_x = mx - x; g.rel_y = my - y; g.rel_z = mz - z;
+    g.s2 = np_dot3(g.rel_x, g.rel_y, g.rel_z, g.rel_x, g.rel_y, g.rel_z);
+    g.R = r + mr;
+    const double pr = (pra == prb) ? 0.5 : fast_div(pra, pra + prb);      // get_PAA, vel_obs3D.py:19-32 (a/(a+a) == 0.5 exactly)
     const double PAAx = pr * (2.0 * x + (vx + mvx) * 1.0), PAAy = pr * (2.0 * y + (vy + mvy) * 1.0), PAAz = pr * (2.0 * z + (vz + mvz) * 1.0);
     const double Bx = x + 2.0 * ax * P.delta_t - PAAx, By = y + 2.0 * ay * P.delta_t - PAAy, Bz = z + 2.0 * az * P.delta_t - PAAz;
-    const double b2 = np_dot3(Bx, By, Bz, Bx, By, Bz), dab = np_dot3(rel_x, rel_y, rel_z, Bx, By, Bz);
-    // Trig-free screen.  inside <=> round(100 alpha) > round(100 beta) with alpha = asin(R/|rel|), beta = acos(c):
-    // beta > alpha + 0.02 rad is certainly outside and beta < alpha - 0.02 certainly inside (each rounding moves a
-    // value by <= 0.005 rad), and both are decided on cosines: cos(alpha -+ 0.02) = cos a cos .02 +- sin a sin .02.
-    // Only the +-0.02 band around alpha (and the degenerate / near-collinear cases, where the reference's
-    // unclamped arccos may return NaN) go through asin/acos.
-    bool need_exact = true, inside = false;
-    alpha_h = CUDART_NAN;
-    if (b2 > 0.0) {
-        const double inab = fast_rsqrt(s2), sin_a = R * inab, c_f = dab * inab * fast_rsqrt(b2);
-        const double cos_a = fast_sqrt(fma(-sin_a, sin_a, 1.0));
-        const double C02 = 0.99980000666657776, S02 = 0.019998666693333084;   // cos(0.02), sin(0.02)
-        if (c_f < cos_a * C02 - sin_a * S02 - 1e-9) return 0;                                   // beta > alpha + 0.02
-        if (sin_a > 0.03 && c_f > cos_a * C02 + sin_a * S02 + 1e-9 && c_f < 1.0 - 1e-9) { need_exact = false; inside = true; }
-    }
-    if (need_exact) {
-        const double nab = sqrt(s2);
-        alpha_h = py_round2_hundredths(asin(R / nab));                     // get_alpha, vel_obs3D.py:8-17 (IEEE ops: rare path)
-        const double AB = nab * sqrt(b2);
-        const double cosang = (AB != 0.0) ? dab / AB : 0.0;
-        const double beta_h = rint(acos(cosang) * 100.0);  // get_beta: unclamped arccos, numpy rounding
-        inside = alpha_h > beta_h;                         // NaN beta -> outside, as in the reference
-    }
-    if (!inside) return 0;
+    g.b2 = np_dot3(Bx, By, Bz, Bx, By, Bz); g.dab = np_dot3(g.rel_x, g.rel_y, g.rel_z, Bx, By, Bz);
+}
+// inside <=> round(100 alpha) > round(100 beta), alpha = asin(R/|rel|), beta = acos(c).  beta > alpha + 0.02 rad is
+// certainly outside and beta < alpha - 0.02 certainly inside (each rounding moves a value by <= 0.005 rad); both are
+// decided on cosines without trig or square roots: with s = sin a, c = cos beta,
+//   beta > a + .02  <=>  c < cos(a + .02)  <=>  c + s S < C sqrt(1 - s^2)      (S = sin .02, C = cos .02)
+//   beta < a - .02  <=>  c - s S > C sqrt(1 - s^2)
+// Returns 0 outside, 1 inside, 2 ambiguous (the +-0.02 band, degenerate |B| = 0, and near-collinear vectors where the
+// reference's unclamped arccos may return NaN).
+__device__ __forceinline__ int cone_screen(const PairGeom &g) {
+    if (!(g.b2 > 0.0)) return 2;
+    const double inab = fast_rsqrt(g.s2), s = g.R * inab, c = g.dab * inab * fast_rsqrt(g.b2);
+    const double C02 = 0.99980000666657776, S02 = 0.019998666693333084;
+    const double rhs2 = fma(-s, s, 1.0) * (C02 * C02), sS = s * S02;
+    const double lo = c + sS, hi = c - sS;
+    if (lo < -1e-9 || (lo >= 0.0 && lo * lo < rhs2 * (1.0 - 1e-9))) return 0;
+    if (s > 0.03 && hi > 1e-9 && hi * hi > rhs2 * (1.0 + 1e-9) && c < 1.0 - 1e-9) return 1;
+    return 2;
+}
+__device__ __forceinline__ bool cone_exact(const PairGeom &g, double &alpha_h) {
+    const double nab = sqrt(g.s2);
+    alpha_h = py_round2_hundredths(asin(g.R / nab));       // get_alpha, vel_obs3D.py:8-17 (IEEE ops: rare path)
+    const double AB = nab * sqrt(g.b2);
+    const double cosang = (AB != 0.0) ? g.dab / AB : 0.0;
+    const double beta_h = rint(acos(cosang) * 100.0);      // get_beta: unclamped arccos, numpy rounding
+    return alpha_h > beta_h;                               // NaN beta -> outside, as in the reference
+}
+// Returns true when the expected collision time is below the threshold (vo_flag); then t_out, md, iet are valid.
+__device__ __forceinline__ bool cone_time(const Params &P, double vx, double vy, double vz, double r, const double *so, int st,
+                                          double ax, double ay, double az, const PairGeom &g, double &t_out, double &md, double &iet) {
+    const double mvx = so[3 * st], mvy = so[4 * st], mvz = so[5 * st], mr = so[6 * st];
     const double rel_vx = 2.0 * ax - mvx - vx, rel_vy = 2.0 * ay - mvy - vy, rel_vz = 2.0 * az - mvz - vz;
-    const double exp_time = cal_vo_exp_tim(rel_x, rel_y, rel_z, rel_vx, rel_vy, rel_vz, r, mr);
-    if (!(exp_time < P.ctime)) return 0;
-    const double d2 = rel_y * rel_y + rel_x * rel_x + rel_z * rel_z;
-    if (alpha_h != alpha_h) alpha_h = py_round2_hundredths(asin(R / sqrt(s2)));   // the row needs the rounded alpha
+    const double exp_time = cal_vo_exp_tim(g.rel_x, g.rel_y, g.rel_z, rel_vx, rel_vy, rel_vz, r, mr);
+    if (!(exp_time < P.ctime)) return false;
+    const double d2 = g.rel_y * g.rel_y + g.rel_x * g.rel_x + g.rel_z * g.rel_z;
     t_out = exp_time;
     md = sqrt(d2) - mr;
     iet = fast_div(1.0, exp_time + 0.2);
-    return PB_VO;
+    return true;
 }
 
 // ---- top-nm neighbour list (rvo_inter.py:50-59) ------------------------------------------------------
 // Kept sorted most-urgent-first; "more urgent" = later in the reference's stable descending sort by
 // (-iet, md): larger iet, then smaller md, then larger drone index.
+// MAXR <= 4 (N <= 5): registers, fully unrolled predicated insertion.  Larger lists live in shared memory
+// (SoA [slot][thread], conflict-free) -- in registers they would spill (50+ registers for MAXR = 10).
+__device__ __forceinline__ bool more_urgent(double a_iet, double a_md, int a_j, double b_iet, double b_md, int b_j) {
+    return (a_iet > b_iet) || (a_iet == b_iet && (a_md < b_md || (a_md == b_md && a_j > b_j)));
+}
+template <int MAXR, bool IN_SMEM = (MAXR > 4)>
+struct TopList;
+
 template <int MAXR>
-struct TopList {
+struct TopList<MAXR, false> {
+    static constexpr size_t smem_bytes(int) { return 0; }
     double iet[MAXR], md[MAXR];
     int j[MAXR], ah[MAXR];
     int cnt;
+    __device__ __forceinline__ void init(void *, int, int) {}
     __device__ __forceinline__ void clear() { cnt = 0; }
     __device__ __forceinline__ void insert(int cap, double c_iet, double c_md, int c_j, int c_ah) {
         bool placed = false;
 #pragma unroll
         for (int s = 0; s < MAXR; s++) {
             bool valid = s < cnt;
-            bool sw = valid && ((c_iet > iet[s]) || (c_iet == iet[s] && (c_md < md[s] || (c_md == md[s] && c_j > j[s]))));
+            bool sw = valid && more_urgent(c_iet, c_md, c_j, iet[s], md[s], j[s]);
             if (sw) {
                 double t0 = iet[s]; iet[s] = c_iet; c_iet = t0;
                 double t1 = md[s]; md[s] = c_md; c_md = t1;
@@ -312,6 +333,37 @@ struct TopList {
             if (!valid && !placed && s < cap) { iet[s] = c_iet; md[s] = c_md; j[s] = c_j; ah[s] = c_ah; placed = true; }
         }
         if (placed) cnt++;
+    }
+    template <typename F>
+    __device__ __forceinline__ void for_each(F &&f) const {   // f(slot, iet, md, j, ah) for slot = 0 (most urgent) .. cnt-1
+#pragma unroll
+        for (int s = 0; s < MAXR; s++) if (s < cnt) f(s, iet[s], md[s], j[s], ah[s]);
+    }
+};
+
+template <int MAXR>
+struct TopList<MAXR, true> {
+    static constexpr size_t smem_bytes(int threads) { return (size_t)threads * MAXR * 24; }
+    double *iet, *md; int *j, *ah;   // this thread's column; slot s at [s * st]
+    int st, cnt;
+    __device__ __forceinline__ void init(void *base, int threads, int tid) {
+        st = threads;
+        iet = reinterpret_cast<double *>(base) + tid; md = iet + (size_t)MAXR * threads;
+        j = reinterpret_cast<int *>(reinterpret_cast<double *>(base) + 2 * (size_t)MAXR * threads) + tid; ah = j + (size_t)MAXR * threads;
+    }
+    __device__ __forceinline__ void clear() { cnt = 0; }
+    __device__ __forceinline__ void insert(int cap, double c_iet, double c_md, int c_j, int c_ah) {
+        int s = cnt;                                   // walk up from the least urgent end, shifting entries down
+        while (s > 0 && more_urgent(c_iet, c_md, c_j, iet[(s - 1) * st], md[(s - 1) * st], j[(s - 1) * st])) {
+            if (s < cap) { iet[s * st] = iet[(s - 1) * st]; md[s * st] = md[(s - 1) * st]; j[s * st] = j[(s - 1) * st]; ah[s * st] = ah[(s - 1) * st]; }
+            s--;
+        }
+        if (s < cap) { iet[s * st] = c_iet; md[s * st] = c_md; j[s * st] = c_j; ah[s * st] = c_ah; }
+        if (cnt < cap) cnt++;
+    }
+    template <typename F>
+    __device__ __forceinline__ void for_each(F &&f) const {
+        for (int s = 0; s < cnt; s++) f(s, iet[s * st], md[s * st], j[s * st], ah[s * st]);
     }
 };
 

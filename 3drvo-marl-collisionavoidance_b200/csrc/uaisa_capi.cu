@@ -279,6 +279,22 @@ int uaisa_cal_des(UaisaHandle *h, float *des, void *stream) {
     return UAISA_OK;
 }
 
+int uaisa_action_transform(UaisaHandle *h, const float *a_inc, float acceler, float *a_inc_rounded, float *action, void *stream) {
+    if (!h || !a_inc || !action) return fail(UAISA_EINVAL, "NULL argument");
+    if (!h->scenarios_set) return fail(UAISA_ESTATE, "uaisa_set_scenarios has not been called");
+    uaisa_action_transform_kernel<<<(h->A + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(h->P, a_inc, acceler, a_inc_rounded, action);
+    h->launches++;
+    CK(cudaGetLastError());
+    return UAISA_OK;
+}
+
+int uaisa_gae(const float *rew, const float *val, const uint8_t *cut, int32_t T, int32_t A, float gamma, float lam, float *adv, float *ret, void *stream) {
+    if (!rew || !val || !cut || !adv || !ret || T < 1 || A < 1) return fail(UAISA_EINVAL, "bad argument");
+    uaisa_gae_kernel<<<(A + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(rew, val, cut, T, A, gamma, lam, adv, ret);
+    CK(cudaGetLastError());
+    return UAISA_OK;
+}
+
 int uaisa_indicators(UaisaHandle *h, float *max_dev, float *extra_len, void *stream) {
     if (!h) return fail(UAISA_EINVAL, "NULL handle");
     cudaStream_t s = static_cast<cudaStream_t>(stream);

@@ -454,6 +454,41 @@ __global__ void uaisa_cal_des_kernel(const __grid_constant__ Params P, float *de
     des[3 * a] = (float)d0; des[3 * a + 1] = (float)d1; des[3 * a + 2] = (float)d2;
 }
 
+// ---- rollout-side kernels (SURVEY.md section 8a rows a-P2) ---------------------------------------------------
+// Trainer action transform, multi_ppo.py:197-205: a_inc = np.round(a_inc, 2) on the float32 sample,
+// abs_action = np.round(acceler * a_inc + cur_vel, 2) in float64 (cur_vel = drone.vel, read from the env state).
+__global__ void uaisa_action_transform_kernel(const __grid_constant__ Params P, const float *a_inc, float acceler, float *a_inc_rounded, float *action) {
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= P.E * P.N) return;
+    const float4 vp = P.vel_pitch[a];
+    const float v[3] = {vp.x, vp.y, vp.z};
+#pragma unroll
+    for (int q = 0; q < 3; q++) {
+        const float ar = __fdiv_rn(rintf(__fmul_rn(a_inc[3 * a + q], 100.0f)), 100.0f);   // np.round on a float32 array
+        if (a_inc_rounded) a_inc_rounded[3 * a + q] = ar;
+        const double ab = (double)__fmul_rn(acceler, ar) + (double)v[q];
+        action[3 * a + q] = np_round2_f32(ab);
+    }
+}
+
+// GAE-lambda over [T][A] buffers, multi_PPObuf.finish_path with last_val = 0 (multi_ppo.py:68-77): a path ends after
+// step t where cut[t][a] != 0 (and at t = T-1); one thread per agent scans its column backwards.
+__global__ void uaisa_gae_kernel(const float *rew, const float *val, const uint8_t *cut, int T, int A, float gamma, float lam, float *adv, float *ret) {
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= A) return;
+    float next_v = 0.f, next_adv = 0.f, next_ret = 0.f;
+    for (int t = T - 1; t >= 0; t--) {
+        const size_t o = (size_t)t * A + a;
+        if (t == T - 1 || cut[o]) { next_v = 0.f; next_adv = 0.f; next_ret = 0.f; }
+        const float r = rew[o], v = val[o];
+        const float delta = r + gamma * next_v - v;
+        next_adv = delta + gamma * lam * next_adv;
+        next_ret = r + gamma * next_ret;
+        next_v = v;
+        adv[o] = next_adv; ret[o] = next_ret;
+    }
+}
+
 #define UAISA_INST(R, T, W) template __global__ void uaisa_env_kernel<R, T, W>(const __grid_constant__ Params, const __grid_constant__ Launch);
 UAISA_INST(4, 128, true) UAISA_INST(10, 128, true) UAISA_INST(16, 128, true)
 UAISA_INST(4, 128, false) UAISA_INST(10, 128, false) UAISA_INST(16, 128, false)

@@ -387,5 +387,7 @@ __device__ __forceinline__ double angle_punish(double A0, double A1, double A2, 
 template <int MAXR, int MAXT, bool WL>
 __global__ void uaisa_env_kernel(const __grid_constant__ Params P, const __grid_constant__ Launch L);
 __global__ void uaisa_cal_des_kernel(const __grid_constant__ Params P, float *des);
+__global__ void uaisa_action_transform_kernel(const __grid_constant__ Params P, const float *a_inc, float acceler, float *a_inc_rounded, float *action);
+__global__ void uaisa_gae_kernel(const float *rew, const float *val, const uint8_t *cut, int T, int A, float gamma, float lam, float *adv, float *ret);
 
 }  // namespace uaisa

@@ -158,6 +158,15 @@ class VecMdin:
         _capi.check(self.L.uaisa_cal_des(self.h, _ptr(des), self._stream()))
         return des
 
+    def action_transform(self, a_inc: torch.Tensor, action_out: Optional[torch.Tensor] = None, a_inc_rounded: Optional[torch.Tensor] = None):
+        """multi_ppo.py:197-205 on device: returns (action[A,3] for step(), rounded increment[A,3] for the buffer)."""
+        if action_out is None:
+            action_out = torch.empty((self.A, 3), dtype=torch.float32, device=self.device)
+        if a_inc_rounded is None:
+            a_inc_rounded = torch.empty((self.A, 3), dtype=torch.float32, device=self.device)
+        _capi.check(self.L.uaisa_action_transform(self.h, _ptr(a_inc.contiguous()), float(self.acceler), _ptr(a_inc_rounded), _ptr(action_out), self._stream()))
+        return action_out, a_inc_rounded
+
     def indicators(self):
         """(max_deviation[A], extra_len[A]) -- ir_gym.indicators_deviation / indicators_extra_len."""
         md = torch.empty(self.A, dtype=torch.float32, device=self.device)

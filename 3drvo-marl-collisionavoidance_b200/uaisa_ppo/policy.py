@@ -1,0 +1,126 @@
+"""Batched actor-critic of the reference (train/policy/policy_rnn_ac.py) over the dense observation layout.
+
+Same architecture and the same ``state_dict`` keys as ``rnn_ac`` (policy_rnn_ac.py:31-72), so the shipped
+checkpoints (train/model_save/*_check_point_0.pt, ``model_state``) load with ``strict=True``:
+shared bi-GRU reader over the neighbour rows (9 -> 256, final hidden states of both directions SUMMED,
+:116-122) -> concat the 12 self values -> LayerNorm(268) -> actor MLP 268-256-256-3 (ReLU, ReLU, Tanh) with a
+learned ``log_std`` / critic MLP 268-256-256-1.
+
+What changes is the batching: the reference calls ``ac.step`` once per drone per step with a ragged vector
+(multi_ppo.py:193-196); here all A agents go through at once from ``obs[A, 12+9nm]`` + ``count[A]`` exactly as
+the env kernel writes them.  A drone without neighbours feeds ONE all-zero row (ir_gym.py:211-212), which is
+what the zero padding already is, so step 0 of the GRU runs densely for everybody and only the (few) agents
+with two or more rows go through the sequential part.
+
+The GEMMs are library calls (cuBLAS through torch); the fused tcgen05 forward is the next step.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+from torch.distributions.normal import Normal
+
+
+def mlp(sizes, activation, output_activation=nn.Identity):   # policy_rnn_ac.py:10-17
+    layers = []
+    for j in range(len(sizes) - 1):
+        act = activation if j < len(sizes) - 2 else output_activation
+        layers += [nn.Linear(sizes[j], sizes[j + 1]), act()]
+    return nn.Sequential(*layers)
+
+
+class rnn_Reader(nn.Module):   # policy_rnn_ac.py:75-168 (mode 'biGRU')
+    def __init__(self, state_dim=12, input_dim=9, hidden_dim=256):
+        super().__init__()
+        self.state_dim, self.input_dim, self.hidden_dim = state_dim, input_dim, hidden_dim
+        self.rnn_net = nn.GRU(input_dim, hidden_dim, batch_first=True, bidirectional=True)
+        self.ln = nn.LayerNorm(state_dim + hidden_dim)
+
+    def _cell(self, x, h, rev: bool):
+        sfx = "_reverse" if rev else ""
+        w_ih, w_hh = getattr(self.rnn_net, "weight_ih_l0" + sfx), getattr(self.rnn_net, "weight_hh_l0" + sfx)
+        b_ih, b_hh = getattr(self.rnn_net, "bias_ih_l0" + sfx), getattr(self.rnn_net, "bias_hh_l0" + sfx)
+        gi, gh = F.linear(x, w_ih, b_ih), F.linear(h, w_hh, b_hh)
+        i_r, i_z, i_n = gi.chunk(3, -1)
+        h_r, h_z, h_n = gh.chunk(3, -1)
+        r, z = torch.sigmoid(i_r + h_r), torch.sigmoid(i_z + h_z)
+        n = torch.tanh(i_n + r * h_n)
+        return (1 - z) * n + z * h
+
+    def forward(self, obs: torch.Tensor, count: torch.Tensor) -> torch.Tensor:
+        """obs [B, 12+9nm] float32, count [B] (rows valid; 0 means one zero row) -> LayerNorm(cat(self, h_f + h_b)) [B, 268]."""
+        B = obs.shape[0]
+        nm = (obs.shape[1] - self.state_dim) // self.input_dim
+        self_state = obs[:, : self.state_dim]
+        rows = obs[:, self.state_dim: self.state_dim + nm * self.input_dim].reshape(B, nm, self.input_dim)
+        h0 = obs.new_zeros((B, self.hidden_dim))
+        x0 = rows[:, 0] if nm > 0 else obs.new_zeros((B, self.input_dim))
+        hsum = self._cell(x0, h0, False) + self._cell(x0, h0, True)          # exact for every agent with <= 1 row
+        if nm > 1:
+            multi = torch.nonzero(count > 1).squeeze(-1)                       # (one host sync; few agents)
+            if multi.numel() > 0:
+                r_m, c_m = rows[multi], count[multi].to(torch.long)
+                lmax = int(c_m.max())
+                hf = obs.new_zeros((multi.numel(), self.hidden_dim)); hb = hf.clone()
+                for l in range(lmax):                                          # forward direction: x_0 .. x_{len-1}
+                    m = (l < c_m).unsqueeze(-1)
+                    hf = torch.where(m, self._cell(r_m[:, l], hf, False), hf)
+                for l in range(lmax - 1, -1, -1):                              # reverse direction: x_{len-1} .. x_0
+                    m = (l < c_m).unsqueeze(-1)
+                    hb = torch.where(m, self._cell(r_m[:, l], hb, True), hb)
+                hsum = hsum.index_copy(0, multi, hf + hb)
+        return self.ln(torch.cat((self_state, hsum), dim=1))
+
+
+class GaussianActor(nn.Module):   # policy_rnn_ac.py:191-235
+    def __init__(self, obs_dim, act_dim, hidden_sizes, activation, output_activation, rnn_reader):
+        super().__init__()
+        self.rnn_reader = rnn_reader
+        self.net_out = mlp([obs_dim] + list(hidden_sizes) + [act_dim], activation, output_activation)
+        self.log_std = nn.Parameter(torch.as_tensor(-1 * np.ones(act_dim, dtype=np.float32)))
+
+    def distribution_from_features(self, feat, std_factor=1.0):
+        mu = self.net_out(feat)
+        std = torch.clamp(std_factor * torch.exp(self.log_std) + 1e-6, min=1e-4, max=10.0)
+        return Normal(mu, std)
+
+
+class Critic(nn.Module):   # policy_rnn_ac.py:238-257
+    def __init__(self, obs_dim, hidden_sizes, activation, output_activation, rnn_reader):
+        super().__init__()
+        self.v_net = mlp([obs_dim] + list(hidden_sizes) + [1], activation, output_activation)
+        self.rnn_reader = rnn_reader
+
+
+class rnn_ac(nn.Module):   # policy_rnn_ac.py:31-72, defaults of train_process.py:37-48
+    def __init__(self, state_dim=12, rnn_input_dim=9, rnn_hidden_dim=256, hidden_sizes_ac=(256, 256), hidden_sizes_v=(256, 256),
+                 act_dim=3, activation=nn.ReLU, output_activation=nn.Tanh, output_activation_v=nn.Identity):
+        super().__init__()
+        obs_dim = rnn_hidden_dim + state_dim
+        rnn = rnn_Reader(state_dim, rnn_input_dim, rnn_hidden_dim)
+        self.pi = GaussianActor(obs_dim, act_dim, hidden_sizes_ac, activation, output_activation, rnn)
+        self.v = Critic(obs_dim, hidden_sizes_v, activation, output_activation_v, rnn)     # the reader is SHARED (:46-54)
+
+    def features(self, obs, count):
+        return self.pi.rnn_reader(obs, count)
+
+    def evaluate(self, obs, count, act=None, std_factor=1.0):
+        """-> (Normal, value[B], logp[B] or None); one reader pass feeds both heads."""
+        feat = self.features(obs, count)
+        dist = self.pi.distribution_from_features(feat, std_factor)
+        v = torch.squeeze(self.v.v_net(feat), -1)
+        logp = dist.log_prob(act).sum(-1) if act is not None else None
+        return dist, v, logp
+
+    @torch.no_grad()
+    def step(self, obs, count, std_factor=1.0):
+        """ac.step for all agents (policy_rnn_ac.py:57-69): sampled action increment, value, log-prob (CUDA tensors)."""
+        dist, v, _ = self.evaluate(obs, count, None, std_factor)
+        a = dist.sample()
+        return a, v, dist.log_prob(a).sum(-1)
+
+    @torch.no_grad()
+    def act(self, obs, count, std_factor=1.0):
+        return self.step(obs, count, std_factor)[0]

@@ -1,0 +1,171 @@
+"""Batched PPO rollout + update around VecMdin: the data-parallel form of ``multi_ppo.training_loop``
+(train/policy/multi_ppo.py:166-339).
+
+What is kept from the reference (cited per line below): the per-step sequence (policy step -> 2-dp action
+transform -> env step -> store -> trainer reset policy -> re-observe), GAE(gamma .99, lambda .97) with last_val = 0
+and paths cut exactly where ``finish_path`` is called, NO advantage normalisation, the PPO-clip loss, the approx-KL
+early stop, grad-norm clipping at 2.0 over ALL actor-critic parameters for the policy step, separate Adam optimisers for
+pi and v that both touch the shared reader, and the hyper-parameters of train_process.py:53-63.
+
+What changes (documented deviation, SURVEY.md section 7 "PPO semantics vs batching"): the reference loops over
+robots and does 50+50 FULL-BATCH iterations on each robot's own 300 samples; here every agent of every env feeds one
+batch that is cut into minibatches, and with world_size > 1 the gradients are all-reduced (NCCL, one flat bucket per
+iteration: 680 991 fp32 = 2.7 MB, plus the KL scalar) before the identical clip + Adam step on every rank.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import time
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+import torch.distributed as dist
+
+from uaisa_env import _capi
+from uaisa_env.vec_env import VecMdin
+from .policy import rnn_ac
+
+
+@dataclass
+class PPOConfig:                      # train_process.py:53-63 defaults
+    steps_per_epoch: int = 300
+    max_ep_len: int = 500
+    gamma: float = 0.99
+    lam: float = 0.97
+    clip_ratio: float = 0.2
+    pi_lr: float = 4e-6
+    vf_lr: float = 5e-5
+    train_pi_iters: int = 50
+    train_v_iters: int = 50
+    target_kl: float = 0.05
+    max_grad_norm: float = 2.0        # multi_ppo.py:367
+    minibatch: int = 65536            # samples per gradient step (the reference's "batch" is one robot's 300 samples)
+    std_factor: float = 1.0
+
+
+def gae(rew, val, cut, gamma, lam):
+    """uaisa_gae: [T,A] float32 CUDA tensors -> (adv, ret)."""
+    T, A = rew.shape
+    adv, ret = torch.empty_like(rew), torch.empty_like(rew)
+    p = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
+    _capi.check(_capi.lib().uaisa_gae(p(rew), p(val), p(cut), T, A, float(gamma), float(lam), p(adv), p(ret),
+                                      C.c_void_p(torch.cuda.current_stream(rew.device).cuda_stream)))
+    return adv, ret
+
+
+class PPOTrainer:
+    def __init__(self, env: VecMdin, ac: Optional[rnn_ac] = None, cfg: Optional[PPOConfig] = None, seed: int = 7):
+        self.env, self.cfg = env, cfg or PPOConfig()
+        self.dev = env.device
+        torch.manual_seed(seed)        # multi_ppo.py:103-105
+        self.ac = (ac or rnn_ac()).to(self.dev)
+        self.world = dist.get_world_size() if dist.is_initialized() else 1
+        if self.world > 1:             # same parameters everywhere (the reference's intended bcast, multi_ppo.py:179-181)
+            for p in self.ac.parameters():
+                dist.broadcast(p.data, 0)
+        self.pi_opt = torch.optim.Adam(self.ac.pi.parameters(), lr=self.cfg.pi_lr)     # multi_ppo.py:115-116
+        self.vf_opt = torch.optim.Adam(self.ac.v.parameters(), lr=self.cfg.vf_lr)
+        T, A, D = self.cfg.steps_per_epoch, env.A, env.obs_dim
+        f32 = dict(dtype=torch.float32, device=self.dev)
+        self.buf = {"obs": torch.empty((T, A, D), **f32), "count": torch.empty((T, A), dtype=torch.uint8, device=self.dev),
+                    "act": torch.empty((T, A, 3), **f32), "rew": torch.empty((T, A), **f32), "val": torch.empty((T, A), **f32),
+                    "logp": torch.empty((T, A), **f32), "cut": torch.empty((T, A), dtype=torch.uint8, device=self.dev)}
+        self.action = torch.empty((A, 3), **f32)
+        self.env.reset()
+        self.stats = {}
+
+    # ------------------------------------------------------------------------------------------------ rollout
+    @torch.no_grad()
+    def rollout(self):
+        """steps_per_epoch env steps of every env (multi_ppo.py:183-281)."""
+        env, cfg, b = self.env, self.cfg, self.buf
+        T = cfg.steps_per_epoch
+        n_done = torch.zeros((), dtype=torch.int64, device=self.dev)
+        for t in range(T):
+            b["obs"][t].copy_(env.obs); b["count"][t].copy_(env.count)                              # :217-219 store(obs, ...)
+            a_inc, v, logp = self.ac.step(env.obs, env.count, cfg.std_factor)                       # :196
+            env.action_transform(a_inc, self.action, b["act"][t])                                   # :197-208
+            env.step(self.action)                                                                   # :210
+            b["rew"][t].copy_(env.reward); b["val"][t].copy_(v); b["logp"][t].copy_(logp)
+            n_done += env.done.sum()
+            env.autoreset(max_ep_len=cfg.max_ep_len, epoch_ended=(t == T - 1))                      # :226-281 (+ env_observation)
+            b["cut"][t].copy_(env.path_cut)
+        self.stats["collisions"] = n_done
+        return b
+
+    # ------------------------------------------------------------------------------------------------ update
+    def _allreduce_grads(self, params, extra: Optional[torch.Tensor] = None):
+        if self.world == 1:
+            return extra
+        flat = [p.grad.reshape(-1) if p.grad is not None else torch.zeros(p.numel(), device=self.dev) for p in params]
+        bucket = torch.cat(flat + ([extra.reshape(-1)] if extra is not None else []))
+        dist.all_reduce(bucket)
+        bucket /= self.world
+        off = 0
+        for p in params:
+            n = p.numel()
+            if p.grad is not None:
+                p.grad.copy_(bucket[off:off + n].view_as(p.grad))
+            off += n
+        return bucket[off:] if extra is not None else None
+
+    def update(self):
+        """PPO-clip update (multi_ppo.py:341-404) on the whole buffer."""
+        cfg, b = self.cfg, self.buf
+        adv, ret = gae(b["rew"], b["val"], b["cut"], cfg.gamma, cfg.lam)                            # finish_path, :68-77
+        T, A = b["rew"].shape
+        n = T * A
+        obs, cnt = b["obs"].view(n, -1), b["count"].view(n)
+        act, logp_old, adv, ret = b["act"].view(n, 3), b["logp"].view(n), adv.view(n), ret.view(n)
+        ok = torch.isfinite(adv) & torch.isfinite(ret)        # the reference's inf/nan rewards (ir_gym.py:88) would poison Adam
+        all_params = list(self.ac.parameters())
+        mb = min(cfg.minibatch, n)
+        pi_iters = 0
+        for i in range(cfg.train_pi_iters):                                                        # :355-368
+            idx = torch.randint(0, n, (mb,), device=self.dev) if mb < n else torch.arange(n, device=self.dev)
+            w = ok[idx].float()
+            self.pi_opt.zero_grad(set_to_none=True)
+            dist_, _, logp = self.ac.evaluate(obs[idx], cnt[idx], act[idx])
+            ratio = torch.exp(logp - logp_old[idx])
+            a_ = torch.nan_to_num(adv[idx], 0.0, 0.0, 0.0)
+            clip_adv = torch.clamp(ratio, 1 - cfg.clip_ratio, 1 + cfg.clip_ratio) * a_
+            loss_pi = -(torch.min(ratio * a_, clip_adv) * w).sum() / w.sum().clamp(min=1)          # :393-397
+            kl = ((logp_old[idx] - logp) * w).sum() / w.sum().clamp(min=1)                          # :399
+            if self.world > 1:
+                kl_all = kl.detach().clone(); dist.all_reduce(kl_all); kl_all /= self.world
+            else:
+                kl_all = kl.detach()
+            if float(kl_all) > cfg.target_kl:                                                       # :362-364
+                break
+            loss_pi.backward()
+            self._allreduce_grads(all_params)
+            torch.nn.utils.clip_grad_norm_(all_params, max_norm=cfg.max_grad_norm)                  # :367 (all ac params)
+            self.pi_opt.step()
+            pi_iters += 1
+        for i in range(cfg.train_v_iters):                                                         # :371-376
+            idx = torch.randint(0, n, (mb,), device=self.dev) if mb < n else torch.arange(n, device=self.dev)
+            w = ok[idx].float()
+            self.vf_opt.zero_grad(set_to_none=True)
+            _, v, _ = self.ac.evaluate(obs[idx], cnt[idx], None)
+            loss_v = (((v - torch.nan_to_num(ret[idx], 0.0, 0.0, 0.0)) ** 2) * w).sum() / w.sum().clamp(min=1)   # :379-383
+            loss_v.backward()
+            self._allreduce_grads(list(self.ac.v.parameters()))
+            self.vf_opt.step()
+        self.stats.update(pi_iters=pi_iters, loss_v=float(loss_v.detach()), kl=float(kl_all), mean_ret=float(torch.nan_to_num(ret, 0.0, 0.0, 0.0).mean()))
+        return self.stats
+
+    def train_epoch(self):
+        t0 = time.perf_counter()
+        self.rollout()
+        torch.cuda.synchronize(self.dev)
+        t1 = time.perf_counter()
+        self.update()
+        torch.cuda.synchronize(self.dev)
+        t2 = time.perf_counter()
+        self.stats.update(rollout_s=t1 - t0, update_s=t2 - t1)
+        return self.stats
+
+    def save_model(self, path):
+        """Same container as multi_ppo.save_model (multi_ppo.py:406-420): {'model_state', 'pi_optimizer', 'vf_optimizer'}."""
+        torch.save(dict(model_state=self.ac.state_dict(), pi_optimizer=self.pi_opt.state_dict(), vf_optimizer=self.vf_opt.state_dict()), path)

@@ -130,6 +130,14 @@ int uaisa_get_state(UaisaHandle *h, const UaisaStateView *dst, void *stream);
 int uaisa_set_state(UaisaHandle *h, const UaisaStateView *src, void *stream);
 /* ir_gym.cal_des_list (ir_gym.py:44-46): des[A][3] */
 int uaisa_cal_des(UaisaHandle *h, float *des, void *stream);
+/* Trainer action transform (multi_ppo.py:197-205): a_inc[A][3] = the policy's float32 sample;
+ * a_inc_rounded = np.round(a_inc, 2) (what the buffer stores, may be NULL); action = np.round(acceler * a_inc_rounded +
+ * drone.vel, 2) = what uaisa_step consumes. */
+int uaisa_action_transform(UaisaHandle *h, const float *a_inc, float acceler, float *a_inc_rounded, float *action, void *stream);
+/* GAE-lambda with last_val = 0 over [T][A] buffers (multi_PPObuf.finish_path, multi_ppo.py:68-77): a path ends after
+ * step t where cut[t][a] != 0 (uaisa_autoreset's path_cut) and at t = T-1.  adv/ret [T][A]. */
+int uaisa_gae(const float *rew, const float *val, const uint8_t *cut, int32_t T, int32_t A, float gamma, float lam,
+              float *adv, float *ret, void *stream);
 /* ir_gym.indicators_deviation / indicators_extra_len (ir_gym.py:414-420): max_dev[A], extra_len[A] */
 int uaisa_indicators(UaisaHandle *h, float *max_dev, float *extra_len, void *stream);
 /* HOST outputs; synchronises `stream`.  in_range_pairs / cone_evals: pair evaluations and full cone

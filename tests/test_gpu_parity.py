@@ -16,7 +16,7 @@ from uaisa_env.scenario import ScenarioSet, scenario_c1, scenario_c3, scenario_c
 from uaisa_env.vec_env import VecMdin, pack_state, unpack_state
 
 pytestmark = pytest.mark.gpu
-GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+GOLDEN = sorted(p for p in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")) if not os.path.basename(p).startswith("policy_"))
 
 
 def swarm(n=12, rad=1.0, seed=0):

@@ -12,7 +12,7 @@ import _util  # noqa: F401  (path setup)
 import oracle
 from uaisa_env.scenario import ScenarioSet
 
-GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+GOLDEN = sorted(p for p in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")) if not os.path.basename(p).startswith("policy_"))
 STATE = ("pos", "vel", "yaw", "pitch", "wp_idx", "arrive_flag", "dest_flag", "real_len", "max_dev", "extra_len")
 TOL = 1e-9
 

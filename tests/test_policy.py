@@ -1,0 +1,63 @@
+"""The batched actor-critic (SURVEY 8a row a-P1) against golden outputs of the reference rnn_ac
+(oracle/gen_policy_golden.py); CPU everywhere, CUDA with -m gpu; plus state_dict compatibility with shipped checkpoints."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import _util  # noqa: F401
+from uaisa_ppo.policy import rnn_ac
+
+G = np.load(os.path.join(os.path.dirname(__file__), "golden", "policy_rnn_ac.npz"))
+
+
+def _model(device):
+    torch.manual_seed(int(G["seed"]))
+    return rnn_ac().to(device)
+
+
+def _check(device, tol):
+    m = _model(device)
+    obs, cnt, act = (torch.from_numpy(G[k]).to(device) for k in ("obs", "count", "act"))
+    with torch.no_grad():
+        dist, v, logp = m.evaluate(obs, cnt, act)
+    assert np.abs(dist.mean.cpu().numpy() - G["mu"]).max() < tol
+    assert np.abs(dist.stddev.cpu().numpy() - G["std"]).max() < 1e-6
+    assert np.abs(v.cpu().numpy() - G["v"]).max() < tol
+    assert np.abs(logp.cpu().numpy() - G["logp"]).max() < 50 * tol
+    return m
+
+
+def test_policy_matches_reference_golden_cpu():
+    m = _check("cpu", 2e-5)
+    assert sum(p.numel() for p in m.parameters()) == 680991            # SURVEY 8a a-P1
+    keys = set(m.state_dict().keys())
+    for k in ("pi.log_std", "pi.rnn_reader.rnn_net.weight_ih_l0_reverse", "pi.rnn_reader.ln.weight", "pi.net_out.4.bias",
+              "v.v_net.0.weight", "v.rnn_reader.rnn_net.bias_hh_l0"):
+        assert k in keys
+
+
+def test_dense_batching_equals_per_agent_evaluation():
+    """The compaction of multi-row agents must not change anybody's result."""
+    m = _model("cpu")
+    obs, cnt = torch.from_numpy(G["obs"]), torch.from_numpy(G["count"])
+    with torch.no_grad():
+        full = m.features(obs, cnt)
+        for b in range(0, obs.shape[0], 7):
+            one = m.features(obs[b:b + 1], cnt[b:b + 1])
+            assert torch.allclose(one[0], full[b], atol=1e-5)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/train/model_save"), reason="reference checkpoints not present")
+def test_loads_shipped_reference_checkpoint_strict():
+    ck = torch.load("/root/reference/train/model_save/r8_0/r8_0_check_point_0.pt", map_location="cpu", weights_only=False)
+    m = rnn_ac()
+    m.load_state_dict(ck["model_state"], strict=True)
+
+
+@pytest.mark.gpu
+def test_policy_matches_reference_golden_cuda():
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    _check("cuda", 5e-5)

@@ -49,8 +49,13 @@ class rnn_Reader(nn.Module):   # policy_rnn_ac.py:75-168 (mode 'biGRU')
         n = torch.tanh(i_n + r * h_n)
         return (1 - z) * n + z * h
 
-    def forward(self, obs: torch.Tensor, count: torch.Tensor) -> torch.Tensor:
-        """obs [B, 12+9nm] float32, count [B] (rows valid; 0 means one zero row) -> LayerNorm(cat(self, h_f + h_b)) [B, 268]."""
+    def forward(self, obs: torch.Tensor, count: torch.Tensor, multi_cap: int = 0) -> torch.Tensor:
+        """obs [B, 12+9nm] float32, count [B] (rows valid; 0 means one zero row) -> LayerNorm(cat(self, h_f + h_b)) [B, 268].
+
+        multi_cap = 0: agents with >= 2 rows are compacted with ``nonzero`` (exact for any input, one host sync).
+        multi_cap = K > 0: static shapes and no host sync (CUDA-graph capturable): the K agents with the most rows go
+        through the sequential part; exact as long as at most K agents have >= 2 rows -- ``self.overflow`` counts the
+        agents that did not fit so the caller can check it once per epoch."""
         B = obs.shape[0]
         nm = (obs.shape[1] - self.state_dim) // self.input_dim
         self_state = obs[:, : self.state_dim]
@@ -59,16 +64,25 @@ class rnn_Reader(nn.Module):   # policy_rnn_ac.py:75-168 (mode 'biGRU')
         x0 = rows[:, 0] if nm > 0 else obs.new_zeros((B, self.input_dim))
         hsum = self._cell(x0, h0, False) + self._cell(x0, h0, True)          # exact for every agent with <= 1 row
         if nm > 1:
-            multi = torch.nonzero(count > 1).squeeze(-1)                       # (one host sync; few agents)
-            if multi.numel() > 0:
-                r_m, c_m = rows[multi], count[multi].to(torch.long)
-                lmax = int(c_m.max())
-                hf = obs.new_zeros((multi.numel(), self.hidden_dim)); hb = hf.clone()
+            if multi_cap > 0:
+                K = min(int(multi_cap), B)
+                c_top, multi = torch.topk(count.to(torch.int32), K)           # static shape, no sync
+                c_m, lmax = c_top.to(torch.long), nm
+                if getattr(self, "overflow", None) is not None:               # device counter owned by the caller (graph-safe: in place)
+                    self.overflow += ((count > 1).sum() - (c_top > 1).sum()).to(torch.int64)
+            else:
+                multi = torch.nonzero(count > 1).squeeze(-1)                   # (one host sync; few agents)
+                c_m = count[multi].to(torch.long)
+                lmax = int(c_m.max()) if multi.numel() > 0 else 0
+            if lmax > 0:
+                r_m = rows[multi]
+                hf = obs.new_zeros((multi.shape[0], self.hidden_dim)); hb = hf.clone()
+                c_eff = c_m.clamp(min=1)                                       # an agent without rows feeds one zero row
                 for l in range(lmax):                                          # forward direction: x_0 .. x_{len-1}
-                    m = (l < c_m).unsqueeze(-1)
+                    m = (l < c_eff).unsqueeze(-1)
                     hf = torch.where(m, self._cell(r_m[:, l], hf, False), hf)
                 for l in range(lmax - 1, -1, -1):                              # reverse direction: x_{len-1} .. x_0
-                    m = (l < c_m).unsqueeze(-1)
+                    m = (l < c_eff).unsqueeze(-1)
                     hb = torch.where(m, self._cell(r_m[:, l], hb, True), hb)
                 hsum = hsum.index_copy(0, multi, hf + hb)
         return self.ln(torch.cat((self_state, hsum), dim=1))
@@ -84,7 +98,7 @@ class GaussianActor(nn.Module):   # policy_rnn_ac.py:191-235
     def distribution_from_features(self, feat, std_factor=1.0):
         mu = self.net_out(feat)
         std = torch.clamp(std_factor * torch.exp(self.log_std) + 1e-6, min=1e-4, max=10.0)
-        return Normal(mu, std)
+        return Normal(mu, std, validate_args=False)   # validation would synchronise (and break graph capture)
 
 
 class Critic(nn.Module):   # policy_rnn_ac.py:238-257
@@ -103,22 +117,24 @@ class rnn_ac(nn.Module):   # policy_rnn_ac.py:31-72, defaults of train_process.p
         self.pi = GaussianActor(obs_dim, act_dim, hidden_sizes_ac, activation, output_activation, rnn)
         self.v = Critic(obs_dim, hidden_sizes_v, activation, output_activation_v, rnn)     # the reader is SHARED (:46-54)
 
-    def features(self, obs, count):
-        return self.pi.rnn_reader(obs, count)
+    def features(self, obs, count, multi_cap=0):
+        return self.pi.rnn_reader(obs, count, multi_cap)
 
-    def evaluate(self, obs, count, act=None, std_factor=1.0):
+    def evaluate(self, obs, count, act=None, std_factor=1.0, multi_cap=0):
         """-> (Normal, value[B], logp[B] or None); one reader pass feeds both heads."""
-        feat = self.features(obs, count)
+        feat = self.features(obs, count, multi_cap)
         dist = self.pi.distribution_from_features(feat, std_factor)
         v = torch.squeeze(self.v.v_net(feat), -1)
         logp = dist.log_prob(act).sum(-1) if act is not None else None
         return dist, v, logp
 
     @torch.no_grad()
-    def step(self, obs, count, std_factor=1.0):
+    def step(self, obs, count, std_factor=1.0, multi_cap=0):
         """ac.step for all agents (policy_rnn_ac.py:57-69): sampled action increment, value, log-prob (CUDA tensors)."""
-        dist, v, _ = self.evaluate(obs, count, None, std_factor)
-        a = dist.sample()
+        dist, v, _ = self.evaluate(obs, count, None, std_factor, multi_cap)
+        # Normal.sample() = torch.normal(mu, std), which checks std >= 0 with a host synchronisation; mu + std * eps is the
+        # same distribution without it (needed inside a CUDA graph)
+        a = dist.mean + dist.stddev * torch.randn_like(dist.mean)
         return a, v, dist.log_prob(a).sum(-1)
 
     @torch.no_grad()

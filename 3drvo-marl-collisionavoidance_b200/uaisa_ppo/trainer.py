@@ -42,6 +42,8 @@ class PPOConfig:                      # train_process.py:53-63 defaults
     max_grad_norm: float = 2.0        # multi_ppo.py:367
     minibatch: int = 65536            # samples per gradient step (the reference's "batch" is one robot's 300 samples)
     std_factor: float = 1.0
+    use_cuda_graph: bool = True       # capture one rollout step (policy + transform + env step + reset policy + stores)
+    multi_cap_frac: float = 1.0 / 64  # static capacity of the multi-row GRU path in the captured step (fraction of A)
 
 
 def gae(rew, val, cut, gamma, lam):
@@ -74,25 +76,64 @@ class PPOTrainer:
         self.action = torch.empty((A, 3), **f32)
         self.env.reset()
         self.stats = {}
+        self._graph = None
+        self._t = torch.zeros(1, dtype=torch.long, device=self.dev)           # device-side step counter (graph-safe buffer index)
+        self._ndone = torch.zeros((), dtype=torch.int64, device=self.dev)
+        self._last = torch.zeros((), dtype=torch.int64, device=self.dev)
 
     # ------------------------------------------------------------------------------------------------ rollout
     @torch.no_grad()
+    def _one_step(self, epoch_ended: bool, cap: int):
+        """One rollout step writing into buf[..][t] through the device-side counter (multi_ppo.py:193-281)."""
+        env, cfg, b, t = self.env, self.cfg, self.buf, self._t
+        b["obs"].index_copy_(0, t, env.obs.unsqueeze(0)); b["count"].index_copy_(0, t, env.count.unsqueeze(0))      # :217-219 store(obs, ...)
+        a_inc, v, logp = self.ac.step(env.obs, env.count, cfg.std_factor, multi_cap=cap)                           # :196
+        _, a_r = env.action_transform(a_inc, self.action)                                                          # :197-208
+        env.step(self.action)                                                                                      # :210
+        b["act"].index_copy_(0, t, a_r.unsqueeze(0)); b["rew"].index_copy_(0, t, env.reward.unsqueeze(0))
+        b["val"].index_copy_(0, t, v.unsqueeze(0)); b["logp"].index_copy_(0, t, logp.unsqueeze(0))
+        self._ndone += env.done.sum()
+        env.autoreset(max_ep_len=cfg.max_ep_len, epoch_ended=epoch_ended)                                          # :226-281 (+ env_observation)
+        b["cut"].index_copy_(0, t, env.path_cut.unsqueeze(0))
+        t += 1
+
+    @torch.no_grad()
     def rollout(self):
-        """steps_per_epoch env steps of every env (multi_ppo.py:183-281)."""
-        env, cfg, b = self.env, self.cfg, self.buf
+        """steps_per_epoch env steps of every env (multi_ppo.py:183-281).  The T-1 ordinary steps replay one CUDA graph
+        (no host synchronisation inside: the policy's multi-row path runs at a static capacity); the last step of the
+        epoch (full reset, multi_ppo.py:244-264) runs eagerly."""
+        cfg = self.cfg
         T = cfg.steps_per_epoch
-        n_done = torch.zeros((), dtype=torch.int64, device=self.dev)
-        for t in range(T):
-            b["obs"][t].copy_(env.obs); b["count"][t].copy_(env.count)                              # :217-219 store(obs, ...)
-            a_inc, v, logp = self.ac.step(env.obs, env.count, cfg.std_factor)                       # :196
-            env.action_transform(a_inc, self.action, b["act"][t])                                   # :197-208
-            env.step(self.action)                                                                   # :210
-            b["rew"][t].copy_(env.reward); b["val"][t].copy_(v); b["logp"][t].copy_(logp)
-            n_done += env.done.sum()
-            env.autoreset(max_ep_len=cfg.max_ep_len, epoch_ended=(t == T - 1))                      # :226-281 (+ env_observation)
-            b["cut"][t].copy_(env.path_cut)
-        self.stats["collisions"] = n_done
-        return b
+        self._t.zero_(); self._ndone.zero_()
+        rd = self.ac.pi.rnn_reader
+        if getattr(rd, "overflow", None) is None:
+            rd.overflow = torch.zeros((), dtype=torch.int64, device=self.dev)
+        rd.overflow.zero_()
+        cap = max(64, int(self.env.A * cfg.multi_cap_frac)) if cfg.use_cuda_graph else 0
+        if cfg.use_cuda_graph and self._graph is None and T > 1:
+            s = torch.cuda.Stream(device=self.dev)
+            s.wait_stream(torch.cuda.current_stream(self.dev))
+            with torch.cuda.stream(s):            # warm-up on a side stream (allocator, cuBLAS workspaces), then capture
+                self._one_step(False, cap); self._one_step(False, cap)
+            torch.cuda.current_stream(self.dev).wait_stream(s)
+            self._t.zero_(); self._ndone.zero_(); rd.overflow.zero_()
+            self.env.reset()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._one_step(False, cap)
+            self._graph = g
+            self._t.zero_(); self._ndone.zero_(); rd.overflow.zero_()
+            self.env.reset()
+        for t in range(T - 1):
+            if self._graph is not None:
+                self._graph.replay()
+            else:
+                self._one_step(False, cap)
+        self._one_step(True, cap)
+        self.stats["collisions"] = self._ndone
+        if cap and int(rd.overflow) > 0:
+            raise RuntimeError("%d agent-steps had >= 2 neighbour rows beyond the static GRU capacity (%d); raise PPOConfig.multi_cap_frac" % (int(rd.overflow), cap))
+        return self.buf
 
     # ------------------------------------------------------------------------------------------------ update
     def _allreduce_grads(self, params, extra: Optional[torch.Tensor] = None):

@@ -164,6 +164,62 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def run_ppo(args):
+    """--workload ppo: PPO samples/s = E*N*steps_per_epoch / (rollout + GAE + update [+ NCCL all-reduce]) per epoch
+    (SURVEY.md section 8d).  configs[4]: 65536 envs x 4 drones over 8 GPUs = 8192 envs per GPU (weak scaling)."""
+    import torch
+    import torch.distributed as dist
+
+    from uaisa_env.vec_env import VecMdin
+    from uaisa_ppo.trainer import PPOConfig, PPOTrainer
+
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    if args.tf32:
+        torch.backends.cuda.matmul.allow_tf32 = True
+    scn = scenario_c1()
+    E = args.ppo_envs
+    env = VecMdin(scn, E, neighbors_num=NM, device=dev)
+    cfg = PPOConfig(steps_per_epoch=args.ppo_steps)
+    tr = PPOTrainer(env, cfg=cfg)
+    epochs, warm = max(1, min(args.steps, 50)), max(1, min(args.warmup, 3))
+    for _ in range(warm):
+        tr.train_epoch()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    clocks = ClockSampler(local) if rank == 0 else None
+    l0 = env.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    ro = up = 0.0
+    for _ in range(epochs):
+        st = tr.train_epoch(); ro += st["rollout_s"]; up += st["update_s"]
+    e1.record(); torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    clk = clocks.stop() if clocks else None
+    samples = world * env.A * cfg.steps_per_epoch * epochs
+    if rank == 0:
+        line = {"metric": "PPO samples/sec (rollout + GAE + update)", "value": samples / (float(ms.item()) * 1e-3), "unit": "samples/s", "n_gpus": world,
+                "steps": epochs, "warmup": warm, "ms_per_step": float(ms.item()) / epochs, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "tf32" if args.tf32 else "f32", "data": "synthetic",
+                "config": {"workload": "configs[4]: %d envs x 4 drones per GPU, %d steps/epoch, rnn_ac 680991 params, reference PPO hyper-parameters" % (E, cfg.steps_per_epoch),
+                           "minibatch": cfg.minibatch, "pi_iters": cfg.train_pi_iters, "v_iters": cfg.train_v_iters,
+                           "policy": "torch (cuBLAS GEMMs) -- library path; fused forward is next", "rollout_frac": ro / max(ro + up, 1e-9)},
+                "gpu_launches": int(env.launch_count - l0), "clocks": clk, "stats": {k: (float(v) if not isinstance(v, (int, float)) else v) for k, v in tr.stats.items()}}
+        print(json.dumps(line))
+    env.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -175,9 +231,14 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--threads-per-block", type=int, default=0)
+    ap.add_argument("--tf32", action="store_true")
+    ap.add_argument("--ppo-envs", type=int, default=8192)
+    ap.add_argument("--ppo-steps", type=int, default=300)
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    if args.workload == "ppo":
+        return run_ppo(args)
 
     import torch
     import torch.distributed as dist

@@ -49,6 +49,19 @@ def test_dense_batching_equals_per_agent_evaluation():
             assert torch.allclose(one[0], full[b], atol=1e-5)
 
 
+def test_static_capacity_path_is_exact_when_it_fits_and_counts_overflow():
+    m = _model("cpu")
+    obs, cnt = torch.from_numpy(G["obs"]), torch.from_numpy(G["count"])
+    n_multi = int((cnt > 1).sum())
+    rd = m.pi.rnn_reader
+    with torch.no_grad():
+        ref = m.features(obs, cnt)
+        rd.overflow = torch.zeros((), dtype=torch.int64)
+        assert torch.allclose(m.features(obs, cnt, multi_cap=n_multi + 3), ref, atol=1e-6) and int(rd.overflow) == 0
+        m.features(obs, cnt, multi_cap=n_multi - 2)
+        assert int(rd.overflow) == 2
+
+
 @pytest.mark.skipif(not os.path.isdir("/root/reference/train/model_save"), reason="reference checkpoints not present")
 def test_loads_shipped_reference_checkpoint_strict():
     ck = torch.load("/root/reference/train/model_save/r8_0/r8_0_check_point_0.pt", map_location="cpu", weights_only=False)

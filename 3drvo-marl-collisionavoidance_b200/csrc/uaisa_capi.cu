@@ -45,6 +45,11 @@ struct UaisaHandle {
     uint8_t *h_count = nullptr, *h_flags = nullptr;   // flags: done | info | finish, A each
     int32_t *h_nbr = nullptr;
     cudaStream_t h_stream = nullptr;
+    // uaisa_step_host_sparse: device block + pinned host mirror + one captured graph
+    char *sp_dev = nullptr, *sp_host = nullptr; float *sp_hact = nullptr;
+    size_t sp_off_reward = 0, sp_off_self = 0, sp_off_flags = 0, sp_off_rows = 0, sp_bytes = 0, sp_phase1 = 0;
+    int sp_cap = 0, sp_r0 = 0, sp_auto = -1, sp_maxlen = -1;
+    cudaGraphExec_t sp_graph = nullptr;
 };
 
 namespace {
@@ -164,6 +169,9 @@ int uaisa_destroy(UaisaHandle *h) {
     DeviceGuard g(h->device);
     cudaDeviceSynchronize();
     for (void *p : h->allocs) cudaFree(p);
+    if (h->sp_graph) cudaGraphExecDestroy(h->sp_graph);
+    if (h->sp_host) cudaFreeHost(h->sp_host);
+    if (h->sp_hact) cudaFreeHost(h->sp_hact);
     if (h->h_stream) cudaStreamDestroy(h->h_stream);
     delete h;
     return UAISA_OK;
@@ -353,6 +361,81 @@ int uaisa_step_host(UaisaHandle *h, const float *action, float *obs, uint8_t *co
     if (info) CK(cudaMemcpyAsync(info, h->h_flags + A, A, cudaMemcpyDeviceToHost, s));
     if (finish) CK(cudaMemcpyAsync(finish, h->h_flags + 2 * A, A, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
+    return UAISA_OK;
+}
+
+static int sparse_setup(UaisaHandle *h) {
+    const size_t A = h->A; const Params &P = h->P;
+    int rc;
+    if (!h->h_action) {
+        if ((rc = dalloc(h, &h->h_action, A * 3)) || (rc = dalloc(h, &h->h_obs, A * P.obs_dim)) || (rc = dalloc(h, &h->h_reward, A)) ||
+            (rc = dalloc(h, &h->h_count, A)) || (rc = dalloc(h, &h->h_flags, A * 3)) || (rc = dalloc(h, &h->h_nbr, A * (P.nm ? P.nm : 1))))
+            return rc;
+        CK(cudaStreamCreateWithFlags(&h->h_stream, cudaStreamNonBlocking));
+    }
+    auto up16 = [](size_t x) { return (x + 15) & ~size_t(15); };
+    const size_t max_rows = A * (size_t)(P.nm ? P.nm : 1);
+    h->sp_cap = (int)(max_rows * sizeof(UaisaRowRec) <= (size_t(256) << 20) ? max_rows : (size_t(256) << 20) / sizeof(UaisaRowRec));
+    h->sp_r0 = (int)(A / 8 > 256 ? A / 8 : 256); if (h->sp_r0 > h->sp_cap) h->sp_r0 = h->sp_cap;
+    h->sp_off_reward = 16;
+    h->sp_off_self = up16(h->sp_off_reward + 4 * A);
+    h->sp_off_flags = up16(h->sp_off_self + 4 * A * UAISA_OBS_SELF);      // done | info | finish | count
+    h->sp_off_rows = up16(h->sp_off_flags + 4 * A);
+    h->sp_phase1 = h->sp_off_rows + sizeof(UaisaRowRec) * (size_t)h->sp_r0;
+    h->sp_bytes = h->sp_off_rows + sizeof(UaisaRowRec) * (size_t)h->sp_cap;
+    if ((rc = dalloc(h, &h->sp_dev, h->sp_bytes))) return rc;
+    CK(cudaHostAlloc(reinterpret_cast<void **>(&h->sp_host), h->sp_bytes, cudaHostAllocDefault));
+    CK(cudaHostAlloc(reinterpret_cast<void **>(&h->sp_hact), sizeof(float) * A * 3, cudaHostAllocDefault));
+    return UAISA_OK;
+}
+
+int uaisa_step_host_sparse(UaisaHandle *h, const float *action, int32_t auto_reset, int32_t max_ep_len, UaisaHostStep *out) {
+    if (!h || !action || !out) return fail(UAISA_EINVAL, "NULL argument");
+    if (!h->scenarios_set) return fail(UAISA_ESTATE, "uaisa_set_scenarios has not been called");
+    DeviceGuard g(h->device);
+    const size_t A = h->A; const Params &P = h->P;
+    if (!h->sp_dev) { int rc = sparse_setup(h); if (rc) return rc; }
+    cudaStream_t s = h->h_stream;
+    if (!h->sp_graph || h->sp_auto != auto_reset || h->sp_maxlen != max_ep_len) {
+        if (h->sp_graph) { cudaGraphExecDestroy(h->sp_graph); h->sp_graph = nullptr; }
+        CK(cudaStreamSynchronize(s));
+        cudaGraph_t graph = nullptr;
+        CK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+        cudaMemcpyAsync(h->h_action, h->sp_hact, sizeof(float) * A * 3, cudaMemcpyHostToDevice, s);
+        cudaMemsetAsync(h->sp_dev, 0, 16, s);
+        uint8_t *fl = reinterpret_cast<uint8_t *>(h->sp_dev + h->sp_off_flags);
+        Launch L{};
+        L.mode = MODE_STEP; L.T = 1; L.auto_reset = auto_reset ? 1 : 0; L.max_ep_len = max_ep_len;
+        L.action = h->h_action; L.obs = h->h_obs; L.count = fl + 3 * A; L.nbr = h->h_nbr;
+        L.reward = reinterpret_cast<float *>(h->sp_dev + h->sp_off_reward); L.done = fl; L.info = fl + A; L.finish = fl + 2 * A;
+        h->kernel<<<h->grid, h->threads, h->smem, s>>>(h->P, L);
+        uaisa_pack_kernel<<<(unsigned)((A + 127) / 128), 128, 0, s>>>((int)A, P.obs_dim, P.nm, h->h_obs, fl + 3 * A, h->h_nbr,
+                                                                    reinterpret_cast<float *>(h->sp_dev + h->sp_off_self),
+                                                                    h->sp_dev + h->sp_off_rows, reinterpret_cast<int *>(h->sp_dev), h->sp_cap);
+        cudaMemcpyAsync(h->sp_host, h->sp_dev, h->sp_phase1, cudaMemcpyDeviceToHost, s);
+        cudaError_t ce = cudaStreamEndCapture(s, &graph);
+        if (ce != cudaSuccess) return cuda_fail(ce, "cudaStreamEndCapture");
+        ce = cudaGraphInstantiate(&h->sp_graph, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ce != cudaSuccess) return cuda_fail(ce, "cudaGraphInstantiate");
+        h->sp_auto = auto_reset; h->sp_maxlen = max_ep_len;
+    }
+    std::memcpy(h->sp_hact, action, sizeof(float) * A * 3);
+    CK(cudaGraphLaunch(h->sp_graph, s));
+    h->launches += 2;
+    CK(cudaStreamSynchronize(s));
+    int n_rows = *reinterpret_cast<int *>(h->sp_host);
+    if (n_rows > h->sp_cap) return fail(UAISA_EINVAL, "neighbour-row capacity of the host block exceeded");
+    if (n_rows > h->sp_r0) {   // rare: more rows than the first-phase window
+        CK(cudaMemcpyAsync(h->sp_host + h->sp_phase1, h->sp_dev + h->sp_phase1, sizeof(UaisaRowRec) * (size_t)(n_rows - h->sp_r0), cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+    }
+    const uint8_t *fl = reinterpret_cast<const uint8_t *>(h->sp_host + h->sp_off_flags);
+    out->reward = reinterpret_cast<const float *>(h->sp_host + h->sp_off_reward);
+    out->self_obs = reinterpret_cast<const float *>(h->sp_host + h->sp_off_self);
+    out->done = fl; out->info = fl + A; out->finish = fl + 2 * A; out->count = fl + 3 * A;
+    out->rows = reinterpret_cast<const UaisaRowRec *>(h->sp_host + h->sp_off_rows);
+    out->n_rows = n_rows; out->reserved = 0;
     return UAISA_OK;
 }
 

@@ -489,6 +489,29 @@ __global__ void uaisa_gae_kernel(const float *rew, const float *val, const uint8
     }
 }
 
+// Pack kernel of uaisa_step_host_sparse: self part of every observation + the existing neighbour rows as records.
+__global__ void uaisa_pack_kernel(int A, int obs_dim, int nm, const float *obs, const uint8_t *count, const int *nbr, float *self_obs,
+                                  void *rows_v, int *n_rows, int cap) {
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= A) return;
+    const float *o = obs + (size_t)a * obs_dim;
+#pragma unroll
+    for (int q = 0; q < OBS_SELF; q++) self_obs[(size_t)a * OBS_SELF + q] = o[q];
+    const int k = count[a];
+    struct Rec { float v[ROW]; int agent, slot, nbr; };
+    Rec *rows = reinterpret_cast<Rec *>(rows_v);
+    for (int r = 0; r < k; r++) {
+        const int idx = atomicAdd(n_rows, 1);
+        if (idx < cap) {
+            Rec rec;
+#pragma unroll
+            for (int q = 0; q < ROW; q++) rec.v[q] = o[OBS_SELF + ROW * r + q];
+            rec.agent = a; rec.slot = r; rec.nbr = nbr[(size_t)a * nm + r];
+            rows[idx] = rec;
+        }
+    }
+}
+
 #define UAISA_INST(R, T, W) template __global__ void uaisa_env_kernel<R, T, W>(const __grid_constant__ Params, const __grid_constant__ Launch);
 UAISA_INST(4, 128, true) UAISA_INST(10, 128, true) UAISA_INST(16, 128, true)
 UAISA_INST(4, 128, false) UAISA_INST(10, 128, false) UAISA_INST(16, 128, false)

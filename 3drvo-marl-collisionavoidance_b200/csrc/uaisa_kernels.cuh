@@ -388,6 +388,8 @@ template <int MAXR, int MAXT, bool WL>
 __global__ void uaisa_env_kernel(const __grid_constant__ Params P, const __grid_constant__ Launch L);
 __global__ void uaisa_cal_des_kernel(const __grid_constant__ Params P, float *des);
 __global__ void uaisa_action_transform_kernel(const __grid_constant__ Params P, const float *a_inc, float acceler, float *a_inc_rounded, float *action);
+__global__ void uaisa_pack_kernel(int A, int obs_dim, int nm, const float *obs, const uint8_t *count, const int *nbr, float *self_obs,
+                                  void *rows_v, int *n_rows, int cap);
 __global__ void uaisa_gae_kernel(const float *rew, const float *val, const uint8_t *cut, int T, int A, float gamma, float lam, float *adv, float *ret);
 
 }  // namespace uaisa

@@ -12,7 +12,7 @@ SYMBOLS = (
     "uaisa_last_error", "uaisa_version", "uaisa_default_config", "uaisa_create", "uaisa_destroy",
     "uaisa_set_scenarios", "uaisa_step", "uaisa_reset", "uaisa_observe", "uaisa_autoreset", "uaisa_rollout",
     "uaisa_get_state", "uaisa_set_state", "uaisa_cal_des", "uaisa_indicators", "uaisa_get_counters",
-    "uaisa_launch_count", "uaisa_step_host", "uaisa_get_region_clocks", "uaisa_action_transform", "uaisa_gae",
+    "uaisa_launch_count", "uaisa_step_host", "uaisa_get_region_clocks", "uaisa_action_transform", "uaisa_gae", "uaisa_step_host_sparse",
 )
 
 
@@ -26,6 +26,15 @@ class UaisaConfig(C.Structure):
 
 class UaisaStateView(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("pos_yaw", "vel_pitch", "real_len", "max_dev", "extra_len", "wp_flags")]
+
+
+class UaisaRowRec(C.Structure):
+    _fields_ = [("v", C.c_float * 9), ("agent", C.c_int32), ("slot", C.c_int32), ("nbr", C.c_int32)]
+
+
+class UaisaHostStep(C.Structure):
+    _fields_ = [("reward", C.c_void_p), ("self_obs", C.c_void_p), ("done", C.c_void_p), ("info", C.c_void_p), ("finish", C.c_void_p),
+                ("count", C.c_void_p), ("rows", C.c_void_p), ("n_rows", C.c_int32), ("reserved", C.c_int32)]
 
 
 class UaisaError(RuntimeError):
@@ -63,6 +72,7 @@ def lib():
         L.uaisa_launch_count.restype = C.c_int64
         L.uaisa_get_region_clocks.argtypes = [vp, vp, vp]
         L.uaisa_action_transform.argtypes = [vp, vp, C.c_float, vp, vp, vp]
+        L.uaisa_step_host_sparse.argtypes = [vp, vp, i32, i32, C.POINTER(UaisaHostStep)]
         L.uaisa_gae.argtypes = [vp, vp, vp, i32, i32, C.c_float, C.c_float, vp, vp, vp]
         L.uaisa_step_host.argtypes = [vp] * 9 + [i32, i32]
         for name in SYMBOLS:

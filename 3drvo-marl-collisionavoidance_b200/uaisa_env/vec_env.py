@@ -200,6 +200,42 @@ class VecMdin:
         return out
 
 
+    ROW_DTYPE = np.dtype([("v", np.float32, (9,)), ("agent", np.int32), ("slot", np.int32), ("nbr", np.int32)])
+
+    def step_host_sparse(self, action: np.ndarray, auto_reset: bool = False, max_ep_len: int = 300) -> dict:
+        """Latency-optimised host round trip (uaisa_step_host_sparse): float32 [A,3] numpy action in; a dict of numpy
+        VIEWS into library-owned pinned memory out (valid until the next call): reward[A], self_obs[A,12], done/info/
+        finish/count[A], rows[n_rows] (structured: v[9], agent, slot, nbr)."""
+        if action.dtype != np.float32 or action.size != self.A * 3 or not action.flags.c_contiguous:
+            raise ValueError("action must be a C-contiguous float32 array with E*N*3 elements")
+        hs = self._hs if hasattr(self, "_hs") else _capi.UaisaHostStep()
+        with torch.cuda.device(self.device):
+            _capi.check(self.L.uaisa_step_host_sparse(self.h, action.ctypes.data_as(C.c_void_p), int(auto_reset), int(max_ep_len), C.byref(hs)))
+        if not hasattr(self, "_hs"):
+            self._hs = hs
+            A = self.A
+            view = lambda p, n, dt: np.frombuffer((C.c_char * (n * np.dtype(dt).itemsize)).from_address(p), dtype=dt, count=n)  # noqa: E731
+            rows_cap = max(1, A * max(self.nm, 1))
+            self._hv = {"reward": view(hs.reward, A, np.float32), "self_obs": view(hs.self_obs, A * 12, np.float32).reshape(A, 12),
+                        "done": view(hs.done, A, np.uint8), "info": view(hs.info, A, np.uint8), "finish": view(hs.finish, A, np.uint8),
+                        "count": view(hs.count, A, np.uint8), "_rows_all": view(hs.rows, min(rows_cap, (256 << 20) // 48), self.ROW_DTYPE)}
+        out = dict(self._hv)
+        out["rows"] = out.pop("_rows_all")[: hs.n_rows]
+        return out
+
+    @staticmethod
+    def ragged_from_sparse(out: dict, nm: int):
+        """Sparse host step -> the reference's ragged observation list (12 + 9*max(k,1) values per agent)."""
+        A = out["self_obs"].shape[0]
+        cnt = out["count"]
+        obs = [np.zeros(12 + 9 * max(int(cnt[a]), 1), np.float32) for a in range(A)]
+        for a in range(A):
+            obs[a][:12] = out["self_obs"][a]
+        for r in out["rows"]:
+            obs[int(r["agent"])][12 + 9 * int(r["slot"]): 21 + 9 * int(r["slot"])] = r["v"]
+        return obs
+
+
 # helpers to move between the packed fp32 device state and the oracle's field names -------------------
 def unpack_state(st: dict) -> dict:
     """Device state dict -> numpy fields named like oracle.STATE_FIELDS (values are exact fp32->fp64)."""

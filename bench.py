@@ -325,33 +325,29 @@ def main():
     s1.record(); torch.cuda.synchronize()
     single_ms = s0.elapsed_time(s1) / Ks
 
-    # ---- end to end through the host-buffer C-ABI call: pinned host action in, all outputs back, every step
-    Ke = args.e2e_steps or min(K, 200 if A <= 65536 else 20)
-    pin = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory()  # noqa: E731
-    h_act = pin((A, 3), torch.float32)
-    h_out_t = {"obs": pin((A, env.obs_dim), torch.float32), "count": pin((A,), torch.uint8), "nbr": pin((A, NM), torch.int32),
-               "reward": pin((A,), torch.float32), "done": pin((A,), torch.uint8), "info": pin((A,), torch.uint8), "finish": pin((A,), torch.uint8)}
-    h_out = {k: v.numpy() for k, v in h_out_t.items()}
+    # ---- end to end through the host C-ABI call (uaisa_step_host_sparse): every step the action is produced on the
+    # host and copied H2D, and the step's complete result (rewards, flags, the 12 self values of every observation and
+    # every neighbour row that exists) is copied D2H and read on the host
+    Ke = args.e2e_steps or min(K, 400 if A <= 65536 else 40)
     h_acts = synth_actions(rng, 8, A)
     for t in range(3):
-        h_act.numpy()[...] = h_acts[t % 8]
-        env.step_host(h_act.numpy(), h_out, auto_reset=True, max_ep_len=MAX_EP_LEN)
+        env.step_host_sparse(h_acts[t % 8], auto_reset=True, max_ep_len=MAX_EP_LEN)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
+    rows_total = 0
     te0 = time.perf_counter()
     for t in range(Ke):
-        h_act.numpy()[...] = h_acts[t % 8]          # the step's input is produced on the host
-        env.step_host(h_act.numpy(), h_out, auto_reset=True, max_ep_len=MAX_EP_LEN)
-        _ = float(h_out["reward"][0])               # the result is read on the host
-    torch.cuda.synchronize()
+        r = env.step_host_sparse(h_acts[t % 8], auto_reset=True, max_ep_len=MAX_EP_LEN)
+        _ = float(r["reward"][0])                   # the result is read on the host
+        rows_total += len(r["rows"])
     e2e_s = time.perf_counter() - te0
     te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = world * A * Ke / float(te.item())
     h2d = A * 3 * 4
-    d2h = A * (env.obs_dim * 4 + 1 + NM * 4 + 4 + 3)
+    d2h = 16 + A * (4 + 48 + 4) + max(256, A // 8) * 48      # first-phase block of the sparse host step (header, reward, self obs, flags+count, row window)
 
     if rank == 0:
         peaks = {}
@@ -380,7 +376,10 @@ def main():
                          "peak_source": peak_src},
             "single_step_launch": {"value": world * A / (single_ms * 1e-3), "unit": "agent-steps/s", "ms_per_step": single_ms,
                                    "note": "one launch per env step (closed-loop use), device-timed over %d steps" % Ks},
-            "e2e": {"value": e2e_value, "unit": "agent-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke},
+            "e2e": {"value": e2e_value, "unit": "agent-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke,
+                    "api": "uaisa_step_host_sparse: one CUDA graph per step (H2D action, env kernel, pack kernel, D2H result block); "
+                           "result = reward/done/info/finish/count + 12 self values per agent + every existing neighbour row",
+                    "neighbour_rows_per_step": rows_total / max(Ke, 1)},
             "gpu_launches": int(launches), "clocks": clk,
         }
         if cb:

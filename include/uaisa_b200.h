@@ -156,6 +156,29 @@ int uaisa_get_region_clocks(UaisaHandle *h, int64_t *out16, void *stream);
 int uaisa_step_host(UaisaHandle *h, const float *action, float *obs, uint8_t *count, int32_t *nbr, float *reward,
                     uint8_t *done, uint8_t *info, uint8_t *finish, int32_t auto_reset, int32_t max_ep_len);
 
+/* ---- latency-optimised host round trip ------------------------------------------------------------------------
+ * One env step with HOST action in / HOST results out, returned in the reference's own ragged spirit: the 12 self
+ * values of every observation plus only the neighbour rows that exist (an observation is 12 + 9*max(k,1) values in
+ * the reference, ir_gym.py:203-229; the fixed-slot padding is never shipped over PCIe).  Internally ONE CUDA graph
+ * (H2D action, env kernel, pack kernel, D2H block) is launched per call.  Pointers in `out` refer to library-owned
+ * pinned host memory and stay valid until the next call on this handle.  Synchronous. */
+typedef struct UaisaRowRec {
+    float v[9];        /* apex(3) rel_pos(3) alpha min_dis 1/(t+0.2), rounded to 2 dp */
+    int32_t agent;     /* a = env * N + drone */
+    int32_t slot;      /* position r of the row in that agent's observation (0 = least urgent, count-1 = most urgent) */
+    int32_t nbr;       /* in-env drone index of the neighbour */
+} UaisaRowRec;
+typedef struct UaisaHostStep {
+    const float *reward;       /* [A] */
+    const float *self_obs;     /* [A][12] */
+    const uint8_t *done, *info, *finish, *count;   /* [A] each */
+    const UaisaRowRec *rows;   /* [n_rows], unordered */
+    int32_t n_rows;
+    int32_t reserved;
+} UaisaHostStep;
+int uaisa_step_host_sparse(UaisaHandle *h, const float *action /* HOST [A][3] */, int32_t auto_reset, int32_t max_ep_len,
+                           UaisaHostStep *out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -194,3 +194,33 @@ def test_step_host_matches_device_step():
         for k in out:
             assert np.array_equal(out[k], getattr(b, k).cpu().numpy(), equal_nan=(k == "reward")), (t, k)
     a.close(); b.close()
+
+
+def test_step_host_sparse_matches_device_step():
+    """uaisa_step_host_sparse (one CUDA graph, ragged results) carries exactly the information of the dense step."""
+    scn = swarm(12, 1.0, 11)
+    a = VecMdin(scn, 20, neighbors_num=10); b = VecMdin(scn, 20, neighbors_num=10)
+    a.reset(); b.reset()
+    rng = np.random.default_rng(4)
+    rows_seen = 0
+    for t in range(40):
+        st = unpack_state(b.get_state())
+        act = _util.training_like_actions(rng, st["vel"]).astype(np.float32) if t % 2 else np.round(rng.uniform(-1, 1, (a.A, 3)), 2).astype(np.float32)
+        out = a.step_host_sparse(act, auto_reset=True, max_ep_len=15)
+        b.rollout(torch.from_numpy(act).cuda().view(1, -1, 3), {"obs": b.obs.view(1, b.A, -1), "count": b.count.view(1, -1), "nbr": b.nbr.view(1, b.A, -1),
+                                                                 "reward": b.reward.view(1, -1), "done": b.done.view(1, -1), "info": b.info.view(1, -1),
+                                                                 "finish": b.finish.view(1, -1)}, auto_reset=True, max_ep_len=15)
+        obs = b.obs.cpu().numpy(); cnt = b.count.cpu().numpy(); nbr = b.nbr.cpu().numpy()
+        assert np.array_equal(out["reward"], b.reward.cpu().numpy(), equal_nan=True)
+        for k in ("done", "info", "finish"):
+            assert np.array_equal(out[k], getattr(b, k).cpu().numpy()), (t, k)
+        assert np.array_equal(out["count"], cnt) and np.array_equal(out["self_obs"], obs[:, :12])
+        assert len(out["rows"]) == int(cnt.sum())
+        for r in out["rows"]:
+            ag, sl = int(r["agent"]), int(r["slot"])
+            assert sl < cnt[ag] and np.array_equal(r["v"], obs[ag, 12 + 9 * sl: 21 + 9 * sl]) and int(r["nbr"]) == nbr[ag, sl]
+        rows_seen += len(out["rows"])
+        rag = VecMdin.ragged_from_sparse(out, 10)
+        assert all(rag[k].shape[0] == 12 + 9 * max(int(cnt[k]), 1) and np.array_equal(rag[k], obs[k, : rag[k].shape[0]]) for k in range(a.A))
+    assert rows_seen > 50
+    a.close(); b.close()

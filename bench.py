@@ -230,6 +230,7 @@ def main():
     ap.add_argument("--chunk", type=int, default=0, help="env steps per rollout launch (0 = auto)")
     ap.add_argument("--e2e-steps", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-sat", action="store_true")
     ap.add_argument("--threads-per-block", type=int, default=0)
     ap.add_argument("--tf32", action="store_true")
     ap.add_argument("--ppo-envs", type=int, default=8192)
@@ -304,6 +305,7 @@ def main():
         dist.barrier()
     ms = t_start.elapsed_time(t_end)
     launches = env.launch_count - l0
+    tpc = env.cfg.threads_per_block
     kern_ms = sum(e0.elapsed_time(e1) for e0, e1, _ in evs)
     clk = clocks.stop() if clocks else None
     tms = torch.tensor([ms], dtype=torch.float64, device=dev)
@@ -349,6 +351,40 @@ def main():
     h2d = A * 3 * 4
     d2h = 16 + A * (4 + 48 + 4) + max(256, A // 8) * 48      # first-phase block of the sparse host step (header, reward, self obs, flags+count, row window)
 
+    # ---- side measurement at the saturating size (the default workload is 4096 agents = 128 warps on 148 SMs, i.e.
+    # latency-bound by construction; SURVEY.md section 8d asks for the exact BASELINE config AND the saturating size)
+    sat = None
+    if args.workload == "c2" and not args.no_sat:
+        env.close()
+        del out, acts
+        torch.cuda.empty_cache()
+        sdesc, sscn, sE = workload("sat")
+        senv = VecMdin(sscn, sE, neighbors_num=NM, device=dev)
+        senv.reset()
+        sA, sT, sK = senv.A, 10, 40
+        sacts = torch.from_numpy(synth_actions(rng, sT, sA)).to(dev)
+        sout = {"obs": torch.empty((sT, sA, senv.obs_dim), dtype=torch.float32, device=dev), "count": torch.empty((sT, sA), dtype=torch.uint8, device=dev),
+                "nbr": torch.empty((sT, sA, NM), dtype=torch.int32, device=dev), "reward": torch.empty((sT, sA), dtype=torch.float32, device=dev),
+                "done": torch.empty((sT, sA), dtype=torch.uint8, device=dev), "info": torch.empty((sT, sA), dtype=torch.uint8, device=dev),
+                "finish": torch.empty((sT, sA), dtype=torch.uint8, device=dev)}
+        senv.rollout(sacts, sout, auto_reset=True, max_ep_len=MAX_EP_LEN)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        q0.record()
+        for _ in range(sK // sT):
+            senv.rollout(sacts, sout, auto_reset=True, max_ep_len=MAX_EP_LEN)
+        q1.record(); torch.cuda.synchronize()
+        sms = torch.tensor([q0.elapsed_time(q1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(sms, op=dist.ReduceOp.MAX)
+        sval = world * sA * sK / (float(sms.item()) * 1e-3)
+        sat = {"workload": sdesc, "value": sval, "unit": "agent-steps/s", "ms_per_step": float(sms.item()) / sK, "steps": sK, "steps_per_launch": sT,
+               "per_gpu_hbm_gbs": sval / world * BYTES_PER_AGENT_STEP / 1e9}
+        senv.close()
+        env = None
+
     if rank == 0:
         peaks = {}
         try:
@@ -360,6 +396,14 @@ def main():
         avg_launch_ms = kern_ms / max(len(evs), 1)
         steps_per_launch = K / max(len(evs), 1)
         achieved = BYTES_PER_AGENT_STEP * A * steps_per_launch / (avg_launch_ms * 1e-3) / 1e9
+        traffic = None
+        try:   # dram__bytes_read+write of one captured launch (profiles/traffic.json, from ncu --set full), scaled per agent-step
+            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+            traffic = tj["dram_bytes_per_agent_step"] * A * steps_per_launch
+        except Exception:
+            pass
+        if sat is not None:
+            sat["roofline_frac"] = sat["per_gpu_hbm_gbs"] / peak
         cb = None
         if not args.no_cpu:
             cb, _, _ = cpu_baseline(scn, min(E, 16384), seconds=12.0)
@@ -368,10 +412,10 @@ def main():
             "steps": K, "warmup": W, "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": desc, "envs_per_gpu": E, "drones_per_env": N, "nm": NM, "auto_reset": "trainer policy (multi_ppo.py:221-281), max_ep_len=300",
-                       "actions": "U(-1,1)^3 rounded to 2 dp, resident in HBM", "steps_per_launch": steps_per_launch, "threads_per_cta": env.cfg.threads_per_block or "auto",
+                       "actions": "U(-1,1)^3 rounded to 2 dp, resident in HBM", "steps_per_launch": steps_per_launch, "threads_per_cta": tpc or "auto",
                        "l2": "flushed (256 MiB write) before the timed region; per-launch outputs %.0f MB" % (per_step_out * steps_per_launch / 1e6),
                        "state": "fp32 SoA in HBM, fp64 arithmetic"},
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "kernel": "uaisa_env_kernel", "bytes_per_agent_step": BYTES_PER_AGENT_STEP, "avg_launch_ms": avg_launch_ms,
                          "peak_source": peak_src},
             "single_step_launch": {"value": world * A / (single_ms * 1e-3), "unit": "agent-steps/s", "ms_per_step": single_ms,
@@ -384,8 +428,11 @@ def main():
         }
         if cb:
             line["cpu_baseline"] = cb
+        if sat is not None:
+            line["saturating"] = sat
         print(json.dumps(line))
-    env.close()
+    if env is not None:
+        env.close()
     if world > 1:
         dist.destroy_process_group()
 

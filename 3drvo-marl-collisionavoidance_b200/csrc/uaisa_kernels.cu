@@ -242,21 +242,27 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 128 ? UAISA_MINB128 : 1)) uaisa
                 // Stage 1 runs over a chunk of up to 32 neighbours with no divergent work and yields a mask of the
                 // pairs whose cone must be evaluated; stage 2 walks that mask (rvo_inter.py:29,67 map both).
                 for (int jb = 0; jb < N; jb += 32) {
-                    unsigned cand = 0, slow = 0;
+                    unsigned cand = 0, slow = 0, near = 0;
                     const int jn = min(32, N - jb);
 #pragma unroll 4
-                    for (int jj = 0; jj < jn; jj++) {
+                    for (int jj = 0; jj < jn; jj++) {            // stage 1a: who is within range (branch-free, overlapped)
                         const int j = jb + jj;
-                        const int bits = (j == k) ? 0 : pair_gate_fast(P, d.px, d.py, d.pz, d.vx, d.vy, d.vz, C.radius, sx + lbase + j, threads);
-                        n_rng += (bits & PB_EVAL) ? 1u : 0u;
+                        const int bits = (j == k) ? 0 : pair_range_fast(P, d.px, d.py, d.pz, sx + lbase + j, threads);
+                        near |= (bits & PB_EVAL) ? (1u << jj) : 0u;
+                        slow |= (bits & PB_SLOW) ? (1u << jj) : 0u;
+                    }
+                    n_rng += __popc(near);
+                    for (unsigned m = near; m; m &= m - 1) {     // stage 1b: collision / moving-away gates of the near ones
+                        const int jj = __ffs(m) - 1;
+                        const int bits = pair_near_fast(P, d.px, d.py, d.pz, d.vx, d.vy, d.vz, C.radius, sx + lbase + jb + jj, threads);
                         col |= (bits & PB_COL) != 0;
                         cand |= (bits & PB_FULL) ? (1u << jj) : 0u;
                         slow |= (bits & PB_SLOW) ? (1u << jj) : 0u;
                     }
-                    for (unsigned m = slow; m; m &= m - 1) {    // squared distance inside a guard band: exact comparison
+                    for (unsigned m = slow; m; m &= m - 1) {     // a squared distance inside a guard band: exact comparisons
                         const int jj = __ffs(m) - 1;
                         const int bits = pair_gate(P, d.px, d.py, d.pz, d.vx, d.vy, d.vz, C.radius, sx + lbase + jb + jj, threads);
-                        n_rng += (bits & PB_EVAL) ? 1u : 0u;
+                        n_rng += ((bits & PB_EVAL) && !((near >> jj) & 1u)) ? 1u : 0u;
                         col |= (bits & PB_COL) != 0;
                         cand |= (bits & PB_FULL) ? (1u << jj) : 0u;
                     }

@@ -239,24 +239,29 @@ __device__ __forceinline__ int pair_gate(const Params &P, double x, double y, do
     return (dotp <= 0.0) ? PB_EVAL : (PB_EVAL | PB_FULL);
 }
 
-// Branch-free form of pair_gate for the hot loop: straight-line arithmetic + predicate logic so that the gates of
-// several neighbours overlap (no branch has to resolve between them).  PB_SLOW is returned for the (1e-14-wide)
-// cases where a squared distance falls inside a guard band; the caller re-runs those few pairs through pair_gate.
+// Branch-free forms of pair_gate for the hot loop: straight-line arithmetic + predicate logic, so the gates of
+// several neighbours overlap (no branch has to resolve between them).  PB_SLOW marks the (1e-14-wide) cases where a
+// squared distance falls inside a guard band; the caller re-runs those few pairs through the exact pair_gate.
 constexpr int PB_SLOW = 16;
-__device__ __forceinline__ int pair_gate_fast(const Params &P, double x, double y, double z, double vx, double vy, double vz,
+// stage 1a: neighbour-range test only (rvo_inter.py:89-97) -> PB_EVAL (in range), PB_SLOW, or 0
+__device__ __forceinline__ int pair_range_fast(const Params &P, double x, double y, double z, const double *so, int st) {
+    const double mx = so[0], my = so[st], mz = so[2 * st];
+    const double rel_x = mx - x, rel_y = my - y, rel_z = mz - z;
+    const double s2 = np_dot3(rel_x, rel_y, rel_z, rel_x, rel_y, rel_z);
+    const bool same = (x == mx) & (y == my) & (z == mz);
+    const bool in = s2 < P.nbr2_lo, amb = !(in | (s2 > P.nbr2_hi));
+    return same ? 0 : (amb ? PB_SLOW : (in ? PB_EVAL : 0));
+}
+// stage 1b, for a pair known to be in range: collision test + "moving away" gate (rvo_inter.py:131-161)
+__device__ __forceinline__ int pair_near_fast(const Params &P, double x, double y, double z, double vx, double vy, double vz,
                                               double r, const double *so, int st) {
     const double mx = so[0], my = so[st], mz = so[2 * st], mr = so[6 * st];
     const double rel_x = mx - x, rel_y = my - y, rel_z = mz - z;
-    const double s2 = np_dot3(rel_x, rel_y, rel_z, rel_x, rel_y, rel_z);
     const double d2 = rel_y * rel_y + rel_x * rel_x + rel_z * rel_z;
     const double Rc = P.env_train ? r + mr : r - P.exp_radius + mr, c2 = Rc * Rc;
     const double dotp = vx * rel_x + vy * rel_y + vz * rel_z;
-    const bool same = (x == mx) & (y == my) & (z == mz);
-    const bool in = s2 < P.nbr2_lo, rng_amb = !(in | (s2 > P.nbr2_hi));
-    const bool col = d2 < c2 * (1.0 - 1e-14), col_amb = !(col | (d2 > c2 * (1.0 + 1e-14)));
-    const bool slow = !same & (rng_amb | ((in | rng_amb) & col_amb));
-    const bool ev = !same & in & !slow;
-    return slow ? PB_SLOW : ((ev ? PB_EVAL : 0) | ((ev & col) ? PB_COL : 0) | ((ev & !col & (dotp > 0.0)) ? PB_FULL : 0));
+    const bool col = d2 < c2 * (1.0 - 1e-14), amb = !(col | (d2 > c2 * (1.0 + 1e-14)));
+    return amb ? PB_SLOW : (col ? PB_COL : ((dotp > 0.0) ? PB_FULL : 0));
 }
 
 // Stage 2 of a pair: the cone (rvo_inter.py:165-196, vel_obs3D.py:8-66,145-182), itself split in three so that the

@@ -66,6 +66,7 @@ class PPOTrainer:
         if self.world > 1:             # same parameters everywhere (the reference's intended bcast, multi_ppo.py:179-181)
             for p in self.ac.parameters():
                 dist.broadcast(p.data, 0)
+            torch.manual_seed(seed + 1000 * dist.get_rank())   # same weights, different exploration noise per shard
         self.pi_opt = torch.optim.Adam(self.ac.pi.parameters(), lr=self.cfg.pi_lr)     # multi_ppo.py:115-116
         self.vf_opt = torch.optim.Adam(self.ac.v.parameters(), lr=self.cfg.vf_lr)
         T, A, D = self.cfg.steps_per_epoch, env.A, env.obs_dim

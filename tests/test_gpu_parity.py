@@ -224,3 +224,45 @@ def test_step_host_sparse_matches_device_step():
         assert all(rag[k].shape[0] == 12 + 9 * max(int(cnt[k]), 1) and np.array_equal(rag[k], obs[k, : rag[k].shape[0]]) for k in range(a.A))
     assert rows_seen > 50
     a.close(); b.close()
+
+
+@pytest.mark.parametrize("name,E", [("c2", 1024), ("c3", 4096), ("c4", 64), ("c5", 65536)])
+def test_full_size_properties(name, E):
+    """BASELINE.json's full sizes, through size-independent properties: (1) every env that shares a scenario and an
+    action stream computes bitwise the same thing wherever it sits in the batch (CTA / warp / lane position);
+    (2) that common result equals the oracle's for one such env; (3) a T-step rollout equals T single steps."""
+    scn = {"c2": scenario_c1, "c5": scenario_c1, "c3": lambda: scenario_c3(seed=0, n_scenarios=1), "c4": lambda: scenario_c4(seed=0, n_scenarios=1)}[name]()
+    N, T, nm = scn.N, 6, 10
+    rng = np.random.default_rng(7)
+    acts1 = np.round(rng.uniform(-1, 1, (T, 1, N, 3)), 2).astype(np.float32)
+    acts = np.broadcast_to(acts1, (T, E, N, 3)).reshape(T, E * N, 3).copy()
+    env = VecMdin(scn, E, neighbors_num=nm); env.reset()
+    ob = oracle.OracleBatch(scn, 1, nm=nm); ob.reset()
+    ep = np.zeros(N, np.int32)
+    A = E * N
+    for t in range(T):
+        ob.set_state({k: v[:N] for k, v in unpack_state(env.get_state()).items()})
+        env.step(torch.from_numpy(acts[t]).cuda())
+        oo, orw, od, oi, of = ob.step(acts1[t, 0].astype(np.float64))
+        for k in ("obs", "reward", "done", "info", "finish", "count", "nbr"):
+            g = getattr(env, k).view(E, N, -1)
+            assert torch.equal(torch.nan_to_num(g.float(), 7.0), torch.nan_to_num(g[:1].float(), 7.0).expand_as(g)), (t, k)
+        assert np.array_equal(env.done.view(E, N)[E - 1].cpu().numpy(), od) and np.array_equal(env.count.view(E, N)[E // 2].cpu().numpy(), ob.count.astype(np.uint8))
+        assert np.array_equal(env.obs.view(E, N, -1)[E - 1].cpu().numpy(), f32(oo))
+        assert np.allclose(env.reward.view(E, N)[0].cpu().numpy(), f32(orw), rtol=1e-5, atol=1e-5, equal_nan=True)
+        env.autoreset(max_ep_len=4)
+        ob.set_state({k: v[:N] for k, v in unpack_state(env.get_state()).items()})    # oracle follows the device state (teacher forcing)
+    # rollout == repeated steps at full size (checksums of every output)
+    env2 = VecMdin(scn, E, neighbors_num=nm); env2.reset()
+    env3 = VecMdin(scn, E, neighbors_num=nm); env3.reset()
+    rew = torch.zeros((T, A), device="cuda"); cnt = torch.zeros((T, A), dtype=torch.uint8, device="cuda")
+    env2.rollout(torch.from_numpy(acts).cuda(), {"reward": rew, "count": cnt}, auto_reset=True, max_ep_len=4)
+    for t in range(T):
+        env3.step(torch.from_numpy(acts[t]).cuda())
+        assert torch.equal(torch.nan_to_num(env3.reward, 7.0), torch.nan_to_num(rew[t], 7.0)), t
+        env3.autoreset(max_ep_len=4)
+        assert torch.equal(env3.count, cnt[t]), t
+    s2, s3 = env2.get_state(), env3.get_state()
+    assert all(torch.equal(s2[k], s3[k]) for k in s2)
+    for e in (env, env2, env3):
+        e.close()

@@ -137,7 +137,8 @@ int uaisa_create(const UaisaConfig *cfg, UaisaHandle **out) {
     h->grid = (E + P.envs_per_cta - 1) / P.envs_per_cta;
     const int need = cfg->nm < N - 1 ? cfg->nm : N - 1;
     const int maxr = threads > 256 ? 16 : (need <= 4 ? 4 : need <= 10 ? 10 : 16);
-    h->smem = sizeof(double) * 8 * threads + sizeof(int) * 2 * P.envs_per_cta + 16 + 2 * 4096   // + TMA fill tiles
+    P.tile0_bytes = ((32 * P.obs_dim * 4) + 15) & ~15; P.tile1_bytes = ((32 * (P.nm ? P.nm : 1) * 4) + 15) & ~15;
+    h->smem = sizeof(double) * 8 * threads + sizeof(int) * 2 * P.envs_per_cta + 16 + P.tile0_bytes + P.tile1_bytes   // + TMA fill tiles
               + (maxr > 4 ? (size_t)threads * maxr * 24 : 0);                                     // + shared top-nm lists
     const bool wl = (N <= 32) && (32 % N == 0) && threads <= 128;   // every env inside one warp
     if (threads > 256) h->kernel = uaisa_env_kernel<16, 1024, false>;

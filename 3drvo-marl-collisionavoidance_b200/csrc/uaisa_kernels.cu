@@ -41,15 +41,14 @@ __device__ __forceinline__ void fill_out(uint32_t *__restrict__ dst, int n, uint
 // ---- TMA bulk stores (cp.async.bulk shared::cta -> global): the zero padding that makes up most of every
 // observation row is streamed to HBM by the copy engine from a constant shared-memory tile, off the warps'
 // critical path and out of the LSU store queue.
-constexpr int FILL_TILE = 4096;   // bytes of each constant tile (zeros / 0xFF)
 __device__ __forceinline__ void bulk_store(void *gdst, const void *ssrc, uint32_t bytes) {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"((uint32_t)__cvta_generic_to_shared(ssrc)), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 // called by ONE lane: fill [dst, dst+bytes) from the constant tile (dst 16-byte aligned, bytes % 16 == 0)
-__device__ __forceinline__ void bulk_fill(char *dst, const void *tile, int bytes) {
-    for (int off = 0; off < bytes; off += FILL_TILE) bulk_store(dst + off, tile, (uint32_t)min(FILL_TILE, bytes - off));
+__device__ __forceinline__ void bulk_fill(char *dst, const void *tile, int tile_bytes, int bytes) {
+    for (int off = 0; off < bytes; off += tile_bytes) bulk_store(dst + off, tile, (uint32_t)min(tile_bytes, bytes - off));   // normally ONE op
 }
 
 enum Phase : int { PH_A = 0, PH_B = 1, PH_OBS = 2 };
@@ -82,10 +81,11 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 128 ? UAISA_MINB128 : 1)) uaisa
     int *ssel = senv + P.envs_per_cta;                                           // [envs_per_cta] obs selected
     // constant tiles for the TMA fills (WL only), 16-byte aligned after the arrays above
     uint4 *tile0 = reinterpret_cast<uint4 *>((reinterpret_cast<uintptr_t>(ssel + P.envs_per_cta) + 15) & ~uintptr_t(15));
-    uint4 *tile1 = tile0 + FILL_TILE / 16;
-    void *stop = tile1 + FILL_TILE / 16;               // top-nm lists of the MAXR > 4 instantiations
+    uint4 *tile1 = tile0 + P.tile0_bytes / 16;           // tile0: one warp's 32 observation rows of zeros; tile1: 32 rows of nbr = -1
+    void *stop = tile1 + P.tile1_bytes / 16;            // top-nm lists of the MAXR > 4 instantiations
     if (WL) {
-        for (int i = threadIdx.x; i < FILL_TILE / 16; i += blockDim.x) { tile0[i] = make_uint4(0u, 0u, 0u, 0u); tile1[i] = make_uint4(~0u, ~0u, ~0u, ~0u); }
+        for (int i = threadIdx.x; i < P.tile0_bytes / 16; i += blockDim.x) tile0[i] = make_uint4(0u, 0u, 0u, 0u);
+        for (int i = threadIdx.x; i < P.tile1_bytes / 16; i += blockDim.x) tile1[i] = make_uint4(~0u, ~0u, ~0u, ~0u);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the copy engine
         __syncthreads();
     }
@@ -142,12 +142,12 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 128 ? UAISA_MINB128 : 1)) uaisa
                     const size_t abase = (size_t)t * A + (size_t)env0 * N + w0;
                     if (L.obs) {
                         char *dst = reinterpret_cast<char *>(L.obs + abase * P.obs_dim); const int bytes = nw * P.obs_dim * 4;
-                        if (((reinterpret_cast<uintptr_t>(dst) | (uintptr_t)bytes) & 15) == 0) { if (lane == 0) bulk_fill(dst, tile0, bytes); }
+                        if (((reinterpret_cast<uintptr_t>(dst) | (uintptr_t)bytes) & 15) == 0) { if (lane == 0) bulk_fill(dst, tile0, P.tile0_bytes, bytes); }
                         else fill_out(reinterpret_cast<uint32_t *>(dst), bytes >> 2, 0u, lane, 32);
                     }
                     if (L.nbr) {
                         char *dst = reinterpret_cast<char *>(L.nbr + abase * P.nm); const int bytes = nw * P.nm * 4;
-                        if (((reinterpret_cast<uintptr_t>(dst) | (uintptr_t)bytes) & 15) == 0) { if (lane == 0) bulk_fill(dst, tile1, bytes); }
+                        if (((reinterpret_cast<uintptr_t>(dst) | (uintptr_t)bytes) & 15) == 0) { if (lane == 0) bulk_fill(dst, tile1, P.tile1_bytes, bytes); }
                         else fill_out(reinterpret_cast<uint32_t *>(dst), bytes >> 2, ~0u, lane, 32);
                     }
                     if (lane == 0) bulk_commit();

@@ -35,6 +35,7 @@ struct Params {
     // geometry
     int E, N, W, M, nm, obs_dim;
     int envs_per_cta, threads;
+    int tile0_bytes, tile1_bytes;   // constant smem tiles behind the TMA fills (zeros / 0xFF), multiples of 16
     int env_train, count_pairs;
     // hyper-parameters (reference constructor defaults, see include/uaisa_b200.h)
     double goal_thr, max_acc, max_ang, dt, vel_max, nbr_range, bld_range, bld_zgate, ctime, delta_t, exp_radius;

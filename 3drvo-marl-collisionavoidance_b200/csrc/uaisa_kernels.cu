@@ -83,12 +83,18 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 128 ? UAISA_MINB128 : 1)) uaisa
     uint4 *tile0 = reinterpret_cast<uint4 *>((reinterpret_cast<uintptr_t>(ssel + P.envs_per_cta) + 15) & ~uintptr_t(15));
     uint4 *tile1 = tile0 + P.tile0_bytes / 16;           // tile0: one warp's 32 observation rows of zeros; tile1: 32 rows of nbr = -1
     void *stop = tile1 + P.tile1_bytes / 16;            // top-nm lists of the MAXR > 4 instantiations
+    // CTA-level compaction of the re-observe phase: parked owner state + list of touched envs
+    double *spk_d = reinterpret_cast<double *>(reinterpret_cast<char *>(stop) + TopList<MAXR>::smem_bytes(threads));   // [4][threads] yaw pitch real_len max_dev
+    int *spk_i = reinterpret_cast<int *>(spk_d + 4 * threads);                                                      // [3][threads] wp index, flags, staged
+    int *s_list = spk_i + 3 * threads;                                                                              // [envs_per_cta]
+    int *s_nt = s_list + P.envs_per_cta;                                                                            // [2] (double-buffered counter)
+    if (threadIdx.x == 0) { s_nt[0] = 0; s_nt[1] = 0; }
     if (WL) {
         for (int i = threadIdx.x; i < P.tile0_bytes / 16; i += blockDim.x) tile0[i] = make_uint4(0u, 0u, 0u, 0u);
         for (int i = threadIdx.x; i < P.tile1_bytes / 16; i += blockDim.x) tile1[i] = make_uint4(~0u, ~0u, ~0u, ~0u);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the copy engine
-        __syncthreads();
     }
+    __syncthreads();
 
     const int tid = threadIdx.x, N = P.N, lane = tid & 31;
     const unsigned env_lanes = WL ? (N >= 32 ? 0xffffffffu : (((1u << N) - 1u) << (lane - lane % N))) : 0u;
@@ -103,6 +109,7 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 128 ? UAISA_MINB128 : 1)) uaisa
     const int cap = min(P.nm, MAXR);
     const bool is_step = L.mode == MODE_STEP;
     const bool do_auto = (L.mode == MODE_AUTORESET) || (is_step && L.auto_reset);
+    const bool compact = is_step && do_auto && P.compact;   // re-observe through CTA-level compaction (uniform)
 
     RG_DECL
     Consts C; Drone d; int ep_len = 0;
@@ -166,6 +173,9 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 128 ? UAISA_MINB128 : 1)) uaisa
         RG_MARK(RG_ACT);
         bool st_done = false, st_fin = false;
         int staged = -1;                                 // rows of mine already in HBM this step (-1: none, row not cleared)
+        // "working identity": normally the thread's own drone; in a compacted re-observe phase the drone it was handed
+        int wk = k, wlbase = lbase, tt = tid; size_t wo = o; float *wobs = myobs; int *wnbr = mynbr;
+        bool remapped = false, worker = false;
 
         for (int ph = is_step ? PH_A : PH_OBS; ph <= PH_OBS; ph++) {
             bool active = valid;
@@ -220,7 +230,36 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 128 ? UAISA_MINB128 : 1)) uaisa
                 sx[0 * threads + tid] = d.px; sx[1 * threads + tid] = d.py; sx[2 * threads + tid] = d.pz;
                 sx[3 * threads + tid] = d.vx; sx[4 * threads + tid] = d.vy; sx[5 * threads + tid] = d.vz;
             }
-            ENV_SYNC();
+            if (ph == PH_OBS && compact) {
+                // Only the envs touched by the reset policy are re-observed (typically a quarter of them, spread over
+                // nearly every warp).  Gather them: owners park their state in shared memory, the touched envs are listed,
+                // and the first nt*N threads of the CTA each take over one drone of a listed env, so whole warps are
+                // either fully busy or skip the phase.
+                if (valid) {
+                    spk_d[0 * threads + tid] = d.yaw; spk_d[1 * threads + tid] = d.pitch; spk_d[2 * threads + tid] = d.real_len; spk_d[3 * threads + tid] = d.max_dev;
+                    spk_i[0 * threads + tid] = d.i; spk_i[1 * threads + tid] = d.flags; spk_i[2 * threads + tid] = staged;
+                }
+                if (active && k == 0) s_list[atomicAdd(&s_nt[t & 1], 1)] = le;
+                __syncthreads();
+                const int nt = s_nt[t & 1];
+                if (tid == 0) s_nt[(t + 1) & 1] = 0;
+                remapped = true;
+                worker = active = tid < nt * N;
+                if (worker) {
+                    const int q = tid / N, e_l = s_list[q];
+                    wk = tid - q * N; wlbase = e_l * N; tt = wlbase + wk;
+                    const int env_t = env0 + e_l, sn_t = __ldg(P.env2scn + env_t) * N + wk;
+                    d.px = sx[0 * threads + tt]; d.py = sx[1 * threads + tt]; d.pz = sx[2 * threads + tt];
+                    d.vx = sx[3 * threads + tt]; d.vy = sx[4 * threads + tt]; d.vz = sx[5 * threads + tt];
+                    d.i = spk_i[0 * threads + tt]; d.max_dev = spk_d[3 * threads + tt]; staged = spk_i[2 * threads + tt];
+                    C.wp = P.wp + (size_t)sn_t * P.W * 3; C.seg = P.seg + (size_t)sn_t * P.W * 4;
+                    C.radius = sx[6 * threads + tt]; C.prio = sx[7 * threads + tt];
+                    wo = (size_t)t * A + (size_t)env_t * N + wk;
+                    wobs = L.obs ? L.obs + wo * P.obs_dim : nullptr; wnbr = L.nbr ? L.nbr + wo * P.nm : nullptr;
+                }
+            } else {
+                ENV_SYNC();
+            }
             RG_MARK(RG_SYNC);
             if (!active) continue;
 
@@ -247,21 +286,21 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 128 ? UAISA_MINB128 : 1)) uaisa
 #pragma unroll 4
                     for (int jj = 0; jj < jn; jj++) {            // stage 1a: who is within range (branch-free, overlapped)
                         const int j = jb + jj;
-                        const int bits = (j == k) ? 0 : pair_range_fast(P, d.px, d.py, d.pz, sx + lbase + j, threads);
+                        const int bits = (j == wk) ? 0 : pair_range_fast(P, d.px, d.py, d.pz, sx + wlbase + j, threads);
                         near |= (bits & PB_EVAL) ? (1u << jj) : 0u;
                         slow |= (bits & PB_SLOW) ? (1u << jj) : 0u;
                     }
                     n_rng += __popc(near);
                     for (unsigned m = near; m; m &= m - 1) {     // stage 1b: collision / moving-away gates of the near ones
                         const int jj = __ffs(m) - 1;
-                        const int bits = pair_near_fast(P, d.px, d.py, d.pz, d.vx, d.vy, d.vz, C.radius, sx + lbase + jb + jj, threads);
+                        const int bits = pair_near_fast(P, d.px, d.py, d.pz, d.vx, d.vy, d.vz, C.radius, sx + wlbase + jb + jj, threads);
                         col |= (bits & PB_COL) != 0;
                         cand |= (bits & PB_FULL) ? (1u << jj) : 0u;
                         slow |= (bits & PB_SLOW) ? (1u << jj) : 0u;
                     }
                     for (unsigned m = slow; m; m &= m - 1) {     // a squared distance inside a guard band: exact comparisons
                         const int jj = __ffs(m) - 1;
-                        const int bits = pair_gate(P, d.px, d.py, d.pz, d.vx, d.vy, d.vz, C.radius, sx + lbase + jb + jj, threads);
+                        const int bits = pair_gate(P, d.px, d.py, d.pz, d.vx, d.vy, d.vz, C.radius, sx + wlbase + jb + jj, threads);
                         n_rng += ((bits & PB_EVAL) && !((near >> jj) & 1u)) ? 1u : 0u;
                         col |= (bits & PB_COL) != 0;
                         cand |= (bits & PB_FULL) ? (1u << jj) : 0u;
@@ -271,21 +310,21 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 128 ? UAISA_MINB128 : 1)) uaisa
                     unsigned ins = 0, amb = 0;
                     for (unsigned m = cand; m; m &= m - 1) {
                         const int jj = __ffs(m) - 1;
-                        PairGeom g; pair_geom(P, d.px, d.py, d.pz, d.vx, d.vy, d.vz, C.radius, C.prio, sx + lbase + jb + jj, threads, bx, by, bz, g);
+                        PairGeom g; pair_geom(P, d.px, d.py, d.pz, d.vx, d.vy, d.vz, C.radius, C.prio, sx + wlbase + jb + jj, threads, bx, by, bz, g);
                         const int c = cone_screen(g);
                         ins |= (c == 1) ? (1u << jj) : 0u; amb |= (c == 2) ? (1u << jj) : 0u;
                     }
                     // stage 2b: the few ambiguous pairs go through asin/acos with the reference's roundings
                     for (unsigned m = amb; m; m &= m - 1) {
                         const int jj = __ffs(m) - 1;
-                        PairGeom g; pair_geom(P, d.px, d.py, d.pz, d.vx, d.vy, d.vz, C.radius, C.prio, sx + lbase + jb + jj, threads, bx, by, bz, g);
+                        PairGeom g; pair_geom(P, d.px, d.py, d.pz, d.vx, d.vy, d.vz, C.radius, C.prio, sx + wlbase + jb + jj, threads, bx, by, bz, g);
                         double ah;
                         if (cone_exact(g, ah)) ins |= 1u << jj;
                     }
                     // stage 2c: pairs inside the cone -> expected collision time, vo_flag, row keys
                     for (unsigned m = ins; m; m &= m - 1) {
                         const int jj = __ffs(m) - 1, j = jb + jj;
-                        const double *so = sx + lbase + j;
+                        const double *so = sx + wlbase + j;
                         PairGeom g; pair_geom(P, d.px, d.py, d.pz, d.vx, d.vy, d.vz, C.radius, C.prio, so, threads, bx, by, bz, g);
                         double tt, md, iet;
                         if (cone_time(P, d.vx, d.vy, d.vz, C.radius, so, threads, bx, by, bz, g, tt, md, iet)) {
@@ -333,7 +372,7 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 128 ? UAISA_MINB128 : 1)) uaisa
             // ------------------------------------------------------------ observation row (ir_gym.py:203-229)
             {
                 bool bad = false;
-                if (myobs) {
+                if (wobs) {
                     const double self[OBS_SELF] = {d.px, d.py, d.pz, d.vx, d.vy, d.vz, C.radius, C.prio, d0, d1, d2, dev};
                     float fs[OBS_SELF];
 #pragma unroll
@@ -344,41 +383,41 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 128 ? UAISA_MINB128 : 1)) uaisa
                     bad |= (chk != chk);
                     if ((P.obs_dim & 1) == 0) {
 #pragma unroll
-                        for (int q = 0; q < OBS_SELF; q += 2) reinterpret_cast<float2 *>(myobs)[q >> 1] = make_float2(fs[q], fs[q + 1]);
+                        for (int q = 0; q < OBS_SELF; q += 2) reinterpret_cast<float2 *>(wobs)[q >> 1] = make_float2(fs[q], fs[q + 1]);
                     } else {
 #pragma unroll
-                        for (int q = 0; q < OBS_SELF; q++) myobs[q] = fs[q];
+                        for (int q = 0; q < OBS_SELF; q++) wobs[q] = fs[q];
                     }
                 }
                 // slot r (least urgent first, most urgent last) = top[cnt-1-r]
                 top.for_each([&](int sl, double t_iet, double t_md, int t_j, int t_ah) {
                     const int r = top.cnt - 1 - sl;
-                    const double *so = sx + lbase + t_j;
-                    if (myobs) {
+                    const double *so = sx + wlbase + t_j;
+                    if (wobs) {
                         const double mx = so[0], my = so[threads], mz = so[2 * threads];
                         const double mvx = so[3 * threads], mvy = so[4 * threads], mvz = so[5 * threads], prb = so[7 * threads];
                         const double pr = (C.prio == prb) ? 0.5 : fast_div(C.prio, C.prio + prb);
                         const double v[ROW] = {pr * (2.0 * d.px + (d.vx + mvx) * 1.0), pr * (2.0 * d.py + (d.vy + mvy) * 1.0),
                                                pr * (2.0 * d.pz + (d.vz + mvz) * 1.0), mx - d.px, my - d.py, mz - d.pz,
                                                (double)t_ah * 0.01, t_md, t_iet};
-                        float *rr = myobs + OBS_SELF + ROW * r;
+                        float *rr = wobs + OBS_SELF + ROW * r;
 #pragma unroll
                         for (int q = 0; q < ROW; q++) { const float w = np_round2_f32(v[q]); bad |= (w * 0.f != 0.f); rr[q] = w; }
                     }
-                    if (mynbr) mynbr[r] = t_j;
+                    if (wnbr) wnbr[r] = t_j;
                 });
                 // rows beyond cnt: untouched zero fill after a step's clear, stale after a re-observe, or
                 // never cleared in the stand-alone observe/reset/autoreset modes
                 const int stale_end = (staged < 0) ? (is_step ? 0 : P.nm) : staged;
                 for (int r = top.cnt; r < stale_end; r++) {
-                    if (myobs) { float *rr = myobs + OBS_SELF + ROW * r;
+                    if (wobs) { float *rr = wobs + OBS_SELF + ROW * r;
 #pragma unroll
                         for (int q = 0; q < ROW; q++) rr[q] = 0.0f; }
-                    if (mynbr) mynbr[r] = -1;
+                    if (wnbr) wnbr[r] = -1;
                 }
                 staged = top.cnt;
                 n_bad += bad ? 1u : 0u;
-                if (L.count) L.count[o] = (uint8_t)top.cnt;
+                if (L.count) L.count[wo] = (uint8_t)top.cnt;
             }
             RG_MARK(RG_OBSROW);
             if (ph == PH_OBS) { d.max_dev = rt(d.max_dev); continue; }
@@ -426,6 +465,19 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 128 ? UAISA_MINB128 : 1)) uaisa
             d.px = rt(d.px); d.py = rt(d.py); d.pz = rt(d.pz); d.vx = rt(d.vx); d.vy = rt(d.vy); d.vz = rt(d.vz);
             d.yaw = rt(d.yaw); d.pitch = rt(d.pitch); d.real_len = rt(d.real_len); d.max_dev = rt(d.max_dev);
             RG_MARK(RG_B_OUT);
+        }
+        if (remapped) {   // hand max_deviation back to the owners and take my own drone up again
+            if (worker) spk_d[3 * threads + tt] = d.max_dev;
+            __syncthreads();
+            if (valid) {
+                d.px = sx[0 * threads + tid]; d.py = sx[1 * threads + tid]; d.pz = sx[2 * threads + tid];
+                d.vx = sx[3 * threads + tid]; d.vy = sx[4 * threads + tid]; d.vz = sx[5 * threads + tid];
+                d.yaw = spk_d[0 * threads + tid]; d.pitch = spk_d[1 * threads + tid]; d.real_len = spk_d[2 * threads + tid]; d.max_dev = spk_d[3 * threads + tid];
+                d.i = spk_i[0 * threads + tid]; d.flags = spk_i[1 * threads + tid];
+                const int sn = scn * N + k;
+                C.wp = P.wp + (size_t)sn * P.W * 3; C.seg = P.seg + (size_t)sn * P.W * 4;
+                C.radius = sx[6 * threads + tid]; C.prio = sx[7 * threads + tid];
+            }
         }
         RG_MARK(RG_TAIL_B);
         ENV_SYNC();   // the next step republishes sx and re-arms senv/ssel

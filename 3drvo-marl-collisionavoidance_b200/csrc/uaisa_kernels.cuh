@@ -36,7 +36,7 @@ struct Params {
     int E, N, W, M, nm, obs_dim;
     int envs_per_cta, threads;
     int tile0_bytes, tile1_bytes;   // constant smem tiles behind the TMA fills (zeros / 0xFF), multiples of 16
-    int env_train, count_pairs;
+    int env_train, count_pairs, compact;
     // hyper-parameters (reference constructor defaults, see include/uaisa_b200.h)
     double goal_thr, max_acc, max_ang, dt, vel_max, nbr_range, bld_range, bld_zgate, ctime, delta_t, exp_radius;
     double goal2_lo, goal2_hi, nbr2_lo, nbr2_hi;   // T^2*(1 -+ 1e-14) guard bands for sqrt(x) <= T (host-computed)
@@ -338,7 +338,7 @@ struct TopList;
 
 template <int MAXR>
 struct TopList<MAXR, false> {
-    static constexpr size_t smem_bytes(int) { return 0; }
+    __host__ __device__ static constexpr size_t smem_bytes(int) { return 0; }
     double iet[MAXR], md[MAXR];
     int j[MAXR], ah[MAXR];
     int cnt;
@@ -369,7 +369,7 @@ struct TopList<MAXR, false> {
 
 template <int MAXR>
 struct TopList<MAXR, true> {
-    static constexpr size_t smem_bytes(int threads) { return (size_t)threads * MAXR * 24; }
+    __host__ __device__ static constexpr size_t smem_bytes(int threads) { return (size_t)threads * MAXR * 24; }
     double *iet, *md; int *j, *ah;   // this thread's column; slot s at [s * st]
     int st, cnt;
     __device__ __forceinline__ void init(void *base, int threads, int tid) {

@@ -231,6 +231,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-sat", action="store_true")
+    ap.add_argument("--no-autoreset", action="store_true", help="diagnostic: plain steps without the trainer reset policy")
     ap.add_argument("--threads-per-block", type=int, default=0)
     ap.add_argument("--tf32", action="store_true")
     ap.add_argument("--ppo-envs", type=int, default=8192)
@@ -282,7 +283,7 @@ def main():
             if events is not None:
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
-            env.rollout(acts[a0:a0 + T], o, auto_reset=True, max_ep_len=MAX_EP_LEN)
+            env.rollout(acts[a0:a0 + T], o, auto_reset=not args.no_autoreset, max_ep_len=MAX_EP_LEN)
             if events is not None:
                 e1.record(); events.append((e0, e1, T))
             done_steps += T

@@ -12,7 +12,7 @@ SYMBOLS = (
     "uaisa_last_error", "uaisa_version", "uaisa_default_config", "uaisa_create", "uaisa_destroy",
     "uaisa_set_scenarios", "uaisa_step", "uaisa_reset", "uaisa_observe", "uaisa_autoreset", "uaisa_rollout",
     "uaisa_get_state", "uaisa_set_state", "uaisa_cal_des", "uaisa_indicators", "uaisa_get_counters",
-    "uaisa_launch_count", "uaisa_step_host", "uaisa_get_region_clocks", "uaisa_action_transform", "uaisa_gae", "uaisa_step_host_sparse",
+    "uaisa_launch_count", "uaisa_step_host", "uaisa_get_region_clocks", "uaisa_action_transform", "uaisa_gae", "uaisa_step_host_sparse", "uaisa_policy_features", "uaisa_policy_heads",
 )
 
 
@@ -73,6 +73,8 @@ def lib():
         L.uaisa_get_region_clocks.argtypes = [vp, vp, vp]
         L.uaisa_action_transform.argtypes = [vp, vp, C.c_float, vp, vp, vp]
         L.uaisa_step_host_sparse.argtypes = [vp, vp, i32, i32, C.POINTER(UaisaHostStep)]
+        L.uaisa_policy_features.argtypes = [vp, i32, i32, vp, vp, vp, vp, vp, vp]
+        L.uaisa_policy_heads.argtypes = [vp, i32, vp, vp, vp, vp]
         L.uaisa_gae.argtypes = [vp, vp, vp, i32, i32, C.c_float, C.c_float, vp, vp, vp]
         L.uaisa_step_host.argtypes = [vp] * 9 + [i32, i32]
         for name in SYMBOLS:

@@ -156,6 +156,17 @@ int uaisa_get_region_clocks(UaisaHandle *h, int64_t *out16, void *stream);
 int uaisa_step_host(UaisaHandle *h, const float *action, float *obs, uint8_t *count, int32_t *nbr, float *reward,
                     uint8_t *done, uint8_t *info, uint8_t *finish, int32_t auto_reset, int32_t max_ep_len);
 
+/* ---- fused rollout forward of the actor-critic (train/policy/policy_rnn_ac.py:57-69, SURVEY 8a row a-P1) --------------------
+ * uaisa_policy_features: obs[A][obs_dim] -> feat[A][288] = LayerNorm(268)(cat(self 12, h_fwd + h_bwd)) zero padded to 288, with the
+ *   bi-GRU run for ONE step from h0 = 0 (exact for agents with <= 1 neighbour row; the caller patches the others).
+ *   wih_t [2][9][768]: weight_ih_l0 / weight_ih_l0_reverse transposed to [k][3H]; bias [2][4][256]: b_ir+b_hr, b_iz+b_hz, b_in, b_hn.
+ * uaisa_policy_heads: feat -> mu[A][3] = tanh(actor MLP), v[A] = critic MLP on the tensor cores (tcgen05.mma kind::tf32, TMEM
+ *   accumulators).  weights: 12 DEVICE pointers W1a[256][288] b1a[256] W2a[256][256] b2a[256] W3a[3][256] b3a[3] W1c b1c W2c b2c
+ *   W3c[1][256] b3c[1] (W1 rows zero padded from 268 to 288).  Both are stateless and asynchronous on `stream`. */
+int uaisa_policy_features(const float *obs, int32_t A, int32_t obs_dim, const float *wih_t, const float *bias, const float *ln_w,
+                          const float *ln_b, float *feat, void *stream);
+int uaisa_policy_heads(const float *feat, int32_t A, const float *const *weights, float *mu, float *v, void *stream);
+
 /* ---- latency-optimised host round trip ------------------------------------------------------------------------
  * One env step with HOST action in / HOST results out, returned in the reference's own ragged spirit: the 12 self
  * values of every observation plus only the neighbour rows that exist (an observation is 12 + 9*max(k,1) values in

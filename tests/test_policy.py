@@ -74,3 +74,35 @@ def test_policy_matches_reference_golden_cuda():
     torch.backends.cuda.matmul.allow_tf32 = False
     torch.backends.cudnn.allow_tf32 = False
     _check("cuda", 5e-5)
+
+
+@pytest.mark.gpu
+def test_fused_features_and_tcgen05_heads_match_torch():
+    """K6a / K6b (csrc/uaisa_policy.cu) against the torch module with the same weights: features to fp32 accuracy, heads to
+    TF32 accuracy (10-bit mantissa inputs, fp32 accumulation)."""
+    from uaisa_ppo.fused import FusedPolicy
+
+    torch.backends.cuda.matmul.allow_tf32 = False
+    m = _model("cuda")
+    fp = FusedPolicy(m, "cuda")
+    rng = np.random.default_rng(3)
+    for A in (96, 128, 1000, 4133):
+        obs = np.zeros((A, 102), np.float32)
+        obs[:, :12] = np.round(rng.normal(0, 5, (A, 12)), 2); obs[:, 0:3] += 20
+        cnt = rng.choice([0, 0, 1, 1, 2, 4], A).astype(np.uint8)
+        for b in range(A):
+            obs[b, 12:12 + 9 * cnt[b]] = np.round(rng.normal(0, 2, 9 * int(cnt[b])), 2)
+        o, c = torch.from_numpy(obs).cuda(), torch.from_numpy(cnt).cuda()
+        with torch.no_grad():
+            ref_feat = m.features(o, c)
+            dist, ref_v, _ = m.evaluate(o, c)
+        feat = fp.features(o)
+        single = (c <= 1)
+        assert torch.allclose(feat[single, :268], ref_feat[single], atol=2e-5, rtol=1e-5), (feat[single, :268] - ref_feat[single]).abs().max()
+        assert bool((feat[:, 268:] == 0).all())
+        featp = feat.clone(); featp[:, :268] = ref_feat
+        mu, v = fp.heads(featp)
+        torch.cuda.synchronize()
+        assert (mu - dist.mean).abs().max() < 5e-3 and (v - ref_v).abs().max() < 5e-3 * max(1.0, float(ref_v.abs().max())), ((mu - dist.mean).abs().max(), (v - ref_v).abs().max())
+        a, vv, logp = fp.step(o, c)
+        assert a.shape == (A, 3) and torch.isfinite(logp).all() and (vv - ref_v).abs().max() < 5e-3 * max(1.0, float(ref_v.abs().max()))

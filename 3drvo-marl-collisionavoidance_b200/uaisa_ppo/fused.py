@@ -21,24 +21,28 @@ class FusedPolicy:
 
     @torch.no_grad()
     def refresh(self):
+        """(Re)pack the module's weights into the kernels' layouts.  Buffers are allocated once and updated in place, so
+        device addresses stay fixed (a CUDA graph that captured the fused forward stays valid)."""
         g, ln = self.ac.pi.rnn_reader.rnn_net, self.ac.pi.rnn_reader.ln
         H = 256
         wih, bias = [], []
         for sfx in ("", "_reverse"):
             w_ih, b_ih, b_hh = getattr(g, "weight_ih_l0" + sfx), getattr(g, "bias_ih_l0" + sfx), getattr(g, "bias_hh_l0" + sfx)
-            wih.append(w_ih.t().contiguous())                                   # [9][768]
+            wih.append(w_ih.t())                                                # [9][768]
             bias.append(torch.stack([b_ih[:H] + b_hh[:H], b_ih[H:2 * H] + b_hh[H:2 * H], b_ih[2 * H:], b_hh[2 * H:]]))   # [4][256]
-        self.wih_t = torch.stack(wih).float().contiguous().to(self.dev)         # [2][9][768]
-        self.bias = torch.stack(bias).float().contiguous().to(self.dev)         # [2][4][256]
-        self.ln_w, self.ln_b = ln.weight.detach().float().contiguous(), ln.bias.detach().float().contiguous()
-        ws = []
+        new = [torch.stack(wih).float(), torch.stack(bias).float(), ln.weight.detach().float(), ln.bias.detach().float()]
         for net in (self.ac.pi.net_out, self.ac.v.v_net):
             w1 = torch.zeros((256, KPAD), device=self.dev); w1[:, :268] = net[0].weight
-            ws += [w1, net[0].bias.detach().float().contiguous(), net[2].weight.detach().float().contiguous(), net[2].bias.detach().float().contiguous(),
-                   net[4].weight.detach().float().contiguous(), net[4].bias.detach().float().contiguous()]
-        self.ws = ws
-        self.wptr = (C.c_void_p * 12)(*[w.data_ptr() for w in ws])
-        self.wptr_dev = None
+            new += [w1, net[0].bias.detach().float(), net[2].weight.detach().float(), net[2].bias.detach().float(),
+                    net[4].weight.detach().float(), net[4].bias.detach().float()]
+        if getattr(self, "_bufs", None) is None:
+            self._bufs = [t.contiguous().to(self.dev).clone() for t in new]
+        else:
+            for b, t in zip(self._bufs, new):
+                b.copy_(t)
+        self.wih_t, self.bias, self.ln_w, self.ln_b = self._bufs[:4]
+        self.ws = self._bufs[4:]
+        self.wptr = (C.c_void_p * 12)(*[w.data_ptr() for w in self.ws])
 
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)
@@ -68,12 +72,16 @@ class FusedPolicy:
         """Drop-in for rnn_ac.step: (a, v, logp).  Agents with >= 2 neighbour rows get their feature row from the torch reader."""
         feat = self.features(obs)
         rd = self.ac.pi.rnn_reader
-        if multi_cap > 0:
+        if multi_cap < 0:
+            pass                      # the caller has checked that no agent has >= 2 rows: K6a is exact for everybody
+        elif multi_cap > 0:
             K = min(int(multi_cap), obs.shape[0])
             c_top, idx = torch.topk(count.to(torch.int32), K)
             if getattr(rd, "overflow", None) is not None:
                 rd.overflow += ((count > 1).sum() - (c_top > 1).sum()).to(torch.int64)
-            f_t = rd(obs[idx], c_top.to(count.dtype))
+            ov = getattr(rd, "overflow", None); rd.overflow = None          # the inner call sees exactly K agents: nothing can overflow
+            f_t = rd(obs[idx], c_top.to(count.dtype), multi_cap=K)                # static shapes, no host sync (graph-capturable)
+            rd.overflow = ov
             feat[:, :268].index_copy_(0, idx, torch.where((c_top > 1).unsqueeze(-1), f_t, feat[idx, :268]))
         else:
             idx = torch.nonzero(count > 1).squeeze(-1)

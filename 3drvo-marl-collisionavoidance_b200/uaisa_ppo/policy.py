@@ -63,7 +63,7 @@ class rnn_Reader(nn.Module):   # policy_rnn_ac.py:75-168 (mode 'biGRU')
         h0 = obs.new_zeros((B, self.hidden_dim))
         x0 = rows[:, 0] if nm > 0 else obs.new_zeros((B, self.input_dim))
         hsum = self._cell(x0, h0, False) + self._cell(x0, h0, True)          # exact for every agent with <= 1 row
-        if nm > 1:
+        if nm > 1 and multi_cap >= 0:   # multi_cap < 0: the caller guarantees that nobody has >= 2 rows
             if multi_cap > 0:
                 K = min(int(multi_cap), B)
                 c_top, multi = torch.topk(count.to(torch.int32), K)           # static shape, no sync

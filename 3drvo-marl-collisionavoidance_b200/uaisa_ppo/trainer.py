@@ -43,6 +43,7 @@ class PPOConfig:                      # train_process.py:53-63 defaults
     minibatch: int = 65536            # samples per gradient step (the reference's "batch" is one robot's 300 samples)
     std_factor: float = 1.0
     use_cuda_graph: bool = True       # capture one rollout step (policy + transform + env step + reset policy + stores)
+    use_fused_policy: bool = True     # rollout forward through csrc/uaisa_policy.cu (K6a features + K6b tcgen05 heads, TF32 inputs)
     multi_cap_frac: float = 1.0 / 64  # static capacity of the multi-row GRU path in the captured step (fraction of A)
 
 
@@ -78,6 +79,13 @@ class PPOTrainer:
         self.env.reset()
         self.stats = {}
         self._graph = None
+        self._graph_fast = None       # same step without the multi-row GRU path (taken when no agent has >= 2 neighbour rows)
+        self._flag_dev = torch.zeros(1, dtype=torch.int32, device=self.dev)
+        self._flag_host = torch.zeros(1, dtype=torch.int32).pin_memory()
+        self.fused = None
+        if self.cfg.use_fused_policy:
+            from .fused import FusedPolicy
+            self.fused = FusedPolicy(self.ac, self.dev)
         self._t = torch.zeros(1, dtype=torch.long, device=self.dev)           # device-side step counter (graph-safe buffer index)
         self._ndone = torch.zeros((), dtype=torch.int64, device=self.dev)
         self._last = torch.zeros((), dtype=torch.int64, device=self.dev)
@@ -88,7 +96,8 @@ class PPOTrainer:
         """One rollout step writing into buf[..][t] through the device-side counter (multi_ppo.py:193-281)."""
         env, cfg, b, t = self.env, self.cfg, self.buf, self._t
         b["obs"].index_copy_(0, t, env.obs.unsqueeze(0)); b["count"].index_copy_(0, t, env.count.unsqueeze(0))      # :217-219 store(obs, ...)
-        a_inc, v, logp = self.ac.step(env.obs, env.count, cfg.std_factor, multi_cap=cap)                           # :196
+        stepper = self.fused if self.fused is not None else self.ac
+        a_inc, v, logp = stepper.step(env.obs, env.count, cfg.std_factor, multi_cap=cap)                          # :196
         _, a_r = env.action_transform(a_inc, self.action)                                                          # :197-208
         env.step(self.action)                                                                                      # :210
         b["act"].index_copy_(0, t, a_r.unsqueeze(0)); b["rew"].index_copy_(0, t, env.reward.unsqueeze(0))
@@ -97,6 +106,8 @@ class PPOTrainer:
         env.autoreset(max_ep_len=cfg.max_ep_len, epoch_ended=epoch_ended)                                          # :226-281 (+ env_observation)
         b["cut"].index_copy_(0, t, env.path_cut.unsqueeze(0))
         t += 1
+        self._flag_dev.copy_((env.count > 1).any().to(torch.int32).reshape(1))      # does the NEXT step need the multi-row path?
+        self._flag_host.copy_(self._flag_dev, non_blocking=True)
 
     @torch.no_grad()
     def rollout(self):
@@ -115,22 +126,26 @@ class PPOTrainer:
             s = torch.cuda.Stream(device=self.dev)
             s.wait_stream(torch.cuda.current_stream(self.dev))
             with torch.cuda.stream(s):            # warm-up on a side stream (allocator, cuBLAS workspaces), then capture
-                self._one_step(False, cap); self._one_step(False, cap)
+                self._one_step(False, cap); self._one_step(False, -1)
             torch.cuda.current_stream(self.dev).wait_stream(s)
-            self._t.zero_(); self._ndone.zero_(); rd.overflow.zero_()
             self.env.reset()
-            g = torch.cuda.CUDAGraph()
+            g, gf = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 self._one_step(False, cap)
-            self._graph = g
+            with torch.cuda.graph(gf, pool=g.pool()):
+                self._one_step(False, -1)
+            self._graph, self._graph_fast = g, gf
             self._t.zero_(); self._ndone.zero_(); rd.overflow.zero_()
             self.env.reset()
+        self._flag_host[0] = int((self.env.count > 1).any())
         for t in range(T - 1):
             if self._graph is not None:
-                self._graph.replay()
+                torch.cuda.current_stream(self.dev).synchronize()        # the flag of the previous step has landed (one small bubble per step)
+                (self._graph if int(self._flag_host[0]) else self._graph_fast).replay()
             else:
                 self._one_step(False, cap)
-        self._one_step(True, cap)
+        torch.cuda.current_stream(self.dev).synchronize()
+        self._one_step(True, cap if int(self._flag_host[0]) or not cfg.use_cuda_graph else -1)
         self.stats["collisions"] = self._ndone
         if cap and int(rd.overflow) > 0:
             raise RuntimeError("%d agent-steps had >= 2 neighbour rows beyond the static GRU capacity (%d); raise PPOConfig.multi_cap_frac" % (int(rd.overflow), cap))
@@ -194,6 +209,8 @@ class PPOTrainer:
             loss_v.backward()
             self._allreduce_grads(list(self.ac.v.parameters()))
             self.vf_opt.step()
+        if self.fused is not None:
+            self.fused.refresh()          # repack the updated weights in place (addresses stay fixed: the captured rollout step stays valid)
         self.stats.update(pi_iters=pi_iters, loss_v=float(loss_v.detach()), kl=float(kl_all), mean_ret=float(torch.nan_to_num(ret, 0.0, 0.0, 0.0).mean()))
         return self.stats
 

@@ -49,6 +49,15 @@ class rnn_Reader(nn.Module):   # policy_rnn_ac.py:75-168 (mode 'biGRU')
         n = torch.tanh(i_n + r * h_n)
         return (1 - z) * n + z * h
 
+    def _cell0(self, x, rev: bool):
+        """GRU cell from h = 0: W_hh h vanishes, so gh is just b_hh (same value and same gradients, 60 % fewer FLOPs)."""
+        sfx = "_reverse" if rev else ""
+        w_ih, b_ih, b_hh = getattr(self.rnn_net, "weight_ih_l0" + sfx), getattr(self.rnn_net, "bias_ih_l0" + sfx), getattr(self.rnn_net, "bias_hh_l0" + sfx)
+        i_r, i_z, i_n = F.linear(x, w_ih, b_ih).chunk(3, -1)
+        h_r, h_z, h_n = b_hh.chunk(3, -1)
+        r, z = torch.sigmoid(i_r + h_r), torch.sigmoid(i_z + h_z)
+        return (1 - z) * torch.tanh(i_n + r * h_n)
+
     def forward(self, obs: torch.Tensor, count: torch.Tensor, multi_cap: int = 0) -> torch.Tensor:
         """obs [B, 12+9nm] float32, count [B] (rows valid; 0 means one zero row) -> LayerNorm(cat(self, h_f + h_b)) [B, 268].
 
@@ -60,9 +69,8 @@ class rnn_Reader(nn.Module):   # policy_rnn_ac.py:75-168 (mode 'biGRU')
         nm = (obs.shape[1] - self.state_dim) // self.input_dim
         self_state = obs[:, : self.state_dim]
         rows = obs[:, self.state_dim: self.state_dim + nm * self.input_dim].reshape(B, nm, self.input_dim)
-        h0 = obs.new_zeros((B, self.hidden_dim))
         x0 = rows[:, 0] if nm > 0 else obs.new_zeros((B, self.input_dim))
-        hsum = self._cell(x0, h0, False) + self._cell(x0, h0, True)          # exact for every agent with <= 1 row
+        hsum = self._cell0(x0, False) + self._cell0(x0, True)                 # exact for every agent with <= 1 row
         if nm > 1 and multi_cap >= 0:   # multi_cap < 0: the caller guarantees that nobody has >= 2 rows
             if multi_cap > 0:
                 K = min(int(multi_cap), B)

@@ -43,6 +43,7 @@ class PPOConfig:                      # train_process.py:53-63 defaults
     minibatch: int = 65536            # samples per gradient step (the reference's "batch" is one robot's 300 samples)
     std_factor: float = 1.0
     use_cuda_graph: bool = True       # capture one rollout step (policy + transform + env step + reset policy + stores)
+    graph_update: bool = True         # capture the update iterations in CUDA graphs (single-GPU; multi-GPU runs them eagerly)
     use_fused_policy: bool = True     # rollout forward through csrc/uaisa_policy.cu (K6a features + K6b tcgen05 heads, TF32 inputs)
     multi_cap_frac: float = 1.0 / 64  # static capacity of the multi-row GRU path in the captured step (fraction of A)
 
@@ -68,8 +69,10 @@ class PPOTrainer:
             for p in self.ac.parameters():
                 dist.broadcast(p.data, 0)
             torch.manual_seed(seed + 1000 * dist.get_rank())   # same weights, different exploration noise per shard
-        self.pi_opt = torch.optim.Adam(self.ac.pi.parameters(), lr=self.cfg.pi_lr)     # multi_ppo.py:115-116
-        self.vf_opt = torch.optim.Adam(self.ac.v.parameters(), lr=self.cfg.vf_lr)
+        cap_ok = self.cfg.graph_update and self.world == 1
+        self.pi_opt = torch.optim.Adam(self.ac.pi.parameters(), lr=self.cfg.pi_lr, capturable=cap_ok)     # multi_ppo.py:115-116
+        self.vf_opt = torch.optim.Adam(self.ac.v.parameters(), lr=self.cfg.vf_lr, capturable=cap_ok)
+        self._upd = None              # captured update graphs
         T, A, D = self.cfg.steps_per_epoch, env.A, env.obs_dim
         f32 = dict(dtype=torch.float32, device=self.dev)
         self.buf = {"obs": torch.empty((T, A, D), **f32), "count": torch.empty((T, A), dtype=torch.uint8, device=self.dev),
@@ -167,6 +170,79 @@ class PPOTrainer:
             off += n
         return bucket[off:] if extra is not None else None
 
+    def _build_update_graphs(self, n, mb):
+        """Capture one policy iteration (forward + loss + KL + backward + clip | optimiser step) and one value iteration
+        (forward + loss + backward + step) over static minibatch buffers (multi_ppo.py:355-376)."""
+        cfg, dev = self.cfg, self.dev
+        u = {"idx": torch.zeros(mb, dtype=torch.long, device=dev), "kl": torch.zeros((), device=dev), "loss_pi": torch.zeros((), device=dev),
+             "loss_v": torch.zeros((), device=dev), "n": n, "mb": mb, "cap": -1}   # -1: no sample has >= 2 neighbour rows (checked per epoch)
+        rd = self.ac.pi.rnn_reader
+        pi_params = list(self.ac.pi.parameters())
+
+        def pi_fb():
+            u["idx"].random_(0, n)
+            idx = u["idx"]
+            w = self._ok[idx].float()
+            dist_, _, logp = self.ac.evaluate(self._obs[idx], self._cnt[idx], self._act[idx], multi_cap=u["cap"])
+            ratio = torch.exp(logp - self._logp_old[idx])
+            a_ = torch.nan_to_num(self._adv[idx], 0.0, 0.0, 0.0)
+            clip_adv = torch.clamp(ratio, 1 - cfg.clip_ratio, 1 + cfg.clip_ratio) * a_
+            loss = -(torch.min(ratio * a_, clip_adv) * w).sum() / w.sum().clamp(min=1)
+            u["kl"].copy_((((self._logp_old[idx] - logp) * w).sum() / w.sum().clamp(min=1)).detach())
+            u["loss_pi"].copy_(loss.detach())
+            loss.backward()
+            torch.nn.utils.clip_grad_norm_(pi_params, max_norm=cfg.max_grad_norm)
+
+        def v_all():
+            u["idx"].random_(0, n)
+            idx = u["idx"]
+            w = self._ok[idx].float()
+            _, v, _ = self.ac.evaluate(self._obs[idx], self._cnt[idx], None, multi_cap=u["cap"])
+            loss = (((v - torch.nan_to_num(self._ret[idx], 0.0, 0.0, 0.0)) ** 2) * w).sum() / w.sum().clamp(min=1)
+            u["loss_v"].copy_(loss.detach())
+            loss.backward()
+            self.vf_opt.step()
+
+        s = torch.cuda.Stream(device=dev)
+        s.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(s):                       # warm-up (optimizer state, cuBLAS workspaces) on a side stream
+            for _ in range(2):
+                self.pi_opt.zero_grad(set_to_none=True); pi_fb(); self.pi_opt.step()
+                self.vf_opt.zero_grad(set_to_none=True); v_all()
+        torch.cuda.current_stream(dev).wait_stream(s)
+        g1, g2, g3 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        self.pi_opt.zero_grad(set_to_none=True)
+        with torch.cuda.graph(g1):
+            pi_fb()
+        with torch.cuda.graph(g2, pool=g1.pool()):
+            self.pi_opt.step()
+        self.vf_opt.zero_grad(set_to_none=True)
+        with torch.cuda.graph(g3, pool=g1.pool()):
+            v_all()
+        u.update(g_pi_fb=g1, g_pi_step=g2, g_v=g3)
+        rd.overflow.zero_()
+        return u
+
+    def _update_graphed(self, n, mb):
+        cfg = self.cfg
+        if self._upd is None or self._upd["n"] != n or self._upd["mb"] != mb:
+            # the warm-up iterations inside the builder are real (tiny-lr) optimiser steps on this epoch's data
+            self._upd = self._build_update_graphs(n, mb)
+        u = self._upd
+        pi_iters = 0
+        for i in range(cfg.train_pi_iters):
+            u["g_pi_fb"].replay()
+            if float(u["kl"].detach()) > cfg.target_kl:  # multi_ppo.py:362-364 (the step is NOT applied)
+                break
+            u["g_pi_step"].replay()
+            pi_iters += 1
+        for i in range(cfg.train_v_iters):
+            u["g_v"].replay()
+        rd = self.ac.pi.rnn_reader
+        if int(rd.overflow) > 0:
+            raise RuntimeError("update minibatches held more multi-row samples than the static GRU capacity (%d)" % u["cap"])
+        return pi_iters, float(u["loss_v"]), float(u["kl"])
+
     def update(self):
         """PPO-clip update (multi_ppo.py:341-404) on the whole buffer."""
         cfg, b = self.cfg, self.buf
@@ -178,6 +254,20 @@ class PPOTrainer:
         ok = torch.isfinite(adv) & torch.isfinite(ret)        # the reference's inf/nan rewards (ir_gym.py:88) would poison Adam
         all_params = list(self.ac.parameters())
         mb = min(cfg.minibatch, n)
+        if cfg.graph_update and self.world == 1 and not bool((cnt > 1).any()):   # multi-row samples present -> eager path below (exact, dynamic shapes)
+            rd = self.ac.pi.rnn_reader
+            if getattr(rd, "overflow", None) is None:
+                rd.overflow = torch.zeros((), dtype=torch.int64, device=self.dev)
+            rd.overflow.zero_()
+            if getattr(self, "_obs", None) is None:      # static views/buffers the captured graphs read (same storage every epoch)
+                self._obs, self._cnt, self._act, self._logp_old = obs, cnt, act, logp_old
+                self._adv, self._ret, self._ok = torch.empty_like(adv), torch.empty_like(ret), torch.empty_like(ok)
+            self._adv.copy_(adv); self._ret.copy_(ret); self._ok.copy_(ok)
+            pi_iters, lv, klv = self._update_graphed(n, mb)
+            if self.fused is not None:
+                self.fused.refresh()
+            self.stats.update(pi_iters=pi_iters, loss_v=lv, kl=klv, mean_ret=float(torch.nan_to_num(ret, 0.0, 0.0, 0.0).mean()))
+            return self.stats
         pi_iters = 0
         for i in range(cfg.train_pi_iters):                                                        # :355-368
             idx = torch.randint(0, n, (mb,), device=self.dev) if mb < n else torch.arange(n, device=self.dev)

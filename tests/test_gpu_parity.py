@@ -56,6 +56,13 @@ def test_dense_256():
     assert st.rows > 0
 
 
+def test_more_than_256_drones_per_env():
+    """N > 256 uses the 1024-thread instantiation (one CTA of ceil32(N) threads per env)."""
+    scn = scenario_c4(seed=3, n_scenarios=1, n_drones=300)
+    st = lockstep(scn, 2, 10, 6, seed=9, block=2)
+    st.assert_parity()
+
+
 def test_edge_shapes():
     # single drone, no neighbours; nm = 0; N=3 (CTA not a multiple of N); explicit CTA sizes
     one = ScenarioSet.from_start_end([[1, 1, 1]], [[3, 3, 2]], (5, 5, 3))

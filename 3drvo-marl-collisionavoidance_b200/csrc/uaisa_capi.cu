@@ -144,7 +144,8 @@ int uaisa_create(const UaisaConfig *cfg, UaisaHandle **out) {
     P.tile0_bytes = ((32 * P.obs_dim * 4) + 15) & ~15; P.tile1_bytes = ((32 * (P.nm ? P.nm : 1) * 4) + 15) & ~15;
     h->smem = sizeof(double) * 8 * threads + sizeof(int) * 2 * P.envs_per_cta + 16 + P.tile0_bytes + P.tile1_bytes   // + TMA fill tiles
               + (maxr > 4 ? (size_t)threads * maxr * 24 : 0)                                      // + shared top-nm lists
-              + (size_t)threads * (4 * 8 + 3 * 4) + sizeof(int) * (P.envs_per_cta + 2) + 16;          // + re-observe compaction
+              + (size_t)threads * (4 * 8 + 3 * 4) + sizeof(int) * (P.envs_per_cta + 2) + 16           // + re-observe compaction
+              + (size_t)threads * 16 + 16;                                                        // + fp32 position copies
     const bool wl = (N <= 32) && (32 % N == 0) && threads <= 128;   // every env inside one warp
     if (threads > 256) h->kernel = uaisa_env_kernel<16, 1024, false>;
     else if (threads > 128) h->kernel = need <= 4 ? uaisa_env_kernel<4, 256, false> : need <= 10 ? uaisa_env_kernel<10, 256, false> : uaisa_env_kernel<16, 256, false>;

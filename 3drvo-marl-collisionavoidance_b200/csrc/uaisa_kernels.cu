@@ -88,7 +88,9 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 128 ? UAISA_MINB128 : 1)) uaisa
     int *spk_i = reinterpret_cast<int *>(spk_d + 4 * threads);                                                      // [3][threads] wp index, flags, staged
     int *s_list = spk_i + 3 * threads;                                                                              // [envs_per_cta]
     int *s_nt = s_list + P.envs_per_cta;                                                                            // [2] (double-buffered counter)
+    float4 *sxf = reinterpret_cast<float4 *>((reinterpret_cast<uintptr_t>(s_nt + 2) + 15) & ~uintptr_t(15));           // [threads] fp32 copies of the positions
     if (threadIdx.x == 0) { s_nt[0] = 0; s_nt[1] = 0; }
+    const float nbr2_lo_f = (float)(P.nbr_range * P.nbr_range * (1.0 - 1e-4)), nbr2_hi_f = (float)(P.nbr_range * P.nbr_range * (1.0 + 1e-4));
     if (WL) {
         for (int i = threadIdx.x; i < P.tile0_bytes / 16; i += blockDim.x) tile0[i] = make_uint4(0u, 0u, 0u, 0u);
         for (int i = threadIdx.x; i < P.tile1_bytes / 16; i += blockDim.x) tile1[i] = make_uint4(~0u, ~0u, ~0u, ~0u);
@@ -229,6 +231,7 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 128 ? UAISA_MINB128 : 1)) uaisa
             if (valid) {
                 sx[0 * threads + tid] = d.px; sx[1 * threads + tid] = d.py; sx[2 * threads + tid] = d.pz;
                 sx[3 * threads + tid] = d.vx; sx[4 * threads + tid] = d.vy; sx[5 * threads + tid] = d.vz;
+                if constexpr (MAXR > 4) sxf[tid] = make_float4((float)d.px, (float)d.py, (float)d.pz, 0.f);
             }
             if (ph == PH_OBS && compact) {
                 // Only the envs touched by the reset policy are re-observed (typically a quarter of them, spread over
@@ -283,17 +286,28 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 128 ? UAISA_MINB128 : 1)) uaisa
                 for (int jb = 0; jb < N; jb += 32) {
                     unsigned cand = 0, slow = 0, near = 0;
                     const int jn = min(32, N - jb);
+                    if constexpr (MAXR > 4) {                     // many neighbours: fp32 pre-gate on float copies of the positions
+                        const float fx = (float)d.px, fy = (float)d.py, fz = (float)d.pz;
+#pragma unroll 8
+                        for (int jj = 0; jj < jn; jj++) {        // stage 1a: who is within range (fp32, branch-free, overlapped)
+                            const int j = jb + jj;
+                            const int bits = (j == wk) ? 0 : pair_range_f32(fx, fy, fz, sxf[wlbase + j], nbr2_lo_f, nbr2_hi_f);
+                            near |= (bits & PB_EVAL) ? (1u << jj) : 0u;
+                            slow |= (bits & PB_SLOW) ? (1u << jj) : 0u;
+                        }
+                    } else {                                      // a handful of neighbours: the fp64 gate directly
 #pragma unroll 4
-                    for (int jj = 0; jj < jn; jj++) {            // stage 1a: who is within range (branch-free, overlapped)
-                        const int j = jb + jj;
-                        const int bits = (j == wk) ? 0 : pair_range_fast(P, d.px, d.py, d.pz, sx + wlbase + j, threads);
-                        near |= (bits & PB_EVAL) ? (1u << jj) : 0u;
-                        slow |= (bits & PB_SLOW) ? (1u << jj) : 0u;
+                        for (int jj = 0; jj < jn; jj++) {
+                            const int j = jb + jj;
+                            const int bits = (j == wk) ? 0 : pair_range_fast(P, d.px, d.py, d.pz, sx + wlbase + j, threads);
+                            near |= (bits & PB_EVAL) ? (1u << jj) : 0u;
+                            slow |= (bits & PB_SLOW) ? (1u << jj) : 0u;
+                        }
                     }
-                    n_rng += __popc(near);
-                    for (unsigned m = near; m; m &= m - 1) {     // stage 1b: collision / moving-away gates of the near ones
+                    for (unsigned m = near; m; m &= m - 1) {     // stage 1b: collision / moving-away gates of the near ones (fp64)
                         const int jj = __ffs(m) - 1;
                         const int bits = pair_near_fast(P, d.px, d.py, d.pz, d.vx, d.vy, d.vz, C.radius, sx + wlbase + jb + jj, threads);
+                        n_rng += (bits & PB_SAME) ? 0u : 1u;
                         col |= (bits & PB_COL) != 0;
                         cand |= (bits & PB_FULL) ? (1u << jj) : 0u;
                         slow |= (bits & PB_SLOW) ? (1u << jj) : 0u;
@@ -301,7 +315,7 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 128 ? UAISA_MINB128 : 1)) uaisa
                     for (unsigned m = slow; m; m &= m - 1) {     // a squared distance inside a guard band: exact comparisons
                         const int jj = __ffs(m) - 1;
                         const int bits = pair_gate(P, d.px, d.py, d.pz, d.vx, d.vy, d.vz, C.radius, sx + wlbase + jb + jj, threads);
-                        n_rng += ((bits & PB_EVAL) && !((near >> jj) & 1u)) ? 1u : 0u;
+                        n_rng += ((bits & PB_EVAL) && !((near >> jj) & 1u)) ? 1u : 0u;   // (pairs already counted in stage 1b are not counted twice)
                         col |= (bits & PB_COL) != 0;
                         cand |= (bits & PB_FULL) ? (1u << jj) : 0u;
                     }

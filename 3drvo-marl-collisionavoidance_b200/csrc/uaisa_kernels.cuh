@@ -243,7 +243,7 @@ __device__ __forceinline__ int pair_gate(const Params &P, double x, double y, do
 // Branch-free forms of pair_gate for the hot loop: straight-line arithmetic + predicate logic, so the gates of
 // several neighbours overlap (no branch has to resolve between them).  PB_SLOW marks the (1e-14-wide) cases where a
 // squared distance falls inside a guard band; the caller re-runs those few pairs through the exact pair_gate.
-constexpr int PB_SLOW = 16;
+constexpr int PB_SLOW = 16, PB_SAME = 32;
 // stage 1a: neighbour-range test only (rvo_inter.py:89-97) -> PB_EVAL (in range), PB_SLOW, or 0
 __device__ __forceinline__ int pair_range_fast(const Params &P, double x, double y, double z, const double *so, int st) {
     const double mx = so[0], my = so[st], mz = so[2 * st];
@@ -253,6 +253,14 @@ __device__ __forceinline__ int pair_range_fast(const Params &P, double x, double
     const bool in = s2 < P.nbr2_lo, amb = !(in | (s2 > P.nbr2_hi));
     return same ? 0 : (amb ? PB_SLOW : (in ? PB_EVAL : 0));
 }
+// stage 1a in fp32 on float copies of the positions: ~3x cheaper than the fp64 gate and enough to settle every pair whose
+// squared distance is not within 1e-4 (relative) of range^2 -- fp32 evaluation error is ~1e-6.  The rest (PB_SLOW) and the
+// exact-equality "self" exclusion are decided in fp64 afterwards.
+__device__ __forceinline__ int pair_range_f32(float x, float y, float z, const float4 &m, float lo, float hi) {
+    const float rx = m.x - x, ry = m.y - y, rz = m.z - z;
+    const float s2 = fmaf(rz, rz, fmaf(ry, ry, rx * rx));
+    return (s2 < lo) ? PB_EVAL : ((s2 > hi) ? 0 : PB_SLOW);      // NaN -> PB_SLOW -> exact path
+}
 // stage 1b, for a pair known to be in range: collision test + "moving away" gate (rvo_inter.py:131-161)
 __device__ __forceinline__ int pair_near_fast(const Params &P, double x, double y, double z, double vx, double vy, double vz,
                                               double r, const double *so, int st) {
@@ -261,8 +269,9 @@ __device__ __forceinline__ int pair_near_fast(const Params &P, double x, double 
     const double d2 = rel_y * rel_y + rel_x * rel_x + rel_z * rel_z;
     const double Rc = P.env_train ? r + mr : r - P.exp_radius + mr, c2 = Rc * Rc;
     const double dotp = vx * rel_x + vy * rel_y + vz * rel_z;
+    const bool same = (x == mx) & (y == my) & (z == mz);     // how the reference excludes "self" (rvo_inter.py:92)
     const bool col = d2 < c2 * (1.0 - 1e-14), amb = !(col | (d2 > c2 * (1.0 + 1e-14)));
-    return amb ? PB_SLOW : (col ? PB_COL : ((dotp > 0.0) ? PB_FULL : 0));
+    return same ? PB_SAME : (amb ? PB_SLOW : (col ? PB_COL : ((dotp > 0.0) ? PB_FULL : 0)));
 }
 
 // Stage 2 of a pair: the cone (rvo_inter.py:165-196, vel_obs3D.py:8-66,145-182), itself split in three so that the

@@ -288,12 +288,21 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 128 ? UAISA_MINB128 : 1)) uaisa
                     const int jn = min(32, N - jb);
                     if constexpr (MAXR > 4) {                     // many neighbours: fp32 pre-gate on float copies of the positions
                         const float fx = (float)d.px, fy = (float)d.py, fz = (float)d.pz;
+                        if (jn == 32) {                          // full chunk: fixed trip count, fully unrolled -> 32 independent gates in flight
+#pragma unroll
+                            for (int jj = 0; jj < 32; jj++) {
+                                const int bits = (jb + jj == wk) ? 0 : pair_range_f32(fx, fy, fz, sxf[wlbase + jb + jj], nbr2_lo_f, nbr2_hi_f);
+                                near |= (bits & PB_EVAL) ? (1u << jj) : 0u;
+                                slow |= (bits & PB_SLOW) ? (1u << jj) : 0u;
+                            }
+                        } else {
 #pragma unroll 8
-                        for (int jj = 0; jj < jn; jj++) {        // stage 1a: who is within range (fp32, branch-free, overlapped)
-                            const int j = jb + jj;
-                            const int bits = (j == wk) ? 0 : pair_range_f32(fx, fy, fz, sxf[wlbase + j], nbr2_lo_f, nbr2_hi_f);
-                            near |= (bits & PB_EVAL) ? (1u << jj) : 0u;
-                            slow |= (bits & PB_SLOW) ? (1u << jj) : 0u;
+                            for (int jj = 0; jj < jn; jj++) {    // stage 1a: who is within range (fp32, branch-free, overlapped)
+                                const int j = jb + jj;
+                                const int bits = (j == wk) ? 0 : pair_range_f32(fx, fy, fz, sxf[wlbase + j], nbr2_lo_f, nbr2_hi_f);
+                                near |= (bits & PB_EVAL) ? (1u << jj) : 0u;
+                                slow |= (bits & PB_SLOW) ? (1u << jj) : 0u;
+                            }
                         }
                     } else {                                      // a handful of neighbours: the fp64 gate directly
 #pragma unroll 4

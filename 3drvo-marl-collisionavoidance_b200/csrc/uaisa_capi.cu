@@ -67,7 +67,16 @@ int dalloc(UaisaHandle *h, T **p, size_t n) {
 
 int launch(UaisaHandle *h, const Launch &L, void *stream) {
     if (!h->scenarios_set) return fail(UAISA_ESTATE, "uaisa_set_scenarios has not been called");
-    h->kernel<<<h->grid, h->threads, h->smem, static_cast<cudaStream_t>(stream)>>>(h->P, L);
+    if (h->P.cl > 1) {     // thread-block cluster launch: the G CTAs of an env are co-scheduled and share the hardware cluster barrier
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(h->grid); cfg.blockDim = dim3(h->threads); cfg.dynamicSmemBytes = h->smem; cfg.stream = static_cast<cudaStream_t>(stream);
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = h->P.cl; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        CK(cudaLaunchKernelEx(&cfg, h->kernel, h->P, L));
+    } else {
+        h->kernel<<<h->grid, h->threads, h->smem, static_cast<cudaStream_t>(stream)>>>(h->P, L);
+    }
     h->launches++;
     CK(cudaGetLastError());
     return UAISA_OK;
@@ -128,28 +137,32 @@ int uaisa_create(const UaisaConfig *cfg, UaisaHandle **out) {
     P.nbr2_lo = P.nbr_range * P.nbr_range * (1.0 - 1e-14); P.nbr2_hi = P.nbr_range * P.nbr_range * (1.0 + 1e-14);
     // launch geometry: whole envs per CTA; shrink the CTA until the grid covers the 148 SMs twice
     int threads = cfg->threads_per_block;
-    const int minthreads = ((N + 31) / 32) * 32;
+    const bool cluster = N > 128;                 // an env that does not fit one 128-thread CTA is spread over a thread-block cluster
+    const int minthreads = cluster ? 32 : ((N + 31) / 32) * 32;
     if (threads <= 0) {
-        threads = minthreads > 128 ? minthreads : 128;
-        while (threads / 2 >= minthreads && threads / 2 >= 32 && (E + (threads / N) - 1) / (threads / N) < 2 * prop.multiProcessorCount) threads /= 2;
+        threads = 128;
+        auto grid_for = [&](int th) { return cluster ? (long long)E * ((N + th - 1) / th) : (long long)(E + (th / N) - 1) / (th / N); };
+        while (threads / 2 >= minthreads && threads / 2 >= 32 && (!cluster || (N + threads / 2 - 1) / (threads / 2) <= 8) &&
+               grid_for(threads) < 2 * prop.multiProcessorCount) threads /= 2;
     }
-    if (threads < N || threads > 1024 || threads % 32) { delete h; return fail(UAISA_EINVAL, "threads_per_block must be a multiple of 32 in [n_drones, 1024]"); }
-    h->threads = threads; P.threads = threads; P.envs_per_cta = threads / N;
+    if (cluster) {
+        if (threads > 128 || threads % 32 || (N + threads - 1) / threads > 8) { delete h; return fail(UAISA_EINVAL, "n_drones > 128 needs threads_per_block in {32,64,96,128} with at most 8 CTAs per env"); }
+        P.cl = (N + threads - 1) / threads;
+    } else if (threads < N || threads > 128 || threads % 32) { delete h; return fail(UAISA_EINVAL, "threads_per_block must be a multiple of 32 in [n_drones, 128]"); }
+    h->threads = threads; P.threads = threads; P.envs_per_cta = cluster ? 1 : threads / N;
     // CTA-level compaction of the re-observe phase pays only with several warps per CTA and more than a handful of
     // drones per env (measured: N=16 +7 %, N=4 +2 % at 128 threads, -10 % with single-warp CTAs)
-    P.compact = (threads >= 128 && N > 4 && !std::getenv("UAISA_NO_COMPACT")) ? 1 : 0;
-    h->grid = (E + P.envs_per_cta - 1) / P.envs_per_cta;
+    P.compact = (!cluster && threads >= 128 && N > 4 && !std::getenv("UAISA_NO_COMPACT")) ? 1 : 0;
+    h->grid = cluster ? E * P.cl : (E + P.envs_per_cta - 1) / P.envs_per_cta;
     const int need = cfg->nm < N - 1 ? cfg->nm : N - 1;
-    const int maxr = threads > 256 ? 16 : (need <= 4 ? 4 : need <= 10 ? 10 : 16);
+    const int maxr = need <= 4 ? 4 : need <= 10 ? 10 : 16;
     P.tile0_bytes = ((32 * P.obs_dim * 4) + 15) & ~15; P.tile1_bytes = ((32 * (P.nm ? P.nm : 1) * 4) + 15) & ~15;
-    h->smem = sizeof(double) * 8 * threads + sizeof(int) * 2 * P.envs_per_cta + 16 + P.tile0_bytes + P.tile1_bytes   // + TMA fill tiles
+    h->smem = sizeof(double) * 8 * (cluster ? N : threads) + sizeof(int) * 2 * P.envs_per_cta + 16 + P.tile0_bytes + P.tile1_bytes   // + TMA fill tiles
               + (maxr > 4 ? (size_t)threads * maxr * 24 : 0)                                      // + shared top-nm lists
               + (size_t)threads * (4 * 8 + 3 * 4) + sizeof(int) * (P.envs_per_cta + 2) + 16           // + re-observe compaction
-              + (size_t)threads * 16 + 16;                                                        // + fp32 position copies
-    const bool wl = (N <= 32) && (32 % N == 0) && threads <= 128;   // every env inside one warp
-    if (threads > 256) h->kernel = uaisa_env_kernel<16, 1024, false>;
-    else if (threads > 128) h->kernel = need <= 4 ? uaisa_env_kernel<4, 256, false> : need <= 10 ? uaisa_env_kernel<10, 256, false> : uaisa_env_kernel<16, 256, false>;
-    else if (wl) h->kernel = need <= 4 ? uaisa_env_kernel<4, 128, true> : need <= 10 ? uaisa_env_kernel<10, 128, true> : uaisa_env_kernel<16, 128, true>;
+              + (size_t)(cluster ? N : threads) * 16 + 16;                                       // + fp32 position copies
+    const bool wl = (N <= 32) && (32 % N == 0);   // every env inside one warp
+    if (wl) h->kernel = need <= 4 ? uaisa_env_kernel<4, 128, true> : need <= 10 ? uaisa_env_kernel<10, 128, true> : uaisa_env_kernel<16, 128, true>;
     else h->kernel = need <= 4 ? uaisa_env_kernel<4, 128, false> : need <= 10 ? uaisa_env_kernel<10, 128, false> : uaisa_env_kernel<16, 128, false>;
     if (h->smem > (size_t)prop.sharedMemPerBlockOptin) { delete h; return fail(UAISA_EINVAL, "shared memory per CTA exceeds the device limit; lower threads_per_block"); }
     cudaError_t e = cudaFuncSetAttribute(reinterpret_cast<const void *>(h->kernel), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem);
@@ -161,11 +174,13 @@ int uaisa_create(const UaisaConfig *cfg, UaisaHandle **out) {
         (rc = dalloc(h, &pr, SN)) || (rc = dalloc(h, &bld, S * P.M * 4)) || (rc = dalloc(h, &nbld, S)) || (rc = dalloc(h, &map, S * 3)) ||
         (rc = dalloc(h, &e2s, (size_t)E)) || (rc = dalloc(h, &P.pos_yaw, A)) || (rc = dalloc(h, &P.vel_pitch, A)) ||
         (rc = dalloc(h, &P.real_len, A)) || (rc = dalloc(h, &P.max_dev, A)) || (rc = dalloc(h, &P.extra_len, A)) ||
-        (rc = dalloc(h, &P.wpf, A)) || (rc = dalloc(h, &P.ep_len, A)) || (rc = dalloc(h, &P.counters, 32))) {
+        (rc = dalloc(h, &P.wpf, A)) || (rc = dalloc(h, &P.ep_len, A)) || (rc = dalloc(h, &P.counters, 32)) ||
+        (cluster && ((rc = dalloc(h, &P.gx, 2 * A * 6)) || (rc = dalloc(h, &P.genv, 2 * (size_t)E))))) {
         uaisa_destroy(h);
         return rc;
     }
     P.wp = wp; P.seg = sg; P.npts = npts; P.route_len = rl; P.radius = rad; P.prio = pr; P.bld = bld; P.nbld = nbld; P.map = map; P.env2scn = e2s;
+    if (cluster) cudaMemset(P.genv, 0, sizeof(int) * 2 * E);
     cudaMemset(P.extra_len, 0, sizeof(float) * A); cudaMemset(P.ep_len, 0, sizeof(int) * A); cudaMemset(P.counters, 0, 32 * 8);
     *out = h;
     return UAISA_OK;
@@ -415,7 +430,7 @@ int uaisa_step_host_sparse(UaisaHandle *h, const float *action, int32_t auto_res
         L.mode = MODE_STEP; L.T = 1; L.auto_reset = auto_reset ? 1 : 0; L.max_ep_len = max_ep_len;
         L.action = h->h_action; L.obs = h->h_obs; L.count = fl + 3 * A; L.nbr = h->h_nbr;
         L.reward = reinterpret_cast<float *>(h->sp_dev + h->sp_off_reward); L.done = fl; L.info = fl + A; L.finish = fl + 2 * A;
-        h->kernel<<<h->grid, h->threads, h->smem, s>>>(h->P, L);
+        { int rc_ = launch(h, L, s); if (rc_) { cudaGraph_t g_ = nullptr; cudaStreamEndCapture(s, &g_); if (g_) cudaGraphDestroy(g_); return rc_; } h->launches--; }
         uaisa_pack_kernel<<<(unsigned)((A + 127) / 128), 128, 0, s>>>((int)A, P.obs_dim, P.nm, h->h_obs, fl + 3 * A, h->h_nbr,
                                                                     reinterpret_cast<float *>(h->sp_dev + h->sp_off_self),
                                                                     h->sp_dev + h->sp_off_rows, reinterpret_cast<int *>(h->sp_dev), h->sp_cap);

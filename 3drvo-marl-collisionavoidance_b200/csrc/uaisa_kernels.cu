@@ -51,6 +51,11 @@ __device__ __forceinline__ void bulk_fill(char *dst, const void *tile, int tile_
     for (int off = 0; off < bytes; off += tile_bytes) bulk_store(dst + off, tile, (uint32_t)min(tile_bytes, bytes - off));   // normally ONE op
 }
 
+// hardware barrier over all threads of the thread-block cluster, with release/acquire ordering at cluster scope
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 enum Phase : int { PH_A = 0, PH_B = 1, PH_OBS = 2 };
 
 // Optional per-region cycle accounting (build with -DUAISA_REGION_CLOCKS; lane 0 of every warp accumulates
@@ -76,8 +81,13 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 128 ? UAISA_MINB128 : 1)) uaisa
 #define ENV_SYNC() do { if (WL) __syncwarp(); else __syncthreads(); } while (0)
     extern __shared__ double smem_d[];
     const int threads = P.threads;
-    double *sx = smem_d;                                                         // [8][threads] exchange
-    int *senv = reinterpret_cast<int *>(sx + 8 * threads);                       // [envs_per_cta] reduction bits
+    // Cluster mode (P.cl = G > 1, N > 128): one env is spread over a thread-block cluster of G CTAs.  Every CTA keeps a full
+    // copy of the env's exchange columns in its own shared memory; at each publish point the CTAs write their slice to a
+    // double-buffered global (L2) exchange array, meet at the hardware cluster barrier and reload all N columns.
+    const bool CLM = !WL && P.cl > 1;
+    const int sst = CLM ? P.N : threads;                                         // column stride of the exchange tile
+    double *sx = smem_d;                                                         // [8][sst] exchange
+    int *senv = reinterpret_cast<int *>(sx + 8 * sst);                           // [envs_per_cta] reduction bits
     int *ssel = senv + P.envs_per_cta;                                           // [envs_per_cta] obs selected
     // constant tiles for the TMA fills (WL only), 16-byte aligned after the arrays above
     uint4 *tile0 = reinterpret_cast<uint4 *>((reinterpret_cast<uintptr_t>(ssel + P.envs_per_cta) + 15) & ~uintptr_t(15));
@@ -99,15 +109,19 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 128 ? UAISA_MINB128 : 1)) uaisa
     __syncthreads();
 
     const int tid = threadIdx.x, N = P.N, lane = tid & 31;
+    const int crank = CLM ? (int)(blockIdx.x % P.cl) : 0;
     const unsigned env_lanes = WL ? (N >= 32 ? 0xffffffffu : (((1u << N) - 1u) << (lane - lane % N))) : 0u;
-    const int le = tid / N, k = tid - le * N;
-    const int env0 = blockIdx.x * P.envs_per_cta;
+    const int le = CLM ? 0 : tid / N, k = CLM ? crank * threads + tid : tid - le * N;
+    const int env0 = CLM ? (int)(blockIdx.x / P.cl) : blockIdx.x * P.envs_per_cta;
     const int env = env0 + le;
-    const bool valid = (le < P.envs_per_cta) && (env < P.E);
+    const bool valid = CLM ? (k < N) : ((le < P.envs_per_cta) && (env < P.E));
     const int lbase = le * N;
     const int A = P.E * N;
     const int a = valid ? env * N + k : 0;
-    const int nag_here = min(P.envs_per_cta, P.E - env0) * N;   // agents of this CTA: contiguous from env0*N
+    const int scol = CLM ? k : tid;                               // my column in the exchange tile
+    const int ag0 = CLM ? env0 * N + crank * threads : env0 * N;  // first agent of this CTA (its agents are contiguous)
+    const int nag_here = CLM ? max(0, min(threads, N - crank * threads)) : min(P.envs_per_cta, P.E - env0) * N;
+    int pubn = 0;                                                 // publish counter (selects the global exchange buffer)
     const int cap = min(P.nm, MAXR);
     const bool is_step = L.mode == MODE_STEP;
     const bool do_auto = (L.mode == MODE_AUTORESET) || (is_step && L.auto_reset);
@@ -128,7 +142,11 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 128 ? UAISA_MINB128 : 1)) uaisa
         d.real_len = P.real_len[a]; d.max_dev = P.max_dev[a];
         const int wf = P.wpf[a]; d.i = wf & WP_MASK; d.flags = wf & (FLAG_ARRIVE | FLAG_DEST);
         if (do_auto) ep_len = P.ep_len[a];
-        sx[6 * threads + tid] = C.radius; sx[7 * threads + tid] = C.prio;      // constant over the launch
+        if (!CLM) { sx[6 * sst + scol] = C.radius; sx[7 * sst + scol] = C.prio; }      // constant over the launch
+    }
+    if (CLM) {   // every CTA of the cluster needs the constants of ALL drones of the env
+        const int s_ = __ldg(P.env2scn + env0);
+        for (int j = tid; j < N; j += blockDim.x) { sx[6 * sst + j] = __ldg(P.radius + s_ * N + j); sx[7 * sst + j] = __ldg(P.prio + s_ * N + j); }
     }
     unsigned n_rng = 0, n_cone = 0, n_bad = 0;
     const int T = is_step ? L.T : 1;
@@ -162,7 +180,7 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 128 ? UAISA_MINB128 : 1)) uaisa
                     if (lane == 0) bulk_commit();
                 }
             } else {
-                const size_t abase = (size_t)t * A + (size_t)env0 * N;
+                const size_t abase = (size_t)t * A + (size_t)ag0;
                 if (L.obs) fill_out(reinterpret_cast<uint32_t *>(L.obs + abase * P.obs_dim), nag_here * P.obs_dim, 0u, tid, blockDim.x);
                 if (L.nbr) fill_out(reinterpret_cast<uint32_t *>(L.nbr + abase * P.nm), nag_here * P.nm, ~0u, tid, blockDim.x);
             }
@@ -189,6 +207,14 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 128 ? UAISA_MINB128 : 1)) uaisa
                 if (L.mode == MODE_RESET) {
                     rs = valid && (L.mask == nullptr || L.mask[a]);
                     if (WL) sel = (__ballot_sync(0xffffffffu, rs) & env_lanes) != 0;
+                    else if (CLM) {
+                        int *ge = P.genv + env0;
+                        if (rs) atomicOr(ge, 1);
+                        cluster_sync_all();
+                        sel = valid && (__ldcg(ge) != 0);
+                        cluster_sync_all();
+                        if (crank == 0 && tid == 0) *ge = 0;
+                    }
                     else { __syncthreads(); if (rs) ssel[le] = 1; __syncthreads(); sel = valid && ssel[le]; }   // benign race: all write 1
                 } else if (L.mode == MODE_OBSERVE) {
                     sel = valid && (L.mask == nullptr || L.mask[env]);
@@ -203,6 +229,13 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 128 ? UAISA_MINB128 : 1)) uaisa
                         const unsigned bd = __ballot_sync(0xffffffffu, valid && st_done), bf = __ballot_sync(0xffffffffu, valid && st_fin);
                         const unsigned bn = __ballot_sync(0xffffffffu, valid && !st_fin), bo = __ballot_sync(0xffffffffu, over);
                         bits = ((bd & env_lanes) ? 1 : 0) | ((bf & env_lanes) ? 2 : 0) | ((bn & env_lanes) ? 4 : 0) | ((bo & env_lanes) ? 8 : 0);
+                    } else if (CLM) {
+                        int *ge = P.genv + env0;
+                        if (valid) atomicOr(ge, (st_done ? 1 : 0) | (st_fin ? 2 : 4) | (over ? 8 : 0));
+                        cluster_sync_all();
+                        bits = valid ? __ldcg(ge) : 0;
+                        cluster_sync_all();                                    // everybody has read the bits: re-arm the slot
+                        if (crank == 0 && tid == 0) *ge = 0;
                     } else {
                         __syncthreads();
                         if (valid) atomicOr(&senv[le], (st_done ? 1 : 0) | (st_fin ? 2 : 4) | (over ? 8 : 0));
@@ -228,10 +261,22 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 128 ? UAISA_MINB128 : 1)) uaisa
             // -------------------------------------------------------- publish my state, then read the others'
             if (WL && is_step && ph == PH_B && lane == 0) bulk_wait_all();   // my warp's cleared rows have landed: rows may now be scattered
             ENV_SYNC();   // everybody is done reading the previous phase's columns
-            if (valid) {
-                sx[0 * threads + tid] = d.px; sx[1 * threads + tid] = d.py; sx[2 * threads + tid] = d.pz;
-                sx[3 * threads + tid] = d.vx; sx[4 * threads + tid] = d.vy; sx[5 * threads + tid] = d.vz;
-                if constexpr (MAXR > 4) sxf[tid] = make_float4((float)d.px, (float)d.py, (float)d.pz, 0.f);
+            if (CLM) {
+                double *gb = P.gx + ((size_t)(pubn & 1) * A + (size_t)env0 * N) * 6;      // this env's slice of the exchange buffer
+                if (valid) { double *g = gb + (size_t)k * 6; g[0] = d.px; g[1] = d.py; g[2] = d.pz; g[3] = d.vx; g[4] = d.vy; g[5] = d.vz; }
+                pubn++;
+                cluster_sync_all();                        // every CTA of the env has written its slice (release/acquire at cluster scope)
+                for (int j = tid; j < N; j += blockDim.x) {
+                    const double *g = gb + (size_t)j * 6;  // L1 is not coherent across SMs: read through L2
+                    const double x_ = __ldcg(g), y_ = __ldcg(g + 1), z_ = __ldcg(g + 2);
+                    sx[0 * sst + j] = x_; sx[1 * sst + j] = y_; sx[2 * sst + j] = z_;
+                    sx[3 * sst + j] = __ldcg(g + 3); sx[4 * sst + j] = __ldcg(g + 4); sx[5 * sst + j] = __ldcg(g + 5);
+                    if constexpr (MAXR > 4) sxf[j] = make_float4((float)x_, (float)y_, (float)z_, 0.f);
+                }
+            } else if (valid) {
+                sx[0 * sst + scol] = d.px; sx[1 * sst + scol] = d.py; sx[2 * sst + scol] = d.pz;
+                sx[3 * sst + scol] = d.vx; sx[4 * sst + scol] = d.vy; sx[5 * sst + scol] = d.vz;
+                if constexpr (MAXR > 4) sxf[scol] = make_float4((float)d.px, (float)d.py, (float)d.pz, 0.f);
             }
             if (ph == PH_OBS && compact) {
                 // Only the envs touched by the reset policy are re-observed (typically a quarter of them, spread over
@@ -308,14 +353,14 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 128 ? UAISA_MINB128 : 1)) uaisa
 #pragma unroll 4
                         for (int jj = 0; jj < jn; jj++) {
                             const int j = jb + jj;
-                            const int bits = (j == wk) ? 0 : pair_range_fast(P, d.px, d.py, d.pz, sx + wlbase + j, threads);
+                            const int bits = (j == wk) ? 0 : pair_range_fast(P, d.px, d.py, d.pz, sx + wlbase + j, sst);
                             near |= (bits & PB_EVAL) ? (1u << jj) : 0u;
                             slow |= (bits & PB_SLOW) ? (1u << jj) : 0u;
                         }
                     }
                     for (unsigned m = near; m; m &= m - 1) {     // stage 1b: collision / moving-away gates of the near ones (fp64)
                         const int jj = __ffs(m) - 1;
-                        const int bits = pair_near_fast(P, d.px, d.py, d.pz, d.vx, d.vy, d.vz, C.radius, sx + wlbase + jb + jj, threads);
+                        const int bits = pair_near_fast(P, d.px, d.py, d.pz, d.vx, d.vy, d.vz, C.radius, sx + wlbase + jb + jj, sst);
                         n_rng += (bits & PB_SAME) ? 0u : 1u;
                         col |= (bits & PB_COL) != 0;
                         cand |= (bits & PB_FULL) ? (1u << jj) : 0u;
@@ -323,7 +368,7 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 128 ? UAISA_MINB128 : 1)) uaisa
                     }
                     for (unsigned m = slow; m; m &= m - 1) {     // a squared distance inside a guard band: exact comparisons
                         const int jj = __ffs(m) - 1;
-                        const int bits = pair_gate(P, d.px, d.py, d.pz, d.vx, d.vy, d.vz, C.radius, sx + wlbase + jb + jj, threads);
+                        const int bits = pair_gate(P, d.px, d.py, d.pz, d.vx, d.vy, d.vz, C.radius, sx + wlbase + jb + jj, sst);
                         n_rng += ((bits & PB_EVAL) && !((near >> jj) & 1u)) ? 1u : 0u;   // (pairs already counted in stage 1b are not counted twice)
                         col |= (bits & PB_COL) != 0;
                         cand |= (bits & PB_FULL) ? (1u << jj) : 0u;
@@ -333,14 +378,14 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 128 ? UAISA_MINB128 : 1)) uaisa
                     unsigned ins = 0, amb = 0;
                     for (unsigned m = cand; m; m &= m - 1) {
                         const int jj = __ffs(m) - 1;
-                        PairGeom g; pair_geom(P, d.px, d.py, d.pz, d.vx, d.vy, d.vz, C.radius, C.prio, sx + wlbase + jb + jj, threads, bx, by, bz, g);
+                        PairGeom g; pair_geom(P, d.px, d.py, d.pz, d.vx, d.vy, d.vz, C.radius, C.prio, sx + wlbase + jb + jj, sst, bx, by, bz, g);
                         const int c = cone_screen(g);
                         ins |= (c == 1) ? (1u << jj) : 0u; amb |= (c == 2) ? (1u << jj) : 0u;
                     }
                     // stage 2b: the few ambiguous pairs go through asin/acos with the reference's roundings
                     for (unsigned m = amb; m; m &= m - 1) {
                         const int jj = __ffs(m) - 1;
-                        PairGeom g; pair_geom(P, d.px, d.py, d.pz, d.vx, d.vy, d.vz, C.radius, C.prio, sx + wlbase + jb + jj, threads, bx, by, bz, g);
+                        PairGeom g; pair_geom(P, d.px, d.py, d.pz, d.vx, d.vy, d.vz, C.radius, C.prio, sx + wlbase + jb + jj, sst, bx, by, bz, g);
                         double ah;
                         if (cone_exact(g, ah)) ins |= 1u << jj;
                     }
@@ -348,9 +393,9 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 128 ? UAISA_MINB128 : 1)) uaisa
                     for (unsigned m = ins; m; m &= m - 1) {
                         const int jj = __ffs(m) - 1, j = jb + jj;
                         const double *so = sx + wlbase + j;
-                        PairGeom g; pair_geom(P, d.px, d.py, d.pz, d.vx, d.vy, d.vz, C.radius, C.prio, so, threads, bx, by, bz, g);
+                        PairGeom g; pair_geom(P, d.px, d.py, d.pz, d.vx, d.vy, d.vz, C.radius, C.prio, so, sst, bx, by, bz, g);
                         double tt, md, iet;
-                        if (cone_time(P, d.vx, d.vy, d.vz, C.radius, so, threads, bx, by, bz, g, tt, md, iet)) {
+                        if (cone_time(P, d.vx, d.vy, d.vz, C.radius, so, sst, bx, by, bz, g, tt, md, iet)) {
                             vo_any = true; if (tt < tmin) tmin = tt;
                             if (ph != PH_A) {
                                 const double ah = py_round2_hundredths(asin(g.R / sqrt(g.s2)));   // get_alpha, vel_obs3D.py:8-17
@@ -417,8 +462,8 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 128 ? UAISA_MINB128 : 1)) uaisa
                     const int r = top.cnt - 1 - sl;
                     const double *so = sx + wlbase + t_j;
                     if (wobs) {
-                        const double mx = so[0], my = so[threads], mz = so[2 * threads];
-                        const double mvx = so[3 * threads], mvy = so[4 * threads], mvz = so[5 * threads], prb = so[7 * threads];
+                        const double mx = so[0], my = so[sst], mz = so[2 * sst];
+                        const double mvx = so[3 * sst], mvy = so[4 * sst], mvz = so[5 * sst], prb = so[7 * sst];
                         const double pr = (C.prio == prb) ? 0.5 : fast_div(C.prio, C.prio + prb);
                         const double v[ROW] = {pr * (2.0 * d.px + (d.vx + mvx) * 1.0), pr * (2.0 * d.py + (d.vy + mvy) * 1.0),
                                                pr * (2.0 * d.pz + (d.vz + mvz) * 1.0), mx - d.px, my - d.py, mz - d.pz,
@@ -604,7 +649,6 @@ __global__ void uaisa_pack_kernel(int A, int obs_dim, int nm, const float *obs, 
 #define UAISA_INST(R, T, W) template __global__ void uaisa_env_kernel<R, T, W>(const __grid_constant__ Params, const __grid_constant__ Launch);
 UAISA_INST(4, 128, true) UAISA_INST(10, 128, true) UAISA_INST(16, 128, true)
 UAISA_INST(4, 128, false) UAISA_INST(10, 128, false) UAISA_INST(16, 128, false)
-UAISA_INST(4, 256, false) UAISA_INST(10, 256, false) UAISA_INST(16, 256, false) UAISA_INST(16, 1024, false)
 #undef UAISA_INST
 
 }  // namespace uaisa

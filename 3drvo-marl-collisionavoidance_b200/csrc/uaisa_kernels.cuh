@@ -37,6 +37,8 @@ struct Params {
     int envs_per_cta, threads;
     int tile0_bytes, tile1_bytes;   // constant smem tiles behind the TMA fills (zeros / 0xFF), multiples of 16
     int env_train, count_pairs, compact;
+    int cl;                          // CTAs per env (thread-block cluster size) when an env does not fit one CTA; 0 = one CTA holds whole envs
+    double *gx; int *genv;           // cluster mode: global exchange buffers [2][A][6] (p, v in fp64) and [2][E] (reset-policy bits)
     // hyper-parameters (reference constructor defaults, see include/uaisa_b200.h)
     double goal_thr, max_acc, max_ang, dt, vel_max, nbr_range, bld_range, bld_zgate, ctime, delta_t, exp_radius;
     double goal2_lo, goal2_hi, nbr2_lo, nbr2_hi;   // T^2*(1 -+ 1e-14) guard bands for sqrt(x) <= T (host-computed)

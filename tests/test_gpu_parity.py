@@ -56,11 +56,13 @@ def test_dense_256():
     assert st.rows > 0
 
 
-def test_more_than_256_drones_per_env():
-    """N > 256 uses the 1024-thread instantiation (one CTA of ceil32(N) threads per env)."""
-    scn = scenario_c4(seed=3, n_scenarios=1, n_drones=300)
-    st = lockstep(scn, 2, 10, 6, seed=9, block=2)
+@pytest.mark.parametrize("N,tpb", [(300, 0), (200, 64), (130, 32), (256, 128)])
+def test_cluster_mode_envs_larger_than_one_cta(N, tpb):
+    """N > 128: one env is spread over a thread-block cluster (exchange through L2 + hardware cluster barrier)."""
+    scn = scenario_c4(seed=3, n_scenarios=1, n_drones=N)
+    st = lockstep(scn, 3, 10, 6, seed=9, block=2, threads_per_block=tpb, max_ep_len=4)
     st.assert_parity()
+    assert st.rows > 0 and st.resets > 0
 
 
 def test_edge_shapes():
@@ -69,7 +71,7 @@ def test_edge_shapes():
     lockstep(one, 5, 10, 40, seed=1).assert_parity()
     lockstep(scenario_world3(), 7, 0, 40, seed=2).assert_parity()
     lockstep(scenario_world3(), 50, 10, 40, seed=3, threads_per_block=32).assert_parity()
-    lockstep(swarm(12, 1.0, 7), 30, 10, 40, seed=4, threads_per_block=256).assert_parity()
+    lockstep(swarm(12, 1.0, 7), 30, 10, 40, seed=4, threads_per_block=64).assert_parity()
     lockstep(scenario_c1(), 9, 10, 40, seed=5, env_train=0).assert_parity()
 
 

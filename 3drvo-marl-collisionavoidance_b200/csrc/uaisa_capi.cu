@@ -2,6 +2,7 @@
 // Host-side only: handle management, scenario upload, launch geometry, error reporting.
 #include <cuda_runtime.h>
 
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -47,7 +48,7 @@ struct UaisaHandle {
     int32_t *h_nbr = nullptr;
     cudaStream_t h_stream = nullptr;
     // uaisa_step_host_sparse: device block + pinned host mirror + one captured graph
-    char *sp_dev = nullptr, *sp_host = nullptr; float *sp_hact = nullptr;
+    char *sp_dev = nullptr, *sp_host = nullptr; float *sp_hact = nullptr, *sp_hact_dev = nullptr;
     size_t sp_off_reward = 0, sp_off_self = 0, sp_off_flags = 0, sp_off_rows = 0, sp_bytes = 0, sp_phase1 = 0;
     int sp_cap = 0, sp_r0 = 0, sp_auto = -1, sp_maxlen = -1;
     cudaGraphExec_t sp_graph = nullptr;
@@ -407,7 +408,8 @@ static int sparse_setup(UaisaHandle *h) {
     h->sp_bytes = h->sp_off_rows + sizeof(UaisaRowRec) * (size_t)h->sp_cap;
     if ((rc = dalloc(h, &h->sp_dev, h->sp_bytes))) return rc;
     CK(cudaHostAlloc(reinterpret_cast<void **>(&h->sp_host), h->sp_bytes, cudaHostAllocDefault));
-    CK(cudaHostAlloc(reinterpret_cast<void **>(&h->sp_hact), sizeof(float) * A * 3, cudaHostAllocDefault));
+    CK(cudaHostAlloc(reinterpret_cast<void **>(&h->sp_hact), sizeof(float) * A * 3, cudaHostAllocMapped));   // read by the kernel straight over PCIe
+    CK(cudaHostGetDevicePointer(reinterpret_cast<void **>(&h->sp_hact_dev), h->sp_hact, 0));
     return UAISA_OK;
 }
 
@@ -423,12 +425,14 @@ int uaisa_step_host_sparse(UaisaHandle *h, const float *action, int32_t auto_res
         CK(cudaStreamSynchronize(s));
         cudaGraph_t graph = nullptr;
         CK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
-        cudaMemcpyAsync(h->h_action, h->sp_hact, sizeof(float) * A * 3, cudaMemcpyHostToDevice, s);
+        // small batches: the kernel reads the action straight from mapped pinned memory (no H2D node); large ones use the copy engine
+        const bool zero_copy = A * 3 * sizeof(float) <= (size_t(1) << 20);
+        if (!zero_copy) cudaMemcpyAsync(h->h_action, h->sp_hact, sizeof(float) * A * 3, cudaMemcpyHostToDevice, s);
         cudaMemsetAsync(h->sp_dev, 0, 16, s);
         uint8_t *fl = reinterpret_cast<uint8_t *>(h->sp_dev + h->sp_off_flags);
         Launch L{};
         L.mode = MODE_STEP; L.T = 1; L.auto_reset = auto_reset ? 1 : 0; L.max_ep_len = max_ep_len;
-        L.action = h->h_action; L.obs = h->h_obs; L.count = fl + 3 * A; L.nbr = h->h_nbr;
+        L.action = zero_copy ? h->sp_hact_dev : h->h_action; L.obs = h->h_obs; L.count = fl + 3 * A; L.nbr = h->h_nbr;
         L.reward = reinterpret_cast<float *>(h->sp_dev + h->sp_off_reward); L.done = fl; L.info = fl + A; L.finish = fl + 2 * A;
         { int rc_ = launch(h, L, s); if (rc_) { cudaGraph_t g_ = nullptr; cudaStreamEndCapture(s, &g_); if (g_) cudaGraphDestroy(g_); return rc_; } h->launches--; }
         uaisa_pack_kernel<<<(unsigned)((A + 127) / 128), 128, 0, s>>>((int)A, P.obs_dim, P.nm, h->h_obs, fl + 3 * A, h->h_nbr,
@@ -442,10 +446,21 @@ int uaisa_step_host_sparse(UaisaHandle *h, const float *action, int32_t auto_res
         if (ce != cudaSuccess) return cuda_fail(ce, "cudaGraphInstantiate");
         h->sp_auto = auto_reset; h->sp_maxlen = max_ep_len;
     }
+    static const bool prof = std::getenv("UAISA_HOST_PROF") != nullptr;
+    static double acc[3] = {0, 0, 0}; static long nprof = 0;
+    auto now = [] { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t0 = prof ? now() : 0;
     std::memcpy(h->sp_hact, action, sizeof(float) * A * 3);
+    const double t1 = prof ? now() : 0;
     CK(cudaGraphLaunch(h->sp_graph, s));
+    const double t2 = prof ? now() : 0;
     h->launches += 2;
     CK(cudaStreamSynchronize(s));
+    if (prof) {
+        const double t3 = now();
+        acc[0] += t1 - t0; acc[1] += t2 - t1; acc[2] += t3 - t2;
+        if (++nprof % 200 == 0) { std::fprintf(stderr, "[uaisa host step] memcpy %.1f us, graph launch %.1f us, sync wait %.1f us (avg of 200)\n", acc[0] / 200, acc[1] / 200, acc[2] / 200); acc[0] = acc[1] = acc[2] = 0; }
+    }
     int n_rows = *reinterpret_cast<int *>(h->sp_host);
     if (n_rows > h->sp_cap) return fail(UAISA_EINVAL, "neighbour-row capacity of the host block exceeded");
     if (n_rows > h->sp_r0) {   // rare: more rows than the first-phase window

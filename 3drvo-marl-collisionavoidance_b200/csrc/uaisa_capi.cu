@@ -48,7 +48,7 @@ struct UaisaHandle {
     int32_t *h_nbr = nullptr;
     cudaStream_t h_stream = nullptr;
     // uaisa_step_host_sparse: device block + pinned host mirror + one captured graph
-    char *sp_dev = nullptr, *sp_host = nullptr; float *sp_hact = nullptr, *sp_hact_dev = nullptr;
+    char *sp_dev = nullptr, *sp_host = nullptr, *sp_host_dev = nullptr; float *sp_hact = nullptr, *sp_hact_dev = nullptr; bool sp_zero_copy = false;
     size_t sp_off_reward = 0, sp_off_self = 0, sp_off_flags = 0, sp_off_rows = 0, sp_bytes = 0, sp_phase1 = 0;
     int sp_cap = 0, sp_r0 = 0, sp_auto = -1, sp_maxlen = -1;
     cudaGraphExec_t sp_graph = nullptr;
@@ -407,7 +407,9 @@ static int sparse_setup(UaisaHandle *h) {
     h->sp_phase1 = h->sp_off_rows + sizeof(UaisaRowRec) * (size_t)h->sp_r0;
     h->sp_bytes = h->sp_off_rows + sizeof(UaisaRowRec) * (size_t)h->sp_cap;
     if ((rc = dalloc(h, &h->sp_dev, h->sp_bytes))) return rc;
-    CK(cudaHostAlloc(reinterpret_cast<void **>(&h->sp_host), h->sp_bytes, cudaHostAllocDefault));
+    CK(cudaHostAlloc(reinterpret_cast<void **>(&h->sp_host), h->sp_bytes, cudaHostAllocMapped));
+    CK(cudaHostGetDevicePointer(reinterpret_cast<void **>(&h->sp_host_dev), h->sp_host, 0));
+    CK(cudaMemset(h->sp_dev, 0, 16));
     CK(cudaHostAlloc(reinterpret_cast<void **>(&h->sp_hact), sizeof(float) * A * 3, cudaHostAllocMapped));   // read by the kernel straight over PCIe
     CK(cudaHostGetDevicePointer(reinterpret_cast<void **>(&h->sp_hact_dev), h->sp_hact, 0));
     return UAISA_OK;
@@ -425,20 +427,36 @@ int uaisa_step_host_sparse(UaisaHandle *h, const float *action, int32_t auto_res
         CK(cudaStreamSynchronize(s));
         cudaGraph_t graph = nullptr;
         CK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
-        // small batches: the kernel reads the action straight from mapped pinned memory (no H2D node); large ones use the copy engine
-        const bool zero_copy = A * 3 * sizeof(float) <= (size_t(1) << 20);
-        if (!zero_copy) cudaMemcpyAsync(h->h_action, h->sp_hact, sizeof(float) * A * 3, cudaMemcpyHostToDevice, s);
-        cudaMemsetAsync(h->sp_dev, 0, 16, s);
+        // Small batches run as ONE kernel node: the env kernel reads the action from mapped pinned memory, writes reward / flags and
+        // (in its host-pack tail) the self parts and existing rows straight into the mapped result block, and its last CTA raises the
+        // ready word the host polls -- no copy-engine, memset or pack nodes and no stream synchronisation on the critical path.
+        // Large batches keep the copy engines: H2D action, env kernel, pack kernel, D2H of the block.
+        const bool zero_copy = A * 3 * sizeof(float) <= (size_t(1) << 20) && std::getenv("UAISA_HOST_COPY_ENGINE") == nullptr;
+        h->sp_zero_copy = zero_copy;
         uint8_t *fl = reinterpret_cast<uint8_t *>(h->sp_dev + h->sp_off_flags);
         Launch L{};
         L.mode = MODE_STEP; L.T = 1; L.auto_reset = auto_reset ? 1 : 0; L.max_ep_len = max_ep_len;
-        L.action = zero_copy ? h->sp_hact_dev : h->h_action; L.obs = h->h_obs; L.count = fl + 3 * A; L.nbr = h->h_nbr;
-        L.reward = reinterpret_cast<float *>(h->sp_dev + h->sp_off_reward); L.done = fl; L.info = fl + A; L.finish = fl + 2 * A;
+        L.obs = h->h_obs; L.count = fl + 3 * A; L.nbr = h->h_nbr;
+        if (zero_copy) {
+            uint8_t *hfl = reinterpret_cast<uint8_t *>(h->sp_host_dev + h->sp_off_flags);
+            L.action = h->sp_hact_dev;
+            L.reward = reinterpret_cast<float *>(h->sp_host_dev + h->sp_off_reward); L.done = hfl; L.info = hfl + A; L.finish = hfl + 2 * A;
+            L.hp_self = reinterpret_cast<float *>(h->sp_host_dev + h->sp_off_self); L.hp_count = hfl + 3 * A;
+            L.hp_rows = h->sp_host_dev + h->sp_off_rows; L.hp_cap = h->sp_cap;
+            L.hp_ctr = reinterpret_cast<int *>(h->sp_dev); L.hp_hdr = reinterpret_cast<unsigned long long *>(h->sp_host_dev);
+        } else {
+            cudaMemcpyAsync(h->h_action, h->sp_hact, sizeof(float) * A * 3, cudaMemcpyHostToDevice, s);
+            cudaMemsetAsync(h->sp_dev, 0, 16, s);
+            L.action = h->h_action;
+            L.reward = reinterpret_cast<float *>(h->sp_dev + h->sp_off_reward); L.done = fl; L.info = fl + A; L.finish = fl + 2 * A;
+        }
         { int rc_ = launch(h, L, s); if (rc_) { cudaGraph_t g_ = nullptr; cudaStreamEndCapture(s, &g_); if (g_) cudaGraphDestroy(g_); return rc_; } h->launches--; }
-        uaisa_pack_kernel<<<(unsigned)((A + 127) / 128), 128, 0, s>>>((int)A, P.obs_dim, P.nm, h->h_obs, fl + 3 * A, h->h_nbr,
-                                                                    reinterpret_cast<float *>(h->sp_dev + h->sp_off_self),
-                                                                    h->sp_dev + h->sp_off_rows, reinterpret_cast<int *>(h->sp_dev), h->sp_cap);
-        cudaMemcpyAsync(h->sp_host, h->sp_dev, h->sp_phase1, cudaMemcpyDeviceToHost, s);
+        if (!zero_copy) {
+            uaisa_pack_kernel<<<(unsigned)((A + 127) / 128), 128, 0, s>>>((int)A, P.obs_dim, P.nm, h->h_obs, fl + 3 * A, h->h_nbr,
+                                                                        reinterpret_cast<float *>(h->sp_dev + h->sp_off_self),
+                                                                        h->sp_dev + h->sp_off_rows, reinterpret_cast<int *>(h->sp_dev), h->sp_cap);
+            cudaMemcpyAsync(h->sp_host, h->sp_dev, h->sp_phase1, cudaMemcpyDeviceToHost, s);
+        }
         cudaError_t ce = cudaStreamEndCapture(s, &graph);
         if (ce != cudaSuccess) return cuda_fail(ce, "cudaStreamEndCapture");
         ce = cudaGraphInstantiate(&h->sp_graph, graph, 0);
@@ -452,18 +470,39 @@ int uaisa_step_host_sparse(UaisaHandle *h, const float *action, int32_t auto_res
     const double t0 = prof ? now() : 0;
     std::memcpy(h->sp_hact, action, sizeof(float) * A * 3);
     const double t1 = prof ? now() : 0;
+    volatile unsigned long long *hdr = reinterpret_cast<volatile unsigned long long *>(h->sp_host);
+    if (h->sp_zero_copy) *hdr = 0;
     CK(cudaGraphLaunch(h->sp_graph, s));
     const double t2 = prof ? now() : 0;
-    h->launches += 2;
-    CK(cudaStreamSynchronize(s));
+    int n_rows;
+    if (h->sp_zero_copy) {
+        h->launches += 1;
+        unsigned long long w = 0;
+        for (unsigned spin = 1;; spin++) {       // poll the ready word; look at the stream now and then so that a failed launch cannot hang us
+            w = __atomic_load_n(reinterpret_cast<unsigned long long *>(h->sp_host), __ATOMIC_ACQUIRE);
+            if (w & 1ull) break;
+            if ((spin & 0x3fff) == 0) {
+                cudaError_t q = cudaStreamQuery(s);
+                if (q == cudaSuccess) { w = __atomic_load_n(reinterpret_cast<unsigned long long *>(h->sp_host), __ATOMIC_ACQUIRE); if (w & 1ull) break; return fail(UAISA_ECUDA, "host step finished without publishing its result"); }
+                if (q != cudaErrorNotReady) return cuda_fail(q, "uaisa_step_host_sparse");
+            }
+#if defined(__x86_64__)
+            __builtin_ia32_pause();
+#endif
+        }
+        n_rows = (int)(w >> 32);
+    } else {
+        h->launches += 2;
+        CK(cudaStreamSynchronize(s));
+        n_rows = *reinterpret_cast<int *>(h->sp_host);
+    }
     if (prof) {
         const double t3 = now();
         acc[0] += t1 - t0; acc[1] += t2 - t1; acc[2] += t3 - t2;
-        if (++nprof % 200 == 0) { std::fprintf(stderr, "[uaisa host step] memcpy %.1f us, graph launch %.1f us, sync wait %.1f us (avg of 200)\n", acc[0] / 200, acc[1] / 200, acc[2] / 200); acc[0] = acc[1] = acc[2] = 0; }
+        if (++nprof % 200 == 0) { std::fprintf(stderr, "[uaisa host step] memcpy %.1f us, graph launch %.1f us, wait %.1f us (avg of 200)\n", acc[0] / 200, acc[1] / 200, acc[2] / 200); acc[0] = acc[1] = acc[2] = 0; }
     }
-    int n_rows = *reinterpret_cast<int *>(h->sp_host);
     if (n_rows > h->sp_cap) return fail(UAISA_EINVAL, "neighbour-row capacity of the host block exceeded");
-    if (n_rows > h->sp_r0) {   // rare: more rows than the first-phase window
+    if (!h->sp_zero_copy && n_rows > h->sp_r0) {   // rare: more rows than the first-phase window
         CK(cudaMemcpyAsync(h->sp_host + h->sp_phase1, h->sp_dev + h->sp_phase1, sizeof(UaisaRowRec) * (size_t)(n_rows - h->sp_r0), cudaMemcpyDeviceToHost, s));
         CK(cudaStreamSynchronize(s));
     }

@@ -560,6 +560,67 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 128 ? UAISA_MINB128 : 1)) uaisa
         if (extra_len_dirty) P.extra_len[a] = (float)extra_len_new;
         if (do_auto) P.ep_len[a] = ep_len;
     }
+    if (L.hp_self) {   // ---- host-pack tail: self part + existing rows of my agent -> mapped host memory, then the completion protocol
+        // Writes over PCIe want full 128-byte lines, so every warp stages its 32 agents' data in a 2 KB slice of the (now idle)
+        // exchange tile and streams it out with consecutive lanes on consecutive 16-byte words.
+        __syncthreads();                                   // all warps are done with sx; re-observe compaction: rows written by other threads
+        const int warp = tid >> 5;
+        uint4 *stg = reinterpret_cast<uint4 *>(reinterpret_cast<char *>(sx) + warp * 2048);      // sx has 64 B per thread
+        float *stg_f = reinterpret_cast<float *>(stg);
+        const int a_w = ag0 + (tid - lane);                 // first agent of this warp (a CTA's agents are contiguous)
+        const int nv_w = max(0, min(32, nag_here - (tid - lane)));
+        int kk = 0;
+        const float *o = L.obs + (size_t)a * P.obs_dim;
+        if (valid) {
+            kk = __ldcg(L.count + a);
+#pragma unroll
+            for (int q = 0; q < OBS_SELF; q++) stg_f[lane * OBS_SELF + q] = __ldcg(o + q);
+            L.hp_count[a] = (uint8_t)kk;
+        }
+        __syncwarp();
+        {
+            uint4 *hs = reinterpret_cast<uint4 *>(L.hp_self + (size_t)a_w * OBS_SELF);
+            for (int i = lane; i < nv_w * (OBS_SELF / 4); i += 32) hs[i] = stg[i];
+        }
+        __syncwarp();
+        int tot = kk, kmax = kk;                           // one reservation per warp
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) { tot += __shfl_xor_sync(0xffffffffu, tot, off); kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, off)); }
+        int base = 0;
+        if (lane == 0 && tot) base = atomicAdd(L.hp_ctr, tot);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        for (int r = 0; r < kmax; r++) {                   // round r: slot r of every agent that has one, packed and streamed together
+            const unsigned have = __ballot_sync(0xffffffffu, kk > r);
+            const int n = __popc(have);
+            if (kk > r) {
+                const int p = __popc(have & ((1u << lane) - 1u));
+                float v[ROW];
+#pragma unroll
+                for (int q = 0; q < ROW; q++) v[q] = __ldcg(o + OBS_SELF + ROW * r + q);
+                const int nb_ = L.nbr ? __ldcg(L.nbr + (size_t)a * P.nm + r) : -1;
+                stg[3 * p + 0] = make_uint4(__float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]), __float_as_uint(v[3]));   // UaisaRowRec
+                stg[3 * p + 1] = make_uint4(__float_as_uint(v[4]), __float_as_uint(v[5]), __float_as_uint(v[6]), __float_as_uint(v[7]));
+                stg[3 * p + 2] = make_uint4(__float_as_uint(v[8]), (unsigned)a, (unsigned)r, (unsigned)nb_);
+            }
+            __syncwarp();
+            const int room = max(0, min(n, L.hp_cap - base));
+            uint4 *hr = reinterpret_cast<uint4 *>(static_cast<char *>(L.hp_rows) + (size_t)base * 48);
+            for (int i = lane; i < 3 * room; i += 32) hr[i] = stg[i];
+            __syncwarp();
+            base += n;
+        }
+        __threadfence_system();                            // my host writes (these and the step's reward / flags) are performed ...
+        __syncthreads();
+        if (tid == 0) {
+            __threadfence_system();                        // ... and ordered before this CTA's arrival
+            if (atomicAdd(L.hp_ctr + 1, 1) == (int)gridDim.x - 1) {
+                __threadfence_system();
+                const int n = atomicExch(L.hp_ctr, 0);     // every reservation precedes its CTA's arrival
+                L.hp_ctr[1] = 0;                           // re-armed for the next launch
+                *reinterpret_cast<volatile unsigned long long *>(L.hp_hdr) = ((unsigned long long)(unsigned)n << 32) | 1ull;
+            }
+        }
+    }
     RG_MARK(RG_EPILOGUE);
     RG_FLUSH();
     const bool any_bad = __any_sync(0xffffffffu, n_bad != 0);

@@ -57,6 +57,14 @@ struct Launch {
     const uint8_t *done_in, *finish_in;  // MODE_AUTORESET
     float *obs; uint8_t *count; int *nbr; float *reward; uint8_t *done, *info, *finish;
     uint8_t *reset_mask, *path_cut;
+    // host-pack tail of uaisa_step_host_sparse (T == 1, NULL otherwise): the CTAs write the ragged result straight into mapped
+    // pinned HOST memory and the last one to finish publishes {1, n_rows} in *hp_hdr, which the host polls.
+    float *hp_self;              // HOST [A][12]
+    uint8_t *hp_count;           // HOST [A]
+    void *hp_rows;               // HOST [hp_cap] UaisaRowRec
+    int hp_cap;
+    int *hp_ctr;                 // DEVICE [2]: rows reserved, CTAs finished (both left at 0 by the last CTA)
+    unsigned long long *hp_hdr;  // HOST: low word = ready flag, high word = n_rows
 };
 
 // ---- numpy / python arithmetic primitives (see oracle/uaisa_oracle.c for the derivation) ----------
@@ -305,7 +313,7 @@ __device__ __forceinline__ void pair_geom(const Params &P, double x, double y, d
 // Returns 0 outside, 1 inside, 2 ambiguous (the +-0.02 band, degenerate |B| = 0, and near-collinear vectors where the
 // reference's unclamped arccos may return NaN).
 __device__ __forceinline__ int cone_screen(const PairGeom &g) {
-    if (!(g.b2 > 0.0)) return 2;
+    if (!(g.b2 > 0.0) || !(g.s2 > g.R * g.R)) return 2;      // asin(R/|rel| > 1) = NaN in the reference: let cone_exact decide
     const double inab = fast_rsqrt(g.s2), s = g.R * inab, c = g.dab * inab * fast_rsqrt(g.b2);
     const double C02 = 0.99980000666657776, S02 = 0.019998666693333084;
     const double rhs2 = fma(-s, s, 1.0) * (C02 * C02), sS = s * S02;

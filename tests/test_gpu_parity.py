@@ -205,11 +205,17 @@ def test_step_host_matches_device_step():
     a.close(); b.close()
 
 
-def test_step_host_sparse_matches_device_step():
-    """uaisa_step_host_sparse (one CUDA graph, ragged results) carries exactly the information of the dense step."""
-    scn = swarm(12, 1.0, 11)
-    a = VecMdin(scn, 20, neighbors_num=10); b = VecMdin(scn, 20, neighbors_num=10)
+@pytest.mark.parametrize("N,E,copy_engine", [(12, 20, False), (4, 67, False), (16, 9, False), (256, 2, False), (12, 20, True)])
+def test_step_host_sparse_matches_device_step(N, E, copy_engine, monkeypatch):
+    """uaisa_step_host_sparse (one CUDA graph, ragged results) carries exactly the information of the dense step: the
+    single-kernel path that writes mapped host memory (warp-local, CTA and cluster geometries) and the copy-engine path
+    used for large batches."""
+    if copy_engine:
+        monkeypatch.setenv("UAISA_HOST_COPY_ENGINE", "1")
+    scn = swarm(N, max(1.0, N / 12.0), 11) if N <= 128 else scenario_c4(seed=0, n_scenarios=1)      # N = 256: thread-block cluster geometry
+    a = VecMdin(scn, E, neighbors_num=10); b = VecMdin(scn, E, neighbors_num=10)
     a.reset(); b.reset()
+    l0 = a.launch_count
     rng = np.random.default_rng(4)
     rows_seen = 0
     for t in range(40):
@@ -231,7 +237,8 @@ def test_step_host_sparse_matches_device_step():
         rows_seen += len(out["rows"])
         rag = VecMdin.ragged_from_sparse(out, 10)
         assert all(rag[k].shape[0] == 12 + 9 * max(int(cnt[k]), 1) and np.array_equal(rag[k], obs[k, : rag[k].shape[0]]) for k in range(a.A))
-    assert rows_seen > 50
+    assert rows_seen > (30 if N <= 128 else 4), rows_seen
+    assert a.launch_count - l0 == (2 * 40 if copy_engine else 40)      # env kernel (+ pack kernel) per call
     a.close(); b.close()
 
 

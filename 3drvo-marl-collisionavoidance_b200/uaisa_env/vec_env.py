@@ -209,8 +209,10 @@ class VecMdin:
         if action.dtype != np.float32 or action.size != self.A * 3 or not action.flags.c_contiguous:
             raise ValueError("action must be a C-contiguous float32 array with E*N*3 elements")
         hs = self._hs if hasattr(self, "_hs") else _capi.UaisaHostStep()
-        with torch.cuda.device(self.device):
-            _capi.check(self.L.uaisa_step_host_sparse(self.h, action.ctypes.data_as(C.c_void_p), int(auto_reset), int(max_ep_len), C.byref(hs)))
+        # no torch device context here: the library selects (and restores) the handle's device itself
+        rc = self.L.uaisa_step_host_sparse(self.h, action.ctypes.data, int(auto_reset), int(max_ep_len), C.byref(hs))
+        if rc:
+            _capi.check(rc)
         if not hasattr(self, "_hs"):
             self._hs = hs
             A = self.A

@@ -70,13 +70,13 @@ int launch(UaisaHandle *h, const Launch &L, void *stream) {
     if (!h->scenarios_set) return fail(UAISA_ESTATE, "uaisa_set_scenarios has not been called");
     if (h->P.cl > 1) {     // thread-block cluster launch: the G CTAs of an env are co-scheduled and share the hardware cluster barrier
         cudaLaunchConfig_t cfg{};
-        cfg.gridDim = dim3(h->grid); cfg.blockDim = dim3(h->threads); cfg.dynamicSmemBytes = h->smem; cfg.stream = static_cast<cudaStream_t>(stream);
+        cfg.gridDim = dim3(h->grid); cfg.blockDim = dim3(h->threads * h->P.slices); cfg.dynamicSmemBytes = h->smem; cfg.stream = static_cast<cudaStream_t>(stream);
         cudaLaunchAttribute at[1];
         at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = h->P.cl; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
         cfg.attrs = at; cfg.numAttrs = 1;
         CK(cudaLaunchKernelEx(&cfg, h->kernel, h->P, L));
     } else {
-        h->kernel<<<h->grid, h->threads, h->smem, static_cast<cudaStream_t>(stream)>>>(h->P, L);
+        h->kernel<<<h->grid, h->threads * h->P.slices, h->smem, static_cast<cudaStream_t>(stream)>>>(h->P, L);
     }
     h->launches++;
     CK(cudaGetLastError());
@@ -136,35 +136,70 @@ int uaisa_create(const UaisaConfig *cfg, UaisaHandle **out) {
     P.bld_zgate = cfg->building_zgate; P.ctime = cfg->ctime_threshold; P.delta_t = cfg->delta_t; P.exp_radius = cfg->exp_radius;
     P.goal2_lo = P.goal_thr * P.goal_thr * (1.0 - 1e-14); P.goal2_hi = P.goal_thr * P.goal_thr * (1.0 + 1e-14);
     P.nbr2_lo = P.nbr_range * P.nbr_range * (1.0 - 1e-14); P.nbr2_hi = P.nbr_range * P.nbr_range * (1.0 + 1e-14);
-    // launch geometry: whole envs per CTA; shrink the CTA until the grid covers the 148 SMs twice
-    int threads = cfg->threads_per_block;
+    // launch geometry: whole envs per CTA (or a cluster of CTAs per env); shrink the CTA until the grid covers the 148 SMs twice
+    int threads = cfg->threads_per_block, slices = 1;
     const bool cluster = N > 128;                 // an env that does not fit one 128-thread CTA is spread over a thread-block cluster
+    const bool wl = (N <= 32) && (32 % N == 0);   // every env inside one warp
+    const int need = cfg->nm < N - 1 ? cfg->nm : N - 1;
+    const int maxr = need <= 4 ? 4 : need <= 10 ? 10 : 16;
     const int minthreads = cluster ? 32 : ((N + 31) / 32) * 32;
-    if (threads <= 0) {
+    const int nch = (N + 31) / 32;                // 32-neighbour chunks of the pair loop
+    P.tile0_bytes = ((32 * P.obs_dim * 4) + 15) & ~15; P.tile1_bytes = ((32 * (P.nm ? P.nm : 1) * 4) + 15) & ~15;
+    auto grid_for = [&](int th) { return cluster ? (long long)E * ((N + th - 1) / th) : (long long)(E + (th / N) - 1) / (th / N); };
+    auto smem_for = [&](int th, int s) {
+        const size_t epc = cluster ? 1 : th / N, cols = cluster ? N : th;
+        return sizeof(double) * 8 * cols + sizeof(int) * 2 * epc + 16 + P.tile0_bytes + P.tile1_bytes   // exchange tile, env bits, TMA fill tiles
+               + (maxr > 4 ? (size_t)th * s * maxr * 24 : 0)                                       // + shared top-nm lists (one set per slice)
+               + (size_t)th * (4 * 8 + 3 * 4) + sizeof(int) * (epc + 2) + 16                         // + re-observe compaction
+               + cols * 16 + 16                                                                    // + fp32 position copies
+               + (size_t)(s - 1) * th * 12 + (size_t)th * 4 + 16;                                    // + helpers' partial results, owners' activity
+    };
+    const bool auto_threads = threads <= 0;
+    if (auto_threads) {
         threads = 128;
-        auto grid_for = [&](int th) { return cluster ? (long long)E * ((N + th - 1) / th) : (long long)(E + (th / N) - 1) / (th / N); };
         while (threads / 2 >= minthreads && threads / 2 >= 32 && (!cluster || (N + threads / 2 - 1) / (threads / 2) <= 8) &&
                grid_for(threads) < 2 * prop.multiProcessorCount) threads /= 2;
+    }
+    if (auto_threads && !wl && maxr > 4 && nch > 1) {
+        // Many neighbours per ego and few egos (dense airspace): add neighbour slices -- helper threads that walk a share of each
+        // ego's neighbours and hand partial results to the owner through shared memory.  Cost model per (egos per CTA, slices):
+        // waves of the grid over the resident CTA slots x (32-neighbour chunks per slice + 1 chunk-equivalent of per-ego work),
+        // stretched by the warps sharing an SM.  The unsliced geometry stays unless slicing is predicted >= 10 % faster.
+        auto est_for = [&](int th, int s) -> double {
+            const int block = th * s;
+            long long per_sm = 65536 / (168LL * block), by_smem = (long long)prop.sharedMemPerMultiprocessor / (long long)(smem_for(th, s) + 1024);
+            if (by_smem < per_sm) per_sm = by_smem;
+            if (per_sm > 32) per_sm = 32;
+            if (per_sm < 1) return 1e300;
+            const long long cap = per_sm * prop.multiProcessorCount, g = grid_for(th), waves = (g + cap - 1) / cap;
+            const double wpsm = (double)(g < cap ? g : cap) * (block / 32) / prop.multiProcessorCount;
+            return (double)waves * ((nch + s - 1) / s + 1.0) * (1.0 + 0.04 * wpsm);
+        };
+        double best = 0.9 * est_for(threads, 1); int bt = threads, bs = 1;
+        for (int th = threads; th >= 32; th -= 32) {
+            if (th < minthreads || (cluster && (N + th - 1) / th > 8)) continue;
+            for (int s = 2; s * th <= 128 && s <= nch; s++) { const double e_ = est_for(th, s); if (e_ < best) { best = e_; bt = th; bs = s; } }
+        }
+        threads = bt; slices = bs;
+    }
+    if (cfg->neighbor_slices > 0) {
+        slices = cfg->neighbor_slices;
+        if (slices > 1 && (wl || maxr <= 4 || slices * threads > 128 || slices > nch)) { delete h; return fail(UAISA_EINVAL, "neighbor_slices > 1 needs n_drones > 32, nm > 4 and slices * threads_per_block <= 128"); }
     }
     if (cluster) {
         if (threads > 128 || threads % 32 || (N + threads - 1) / threads > 8) { delete h; return fail(UAISA_EINVAL, "n_drones > 128 needs threads_per_block in {32,64,96,128} with at most 8 CTAs per env"); }
         P.cl = (N + threads - 1) / threads;
     } else if (threads < N || threads > 128 || threads % 32) { delete h; return fail(UAISA_EINVAL, "threads_per_block must be a multiple of 32 in [n_drones, 128]"); }
-    h->threads = threads; P.threads = threads; P.envs_per_cta = cluster ? 1 : threads / N;
+    h->threads = threads; P.threads = threads; P.slices = slices; P.envs_per_cta = cluster ? 1 : threads / N;
     // CTA-level compaction of the re-observe phase pays only with several warps per CTA and more than a handful of
     // drones per env (measured: N=16 +7 %, N=4 +2 % at 128 threads, -10 % with single-warp CTAs)
-    P.compact = (!cluster && threads >= 128 && N > 4 && !std::getenv("UAISA_NO_COMPACT")) ? 1 : 0;
+    P.compact = (!cluster && slices == 1 && threads >= 128 && N > 4 && !std::getenv("UAISA_NO_COMPACT")) ? 1 : 0;
     h->grid = cluster ? E * P.cl : (E + P.envs_per_cta - 1) / P.envs_per_cta;
-    const int need = cfg->nm < N - 1 ? cfg->nm : N - 1;
-    const int maxr = need <= 4 ? 4 : need <= 10 ? 10 : 16;
-    P.tile0_bytes = ((32 * P.obs_dim * 4) + 15) & ~15; P.tile1_bytes = ((32 * (P.nm ? P.nm : 1) * 4) + 15) & ~15;
-    h->smem = sizeof(double) * 8 * (cluster ? N : threads) + sizeof(int) * 2 * P.envs_per_cta + 16 + P.tile0_bytes + P.tile1_bytes   // + TMA fill tiles
-              + (maxr > 4 ? (size_t)threads * maxr * 24 : 0)                                      // + shared top-nm lists
-              + (size_t)threads * (4 * 8 + 3 * 4) + sizeof(int) * (P.envs_per_cta + 2) + 16           // + re-observe compaction
-              + (size_t)(cluster ? N : threads) * 16 + 16;                                       // + fp32 position copies
-    const bool wl = (N <= 32) && (32 % N == 0);   // every env inside one warp
-    if (wl) h->kernel = need <= 4 ? uaisa_env_kernel<4, 128, true> : need <= 10 ? uaisa_env_kernel<10, 128, true> : uaisa_env_kernel<16, 128, true>;
-    else h->kernel = need <= 4 ? uaisa_env_kernel<4, 128, false> : need <= 10 ? uaisa_env_kernel<10, 128, false> : uaisa_env_kernel<16, 128, false>;
+    h->smem = smem_for(threads, slices);
+    if (std::getenv("UAISA_VERBOSE")) std::fprintf(stderr, "[uaisa] E=%d N=%d: %s, %d egos x %d slices per CTA, %d CTAs%s, %zu B smem\n", E, N, wl ? "warp-local" : "CTA", threads, slices, h->grid, cluster ? " (clustered)" : "", h->smem);
+    if (wl) h->kernel = need <= 4 ? uaisa_env_kernel<4, 128, true, false> : need <= 10 ? uaisa_env_kernel<10, 128, true, false> : uaisa_env_kernel<16, 128, true, false>;
+    else if (slices > 1 || (maxr > 4 && std::getenv("UAISA_FORCE_SL"))) h->kernel = need <= 10 ? uaisa_env_kernel<10, 128, false, true> : uaisa_env_kernel<16, 128, false, true>;
+    else h->kernel = need <= 4 ? uaisa_env_kernel<4, 128, false, false> : need <= 10 ? uaisa_env_kernel<10, 128, false, false> : uaisa_env_kernel<16, 128, false, false>;
     if (h->smem > (size_t)prop.sharedMemPerBlockOptin) { delete h; return fail(UAISA_EINVAL, "shared memory per CTA exceeds the device limit; lower threads_per_block"); }
     cudaError_t e = cudaFuncSetAttribute(reinterpret_cast<const void *>(h->kernel), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem);
     if (e != cudaSuccess) { delete h; return cuda_fail(e, "cudaFuncSetAttribute"); }

@@ -18,8 +18,8 @@ namespace uaisa {
 // fp32 round trip: what a store to HBM followed by the next step's load would do
 __device__ __forceinline__ double rt(double x) { return (double)(float)x; }
 
-__device__ __forceinline__ void reset_drone(Drone &d, const Consts &C) {   // drone.reset, drone.py:270-291
-    load3(C.wp, d.px, d.py, d.pz);
+__device__ __forceinline__ void reset_drone(const Params &P, Drone &d, const Consts &C) {   // drone.reset, drone.py:270-291
+    load3(C.wp(P), d.px, d.py, d.pz);
     d.px = rt(d.px); d.py = rt(d.py); d.pz = rt(d.pz);   // the state is fp32: a start point is stored rounded
     d.vx = d.vy = d.vz = 0.0; d.yaw = d.pitch = 0.0; d.real_len = 0.0; d.max_dev = 0.0;
     d.i = 1; d.flags = 0;   // extra_len is deliberately not cleared
@@ -71,34 +71,52 @@ enum Region : int { RG_PROLOGUE = 0, RG_FILL, RG_SYNC, RG_DRONESTATE, RG_PAIRS, 
 #define RG_FLUSH() do { } while (0)
 #endif
 
+#ifndef UAISA_LB_THREADS
+#define UAISA_LB_THREADS MAXT   // experiments: smaller CTAs with a different register cap (profiles/variants.sh)
+#endif
 #ifndef UAISA_MINB128
 #define UAISA_MINB128 3   // CTAs of 128 threads per SM the register allocator must leave room for
 #endif
 // WL ("warp local"): N divides 32, so every env lives inside one warp -- all CTA barriers become __syncwarp(),
 // the per-env reductions of the reset policy become ballots, and each warp clears its own 32 output rows.
-template <int MAXR, int MAXT, bool WL>
-__global__ void __launch_bounds__(MAXT, (MAXT <= 128 ? UAISA_MINB128 : 1)) uaisa_env_kernel(const __grid_constant__ Params P, const __grid_constant__ Launch L) {
+template <int MAXR, int MAXT, bool WL, bool SL>
+#ifdef UAISA_NO_LB   // experiments: register cap from -maxrregcount instead
+__global__ void uaisa_env_kernel(
+#else
+__global__ void __launch_bounds__(UAISA_LB_THREADS, (MAXT <= 128 ? UAISA_MINB128 : 1)) uaisa_env_kernel(
+#endif
+    const __grid_constant__ Params P, const __grid_constant__ Launch L) {
 #define ENV_SYNC() do { if (WL) __syncwarp(); else __syncthreads(); } while (0)
-    extern __shared__ double smem_d[];
+    extern __shared__ __align__(16) unsigned char smem_raw[];
     const int threads = P.threads;
     // Cluster mode (P.cl = G > 1, N > 128): one env is spread over a thread-block cluster of G CTAs.  Every CTA keeps a full
     // copy of the env's exchange columns in its own shared memory; at each publish point the CTAs write their slice to a
     // double-buffered global (L2) exchange array, meet at the hardware cluster barrier and reload all N columns.
     const bool CLM = !WL && P.cl > 1;
     const int sst = CLM ? P.N : threads;                                         // column stride of the exchange tile
-    double *sx = smem_d;                                                         // [8][sst] exchange
-    int *senv = reinterpret_cast<int *>(sx + 8 * sst);                           // [envs_per_cta] reduction bits
-    int *ssel = senv + P.envs_per_cta;                                           // [envs_per_cta] obs selected
-    // constant tiles for the TMA fills (WL only), 16-byte aligned after the arrays above
-    uint4 *tile0 = reinterpret_cast<uint4 *>((reinterpret_cast<uintptr_t>(ssel + P.envs_per_cta) + 15) & ~uintptr_t(15));
-    uint4 *tile1 = tile0 + P.tile0_bytes / 16;           // tile0: one warp's 32 observation rows of zeros; tile1: 32 rows of nbr = -1
-    void *stop = tile1 + P.tile1_bytes / 16;            // top-nm lists of the MAXR > 4 instantiations
+    // Shared memory is carved up by byte offsets from the one __shared__ array, never through integer round trips of a pointer, so
+    // that every access below compiles to LDS/STS (a pointer rebuilt from a uintptr_t is generic: LD.E on the long scoreboard).
+    const int S = SL ? P.slices : 1;                   // neighbour slices per ego: slice 0 = the owner threads, the others are helpers (pair loops only)
+    unsigned off = 0;
+    auto take = [&](unsigned bytes) { unsigned char *p_ = smem_raw + off; off += bytes; return p_; };
+    auto align16 = [&]() { off = (off + 15u) & ~15u; };
+    double *sx = reinterpret_cast<double *>(take(8u * 8u * sst));                                    // [8][sst] exchange
+    int *senv = reinterpret_cast<int *>(take(4u * P.envs_per_cta));                                  // [envs_per_cta] reduction bits
+    int *ssel = reinterpret_cast<int *>(take(4u * P.envs_per_cta));                                  // [envs_per_cta] obs selected
+    align16();                                                                                      // constant tiles for the TMA fills (WL only)
+    uint4 *tile0 = reinterpret_cast<uint4 *>(take(P.tile0_bytes));                                   // one warp's 32 observation rows of zeros
+    uint4 *tile1 = reinterpret_cast<uint4 *>(take(P.tile1_bytes));                                   // 32 rows of nbr = -1
+    unsigned char *stop = take((unsigned)(S * TopList<MAXR>::smem_bytes(threads)));                  // top-nm lists of the MAXR > 4 instantiations, one set per slice
     // CTA-level compaction of the re-observe phase: parked owner state + list of touched envs
-    double *spk_d = reinterpret_cast<double *>(reinterpret_cast<char *>(stop) + TopList<MAXR>::smem_bytes(threads));   // [4][threads] yaw pitch real_len max_dev
-    int *spk_i = reinterpret_cast<int *>(spk_d + 4 * threads);                                                      // [3][threads] wp index, flags, staged
-    int *s_list = spk_i + 3 * threads;                                                                              // [envs_per_cta]
-    int *s_nt = s_list + P.envs_per_cta;                                                                            // [2] (double-buffered counter)
-    float4 *sxf = reinterpret_cast<float4 *>((reinterpret_cast<uintptr_t>(s_nt + 2) + 15) & ~uintptr_t(15));           // [threads] fp32 copies of the positions
+    double *spk_d = reinterpret_cast<double *>(take(8u * 4u * threads));                             // [4][threads] yaw pitch real_len max_dev
+    int *spk_i = reinterpret_cast<int *>(take(4u * 3u * threads));                                   // [3][threads] wp index, flags, staged
+    int *s_list = reinterpret_cast<int *>(take(4u * P.envs_per_cta));                                // [envs_per_cta]
+    int *s_nt = reinterpret_cast<int *>(take(8u));                                                   // [2] (double-buffered counter)
+    align16();
+    float4 *sxf = reinterpret_cast<float4 *>(take(16u * sst));                                       // [sst] fp32 copies of the positions
+    double *spart_t = reinterpret_cast<double *>(take(8u * (S - 1) * threads));                      // [S-1][threads] helpers' partial tmin
+    int *spart_f = reinterpret_cast<int *>(take(4u * (S - 1) * threads));                            // [S-1][threads] helpers' vo_any | col << 1 | cnt << 2
+    int *s_act = reinterpret_cast<int *>(take(4u * threads));                                        // [threads] owner is active in the re-observe phase
     if (threadIdx.x == 0) { s_nt[0] = 0; s_nt[1] = 0; }
     const float nbr2_lo_f = (float)(P.nbr_range * P.nbr_range * (1.0 - 1e-4)), nbr2_hi_f = (float)(P.nbr_range * P.nbr_range * (1.0 + 1e-4));
     if (WL) {
@@ -108,16 +126,18 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 128 ? UAISA_MINB128 : 1)) uaisa
     }
     __syncthreads();
 
-    const int tid = threadIdx.x, N = P.N, lane = tid & 31;
+    const int tix = threadIdx.x, slice = (S > 1) ? tix / threads : 0, tid = tix - slice * threads, N = P.N, lane = tix & 31;
+    const bool helper = slice > 0;                     // whole warps (threads % 32 == 0)
     const int crank = CLM ? (int)(blockIdx.x % P.cl) : 0;
     const unsigned env_lanes = WL ? (N >= 32 ? 0xffffffffu : (((1u << N) - 1u) << (lane - lane % N))) : 0u;
     const int le = CLM ? 0 : tid / N, k = CLM ? crank * threads + tid : tid - le * N;
     const int env0 = CLM ? (int)(blockIdx.x / P.cl) : blockIdx.x * P.envs_per_cta;
     const int env = env0 + le;
-    const bool valid = CLM ? (k < N) : ((le < P.envs_per_cta) && (env < P.E));
+    const bool evalid = CLM ? (k < N) : ((le < P.envs_per_cta) && (env < P.E));   // my ego exists
+    const bool valid = evalid && !helper;              // ... and I own it: all state, flags and outputs are the owner's business
     const int lbase = le * N;
     const int A = P.E * N;
-    const int a = valid ? env * N + k : 0;
+    const int a = evalid ? env * N + k : 0;
     const int scol = CLM ? k : tid;                               // my column in the exchange tile
     const int ag0 = CLM ? env0 * N + crank * threads : env0 * N;  // first agent of this CTA (its agents are contiguous)
     const int nag_here = CLM ? max(0, min(threads, N - crank * threads)) : min(P.envs_per_cta, P.E - env0) * N;
@@ -130,12 +150,11 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 128 ? UAISA_MINB128 : 1)) uaisa
     RG_DECL
     Consts C; Drone d; int ep_len = 0;
     const double *bld = nullptr; int nb = 0, scn = 0;
-    double extra_len_new = 0.0; bool extra_len_dirty = false;
     if (valid) {
         scn = __ldg(P.env2scn + env);
         const int sn = scn * N + k;
-        C.wp = P.wp + (size_t)sn * P.W * 3; C.radius = __ldg(P.radius + sn); C.prio = __ldg(P.prio + sn);
-        C.route_len = __ldg(P.route_len + sn); C.n = __ldg(P.npts + sn); C.seg = P.seg + (size_t)sn * P.W * 4;
+        C.set(P, sn); C.radius = __ldg(P.radius + sn); C.prio = __ldg(P.prio + sn);
+        C.route_len = __ldg(P.route_len + sn); C.n = __ldg(P.npts + sn);
         bld = P.bld + (size_t)scn * P.M * 4; nb = __ldg(P.nbld + scn);
         const float4 py = P.pos_yaw[a], vp = P.vel_pitch[a];
         d.px = py.x; d.py = py.y; d.pz = py.z; d.yaw = py.w; d.vx = vp.x; d.vy = vp.y; d.vz = vp.z; d.pitch = vp.w;
@@ -146,22 +165,20 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 128 ? UAISA_MINB128 : 1)) uaisa
     }
     if (CLM) {   // every CTA of the cluster needs the constants of ALL drones of the env
         const int s_ = __ldg(P.env2scn + env0);
-        for (int j = tid; j < N; j += blockDim.x) { sx[6 * sst + j] = __ldg(P.radius + s_ * N + j); sx[7 * sst + j] = __ldg(P.prio + s_ * N + j); }
+        for (int j = tix; j < N; j += blockDim.x) { sx[6 * sst + j] = __ldg(P.radius + s_ * N + j); sx[7 * sst + j] = __ldg(P.prio + s_ * N + j); }
     }
     unsigned n_rng = 0, n_cone = 0, n_bad = 0;
     const int T = is_step ? L.T : 1;
     RG_MARK(RG_PROLOGUE);
 
     for (int t = 0; t < T; t++) {
-        const size_t o = (size_t)t * A + a;              // this thread's slot in the [T][A] outputs
-        float *const myobs = L.obs ? L.obs + o * P.obs_dim : nullptr;
-        int *const mynbr = L.nbr ? L.nbr + o * P.nm : nullptr;
+#define OUT_SLOT(agent) ((size_t)t * A + (size_t)(agent))   // slot in the [T][A] outputs (recomputed at the use sites: no live 64-bit pointers)
         float a32x = 0.f, a32y = 0.f, a32z = 0.f;        // issue the action loads ahead of the burst of clearing stores
-        if (is_step && valid) {
-            const float *ap = L.action + o * 3; a32x = ap[0]; a32y = ap[1]; a32z = ap[2];
+        if (is_step && evalid) {
+            const float *ap = L.action + OUT_SLOT(a) * 3; a32x = ap[0]; a32y = ap[1]; a32z = ap[2];
             if (t + 1 < T) asm volatile("prefetch.global.L2 [%0];" ::"l"(ap + (size_t)A * 3));   // next step's action
         }
-        if (!WL && tid < P.envs_per_cta) { senv[tid] = 0; ssel[tid] = 0; }
+        if (!WL && tix < P.envs_per_cta) { senv[tix] = 0; ssel[tix] = 0; }
         if (is_step) {   // every row is written this step: clear the output region once, coalesced 16-byte stores
             if (WL) {    // my warp's 32 rows
                 const int w0 = tid - lane, nw = min(32, nag_here - w0);
@@ -181,8 +198,8 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 128 ? UAISA_MINB128 : 1)) uaisa
                 }
             } else {
                 const size_t abase = (size_t)t * A + (size_t)ag0;
-                if (L.obs) fill_out(reinterpret_cast<uint32_t *>(L.obs + abase * P.obs_dim), nag_here * P.obs_dim, 0u, tid, blockDim.x);
-                if (L.nbr) fill_out(reinterpret_cast<uint32_t *>(L.nbr + abase * P.nm), nag_here * P.nm, ~0u, tid, blockDim.x);
+                if (L.obs) fill_out(reinterpret_cast<uint32_t *>(L.obs + abase * P.obs_dim), nag_here * P.obs_dim, 0u, tix, blockDim.x);
+                if (L.nbr) fill_out(reinterpret_cast<uint32_t *>(L.nbr + abase * P.nm), nag_here * P.nm, ~0u, tix, blockDim.x);
             }
         }
         RG_MARK(RG_FILL);
@@ -194,7 +211,7 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 128 ? UAISA_MINB128 : 1)) uaisa
         bool st_done = false, st_fin = false;
         int staged = -1;                                 // rows of mine already in HBM this step (-1: none, row not cleared)
         // "working identity": normally the thread's own drone; in a compacted re-observe phase the drone it was handed
-        int wk = k, wlbase = lbase, tt = tid; size_t wo = o; float *wobs = myobs; int *wnbr = mynbr;
+        int wk = k, wlbase = lbase, tt = tid, wa = a;
         bool remapped = false, worker = false;
 
         for (int ph = is_step ? PH_A : PH_OBS; ph <= PH_OBS; ph++) {
@@ -213,7 +230,7 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 128 ? UAISA_MINB128 : 1)) uaisa
                         cluster_sync_all();
                         sel = valid && (__ldcg(ge) != 0);
                         cluster_sync_all();
-                        if (crank == 0 && tid == 0) *ge = 0;
+                        if (crank == 0 && tix == 0) *ge = 0;
                     }
                     else { __syncthreads(); if (rs) ssel[le] = 1; __syncthreads(); sel = valid && ssel[le]; }   // benign race: all write 1
                 } else if (L.mode == MODE_OBSERVE) {
@@ -235,7 +252,7 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 128 ? UAISA_MINB128 : 1)) uaisa
                         cluster_sync_all();
                         bits = valid ? __ldcg(ge) : 0;
                         cluster_sync_all();                                    // everybody has read the bits: re-arm the slot
-                        if (crank == 0 && tid == 0) *ge = 0;
+                        if (crank == 0 && tix == 0) *ge = 0;
                     } else {
                         __syncthreads();
                         if (valid) atomicOr(&senv[le], (st_done ? 1 : 0) | (st_fin ? 2 : 4) | (over ? 8 : 0));
@@ -248,14 +265,15 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 128 ? UAISA_MINB128 : 1)) uaisa
                         if (bits & 1) { if (st_done) { rs = true; ep_len = 0; } sel = true; }                   // :230-242
                         if (L.epoch_ended || all_fin) { rs = true; ep_len = 0; cut = true; sel = true; }        // :244-264
                         else if (terminal) { if (st_fin || ep_len > L.max_ep_len) { rs = true; ep_len = 0; } cut = true; sel = true; }   // :266-281
-                        if (L.reset_mask) L.reset_mask[o] = rs;
-                        if (L.path_cut) L.path_cut[o] = cut;
+                        if (L.reset_mask) L.reset_mask[OUT_SLOT(a)] = rs;
+                        if (L.path_cut) L.path_cut[OUT_SLOT(a)] = cut;
                     }
                 } else if (is_step) {
                     break;       // plain step: nothing to re-observe (uniform over the CTA)
                 }
-                if (rs) reset_drone(d, C);
+                if (rs) reset_drone(P, d, C);
                 active = valid && sel && (L.obs || L.count || L.nbr);
+                if (S > 1 && !helper) s_act[tid] = active;             // read by my helpers after the barriers below
                 RG_MARK(RG_AUTORESET);
             }
             // -------------------------------------------------------- publish my state, then read the others'
@@ -266,7 +284,7 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 128 ? UAISA_MINB128 : 1)) uaisa
                 if (valid) { double *g = gb + (size_t)k * 6; g[0] = d.px; g[1] = d.py; g[2] = d.pz; g[3] = d.vx; g[4] = d.vy; g[5] = d.vz; }
                 pubn++;
                 cluster_sync_all();                        // every CTA of the env has written its slice (release/acquire at cluster scope)
-                for (int j = tid; j < N; j += blockDim.x) {
+                for (int j = tix; j < N; j += blockDim.x) {
                     const double *g = gb + (size_t)j * 6;  // L1 is not coherent across SMs: read through L2
                     const double x_ = __ldcg(g), y_ = __ldcg(g + 1), z_ = __ldcg(g + 2);
                     sx[0 * sst + j] = x_; sx[1 * sst + j] = y_; sx[2 * sst + j] = z_;
@@ -290,7 +308,7 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 128 ? UAISA_MINB128 : 1)) uaisa
                 if (active && k == 0) s_list[atomicAdd(&s_nt[t & 1], 1)] = le;
                 __syncthreads();
                 const int nt = s_nt[t & 1];
-                if (tid == 0) s_nt[(t + 1) & 1] = 0;
+                if (tix == 0) s_nt[(t + 1) & 1] = 0;
                 remapped = true;
                 worker = active = tid < nt * N;
                 if (worker) {
@@ -300,55 +318,65 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 128 ? UAISA_MINB128 : 1)) uaisa
                     d.px = sx[0 * threads + tt]; d.py = sx[1 * threads + tt]; d.pz = sx[2 * threads + tt];
                     d.vx = sx[3 * threads + tt]; d.vy = sx[4 * threads + tt]; d.vz = sx[5 * threads + tt];
                     d.i = spk_i[0 * threads + tt]; d.max_dev = spk_d[3 * threads + tt]; staged = spk_i[2 * threads + tt];
-                    C.wp = P.wp + (size_t)sn_t * P.W * 3; C.seg = P.seg + (size_t)sn_t * P.W * 4;
+                    C.set(P, sn_t);
                     C.radius = sx[6 * threads + tt]; C.prio = sx[7 * threads + tt];
-                    wo = (size_t)t * A + (size_t)env_t * N + wk;
-                    wobs = L.obs ? L.obs + wo * P.obs_dim : nullptr; wnbr = L.nbr ? L.nbr + wo * P.nm : nullptr;
+                    wa = env_t * N + wk;
                 }
             } else {
                 ENV_SYNC();
             }
             RG_MARK(RG_SYNC);
-            if (!active) continue;
+            // helper threads (slices > 1) walk their share of the ego's neighbours whenever its owner is active
+            const bool hact = S > 1 && helper && evalid && (ph != PH_OBS || s_act[tid] != 0);
+            // (threads with nothing to do still meet the others at the merge barrier below: barrier.sync without .aligned
+            // counts thread arrivals on barrier 0 wherever the instruction sits)
+            if (!active && !hact) { if (S > 1) asm volatile("barrier.sync 0;" ::: "memory"); continue; }
 
             // drone.dronestate (drone.py:254-263): desired velocity + deviation, side effect on max_deviation
-            double d0, d1, d2, dev;
-            {
-                const double *cur = C.wp + 3 * d.i;
+            double d0 = 0, d1 = 0, d2 = 0, dev = 0;
+            if (!SL || !helper) {
+                const double *cur = C.wp(P) + 3 * d.i;
                 cal_des_vel(P, d.px, d.py, d.pz, cur, d0, d1, d2);
-                dev = deviation(cur - 3, C.seg + 4 * d.i, d.px, d.py, d.pz);
+                dev = deviation(cur - 3, C.seg(P) + 4 * d.i, d.px, d.py, d.pz);
                 if (dev > d.max_dev) d.max_dev = dev;
+            } else {   // the ego as its owner just published it
+                d.px = sx[0 * sst + scol]; d.py = sx[1 * sst + scol]; d.pz = sx[2 * sst + scol];
+                d.vx = sx[3 * sst + scol]; d.vy = sx[4 * sst + scol]; d.vz = sx[5 * sst + scol];
+                C.radius = sx[6 * sst + scol]; C.prio = sx[7 * sst + scol];
             }
             RG_MARK(RG_DRONESTATE);
             // pairwise pass over the drones of my env (rvo_inter.py:20-83)
             bool vo_any = false, col = false; double tmin = CUDART_INF;
-            TopList<MAXR> top; top.init(stop, threads, tid); top.clear();
+            TopList<MAXR> top; top.init(stop + (unsigned)(slice * TopList<MAXR>::smem_bytes(threads)), threads, tid); top.clear();
+            int jb_lo = 0, jb_hi = N;                          // my slice: whole 32-neighbour chunks
+            if (S > 1) { const int nch = (N + 31) >> 5; jb_lo = ((slice * nch) / S) << 5; jb_hi = min(N, (((slice + 1) * nch) / S) << 5); }
             {
                 double bx = (ph == PH_OBS) ? 0.0 : ax, by = (ph == PH_OBS) ? 0.0 : ay, bz = (ph == PH_OBS) ? 0.0 : az;
                 if (np_dot3(bx, by, bz, bx, by, bz) < 1e-10 * (1.0 - 1e-14)) { bx = by = bz = 0.0; }   // norm(a) < 1e-5, rvo_inter.py:118-119
                 // Stage 1 runs over a chunk of up to 32 neighbours with no divergent work and yields a mask of the
                 // pairs whose cone must be evaluated; stage 2 walks that mask (rvo_inter.py:29,67 map both).
-                for (int jb = 0; jb < N; jb += 32) {
+                for (int jb = jb_lo; jb < jb_hi; jb += 32) {
                     unsigned cand = 0, slow = 0, near = 0;
-                    const int jn = min(32, N - jb);
+                    const int jn = min(32, jb_hi - jb);
                     if constexpr (MAXR > 4) {                     // many neighbours: fp32 pre-gate on float copies of the positions
                         const float fx = (float)d.px, fy = (float)d.py, fz = (float)d.pz;
                         if (jn == 32) {                          // full chunk: fixed trip count, fully unrolled -> 32 independent gates in flight
 #pragma unroll
-                            for (int jj = 0; jj < 32; jj++) {
-                                const int bits = (jb + jj == wk) ? 0 : pair_range_f32(fx, fy, fz, sxf[wlbase + jb + jj], nbr2_lo_f, nbr2_hi_f);
+                            for (int jj = 0; jj < 32; jj++) {    // straight-line: "self" is gated like everybody else and masked out below
+                                const int bits = pair_range_f32(fx, fy, fz, sxf[wlbase + jb + jj], nbr2_lo_f, nbr2_hi_f);
                                 near |= (bits & PB_EVAL) ? (1u << jj) : 0u;
                                 slow |= (bits & PB_SLOW) ? (1u << jj) : 0u;
                             }
                         } else {
 #pragma unroll 8
                             for (int jj = 0; jj < jn; jj++) {    // stage 1a: who is within range (fp32, branch-free, overlapped)
-                                const int j = jb + jj;
-                                const int bits = (j == wk) ? 0 : pair_range_f32(fx, fy, fz, sxf[wlbase + j], nbr2_lo_f, nbr2_hi_f);
+                                const int bits = pair_range_f32(fx, fy, fz, sxf[wlbase + jb + jj], nbr2_lo_f, nbr2_hi_f);
                                 near |= (bits & PB_EVAL) ? (1u << jj) : 0u;
                                 slow |= (bits & PB_SLOW) ? (1u << jj) : 0u;
                             }
                         }
+                        const unsigned notself = ((unsigned)(wk - jb) < 32u) ? ~(1u << (wk - jb)) : ~0u;
+                        near &= notself; slow &= notself;
                     } else {                                      // a handful of neighbours: the fp64 gate directly
 #pragma unroll 4
                         for (int jj = 0; jj < jn; jj++) {
@@ -406,6 +434,19 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 128 ? UAISA_MINB128 : 1)) uaisa
                 }
             }
             RG_MARK(RG_PAIRS);
+            if (S > 1) {       // helpers hand their partial results to the owner: flags, earliest collision time, their top-nm lists
+                if constexpr (MAXR > 4) {
+                    if (helper) { spart_t[(slice - 1) * threads + tid] = tmin; spart_f[(slice - 1) * threads + tid] = (vo_any ? 1 : 0) | (col ? 2 : 0) | (top.cnt << 2); }
+                    asm volatile("barrier.sync 0;" ::: "memory");
+                    if (helper) continue;
+                    for (int sl = 1; sl < S; sl++) {
+                        const int f = spart_f[(sl - 1) * threads + tid]; const double pt = spart_t[(sl - 1) * threads + tid];
+                        vo_any |= (f & 1) != 0; col |= (f & 2) != 0; if (pt < tmin) tmin = pt;
+                        TopList<MAXR> oth; oth.init(stop + (unsigned)(sl * TopList<MAXR>::smem_bytes(threads)), threads, tid); oth.cnt = f >> 2;
+                        oth.for_each([&](int, double o_iet, double o_md, int o_j, int o_ah) { top.insert(cap, o_iet, o_md, o_j, o_ah); });   // (iet, md, j) is a total order
+                    }
+                }
+            }
             if (ph == PH_A) {
                 // ---------------------------------------------------- ir_gym.rvo_reward_cal (ir_gym.py:64-133)
                 const double vnum = 0.2 * fast_sqrt(np_dot3(ax, ay, az, ax, ay, az)), vden = fast_sqrt(np_dot3(d0, d1, d2, d0, d1, d2));
@@ -428,9 +469,9 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 128 ? UAISA_MINB128 : 1)) uaisa
                 const double nx = d.px + nvx * P.dt, ny = d.py + nvy * P.dt, nz = d.pz + nvz * P.dt;
                 { const double ux = nx - d.px, uy = ny - d.py, uz = nz - d.pz; d.real_len = d.real_len + fast_sqrt(np_dot3(ux, uy, uz, ux, uy, uz)); }
                 d.px = nx; d.py = ny; d.pz = nz; d.vx = nvx; d.vy = nvy; d.vz = nvz;
-                if (within_goal(P, d.px, d.py, d.pz, C.wp + 3 * d.i)) {           // drone.py:116-129
-                    const bool at_dest = within_goal(P, d.px, d.py, d.pz, C.wp + 3 * (C.n - 1));
-                    if (at_dest) { extra_len_new = d.real_len - C.route_len; extra_len_dirty = true; }
+                if (within_goal(P, d.px, d.py, d.pz, C.wp(P) + 3 * d.i)) {           // drone.py:116-129
+                    const bool at_dest = within_goal(P, d.px, d.py, d.pz, C.wp(P) + 3 * (C.n - 1));
+                    if (at_dest) P.extra_len[a] = (float)(d.real_len - C.route_len);      // (stored right away: one live double less)
                     if (!at_dest && d.i < C.n - 1) { d.i += 1; d.flags &= ~FLAG_ARRIVE; }
                 }
                 RG_MARK(RG_MOVE);
@@ -440,6 +481,8 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 128 ? UAISA_MINB128 : 1)) uaisa
             // ------------------------------------------------------------ observation row (ir_gym.py:203-229)
             {
                 bool bad = false;
+                const size_t wo = OUT_SLOT(wa);
+                float *const wobs = L.obs ? L.obs + wo * P.obs_dim : nullptr; int *const wnbr = L.nbr ? L.nbr + wo * P.nm : nullptr;
                 if (wobs) {
                     const double self[OBS_SELF] = {d.px, d.py, d.pz, d.vx, d.vy, d.vz, C.radius, C.prio, d0, d1, d2, dev};
                     float fs[OBS_SELF];
@@ -492,10 +535,10 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 128 ? UAISA_MINB128 : 1)) uaisa
 
             // ------------------------------------------------------------ phase B only: flags, collisions, reward
             bool arr_now = false, dest_now = false;
-            if (within_goal(P, d.px, d.py, d.pz, C.wp + 3 * d.i) && !(d.flags & FLAG_ARRIVE)) { d.flags |= FLAG_ARRIVE; arr_now = true; }
+            if (within_goal(P, d.px, d.py, d.pz, C.wp(P) + 3 * d.i) && !(d.flags & FLAG_ARRIVE)) { d.flags |= FLAG_ARRIVE; arr_now = true; }
             if (d.flags & FLAG_ARRIVE) {
-                const bool at_dest = within_goal(P, d.px, d.py, d.pz, C.wp + 3 * (C.n - 1));
-                if (at_dest) { extra_len_new = d.real_len - C.route_len; extra_len_dirty = true; }
+                const bool at_dest = within_goal(P, d.px, d.py, d.pz, C.wp(P) + 3 * (C.n - 1));
+                if (at_dest) P.extra_len[a] = (float)(d.real_len - C.route_len);
                 if (at_dest && !(d.flags & FLAG_DEST)) { d.flags |= FLAG_DEST; dest_now = true; }
             }
             RG_MARK(RG_B_FLAGS);
@@ -525,10 +568,11 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 128 ? UAISA_MINB128 : 1)) uaisa
             }
             RG_MARK(RG_B_REWARD);
             st_done = col; st_fin = (d.flags & FLAG_DEST) != 0;
-            if (L.reward) L.reward[o] = (float)(rA + rB);
-            if (L.done) L.done[o] = col;
-            if (L.info) L.info[o] = (d.flags & FLAG_ARRIVE) != 0;
-            if (L.finish) L.finish[o] = st_fin;
+            { const size_t o = OUT_SLOT(a);
+              if (L.reward) L.reward[o] = (float)(rA + rB);
+              if (L.done) L.done[o] = col;
+              if (L.info) L.info[o] = (d.flags & FLAG_ARRIVE) != 0;
+              if (L.finish) L.finish[o] = st_fin; }
             // what the next step will load from HBM
             d.px = rt(d.px); d.py = rt(d.py); d.pz = rt(d.pz); d.vx = rt(d.vx); d.vy = rt(d.vy); d.vz = rt(d.vz);
             d.yaw = rt(d.yaw); d.pitch = rt(d.pitch); d.real_len = rt(d.real_len); d.max_dev = rt(d.max_dev);
@@ -543,7 +587,7 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 128 ? UAISA_MINB128 : 1)) uaisa
                 d.yaw = spk_d[0 * threads + tid]; d.pitch = spk_d[1 * threads + tid]; d.real_len = spk_d[2 * threads + tid]; d.max_dev = spk_d[3 * threads + tid];
                 d.i = spk_i[0 * threads + tid]; d.flags = spk_i[1 * threads + tid];
                 const int sn = scn * N + k;
-                C.wp = P.wp + (size_t)sn * P.W * 3; C.seg = P.seg + (size_t)sn * P.W * 4;
+                C.set(P, sn);
                 C.radius = sx[6 * threads + tid]; C.prio = sx[7 * threads + tid];
             }
         }
@@ -557,7 +601,6 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 128 ? UAISA_MINB128 : 1)) uaisa
         P.vel_pitch[a] = make_float4((float)d.vx, (float)d.vy, (float)d.vz, (float)d.pitch);
         P.real_len[a] = (float)d.real_len; P.max_dev[a] = (float)d.max_dev;
         P.wpf[a] = d.i | d.flags;
-        if (extra_len_dirty) P.extra_len[a] = (float)extra_len_new;
         if (do_auto) P.ep_len[a] = ep_len;
     }
     if (L.hp_self) {   // ---- host-pack tail: self part + existing rows of my agent -> mapped host memory, then the completion protocol
@@ -568,7 +611,7 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 128 ? UAISA_MINB128 : 1)) uaisa
         uint4 *stg = reinterpret_cast<uint4 *>(reinterpret_cast<char *>(sx) + warp * 2048);      // sx has 64 B per thread
         float *stg_f = reinterpret_cast<float *>(stg);
         const int a_w = ag0 + (tid - lane);                 // first agent of this warp (a CTA's agents are contiguous)
-        const int nv_w = max(0, min(32, nag_here - (tid - lane)));
+        const int nv_w = helper ? 0 : max(0, min(32, nag_here - (tid - lane)));
         int kk = 0;
         const float *o = L.obs + (size_t)a * P.obs_dim;
         if (valid) {
@@ -611,7 +654,7 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 128 ? UAISA_MINB128 : 1)) uaisa
         }
         __threadfence_system();                            // my host writes (these and the step's reward / flags) are performed ...
         __syncthreads();
-        if (tid == 0) {
+        if (tix == 0) {
             __threadfence_system();                        // ... and ordered before this CTA's arrival
             if (atomicAdd(L.hp_ctr + 1, 1) == (int)gridDim.x - 1) {
                 __threadfence_system();
@@ -707,9 +750,10 @@ __global__ void uaisa_pack_kernel(int A, int obs_dim, int nm, const float *obs, 
     }
 }
 
-#define UAISA_INST(R, T, W) template __global__ void uaisa_env_kernel<R, T, W>(const __grid_constant__ Params, const __grid_constant__ Launch);
-UAISA_INST(4, 128, true) UAISA_INST(10, 128, true) UAISA_INST(16, 128, true)
-UAISA_INST(4, 128, false) UAISA_INST(10, 128, false) UAISA_INST(16, 128, false)
+#define UAISA_INST(R, T, W, S) template __global__ void uaisa_env_kernel<R, T, W, S>(const __grid_constant__ Params, const __grid_constant__ Launch);
+UAISA_INST(4, 128, true, false) UAISA_INST(10, 128, true, false) UAISA_INST(16, 128, true, false)
+UAISA_INST(4, 128, false, false) UAISA_INST(10, 128, false, false) UAISA_INST(16, 128, false, false)
+UAISA_INST(10, 128, false, true) UAISA_INST(16, 128, false, true)      // with neighbour slices (helper threads)
 #undef UAISA_INST
 
 }  // namespace uaisa

@@ -37,6 +37,7 @@ struct Params {
     int envs_per_cta, threads;
     int tile0_bytes, tile1_bytes;   // constant smem tiles behind the TMA fills (zeros / 0xFF), multiples of 16
     int env_train, count_pairs, compact;
+    int slices;                      // neighbour slices per ego (helper threads; 1 = off).  blockDim.x = threads * slices
     int cl;                          // CTAs per env (thread-block cluster size) when an env does not fit one CTA; 0 = one CTA holds whole envs
     double *gx; int *genv;           // cluster mode: global exchange buffers [2][A][6] (p, v in fp64) and [2][E] (reset-policy bits)
     // hyper-parameters (reference constructor defaults, see include/uaisa_b200.h)
@@ -170,8 +171,17 @@ struct Drone {
 };
 
 struct Consts {   // per-drone scenario constants
-    const double *wp;   // this drone's waypoint list [W][3]
-    const double *seg;  // [W][4]: unit direction and length of the segment wp[i-1] -> wp[i]
+#ifdef UAISA_CONSTS_PTR
+    const double *wp_, *seg_;
+    __device__ __forceinline__ void set(const Params &P, int sn) { wp_ = P.wp + (size_t)sn * P.W * 3; seg_ = P.seg + (size_t)sn * P.W * 4; }
+    __device__ __forceinline__ const double *wp(const Params &) const { return wp_; }
+    __device__ __forceinline__ const double *seg(const Params &) const { return seg_; }
+#else
+    int snw;            // (scenario * N + drone) * W: row of this drone's waypoint list (kept as an index: two 64-bit pointers cost 3 more registers)
+    __device__ __forceinline__ void set(const Params &P, int sn) { snw = sn * P.W; }
+    __device__ __forceinline__ const double *wp(const Params &P) const { return P.wp + (size_t)snw * 3; }     // [W][3]
+    __device__ __forceinline__ const double *seg(const Params &P) const { return P.seg + (size_t)snw * 4; }   // [W][4]: unit direction and length of the segment wp[i-1] -> wp[i]
+#endif
     double radius, prio, route_len;
     int n;              // n_points
 };
@@ -429,7 +439,7 @@ __device__ __forceinline__ double angle_punish(double A0, double A1, double A2, 
     return -4.0;
 }
 
-template <int MAXR, int MAXT, bool WL>
+template <int MAXR, int MAXT, bool WL, bool SL>
 __global__ void uaisa_env_kernel(const __grid_constant__ Params P, const __grid_constant__ Launch L);
 __global__ void uaisa_cal_des_kernel(const __grid_constant__ Params P, float *des);
 __global__ void uaisa_action_transform_kernel(const __grid_constant__ Params P, const float *a_inc, float acceler, float *a_inc_rounded, float *action);

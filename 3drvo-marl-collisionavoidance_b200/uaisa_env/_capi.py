@@ -19,7 +19,7 @@ SYMBOLS = (
 class UaisaConfig(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "n_envs", "n_drones", "max_waypoints", "max_buildings", "n_scenarios", "nm", "env_train",
-        "threads_per_block", "count_pairs", "reserved")] + [(n, C.c_double) for n in (
+        "threads_per_block", "count_pairs", "neighbor_slices")] + [(n, C.c_double) for n in (
         "goal_threshold", "max_acc", "max_angle_change", "dt", "vel_max", "neighbor_range", "building_range",
         "building_zgate", "ctime_threshold", "delta_t", "exp_radius")]
 

@@ -233,6 +233,7 @@ def main():
     ap.add_argument("--no-sat", action="store_true")
     ap.add_argument("--no-autoreset", action="store_true", help="diagnostic: plain steps without the trainer reset policy")
     ap.add_argument("--threads-per-block", type=int, default=0)
+    ap.add_argument("--slices", type=int, default=0, help="neighbour slices per drone (0 = auto)")
     ap.add_argument("--tf32", action="store_true")
     ap.add_argument("--ppo-envs", type=int, default=8192)
     ap.add_argument("--ppo-steps", type=int, default=300)
@@ -258,7 +259,7 @@ def main():
     N = scn.N
     A = E * N
     K, W = max(args.steps, 1), max(args.warmup, 3)
-    env = VecMdin(scn, E, neighbors_num=NM, device=dev, threads_per_block=args.threads_per_block)
+    env = VecMdin(scn, E, neighbors_num=NM, device=dev, threads_per_block=args.threads_per_block, neighbor_slices=args.slices)
     env.reset()
     # ---- inputs resident in HBM: K steps of actions, outputs for one chunk of steps
     per_step_out = A * (env.obs_dim * 4 + 1 + NM * 4 + 4 + 3)

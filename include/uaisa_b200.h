@@ -54,7 +54,7 @@ typedef struct UaisaConfig {
     int32_t env_train;       /* ir_gym.py:18 env_train=True */
     int32_t threads_per_block; /* 0 = auto */
     int32_t count_pairs;     /* 1 = maintain the pair counters of uaisa_get_counters (costs atomics) */
-    int32_t reserved;
+    int32_t neighbor_slices; /* 0 = auto; s > 1: s threads per drone share its neighbour loop (N > 32 only; s * threads_per_block <= 128) */
     double goal_threshold;   /* drone.py:15      0.4 */
     double max_acc;          /* drone.py:72      1.0 */
     double max_angle_change; /* drone.py:73      90  */

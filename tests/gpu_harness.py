@@ -70,11 +70,12 @@ def make_actions(rng, t, ob, st, block=25):
 
 
 def lockstep(scn, E, nm, steps, seed, env2scn=None, max_ep_len=60, epoch_len=0, block=25, threads_per_block=0,
-             device="cuda", stats=None, **hyper):
+             device="cuda", stats=None, neighbor_slices=0, **hyper):
     """Teacher-forced lock-step: every step the oracle is loaded with the device's fp32 state, both
     step on identical actions, every output is compared, then both apply the trainer reset policy."""
     stats = stats or Stats()
-    env = VecMdin(scn, E, env2scenario=env2scn, neighbors_num=nm, device=device, threads_per_block=threads_per_block, **hyper)
+    env = VecMdin(scn, E, env2scenario=env2scn, neighbors_num=nm, device=device, threads_per_block=threads_per_block,
+                  neighbor_slices=neighbor_slices, **hyper)
     ob = oracle.OracleBatch(scn, E, env2scn=env2scn, nm=nm, **hyper)
     rng = np.random.default_rng(seed)
     env.reset()

@@ -65,6 +65,20 @@ def test_cluster_mode_envs_larger_than_one_cta(N, tpb):
     assert st.rows > 0 and st.resets > 0
 
 
+@pytest.mark.parametrize("N,tpb,slices", [(256, 32, 3), (256, 32, 4), (256, 64, 2), (300, 0, 0), (64, 64, 2), (100, 0, 0), (40, 64, 2)])
+def test_neighbour_slices(N, tpb, slices):
+    """Helper threads share each ego's neighbour loop (dense airspace, few envs): thread-block clusters (N > 128, also
+    with a ragged last CTA) and single-CTA envs, explicit and auto-selected geometries; parity incl. the top-nm lists merged
+    from the slices."""
+    scn = scenario_c4(seed=4, n_scenarios=1, n_drones=N) if N > 128 else swarm(N, N / 12.0, 5)
+    if N <= 128 and tpb and tpb < N:
+        tpb = ((N + 31) // 32) * 32
+        slices = min(slices, 128 // tpb)
+    st = lockstep(scn, 3, 10, 6, seed=11, block=2, threads_per_block=tpb, neighbor_slices=slices, max_ep_len=4)
+    st.assert_parity()
+    assert st.rows > 0 and st.resets > 0
+
+
 def test_edge_shapes():
     # single drone, no neighbours; nm = 0; N=3 (CTA not a multiple of N); explicit CTA sizes
     one = ScenarioSet.from_start_end([[1, 1, 1]], [[3, 3, 2]], (5, 5, 3))

@@ -18,7 +18,8 @@ namespace uaisa {
 // fp32 round trip: what a store to HBM followed by the next step's load would do
 __device__ __forceinline__ double rt(double x) { return (double)(float)x; }
 
-__device__ __forceinline__ void reset_drone(const Params &P, Drone &d, const Consts &C) {   // drone.reset, drone.py:270-291
+template <class CONSTS>
+__device__ __forceinline__ void reset_drone(const Params &P, Drone &d, const CONSTS &C) {   // drone.reset, drone.py:270-291
     load3(C.wp(P), d.px, d.py, d.pz);
     d.px = rt(d.px); d.py = rt(d.py); d.pz = rt(d.pz);   // the state is fp32: a start point is stored rounded
     d.vx = d.vy = d.vz = 0.0; d.yaw = d.pitch = 0.0; d.real_len = 0.0; d.max_dev = 0.0;
@@ -148,7 +149,7 @@ __global__ void __launch_bounds__(UAISA_LB_THREADS, (MAXT <= 128 ? UAISA_MINB128
     const bool compact = is_step && do_auto && P.compact;   // re-observe through CTA-level compaction (uniform)
 
     RG_DECL
-    Consts C; Drone d; int ep_len = 0;
+    ConstsT<(MAXR <= 4)> C; Drone d; int ep_len = 0;
     const double *bld = nullptr; int nb = 0, scn = 0;
     if (valid) {
         scn = __ldg(P.env2scn + env);
@@ -379,12 +380,12 @@ __global__ void __launch_bounds__(UAISA_LB_THREADS, (MAXT <= 128 ? UAISA_MINB128
                         near &= notself; slow &= notself;
                     } else {                                      // a handful of neighbours: the fp64 gate directly
 #pragma unroll 4
-                        for (int jj = 0; jj < jn; jj++) {
-                            const int j = jb + jj;
-                            const int bits = (j == wk) ? 0 : pair_range_fast(P, d.px, d.py, d.pz, sx + wlbase + j, sst);
+                        for (int jj = 0; jj < jn; jj++) {        // straight-line like the fp32 gates: +1 gate (self), no branch (+6..9 % per step)
+                            const int bits = pair_range_fast(P, d.px, d.py, d.pz, sx + wlbase + jb + jj, sst);
                             near |= (bits & PB_EVAL) ? (1u << jj) : 0u;
                             slow |= (bits & PB_SLOW) ? (1u << jj) : 0u;
                         }
+                        { const unsigned notself = ((unsigned)(wk - jb) < 32u) ? ~(1u << (wk - jb)) : ~0u; near &= notself; slow &= notself; }
                     }
                     for (unsigned m = near; m; m &= m - 1) {     // stage 1b: collision / moving-away gates of the near ones (fp64)
                         const int jj = __ffs(m) - 1;

@@ -170,20 +170,28 @@ struct Drone {
     int i, flags;   // waypoint index, FLAG_ARRIVE | FLAG_DEST
 };
 
-struct Consts {   // per-drone scenario constants
-#ifdef UAISA_CONSTS_PTR
+// per-drone scenario constants.  PTR: keep the two waypoint-table pointers in registers (small-N kernels, where the waypoint
+// loads sit on the critical path) or rebuild them from a 32-bit row index at each use (many-neighbour kernels, where the
+// 3 registers buy more independent range gates in flight).
+template <bool PTR>
+struct ConstsT;
+template <>
+struct ConstsT<true> {
     const double *wp_, *seg_;
-    __device__ __forceinline__ void set(const Params &P, int sn) { wp_ = P.wp + (size_t)sn * P.W * 3; seg_ = P.seg + (size_t)sn * P.W * 4; }
-    __device__ __forceinline__ const double *wp(const Params &) const { return wp_; }
-    __device__ __forceinline__ const double *seg(const Params &) const { return seg_; }
-#else
-    int snw;            // (scenario * N + drone) * W: row of this drone's waypoint list (kept as an index: two 64-bit pointers cost 3 more registers)
-    __device__ __forceinline__ void set(const Params &P, int sn) { snw = sn * P.W; }
-    __device__ __forceinline__ const double *wp(const Params &P) const { return P.wp + (size_t)snw * 3; }     // [W][3]
-    __device__ __forceinline__ const double *seg(const Params &P) const { return P.seg + (size_t)snw * 4; }   // [W][4]: unit direction and length of the segment wp[i-1] -> wp[i]
-#endif
     double radius, prio, route_len;
     int n;              // n_points
+    __device__ __forceinline__ void set(const Params &P, int sn) { wp_ = P.wp + (size_t)sn * P.W * 3; seg_ = P.seg + (size_t)sn * P.W * 4; }
+    __device__ __forceinline__ const double *wp(const Params &) const { return wp_; }     // [W][3]
+    __device__ __forceinline__ const double *seg(const Params &) const { return seg_; }   // [W][4]: unit direction and length of the segment wp[i-1] -> wp[i]
+};
+template <>
+struct ConstsT<false> {
+    int snw;            // (scenario * N + drone) * W
+    double radius, prio, route_len;
+    int n;
+    __device__ __forceinline__ void set(const Params &P, int sn) { snw = sn * P.W; }
+    __device__ __forceinline__ const double *wp(const Params &P) const { return P.wp + (size_t)snw * 3; }
+    __device__ __forceinline__ const double *seg(const Params &P) const { return P.seg + (size_t)snw * 4; }
 };
 
 __device__ __forceinline__ void load3(const double *p, double &x, double &y, double &z) { x = __ldg(p); y = __ldg(p + 1); z = __ldg(p + 2); }

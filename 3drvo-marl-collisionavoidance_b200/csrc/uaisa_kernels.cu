@@ -277,6 +277,8 @@ __global__ void __launch_bounds__(UAISA_LB_THREADS, (MAXT <= 128 ? UAISA_MINB128
                 if (S > 1 && !helper) s_act[tid] = active;             // read by my helpers after the barriers below
                 RG_MARK(RG_AUTORESET);
             }
+            // a warp none of whose envs is re-observed has nothing to publish or read (warp-local envs only)
+            if (WL && !compact && ph == PH_OBS && !__any_sync(0xffffffffu, active)) continue;      // (the compacted variant meets at CTA barriers)
             // -------------------------------------------------------- publish my state, then read the others'
             if (WL && is_step && ph == PH_B && lane == 0) bulk_wait_all();   // my warp's cleared rows have landed: rows may now be scattered
             ENV_SYNC();   // everybody is done reading the previous phase's columns
@@ -387,6 +389,7 @@ __global__ void __launch_bounds__(UAISA_LB_THREADS, (MAXT <= 128 ? UAISA_MINB128
                         }
                         { const unsigned notself = ((unsigned)(wk - jb) < 32u) ? ~(1u << (wk - jb)) : ~0u; near &= notself; slow &= notself; }
                     }
+                    if ((near | slow) == 0u) continue;          // nobody in range in this chunk (the common case in sparse airspace): one branch instead of five empty loops
                     for (unsigned m = near; m; m &= m - 1) {     // stage 1b: collision / moving-away gates of the near ones (fp64)
                         const int jj = __ffs(m) - 1;
                         const int bits = pair_near_fast(P, d.px, d.py, d.pz, d.vx, d.vy, d.vz, C.radius, sx + wlbase + jb + jj, sst);

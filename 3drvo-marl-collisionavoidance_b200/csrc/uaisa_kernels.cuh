@@ -399,6 +399,7 @@ struct TopList<MAXR, false> {
     }
     template <typename F>
     __device__ __forceinline__ void for_each(F &&f) const {   // f(slot, iet, md, j, ah) for slot = 0 (most urgent) .. cnt-1
+        if (cnt == 0) return;                                  // the common case in sparse airspace: one branch, not MAXR predicated bodies
 #pragma unroll
         for (int s = 0; s < MAXR; s++) if (s < cnt) f(s, iet[s], md[s], j[s], ah[s]);
     }

@@ -158,7 +158,13 @@ __device__ __forceinline__ double py_round2_hundredths(double x) {
     return r;
 }
 __device__ __forceinline__ double py_mod360(double x) {  // drone.py:457, Python float %
-    if (x > 0.0 && x < 360.0) return x;
+    // CPython float_rem: m = fmod(x, 360); if (m != 0 && m < 0) m += 360; else if (m == 0) m = +0.0.
+    // yaw + dyaw lives in (-360, 720) (yaw in [0, 360], |dyaw| <= 90), where fmod is one exact subtraction (x - 360 is exact
+    // for x in [360, 720)) or the identity -- branch-free selects; anything else (a state loaded by the caller) takes libm's fmod.
+    if (x > -360.0 && x < 720.0) {
+        const double m = (x >= 360.0) ? x - 360.0 : x;     // fmod(x, 360), sign of x
+        return (m < 0.0) ? m + 360.0 : m + 0.0;            // (-0.0 + 0.0 = +0.0; a tiny negative m rounds up to 360.0 exactly like CPython)
+    }
     double m = fmod(x, 360.0);
     if (m != 0.0) { if (m < 0.0) m += 360.0; } else m = 0.0;
     return m;

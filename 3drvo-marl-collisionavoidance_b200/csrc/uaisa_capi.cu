@@ -435,7 +435,7 @@ static int sparse_setup(UaisaHandle *h) {
     const size_t max_rows = A * (size_t)(P.nm ? P.nm : 1);
     h->sp_cap = (int)(max_rows * sizeof(UaisaRowRec) <= (size_t(256) << 20) ? max_rows : (size_t(256) << 20) / sizeof(UaisaRowRec));
     h->sp_r0 = (int)(A / 8 > 256 ? A / 8 : 256); if (h->sp_r0 > h->sp_cap) h->sp_r0 = h->sp_cap;
-    h->sp_off_reward = 16;
+    h->sp_off_reward = 32;      // header: ready word, two profiling timestamps
     h->sp_off_self = up16(h->sp_off_reward + 4 * A);
     h->sp_off_flags = up16(h->sp_off_self + 4 * A * UAISA_OBS_SELF);      // done | info | finish | count
     h->sp_off_rows = up16(h->sp_off_flags + 4 * A);
@@ -478,7 +478,7 @@ int uaisa_step_host_sparse(UaisaHandle *h, const float *action, int32_t auto_res
             L.reward = reinterpret_cast<float *>(h->sp_host_dev + h->sp_off_reward); L.done = hfl; L.info = hfl + A; L.finish = hfl + 2 * A;
             L.hp_self = reinterpret_cast<float *>(h->sp_host_dev + h->sp_off_self); L.hp_count = hfl + 3 * A;
             L.hp_rows = h->sp_host_dev + h->sp_off_rows; L.hp_cap = h->sp_cap;
-            L.hp_ctr = reinterpret_cast<int *>(h->sp_dev); L.hp_hdr = reinterpret_cast<unsigned long long *>(h->sp_host_dev);
+            L.hp_ctr = reinterpret_cast<unsigned long long *>(h->sp_dev); L.hp_hdr = reinterpret_cast<unsigned long long *>(h->sp_host_dev);
         } else {
             cudaMemcpyAsync(h->h_action, h->sp_hact, sizeof(float) * A * 3, cudaMemcpyHostToDevice, s);
             cudaMemsetAsync(h->sp_dev, 0, 16, s);
@@ -534,7 +534,9 @@ int uaisa_step_host_sparse(UaisaHandle *h, const float *action, int32_t auto_res
     if (prof) {
         const double t3 = now();
         acc[0] += t1 - t0; acc[1] += t2 - t1; acc[2] += t3 - t2;
-        if (++nprof % 200 == 0) { std::fprintf(stderr, "[uaisa host step] memcpy %.1f us, graph launch %.1f us, wait %.1f us (avg of 200)\n", acc[0] / 200, acc[1] / 200, acc[2] / 200); acc[0] = acc[1] = acc[2] = 0; }
+        static double kacc = 0;
+        if (h->sp_zero_copy) { const unsigned long long *hd = reinterpret_cast<const unsigned long long *>(h->sp_host); kacc += (double)(hd[2] - hd[1]) * 1e-3; }
+        if (++nprof % 200 == 0) { std::fprintf(stderr, "[uaisa host step] memcpy %.1f us, graph launch %.1f us, wait %.1f us of which first CTA start -> publication %.1f us (avg of 200)\n", acc[0] / 200, acc[1] / 200, acc[2] / 200, kacc / 200); acc[0] = acc[1] = acc[2] = 0; kacc = 0; }
     }
     if (n_rows > h->sp_cap) return fail(UAISA_EINVAL, "neighbour-row capacity of the host block exceeded");
     if (!h->sp_zero_copy && n_rows > h->sp_r0) {   // rare: more rows than the first-phase window

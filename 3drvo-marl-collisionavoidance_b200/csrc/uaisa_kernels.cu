@@ -149,6 +149,7 @@ __global__ void __launch_bounds__(UAISA_LB_THREADS, (MAXT <= 128 ? UAISA_MINB128
     const bool compact = is_step && do_auto && P.compact;   // re-observe through CTA-level compaction (uniform)
 
     RG_DECL
+    if (L.hp_self && blockIdx.x == 0 && threadIdx.x == 0) { unsigned long long g_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_)); L.hp_hdr[1] = g_; }   // host-step profiling: first CTA's start
     ConstsT<(MAXR <= 4)> C; Drone d; int ep_len = 0;
     const double *bld = nullptr; int nb = 0, scn = 0;
     if (valid) {
@@ -162,6 +163,11 @@ __global__ void __launch_bounds__(UAISA_LB_THREADS, (MAXT <= 128 ? UAISA_MINB128
         d.real_len = P.real_len[a]; d.max_dev = P.max_dev[a];
         const int wf = P.wpf[a]; d.i = wf & WP_MASK; d.flags = wf & (FLAG_ARRIVE | FLAG_DEST);
         if (do_auto) ep_len = P.ep_len[a];
+        {   // a launch starts cold: ask for the waypoint / segment / map lines this step will walk through, all at once
+            const double *w_ = C.wp(P) + 3 * max(d.i - 1, 0), *s_ = C.seg(P) + 4 * d.i;
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(w_)); asm volatile("prefetch.global.L1 [%0];" ::"l"(w_ + 5));
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(s_)); asm volatile("prefetch.global.L1 [%0];" ::"l"(P.map + 3 * scn));
+        }
         if (!CLM) { sx[6 * sst + scol] = C.radius; sx[7 * sst + scol] = C.prio; }      // constant over the launch
     }
     if (CLM) {   // every CTA of the cluster needs the constants of ALL drones of the env
@@ -180,7 +186,8 @@ __global__ void __launch_bounds__(UAISA_LB_THREADS, (MAXT <= 128 ? UAISA_MINB128
             if (t + 1 < T) asm volatile("prefetch.global.L2 [%0];" ::"l"(ap + (size_t)A * 3));   // next step's action
         }
         if (!WL && tix < P.envs_per_cta) { senv[tix] = 0; ssel[tix] = 0; }
-        if (is_step) {   // every row is written this step: clear the output region once, coalesced 16-byte stores
+        const bool clear_rows = is_step && !L.hp_self;   // (the host round trip reads back only the rows that exist: its staging buffers are not cleared)
+        if (clear_rows) {   // every row is written this step: clear the output region once, coalesced 16-byte stores
             if (WL) {    // my warp's 32 rows
                 const int w0 = tid - lane, nw = min(32, nag_here - w0);
                 if (nw > 0) {
@@ -280,7 +287,7 @@ __global__ void __launch_bounds__(UAISA_LB_THREADS, (MAXT <= 128 ? UAISA_MINB128
             // a warp none of whose envs is re-observed has nothing to publish or read (warp-local envs only)
             if (WL && !compact && ph == PH_OBS && !__any_sync(0xffffffffu, active)) continue;      // (the compacted variant meets at CTA barriers)
             // -------------------------------------------------------- publish my state, then read the others'
-            if (WL && is_step && ph == PH_B && lane == 0) bulk_wait_all();   // my warp's cleared rows have landed: rows may now be scattered
+            if (WL && clear_rows && ph == PH_B && lane == 0) bulk_wait_all();   // my warp's cleared rows have landed: rows may now be scattered
             ENV_SYNC();   // everybody is done reading the previous phase's columns
             if (CLM) {
                 double *gb = P.gx + ((size_t)(pubn & 1) * A + (size_t)env0 * N) * 6;      // this env's slice of the exchange buffer
@@ -634,7 +641,7 @@ __global__ void __launch_bounds__(UAISA_LB_THREADS, (MAXT <= 128 ? UAISA_MINB128
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) { tot += __shfl_xor_sync(0xffffffffu, tot, off); kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, off)); }
         int base = 0;
-        if (lane == 0 && tot) base = atomicAdd(L.hp_ctr, tot);
+        if (lane == 0 && tot) base = (int)(unsigned)atomicAdd(L.hp_ctr, (unsigned long long)tot);       // low word: rows reserved so far
         base = __shfl_sync(0xffffffffu, base, 0);
         for (int r = 0; r < kmax; r++) {                   // round r: slot r of every agent that has one, packed and streamed together
             const unsigned have = __ballot_sync(0xffffffffu, kk > r);
@@ -656,15 +663,18 @@ __global__ void __launch_bounds__(UAISA_LB_THREADS, (MAXT <= 128 ? UAISA_MINB128
             __syncwarp();
             base += n;
         }
-        __threadfence_system();                            // my host writes (these and the step's reward / flags) are performed ...
+        // Completion (the pattern of a cooperative-groups grid barrier, at system scope): the CTA barrier orders every thread's host
+        // writes -- these and the step's reward / flags -- before thread 0's fence; the fence is cumulative, so they are performed
+        // system-wide before the CTA's arrival; the CTA that sees all others arrived fences once more and raises the ready word.
         __syncthreads();
         if (tix == 0) {
-            __threadfence_system();                        // ... and ordered before this CTA's arrival
-            if (atomicAdd(L.hp_ctr + 1, 1) == (int)gridDim.x - 1) {
+            __threadfence_system();
+            const unsigned long long old_ = atomicAdd(L.hp_ctr, 1ull << 32);      // high word: CTAs finished (their reservations precede their arrival)
+            if ((unsigned)(old_ >> 32) == gridDim.x - 1) {
                 __threadfence_system();
-                const int n = atomicExch(L.hp_ctr, 0);     // every reservation precedes its CTA's arrival
-                L.hp_ctr[1] = 0;                           // re-armed for the next launch
-                *reinterpret_cast<volatile unsigned long long *>(L.hp_hdr) = ((unsigned long long)(unsigned)n << 32) | 1ull;
+                *L.hp_ctr = 0ull;                          // re-armed for the next launch
+                { unsigned long long g_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_)); L.hp_hdr[2] = g_; }                   // (profiling: the moment of publication)
+                *reinterpret_cast<volatile unsigned long long *>(L.hp_hdr) = ((unsigned long long)(unsigned)old_ << 32) | 1ull;      // {ready, n_rows}
             }
         }
     }

@@ -64,7 +64,7 @@ struct Launch {
     uint8_t *hp_count;           // HOST [A]
     void *hp_rows;               // HOST [hp_cap] UaisaRowRec
     int hp_cap;
-    int *hp_ctr;                 // DEVICE [2]: rows reserved, CTAs finished (both left at 0 by the last CTA)
+    unsigned long long *hp_ctr;  // DEVICE: low word rows reserved, high word CTAs finished (left at 0 by the last CTA)
     unsigned long long *hp_hdr;  // HOST: low word = ready flag, high word = n_rows
 };
 

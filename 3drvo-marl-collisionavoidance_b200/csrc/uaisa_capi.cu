@@ -152,7 +152,8 @@ int uaisa_create(const UaisaConfig *cfg, UaisaHandle **out) {
                + (maxr > 4 ? (size_t)th * s * maxr * 24 : 0)                                       // + shared top-nm lists (one set per slice)
                + (size_t)th * (4 * 8 + 3 * 4) + sizeof(int) * (epc + 2) + 16                         // + re-observe compaction
                + cols * 16 + 16                                                                    // + fp32 position copies
-               + (size_t)(s - 1) * th * 12 + (size_t)th * 4 + 16;                                    // + helpers' partial results, owners' activity
+               + (size_t)(s - 1) * th * 12 + (size_t)th * 4 + 16                                     // + helpers' partial results, owners' activity
+               + (size_t)th * 80 + epc * 24 + 16;                                                  // + per-drone route cache, map sizes
     };
     const bool auto_threads = threads <= 0;
     if (auto_threads) {

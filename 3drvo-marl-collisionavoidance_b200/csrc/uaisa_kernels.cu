@@ -118,6 +118,12 @@ __global__ void __launch_bounds__(UAISA_LB_THREADS, (MAXT <= 128 ? UAISA_MINB128
     double *spart_t = reinterpret_cast<double *>(take(8u * (S - 1) * threads));                      // [S-1][threads] helpers' partial tmin
     int *spart_f = reinterpret_cast<int *>(take(4u * (S - 1) * threads));                            // [S-1][threads] helpers' vo_any | col << 1 | cnt << 2
     int *s_act = reinterpret_cast<int *>(take(4u * threads));                                        // [threads] owner is active in the re-observe phase
+    align16();
+    // Per-drone route cache: current waypoint (3), previous waypoint (3), unit direction + length of the segment between them (4).
+    // They are read four times per step and change only at a waypoint switch or a reset; from L1 each read is a ~100-cycle
+    // long-scoreboard round trip that small batches (one warp per scheduler) cannot hide.  smap: map size of each env of the CTA.
+    double *swp = reinterpret_cast<double *>(take(8u * 10u * threads));                              // [10][threads]
+    double *smap = reinterpret_cast<double *>(take(8u * 3u * P.envs_per_cta));                       // [3][envs_per_cta]
     if (threadIdx.x == 0) { s_nt[0] = 0; s_nt[1] = 0; }
     const float nbr2_lo_f = (float)(P.nbr_range * P.nbr_range * (1.0 - 1e-4)), nbr2_hi_f = (float)(P.nbr_range * P.nbr_range * (1.0 + 1e-4));
     if (WL) {
@@ -151,6 +157,10 @@ __global__ void __launch_bounds__(UAISA_LB_THREADS, (MAXT <= 128 ? UAISA_MINB128
     RG_DECL
     if (L.hp_self && blockIdx.x == 0 && threadIdx.x == 0) { unsigned long long g_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_)); L.hp_hdr[1] = g_; }   // host-step profiling: first CTA's start
     ConstsT<(MAXR <= 4)> C; Drone d; int ep_len = 0;
+#define FILL_WP(col) do { const double *w_ = C.wp(P) + 3 * d.i, *wp_ = C.wp(P) + 3 * max(d.i - 1, 0), *sg_ = C.seg(P) + 4 * d.i; \
+        swp[0 * threads + (col)] = __ldg(w_); swp[1 * threads + (col)] = __ldg(w_ + 1); swp[2 * threads + (col)] = __ldg(w_ + 2); \
+        swp[3 * threads + (col)] = __ldg(wp_); swp[4 * threads + (col)] = __ldg(wp_ + 1); swp[5 * threads + (col)] = __ldg(wp_ + 2); \
+        swp[6 * threads + (col)] = __ldg(sg_); swp[7 * threads + (col)] = __ldg(sg_ + 1); swp[8 * threads + (col)] = __ldg(sg_ + 2); swp[9 * threads + (col)] = __ldg(sg_ + 3); } while (0)
     const double *bld = nullptr; int nb = 0, scn = 0;
     if (valid) {
         scn = __ldg(P.env2scn + env);
@@ -163,11 +173,8 @@ __global__ void __launch_bounds__(UAISA_LB_THREADS, (MAXT <= 128 ? UAISA_MINB128
         d.real_len = P.real_len[a]; d.max_dev = P.max_dev[a];
         const int wf = P.wpf[a]; d.i = wf & WP_MASK; d.flags = wf & (FLAG_ARRIVE | FLAG_DEST);
         if (do_auto) ep_len = P.ep_len[a];
-        {   // a launch starts cold: ask for the waypoint / segment / map lines this step will walk through, all at once
-            const double *w_ = C.wp(P) + 3 * max(d.i - 1, 0), *s_ = C.seg(P) + 4 * d.i;
-            asm volatile("prefetch.global.L1 [%0];" ::"l"(w_)); asm volatile("prefetch.global.L1 [%0];" ::"l"(w_ + 5));
-            asm volatile("prefetch.global.L1 [%0];" ::"l"(s_)); asm volatile("prefetch.global.L1 [%0];" ::"l"(P.map + 3 * scn));
-        }
+        FILL_WP(tid);
+        if (k == 0 || CLM) { const int le_ = CLM ? 0 : le; smap[0 * P.envs_per_cta + le_] = __ldg(P.map + 3 * scn); smap[1 * P.envs_per_cta + le_] = __ldg(P.map + 3 * scn + 1); smap[2 * P.envs_per_cta + le_] = __ldg(P.map + 3 * scn + 2); }
         if (!CLM) { sx[6 * sst + scol] = C.radius; sx[7 * sst + scol] = C.prio; }      // constant over the launch
     }
     if (CLM) {   // every CTA of the cluster needs the constants of ALL drones of the env
@@ -279,7 +286,7 @@ __global__ void __launch_bounds__(UAISA_LB_THREADS, (MAXT <= 128 ? UAISA_MINB128
                 } else if (is_step) {
                     break;       // plain step: nothing to re-observe (uniform over the CTA)
                 }
-                if (rs) reset_drone(P, d, C);
+                if (rs) { reset_drone(P, d, C); FILL_WP(tid); }
                 active = valid && sel && (L.obs || L.count || L.nbr);
                 if (S > 1 && !helper) s_act[tid] = active;             // read by my helpers after the barriers below
                 RG_MARK(RG_AUTORESET);
@@ -345,9 +352,9 @@ __global__ void __launch_bounds__(UAISA_LB_THREADS, (MAXT <= 128 ? UAISA_MINB128
             // drone.dronestate (drone.py:254-263): desired velocity + deviation, side effect on max_deviation
             double d0 = 0, d1 = 0, d2 = 0, dev = 0;
             if (!SL || !helper) {
-                const double *cur = C.wp(P) + 3 * d.i;
-                cal_des_vel(P, d.px, d.py, d.pz, cur, d0, d1, d2);
-                dev = deviation(cur - 3, C.seg(P) + 4 * d.i, d.px, d.py, d.pz);
+                cal_des_vel_v(P, d.px, d.py, d.pz, swp[0 * threads + tt], swp[1 * threads + tt], swp[2 * threads + tt], d0, d1, d2);
+                dev = deviation(swp[3 * threads + tt], swp[4 * threads + tt], swp[5 * threads + tt], swp[6 * threads + tt], swp[7 * threads + tt],
+                                swp[8 * threads + tt], swp[9 * threads + tt], d.px, d.py, d.pz);
                 if (dev > d.max_dev) d.max_dev = dev;
             } else {   // the ego as its owner just published it
                 d.px = sx[0 * sst + scol]; d.py = sx[1 * sst + scol]; d.pz = sx[2 * sst + scol];
@@ -480,10 +487,10 @@ __global__ void __launch_bounds__(UAISA_LB_THREADS, (MAXT <= 128 ? UAISA_MINB128
                 const double nx = d.px + nvx * P.dt, ny = d.py + nvy * P.dt, nz = d.pz + nvz * P.dt;
                 { const double ux = nx - d.px, uy = ny - d.py, uz = nz - d.pz; d.real_len = d.real_len + fast_sqrt(np_dot3(ux, uy, uz, ux, uy, uz)); }
                 d.px = nx; d.py = ny; d.pz = nz; d.vx = nvx; d.vy = nvy; d.vz = nvz;
-                if (within_goal(P, d.px, d.py, d.pz, C.wp(P) + 3 * d.i)) {           // drone.py:116-129
+                if (within_goal_v(P, d.px, d.py, d.pz, swp[0 * threads + tt], swp[1 * threads + tt], swp[2 * threads + tt])) {           // drone.py:116-129
                     const bool at_dest = within_goal(P, d.px, d.py, d.pz, C.wp(P) + 3 * (C.n - 1));
                     if (at_dest) P.extra_len[a] = (float)(d.real_len - C.route_len);      // (stored right away: one live double less)
-                    if (!at_dest && d.i < C.n - 1) { d.i += 1; d.flags &= ~FLAG_ARRIVE; }
+                    if (!at_dest && d.i < C.n - 1) { d.i += 1; d.flags &= ~FLAG_ARRIVE; FILL_WP(tt); }
                 }
                 RG_MARK(RG_MOVE);
                 continue;
@@ -546,7 +553,7 @@ __global__ void __launch_bounds__(UAISA_LB_THREADS, (MAXT <= 128 ? UAISA_MINB128
 
             // ------------------------------------------------------------ phase B only: flags, collisions, reward
             bool arr_now = false, dest_now = false;
-            if (within_goal(P, d.px, d.py, d.pz, C.wp(P) + 3 * d.i) && !(d.flags & FLAG_ARRIVE)) { d.flags |= FLAG_ARRIVE; arr_now = true; }
+            if (within_goal_v(P, d.px, d.py, d.pz, swp[0 * threads + tt], swp[1 * threads + tt], swp[2 * threads + tt]) && !(d.flags & FLAG_ARRIVE)) { d.flags |= FLAG_ARRIVE; arr_now = true; }
             if (d.flags & FLAG_ARRIVE) {
                 const bool at_dest = within_goal(P, d.px, d.py, d.pz, C.wp(P) + 3 * (C.n - 1));
                 if (at_dest) P.extra_len[a] = (float)(d.real_len - C.route_len);
@@ -561,7 +568,7 @@ __global__ void __launch_bounds__(UAISA_LB_THREADS, (MAXT <= 128 ? UAISA_MINB128
                 }
             }
             {   // drone.drone_out_map (drone.py:213-225)
-                const double mapx = __ldg(P.map + 3 * scn), mapy = __ldg(P.map + 3 * scn + 1), mapz = __ldg(P.map + 3 * scn + 2);
+                const int le_ = CLM ? 0 : le; const double mapx = smap[0 * P.envs_per_cta + le_], mapy = smap[1 * P.envs_per_cta + le_], mapz = smap[2 * P.envs_per_cta + le_];
                 if (d.px < 0 || d.px > mapx || d.py < 0 || d.py > mapy || d.pz < 0 || d.pz > mapz) col = true;
             }
             RG_MARK(RG_B_COL);

@@ -202,6 +202,10 @@ struct ConstsT<false> {
 
 __device__ __forceinline__ void load3(const double *p, double &x, double &y, double &z) { x = __ldg(p); y = __ldg(p + 1); z = __ldg(p + 2); }
 
+__device__ __forceinline__ bool within_goal_v(const Params &P, double px, double py, double pz, double qx, double qy, double qz) {
+    const double fx = px - qx, fy = py - qy, fz = pz - qz;
+    return sqrt_le_band(np_dot3(fx, fy, fz, fx, fy, fz), P.goal_thr, P.goal2_lo, P.goal2_hi);   // norm(p - q) <= 0.4, drone.py:172-192
+}
 __device__ __forceinline__ bool within_goal(const Params &P, double px, double py, double pz, const double *q) {
     double qx, qy, qz; load3(q, qx, qy, qz);
     const double fx = px - qx, fy = py - qy, fz = pz - qz;
@@ -210,10 +214,8 @@ __device__ __forceinline__ bool within_goal(const Params &P, double px, double p
 
 // drone.calculate_deviation (drone.py:366-406).  `st` = previous waypoint; `sg` = (dx/|d|, dy/|d|, dz/|d|, |d|) of
 // the segment previous -> current, computed once on the host with the reference's own operations.
-__device__ __forceinline__ double deviation(const double *st, const double *sg, double x0, double y0, double z0) {
-    const double mag = __ldg(sg + 3);
+__device__ __forceinline__ double deviation(double x1, double y1, double z1, double dxh, double dyh, double dzh, double mag, double x0, double y0, double z0) {
     if (mag == 0.0) return 0.0;
-    double x1, y1, z1, dxh, dyh, dzh; load3(st, x1, y1, z1); load3(sg, dxh, dyh, dzh);
     const double px = x0 - x1, py = y0 - y1, pz = z0 - z1;
     const double t = px * dxh + py * dyh + pz * dzh;
     const double qx = x1 + t * dxh, qy = y1 + t * dyh, qz = z1 + t * dzh;
@@ -223,9 +225,8 @@ __device__ __forceinline__ double deviation(const double *st, const double *sg, 
 
 // drone.cal_des_vel (drone.py:199-210, 319-352).  cos(atan2(fy,fx))*cos(atan2(fz,h)) == fx/|f| etc. up to a few
 // ulp (<< the 1e-3 rounding quantum); h == 0 gives (0,0,+-1) on both routes.
-__device__ __forceinline__ void cal_des_vel(const Params &P, double px, double py, double pz, const double *cur,
-                                            double &d0, double &d1, double &d2) {
-    double cx, cy, cz; load3(cur, cx, cy, cz);
+__device__ __forceinline__ void cal_des_vel_v(const Params &P, double px, double py, double pz, double cx, double cy, double cz,
+                                              double &d0, double &d1, double &d2) {
     const double fx = cx - px, fy = cy - py, fz = cz - pz;
     const double s2 = np_dot3(fx, fy, fz, fx, fy, fz);
     if (!sqrt_le_band(s2, P.goal_thr, P.goal2_lo, P.goal2_hi) && s2 == s2) {      // dis > goal_threshold
@@ -234,6 +235,11 @@ __device__ __forceinline__ void cal_des_vel(const Params &P, double px, double p
     } else {
         d0 = d1 = d2 = 0.0;
     }
+}
+
+__device__ __forceinline__ void cal_des_vel(const Params &P, double px, double py, double pz, const double *cur, double &d0, double &d1, double &d2) {
+    double cx, cy, cz; load3(cur, cx, cy, cz);
+    cal_des_vel_v(P, px, py, pz, cx, cy, cz, d0, d1, d2);
 }
 
 // vel_obs3D.cal_vo_exp_tim (vel_obs3D.py:145-182)

@@ -128,12 +128,13 @@ class rnn_ac(nn.Module):   # policy_rnn_ac.py:31-72, defaults of train_process.p
     def features(self, obs, count, multi_cap=0):
         return self.pi.rnn_reader(obs, count, multi_cap)
 
-    def evaluate(self, obs, count, act=None, std_factor=1.0, multi_cap=0):
-        """-> (Normal, value[B], logp[B] or None); one reader pass feeds both heads."""
+    def evaluate(self, obs, count, act=None, std_factor=1.0, multi_cap=0, heads="both"):
+        """-> (Normal, value[B], logp[B] or None); one reader pass feeds both heads.  `heads` = "pi" / "v" skips the head an update
+        iteration does not use (its forward would be thrown away): the skipped entry comes back as None."""
         feat = self.features(obs, count, multi_cap)
-        dist = self.pi.distribution_from_features(feat, std_factor)
-        v = torch.squeeze(self.v.v_net(feat), -1)
-        logp = dist.log_prob(act).sum(-1) if act is not None else None
+        dist = self.pi.distribution_from_features(feat, std_factor) if heads != "v" else None
+        v = torch.squeeze(self.v.v_net(feat), -1) if heads != "pi" else None
+        logp = dist.log_prob(act).sum(-1) if (act is not None and dist is not None) else None
         return dist, v, logp
 
     @torch.no_grad()

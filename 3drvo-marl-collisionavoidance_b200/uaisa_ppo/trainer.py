@@ -183,7 +183,7 @@ class PPOTrainer:
             u["idx"].random_(0, n)
             idx = u["idx"]
             w = self._ok[idx].float()
-            dist_, _, logp = self.ac.evaluate(self._obs[idx], self._cnt[idx], self._act[idx], multi_cap=u["cap"])
+            dist_, _, logp = self.ac.evaluate(self._obs[idx], self._cnt[idx], self._act[idx], multi_cap=u["cap"], heads="pi")
             ratio = torch.exp(logp - self._logp_old[idx])
             a_ = torch.nan_to_num(self._adv[idx], 0.0, 0.0, 0.0)
             clip_adv = torch.clamp(ratio, 1 - cfg.clip_ratio, 1 + cfg.clip_ratio) * a_
@@ -197,7 +197,7 @@ class PPOTrainer:
             u["idx"].random_(0, n)
             idx = u["idx"]
             w = self._ok[idx].float()
-            _, v, _ = self.ac.evaluate(self._obs[idx], self._cnt[idx], None, multi_cap=u["cap"])
+            _, v, _ = self.ac.evaluate(self._obs[idx], self._cnt[idx], None, multi_cap=u["cap"], heads="v")
             loss = (((v - torch.nan_to_num(self._ret[idx], 0.0, 0.0, 0.0)) ** 2) * w).sum() / w.sum().clamp(min=1)
             u["loss_v"].copy_(loss.detach())
             loss.backward()
@@ -273,7 +273,7 @@ class PPOTrainer:
             idx = torch.randint(0, n, (mb,), device=self.dev) if mb < n else torch.arange(n, device=self.dev)
             w = ok[idx].float()
             self.pi_opt.zero_grad(set_to_none=True)
-            dist_, _, logp = self.ac.evaluate(obs[idx], cnt[idx], act[idx])
+            dist_, _, logp = self.ac.evaluate(obs[idx], cnt[idx], act[idx], heads="pi")
             ratio = torch.exp(logp - logp_old[idx])
             a_ = torch.nan_to_num(adv[idx], 0.0, 0.0, 0.0)
             clip_adv = torch.clamp(ratio, 1 - cfg.clip_ratio, 1 + cfg.clip_ratio) * a_
@@ -294,7 +294,7 @@ class PPOTrainer:
             idx = torch.randint(0, n, (mb,), device=self.dev) if mb < n else torch.arange(n, device=self.dev)
             w = ok[idx].float()
             self.vf_opt.zero_grad(set_to_none=True)
-            _, v, _ = self.ac.evaluate(obs[idx], cnt[idx], None)
+            _, v, _ = self.ac.evaluate(obs[idx], cnt[idx], None, heads="v")
             loss_v = (((v - torch.nan_to_num(ret[idx], 0.0, 0.0, 0.0)) ** 2) * w).sum() / w.sum().clamp(min=1)   # :379-383
             loss_v.backward()
             self._allreduce_grads(list(self.ac.v.parameters()))

@@ -191,6 +191,7 @@ int uaisa_create(const UaisaConfig *cfg, UaisaHandle **out) {
         if (threads > 128 || threads % 32 || (N + threads - 1) / threads > 8) { delete h; return fail(UAISA_EINVAL, "n_drones > 128 needs threads_per_block in {32,64,96,128} with at most 8 CTAs per env"); }
         P.cl = (N + threads - 1) / threads;
     } else if (threads < N || threads > 128 || threads % 32) { delete h; return fail(UAISA_EINVAL, "threads_per_block must be a multiple of 32 in [n_drones, 128]"); }
+    P.dsmem = (cluster && !std::getenv("UAISA_CLUSTER_L2")) ? 1 : 0;   // exchange through distributed shared memory unless asked for the L2 path
     h->threads = threads; P.threads = threads; P.slices = slices; P.envs_per_cta = cluster ? 1 : threads / N;
     // CTA-level compaction of the re-observe phase pays only with several warps per CTA and more than a handful of
     // drones per env (measured: N=16 +7 %, N=4 +2 % at 128 threads, -10 % with single-warp CTAs)

@@ -57,6 +57,14 @@ __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
+// distributed shared memory: the address of `saddr` (a shared::cta address of this CTA) inside CTA `rank` of the cluster, and stores to it
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t saddr, uint32_t rank) {
+    uint32_t r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank)); return r;
+}
+__device__ __forceinline__ void st_cluster_f64(uint32_t addr, double v) { asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory"); }
+__device__ __forceinline__ void st_cluster_v4f32(uint32_t addr, float x, float y, float z, float w) {
+    asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
+}
 enum Phase : int { PH_A = 0, PH_B = 1, PH_OBS = 2 };
 
 // Optional per-region cycle accounting (build with -DUAISA_REGION_CLOCKS; lane 0 of every warp accumulates
@@ -295,8 +303,23 @@ __global__ void __launch_bounds__(UAISA_LB_THREADS, (MAXT <= 128 ? UAISA_MINB128
             if (WL && !compact && ph == PH_OBS && !__any_sync(0xffffffffu, active)) continue;      // (the compacted variant meets at CTA barriers)
             // -------------------------------------------------------- publish my state, then read the others'
             if (WL && clear_rows && ph == PH_B && lane == 0) bulk_wait_all();   // my warp's cleared rows have landed: rows may now be scattered
-            ENV_SYNC();   // everybody is done reading the previous phase's columns
-            if (CLM) {
+            const bool DSM = CLM && P.dsmem;
+            if (DSM) cluster_sync_all(); else ENV_SYNC();   // everybody (of the cluster / the CTA) is done reading the previous phase's columns
+            if (DSM) {
+                // Distributed shared memory: every owner stores its six values (+ the fp32 copy) straight into the exchange tile of
+                // each CTA of the cluster (st.shared::cluster through mapa); the cluster barrier below makes them visible.  No trip
+                // through L2, no reload loop.
+                if (valid) {
+                    const uint32_t sx_a = (uint32_t)__cvta_generic_to_shared(sx) + 8u * (uint32_t)k, sxf_a = (uint32_t)__cvta_generic_to_shared(sxf) + 16u * (uint32_t)k;
+                    const uint32_t fs = 8u * (uint32_t)sst;
+                    for (int r = 0; r < P.cl; r++) {
+                        const uint32_t b_ = mapa_shared(sx_a, (uint32_t)r);
+                        st_cluster_f64(b_, d.px); st_cluster_f64(b_ + fs, d.py); st_cluster_f64(b_ + 2 * fs, d.pz);
+                        st_cluster_f64(b_ + 3 * fs, d.vx); st_cluster_f64(b_ + 4 * fs, d.vy); st_cluster_f64(b_ + 5 * fs, d.vz);
+                        if constexpr (MAXR > 4) st_cluster_v4f32(mapa_shared(sxf_a, (uint32_t)r), (float)d.px, (float)d.py, (float)d.pz, 0.f);
+                    }
+                }
+            } else if (CLM) {
                 double *gb = P.gx + ((size_t)(pubn & 1) * A + (size_t)env0 * N) * 6;      // this env's slice of the exchange buffer
                 if (valid) { double *g = gb + (size_t)k * 6; g[0] = d.px; g[1] = d.py; g[2] = d.pz; g[3] = d.vx; g[4] = d.vy; g[5] = d.vz; }
                 pubn++;
@@ -340,7 +363,7 @@ __global__ void __launch_bounds__(UAISA_LB_THREADS, (MAXT <= 128 ? UAISA_MINB128
                     wa = env_t * N + wk;
                 }
             } else {
-                ENV_SYNC();
+                if (DSM) cluster_sync_all(); else ENV_SYNC();   // all columns are in place
             }
             RG_MARK(RG_SYNC);
             // helper threads (slices > 1) walk their share of the ego's neighbours whenever its owner is active

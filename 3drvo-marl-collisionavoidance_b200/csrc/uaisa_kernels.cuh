@@ -38,6 +38,7 @@ struct Params {
     int tile0_bytes, tile1_bytes;   // constant smem tiles behind the TMA fills (zeros / 0xFF), multiples of 16
     int env_train, count_pairs, compact;
     int slices;                      // neighbour slices per ego (helper threads; 1 = off).  blockDim.x = threads * slices
+    int dsmem;                       // cluster mode: exchange the columns through distributed shared memory (1) or through L2 (0)
     int cl;                          // CTAs per env (thread-block cluster size) when an env does not fit one CTA; 0 = one CTA holds whole envs
     double *gx; int *genv;           // cluster mode: global exchange buffers [2][A][6] (p, v in fp64) and [2][E] (reset-policy bits)
     // hyper-parameters (reference constructor defaults, see include/uaisa_b200.h)

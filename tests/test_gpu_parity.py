@@ -56,9 +56,12 @@ def test_dense_256():
     assert st.rows > 0
 
 
-@pytest.mark.parametrize("N,tpb", [(300, 0), (200, 64), (130, 32), (256, 128)])
-def test_cluster_mode_envs_larger_than_one_cta(N, tpb):
-    """N > 128: one env is spread over a thread-block cluster (exchange through L2 + hardware cluster barrier)."""
+@pytest.mark.parametrize("N,tpb,l2", [(300, 0, False), (200, 64, False), (130, 32, False), (256, 128, False), (200, 64, True), (256, 0, True)])
+def test_cluster_mode_envs_larger_than_one_cta(N, tpb, l2, monkeypatch):
+    """N > 128: one env is spread over a thread-block cluster; the columns are exchanged through distributed shared memory
+    (st.shared::cluster + cluster barrier) or, with UAISA_CLUSTER_L2, through a double-buffered array in L2."""
+    if l2:
+        monkeypatch.setenv("UAISA_CLUSTER_L2", "1")
     scn = scenario_c4(seed=3, n_scenarios=1, n_drones=N)
     st = lockstep(scn, 3, 10, 6, seed=9, block=2, threads_per_block=tpb, max_ep_len=4)
     st.assert_parity()

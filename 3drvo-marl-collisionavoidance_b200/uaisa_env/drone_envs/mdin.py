@@ -173,15 +173,27 @@ class ir_gym:
             raise ValueError("expected %d actions" % self.drone_num)
         act = np.stack([np.asarray(a, dtype=np.float64).reshape(-1) for a in action_list])
         assert act.shape == (self.drone_num, 3)            # drone.py:101
-        v = self._vec
-        v.step(torch.from_numpy(act.astype(np.float32)).to(v.device))
+        # one latency-optimised host round trip (uaisa_step_host_sparse): host action in, ragged result out
+        r = self._vec.step_host_sparse(np.ascontiguousarray(act, dtype=np.float32), auto_reset=False)
         self._dirty()
-        obs = self._obs_list()
-        rew = np.round(v.reward.cpu().numpy().astype(np.float64), 3)
-        done = [bool(x) for x in v.done.cpu().numpy()]
-        info = [bool(x) for x in v.info.cpu().numpy()]
-        fin = [bool(x) for x in v.finish.cpu().numpy()]
-        return obs, [r for r in rew], done, info, fin
+        cnt = r["count"]
+        self_obs = np.round(r["self_obs"].astype(np.float64), 2)          # fp32 image -> the reference's 2-dp doubles
+        obs = [np.zeros(12 + 9 * max(int(cnt[k]), 1)) for k in range(self.drone_num)]
+        for k in range(self.drone_num):
+            obs[k][:12] = self_obs[k]
+        rows = r["rows"]
+        if len(rows):
+            rv = np.round(rows["v"].astype(np.float64), 2)
+            for q in range(len(rows)):
+                sl = int(rows["slot"][q])
+                obs[int(rows["agent"][q])][12 + 9 * sl: 21 + 9 * sl] = rv[q]
+        if not all(np.isfinite(o).all() for o in obs):
+            raise ValueError("observation contains NaN/Inf (ir_gym.py:232-239)")
+        rew = np.round(r["reward"].astype(np.float64), 3)
+        done = [bool(x) for x in r["done"]]
+        info = [bool(x) for x in r["info"]]
+        fin = [bool(x) for x in r["finish"]]
+        return obs, [x for x in rew], done, info, fin
 
     def render(self, *a, **k):                             # plotting is out of scope
         pass

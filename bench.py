@@ -356,6 +356,29 @@ def main():
     else:                      # copy-engine path: first-phase block (header, reward, self obs, flags + count, row window)
         d2h = 16 + A * (4 + 48 + 4) + max(256, A // 8) * 48
 
+    # ---- arithmetic roofline: algorithmic flops per agent-step from the kernel's own pair counters, measured on a
+    # small copy of the workload (counting costs atomics, so it is not done in the timed region)
+    flops = None
+    try:
+        cE = min(E, 1024)
+        cenv = VecMdin(scn, cE, neighbors_num=NM, device=dev, count_pairs=True)
+        cenv.reset()
+        cT = 50
+        cacts = torch.from_numpy(synth_actions(np.random.default_rng(123), cT, cenv.A)).to(dev)
+        cenv.rollout(cacts, {}, auto_reset=True, max_ep_len=MAX_EP_LEN); cenv.counters()
+        cenv.rollout(cacts, {"count": torch.empty((cT, cenv.A), dtype=torch.uint8, device=dev)}, auto_reset=True, max_ep_len=MAX_EP_LEN)
+        cc = cenv.counters()
+        rng_pp = cc["in_range_pairs"] / (cenv.A * cT); cone_pp = cc["cone_evals"] / (cenv.A * cT)
+        M_ = int(scn.n_buildings.max()) if hasattr(scn, "n_buildings") else 0
+        F = 150.0 + 2.0 * (N - 1) * 10.0 + cone_pp * 112.0 + M_ * 12.0      # F_self + range tests of both passes + full cone evaluations + cylinders
+        fp64_peak = 148 * 64 * 2 * 1.965e9 / 1e12
+        flops = {"bound": "fp64 pipe", "flops_per_agent_step": F, "in_range_pairs_per_agent_step": rng_pp, "cone_evaluations_per_agent_step": cone_pp,
+                 "achieved": None, "peak": fp64_peak, "unit": "TFLOP/s", "peak_source": "nominal 148 SMs x 64 FMA/clk x 2 x 1.965 GHz (the step computes in fp64)",
+                 "formula": "150 + 2 (N-1) 10 + cone_evals 112 + M 12 (SURVEY.md 8d; every add/mul/cmp/div/sqrt/transcendental counts 1)"}
+        cenv.close()
+    except Exception as ex:      # counters are diagnostics: never fail the bench line on them
+        flops = {"error": str(ex)}
+
     # ---- side measurement at the saturating size (the default workload is 4096 agents = 128 warps on 148 SMs, i.e.
     # latency-bound by construction; SURVEY.md section 8d asks for the exact BASELINE config AND the saturating size)
     sat = None
@@ -432,6 +455,10 @@ def main():
                     "neighbour_rows_per_step": rows_total / max(Ke, 1)},
             "gpu_launches": int(launches), "clocks": clk,
         }
+        if flops and "flops_per_agent_step" in flops:
+            flops["achieved"] = value / world * flops["flops_per_agent_step"] / 1e12
+            flops["frac"] = flops["achieved"] / flops["peak"]
+        line["roofline_flops"] = flops
         if cb:
             line["cpu_baseline"] = cb
         if sat is not None:

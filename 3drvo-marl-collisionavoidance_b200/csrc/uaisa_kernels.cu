@@ -11,6 +11,15 @@
 //
 // The three phases run through ONE copy of the dronestate / pair / row-writer code (a 3-trip loop), which
 // keeps the kernel small enough for the instruction cache and the live register set below 168.
+//
+// Geometries (template <MAXR, MAXT, WL, SL>, chosen by uaisa_create):
+//   WL  N divides 32: every env inside one warp, barriers are __syncwarp, reductions are ballots, output rows are cleared by a
+//       TMA bulk store per warp (cp.async.bulk shared -> global)
+//   CTA whole envs per CTA, __syncthreads; optional CTA-level compaction of the re-observe phase
+//   CLM N > 128: one env per thread-block cluster, columns exchanged through distributed shared memory (or L2) around cluster barriers
+//   SL  neighbour slices: helper warps walk a share of each ego's neighbour chunks and hand partial results to the owner
+// Other pieces: per-drone route cache and map sizes in shared memory; the host-pack tail of uaisa_step_host_sparse (results
+// written straight to mapped host memory, completion word raised by the last CTA).
 #include "uaisa_kernels.cuh"
 
 namespace uaisa {

@@ -48,7 +48,7 @@ struct UaisaHandle {
     int32_t *h_nbr = nullptr;
     cudaStream_t h_stream = nullptr;
     // uaisa_step_host_sparse: device block + pinned host mirror + one captured graph
-    char *sp_dev = nullptr, *sp_host = nullptr, *sp_host_dev = nullptr; float *sp_hact = nullptr, *sp_hact_dev = nullptr; bool sp_zero_copy = false;
+    char *sp_dev = nullptr, *sp_host = nullptr, *sp_host_dev = nullptr; float *sp_hact = nullptr, *sp_hact_dev = nullptr; bool sp_zero_copy = false, sp_zc_action = false;
     size_t sp_off_reward = 0, sp_off_self = 0, sp_off_flags = 0, sp_off_rows = 0, sp_bytes = 0, sp_phase1 = 0;
     int sp_cap = 0, sp_r0 = 0, sp_auto = -1, sp_maxlen = -1;
     cudaGraphExec_t sp_graph = nullptr;
@@ -464,19 +464,22 @@ int uaisa_step_host_sparse(UaisaHandle *h, const float *action, int32_t auto_res
         CK(cudaStreamSynchronize(s));
         cudaGraph_t graph = nullptr;
         CK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
-        // Small batches run as ONE kernel node: the env kernel reads the action from mapped pinned memory, writes reward / flags and
-        // (in its host-pack tail) the self parts and existing rows straight into the mapped result block, and its last CTA raises the
-        // ready word the host polls -- no copy-engine, memset or pack nodes and no stream synchronisation on the critical path.
-        // Large batches keep the copy engines: H2D action, env kernel, pack kernel, D2H of the block.
-        const bool zero_copy = A * 3 * sizeof(float) <= (size_t(1) << 20) && std::getenv("UAISA_HOST_COPY_ENGINE") == nullptr;
-        h->sp_zero_copy = zero_copy;
+        // The graph holds ONE kernel node: the env kernel writes reward / flags and (in its host-pack tail) the self parts and existing
+        // rows straight into the mapped result block, and its last CTA raises the ready word the host polls -- no copy-engine D2H,
+        // memset or pack nodes and no stream synchronisation on the critical path.  UAISA_HOST_COPY_ENGINE selects the older
+        // H2D action / env kernel / pack kernel / D2H block graph (kept as a fallback and for A/B runs).
+        const bool zero_copy = std::getenv("UAISA_HOST_COPY_ENGINE") == nullptr;
+        // small action blocks are read over PCIe by the kernel itself; large ones are copied by the copy engine straight from the caller's
+        // buffer (outside the graph: its address changes from call to call), without a staging memcpy on the host
+        const bool zc_action = zero_copy && A * 3 * sizeof(float) <= (size_t(1) << 20);
+        h->sp_zero_copy = zero_copy; h->sp_zc_action = zc_action;
         uint8_t *fl = reinterpret_cast<uint8_t *>(h->sp_dev + h->sp_off_flags);
         Launch L{};
         L.mode = MODE_STEP; L.T = 1; L.auto_reset = auto_reset ? 1 : 0; L.max_ep_len = max_ep_len;
         L.obs = h->h_obs; L.count = fl + 3 * A; L.nbr = h->h_nbr;
         if (zero_copy) {
             uint8_t *hfl = reinterpret_cast<uint8_t *>(h->sp_host_dev + h->sp_off_flags);
-            L.action = h->sp_hact_dev;
+            L.action = zc_action ? h->sp_hact_dev : h->h_action;
             L.reward = reinterpret_cast<float *>(h->sp_host_dev + h->sp_off_reward); L.done = hfl; L.info = hfl + A; L.finish = hfl + 2 * A;
             L.hp_self = reinterpret_cast<float *>(h->sp_host_dev + h->sp_off_self); L.hp_count = hfl + 3 * A;
             L.hp_rows = h->sp_host_dev + h->sp_off_rows; L.hp_cap = h->sp_cap;
@@ -505,7 +508,8 @@ int uaisa_step_host_sparse(UaisaHandle *h, const float *action, int32_t auto_res
     static double acc[3] = {0, 0, 0}; static long nprof = 0;
     auto now = [] { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     const double t0 = prof ? now() : 0;
-    std::memcpy(h->sp_hact, action, sizeof(float) * A * 3);
+    if (h->sp_zero_copy && !h->sp_zc_action) CK(cudaMemcpyAsync(h->h_action, action, sizeof(float) * A * 3, cudaMemcpyHostToDevice, s));
+    else std::memcpy(h->sp_hact, action, sizeof(float) * A * 3);
     const double t1 = prof ? now() : 0;
     volatile unsigned long long *hdr = reinterpret_cast<volatile unsigned long long *>(h->sp_host);
     if (h->sp_zero_copy) *hdr = 0;

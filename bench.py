@@ -351,10 +351,8 @@ def main():
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = world * A * Ke / float(te.item())
     h2d = A * 3 * 4
-    if h2d <= (1 << 20):       # single-kernel path: ready word, reward, self obs, flags + count, and the rows that exist
-        d2h = int(8 + A * (4 + 48 + 4) + rows_total / max(Ke, 1) * 48)
-    else:                      # copy-engine path: first-phase block (header, reward, self obs, flags + count, row window)
-        d2h = 16 + A * (4 + 48 + 4) + max(256, A // 8) * 48
+    # result block written by the kernel: header (ready word + 2 timestamps), reward, self obs, flags + count, and the rows that exist
+    d2h = int(24 + A * (4 + 48 + 4) + rows_total / max(Ke, 1) * 48)
 
     # ---- arithmetic roofline: algorithmic flops per agent-step from the kernel's own pair counters, measured on a
     # small copy of the workload (counting costs atomics, so it is not done in the timed region)
@@ -449,8 +447,8 @@ def main():
             "single_step_launch": {"value": world * A / (single_ms * 1e-3), "unit": "agent-steps/s", "ms_per_step": single_ms,
                                    "note": "one launch per env step (closed-loop use), device-timed over %d steps" % Ks},
             "e2e": {"value": e2e_value, "unit": "agent-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke,
-                    "api": "uaisa_step_host_sparse: one CUDA graph per step; <= 87381 agents: single env-kernel node reading the action from / writing the result block to "
-                           "mapped pinned host memory (PCIe traffic inside the kernel, host polls a ready word); larger: H2D action, env kernel, pack kernel, D2H block; "
+                    "api": "uaisa_step_host_sparse: one CUDA graph per step with a single env-kernel node that writes the result block to mapped pinned host memory "
+                           "(PCIe traffic inside the kernel, host polls a ready word); the action is read from mapped pinned memory (<= 1 MiB) or copied H2D from the caller's buffer; "
                            "result = reward/done/info/finish/count + 12 self values per agent + every existing neighbour row",
                     "neighbour_rows_per_step": rows_total / max(Ke, 1)},
             "gpu_launches": int(launches), "clocks": clk,

@@ -171,10 +171,11 @@ int uaisa_policy_heads(const float *feat, int32_t A, const float *const *weights
  * One env step with HOST action in / HOST results out, returned in the reference's own ragged spirit: the 12 self
  * values of every observation plus only the neighbour rows that exist (an observation is 12 + 9*max(k,1) values in
  * the reference, ir_gym.py:203-229; the fixed-slot padding is never shipped over PCIe).  Internally ONE CUDA graph is
- * launched per call.  Up to 87381 agents it holds a single node: the env kernel reads the action from mapped pinned
- * memory, writes the result block straight into mapped pinned memory and its last CTA raises a ready word the host
- * polls (no copy-engine work, no stream synchronisation).  Larger batches use H2D action, env kernel, pack kernel, D2H
- * block.  Pointers in `out` refer to library-owned pinned host memory and stay valid until the next call on this
+ * launched per call and holds a single node: the env kernel writes the result block straight into mapped pinned memory and
+ * its last CTA raises a ready word the host polls (no copy-engine D2H, no stream synchronisation).  Action blocks up to
+ * 1 MiB are read by the kernel from mapped pinned memory; larger ones are copied by the copy engine straight from the
+ * caller's buffer (pinned memory makes that a direct DMA).  Pointers in `out` refer to library-owned pinned host memory and
+ * stay valid until the next call on this
  * handle.  Synchronous. */
 typedef struct UaisaRowRec {
     float v[9];        /* apex(3) rel_pos(3) alpha min_dis 1/(t+0.2), rounded to 2 dp */

@@ -48,7 +48,7 @@ struct UaisaHandle {
     int32_t *h_nbr = nullptr;
     cudaStream_t h_stream = nullptr;
     // uaisa_step_host_sparse: device block + pinned host mirror + one captured graph
-    char *sp_dev = nullptr, *sp_host = nullptr, *sp_host_dev = nullptr; float *sp_hact = nullptr, *sp_hact_dev = nullptr; bool sp_zero_copy = false, sp_zc_action = false;
+    char *sp_dev = nullptr, *sp_host = nullptr, *sp_host_dev = nullptr; float *sp_hact = nullptr, *sp_hact_dev = nullptr; bool sp_zero_copy = false, sp_zc_action = false, sp_inflight = false;
     size_t sp_off_reward = 0, sp_off_self = 0, sp_off_flags = 0, sp_off_rows = 0, sp_bytes = 0, sp_phase1 = 0;
     int sp_cap = 0, sp_r0 = 0, sp_auto = -1, sp_maxlen = -1;
     cudaGraphExec_t sp_graph = nullptr;
@@ -66,8 +66,17 @@ int dalloc(UaisaHandle *h, T **p, size_t n) {
     return UAISA_OK;
 }
 
+// The polled host step returns when its kernel has PUBLISHED the results, a few microseconds before the kernel retires (state is
+// already written; the pair / non-finite counters are not).  Every other entry point that touches the handle's device memory on
+// another stream first lets that kernel finish.
+int settle(UaisaHandle *h, void *stream) {
+    if (h->sp_inflight && static_cast<cudaStream_t>(stream) != h->h_stream) { CK(cudaStreamSynchronize(h->h_stream)); h->sp_inflight = false; }
+    return UAISA_OK;
+}
+
 int launch(UaisaHandle *h, const Launch &L, void *stream) {
     if (!h->scenarios_set) return fail(UAISA_ESTATE, "uaisa_set_scenarios has not been called");
+    { int rc_ = settle(h, stream); if (rc_) return rc_; }
     if (h->P.cl > 1) {     // thread-block cluster launch: the G CTAs of an env are co-scheduled and share the hardware cluster barrier
         cudaLaunchConfig_t cfg{};
         cfg.gridDim = dim3(h->grid); cfg.blockDim = dim3(h->threads * h->P.slices); cfg.dynamicSmemBytes = h->smem; cfg.stream = static_cast<cudaStream_t>(stream);
@@ -325,6 +334,7 @@ int uaisa_autoreset(UaisaHandle *h, const uint8_t *done, const uint8_t *finish, 
 
 static int copy_state(UaisaHandle *h, const UaisaStateView *v, bool to_handle, void *stream) {
     if (!h || !v) return fail(UAISA_EINVAL, "NULL argument");
+    { int rc_ = settle(h, stream); if (rc_) return rc_; }
     const Params &P = h->P;
     const size_t A = h->A;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -341,6 +351,7 @@ int uaisa_set_state(UaisaHandle *h, const UaisaStateView *src, void *stream) { r
 int uaisa_cal_des(UaisaHandle *h, float *des, void *stream) {
     if (!h || !des) return fail(UAISA_EINVAL, "NULL argument");
     if (!h->scenarios_set) return fail(UAISA_ESTATE, "uaisa_set_scenarios has not been called");
+    { int rc_ = settle(h, stream); if (rc_) return rc_; }
     uaisa_cal_des_kernel<<<(h->A + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(h->P, des);
     h->launches++;
     CK(cudaGetLastError());
@@ -350,6 +361,7 @@ int uaisa_cal_des(UaisaHandle *h, float *des, void *stream) {
 int uaisa_action_transform(UaisaHandle *h, const float *a_inc, float acceler, float *a_inc_rounded, float *action, void *stream) {
     if (!h || !a_inc || !action) return fail(UAISA_EINVAL, "NULL argument");
     if (!h->scenarios_set) return fail(UAISA_ESTATE, "uaisa_set_scenarios has not been called");
+    { int rc_ = settle(h, stream); if (rc_) return rc_; }
     uaisa_action_transform_kernel<<<(h->A + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(h->P, a_inc, acceler, a_inc_rounded, action);
     h->launches++;
     CK(cudaGetLastError());
@@ -365,6 +377,7 @@ int uaisa_gae(const float *rew, const float *val, const uint8_t *cut, int32_t T,
 
 int uaisa_indicators(UaisaHandle *h, float *max_dev, float *extra_len, void *stream) {
     if (!h) return fail(UAISA_EINVAL, "NULL handle");
+    { int rc_ = settle(h, stream); if (rc_) return rc_; }
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (max_dev) CK(cudaMemcpyAsync(max_dev, h->P.max_dev, sizeof(float) * h->A, cudaMemcpyDefault, s));
     if (extra_len) CK(cudaMemcpyAsync(extra_len, h->P.extra_len, sizeof(float) * h->A, cudaMemcpyDefault, s));
@@ -373,6 +386,7 @@ int uaisa_indicators(UaisaHandle *h, float *max_dev, float *extra_len, void *str
 
 int uaisa_get_counters(UaisaHandle *h, int64_t *in_range_pairs, int64_t *cone_evals, int64_t *nonfinite_obs, void *stream) {
     if (!h) return fail(UAISA_EINVAL, "NULL handle");
+    { int rc_ = settle(h, stream); if (rc_) return rc_; }
     unsigned long long c[4] = {0, 0, 0, 0};
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     CK(cudaMemcpyAsync(c, h->P.counters, sizeof(c), cudaMemcpyDeviceToHost, s));
@@ -532,6 +546,7 @@ int uaisa_step_host_sparse(UaisaHandle *h, const float *action, int32_t auto_res
 #endif
         }
         n_rows = (int)(w >> 32);
+        h->sp_inflight = true;        // published, not necessarily retired (see settle())
     } else {
         h->launches += 2;
         CK(cudaStreamSynchronize(s));

@@ -252,6 +252,9 @@ def test_step_host_sparse_matches_device_step(N, E, copy_engine, monkeypatch):
             ag, sl = int(r["agent"]), int(r["slot"])
             assert sl < cnt[ag] and np.array_equal(r["v"], obs[ag, 12 + 9 * sl: 21 + 9 * sl]) and int(r["nbr"]) == nbr[ag, sl]
         rows_seen += len(out["rows"])
+        if t % 8 == 7:      # the device state behind a polled host step is complete and visible to other streams right away
+            sa, sb = a.get_state(), b.get_state()
+            assert all(torch.equal(sa[k], sb[k]) for k in sa), t
         rag = VecMdin.ragged_from_sparse(out, 10)
         assert all(rag[k].shape[0] == 12 + 9 * max(int(cnt[k]), 1) and np.array_equal(rag[k], obs[k, : rag[k].shape[0]]) for k in range(a.A))
     assert rows_seen > (30 if N <= 128 else 4), rows_seen

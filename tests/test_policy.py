@@ -106,3 +106,19 @@ def test_fused_features_and_tcgen05_heads_match_torch():
         assert (mu - dist.mean).abs().max() < 5e-3 and (v - ref_v).abs().max() < 5e-3 * max(1.0, float(ref_v.abs().max())), ((mu - dist.mean).abs().max(), (v - ref_v).abs().max())
         a, vv, logp = fp.step(o, c)
         assert a.shape == (A, 3) and torch.isfinite(logp).all() and (vv - ref_v).abs().max() < 5e-3 * max(1.0, float(ref_v.abs().max()))
+
+
+def test_eval_parity_policy_forms_agree():
+    """The numpy form (run inside the reference's policy_test when the golden is made) and the torch form (run by the batched loop)
+    of the scripted evaluation policy are the same function: identical float32 outputs on 2-dp observations."""
+    import numpy as np
+    import torch
+    from _util import goal_policy_np, goal_policy_torch
+    rng = np.random.default_rng(3)
+    obs = np.round(rng.normal(0, 2, (4000, 21)), 2)
+    obs[:200, 3:6] = 0.0                      # standing still
+    obs[200:300, 8:11] = 0.0                  # no desired velocity (at the waypoint)
+    a = np.stack([goal_policy_np(o) for o in obs])
+    b = goal_policy_torch(torch.from_numpy(obs.astype(np.float32))).numpy()
+    ra, rb = np.round(a, 2), np.round(b, 2)
+    assert (ra != rb).mean() == 0 and np.abs(a - b).max() < 1e-6

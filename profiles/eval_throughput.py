@@ -14,8 +14,9 @@ for E in (1, 256, 4096):
     env = VecMdin(scenario_c1(), E, neighbors_num=10)
     pt = post_train(env, num_episodes=2 * E, max_ep_len=150)
     pt.policy_test(ac, policy_name="warmup") if E == 1 else None
-    torch.cuda.synchronize(); t0 = time.perf_counter()
-    r = pt.policy_test(ac, policy_name="random_init_E%d" % E)
-    torch.cuda.synchronize(); dt = time.perf_counter() - t0
-    print("E=%d: %d episodes in %.2f s = %.0f episodes/s, %.3g agent-steps/s (%d env steps)" % (E, len(r["episodes"]), dt, len(r["episodes"]) / dt, r["env_steps"] * E * env.N / dt, r["env_steps"]))
+    for g in (False, True):
+      torch.cuda.synchronize(); t0 = time.perf_counter()
+      r = pt.policy_test(ac, policy_name="random_init_E%d" % E, use_cuda_graph=g)
+      torch.cuda.synchronize(); dt = time.perf_counter() - t0
+      print("graph=%s E=%d: %d episodes in %.2f s = %.0f episodes/s, %.3g agent-steps/s (%d env steps)" % (g, E, len(r["episodes"]), dt, len(r["episodes"]) / dt, r["env_steps"] * E * env.N / dt, r["env_steps"]))
     env.close()

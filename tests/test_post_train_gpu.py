@@ -30,8 +30,8 @@ def _stats(line):
 
 
 @pytest.mark.parametrize("name", sorted(GOLD))
-@pytest.mark.parametrize("E", [1, 4])
-def test_policy_test_matches_the_reference_loop(name, E):
+@pytest.mark.parametrize("E,graph", [(1, False), (1, True), (4, True)])
+def test_policy_test_matches_the_reference_loop(name, E, graph):
     from uaisa_env.vec_env import VecMdin
     from uaisa_ppo.post_train import post_train
 
@@ -39,7 +39,7 @@ def test_policy_test_matches_the_reference_loop(name, E):
     scn = _scenario(name)
     env = VecMdin(scn, E, neighbors_num=10)
     pt = post_train(env, num_episodes=g["num_episodes"] * E, max_ep_len=g["max_ep_len"], acceler_vel=g["acceler_vel"])
-    res = pt.policy_test(NoisyGoalPolicyTorch(eval_noise_table(16, 256, scn.N, g["noise_seed"], g["noise_scale"])), policy_name=name)
+    res = pt.policy_test(NoisyGoalPolicyTorch(eval_noise_table(16, 256, scn.N, g["noise_seed"], g["noise_scale"])), policy_name=name, use_cuda_graph=graph)
     ref = [EP.match(e).groups() for e in g["episodes"]]
     assert len(res["episodes"]) == len(ref) * E
     for e in range(E):      # every env replays the reference's episode sequence (same scenario, same policy, same noise rows)
@@ -72,7 +72,10 @@ def test_policy_test_with_the_actor_critic():
     torch.manual_seed(0)
     env = VecMdin(scenario_c1(), 64, neighbors_num=10)
     d = tempfile.mkdtemp()
-    res = post_train(env, num_episodes=128, max_ep_len=30).policy_test(rnn_ac().cuda(), policy_name="random_init", result_path=d)
+    ac = rnn_ac().cuda()
+    res = post_train(env, num_episodes=128, max_ep_len=30).policy_test(ac, policy_name="random_init", result_path=d)
+    res2 = post_train(env, num_episodes=128, max_ep_len=30).policy_test(ac, policy_name="random_init", use_cuda_graph=False)
+    assert len(res2["episodes"]) == 128
     assert len(res["episodes"]) == 128 and all(1 <= ep["ep_len"] <= 30 for ep in res["episodes"])
     assert open(d + "/result.txt").read().startswith("policy_name: random_init  successful rate: ")
     env.close()

@@ -73,7 +73,7 @@ def test_policy_test_with_the_actor_critic():
     env = VecMdin(scenario_c1(), 64, neighbors_num=10)
     d = tempfile.mkdtemp()
     ac = rnn_ac().cuda()
-    res = post_train(env, num_episodes=128, max_ep_len=30).policy_test(ac, policy_name="random_init", result_path=d)
+    res = post_train(env, num_episodes=128, max_ep_len=30).policy_test(ac, policy_name="random_init", result_path=d, use_cuda_graph=True)
     res2 = post_train(env, num_episodes=128, max_ep_len=30).policy_test(ac, policy_name="random_init", use_cuda_graph=False)
     assert len(res2["episodes"]) == 128
     assert len(res["episodes"]) == 128 and all(1 <= ep["ep_len"] <= 30 for ep in res["episodes"])

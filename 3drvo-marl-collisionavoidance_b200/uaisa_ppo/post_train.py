@@ -32,14 +32,16 @@ class post_train:
 
     # ------------------------------------------------------------------------------------------------------------
     def _policy_fn(self, policy, static_shapes: bool) -> Callable:
-        """``policy``: an ``rnn_ac`` (sampled with ``std_factor`` like load_policy/get_action, post_train.py:131-152) or a
+        """``policy``: an ``rnn_ac`` (sampled with ``std_factor`` like load_policy/get_action, post_train.py:131-152), a
+        ``FusedPolicy`` around one (fused forward: K6a features + tcgen05 heads), or a
         callable ``f(obs[A, obs_dim], count[A]) -> a_inc[A, 3]`` on CUDA tensors; a callable with ``wants_episode_info = True`` is also
         given each env's episode index and step within the episode (scripted policies)."""
-        if hasattr(policy, "step") and hasattr(policy, "pi"):
-            policy.eval()
+        if hasattr(policy, "step") and (hasattr(policy, "pi") or hasattr(policy, "ac")):     # rnn_ac, or uaisa_ppo.fused.FusedPolicy wrapping one
+            module = policy if hasattr(policy, "pi") else policy.ac
+            module.eval()
             # inside a CUDA graph the GRU path of agents with >= 2 neighbour rows needs a static capacity (checked after the run)
             cap = max(64, self.env.A // 4) if static_shapes else 0
-            self._reader = policy.pi.rnn_reader if static_shapes else None
+            self._reader = module.pi.rnn_reader if static_shapes else None
             if static_shapes and getattr(self._reader, "overflow", None) is None:
                 self._reader.overflow = torch.zeros((), dtype=torch.int64, device=self.env.device)
             return lambda obs, cnt: policy.step(obs, cnt, self.std_factor, multi_cap=cap)[0]

@@ -76,6 +76,9 @@ def test_policy_test_with_the_actor_critic():
     res = post_train(env, num_episodes=128, max_ep_len=30).policy_test(ac, policy_name="random_init", result_path=d, use_cuda_graph=True)
     res2 = post_train(env, num_episodes=128, max_ep_len=30).policy_test(ac, policy_name="random_init", use_cuda_graph=False)
     assert len(res2["episodes"]) == 128
+    from uaisa_ppo.fused import FusedPolicy
+    res3 = post_train(env, num_episodes=128, max_ep_len=30).policy_test(FusedPolicy(ac, env.device), policy_name="random_init_fused")
+    assert len(res3["episodes"]) == 128 and abs(res3["average_speed"] - res2["average_speed"]) < 0.1      # same policy through the fused forward
     assert len(res["episodes"]) == 128 and all(1 <= ep["ep_len"] <= 30 for ep in res["episodes"])
     assert open(d + "/result.txt").read().startswith("policy_name: random_init  successful rate: ")
     env.close()

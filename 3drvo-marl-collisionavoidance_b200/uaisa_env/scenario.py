@@ -110,6 +110,29 @@ class ScenarioSet:
             "building_list": self.buildings[s, : self.n_buildings[s]].tolist(),
         }
 
+    def save_scenario_dir(self, path: str, s: int = 0) -> str:
+        """Write scenario ``s`` as a directory the REFERENCE can load (``env_base.load_data``, env_base.py:26-47):
+        ``data_1.json`` plus the two occupancy grids it opens next to it (``E3d.npy`` / ``E3d_safe.npy``, only used by the
+        reference's plotting and offline planner; written as empty 1 m grids of the map's extent)."""
+        os.makedirs(path, exist_ok=True)
+        with open(os.path.join(path, "data_1.json"), "w") as f:
+            json.dump(self.to_dict(s), f)
+        shape = tuple(int(max(1, np.ceil(x))) for x in self.map_size[s])
+        for name in ("E3d.npy", "E3d_safe.npy"):
+            np.save(os.path.join(path, name), np.zeros(shape, dtype=np.int8))
+        return path
+
+    def save_drone_paths_yaml(self, path: str, s: int = 0) -> str:
+        """Start and end points of scenario ``s`` in the ``drone_paths.yaml`` schema (train/drone_paths.yaml:1-12), the input of
+        the reference's offline planner (path_planning_main.py:20-46)."""
+        import yaml
+
+        starts = [self.waypoints[s, k, 0].tolist() for k in range(self.N)]
+        ends = [self.waypoints[s, k, self.n_points[s, k] - 1].tolist() for k in range(self.N)]
+        with open(path, "w") as f:
+            yaml.safe_dump({"start_points": starts, "end_points": ends}, f)
+        return path
+
     # -- drone_paths.yaml ----------------------------------------------------------------------
     @staticmethod
     def from_drone_paths_yaml(path: str, map_size: Sequence[float] = (50, 50, 10), **kw) -> "ScenarioSet":

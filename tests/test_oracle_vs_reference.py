@@ -69,3 +69,29 @@ def test_pair_function_known_answers():
         assert close(t, ref[2], 1e-10) and close(md, ref[4], 1e-10), it
         n_full += row[6] != 0
     assert n_full > 500
+
+
+def test_reference_loads_a_scenario_directory_written_by_the_product(tmp_path):
+    """ScenarioSet.save_scenario_dir / save_drone_paths_yaml produce what the reference's own loaders read (env_base.py:26-47,
+    train/drone_paths.yaml): the unmodified reference env built from the written directory has the same drones, routes, buildings
+    and map, and its reset observation equals the oracle's."""
+    from uaisa_env.scenario import scenario_c3
+
+    scn = scenario_c3(seed=4, n_scenarios=1, n_drones=6, n_buildings=3)
+    d = scn.save_scenario_dir(str(tmp_path / "world_x"))
+    back = ScenarioSet.from_json(d)
+    assert np.array_equal(back.waypoints, scn.waypoints) and np.array_equal(back.buildings, scn.buildings) and np.array_equal(back.map_size, scn.map_size)
+    env = ref_shim.make_reference_env(d, nm=10)
+    g = env.ir_gym
+    assert g.drone_num == scn.N and [float(x) for x in g.map_size] == [float(x) for x in scn.map_size[0]]
+    assert np.allclose(np.array(g.building_list, dtype=np.float64).reshape(-1, 4), scn.buildings[0, : scn.n_buildings[0]])
+    for k, dr in enumerate(g.drone_list):
+        assert np.allclose(np.array(dr.waypoints, dtype=np.float64), scn.waypoints[0, k, : scn.n_points[0, k]])
+    obs_ref, cnt_ref = ref_shim.pad_obs(env.drone_reset(False), 10)
+    ob = oracle.OracleBatch(scn, 1, nm=10)
+    ob.reset()
+    obs, cnt, _ = ob.observe()
+    assert close(obs, obs_ref, 1e-8) and np.array_equal(cnt, cnt_ref)
+    y = scn.save_drone_paths_yaml(str(tmp_path / "drone_paths.yaml"))
+    s2 = ScenarioSet.from_drone_paths_yaml(y, map_size=scn.map_size[0])
+    assert np.array_equal(s2.waypoints[0, :, 0], scn.waypoints[0, :, 0]) and s2.N == scn.N

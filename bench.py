@@ -4,10 +4,18 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload c2|c3|c4|c5|sat]
 
 A "step" is one env step (PASS A -> move -> PASS B -> trainer auto-reset + re-observe) of every env of
-the workload; `value` = agent-steps/s over all ranks with actions and state resident in HBM, `e2e` = the
-same through uaisa_step_host with pinned HOST buffers (H2D actions + D2H outputs every step).
+the workload; `value` = agent-steps/s over all ranks with actions and state resident in HBM (T-step rollout
+launches, device-timed with CUDA events, L2 flushed before the timed region); `e2e` = the same metric through
+the reference-facing host call uaisa_step_host_sparse: HOST action in, HOST results out (reward, flags, count,
+12 self values per agent and every existing neighbour row) every step, wall-clock timed.
 Default workload = BASELINE.json configs[1]: 1024 envs x 4 drones (train/drone_paths.yaml scenario).
 Envs are independent, so ranks shard them with no data-path collective ("weak": E per GPU is fixed).
+
+Extra objects in the JSON line: `roofline` (HBM: 556 algorithmic bytes per agent-step over the kernel's launch time, DRAM traffic
+from the committed ncu capture), `roofline_flops` (SURVEY 8d's flop formula fed by the kernel's own pair counters, against the
+nominal fp64 pipe), `saturating` (the same kernel at 262144 x 4 agents: the default workload is latency-bound by size),
+`single_step_launch`, `cpu_baseline` (the C oracle with OpenMP on the host cores, bounded sample), `clocks`, `gpu_launches`.
+`--impl reference` times that CPU port alone (rank 0 only); `--workload ppo` reports PPO samples/s.
 """
 from __future__ import annotations
 

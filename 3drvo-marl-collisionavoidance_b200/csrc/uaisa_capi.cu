@@ -56,6 +56,14 @@ struct UaisaHandle {
 
 namespace {
 
+// every entry point that launches or copies selects the handle's device (and restores the caller's): a handle created on cuda:1 works
+// whatever device is current in the calling thread
+struct DeviceGuard {
+    int prev = -1; bool ok = true;
+    explicit DeviceGuard(int dev) { if (cudaGetDevice(&prev) != cudaSuccess) ok = false; else if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false; if (prev == dev) prev = -1; }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
 template <typename T>
 int dalloc(UaisaHandle *h, T **p, size_t n) {
     void *q = nullptr;
@@ -76,6 +84,7 @@ int settle(UaisaHandle *h, void *stream) {
 
 int launch(UaisaHandle *h, const Launch &L, void *stream) {
     if (!h->scenarios_set) return fail(UAISA_ESTATE, "uaisa_set_scenarios has not been called");
+    DeviceGuard g(h->device);
     { int rc_ = settle(h, stream); if (rc_) return rc_; }
     if (h->P.cl > 1) {     // thread-block cluster launch: the G CTAs of an env are co-scheduled and share the hardware cluster barrier
         cudaLaunchConfig_t cfg{};
@@ -91,12 +100,6 @@ int launch(UaisaHandle *h, const Launch &L, void *stream) {
     CK(cudaGetLastError());
     return UAISA_OK;
 }
-
-struct DeviceGuard {
-    int prev = -1; bool ok = true;
-    explicit DeviceGuard(int dev) { if (cudaGetDevice(&prev) != cudaSuccess) ok = false; else if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false; }
-    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
-};
 
 }  // namespace
 
@@ -124,16 +127,17 @@ int uaisa_create(const UaisaConfig *cfg, UaisaHandle **out) {
     if (cfg->max_buildings < 1 || cfg->n_scenarios < 1) return fail(UAISA_EINVAL, "max_buildings >= 1 and n_scenarios >= 1 required");
     if (cfg->nm < 0 || cfg->nm > UAISA_MAX_NM) return fail(UAISA_EINVAL, "0 <= nm <= 16 required");
     if ((long long)cfg->n_envs * cfg->n_drones > 0x7fffffffLL / 128) return fail(UAISA_EINVAL, "too many agents");
-    int ndev = 0;
+    int ndev = 0, cur_dev = 0;
     CK(cudaGetDeviceCount(&ndev));
     if (ndev < 1) return fail(UAISA_ECUDA, "no CUDA device");
+    CK(cudaGetDevice(&cur_dev));              // (every CUDA query that can fail early runs before the handle exists: nothing to free on that path)
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, cur_dev));
+    if (prop.major != 10) return fail(UAISA_ECUDA, "libuaisa_b200 is built for sm_100a (B200) only");
     UaisaHandle *h = new (std::nothrow) UaisaHandle();
     if (!h) return fail(UAISA_ENOMEM, "out of host memory");
     h->cfg = *cfg;
-    CK(cudaGetDevice(&h->device));
-    cudaDeviceProp prop;
-    CK(cudaGetDeviceProperties(&prop, h->device));
-    if (prop.major != 10) { delete h; return fail(UAISA_ECUDA, "libuaisa_b200 is built for sm_100a (B200) only"); }
+    h->device = cur_dev;
     const int E = cfg->n_envs, N = cfg->n_drones;
     h->A = E * N;
     Params &P = h->P;
@@ -334,6 +338,7 @@ int uaisa_autoreset(UaisaHandle *h, const uint8_t *done, const uint8_t *finish, 
 
 static int copy_state(UaisaHandle *h, const UaisaStateView *v, bool to_handle, void *stream) {
     if (!h || !v) return fail(UAISA_EINVAL, "NULL argument");
+    DeviceGuard g(h->device);
     { int rc_ = settle(h, stream); if (rc_) return rc_; }
     const Params &P = h->P;
     const size_t A = h->A;
@@ -351,6 +356,7 @@ int uaisa_set_state(UaisaHandle *h, const UaisaStateView *src, void *stream) { r
 int uaisa_cal_des(UaisaHandle *h, float *des, void *stream) {
     if (!h || !des) return fail(UAISA_EINVAL, "NULL argument");
     if (!h->scenarios_set) return fail(UAISA_ESTATE, "uaisa_set_scenarios has not been called");
+    DeviceGuard g(h->device);
     { int rc_ = settle(h, stream); if (rc_) return rc_; }
     uaisa_cal_des_kernel<<<(h->A + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(h->P, des);
     h->launches++;
@@ -361,6 +367,7 @@ int uaisa_cal_des(UaisaHandle *h, float *des, void *stream) {
 int uaisa_action_transform(UaisaHandle *h, const float *a_inc, float acceler, float *a_inc_rounded, float *action, void *stream) {
     if (!h || !a_inc || !action) return fail(UAISA_EINVAL, "NULL argument");
     if (!h->scenarios_set) return fail(UAISA_ESTATE, "uaisa_set_scenarios has not been called");
+    DeviceGuard g(h->device);
     { int rc_ = settle(h, stream); if (rc_) return rc_; }
     uaisa_action_transform_kernel<<<(h->A + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(h->P, a_inc, acceler, a_inc_rounded, action);
     h->launches++;
@@ -377,6 +384,7 @@ int uaisa_gae(const float *rew, const float *val, const uint8_t *cut, int32_t T,
 
 int uaisa_indicators(UaisaHandle *h, float *max_dev, float *extra_len, void *stream) {
     if (!h) return fail(UAISA_EINVAL, "NULL handle");
+    DeviceGuard g(h->device);
     { int rc_ = settle(h, stream); if (rc_) return rc_; }
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (max_dev) CK(cudaMemcpyAsync(max_dev, h->P.max_dev, sizeof(float) * h->A, cudaMemcpyDefault, s));
@@ -386,6 +394,7 @@ int uaisa_indicators(UaisaHandle *h, float *max_dev, float *extra_len, void *str
 
 int uaisa_get_counters(UaisaHandle *h, int64_t *in_range_pairs, int64_t *cone_evals, int64_t *nonfinite_obs, void *stream) {
     if (!h) return fail(UAISA_EINVAL, "NULL handle");
+    DeviceGuard g(h->device);
     { int rc_ = settle(h, stream); if (rc_) return rc_; }
     unsigned long long c[4] = {0, 0, 0, 0};
     cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -402,6 +411,7 @@ int64_t uaisa_launch_count(const UaisaHandle *h) { return h ? h->launches : 0; }
 
 int uaisa_get_region_clocks(UaisaHandle *h, int64_t *out16, void *stream) {
     if (!h || !out16) return fail(UAISA_EINVAL, "NULL argument");
+    DeviceGuard g(h->device);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     CK(cudaMemcpyAsync(out16, h->P.counters + 8, 16 * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
     CK(cudaMemsetAsync(h->P.counters + 8, 0, 16 * sizeof(int64_t), s));

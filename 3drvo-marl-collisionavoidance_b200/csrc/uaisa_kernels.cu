@@ -304,6 +304,7 @@ __global__ void __launch_bounds__(UAISA_LB_THREADS, (MAXT <= 128 ? UAISA_MINB128
                     break;       // plain step: nothing to re-observe (uniform over the CTA)
                 }
                 if (rs) { reset_drone(P, d, C); FILL_WP(tid); }
+                if (rs && L.mode == MODE_RESET) P.ep_len[a] = 0;      // a reset starts a new episode (multi_ppo.py:168,238,261: ep_len_list[i] = 0)
                 active = valid && sel && (L.obs || L.count || L.nbr);
                 if (S > 1 && !helper) s_act[tid] = active;             // read by my helpers after the barriers below
                 RG_MARK(RG_AUTORESET);

@@ -288,10 +288,12 @@ int uaisa_policy_features(const float *obs, int32_t A, int32_t obs_dim, const fl
 int uaisa_policy_heads(const float *feat, int32_t A, const float *const *weights /* 12 device pointers: W1a b1a W2a b2a W3a b3a W1c b1c W2c b2c W3c b3c */,
                        float *mu, float *v, void *stream) {
     if (!feat || !weights || !mu || !v || A < 1) return -1;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[64] = {};      // the attribute is per device (the launch runs on the device current in the calling thread)
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return -2;
+    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
         if (cudaFuncSetAttribute(uaisa::uaisa_policy_heads_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, uaisa::HD_SMEM) != cudaSuccess) return -2;
-        attr_set = true;
+        if (dev >= 0 && dev < 64) attr_set[dev] = true;
     }
     uaisa::HeadsParams P{};
     P.feat = feat; P.A = A; P.mu = mu; P.v = v;

@@ -5,12 +5,20 @@ What is kept from the reference (cited per line below): the per-step sequence (p
 transform -> env step -> store -> trainer reset policy -> re-observe), GAE(gamma .99, lambda .97) with last_val = 0
 and paths cut exactly where ``finish_path`` is called, NO advantage normalisation, the PPO-clip loss, the approx-KL
 early stop, grad-norm clipping at 2.0 over ALL actor-critic parameters for the policy step, separate Adam optimisers for
-pi and v that both touch the shared reader, and the hyper-parameters of train_process.py:53-63.
+pi and v that both touch the shared reader (each with its own moments for it), and the hyper-parameters of train_process.py:53-63.
 
 What changes (documented deviation, SURVEY.md section 7 "PPO semantics vs batching"): the reference loops over
-robots and does 50+50 FULL-BATCH iterations on each robot's own 300 samples; here every agent of every env feeds one
-batch that is cut into minibatches, and with world_size > 1 the gradients are all-reduced (NCCL, one flat bucket per
-iteration: 680 991 fp32 = 2.7 MB, plus the KL scalar) before the identical clip + Adam step on every rank.
+robots and does 50+50 FULL-BATCH iterations on each robot's own 300 samples, i.e. every sample is visited 50+50 times.
+Here every agent of every env feeds ONE buffer of n = T x A samples and an iteration is one minibatch of ``minibatch``
+samples taken from a fresh random permutation of the buffer (without replacement).  With the defaults (50+50 iterations of
+65 536) a sample is visited 50 * 65536 / n times per head -- 0.33 at n = 9.8 M -- so samples/s here is NOT a like-for-like
+ratio to the reference's; ``PPOConfig.passes`` = k makes the iteration count cover the buffer k times instead, and bench.py
+prints ``passes_per_sample`` next to every PPO number.
+
+Data-parallel update: parameters, gradients and Adam moments are flat fp32 buckets (``FlatParams``); with world_size > 1
+each iteration all-reduces ONE slice of the gradient bucket (NCCL over NVLink; the KL scalar rides in the same bucket), and
+the early-stop rule, clip_grad_norm_ and Adam run on the device (csrc/uaisa_train.cu) -- an iteration has no host
+synchronisation and is replayed as a CUDA graph (the all-reduce is a node of the graph).
 """
 from __future__ import annotations
 
@@ -41,9 +49,10 @@ class PPOConfig:                      # train_process.py:53-63 defaults
     target_kl: float = 0.05
     max_grad_norm: float = 2.0        # multi_ppo.py:367
     minibatch: int = 65536            # samples per gradient step (the reference's "batch" is one robot's 300 samples)
+    passes: float = 0.0               # > 0: ceil(passes * n / minibatch) iterations per head (cover the buffer `passes` times) instead of train_*_iters
     std_factor: float = 1.0
     use_cuda_graph: bool = True       # capture one rollout step (policy + transform + env step + reset policy + stores)
-    graph_update: bool = True         # capture the update iterations in CUDA graphs (single-GPU; multi-GPU runs them eagerly)
+    graph_update: bool = True         # replay the update iterations as CUDA graphs (also with world_size > 1: the all-reduce is captured)
     use_fused_policy: bool = True     # rollout forward through csrc/uaisa_policy.cu (K6a features + K6b tcgen05 heads, TF32 inputs)
     multi_cap_frac: float = 1.0 / 64  # static capacity of the multi-row GRU path in the captured step (fraction of A)
 
@@ -58,6 +67,73 @@ def gae(rew, val, cut, gamma, lam):
     return adv, ret
 
 
+class FlatAdam:
+    """Adam moments + device-side step counter of one optimiser over the flat bucket (torch.optim.Adam defaults, multi_ppo.py:115-116)."""
+
+    def __init__(self, n, lr, dev, betas=(0.9, 0.999), eps=1e-8):
+        self.m = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.v = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.step = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.lr, self.betas, self.eps = float(lr), betas, float(eps)
+
+
+class FlatParams:
+    """Every actor-critic parameter as a view into ONE fp32 bucket ``p`` (and its gradient into ``g``), laid out
+    [ v.v_net | shared rnn_reader | pi.net_out, pi.log_std | kl, loss, 2 spare ] so that the value optimiser's parameters
+    ([0, v_hi)) and the policy optimiser's ([pi_lo, n)) are each one contiguous range -- one all-reduce per iteration."""
+
+    def __init__(self, ac: rnn_ac, dev):
+        v_only = list(ac.v.v_net.parameters())
+        reader = list(ac.pi.rnn_reader.parameters())
+        pi_only = list(ac.pi.net_out.parameters()) + [ac.pi.log_std]
+        self.params = v_only + reader + pi_only
+        if {id(q) for q in self.params} != {id(q) for q in ac.parameters()} or len(self.params) != len(list(ac.parameters())):
+            raise ValueError("FlatParams does not cover the module's parameters (unexpected rnn_ac layout)")
+        n_v, n_r, n_pi = (sum(q.numel() for q in grp) for grp in (v_only, reader, pi_only))
+        self.n, self.pi_lo, self.v_hi = n_v + n_r + n_pi, n_v, n_v + n_r
+        self.p = torch.empty(self.n, dtype=torch.float32, device=dev)
+        self.g = torch.zeros(self.n + 4, dtype=torch.float32, device=dev)
+        off = 0
+        for q in self.params:
+            k = q.numel()
+            self.p[off:off + k].copy_(q.data.reshape(-1))
+            q.data = self.p[off:off + k].view_as(q)
+            q.grad = self.g[off:off + k].view_as(q)
+            off += k
+        self.L = _capi.lib()
+        self.partials = torch.zeros(int(self.L.uaisa_opt_partials_len()), dtype=torch.float64, device=dev)
+        self.dev = dev
+
+    def _s(self):
+        return C.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)
+
+    def prepare(self, opt: FlatAdam, want_norm: bool, kl=None, target_kl: float = 0.0, ctl=None):
+        p = lambda t: None if t is None else C.c_void_p(t.data_ptr())  # noqa: E731
+        rc = self.L.uaisa_opt_prepare(p(self.g), self.n, int(want_norm), p(self.partials), p(kl), float(target_kl), p(ctl), p(opt.step), self._s())
+        if rc:
+            raise _capi.UaisaError("uaisa_opt_prepare failed (%d)" % rc)
+
+    def clip_adam(self, opt: FlatAdam, r_off: int, r_cnt: int, max_norm: float, ctl=None):
+        p = lambda t: None if t is None else C.c_void_p(t.data_ptr())  # noqa: E731
+        rc = self.L.uaisa_clip_adam(p(self.p), p(self.g), p(opt.m), p(opt.v), self.n, int(r_off), int(r_cnt), p(self.partials), float(max_norm), opt.lr,
+                                    opt.betas[0], opt.betas[1], opt.eps, p(opt.step), p(ctl), self._s())
+        if rc:
+            raise _capi.UaisaError("uaisa_clip_adam failed (%d)" % rc)
+
+    def torch_state_dict(self, opt: FlatAdam, lo: int, hi: int):
+        """The optimiser's state in torch.optim.Adam's state_dict layout (multi_ppo.save_model stores one, multi_ppo.py:406-420)."""
+        state, ids, off, k = {}, [], 0, 0
+        for q in self.params:
+            n = q.numel()
+            if off >= lo and off + n <= hi:
+                state[k] = {"step": opt.step.float().cpu().reshape(()), "exp_avg": opt.m[off:off + n].view_as(q).clone(), "exp_avg_sq": opt.v[off:off + n].view_as(q).clone()}
+                ids.append(k); k += 1
+            off += n
+        group = {"lr": opt.lr, "betas": opt.betas, "eps": opt.eps, "weight_decay": 0, "amsgrad": False, "maximize": False, "foreach": None, "capturable": False,
+                 "differentiable": False, "fused": None, "params": ids}
+        return {"state": state, "param_groups": [group]}
+
+
 class PPOTrainer:
     def __init__(self, env: VecMdin, ac: Optional[rnn_ac] = None, cfg: Optional[PPOConfig] = None, seed: int = 7):
         self.env, self.cfg = env, cfg or PPOConfig()
@@ -69,10 +145,13 @@ class PPOTrainer:
             for p in self.ac.parameters():
                 dist.broadcast(p.data, 0)
             torch.manual_seed(seed + 1000 * dist.get_rank())   # same weights, different exploration noise per shard
-        cap_ok = self.cfg.graph_update and self.world == 1
-        self.pi_opt = torch.optim.Adam(self.ac.pi.parameters(), lr=self.cfg.pi_lr, capturable=cap_ok)     # multi_ppo.py:115-116
-        self.vf_opt = torch.optim.Adam(self.ac.v.parameters(), lr=self.cfg.vf_lr, capturable=cap_ok)
+        self.flat = FlatParams(self.ac, self.dev)
+        self.pi_opt = FlatAdam(self.flat.n, self.cfg.pi_lr, self.dev)        # Adam(ac.pi.parameters()): reader + net_out + log_std = [pi_lo, n)
+        self.vf_opt = FlatAdam(self.flat.n, self.cfg.vf_lr, self.dev)        # Adam(ac.v.parameters()):  v_net + reader = [0, v_hi)   (multi_ppo.py:115-116)
+        self._ctl = torch.zeros(2, dtype=torch.int32, device=self.dev)       # device side of the KL early stop: {stopped latch, iterations applied}
         self._upd = None              # captured update graphs
+        self.policy_path = "fused forward (K6a features + K6b tcgen05 heads, TF32)" if self.cfg.use_fused_policy else "torch module (cuBLAS)"
+        self.update_path = "not run yet"
         T, A, D = self.cfg.steps_per_epoch, env.A, env.obs_dim
         f32 = dict(dtype=torch.float32, device=self.dev)
         self.buf = {"obs": torch.empty((T, A, D), **f32), "count": torch.empty((T, A), dtype=torch.uint8, device=self.dev),
@@ -155,166 +234,183 @@ class PPOTrainer:
         return self.buf
 
     # ------------------------------------------------------------------------------------------------ update
-    def _allreduce_grads(self, params, extra: Optional[torch.Tensor] = None):
-        if self.world == 1:
-            return extra
-        flat = [p.grad.reshape(-1) if p.grad is not None else torch.zeros(p.numel(), device=self.dev) for p in params]
-        bucket = torch.cat(flat + ([extra.reshape(-1)] if extra is not None else []))
-        dist.all_reduce(bucket)
-        bucket /= self.world
-        off = 0
-        for p in params:
-            n = p.numel()
-            if p.grad is not None:
-                p.grad.copy_(bucket[off:off + n].view_as(p.grad))
-            off += n
-        return bucket[off:] if extra is not None else None
+    def _next_idx(self):
+        """Next minibatch of this epoch's permutation (sampling WITHOUT replacement; wraps around after a full pass)."""
+        u = self._u
+        idx = u["perm"][(u["off"] + u["ar"]) % u["n"]]
+        u["off"] += u["mb"]
+        return idx
 
-    def _build_update_graphs(self, n, mb):
-        """Capture one policy iteration (forward + loss + KL + backward + clip | optimiser step) and one value iteration
-        (forward + loss + backward + step) over static minibatch buffers (multi_ppo.py:355-376)."""
-        cfg, dev = self.cfg, self.dev
-        u = {"idx": torch.zeros(mb, dtype=torch.long, device=dev), "kl": torch.zeros((), device=dev), "loss_pi": torch.zeros((), device=dev),
-             "loss_v": torch.zeros((), device=dev), "n": n, "mb": mb, "cap": -1}   # -1: no sample has >= 2 neighbour rows (checked per epoch)
-        rd = self.ac.pi.rnn_reader
-        pi_params = list(self.ac.pi.parameters())
+    def _pi_fb(self):
+        """Forward + PPO-clip loss + approx-KL + backward of one policy iteration (multi_ppo.py:385-404) into the flat gradient bucket, then
+        ONE all-reduce of [reader | pi-only | kl, loss] across ranks.  No host round trip."""
+        cfg, F, u, W = self.cfg, self.flat, self._u, self.world
+        F.g[F.pi_lo:].zero_()                                      # pi_optimizer.zero_grad() (+ the kl / loss slots)
+        idx = self._next_idx()
+        w = self._ok[idx].float()
+        wsum = w.sum().clamp(min=1)
+        _, _, logp = self.ac.evaluate(self._obs[idx], self._cnt[idx], self._act[idx], multi_cap=u["cap"], heads="pi")
+        lo = self._logp_old[idx]
+        ratio = torch.exp(logp - lo)
+        a_ = torch.nan_to_num(self._adv[idx], 0.0, 0.0, 0.0)
+        clip_adv = torch.clamp(ratio, 1 - cfg.clip_ratio, 1 + cfg.clip_ratio) * a_
+        loss = -(torch.min(ratio * a_, clip_adv) * w).sum() / wsum                                # :393-397
+        kl = ((lo - logp) * w).sum() / wsum                                                      # :399
+        (loss / W).backward()
+        F.g[F.n].copy_(kl.detach() / W); F.g[F.n + 1].copy_(loss.detach() / W)
+        if W > 1:
+            dist.all_reduce(F.g[F.pi_lo:])                        # sum of per-rank means / W = the global mean (equal minibatches per rank)
 
-        def pi_fb():
-            u["idx"].random_(0, n)
-            idx = u["idx"]
-            w = self._ok[idx].float()
-            dist_, _, logp = self.ac.evaluate(self._obs[idx], self._cnt[idx], self._act[idx], multi_cap=u["cap"], heads="pi")
-            ratio = torch.exp(logp - self._logp_old[idx])
-            a_ = torch.nan_to_num(self._adv[idx], 0.0, 0.0, 0.0)
-            clip_adv = torch.clamp(ratio, 1 - cfg.clip_ratio, 1 + cfg.clip_ratio) * a_
-            loss = -(torch.min(ratio * a_, clip_adv) * w).sum() / w.sum().clamp(min=1)
-            u["kl"].copy_((((self._logp_old[idx] - logp) * w).sum() / w.sum().clamp(min=1)).detach())
-            u["loss_pi"].copy_(loss.detach())
-            loss.backward()
-            torch.nn.utils.clip_grad_norm_(pi_params, max_norm=cfg.max_grad_norm)
+    def _pi_iter(self):
+        """One policy iteration (multi_ppo.py:355-368): _pi_fb, then the device-side early-stop rule + clip_grad_norm_(ALL parameters, 2.0) +
+        Adam on the policy optimiser's range (csrc/uaisa_train.cu)."""
+        cfg, F = self.cfg, self.flat
+        self._pi_fb()
+        F.prepare(self.pi_opt, want_norm=True, kl=F.g[F.n:], target_kl=cfg.target_kl, ctl=self._ctl)
+        F.clip_adam(self.pi_opt, F.pi_lo, F.n - F.pi_lo, max_norm=cfg.max_grad_norm, ctl=self._ctl)   # :367 clips all ac parameters' gradients
 
-        def v_all():
-            u["idx"].random_(0, n)
-            idx = u["idx"]
-            w = self._ok[idx].float()
-            _, v, _ = self.ac.evaluate(self._obs[idx], self._cnt[idx], None, multi_cap=u["cap"], heads="v")
-            loss = (((v - torch.nan_to_num(self._ret[idx], 0.0, 0.0, 0.0)) ** 2) * w).sum() / w.sum().clamp(min=1)
-            u["loss_v"].copy_(loss.detach())
-            loss.backward()
-            self.vf_opt.step()
+    def _v_fb(self):
+        """Forward + MSE loss + backward of one value iteration (multi_ppo.py:379-383), all-reduce of [v_net | reader]."""
+        F, u, W = self.flat, self._u, self.world
+        F.g[:F.v_hi].zero_()                                       # vf_optimizer.zero_grad()
+        idx = self._next_idx()
+        w = self._ok[idx].float()
+        _, v, _ = self.ac.evaluate(self._obs[idx], self._cnt[idx], None, multi_cap=u["cap"], heads="v")
+        loss = (((v - torch.nan_to_num(self._ret[idx], 0.0, 0.0, 0.0)) ** 2) * w).sum() / w.sum().clamp(min=1)
+        (loss / W).backward()
+        u["loss_v"].copy_(loss.detach())
+        if W > 1:
+            dist.all_reduce(F.g[:F.v_hi])
 
+    def _v_iter(self):
+        """One value iteration (multi_ppo.py:371-376): _v_fb, Adam on the value optimiser's range (no clipping, no early stop)."""
+        F = self.flat
+        self._v_fb()
+        F.prepare(self.vf_opt, want_norm=False)
+        F.clip_adam(self.vf_opt, 0, F.v_hi, max_norm=0.0)
+
+    def _snapshot(self):
+        F = self.flat
+        return [t.clone() for t in (F.p, F.g, self.pi_opt.m, self.pi_opt.v, self.pi_opt.step, self.vf_opt.m, self.vf_opt.v, self.vf_opt.step, self._ctl, self._u["off"])]
+
+    def _restore(self, snap):
+        F = self.flat
+        for dst, src in zip((F.p, F.g, self.pi_opt.m, self.pi_opt.v, self.pi_opt.step, self.vf_opt.m, self.vf_opt.v, self.vf_opt.step, self._ctl, self._u["off"]), snap):
+            dst.copy_(src)
+
+    def _build_update_graphs(self):
+        """Capture one policy iteration and one value iteration as CUDA graphs (with world_size > 1 the NCCL all-reduce is a node of the
+        graph).  The warm-up iterations that precede the capture run on a snapshot: parameters, gradients, Adam moments, step counters
+        and the sampling offset are restored afterwards, so the first epoch applies exactly the counted iterations."""
+        dev = self.dev
+        snap = self._snapshot()
         s = torch.cuda.Stream(device=dev)
         s.wait_stream(torch.cuda.current_stream(dev))
-        with torch.cuda.stream(s):                       # warm-up (optimizer state, cuBLAS workspaces) on a side stream
+        with torch.cuda.stream(s):
             for _ in range(2):
-                self.pi_opt.zero_grad(set_to_none=True); pi_fb(); self.pi_opt.step()
-                self.vf_opt.zero_grad(set_to_none=True); v_all()
+                self._pi_iter(); self._v_iter()
         torch.cuda.current_stream(dev).wait_stream(s)
-        g1, g2, g3 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
-        self.pi_opt.zero_grad(set_to_none=True)
-        with torch.cuda.graph(g1):
-            pi_fb()
-        with torch.cuda.graph(g2, pool=g1.pool()):
-            self.pi_opt.step()
-        self.vf_opt.zero_grad(set_to_none=True)
-        with torch.cuda.graph(g3, pool=g1.pool()):
-            v_all()
-        u.update(g_pi_fb=g1, g_pi_step=g2, g_v=g3)
-        rd.overflow.zero_()
-        return u
-
-    def _update_graphed(self, n, mb):
-        cfg = self.cfg
-        if self._upd is None or self._upd["n"] != n or self._upd["mb"] != mb:
-            # the warm-up iterations inside the builder are real (tiny-lr) optimiser steps on this epoch's data
-            self._upd = self._build_update_graphs(n, mb)
-        u = self._upd
-        pi_iters = 0
-        for i in range(cfg.train_pi_iters):
-            u["g_pi_fb"].replay()
-            if float(u["kl"].detach()) > cfg.target_kl:  # multi_ppo.py:362-364 (the step is NOT applied)
-                break
-            u["g_pi_step"].replay()
-            pi_iters += 1
-        for i in range(cfg.train_v_iters):
-            u["g_v"].replay()
+        torch.cuda.synchronize(dev)
+        g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        kw = dict(capture_error_mode="thread_local") if self.world > 1 else {}
+        with torch.cuda.graph(g1, **kw):
+            self._pi_iter()
+        with torch.cuda.graph(g2, pool=g1.pool(), **kw):
+            self._v_iter()
+        self._restore(snap)
         rd = self.ac.pi.rnn_reader
-        if int(rd.overflow) > 0:
-            raise RuntimeError("update minibatches held more multi-row samples than the static GRU capacity (%d)" % u["cap"])
-        return pi_iters, float(u["loss_v"]), float(u["kl"])
+        if getattr(rd, "overflow", None) is not None:
+            rd.overflow.zero_()
+        return g1, g2
 
-    def update(self):
-        """PPO-clip update (multi_ppo.py:341-404) on the whole buffer."""
+    def _begin_update(self, adv=None, ret=None):
+        """GAE over the epoch's buffer (or injected advantages / returns: tests) into the static tensors every iteration reads; a fresh
+        permutation; early-stop latch cleared.  -> (n, mb)"""
         cfg, b = self.cfg, self.buf
-        adv, ret = gae(b["rew"], b["val"], b["cut"], cfg.gamma, cfg.lam)                            # finish_path, :68-77
+        if adv is None:
+            adv, ret = gae(b["rew"], b["val"], b["cut"], cfg.gamma, cfg.lam)                        # finish_path, multi_ppo.py:68-77
         T, A = b["rew"].shape
         n = T * A
-        obs, cnt = b["obs"].view(n, -1), b["count"].view(n)
-        act, logp_old, adv, ret = b["act"].view(n, 3), b["logp"].view(n), adv.view(n), ret.view(n)
-        ok = torch.isfinite(adv) & torch.isfinite(ret)        # the reference's inf/nan rewards (ir_gym.py:88) would poison Adam
-        all_params = list(self.ac.parameters())
         mb = min(cfg.minibatch, n)
-        if cfg.graph_update and self.world == 1 and not bool((cnt > 1).any()):   # multi-row samples present -> eager path below (exact, dynamic shapes)
-            rd = self.ac.pi.rnn_reader
-            if getattr(rd, "overflow", None) is None:
-                rd.overflow = torch.zeros((), dtype=torch.int64, device=self.dev)
-            rd.overflow.zero_()
-            if getattr(self, "_obs", None) is None:      # static views/buffers the captured graphs read (same storage every epoch)
-                self._obs, self._cnt, self._act, self._logp_old = obs, cnt, act, logp_old
-                self._adv, self._ret, self._ok = torch.empty_like(adv), torch.empty_like(ret), torch.empty_like(ok)
-            self._adv.copy_(adv); self._ret.copy_(ret); self._ok.copy_(ok)
-            pi_iters, lv, klv = self._update_graphed(n, mb)
-            if self.fused is not None:
-                self.fused.refresh()
-            self.stats.update(pi_iters=pi_iters, loss_v=lv, kl=klv, mean_ret=float(torch.nan_to_num(ret, 0.0, 0.0, 0.0).mean()))
-            return self.stats
-        pi_iters = 0
-        for i in range(cfg.train_pi_iters):                                                        # :355-368
-            idx = torch.randint(0, n, (mb,), device=self.dev) if mb < n else torch.arange(n, device=self.dev)
-            w = ok[idx].float()
-            self.pi_opt.zero_grad(set_to_none=True)
-            dist_, _, logp = self.ac.evaluate(obs[idx], cnt[idx], act[idx], heads="pi")
-            ratio = torch.exp(logp - logp_old[idx])
-            a_ = torch.nan_to_num(adv[idx], 0.0, 0.0, 0.0)
-            clip_adv = torch.clamp(ratio, 1 - cfg.clip_ratio, 1 + cfg.clip_ratio) * a_
-            loss_pi = -(torch.min(ratio * a_, clip_adv) * w).sum() / w.sum().clamp(min=1)          # :393-397
-            kl = ((logp_old[idx] - logp) * w).sum() / w.sum().clamp(min=1)                          # :399
-            if self.world > 1:
-                kl_all = kl.detach().clone(); dist.all_reduce(kl_all); kl_all /= self.world
-            else:
-                kl_all = kl.detach()
-            if float(kl_all) > cfg.target_kl:                                                       # :362-364
-                break
-            loss_pi.backward()
-            self._allreduce_grads(all_params)
-            torch.nn.utils.clip_grad_norm_(all_params, max_norm=cfg.max_grad_norm)                  # :367 (all ac params)
-            self.pi_opt.step()
-            pi_iters += 1
-        for i in range(cfg.train_v_iters):                                                         # :371-376
-            idx = torch.randint(0, n, (mb,), device=self.dev) if mb < n else torch.arange(n, device=self.dev)
-            w = ok[idx].float()
-            self.vf_opt.zero_grad(set_to_none=True)
-            _, v, _ = self.ac.evaluate(obs[idx], cnt[idx], None, heads="v")
-            loss_v = (((v - torch.nan_to_num(ret[idx], 0.0, 0.0, 0.0)) ** 2) * w).sum() / w.sum().clamp(min=1)   # :379-383
-            loss_v.backward()
-            self._allreduce_grads(list(self.ac.v.parameters()))
-            self.vf_opt.step()
+        if getattr(self, "_obs", None) is None:      # static views / buffers (same storage every epoch: graph-safe)
+            self._obs, self._cnt = b["obs"].view(n, -1), b["count"].view(n)
+            self._act, self._logp_old = b["act"].view(n, 3), b["logp"].view(n)
+            self._adv, self._ret = torch.empty(n, dtype=torch.float32, device=self.dev), torch.empty(n, dtype=torch.float32, device=self.dev)
+            self._ok = torch.empty(n, dtype=torch.bool, device=self.dev)
+            self._u = {"n": n, "mb": mb, "cap": -1, "perm": torch.empty(n, dtype=torch.long, device=self.dev), "off": torch.zeros((), dtype=torch.long, device=self.dev),
+                       "ar": torch.arange(mb, device=self.dev), "loss_v": torch.zeros((), device=self.dev)}
+        u = self._u
+        self._adv.copy_(adv.reshape(n)); self._ret.copy_(ret.reshape(n))
+        torch.logical_and(torch.isfinite(self._adv), torch.isfinite(self._ret), out=self._ok)   # the reference's inf/nan rewards (ir_gym.py:88) would poison Adam
+        torch.randperm(n, device=self.dev, out=u["perm"]); u["off"].zero_(); self._ctl.zero_()
+        return n, mb
+
+    def update(self, adv=None, ret=None):
+        """PPO-clip update (multi_ppo.py:341-404) on the whole buffer.
+
+        Sampling (documented deviation, see the module docstring): every iteration takes the next `minibatch` samples of a fresh random
+        permutation of the epoch's T x A samples (without replacement).  `PPOConfig.passes` > 0 makes the iteration count cover the
+        buffer that many times (ceil(passes * n / minibatch) iterations per head) instead of train_pi_iters / train_v_iters."""
+        cfg = self.cfg
+        n, mb = self._begin_update(adv, ret)
+        u = self._u
+        n_pi = cfg.train_pi_iters if cfg.passes <= 0 else int(-(-cfg.passes * n // mb))
+        n_v = cfg.train_v_iters if cfg.passes <= 0 else int(-(-cfg.passes * n // mb))
+        multi = bool((self._cnt > 1).any())          # (one host sync per epoch)
+        rd = self.ac.pi.rnn_reader
+        if getattr(rd, "overflow", None) is None:
+            rd.overflow = torch.zeros((), dtype=torch.int64, device=self.dev)
+        rd.overflow.zero_()
+        graphed = False
+        if cfg.graph_update and not multi:           # multi-row samples present -> eager iterations (exact, dynamic shapes in the reader)
+            u["cap"] = -1
+            if self._upd is None:
+                try:
+                    self._upd = self._build_update_graphs()
+                except Exception as ex:              # e.g. an NCCL build that cannot be captured: same iterations, launched eagerly
+                    self._upd = False
+                    self.stats["graph_update_error"] = repr(ex)
+                    torch.cuda.synchronize(self.dev)
+            graphed = bool(self._upd)
+        else:
+            u["cap"] = 0 if multi else -1
+        if graphed:
+            g1, g2 = self._upd
+            for _ in range(n_pi):
+                g1.replay()
+            for _ in range(n_v):
+                g2.replay()
+        else:
+            for _ in range(n_pi):
+                self._pi_iter()
+            for _ in range(n_v):
+                self._v_iter()
         if self.fused is not None:
             self.fused.refresh()          # repack the updated weights in place (addresses stay fixed: the captured rollout step stays valid)
-        self.stats.update(pi_iters=pi_iters, loss_v=float(loss_v.detach()), kl=float(kl_all), mean_ret=float(torch.nan_to_num(ret, 0.0, 0.0, 0.0).mean()))
+        ctl = self._ctl.tolist()          # the update's only host read: iterations applied / early-stop latch
+        self.update_path = ("CUDA graph per iteration" if graphed else "eager iterations") + "; torch autograd GEMMs (cuBLAS) + flat-bucket all-reduce + fused clip/Adam kernel"
+        self.stats.update(pi_iters=int(ctl[1]), early_stop=bool(ctl[0]), loss_v=float(u["loss_v"]), kl=float(self.flat.g[self.flat.n]), loss_pi=float(self.flat.g[self.flat.n + 1]),
+                          passes_pi=ctl[1] * mb / n, passes_v=n_v * mb / n, mean_ret=float(torch.nan_to_num(self._ret, 0.0, 0.0, 0.0).mean()))
         return self.stats
 
     def train_epoch(self):
+        nvtx = torch.cuda.nvtx
         t0 = time.perf_counter()
+        nvtx.range_push("uaisa.rollout")
         self.rollout()
         torch.cuda.synchronize(self.dev)
+        nvtx.range_pop()
         t1 = time.perf_counter()
+        nvtx.range_push("uaisa.update")
         self.update()
         torch.cuda.synchronize(self.dev)
+        nvtx.range_pop()
         t2 = time.perf_counter()
         self.stats.update(rollout_s=t1 - t0, update_s=t2 - t1)
         return self.stats
 
     def save_model(self, path):
         """Same container as multi_ppo.save_model (multi_ppo.py:406-420): {'model_state', 'pi_optimizer', 'vf_optimizer'}."""
-        torch.save(dict(model_state=self.ac.state_dict(), pi_optimizer=self.pi_opt.state_dict(), vf_optimizer=self.vf_opt.state_dict()), path)
+        F = self.flat
+        torch.save(dict(model_state={k: v.detach().clone() for k, v in self.ac.state_dict().items()},
+                        pi_optimizer=F.torch_state_dict(self.pi_opt, F.pi_lo, F.n), vf_optimizer=F.torch_state_dict(self.vf_opt, 0, F.v_hi)), path)

@@ -1,26 +1,37 @@
 #!/usr/bin/env python
-"""bench.py -- agent-steps/s of the batched 3-D RVO env step (BASELINE.json metric) on N B200s.
+"""bench.py -- agent-steps/s of the batched 3-D RVO env step and PPO samples/s (BASELINE.json metric) on N B200s.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload c2|c3|c4|c5|sat]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload c2|c3|c4|c5|sat|ppo]
 
-A "step" is one env step (PASS A -> move -> PASS B -> trainer auto-reset + re-observe) of every env of
-the workload; `value` = agent-steps/s over all ranks with actions and state resident in HBM (T-step rollout
-launches, device-timed with CUDA events, L2 flushed before the timed region); `e2e` = the same metric through
-the reference-facing host call uaisa_step_host_sparse: HOST action in, HOST results out (reward, flags, count,
-12 self values per agent and every existing neighbour row) every step, wall-clock timed.
-Default workload = BASELINE.json configs[1]: 1024 envs x 4 drones (train/drone_paths.yaml scenario).
-Envs are independent, so ranks shard them with no data-path collective ("weak": E per GPU is fixed).
+A "step" is one env step (PASS A -> move -> PASS B -> trainer auto-reset + re-observe) of every env of the workload.
 
-Extra objects in the JSON line: `roofline` (HBM: 556 algorithmic bytes per agent-step over the kernel's launch time, DRAM traffic
+`value` = agent-steps/s over all ranks with actions and state resident in HBM.  One *repetition* is the K steps the caller
+asked for (`--steps`), issued as uaisa_rollout launches of `steps_per_launch` steps; the timed region holds `config.repeats`
+= R repetitions, R chosen so that the region lasts >= 100 ms whatever K is.  The repetitions are captured in a CUDA graph
+(kernel nodes back to back) and the graph replays are enqueued behind a device-side gate (a spin kernel queued BEFORE the
+start event), so no host launch latency sits between the two CUDA events.  Outputs rotate through buffers whose footprint
+exceeds the 126 MB L2, and L2 is flushed before the region.  Time = max over ranks of the device-timed region.
+
+`e2e` = the same metric through the reference-facing host call uaisa_step_host_sparse: HOST action in, HOST results out
+(reward, flags, count, 12 self values per agent and every existing neighbour row) every step, wall-clock timed.
+
+Default workload = BASELINE.json configs[1] (1024 envs x 4 drones per GPU, train/drone_paths.yaml scenario).  Envs are
+independent, so ranks shard them with no data-path collective ("weak": E per GPU is fixed).  The default line also carries
+time-bounded sub-measurements under `workloads`: configs[2] (4096x16 + cylinders), configs[3] (64x256), configs[4]'s env part
+(65536x4 per GPU), the saturating size (262144x4) and PPO samples/s on configs[4] (65536 envs TOTAL over the run's ranks:
+rollout + GAE + update with the NCCL gradient all-reduce) -- so the driver's BENCH/SCALE records hold them at every N.
+
+Other objects in the JSON line: `roofline` (HBM: 556 algorithmic bytes per agent-step over the kernel's launch time; DRAM traffic
 from the committed ncu capture), `roofline_flops` (SURVEY 8d's flop formula fed by the kernel's own pair counters, against the
-nominal fp64 pipe), `saturating` (the same kernel at 262144 x 4 agents: the default workload is latency-bound by size),
-`single_step_launch`, `cpu_baseline` (the C oracle with OpenMP on the host cores, bounded sample), `clocks`, `gpu_launches`.
-`--impl reference` times that CPU port alone (rank 0 only); `--workload ppo` reports PPO samples/s.
+fp64 pipe peak measured by profiles/fma_peak), `cpu_baseline` (the C oracle with OpenMP on the host cores, bounded sample, plus the
+unmodified Python reference as measured in the build container), `clocks`, `gpu_launches`.
+`--impl reference` times the CPU port alone (rank 0 only); `--workload ppo` prints the PPO line alone.
 """
 from __future__ import annotations
 
 import argparse
 import json
+import math
 import os
 import subprocess
 import sys
@@ -40,6 +51,8 @@ from uaisa_env.scenario import scenario_c1, scenario_c3, scenario_c4  # noqa: E4
 NM = 10
 MAX_EP_LEN = 300             # train_process.py default max_ep_len
 BYTES_PER_AGENT_STEP = 156 + 40 * NM   # 556 B at nm=10
+PPO_ENVS_TOTAL = 65536       # BASELINE.json configs[4]
+MIN_REGION_MS = 120.0
 
 
 def workload(name):
@@ -57,6 +70,13 @@ def workload(name):
     raise SystemExit("unknown workload %r" % name)
 
 
+def base_config(desc, E, N):
+    """The part of `config` both arms (this one and --impl reference) print identically."""
+    return {"workload": desc, "envs_per_gpu": E, "drones_per_env": N, "nm": NM,
+            "auto_reset": "trainer policy (multi_ppo.py:221-281), max_ep_len=300",
+            "actions": "U(-1,1)^3 rounded to 2 dp"}
+
+
 def synth_actions(rng, T, A):
     """i.i.d. U(-1,1)^3 rounded to 2 dp (the trainer rounds its actions to 2 dp, multi_ppo.py:197-205)."""
     return np.round(rng.uniform(-1.0, 1.0, size=(T, A, 3)), 2).astype(np.float32)
@@ -71,7 +91,7 @@ class ClockSampler:
         self.rows = []
         self.proc = None
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
@@ -85,7 +105,7 @@ class ClockSampler:
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.12)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
@@ -105,6 +125,14 @@ class ClockSampler:
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def container_reference():
+    """The UNMODIFIED Python reference, timed in the build container by oracle/time_reference.py (it cannot travel to the GPU box)."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "r2", "container_reference.json")))
+    except Exception:
+        return None
 
 
 def cpu_baseline(scn, E, seconds=12.0, threads=0, seed=0):
@@ -142,8 +170,14 @@ def cpu_baseline(scn, E, seconds=12.0, threads=0, seed=0):
         el = time.perf_counter() - t0
         if el >= seconds or n >= 100000:
             break
-    return {"value": A * n / el, "unit": "agent-steps/s", "cores": int(cores), "kind": "port",
-            "sample": "%d steps of %d envs x %d drones in %.1f s (oracle/uaisa_oracle.c, fp64, OpenMP over envs)" % (n, E, scn.N, el)}, n, el
+    cb = {"value": A * n / el, "unit": "agent-steps/s", "cores": int(cores), "kind": "port",
+          "sample": "%d steps of %d envs x %d drones in %.1f s (oracle/uaisa_oracle.c, fp64, OpenMP over envs)" % (n, E, scn.N, el)}
+    cr = container_reference()
+    if cr and "env" in cr:
+        cb["python_reference_build_container"] = {
+            "note": "the UNMODIFIED reference env (uaisa_env/drone_envs/mdin.py:19-30) through oracle/ref_shim.py, P processes x 1 env, measured in the "
+                    "build container (it cannot travel to the GPU box): oracle/time_reference.py", "cpu": cr.get("cpu"), "cores": cr.get("cores"), "env": cr["env"]}
+    return cb, n, el
 
 
 def run_reference(args):
@@ -152,54 +186,278 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    desc, scn, E = workload(args.workload)
+    wl = args.workload if args.workload != "ppo" else "c2"
+    desc, scn, E = workload(wl)
     E_total = E * args.gpus
-    # bounded sample: each "step" is one env step of the full E_total-env workload on the host
+    # bounded sample: each "step" is one env step of (a sample of) the full E_total-env workload on the host
     E_run = min(E_total, 16384)
     budget = 20.0
     cb, n, el = cpu_baseline(scn, E_run, seconds=budget)
-    K = max(args.steps, 1)
+    cfg = base_config(desc, E, scn.N)
+    cfg.update({"repeats": 1, "l2": "n/a (CPU arm)", "state": "fp64 (reference arithmetic)", "steps_per_launch": None})
     line = {
         "impl": "reference", "metric": "agent-steps/sec (batched 3D RVO env step)", "value": cb["value"], "unit": "agent-steps/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * E_total * scn.N / cb["value"],
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": desc, "envs_total": E_total, "drones_per_env": scn.N, "nm": NM,
-                   "sampled_envs": E_run, "sampled_steps": n, "note": "steps/warmup flags bound nothing here: the sample is time-bounded (%.0f s)" % budget},
+        "config": cfg,
+        "sample": {"envs_total": E_total, "sampled_envs": E_run, "sampled_steps": n, "note": "steps/warmup flags bound nothing here: the sample is time-bounded (%.0f s)" % budget},
         "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": "agent-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    del K
+    cr = container_reference()
+    if cr and "ppo" in cr:
+        line["ppo_python_reference_build_container"] = cr["ppo"]
     print(json.dumps(line))
 
 
-def run_ppo(args):
-    """--workload ppo: PPO samples/s = E*N*steps_per_epoch / (rollout + GAE + update [+ NCCL all-reduce]) per epoch
-    (SURVEY.md section 8d).  configs[4]: 65536 envs x 4 drones over 8 GPUs = 8192 envs per GPU (weak scaling)."""
-    import torch
-    import torch.distributed as dist
+# ---------------------------------------------------------------------------------------------------------------------------
+class Dist:
+    def __init__(self):
+        import torch
+        self.torch = torch
+        self.rank = int(os.environ.get("RANK", "0")); self.world = int(os.environ.get("WORLD_SIZE", "1")); self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.init_process_group("nccl", device_id=self.dev)
+            self.dist = dist
+        else:
+            self.dist = None
+        self.sm_hz = float(torch.cuda.get_device_properties(self.dev).clock_rate) * 1e3     # kHz -> Hz (max SM clock)
 
+    def barrier(self):
+        if self.dist is not None:
+            self.dist.barrier()
+
+    def max_min(self, x):
+        """max and min over ranks of a python float"""
+        t = self.torch.tensor([x, -x], dtype=self.torch.float64, device=self.dev)
+        if self.dist is not None:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t[0].item()), -float(t[1].item())
+
+    def gate(self, ms):
+        """device-side gate: a spin kernel that keeps the stream busy for ~ms while the host enqueues what follows"""
+        self.torch.cuda._sleep(int(ms * 1e-3 * self.sm_hz))
+
+    def close(self):
+        if self.dist is not None:
+            self.dist.destroy_process_group()
+
+
+def measure_env(D, name, K, W, args, min_ms=MIN_REGION_MS, e2e=True, counters=True, single=True, clocks=False):
+    """Device-resident throughput (+ optional e2e, flop counters) of one env workload at this run's world size."""
+    torch = D.torch
+    from uaisa_env.vec_env import VecMdin
+
+    desc, scn, E = workload(name)
+    N = scn.N
+    A = E * N
+    dev = D.dev
+    env = VecMdin(scn, E, neighbors_num=NM, device=dev, threads_per_block=args.threads_per_block, neighbor_slices=args.slices)
+    env.reset()
+    auto = not args.no_autoreset
+    per_step_out = A * (env.obs_dim * 4 + 1 + NM * 4 + 4 + 3)
+    T = args.chunk or max(1, min(K, int(2e9 // per_step_out)))           # env steps per launch
+    lpr = (K + T - 1) // T                                               # launches per repetition (K steps)
+    nbuf = int(min(64, max(2, math.ceil(300e6 / (per_step_out * T)))))     # output buffers rotate: footprint > L2
+    rng = np.random.default_rng(1234 + D.rank)
+    acts = torch.from_numpy(synth_actions(rng, K, A)).to(dev)
+    outs = [{"obs": torch.empty((T, A, env.obs_dim), dtype=torch.float32, device=dev), "count": torch.empty((T, A), dtype=torch.uint8, device=dev),
+             "nbr": torch.empty((T, A, NM), dtype=torch.int32, device=dev), "reward": torch.empty((T, A), dtype=torch.float32, device=dev),
+             "done": torch.empty((T, A), dtype=torch.uint8, device=dev), "info": torch.empty((T, A), dtype=torch.uint8, device=dev),
+             "finish": torch.empty((T, A), dtype=torch.uint8, device=dev)} for _ in range(nbuf)]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)          # > 126 MB L2
+    ctr = [0]
+
+    def repetition():
+        """K env steps = lpr launches, each into the next output buffer"""
+        s = 0
+        while s < K:
+            t = min(T, K - s)
+            o = {k: v[:t] for k, v in outs[ctr[0] % nbuf].items()}
+            env.rollout(acts[s:s + t], o, auto_reset=auto, max_ep_len=MAX_EP_LEN)
+            ctr[0] += 1
+            s += t
+
+    # ---- warm-up (W untimed steps at least), then calibrate R on a short eager run
+    wsteps = 0
+    while wsteps < max(W, 3):
+        repetition(); wsteps += K
+    torch.cuda.synchronize()
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    D.gate(2.0)
+    c0.record()
+    for _ in range(3):
+        repetition()
+    c1.record(); torch.cuda.synchronize()
+    rep_ms = max(c0.elapsed_time(c1) / 3.0, 1e-3)
+    rep_ms, _ = D.max_min(rep_ms)
+    R = int(min(20000, max(1, math.ceil(min_ms / rep_ms))))
+    G = int(max(1, min(R, max(1, 192 // lpr))))                           # repetitions per captured graph (<= ~192 kernel nodes)
+    replays = (R + G - 1) // G
+    R = replays * G
+    side = torch.cuda.Stream(device=dev)
+    side.wait_stream(torch.cuda.current_stream(dev))
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(side):
+        with torch.cuda.graph(graph, stream=side):
+            for _ in range(G):
+                repetition()
+    torch.cuda.current_stream(dev).wait_stream(side)
+    graph.replay()                                                        # one untimed replay (graph upload)
+    torch.cuda.synchronize()
+    flush.fill_(1)
+    sampler = ClockSampler(D.local) if (clocks and D.rank == 0) else None
+    D.barrier()
+    torch.cuda.synchronize()
+    t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    D.gate(max(3.0, 0.03 * replays))                                      # the host enqueues every replay while the stream spins
+    t_start.record()
+    for _ in range(replays):
+        graph.replay()
+    t_end.record()
+    torch.cuda.synchronize()
+    D.barrier()
+    ms = t_start.elapsed_time(t_end)
+    ms_max, ms_min = D.max_min(ms)
+    clk = sampler.stop() if sampler else None
+    n_launch = replays * G * lpr
+    value = D.world * A * K * R / (ms_max * 1e-3)
+    avg_launch_ms = ms / n_launch
+    spl = K / lpr
+    res = {"desc": desc, "scn": scn, "E": E, "N": N, "A": A, "value": value, "ms_per_step": ms_max / (K * R), "repeats": R, "steps_per_launch": spl,
+           "launches": n_launch, "region_ms": ms_max, "region_ms_min_rank": ms_min, "avg_launch_ms": avg_launch_ms, "clocks": clk,
+           "per_gpu_hbm_gbs": BYTES_PER_AGENT_STEP * A * spl / (avg_launch_ms * 1e-3) / 1e9, "threads_per_cta": env.cfg.threads_per_block or "auto",
+           "l2": "flushed (256 MiB write) before the region; outputs rotate through %d buffers = %.0f MB (> 126 MB L2)" % (nbuf, nbuf * per_step_out * T / 1e6)}
+
+    # ---- single launch per env step (what a closed-loop caller sees), device timed, launch latency included on purpose
+    if single:
+        Ks = 200
+        o1 = {k: v[:1] for k, v in outs[0].items()}
+        for t in range(3):
+            env.rollout(acts[t % K:t % K + 1], o1, auto_reset=True, max_ep_len=MAX_EP_LEN)
+        torch.cuda.synchronize()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for t in range(Ks):
+            env.rollout(acts[t % K:t % K + 1], o1, auto_reset=True, max_ep_len=MAX_EP_LEN)
+        s1.record(); torch.cuda.synchronize()
+        single_ms = s0.elapsed_time(s1) / Ks
+        res["single_step_launch"] = {"value": D.world * A / (single_ms * 1e-3), "unit": "agent-steps/s", "ms_per_step": single_ms,
+                                     "note": "one launch per env step (closed-loop use), device-timed over %d steps, host launch latency included" % Ks}
+
+    # ---- end to end through the host C-ABI call (uaisa_step_host_sparse): every step the action comes from host memory and the step's
+    # complete result (rewards, flags, the 12 self values of every observation and every neighbour row that exists) is read on the host
+    if e2e:
+        h_acts = synth_actions(rng, 8, A)
+        tc0 = time.perf_counter()
+        for t in range(4):
+            env.step_host_sparse(h_acts[t % 8], auto_reset=True, max_ep_len=MAX_EP_LEN)
+        per_call = (time.perf_counter() - tc0) / 4
+        Ke = args.e2e_steps or int(min(2000, max(20, math.ceil(0.25 / max(per_call, 1e-6)))))
+        D.barrier()
+        torch.cuda.synchronize()
+        rows_total = 0
+        te0 = time.perf_counter()
+        for t in range(Ke):
+            r = env.step_host_sparse(h_acts[t % 8], auto_reset=True, max_ep_len=MAX_EP_LEN)
+            _ = float(r["reward"][0])                   # the result is read on the host
+            rows_total += len(r["rows"])
+        e2e_s = time.perf_counter() - te0
+        e2e_max, _ = D.max_min(e2e_s)
+        # result block written by the kernel: header (ready word + 2 timestamps), reward, self obs, flags + count, and the rows that exist
+        res["e2e"] = {"value": D.world * A * Ke / e2e_max, "unit": "agent-steps/s", "h2d_bytes_per_step": A * 3 * 4,
+                      "d2h_bytes_per_step": int(24 + A * (4 + 48 + 4) + rows_total / max(Ke, 1) * 48), "steps": Ke,
+                      "neighbour_rows_per_step": rows_total / max(Ke, 1)}
+
+    # ---- arithmetic roofline (SURVEY.md section 8d): algorithmic flops per agent-step from the kernel's own pair counters, measured on a
+    # small copy of the workload (counting costs atomics, so it is not done in the timed region)
+    if counters:
+        try:
+            cE = min(E, 1024)
+            cenv = VecMdin(scn, cE, neighbors_num=NM, device=dev, count_pairs=True)
+            cenv.reset()
+            cT = 50
+            cacts = torch.from_numpy(synth_actions(np.random.default_rng(123), cT, cenv.A)).to(dev)
+            cenv.rollout(cacts, {}, auto_reset=True, max_ep_len=MAX_EP_LEN); cenv.counters()
+            cenv.rollout(cacts, {"count": torch.empty((cT, cenv.A), dtype=torch.uint8, device=dev)}, auto_reset=True, max_ep_len=MAX_EP_LEN)
+            cc = cenv.counters()
+            rng_pp = cc["in_range_pairs"] / (cenv.A * cT); cone_pp = cc["cone_evals"] / (cenv.A * cT)
+            M_ = int(scn.n_buildings.max()) if hasattr(scn, "n_buildings") else 0
+            F = 150.0 + 2.0 * (N - 1) * 10.0 + cone_pp * 112.0 + M_ * 12.0      # F_self + range tests of both passes + full cone evaluations + cylinders
+            peak, src = fp64_peak()
+            ach = value / D.world * F / 1e12
+            res["roofline_flops"] = {"bound": "fp64 pipe", "flops_per_agent_step": F, "in_range_pairs_per_agent_step": rng_pp, "cone_evaluations_per_agent_step": cone_pp,
+                                     "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "peak_source": src,
+                                     "formula": "150 + 2 (N-1) 10 + cone_evals 112 + M 12 (SURVEY.md 8d; every add/mul/cmp/div/sqrt/transcendental counts 1)"}
+            cenv.close()
+        except Exception as ex:      # counters are diagnostics: never fail the bench line on them
+            res["roofline_flops"] = {"error": str(ex)}
+    env.close()
+    del outs, acts, flush
+    torch.cuda.empty_cache()
+    return res
+
+
+def fp64_peak():
+    """fp64 FMA peak of the B200 as measured by profiles/fma_peak (micro-kernel of independent DFMA chains); nominal otherwise."""
+    try:
+        j = json.load(open(os.path.join(ROOT, "profiles", "r2", "fma_peak.json")))
+        return float(j["fp64_tflops"]), "measured: profiles/fma_peak.py DFMA micro-kernel on B200 (profiles/r2/fma_peak.json)"
+    except Exception:
+        return 148 * 64 * 2 * 1.965e9 / 1e12, "nominal 148 SMs x 64 FMA/clk x 2 x 1.965 GHz (the step computes in fp64)"
+
+
+def hbm_peak():
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(peaks["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def roofline_obj(res):
+    peak, src = hbm_peak()
+    traffic = None
+    try:   # dram__bytes_read+write of one captured launch (profiles/traffic.json, from ncu --set full), scaled per agent-step
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        traffic = tj["dram_bytes_per_agent_step"] * res["A"] * res["steps_per_launch"]
+    except Exception:
+        pass
+    return {"bound": "hbm", "achieved": res["per_gpu_hbm_gbs"], "peak": peak, "unit": "GB/s", "frac": res["per_gpu_hbm_gbs"] / peak, "traffic": traffic,
+            "kernel": "uaisa_env_kernel", "bytes_per_agent_step": BYTES_PER_AGENT_STEP, "avg_launch_ms": res["avg_launch_ms"],
+            "avg_launch_ms_from": "timed region / launches (graph kernel nodes run back to back behind a device-side gate)", "peak_source": src}
+
+
+def sub_object(res):
+    o = {"workload": res["desc"], "value": res["value"], "unit": "agent-steps/s", "ms_per_step": res["ms_per_step"], "repeats": res["repeats"],
+         "steps_per_launch": res["steps_per_launch"], "region_ms": res["region_ms"], "roofline": roofline_obj(res)}
+    for k in ("e2e", "roofline_flops"):
+        if k in res:
+            o[k] = res[k]
+    return o
+
+
+def measure_ppo(D, args, envs_per_gpu, epochs=1, warm=1):
+    """PPO samples/s = E*N*steps_per_epoch / (rollout + GAE + update [+ NCCL all-reduce]) per epoch."""
+    torch = D.torch
     from uaisa_env.vec_env import VecMdin
     from uaisa_ppo.trainer import PPOConfig, PPOTrainer
 
-    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
     if args.tf32:
         torch.backends.cuda.matmul.allow_tf32 = True
     scn = scenario_c1()
-    E = args.ppo_envs
-    env = VecMdin(scn, E, neighbors_num=NM, device=dev)
+    env = VecMdin(scn, envs_per_gpu, neighbors_num=NM, device=D.dev)
     cfg = PPOConfig(steps_per_epoch=args.ppo_steps)
     tr = PPOTrainer(env, cfg=cfg)
-    epochs, warm = max(1, min(args.steps, 50)), max(1, min(args.warmup, 3))
     for _ in range(warm):
         tr.train_epoch()
-    if world > 1:
-        dist.barrier()
+    D.barrier()
     torch.cuda.synchronize()
-    clocks = ClockSampler(local) if rank == 0 else None
     l0 = env.launch_count
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -207,273 +465,105 @@ def run_ppo(args):
     for _ in range(epochs):
         st = tr.train_epoch(); ro += st["rollout_s"]; up += st["update_s"]
     e1.record(); torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    clk = clocks.stop() if clocks else None
-    samples = world * env.A * cfg.steps_per_epoch * epochs
-    if rank == 0:
-        line = {"metric": "PPO samples/sec (rollout + GAE + update)", "value": samples / (float(ms.item()) * 1e-3), "unit": "samples/s", "n_gpus": world,
-                "steps": epochs, "warmup": warm, "ms_per_step": float(ms.item()) / epochs, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "tf32" if args.tf32 else "f32", "data": "synthetic",
-                "config": {"workload": "configs[4]: %d envs x 4 drones per GPU, %d steps/epoch, rnn_ac 680991 params, reference PPO hyper-parameters" % (E, cfg.steps_per_epoch),
-                           "minibatch": cfg.minibatch, "pi_iters": cfg.train_pi_iters, "v_iters": cfg.train_v_iters,
-                           "policy": "torch (cuBLAS GEMMs) -- library path; fused forward is next", "rollout_frac": ro / max(ro + up, 1e-9)},
-                "gpu_launches": int(env.launch_count - l0), "clocks": clk, "stats": {k: (float(v) if not isinstance(v, (int, float)) else v) for k, v in tr.stats.items()}}
-        print(json.dumps(line))
+    D.barrier()
+    ms_max, _ = D.max_min(e0.elapsed_time(e1))
+    samples = D.world * env.A * cfg.steps_per_epoch * epochs
+    n = env.A * cfg.steps_per_epoch
+    out = {"metric": "PPO samples/sec (rollout + GAE + update)", "value": samples / (ms_max * 1e-3), "unit": "samples/s", "epochs_timed": epochs, "epochs_warmup": warm,
+           "ms_per_epoch": ms_max / epochs, "rollout_s_per_epoch": ro / epochs, "update_s_per_epoch": up / epochs, "dtype": "tf32" if args.tf32 else "f32",
+           "workload": "configs[4]: %d envs x 4 drones per GPU x %d GPUs, %d steps/epoch, rnn_ac 680991 params, reference PPO hyper-parameters" % (envs_per_gpu, D.world, cfg.steps_per_epoch),
+           "minibatch": cfg.minibatch, "pi_iters": cfg.train_pi_iters, "v_iters": cfg.train_v_iters,
+           "passes_per_sample": {"pi": tr.stats.get("pi_iters", 0) * min(cfg.minibatch, n) / n, "v": cfg.train_v_iters * min(cfg.minibatch, n) / n,
+                                 "note": "the reference makes 50+50 FULL-BATCH passes over each robot's 300 samples (multi_ppo.py:355-376); here each iteration is one "
+                                         "minibatch drawn without replacement from the whole [T x A] buffer -- samples/s is NOT a like-for-like ratio to the reference's"},
+           "policy": tr.policy_path, "update": tr.update_path, "gpu_launches_env": int(env.launch_count - l0),
+           "stats": {k: (float(v) if not isinstance(v, (int, float, str)) else v) for k, v in tr.stats.items()}}
     env.close()
-    if world > 1:
-        dist.destroy_process_group()
+    del tr
+    torch.cuda.empty_cache()
+    return out
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=2000)
-    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c2")
     ap.add_argument("--chunk", type=int, default=0, help="env steps per rollout launch (0 = auto)")
     ap.add_argument("--e2e-steps", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--no-sat", action="store_true")
+    ap.add_argument("--no-subs", action="store_true", help="skip the sub-measurements (configs[2..4], saturating size, PPO) of the default line")
+    ap.add_argument("--no-ppo", action="store_true")
     ap.add_argument("--no-autoreset", action="store_true", help="diagnostic: plain steps without the trainer reset policy")
     ap.add_argument("--threads-per-block", type=int, default=0)
     ap.add_argument("--slices", type=int, default=0, help="neighbour slices per drone (0 = auto)")
     ap.add_argument("--tf32", action="store_true")
-    ap.add_argument("--ppo-envs", type=int, default=8192)
+    ap.add_argument("--ppo-envs", type=int, default=0, help="envs per GPU for PPO (0 = 65536 / world size)")
     ap.add_argument("--ppo-steps", type=int, default=300)
+    ap.add_argument("--ppo-epochs", type=int, default=1)
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
-    if args.workload == "ppo":
-        return run_ppo(args)
 
-    import torch
-    import torch.distributed as dist
-
-    from uaisa_env.vec_env import VecMdin
-
-    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    desc, scn, E = workload(args.workload)
-    N = scn.N
-    A = E * N
+    D = Dist()
     K, W = max(args.steps, 1), max(args.warmup, 3)
-    env = VecMdin(scn, E, neighbors_num=NM, device=dev, threads_per_block=args.threads_per_block, neighbor_slices=args.slices)
-    env.reset()
-    # ---- inputs resident in HBM: K steps of actions, outputs for one chunk of steps
-    per_step_out = A * (env.obs_dim * 4 + 1 + NM * 4 + 4 + 3)
-    chunk = args.chunk or max(1, min(K, int(6e9 // per_step_out), 512))
-    rng = np.random.default_rng(1234 + rank)
-    n_act = min(K, max(chunk, 64))
-    acts = torch.from_numpy(synth_actions(rng, n_act, A)).to(dev)           # reused cyclically when K > n_act
-    out = {"obs": torch.empty((chunk, A, env.obs_dim), dtype=torch.float32, device=dev), "count": torch.empty((chunk, A), dtype=torch.uint8, device=dev),
-           "nbr": torch.empty((chunk, A, NM), dtype=torch.int32, device=dev), "reward": torch.empty((chunk, A), dtype=torch.float32, device=dev),
-           "done": torch.empty((chunk, A), dtype=torch.uint8, device=dev), "info": torch.empty((chunk, A), dtype=torch.uint8, device=dev),
-           "finish": torch.empty((chunk, A), dtype=torch.uint8, device=dev)}
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)          # > 126 MB L2
+    ppo_envs = args.ppo_envs or max(1, PPO_ENVS_TOTAL // D.world)
+    if args.workload == "ppo":
+        p = measure_ppo(D, args, ppo_envs, epochs=max(1, args.ppo_epochs), warm=1)
+        if D.rank == 0:
+            line = {"metric": p["metric"], "value": p["value"], "unit": p["unit"], "n_gpus": D.world, "steps": args.steps, "warmup": args.warmup,
+                    "ms_per_step": p["ms_per_epoch"], "higher_is_better": True, "scaling": "strong" if not args.ppo_envs else "weak", "vs_baseline": None,
+                    "dtype": p["dtype"], "data": "synthetic", "config": {"workload": p["workload"], "a_step_is": "one PPO epoch"}, "ppo": p}
+            print(json.dumps(line))
+        D.close()
+        return
 
-    def run_steps(nsteps, events=None):
-        done_steps = 0
-        while done_steps < nsteps:
-            T = min(chunk, nsteps - done_steps, n_act)
-            a0 = done_steps % n_act
-            if a0 + T > n_act:
-                T = n_act - a0
-            o = {k: v[:T] for k, v in out.items()}
-            if events is not None:
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record()
-            env.rollout(acts[a0:a0 + T], o, auto_reset=not args.no_autoreset, max_ep_len=MAX_EP_LEN)
-            if events is not None:
-                e1.record(); events.append((e0, e1, T))
-            done_steps += T
+    main_res = measure_env(D, args.workload, K, W, args, clocks=True)
+    subs = {}
+    if args.workload == "c2" and not args.no_subs:
+        for key, name in (("configs[2]", "c3"), ("configs[3]", "c4"), ("configs[4]_env", "c5"), ("saturating", "sat")):
+            r = measure_env(D, name, K, W, args, min_ms=100.0, e2e=name in ("c3", "c4"), counters=name in ("c3", "c4"), single=False)
+            subs[key] = sub_object(r)
+        if not args.no_ppo:
+            try:
+                p = measure_ppo(D, args, ppo_envs, epochs=1, warm=1)
+                p["scaling"] = "strong (65536 envs in total, split over the ranks)"
+                subs["ppo"] = p
+            except Exception as ex:      # keep the env line even if the PPO leg fails (reported, not hidden)
+                subs["ppo"] = {"error": repr(ex)}
 
-    run_steps(W)
-    torch.cuda.synchronize()
-    flush.fill_(1)
-    clocks = ClockSampler(local) if rank == 0 else None
-    l0 = env.launch_count
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    evs = []
-    t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t_start.record()
-    run_steps(K, evs)
-    t_end.record()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    ms = t_start.elapsed_time(t_end)
-    launches = env.launch_count - l0
-    tpc = env.cfg.threads_per_block
-    kern_ms = sum(e0.elapsed_time(e1) for e0, e1, _ in evs)
-    clk = clocks.stop() if clocks else None
-    tms = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-    ms_max = float(tms.item())
-    value = world * A * K / (ms_max * 1e-3)
-
-    # ---- single-launch-per-step variant (what a closed-loop policy would see), device timed
-    Ks = min(K, 200)
-    o1 = {k: v[:1] for k, v in out.items()}
-    for t in range(3):
-        env.rollout(acts[t % n_act:t % n_act + 1], o1, auto_reset=True, max_ep_len=MAX_EP_LEN)
-    torch.cuda.synchronize()
-    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    s0.record()
-    for t in range(Ks):
-        env.rollout(acts[t % n_act:t % n_act + 1], o1, auto_reset=True, max_ep_len=MAX_EP_LEN)
-    s1.record(); torch.cuda.synchronize()
-    single_ms = s0.elapsed_time(s1) / Ks
-
-    # ---- end to end through the host C-ABI call (uaisa_step_host_sparse): every step the action is produced on the
-    # host and copied H2D, and the step's complete result (rewards, flags, the 12 self values of every observation and
-    # every neighbour row that exists) is copied D2H and read on the host
-    Ke = args.e2e_steps or min(K, 400 if A <= 65536 else 40)
-    h_acts = synth_actions(rng, 8, A)
-    for t in range(3):
-        env.step_host_sparse(h_acts[t % 8], auto_reset=True, max_ep_len=MAX_EP_LEN)
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    rows_total = 0
-    te0 = time.perf_counter()
-    for t in range(Ke):
-        r = env.step_host_sparse(h_acts[t % 8], auto_reset=True, max_ep_len=MAX_EP_LEN)
-        _ = float(r["reward"][0])                   # the result is read on the host
-        rows_total += len(r["rows"])
-    e2e_s = time.perf_counter() - te0
-    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = world * A * Ke / float(te.item())
-    h2d = A * 3 * 4
-    # result block written by the kernel: header (ready word + 2 timestamps), reward, self obs, flags + count, and the rows that exist
-    d2h = int(24 + A * (4 + 48 + 4) + rows_total / max(Ke, 1) * 48)
-
-    # ---- arithmetic roofline: algorithmic flops per agent-step from the kernel's own pair counters, measured on a
-    # small copy of the workload (counting costs atomics, so it is not done in the timed region)
-    flops = None
-    try:
-        cE = min(E, 1024)
-        cenv = VecMdin(scn, cE, neighbors_num=NM, device=dev, count_pairs=True)
-        cenv.reset()
-        cT = 50
-        cacts = torch.from_numpy(synth_actions(np.random.default_rng(123), cT, cenv.A)).to(dev)
-        cenv.rollout(cacts, {}, auto_reset=True, max_ep_len=MAX_EP_LEN); cenv.counters()
-        cenv.rollout(cacts, {"count": torch.empty((cT, cenv.A), dtype=torch.uint8, device=dev)}, auto_reset=True, max_ep_len=MAX_EP_LEN)
-        cc = cenv.counters()
-        rng_pp = cc["in_range_pairs"] / (cenv.A * cT); cone_pp = cc["cone_evals"] / (cenv.A * cT)
-        M_ = int(scn.n_buildings.max()) if hasattr(scn, "n_buildings") else 0
-        F = 150.0 + 2.0 * (N - 1) * 10.0 + cone_pp * 112.0 + M_ * 12.0      # F_self + range tests of both passes + full cone evaluations + cylinders
-        fp64_peak = 148 * 64 * 2 * 1.965e9 / 1e12
-        flops = {"bound": "fp64 pipe", "flops_per_agent_step": F, "in_range_pairs_per_agent_step": rng_pp, "cone_evaluations_per_agent_step": cone_pp,
-                 "achieved": None, "peak": fp64_peak, "unit": "TFLOP/s", "peak_source": "nominal 148 SMs x 64 FMA/clk x 2 x 1.965 GHz (the step computes in fp64)",
-                 "formula": "150 + 2 (N-1) 10 + cone_evals 112 + M 12 (SURVEY.md 8d; every add/mul/cmp/div/sqrt/transcendental counts 1)"}
-        cenv.close()
-    except Exception as ex:      # counters are diagnostics: never fail the bench line on them
-        flops = {"error": str(ex)}
-
-    # ---- side measurement at the saturating size (the default workload is 4096 agents = 128 warps on 148 SMs, i.e.
-    # latency-bound by construction; SURVEY.md section 8d asks for the exact BASELINE config AND the saturating size)
-    sat = None
-    if args.workload == "c2" and not args.no_sat:
-        env.close()
-        del out, acts
-        torch.cuda.empty_cache()
-        sdesc, sscn, sE = workload("sat")
-        senv = VecMdin(sscn, sE, neighbors_num=NM, device=dev)
-        senv.reset()
-        sA, sT, sK = senv.A, 10, 40
-        sacts = torch.from_numpy(synth_actions(rng, sT, sA)).to(dev)
-        sout = {"obs": torch.empty((sT, sA, senv.obs_dim), dtype=torch.float32, device=dev), "count": torch.empty((sT, sA), dtype=torch.uint8, device=dev),
-                "nbr": torch.empty((sT, sA, NM), dtype=torch.int32, device=dev), "reward": torch.empty((sT, sA), dtype=torch.float32, device=dev),
-                "done": torch.empty((sT, sA), dtype=torch.uint8, device=dev), "info": torch.empty((sT, sA), dtype=torch.uint8, device=dev),
-                "finish": torch.empty((sT, sA), dtype=torch.uint8, device=dev)}
-        senv.rollout(sacts, sout, auto_reset=True, max_ep_len=MAX_EP_LEN)
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        q0.record()
-        for _ in range(sK // sT):
-            senv.rollout(sacts, sout, auto_reset=True, max_ep_len=MAX_EP_LEN)
-        q1.record(); torch.cuda.synchronize()
-        sms = torch.tensor([q0.elapsed_time(q1)], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(sms, op=dist.ReduceOp.MAX)
-        sval = world * sA * sK / (float(sms.item()) * 1e-3)
-        sat = {"workload": sdesc, "value": sval, "unit": "agent-steps/s", "ms_per_step": float(sms.item()) / sK, "steps": sK, "steps_per_launch": sT,
-               "per_gpu_hbm_gbs": sval / world * BYTES_PER_AGENT_STEP / 1e9}
-        senv.close()
-        env = None
-
-    if rank == 0:
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
-        peak = float(peaks.get("hbm_gbs", 6650.0))
-        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md 6.65 TB/s)"
-        avg_launch_ms = kern_ms / max(len(evs), 1)
-        steps_per_launch = K / max(len(evs), 1)
-        achieved = BYTES_PER_AGENT_STEP * A * steps_per_launch / (avg_launch_ms * 1e-3) / 1e9
-        traffic = None
-        try:   # dram__bytes_read+write of one captured launch (profiles/traffic.json, from ncu --set full), scaled per agent-step
-            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-            traffic = tj["dram_bytes_per_agent_step"] * A * steps_per_launch
-        except Exception:
-            pass
-        if sat is not None:
-            sat["roofline_frac"] = sat["per_gpu_hbm_gbs"] / peak
+    if D.rank == 0:
+        desc, scn, E, N = main_res["desc"], main_res["scn"], main_res["E"], main_res["N"]
         cb = None
         if not args.no_cpu:
             cb, _, _ = cpu_baseline(scn, min(E, 16384), seconds=12.0)
+        cfg = base_config(desc, E, N)
+        cfg.update({"repeats": main_res["repeats"], "l2": main_res["l2"], "state": "fp32 SoA in HBM, fp64 arithmetic", "steps_per_launch": main_res["steps_per_launch"],
+                    "threads_per_cta": main_res["threads_per_cta"], "timing": "R repetitions of the K steps in CUDA graphs behind a device-side gate; region %.1f ms (min over ranks %.1f ms)" % (main_res["region_ms"], main_res["region_ms_min_rank"])})
         line = {
-            "metric": "agent-steps/sec (batched 3D RVO env step)", "value": value, "unit": "agent-steps/s", "n_gpus": world,
-            "steps": K, "warmup": W, "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
-            "config": {"workload": desc, "envs_per_gpu": E, "drones_per_env": N, "nm": NM, "auto_reset": "trainer policy (multi_ppo.py:221-281), max_ep_len=300",
-                       "actions": "U(-1,1)^3 rounded to 2 dp, resident in HBM", "steps_per_launch": steps_per_launch, "threads_per_cta": tpc or "auto",
-                       "l2": "flushed (256 MiB write) before the timed region; per-launch outputs %.0f MB" % (per_step_out * steps_per_launch / 1e6),
-                       "state": "fp32 SoA in HBM, fp64 arithmetic"},
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                         "kernel": "uaisa_env_kernel", "bytes_per_agent_step": BYTES_PER_AGENT_STEP, "avg_launch_ms": avg_launch_ms,
-                         "peak_source": peak_src},
-            "single_step_launch": {"value": world * A / (single_ms * 1e-3), "unit": "agent-steps/s", "ms_per_step": single_ms,
-                                   "note": "one launch per env step (closed-loop use), device-timed over %d steps" % Ks},
-            "e2e": {"value": e2e_value, "unit": "agent-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke,
-                    "api": "uaisa_step_host_sparse: one CUDA graph per step with a single env-kernel node that writes the result block to mapped pinned host memory "
-                           "(PCIe traffic inside the kernel, host polls a ready word); the action is read from mapped pinned memory (<= 1 MiB) or copied H2D from the caller's buffer; "
-                           "result = reward/done/info/finish/count + 12 self values per agent + every existing neighbour row",
-                    "neighbour_rows_per_step": rows_total / max(Ke, 1)},
-            "gpu_launches": int(launches), "clocks": clk,
+            "metric": "agent-steps/sec (batched 3D RVO env step)", "value": main_res["value"], "unit": "agent-steps/s", "n_gpus": D.world,
+            "steps": K, "warmup": W, "ms_per_step": main_res["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": cfg, "roofline": roofline_obj(main_res),
+            "e2e": dict(main_res.get("e2e", {}), api="uaisa_step_host_sparse: one CUDA graph per step with a single env-kernel node that writes the result block to mapped pinned host memory "
+                        "(PCIe traffic inside the kernel, host polls a ready word); the action is read from mapped pinned memory (<= 1 MiB) or copied H2D from the caller's buffer; "
+                        "result = reward/done/info/finish/count + 12 self values per agent + every existing neighbour row"),
+            "gpu_launches": int(main_res["launches"]), "clocks": main_res["clocks"],
         }
-        if flops and "flops_per_agent_step" in flops:
-            flops["achieved"] = value / world * flops["flops_per_agent_step"] / 1e12
-            flops["frac"] = flops["achieved"] / flops["peak"]
-        line["roofline_flops"] = flops
+        for k in ("single_step_launch", "roofline_flops"):
+            if k in main_res:
+                line[k] = main_res[k]
         if cb:
             line["cpu_baseline"] = cb
-        if sat is not None:
-            line["saturating"] = sat
+        if subs:
+            line["workloads"] = subs
+            if "saturating" in subs:       # kept under its round-1 name too
+                s = subs["saturating"]
+                line["saturating"] = {"workload": s["workload"], "value": s["value"], "unit": "agent-steps/s", "ms_per_step": s["ms_per_step"],
+                                      "per_gpu_hbm_gbs": s["roofline"]["achieved"], "roofline_frac": s["roofline"]["frac"]}
         print(json.dumps(line))
-    if env is not None:
-        env.close()
-    if world > 1:
-        dist.destroy_process_group()
+    D.close()
 
 
 if __name__ == "__main__":

@@ -167,6 +167,22 @@ int uaisa_policy_features(const float *obs, int32_t A, int32_t obs_dim, const fl
                           const float *ln_b, float *feat, void *stream);
 int uaisa_policy_heads(const float *feat, int32_t A, const float *const *weights, float *mu, float *v, void *stream);
 
+/* ---- optimiser epilogue of the PPO update (train/policy/multi_ppo.py:355-376; SURVEY.md section 5 "fused grad-norm + clip + Adam") -----------
+ * Parameters, gradients and Adam moments are FLAT fp32 DEVICE buckets.  One update iteration ends with
+ *   uaisa_opt_prepare : partial sums of |g|^2 (fp64, fixed partition: bit-identical on every rank) when want_norm != 0, and the early-stop rule
+ *                       on the device -- `ctl[0]` latches once *kl > target_kl ("Early stopping ... break", multi_ppo.py:362-364), otherwise
+ *                       `step[0]` (the optimiser's step count) and `ctl[1]` (iterations applied) are incremented.  kl / ctl may be NULL
+ *                       (value optimiser: no early stop).
+ *   uaisa_clip_adam   : clip_grad_norm_(max_norm) over the WHOLE gradient bucket g[0..n_total) in place (multi_ppo.py:367; max_norm <= 0: off),
+ *                       then torch.optim.Adam's step (betas, eps as given, no weight decay) on p[r_off .. r_off+r_cnt); nothing is touched
+ *                       when ctl[0] is set.
+ * partials: double[uaisa_opt_partials_len()].  Asynchronous on `stream`, capturable in a CUDA graph. */
+int uaisa_opt_partials_len(void);
+int uaisa_opt_prepare(const float *g, int64_t n, int32_t want_norm, double *partials, const float *kl, float target_kl, int32_t *ctl,
+                      int32_t *step, void *stream);
+int uaisa_clip_adam(float *p, float *g, float *m, float *v, int64_t n_total, int64_t r_off, int64_t r_cnt, const double *partials,
+                    float max_norm, float lr, float beta1, float beta2, float eps, const int32_t *step, const int32_t *ctl, void *stream);
+
 /* ---- latency-optimised host round trip ------------------------------------------------------------------------
  * One env step with HOST action in / HOST results out, returned in the reference's own ragged spirit: the 12 self
  * values of every observation plus only the neighbour rows that exist (an observation is 12 + 9*max(k,1) values in

@@ -78,3 +78,154 @@ def test_ppo_epoch_runs_and_learns_something():
     ck = torch.load(f, map_location="cpu", weights_only=False)
     assert set(ck) == {"model_state", "pi_optimizer", "vf_optimizer"}
     env.close()
+
+
+def _digest(named, stride):
+    norms, samp = [], []
+    for _, t in named:
+        a = t.detach().reshape(-1).double().cpu().numpy()
+        norms.append(np.sqrt((a * a).sum())); samp.append(a[::stride])
+    return np.array(norms), np.concatenate(samp)
+
+
+def _golden_trainer(z, graph_update=False):
+    """PPOTrainer over a 1-env x 4-drone VecMdin whose buffer is overwritten with the golden's 300 samples (T = 75, A = 4)."""
+    from uaisa_env.scenario import scenario_c1
+    from uaisa_env.vec_env import VecMdin
+    from uaisa_ppo.policy import rnn_ac
+    from uaisa_ppo.trainer import PPOConfig, PPOTrainer
+
+    pi_lr, vf_lr, pi_it, v_it, tkl, _ = z["hyper"]
+    torch.manual_seed(int(z["seed"]))
+    ac = rnn_ac()                                   # CPU generator: the weights the golden was recorded with
+    env = VecMdin(scenario_c1(), 1)
+    cfg = PPOConfig(steps_per_epoch=75, pi_lr=float(pi_lr), vf_lr=float(vf_lr), train_pi_iters=int(pi_it), train_v_iters=int(v_it), target_kl=float(tkl),
+                    minibatch=300, use_fused_policy=False, use_cuda_graph=False, graph_update=graph_update)
+    tr = PPOTrainer(env, ac=ac, cfg=cfg)
+    dev = tr.dev
+    tr.buf["obs"].view(300, -1).copy_(torch.from_numpy(z["obs"]).to(dev)); tr.buf["count"].view(300).copy_(torch.from_numpy(z["count"].astype(np.uint8)).to(dev))
+    tr.buf["act"].view(300, 3).copy_(torch.from_numpy(z["act"]).to(dev)); tr.buf["logp"].view(300).copy_(torch.from_numpy(z["logp_old"]).to(dev))
+    adv, ret = torch.from_numpy(z["adv"]).to(dev), torch.from_numpy(z["ret"]).to(dev)
+    return tr, env, adv, ret
+
+
+def test_update_matches_reference_multi_ppo_golden():
+    """Losses, approx-KL, first gradients and the parameters after ONE reference update (multi_ppo.py:341-404: 3 + 3 full-batch iterations,
+    clip_grad_norm_ 2.0 -- active here, |g| = 3.85 -- and Adam) on a fixed 300-sample buffer with ragged observations, recorded from the
+    unmodified reference by oracle/gen_ppo_golden.py."""
+    import os
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "policy_ppo_update.npz"))
+    stride = int(z["hyper"][5])
+    tr, env, adv, ret = _golden_trainer(z)
+    named = [(k, dict(tr.ac.named_parameters())[str(k)]) for k in z["names"]]
+    F = tr.flat
+    tr._begin_update(adv, ret)
+    tr._u["cap"] = 0
+    tr._pi_fb()
+    assert abs(float(F.g[F.n + 1]) - float(z["loss_pi"])) <= 2e-5 * max(1.0, abs(float(z["loss_pi"])))
+    assert abs(float(F.g[F.n]) - float(z["kl"])) <= 2e-6
+    gn, gs = _digest([(k, p.grad) for k, p in named], stride)
+    assert np.allclose(gn, z["grad_pi_norm"], rtol=2e-4, atol=1e-6) and np.allclose(gs, z["grad_pi_sample"], rtol=2e-3, atol=2e-6)
+    F.g.zero_()
+    tr._v_fb()
+    assert abs(float(tr._u["loss_v"]) - float(z["loss_v"])) <= 2e-5 * abs(float(z["loss_v"]))
+    gn, gs = _digest([(k, p.grad) for k, p in named], stride)
+    assert np.allclose(gn, z["grad_v_norm"], rtol=2e-4, atol=1e-6) and np.allclose(gs, z["grad_v_sample"], rtol=2e-3, atol=2e-5)
+    F.g.zero_()
+    st = tr.update(adv, ret)
+    assert st["pi_iters"] == int(z["hyper"][2]) and not st["early_stop"]
+    pn, ps = _digest(named, stride)
+    lr = float(z["hyper"][0])
+    # Adam moves every parameter by ~lr per iteration whatever the gradient's size, so elements whose gradient is at rounding-noise level may
+    # differ by a fraction of lr between fp32 GPU and fp32 CPU arithmetic; everything else agrees to 1e-5
+    assert np.allclose(pn, z["param_norm"], rtol=2e-5)
+    d = np.abs(ps - z["param_sample"])
+    assert np.mean(d <= 0.02 * lr) >= 0.98 and d.max() <= 6.5 * lr, (np.mean(d <= 0.02 * lr), d.max())
+    with torch.no_grad():
+        _, v1, logp1 = tr.ac.evaluate(tr._obs, tr._cnt, tr._act)
+    assert np.allclose(logp1.cpu().numpy(), z["logp_after"], rtol=1e-3, atol=2e-3) and np.allclose(v1.cpu().numpy(), z["v_after"], rtol=1e-3, atol=2e-3)
+    env.close()
+
+
+def test_graphed_update_equals_eager_update():
+    """The CUDA-graph iterations and the eager iterations apply the same rule (same clip over ALL parameters, same Adam, the warm-up before
+    the capture leaves no trace): identical buffer + seed -> identical parameters."""
+    import os
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "policy_ppo_update.npz"))
+    z = dict(z)
+    z["count"] = np.minimum(z["count"], 1)            # (the graphed path is taken when no sample has >= 2 rows)
+    outs = []
+    for graphed in (False, True):
+        tr, env, adv, ret = _golden_trainer(z, graph_update=graphed)
+        torch.manual_seed(99)
+        st = tr.update(adv, ret)
+        assert ("graph" in tr.update_path.split(";")[0].lower()) == graphed, tr.update_path
+        st2 = tr.update(adv, ret)
+        outs.append((tr.flat.p.clone(), tr.pi_opt.step.item(), tr.vf_opt.step.item(), st["pi_iters"], st2["pi_iters"]))
+        env.close()
+    assert outs[0][1:] == outs[1][1:] == (6, 6, 3, 3)
+    assert torch.allclose(outs[0][0], outs[1][0], rtol=0, atol=2e-6), float((outs[0][0] - outs[1][0]).abs().max())
+
+
+def test_clip_adam_kernel_matches_torch_and_early_stop_latches():
+    """uaisa_opt_prepare + uaisa_clip_adam against clip_grad_norm_ + torch.optim.Adam on a flat bucket; the KL latch stops later iterations."""
+    import ctypes as C
+    from uaisa_env import _capi
+    L = _capi.lib()
+    dev = torch.device("cuda")
+    g0 = torch.Generator(device="cpu").manual_seed(3)
+    n, lo, cnt = 100003, 1000, 90000
+    p = torch.randn(n, generator=g0).to(dev); ref_p = p.clone().requires_grad_(True)
+    m, v = torch.zeros(n, device=dev), torch.zeros(n, device=dev)
+    step = torch.zeros(1, dtype=torch.int32, device=dev); ctl = torch.zeros(2, dtype=torch.int32, device=dev)
+    partials = torch.zeros(L.uaisa_opt_partials_len(), dtype=torch.float64, device=dev)
+    kl = torch.zeros(1, device=dev)
+    opt = torch.optim.Adam([ref_p], lr=1e-2)
+    P = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
+    s = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    for it in range(5):
+        g = (torch.randn(n, generator=g0) * (0.02 if it % 2 else 0.001)).to(dev)     # norm 6.3 (clipped) / 0.3 (not clipped)
+        ref_p.grad = g.clone(); ref_p.grad[:lo] = 0; ref_p.grad[lo + cnt:] = 0        # the reference optimiser only sees its own range ...
+        total = torch.linalg.vector_norm(g)                                            # ... but the clip norm covers the whole bucket
+        coef = torch.clamp(2.0 / (total + 1e-6), max=1.0)
+        ref_p.grad.mul_(coef)
+        before = ref_p.detach().clone()
+        opt.step()
+        ref_p.data[:lo] = before[:lo]; ref_p.data[lo + cnt:] = before[lo + cnt:]
+        assert L.uaisa_opt_prepare(P(g), n, 1, P(partials), P(kl), 0.05, P(ctl), P(step), s) == 0
+        assert L.uaisa_clip_adam(P(p), P(g), P(m), P(v), n, lo, cnt, P(partials), 2.0, 1e-2, 0.9, 0.999, 1e-8, P(step), P(ctl), s) == 0
+        assert torch.allclose(p, ref_p.detach(), rtol=1e-5, atol=2e-6), (it, float((p - ref_p.detach()).abs().max()))
+    assert step.item() == 5 and ctl.tolist() == [0, 5]
+    kl.fill_(0.06)                                   # KL above the target: latch, nothing is applied any more (multi_ppo.py:362-364)
+    snap = p.clone()
+    for it in range(2):
+        if it == 1:
+            kl.fill_(0.0)                            # the latch holds for the rest of the update
+        g = torch.randn(n, generator=g0).to(dev)
+        assert L.uaisa_opt_prepare(P(g), n, 1, P(partials), P(kl), 0.05, P(ctl), P(step), s) == 0
+        assert L.uaisa_clip_adam(P(p), P(g), P(m), P(v), n, lo, cnt, P(partials), 2.0, 1e-2, 0.9, 0.999, 1e-8, P(step), P(ctl), s) == 0
+    assert torch.equal(p, snap) and step.item() == 5 and ctl.tolist() == [1, 5]
+
+
+def test_fused_forward_logp_and_value_are_close_to_the_update_path():
+    """The rollout's logp_old / value come from the fused forward (TF32 tcgen05 heads), the update evaluates with torch in fp32: bound the
+    mismatch that feeds the PPO ratio and the approx-KL early stop (target_kl 0.05)."""
+    from uaisa_env.scenario import scenario_c3
+    from uaisa_env.vec_env import VecMdin
+    from uaisa_ppo.fused import FusedPolicy
+    from uaisa_ppo.policy import rnn_ac
+
+    env = VecMdin(scenario_c3(seed=3, n_drones=8, n_buildings=2), 256); env.reset()
+    rng = np.random.default_rng(0)
+    for _ in range(12):
+        env.step(torch.from_numpy(np.round(rng.uniform(-1, 1, (env.A, 3)), 2).astype(np.float32)).cuda())
+    torch.manual_seed(5)
+    ac = rnn_ac().cuda()
+    fp = FusedPolicy(ac, env.device)
+    torch.manual_seed(11)
+    a, v, logp = fp.step(env.obs, env.count)
+    with torch.no_grad():
+        _, v_t, logp_t = ac.evaluate(env.obs, env.count, a)
+    assert float((logp - logp_t).abs().max()) < 2e-2 and float((logp - logp_t).abs().mean()) < 3e-3
+    assert float((v - v_t).abs().max()) < 2e-2
+    env.close()

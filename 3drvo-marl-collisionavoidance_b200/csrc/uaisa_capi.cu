@@ -364,6 +364,18 @@ int uaisa_cal_des(UaisaHandle *h, float *des, void *stream) {
     return UAISA_OK;
 }
 
+int uaisa_rvo_select(UaisaHandle *h, double vmax, double acceler, float *vel_out, float *ctrl_out, void *stream) {
+    if (!h || !vel_out) return fail(UAISA_EINVAL, "NULL argument");
+    if (!h->scenarios_set) return fail(UAISA_ESTATE, "uaisa_set_scenarios has not been called");
+    if (!(vmax > 0.0) || !(acceler > 0.0) || acceler > 1.0) return fail(UAISA_EINVAL, "vmax > 0 and 0 < acceler <= 1 required (at most 5 grid points per axis)");
+    DeviceGuard g(h->device);
+    { int rc_ = settle(h, stream); if (rc_) return rc_; }
+    uaisa_rvo_select_kernel<<<(h->A + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(h->P, vmax, acceler, vel_out, ctrl_out);
+    h->launches++;
+    CK(cudaGetLastError());
+    return UAISA_OK;
+}
+
 int uaisa_action_transform(UaisaHandle *h, const float *a_inc, float acceler, float *a_inc_rounded, float *action, void *stream) {
     if (!h || !a_inc || !action) return fail(UAISA_EINVAL, "NULL argument");
     if (!h->scenarios_set) return fail(UAISA_ESTATE, "uaisa_set_scenarios has not been called");

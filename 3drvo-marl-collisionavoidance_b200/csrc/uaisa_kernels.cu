@@ -746,6 +746,115 @@ __global__ void uaisa_cal_des_kernel(const __grid_constant__ Params P, float *de
     des[3 * a] = (float)d0; des[3 * a + 1] = (float)d1; des[3 * a + 2] = (float)d2;
 }
 
+// ---- K7: classic RVO velocity selection ------------------------------------------------------------------
+// reciprocal_vel_obs.cal_vel -> config_vo -> vel_candidate -> vo_out2 -> vel_select -> penalty (uaisa_env/vel_obs/reciprocal_vel_obs.py:21-166).
+// PARITY UNPINNED: that code is dead in the reference and raises on its first call; the behaviour implemented here is the corrected restatement
+// oracle/uaisa_oracle.c:uo_rvo_select (fixes F1-F9 documented there and in DESIGN.md), against which the candidate choice is tested bit for bit.
+// One thread per drone.  The neighbours of the env are walked ONCE: per neighbour the cone (apex PAA, axis, half-angle alpha) is built and every
+// candidate velocity of the 0.5-spaced grid within +-acceler of the current velocity is classified against it (inside <=> alpha > beta) and its
+// expected collision time folded into the candidate's minimum; the selection then runs over the candidates in the reference's loop order
+// (vx outer, vz inner; first minimum wins): nearest to des_vel among the candidates outside every cone, else the one minimising
+// 1/tc_min + |v - des_vel|.  ctrl (optional): the chosen velocity in the env's own controls [acc, dyaw/90, dpitch/90] (see the oracle's note).
+constexpr int K7_MAXC = 5;                 // grid points per axis (2 * acceler / 0.5 + 1, acceler <= 1)
+__device__ __forceinline__ double k7_exp_tim(double pax, double pay, double paz, double pbx, double pby, double pbz, double vax, double vay, double vaz,
+                                             double vbx, double vby, double vbz, double ra, double rb) {       // vel_obs3D.cal_exp_tim, vel_obs3D.py:104-143
+    const double rx = pax - pbx, ry = pay - pby, rz = paz - pbz, vx = vax - vbx, vy = vay - vby, vz = vaz - vbz, r = ra + rb;
+    const double a = vx * vx + vy * vy + vz * vz, b = 2 * rx * vx + 2 * ry * vy + 2 * rz * vz, c = rx * rx + ry * ry + rz * rz - r * r;
+    if (c <= 0) return 0.0;
+    const double temp = b * b - 4 * a * c;
+    if (temp <= 0) return CUDART_INF;
+    const double sq = sqrt(temp), t1 = (-b + sq) / (2 * a), t2 = (-b - sq) / (2 * a);
+    const double t3 = t1 >= 0 ? t1 : CUDART_INF, t4 = t2 >= 0 ? t2 : CUDART_INF;
+    return t3 < t4 ? t3 : t4;
+}
+__global__ void __launch_bounds__(128) uaisa_rvo_select_kernel(const __grid_constant__ Params P, double vmax, double acceler, float *vel_out, float *ctrl_out) {
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= P.E * P.N) return;
+    const int N = P.N, env = a / N, k = a - env * N, scn = __ldg(P.env2scn + env), sn = scn * N + k;
+    const float4 py = P.pos_yaw[a], vp = P.vel_pitch[a];
+    const double pax = py.x, pay = py.y, paz = py.z, vax = vp.x, vay = vp.y, vaz = vp.z;
+    const double ra = __ldg(P.radius + sn), pra = __ldg(P.prio + sn);
+    double des0, des1, des2;
+    cal_des_vel(P, pax, pay, paz, P.wp + ((size_t)sn * P.W + (P.wpf[a] & WP_MASK)) * 3, des0, des1, des2);        // agent_state[8:11]
+    double grid[3][K7_MAXC]; int ng[3];
+    const double va3[3] = {vax, vay, vaz};
+#pragma unroll
+    for (int ax = 0; ax < 3; ax++) {                                       // vel_candidate, reciprocal_vel_obs.py:85-96 (F9: end point included)
+        const double lo = np_clip(va3[ax] - acceler, -vmax, vmax), hi = np_clip(va3[ax] + acceler, -vmax, vmax);
+        int n = 0;
+        while (n < K7_MAXC && lo + n * 0.5 <= hi + 1e-9) { grid[ax][n] = lo + n * 0.5; n++; }
+        ng[ax] = n;
+    }
+    const int nc = ng[0] * ng[1] * ng[2];
+    double tcmin[K7_MAXC * K7_MAXC * K7_MAXC];
+    unsigned inside[4] = {0u, 0u, 0u, 0u}, slow[4] = {0u, 0u, 0u, 0u};
+    for (int c = 0; c < nc; c++) {
+        const int iz = c % ng[2], iy = (c / ng[2]) % ng[1], ix = c / (ng[2] * ng[1]);
+        const double vx = grid[0][ix], vy = grid[1][iy], vz = grid[2][iz];
+        tcmin[c] = CUDART_INF;
+        if (sqrt(vx * vx + vy * vy + vz * vz) < 0.3) slow[c >> 5] |= 1u << (c & 31);                               // :98
+    }
+    for (int j = 0; j < N; j++) {
+        if (j == k) continue;                                                                                        // F8
+        const int o = env * N + j;
+        const float4 qy = P.pos_yaw[o], qv = P.vel_pitch[o];
+        const double pbx = qy.x, pby = qy.y, pbz = qy.z, vbx = qv.x, vby = qv.y, vbz = qv.z;
+        const double fx = pax - pbx, fy = pay - pby, fz = paz - pbz;
+        if (!(sqrt(np_dot3(fx, fy, fz, fx, fy, fz)) <= 10.0)) continue;                                              // preprocess :38-44
+        const double rb = __ldg(P.radius + scn * N + j), prb = __ldg(P.prio + scn * N + j);
+        const double rx = pbx - pax, ry = pby - pay, rz = pbz - paz;                                                 // get_rvo_array
+        const double nab = sqrt(np_dot3(rx, ry, rz, rx, ry, rz)), R = ra + rb;
+        const double q = R / nab;
+        const double alpha_h = (q <= 1.0) ? py_round2_hundredths(asin(q)) : py_round2_hundredths(CUDART_PI / 2);     // get_alpha (F3), in hundredths
+        const double pr = pra / (pra + prb);
+        const double PAAx = pr * (2 * pax + (vax + vbx) * 1), PAAy = pr * (2 * pay + (vay + vby) * 1), PAAz = pr * (2 * paz + (vaz + vbz) * 1);
+        for (int c = 0; c < nc; c++) {
+            if (slow[c >> 5] & (1u << (c & 31))) continue;
+            const int iz = c % ng[2], iy = (c / ng[2]) % ng[1], ix = c / (ng[2] * ng[1]);
+            const double vx = grid[0][ix], vy = grid[1][iy], vz = grid[2][iz];
+            const double Bx = (pax + vx * P.delta_t) - PAAx, By = (pay + vy * P.delta_t) - PAAy, Bz = (paz + vz * P.delta_t) - PAAz;   // vo_out2 :111-123
+            const double AB = nab * sqrt(np_dot3(Bx, By, Bz, Bx, By, Bz));
+            const double cosang = (AB != 0.0) ? np_dot3(rx, ry, rz, Bx, By, Bz) / AB : 0.0;                          // get_beta: unclamped arccos
+            const double beta_h = rint(acos(cosang) * 100.0);
+            if (alpha_h > beta_h) inside[c >> 5] |= 1u << (c & 31);                                                  // :125-126 (NaN beta -> outside)
+            const double tc = k7_exp_tim(pax, pay, paz, pbx, pby, pbz, vx, vy, vz, vbx, vby, vbz, ra, rb);             // penalty :151-153 (F6)
+            if (tc < tcmin[c]) tcmin[c] = tc;
+        }
+    }
+    bool have_out = false, have_in = false;
+    double best_out = 0, best_in = 0, ox = 0, oy = 0, oz = 0, ix_ = 0, iy_ = 0, iz_ = 0;
+    for (int c = 0; c < nc; c++) {                                                                                   // vel_select :131-138
+        if (slow[c >> 5] & (1u << (c & 31))) continue;
+        const int iz = c % ng[2], iy = (c / ng[2]) % ng[1], ix = c / (ng[2] * ng[1]);
+        const double vx = grid[0][ix], vy = grid[1][iy], vz = grid[2][iz];
+        const double dx = des0 - vx, dy = des1 - vy, dz = des2 - vz;
+        if (!(inside[c >> 5] & (1u << (c & 31)))) {
+            const double dd = sqrt(dx * dx + dy * dy + dz * dz);                                                     // distance(v, vel_des)
+            if (!have_out || dd < best_out) { have_out = true; best_out = dd; ox = vx; oy = vy; oz = vz; }
+        } else {
+            const double ex = vx - des0, ey = vy - des1, ez = vz - des2;                                             // distance(vel_des, v)
+            const double tc_inv = (tcmin[c] == 0.0) ? CUDART_INF : 1.0 / tcmin[c];
+            const double pen = 1.0 * tc_inv + sqrt(ex * ex + ey * ey + ez * ez);
+            if (!have_in || pen < best_in) { have_in = true; best_in = pen; ix_ = vx; iy_ = vy; iz_ = vz; }
+        }
+    }
+    double sx_ = vax, sy_ = vay, sz_ = vaz;                                                                          // F7
+    if (have_out) { sx_ = ox; sy_ = oy; sz_ = oz; } else if (have_in) { sx_ = ix_; sy_ = iy_; sz_ = iz_; }
+    vel_out[3 * a] = (float)sx_; vel_out[3 * a + 1] = (float)sy_; vel_out[3 * a + 2] = (float)sz_;
+    if (ctrl_out) {
+        const double sp_new = sqrt(sx_ * sx_ + sy_ * sy_ + sz_ * sz_), sp = sqrt(vax * vax + vay * vay + vaz * vaz);
+        double dyaw = 0, dpitch = 0;
+        if (sp_new > 0) {
+            const double yaw_t = atan2(sy_, sx_) * (180.0 / CUDART_PI), pitch_t = atan2(sz_, sqrt(sx_ * sx_ + sy_ * sy_)) * (180.0 / CUDART_PI);
+            double m = fmod(yaw_t - (double)py.w + 180.0, 360.0);
+            if (m != 0.0) { if (m < 0.0) m += 360.0; } else m = 0.0;                                                 // Python float %
+            dyaw = m - 180.0; dpitch = pitch_t - (double)vp.w;
+        }
+        ctrl_out[3 * a] = (float)np_clip(sp_new - sp, -1.0, 1.0); ctrl_out[3 * a + 1] = (float)np_clip(dyaw / 90.0, -1.0, 1.0);
+        ctrl_out[3 * a + 2] = (float)np_clip(dpitch / 90.0, -1.0, 1.0);
+    }
+}
+
 // ---- rollout-side kernels (SURVEY.md section 8a rows a-P2) ---------------------------------------------------
 // Trainer action transform, multi_ppo.py:197-205: a_inc = np.round(a_inc, 2) on the float32 sample,
 // abs_action = np.round(acceler * a_inc + cur_vel, 2) in float64 (cur_vel = drone.vel, read from the env state).

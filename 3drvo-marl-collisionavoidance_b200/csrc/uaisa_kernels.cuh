@@ -464,6 +464,7 @@ __device__ __forceinline__ double angle_punish(double A0, double A1, double A2, 
 template <int MAXR, int MAXT, bool WL, bool SL>
 __global__ void uaisa_env_kernel(const __grid_constant__ Params P, const __grid_constant__ Launch L);
 __global__ void uaisa_cal_des_kernel(const __grid_constant__ Params P, float *des);
+__global__ void uaisa_rvo_select_kernel(const __grid_constant__ Params P, double vmax, double acceler, float *vel_out, float *ctrl_out);
 __global__ void uaisa_action_transform_kernel(const __grid_constant__ Params P, const float *a_inc, float acceler, float *a_inc_rounded, float *action);
 __global__ void uaisa_pack_kernel(int A, int obs_dim, int nm, const float *obs, const uint8_t *count, const int *nbr, float *self_obs,
                                   void *rows_v, int *n_rows, int cap);

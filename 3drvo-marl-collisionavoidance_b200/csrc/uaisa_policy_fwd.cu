@@ -1,0 +1,468 @@
+// uaisa_policy_fwd.cu -- K6: the COMPLETE rollout forward of the reference's actor-critic (train/policy/policy_rnn_ac.py:57-69) in one kernel
+// for sm_100a:  obs row -> masked bi-GRU over the agent's neighbour rows (policy_rnn_ac.py:102-168: L = max(count, 1) steps per direction, final
+// hidden states of both directions SUMMED) -> concat the 12 self values -> LayerNorm(268) -> actor 268-256-256-3 (ReLU, ReLU, Tanh) and critic
+// 268-256-256-1.  One CTA = 128 agents (row = thread).  Nothing but the inputs and mu / v touches HBM: the GRU state, the features and the hidden
+// activations live in shared memory (as the next GEMM's A operand) and in TMEM.
+//
+//   * every GEMM runs on the 5th-generation tensor cores: tcgen05.mma kind::tf32, A (activations) and B (weights) K-major with 128-byte swizzle in
+//     shared memory, fp32 accumulators in TMEM.  GRU step: for a slice of 64 hidden units the accumulator holds [ r | z | i_n | h_n ] = 256 columns
+//     (x_t W_i^T and h W_h^T accumulate into the same r / z columns); the epilogue (tcgen05.ld) applies the gates and stores the NEW hidden state into
+//     a second TMEM region (tcgen05.st) because the old state is still the A operand of the other slices; after the 4 slices the new state is copied
+//     back into the swizzled A tile.  Steps beyond an agent's own row count leave its state untouched (mask), a CTA runs max(count) steps.
+//   * weights are PRE-SWIZZLED on the device into the exact shared-memory image of each [rows x 32] tile (uaisa_policy_pack), so a weight tile is ONE
+//     bulk copy (cp.async.bulk global -> shared, the TMA engine; SASS UBLKCP) completing on an mbarrier.  One elected thread is producer and MMA issuer:
+//     a 2-stage ring (full / empty mbarriers, tcgen05.commit releases a stage) keeps the next two tiles in flight, also across the epilogues.
+//   * the 4 epilogue warps own one TMEM lane quarter each.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "uaisa_tc.cuh"
+
+namespace uaisa {
+using namespace tc;
+
+constexpr int FW_M = 128, FW_H = 256, FW_IN = 9, FW_SELF = 12, FW_FEAT = 268;
+constexpr int FW_TILE_G = 192 * 32;                              // floats of a GRU weight tile  [r(64) | z(64) | n(64)] x 32
+constexpr int FW_TILE_W = 256 * 32;                              // floats of a heads weight tile
+constexpr int FW_OFF_GX = 0;                                     // [2 dir][4 slice]            x FW_TILE_G : weight_ih (k < 9, zero padded to 32)
+constexpr int FW_OFF_GH = FW_OFF_GX + 2 * 4 * FW_TILE_G;         // [2 dir][4 slice][8 chunk]   x FW_TILE_G : weight_hh
+constexpr int FW_OFF_W1 = FW_OFF_GH + 2 * 4 * 8 * FW_TILE_G;     // [9 chunk][2 head]           x FW_TILE_W : layer 1, K order [h(256) | self(12) | 0(20)]
+constexpr int FW_OFF_W2 = FW_OFF_W1 + 18 * FW_TILE_W;            // [2 head][8 chunk]           x FW_TILE_W : layer 2
+constexpr int FW_OFF_GB = FW_OFF_W2 + 16 * FW_TILE_W;            // [2 dir][4][256]: b_ir+b_hr, b_iz+b_hz, b_in, b_hn
+constexpr int FW_OFF_LN = FW_OFF_GB + 2 * 4 * 256;               // ln weight[288], ln bias[288] in the kernel's K order
+constexpr int FW_OFF_B1 = FW_OFF_LN + 2 * 288;                   // [2 head][256]
+constexpr int FW_OFF_B2 = FW_OFF_B1 + 512;                       // [2 head][256]
+constexpr int FW_OFF_W3 = FW_OFF_B2 + 512;                       // [4][256]: actor rows 0..2, critic row 3
+constexpr int FW_OFF_B3 = FW_OFF_W3 + 1024;                      // [4]
+constexpr int FW_PACK_FLOATS = FW_OFF_B3 + 16;
+
+constexpr int FW_A_CHUNK = FW_M * 128;                           // bytes of one A chunk [128 rows x 32 fp32]
+constexpr int FW_STAGE = 256 * 128;                              // bytes of one B stage
+constexpr int FW_SMEM = 1024 + 9 * FW_A_CHUNK + 2 * FW_STAGE + 128;
+
+struct PackSrc {       // raw module parameters (device pointers), torch layouts
+    const float *w_ih[2], *w_hh[2], *b_ih[2], *b_hh[2];          // GRU, [768][9] / [768][256] / [768] (gate order r, z, n); [1] = reverse direction
+    const float *ln_w, *ln_b;                                    // [268] in [self | h] order
+    const float *W1[2], *b1[2], *W2[2], *b2[2], *W3[2], *b3[2];  // [0] actor, [1] critic; W1 [256][268], W2 [256][256], W3 [3 | 1][256]
+};
+
+// (row, k) of float index w inside a swizzled tile image (inverse of tc::swz_float_index)
+__device__ __forceinline__ void unswz(int w, int &row, int &k) {
+    const int grp = w >> 8, rem = w & 255, r7 = rem >> 5, pos = rem & 31;
+    row = grp * 8 + r7; k = (((pos >> 2) ^ r7) << 2) | (pos & 3);
+}
+
+__global__ void uaisa_policy_pack_kernel(const __grid_constant__ PackSrc S, float *__restrict__ wp) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= FW_PACK_FLOATS) return;
+    float val = 0.0f;
+    if (i < FW_OFF_GH) {                                           // GRU input weights
+        const int t = i / FW_TILE_G, dir = t >> 2, slice = t & 3;
+        int row, k; unswz(i - t * FW_TILE_G, row, k);
+        const int gate = row >> 6, u = slice * 64 + (row & 63);
+        if (k < FW_IN) val = S.w_ih[dir][(gate * FW_H + u) * FW_IN + k];
+    } else if (i < FW_OFF_W1) {                                    // GRU recurrent weights
+        const int t = (i - FW_OFF_GH) / FW_TILE_G, dir = t >> 5, slice = (t >> 3) & 3, chunk = t & 7;
+        int row, k; unswz((i - FW_OFF_GH) - t * FW_TILE_G, row, k);
+        const int gate = row >> 6, u = slice * 64 + (row & 63);
+        val = S.w_hh[dir][(size_t)(gate * FW_H + u) * FW_H + chunk * 32 + k];
+    } else if (i < FW_OFF_W2) {                                    // heads layer 1, K re-ordered to [h | self | pad]
+        const int t = (i - FW_OFF_W1) / FW_TILE_W, chunk = t >> 1, head = t & 1;
+        int n, k; unswz((i - FW_OFF_W1) - t * FW_TILE_W, n, k);
+        const int q = chunk * 32 + k;
+        if (q < FW_H) val = S.W1[head][n * FW_FEAT + FW_SELF + q];
+        else if (q < FW_FEAT) val = S.W1[head][n * FW_FEAT + (q - FW_H)];
+    } else if (i < FW_OFF_GB) {                                    // heads layer 2
+        const int t = (i - FW_OFF_W2) / FW_TILE_W, head = t >> 3, chunk = t & 7;
+        int n, k; unswz((i - FW_OFF_W2) - t * FW_TILE_W, n, k);
+        val = S.W2[head][n * FW_H + chunk * 32 + k];
+    } else if (i < FW_OFF_LN) {
+        const int j = i - FW_OFF_GB, dir = j >> 10, which = (j >> 8) & 3, u = j & 255;
+        val = which == 0 ? S.b_ih[dir][u] + S.b_hh[dir][u] : which == 1 ? S.b_ih[dir][256 + u] + S.b_hh[dir][256 + u] : which == 2 ? S.b_ih[dir][512 + u] : S.b_hh[dir][512 + u];
+    } else if (i < FW_OFF_B1) {
+        const int j = i - FW_OFF_LN, q = j % 288;
+        const float *src = j < 288 ? S.ln_w : S.ln_b;
+        if (q < FW_H) val = src[FW_SELF + q]; else if (q < FW_FEAT) val = src[q - FW_H];
+    } else if (i < FW_OFF_B2) { const int j = i - FW_OFF_B1; val = S.b1[j >> 8][j & 255]; }
+    else if (i < FW_OFF_W3) { const int j = i - FW_OFF_B2; val = S.b2[j >> 8][j & 255]; }
+    else if (i < FW_OFF_B3) { const int j = i - FW_OFF_W3, r = j >> 8; val = r < 3 ? S.W3[0][r * 256 + (j & 255)] : S.W3[1][j & 255]; }
+    else { const int j = i - FW_OFF_B3; if (j < 3) val = S.b3[0][j]; else if (j == 3) val = S.b3[1][0]; }
+    wp[i] = val;
+}
+
+struct FwdParams {
+    const float *obs; const uint8_t *count; int A, obs_dim, nm;
+    const float *wp;              // packed weights (uaisa_policy_pack)
+    float *mu, *v;                // [A][3], [A]
+    float *feat_out;              // optional [A][268] LayerNorm output in the module's [self | h] order (tests)
+    float4 *scratch;              // [ceil(A/128)][64][128] float4: forward-direction state of CTAs that run the recurrence
+    int *stats;                   // optional: [0] += CTAs that ran the recurrence, [1] = max steps seen
+};
+
+// order in which the weight tiles are consumed (thread 0's prefetcher walks it independently of the consumer)
+struct TileIter {
+    int lmax, phase, dir, step, slice, sub, lin;
+    __device__ __forceinline__ void init(int lmax_) { lmax = lmax_; phase = 0; dir = step = slice = sub = lin = 0; }
+    __device__ __forceinline__ bool next(const float *wp, const float *&addr, uint32_t &bytes) {
+        if (phase == 0) {
+            bytes = FW_TILE_G * 4;
+            if (lmax == 1) {                                       // step 0 only: per slice, both directions
+                addr = wp + FW_OFF_GX + ((lin & 1) * 4 + (lin >> 1)) * FW_TILE_G;
+                if (++lin == 8) { phase = 1; lin = 0; }
+                return true;
+            }
+            addr = sub == 0 ? wp + FW_OFF_GX + (dir * 4 + slice) * FW_TILE_G : wp + FW_OFF_GH + ((dir * 4 + slice) * 8 + (sub - 1)) * FW_TILE_G;
+            const int nsub = step > 0 ? 9 : 1;
+            if (++sub == nsub) { sub = 0; if (++slice == 4) { slice = 0; if (++step == lmax) { step = 0; if (++dir == 2) { phase = 1; lin = 0; } } } }
+            return true;
+        }
+        if (phase == 1) { addr = wp + FW_OFF_W1 + lin * FW_TILE_W; bytes = FW_TILE_W * 4; if (++lin == 18) { phase = 2; lin = 0; } return true; }
+        if (phase == 2) { addr = wp + FW_OFF_W2 + lin * FW_TILE_W; bytes = FW_TILE_W * 4; if (++lin == 16) phase = 3; return true; }
+        return false;
+    }
+};
+
+__device__ __forceinline__ float sigm(float x) { return 1.0f / (1.0f + __expf(-x)); }
+__device__ __forceinline__ float tanh_fast(float x) { return 1.0f - 2.0f / (1.0f + __expf(2.0f * x)); }
+
+__global__ void __launch_bounds__(128, 1) uaisa_policy_forward_kernel(const __grid_constant__ FwdParams P) {
+    extern __shared__ unsigned char fw_smem_raw[];
+    char *base = reinterpret_cast<char *>((reinterpret_cast<uintptr_t>(fw_smem_raw) + 1023) & ~uintptr_t(1023));   // SWIZZLE_128B needs 1024-byte alignment
+    char *As = base;                                   // 9 chunks [128 x 32] fp32: chunks 0..7 = GRU state / features h / hidden activations, chunk 8 = x_t / self
+    char *Bs = As + 9 * FW_A_CHUNK;                    // 2 stages
+    uint64_t *bars = reinterpret_cast<uint64_t *>(Bs + 2 * FW_STAGE);   // full[2], empty[2], done
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 5);
+    int *s_lmax = reinterpret_cast<int *>(tmem_slot + 1);
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int a0 = blockIdx.x * FW_M, a = a0 + tid;
+    const bool ok = a < P.A;
+    const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[2]), done = smem_u32(&bars[4]);
+
+    if (warp == 0) tmem_alloc(smem_u32(tmem_slot), 512u);
+    if (tid == 0) {
+        for (int i = 0; i < 5; i++) mbar_init(smem_u32(&bars[i]), 1);
+        mbar_init_fence();
+        *s_lmax = 1;
+    }
+    __syncthreads();
+    int cnt = ok ? (int)P.count[a] : 0;
+    cnt = cnt < P.nm ? cnt : P.nm;
+    const int c_eff = cnt > 1 ? cnt : 1;               // an agent without neighbours feeds ONE zero row (ir_gym.py:211-212)
+    {
+        const int wmax = __reduce_max_sync(0xffffffffu, c_eff);
+        if ((tid & 31) == 0) atomicMax(s_lmax, wmax);
+    }
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tmem = *tmem_slot;
+    const int lmax = *s_lmax;
+    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    const float *orow = P.obs + (size_t)(ok ? a : 0) * P.obs_dim;
+    const float *wp = P.wp;
+    uint32_t dpar = 0;                                 // parity of the `done` barrier (all threads)
+    // ---- thread 0: weight-tile ring
+    TileIter it; it.init(lmax);
+    int pf = 0, cs = 0; uint32_t fpar[2] = {0u, 0u}, epar[2] = {0u, 0u};
+    auto topup = [&]() {
+        while (pf < cs + 2) {
+            const float *addr; uint32_t bytes;
+            if (!it.next(wp, addr, bytes)) break;
+            const int s = pf & 1;
+            if (pf >= 2) { mbar_wait(empty0 + 8 * s, epar[s]); epar[s] ^= 1u; }      // the MMAs that read this stage have completed
+            mbar_expect_tx(full0 + 8 * s, bytes);
+            bulk_g2s(smem_u32(Bs + s * FW_STAGE), addr, bytes, full0 + 8 * s);
+            pf++;
+        }
+    };
+    auto acquire = [&]() -> int {
+        topup();
+        const int s = cs & 1;
+        mbar_wait(full0 + 8 * s, fpar[s]); fpar[s] ^= 1u;
+        fence_after_sync();
+        return s;
+    };
+    auto release = [&](int s) { umma_commit(empty0 + 8 * s); cs++; };
+    auto mma = [&](int a_chunk, uint32_t b_saddr, int ksteps, uint32_t idesc, uint32_t tmem_d, bool acc) {
+        const uint32_t sa = smem_u32(As + a_chunk * FW_A_CHUNK);
+        for (int k = 0; k < ksteps; k++) umma_tf32(tmem_d, umma_desc(sa + k * 32), umma_desc(b_saddr + k * 32), idesc, (acc || k > 0) ? 1u : 0u);   // UMMA K = 8 tf32 = 32 bytes
+    };
+    auto group_done = [&]() { umma_commit(done); topup(); };               // (thread 0) accumulators ready -> `done`; next tiles stream during the epilogue
+    auto wait_done = [&]() { mbar_wait(done, dpar); dpar ^= 1u; __syncwarp(); fence_after_sync(); };   // (warp 0 reconverges after thread 0's issue block: tcgen05.ld / st are .aligned)
+    auto sync_smem_to_mma = [&]() { fence_proxy_async(); fence_before_sync(); __syncthreads(); fence_after_sync(); };
+    constexpr uint32_t ID192 = umma_idesc_tf32(128, 192), ID128 = umma_idesc_tf32(128, 128), ID64 = umma_idesc_tf32(128, 64), ID256 = umma_idesc_tf32(128, 256);
+
+    // x_t of my row into the A tile of chunk 8 (9 values, zero padded to 32)
+    auto write_x = [&](int idx, bool valid) {
+        float x[12];
+#pragma unroll
+        for (int k = 0; k < 12; k++) x[k] = 0.0f;
+        if (valid && ok && idx < P.nm) {
+#pragma unroll
+            for (int k = 0; k < FW_IN; k++) x[k] = __ldg(orow + FW_SELF + FW_IN * idx + k);
+        }
+        char *t8 = As + 8 * FW_A_CHUNK;
+        *swz(t8, tid, 0) = make_float4(x[0], x[1], x[2], x[3]); *swz(t8, tid, 1) = make_float4(x[4], x[5], x[6], x[7]);
+        *swz(t8, tid, 2) = make_float4(x[8], 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int k4 = 3; k4 < 8; k4++) *swz(t8, tid, k4) = make_float4(0.f, 0.f, 0.f, 0.f);
+    };
+    // gates of 16 hidden units [u0, u0+16) of direction `dir` from the accumulator columns at `dcol`: out = (1 - z) n + z h_old
+    auto gates16 = [&](int dir, int u0, uint32_t dcol, int jb, bool has_h, const float *h_old, float *out) {
+        float r[16], z[16], gi[16], gh[16];
+        tmem_ld16(tmem + lane_base + dcol + jb * 16, r);
+        tmem_ld16(tmem + lane_base + dcol + 64 + jb * 16, z);
+        tmem_ld16(tmem + lane_base + dcol + 128 + jb * 16, gi);
+        if (has_h) tmem_ld16(tmem + lane_base + dcol + 192 + jb * 16, gh);
+        const float *gb = wp + FW_OFF_GB + dir * 1024 + u0;
+#pragma unroll
+        for (int q = 0; q < 16; q++) {
+            const float rr = sigm(r[q] + __ldg(gb + q)), zz = sigm(z[q] + __ldg(gb + 256 + q));
+            const float hn = (has_h ? gh[q] : 0.0f) + __ldg(gb + 768 + q);
+            const float nn = tanh_fast(gi[q] + __ldg(gb + 512 + q) + rr * hn);
+            out[q] = (1.0f - zz) * nn + zz * (has_h ? h_old[q] : 0.0f);
+        }
+    };
+    auto read_h16 = [&](int u0, float *h) {            // my row's state, units [u0, u0+16), from the swizzled A tile
+        char *t = As + (u0 >> 5) * FW_A_CHUNK;
+#pragma unroll
+        for (int q4 = 0; q4 < 4; q4++) { const float4 f = *swz(t, tid, ((u0 & 31) >> 2) + q4); h[4 * q4] = f.x; h[4 * q4 + 1] = f.y; h[4 * q4 + 2] = f.z; h[4 * q4 + 3] = f.w; }
+    };
+    auto write_h16 = [&](int u0, const float *h) {
+        char *t = As + (u0 >> 5) * FW_A_CHUNK;
+#pragma unroll
+        for (int q4 = 0; q4 < 4; q4++) *swz(t, tid, ((u0 & 31) >> 2) + q4) = make_float4(h[4 * q4], h[4 * q4 + 1], h[4 * q4 + 2], h[4 * q4 + 3]);
+    };
+
+    // =========================================================================================== bi-GRU reader
+    if (lmax == 1) {
+        // every agent of the tile has <= 1 row: one step from h = 0 in both directions (no recurrent GEMM); both directions' accumulators side by side
+        write_x(0, true);
+        sync_smem_to_mma();
+        for (int slice = 0; slice < 4; slice++) {
+            if (tid == 0) {
+                int s = acquire(); mma(8, smem_u32(Bs + s * FW_STAGE), 2, ID192, tmem + 0, false); release(s);
+                s = acquire(); mma(8, smem_u32(Bs + s * FW_STAGE), 2, ID192, tmem + 256, false); release(s);
+                group_done();
+            }
+            wait_done();
+#pragma unroll 1
+            for (int jb = 0; jb < 4; jb++) {
+                const int u0 = slice * 64 + jb * 16;
+                float hf[16], hb[16];
+                gates16(0, u0, 0, jb, false, nullptr, hf);
+                gates16(1, u0, 256, jb, false, nullptr, hb);
+#pragma unroll
+                for (int q = 0; q < 16; q++) hf[q] += hb[q];
+                write_h16(u0, hf);
+            }
+            fence_before_sync();
+            __syncthreads();                           // the accumulators are free for the next slice
+            fence_after_sync();
+        }
+    } else {
+        float4 *stash = P.scratch + (size_t)blockIdx.x * 64 * FW_M;
+        for (int dir = 0; dir < 2; dir++) {
+            for (int step = 0; step < lmax; step++) {
+                const bool active = step < c_eff;
+                // ---- this step's x tile; (from step 1 on) the previous step's new state, TMEM -> A tile
+                write_x(dir == 0 ? step : c_eff - 1 - step, active);
+                if (step > 0) {
+#pragma unroll 1
+                    for (int ub = 0; ub < 16; ub++) { float h[16]; tmem_ld16(tmem + lane_base + 256 + ub * 16, h); write_h16(ub * 16, h); }
+                }
+                sync_smem_to_mma();
+                for (int slice = 0; slice < 4; slice++) {
+                    if (tid == 0) {
+                        int s = acquire(); mma(8, smem_u32(Bs + s * FW_STAGE), 2, ID192, tmem + 0, false); release(s);           // x_t W_i^T -> [r | z | i_n]
+                        if (step > 0) {
+                            for (int c = 0; c < 8; c++) {                                                                         // h W_h^T
+                                s = acquire();
+                                const uint32_t b = smem_u32(Bs + s * FW_STAGE);
+                                mma(c, b, 4, ID128, tmem + 0, true);                                                              //   -> += [r | z]
+                                mma(c, b + 128 * 128, 4, ID64, tmem + 192, c > 0);                                                //   -> h_n (kept apart: n = tanh(i_n + r * h_n))
+                                release(s);
+                            }
+                        }
+                        group_done();
+                    }
+                    wait_done();
+#pragma unroll 1
+                    for (int jb = 0; jb < 4; jb++) {
+                        const int u0 = slice * 64 + jb * 16;
+                        float ho[16], hn[16];
+                        if (step > 0) read_h16(u0, ho);
+                        gates16(dir, u0, 0, jb, step > 0, ho, hn);
+                        if (!active) {
+#pragma unroll
+                            for (int q = 0; q < 16; q++) hn[q] = ho[q];      // (step > 0 here: every row is active at step 0)
+                        }
+                        tmem_st16(tmem + lane_base + 256 + u0, hn);
+                    }
+                    tmem_st_wait();
+                    fence_before_sync();
+                    __syncthreads();                   // accumulator columns free; the new state of this slice is in TMEM
+                    fence_after_sync();
+                }
+            }
+            // ---- final state of this direction (TMEM columns 256..511)
+            if (dir == 0) {
+#pragma unroll 1
+                for (int ub = 0; ub < 16; ub++) {
+                    float h[16]; tmem_ld16(tmem + lane_base + 256 + ub * 16, h);
+#pragma unroll
+                    for (int q4 = 0; q4 < 4; q4++) stash[(size_t)(ub * 4 + q4) * FW_M + tid] = make_float4(h[4 * q4], h[4 * q4 + 1], h[4 * q4 + 2], h[4 * q4 + 3]);
+                }
+            } else {
+#pragma unroll 1
+                for (int ub = 0; ub < 16; ub++) {
+                    float h[16]; tmem_ld16(tmem + lane_base + 256 + ub * 16, h);
+#pragma unroll
+                    for (int q4 = 0; q4 < 4; q4++) { const float4 f = stash[(size_t)(ub * 4 + q4) * FW_M + tid]; h[4 * q4] += f.x; h[4 * q4 + 1] += f.y; h[4 * q4 + 2] += f.z; h[4 * q4 + 3] += f.w; }
+                    write_h16(ub * 16, h);             // h_fwd + h_bwd (policy_rnn_ac.py:122, 163)
+                }
+            }
+            fence_before_sync();
+            __syncthreads();
+            fence_after_sync();
+        }
+        if (P.stats && tid == 0) { atomicAdd(P.stats, 1); atomicMax(P.stats + 1, lmax); }
+    }
+
+    // =========================================================================================== concat + LayerNorm(268), in place in the A tile
+    {
+        float self[FW_SELF];
+#pragma unroll
+        for (int k = 0; k < FW_SELF; k++) self[k] = ok ? __ldg(orow + k) : 0.0f;
+        float sum = 0.0f;
+#pragma unroll
+        for (int k = 0; k < FW_SELF; k++) sum += self[k];
+#pragma unroll 1
+        for (int ub = 0; ub < 16; ub++) { float h[16]; read_h16(ub * 16, h);
+#pragma unroll
+            for (int q = 0; q < 16; q++) sum += h[q]; }
+        const float mean = sum * (1.0f / FW_FEAT);
+        float ss = 0.0f;
+#pragma unroll
+        for (int k = 0; k < FW_SELF; k++) ss += (self[k] - mean) * (self[k] - mean);
+#pragma unroll 1
+        for (int ub = 0; ub < 16; ub++) { float h[16]; read_h16(ub * 16, h);
+#pragma unroll
+            for (int q = 0; q < 16; q++) ss += (h[q] - mean) * (h[q] - mean); }
+        const float rstd = rsqrtf(ss * (1.0f / FW_FEAT) + 1e-5f);                  // nn.LayerNorm: biased variance, eps 1e-5
+        const float *lw = wp + FW_OFF_LN, *lb = lw + 288;
+        float *fo = (P.feat_out && ok) ? P.feat_out + (size_t)a * FW_FEAT : nullptr;
+#pragma unroll 1
+        for (int ub = 0; ub < 16; ub++) {
+            float h[16]; read_h16(ub * 16, h);
+#pragma unroll
+            for (int q = 0; q < 16; q++) h[q] = (h[q] - mean) * rstd * __ldg(lw + ub * 16 + q) + __ldg(lb + ub * 16 + q);
+            write_h16(ub * 16, h);
+            if (fo) {
+#pragma unroll
+                for (int q = 0; q < 16; q++) fo[FW_SELF + ub * 16 + q] = h[q];
+            }
+        }
+        float sn[FW_SELF];
+#pragma unroll
+        for (int k = 0; k < FW_SELF; k++) { sn[k] = (self[k] - mean) * rstd * __ldg(lw + 256 + k) + __ldg(lb + 256 + k); if (fo) fo[k] = sn[k]; }
+        char *t8 = As + 8 * FW_A_CHUNK;
+        *swz(t8, tid, 0) = make_float4(sn[0], sn[1], sn[2], sn[3]); *swz(t8, tid, 1) = make_float4(sn[4], sn[5], sn[6], sn[7]);
+        *swz(t8, tid, 2) = make_float4(sn[8], sn[9], sn[10], sn[11]);
+#pragma unroll
+        for (int k4 = 3; k4 < 8; k4++) *swz(t8, tid, k4) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    sync_smem_to_mma();
+
+    // =========================================================================================== actor / critic heads
+    if (tid == 0) {                                    // layer 1 of both heads from the same A (features): columns 0..255 actor, 256..511 critic
+        for (int c = 0; c < 9; c++) {
+            const int ks = c < 8 ? 4 : 2;              // chunk 8 holds the 12 self values: K = 16 covers them
+            int s = acquire(); mma(c, smem_u32(Bs + s * FW_STAGE), ks, ID256, tmem + 0, c > 0); release(s);
+            s = acquire(); mma(c, smem_u32(Bs + s * FW_STAGE), ks, ID256, tmem + 256, c > 0); release(s);
+        }
+        group_done();
+    }
+    wait_done();
+    for (int head = 0; head < 2; head++) {
+        // epilogue of layer 1: bias + ReLU -> A chunks 0..7 (the features are no longer needed)
+        const float *b1 = wp + FW_OFF_B1 + head * 256;
+#pragma unroll 1
+        for (int ub = 0; ub < 16; ub++) {
+            float h[16]; tmem_ld16(tmem + lane_base + (head ? 256 : 0) + ub * 16, h);
+#pragma unroll
+            for (int q = 0; q < 16; q++) h[q] = fmaxf(h[q] + __ldg(b1 + ub * 16 + q), 0.0f);
+            write_h16(ub * 16, h);
+        }
+        sync_smem_to_mma();
+        if (tid == 0) {                                // layer 2 -> columns 0..255 (the critic's layer-1 accumulator still sits in 256..511)
+            for (int c = 0; c < 8; c++) { const int s = acquire(); mma(c, smem_u32(Bs + s * FW_STAGE), 4, ID256, tmem + 0, c > 0); release(s); }
+            group_done();
+        }
+        wait_done();
+        // epilogue of layer 2: bias + ReLU, then the tiny output layer on the CUDA cores (row = thread)
+        const float *b2 = wp + FW_OFF_B2 + head * 256, *w3 = wp + FW_OFF_W3 + (head ? 768 : 0);
+        float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f;
+#pragma unroll 1
+        for (int ub = 0; ub < 16; ub++) {
+            float h[16]; tmem_ld16(tmem + lane_base + ub * 16, h);
+#pragma unroll
+            for (int q = 0; q < 16; q++) {
+                const float hq = fmaxf(h[q] + __ldg(b2 + ub * 16 + q), 0.0f);
+                acc0 = fmaf(hq, __ldg(w3 + ub * 16 + q), acc0);
+                if (!head) { acc1 = fmaf(hq, __ldg(w3 + 256 + ub * 16 + q), acc1); acc2 = fmaf(hq, __ldg(w3 + 512 + ub * 16 + q), acc2); }
+            }
+        }
+        if (ok) {
+            const float *b3 = wp + FW_OFF_B3;
+            if (!head) { P.mu[(size_t)a * 3] = tanhf(acc0 + __ldg(b3)); P.mu[(size_t)a * 3 + 1] = tanhf(acc1 + __ldg(b3 + 1)); P.mu[(size_t)a * 3 + 2] = tanhf(acc2 + __ldg(b3 + 2)); }
+            else P.v[a] = acc0 + __ldg(b3 + 3);
+        }
+        fence_before_sync();
+        __syncthreads();                               // columns 0..255 fully read before the next head's layer 2 overwrites them
+        fence_after_sync();
+    }
+    if (warp == 0) tmem_dealloc(tmem, 512u);
+}
+
+}  // namespace uaisa
+
+// ---- C ABI -----------------------------------------------------------------------------------------------------------
+extern "C" {
+
+int uaisa_policy_pack_floats(void) { return uaisa::FW_PACK_FLOATS; }
+
+// params: 22 DEVICE pointers in the order  weight_ih_l0, weight_hh_l0, bias_ih_l0, bias_hh_l0, the same four of the reverse direction, ln.weight, ln.bias,
+// actor W1 b1 W2 b2 W3 b3, critic W1 b1 W2 b2 W3 b3  (torch layouts, fp32, contiguous).  wpack: [uaisa_policy_pack_floats()] floats, 16-byte aligned.
+int uaisa_policy_pack(const float *const *params, float *wpack, void *stream) {
+    if (!params || !wpack || (reinterpret_cast<uintptr_t>(wpack) & 15)) return -1;
+    for (int i = 0; i < 22; i++) if (!params[i]) return -1;
+    uaisa::PackSrc S{};
+    for (int d = 0; d < 2; d++) { S.w_ih[d] = params[4 * d]; S.w_hh[d] = params[4 * d + 1]; S.b_ih[d] = params[4 * d + 2]; S.b_hh[d] = params[4 * d + 3]; }
+    S.ln_w = params[8]; S.ln_b = params[9];
+    for (int h = 0; h < 2; h++) {
+        S.W1[h] = params[10 + 6 * h]; S.b1[h] = params[11 + 6 * h]; S.W2[h] = params[12 + 6 * h];
+        S.b2[h] = params[13 + 6 * h]; S.W3[h] = params[14 + 6 * h]; S.b3[h] = params[15 + 6 * h];
+    }
+    uaisa::uaisa_policy_pack_kernel<<<(uaisa::FW_PACK_FLOATS + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(S, wpack);
+    return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+
+int uaisa_policy_forward(const float *obs, const uint8_t *count, int32_t A, int32_t obs_dim, const float *wpack, float *mu, float *v, float *feat_out,
+                         void *scratch, int32_t *stats, void *stream) {
+    if (!obs || !count || !wpack || !mu || !v || !scratch || A < 1 || obs_dim < uaisa::FW_SELF || (obs_dim - uaisa::FW_SELF) % uaisa::FW_IN) return -1;
+    static bool attr_set[64] = {};      // per device
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return -2;
+    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+        if (cudaFuncSetAttribute(uaisa::uaisa_policy_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, uaisa::FW_SMEM) != cudaSuccess) return -2;
+        if (dev >= 0 && dev < 64) attr_set[dev] = true;
+    }
+    uaisa::FwdParams P{};
+    P.obs = obs; P.count = count; P.A = A; P.obs_dim = obs_dim; P.nm = (obs_dim - uaisa::FW_SELF) / uaisa::FW_IN;
+    P.wp = wpack; P.mu = mu; P.v = v; P.feat_out = feat_out; P.scratch = static_cast<float4 *>(scratch); P.stats = stats;
+    uaisa::uaisa_policy_forward_kernel<<<(A + uaisa::FW_M - 1) / uaisa::FW_M, 128, uaisa::FW_SMEM, static_cast<cudaStream_t>(stream)>>>(P);
+    return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+
+}  // extern "C"

@@ -158,6 +158,14 @@ class VecMdin:
         _capi.check(self.L.uaisa_cal_des(self.h, _ptr(des), self._stream()))
         return des
 
+    def rvo_select(self, vmax: float = 2.0, acceler: float = 0.5, controls: bool = True):
+        """K7, classic RVO velocity selection (reciprocal_vel_obs.cal_vel, reciprocal_vel_obs.py:21-166; corrected restatement, see include/uaisa_b200.h)
+        -> (selected velocity [A,3], the same as env controls [A,3] to feed :meth:`step`, or None)."""
+        vel = torch.empty((self.A, 3), dtype=torch.float32, device=self.device)
+        ctrl = torch.empty((self.A, 3), dtype=torch.float32, device=self.device) if controls else None
+        _capi.check(self.L.uaisa_rvo_select(self.h, float(vmax), float(acceler), _ptr(vel), _ptr(ctrl), self._stream()))
+        return vel, ctrl
+
     def action_transform(self, a_inc: torch.Tensor, action_out: Optional[torch.Tensor] = None, a_inc_rounded: Optional[torch.Tensor] = None):
         """multi_ppo.py:197-205 on device: returns (action[A,3] for step(), rounded increment[A,3] for the buffer)."""
         if action_out is None:

@@ -1,6 +1,10 @@
-"""Fused rollout forward of rnn_ac through libuaisa_b200.so (csrc/uaisa_policy.cu): K6a features (bi-GRU step 0 + LayerNorm,
-CUDA cores) and K6b heads (actor / critic MLPs on tcgen05 tensor cores, TF32 inputs, fp32 accumulation in TMEM).
-Inference only (the update goes through torch autograd); call :meth:`refresh` after every optimiser step."""
+"""Fused rollout forward of rnn_ac through libuaisa_b200.so.
+
+Default (``kernel="full"``, csrc/uaisa_policy_fwd.cu): ONE kernel for the whole ``ac.step`` forward (policy_rnn_ac.py:57-69) -- the masked bi-GRU
+recurrence over each agent's neighbour rows, LayerNorm(268) and both MLP heads on the tensor cores (tcgen05.mma kind::tf32, fp32 accumulation in
+TMEM), weights fetched as pre-swizzled tiles by the bulk-copy engine.  No torch branch, no host synchronisation, any count in 0..nm.
+``kernel="split"`` keeps the round-1 pair (csrc/uaisa_policy.cu: K6a step-0 features on the CUDA cores + K6b tcgen05 heads, agents with >= 2 rows
+patched from the torch reader) for A/B runs.  Inference only (the update goes through torch autograd); call :meth:`refresh` after every optimiser step."""
 from __future__ import annotations
 
 import ctypes as C
@@ -14,15 +18,44 @@ KPAD = 288
 
 
 class FusedPolicy:
-    def __init__(self, ac: rnn_ac, device):
+    def __init__(self, ac: rnn_ac, device, kernel: str = "full"):
         self.ac, self.dev = ac, torch.device(device)
         self.L = _capi.lib()
+        if kernel not in ("full", "split"):
+            raise ValueError("kernel must be 'full' or 'split'")
+        self.kernel = kernel
+        rd = ac.pi.rnn_reader
+        shapes = (tuple(rd.rnn_net.weight_ih_l0.shape), tuple(rd.rnn_net.weight_hh_l0.shape), tuple(rd.ln.weight.shape), tuple(ac.pi.net_out[0].weight.shape),
+                  tuple(ac.pi.net_out[2].weight.shape), tuple(ac.pi.net_out[4].weight.shape), tuple(ac.v.v_net[0].weight.shape), tuple(ac.v.v_net[4].weight.shape))
+        if shapes != ((768, 9), (768, 256), (268,), (256, 268), (256, 256), (3, 256), (256, 268), (1, 256)) or not rd.rnn_net.bidirectional:
+            raise ValueError("the fused kernels are built for the reference architecture (bi-GRU 9->256, LayerNorm 268, MLPs 268-256-256-3/1); got %r" % (shapes,))
+        self._scratch = None
+        self.stats = torch.zeros(2, dtype=torch.int32, device=self.dev)      # {tiles that ran the recurrence, max steps}
         self.refresh()
+
+    def _params22(self):
+        g, ln, pi, v = self.ac.pi.rnn_reader.rnn_net, self.ac.pi.rnn_reader.ln, self.ac.pi.net_out, self.ac.v.v_net
+        ps = [g.weight_ih_l0, g.weight_hh_l0, g.bias_ih_l0, g.bias_hh_l0, g.weight_ih_l0_reverse, g.weight_hh_l0_reverse, g.bias_ih_l0_reverse, g.bias_hh_l0_reverse,
+              ln.weight, ln.bias, pi[0].weight, pi[0].bias, pi[2].weight, pi[2].bias, pi[4].weight, pi[4].bias,
+              v[0].weight, v[0].bias, v[2].weight, v[2].bias, v[4].weight, v[4].bias]
+        for t in ps:
+            if t.dtype != torch.float32 or not t.is_contiguous() or t.device != self.dev:
+                raise ValueError("fused forward needs contiguous fp32 parameters on %s" % self.dev)
+        return ps
 
     @torch.no_grad()
     def refresh(self):
         """(Re)pack the module's weights into the kernels' layouts.  Buffers are allocated once and updated in place, so
         device addresses stay fixed (a CUDA graph that captured the fused forward stays valid)."""
+        if self.kernel == "full":
+            if getattr(self, "wpack", None) is None:
+                self.wpack = torch.zeros(int(self.L.uaisa_policy_pack_floats()), dtype=torch.float32, device=self.dev)
+            ps = self._params22()
+            ptrs = (C.c_void_p * 22)(*[t.data_ptr() for t in ps])
+            rc = self.L.uaisa_policy_pack(ptrs, C.c_void_p(self.wpack.data_ptr()), self._stream())
+            if rc:
+                raise _capi.UaisaError("uaisa_policy_pack failed (%d)" % rc)
+            return
         g, ln = self.ac.pi.rnn_reader.rnn_net, self.ac.pi.rnn_reader.ln
         H = 256
         wih, bias = [], []
@@ -47,6 +80,26 @@ class FusedPolicy:
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)
 
+    # ---- kernel = "full" ---------------------------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def forward(self, obs: torch.Tensor, count: torch.Tensor, want_features: bool = False):
+        """-> (mu [A,3], v [A], LayerNorm features [A,268] or None)"""
+        A = obs.shape[0]
+        if obs.dtype != torch.float32 or not obs.is_contiguous() or count.dtype != torch.uint8 or count.numel() != A:
+            raise ValueError("obs must be contiguous float32 [A, 12+9nm] and count uint8 [A]")
+        tiles = (A + 127) // 128
+        if self._scratch is None or self._scratch.numel() < tiles * 128 * 256:
+            self._scratch = torch.empty(tiles * 128 * 256, dtype=torch.float32, device=self.dev)
+        mu = torch.empty((A, 3), dtype=torch.float32, device=self.dev)
+        v = torch.empty(A, dtype=torch.float32, device=self.dev)
+        feat = torch.empty((A, 268), dtype=torch.float32, device=self.dev) if want_features else None
+        p = lambda t: None if t is None else C.c_void_p(t.data_ptr())  # noqa: E731
+        rc = self.L.uaisa_policy_forward(p(obs), p(count), A, obs.shape[1], p(self.wpack), p(mu), p(v), p(feat), p(self._scratch), p(self.stats), self._stream())
+        if rc:
+            raise _capi.UaisaError("uaisa_policy_forward failed (%d)" % rc)
+        return mu, v, feat
+
+    # ---- kernel = "split" --------------------------------------------------------------------------------------------------------------
     @torch.no_grad()
     def features(self, obs: torch.Tensor) -> torch.Tensor:
         A = obs.shape[0]
@@ -67,9 +120,7 @@ class FusedPolicy:
             raise _capi.UaisaError("uaisa_policy_heads failed (%d)" % rc)
         return mu, v
 
-    @torch.no_grad()
-    def step(self, obs, count, std_factor=1.0, multi_cap=0):
-        """Drop-in for rnn_ac.step: (a, v, logp).  Agents with >= 2 neighbour rows get their feature row from the torch reader."""
+    def _split_mu_v(self, obs, count, multi_cap):
         feat = self.features(obs)
         rd = self.ac.pi.rnn_reader
         if multi_cap < 0:
@@ -87,7 +138,16 @@ class FusedPolicy:
             idx = torch.nonzero(count > 1).squeeze(-1)
             if idx.numel():
                 feat[idx, :268] = rd(obs[idx], count[idx])
-        mu, v = self.heads(feat)
+        return self.heads(feat)
+
+    # -----------------------------------------------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def step(self, obs, count, std_factor=1.0, multi_cap=0):
+        """Drop-in for rnn_ac.step: (a, v, logp).  (`multi_cap` only matters for kernel = "split".)"""
+        if self.kernel == "full":
+            mu, v, _ = self.forward(obs, count)
+        else:
+            mu, v = self._split_mu_v(obs, count, multi_cap)
         std = torch.clamp(std_factor * torch.exp(self.ac.pi.log_std) + 1e-6, min=1e-4, max=10.0)
         a = mu + std * torch.randn_like(mu)
         logp = (-((a - mu) ** 2) / (2 * std * std) - torch.log(std) - 0.9189385332046727).sum(-1)

@@ -10,6 +10,10 @@ Reference semantics kept per environment:
     success rate when every drone finished (:103-104)
   * the result line has the reference's format (:122-128)
 
+``policy = "rvo"`` runs the non-learned baseline instead: the classic RVO velocity selection (reciprocal_vel_obs.cal_vel,
+uaisa_env/vel_obs/reciprocal_vel_obs.py:21-166 -- dead code in the reference, here kernel K7 ``uaisa_rvo_select``) picks a velocity per drone
+and the env is fed that velocity expressed in its own controls (rounded to 2 dp like every action of the trainer).
+
 Every environment runs ``ceil(num_episodes / E)`` episodes (no bias towards short episodes); with E = 1 the episode order is the
 reference's.  All per-step work stays on the device; the host only learns how many environments still have episodes to run.
 """
@@ -29,6 +33,7 @@ class post_train:
         self.num_episodes, self.max_ep_len = int(num_episodes), int(max_ep_len)
         self.acceler_vel, self.std_factor, self.inf_print = float(acceler_vel), float(std_factor), bool(inf_print)
         self.drone_number = env.N
+        self.rvo_vmax, self.rvo_acceler = float(kwargs.get("rvo_vmax", 2.0)), float(kwargs.get("rvo_acceler", 0.5))     # ir_gym.py:18-29 constructor values
 
     # ------------------------------------------------------------------------------------------------------------
     def _policy_fn(self, policy, static_shapes: bool) -> Callable:
@@ -36,6 +41,11 @@ class post_train:
         ``FusedPolicy`` around one (fused forward: K6a features + tcgen05 heads), or a
         callable ``f(obs[A, obs_dim], count[A]) -> a_inc[A, 3]`` on CUDA tensors; a callable with ``wants_episode_info = True`` is also
         given each env's episode index and step within the episode (scripted policies)."""
+        if isinstance(policy, str):
+            if policy != "rvo":
+                raise ValueError("the only scripted policy is 'rvo' (classic RVO velocity selection)")
+            self._reader = None
+            return None
         if hasattr(policy, "step") and (hasattr(policy, "pi") or hasattr(policy, "ac")):     # rnn_ac, or uaisa_ppo.fused.FusedPolicy wrapping one
             module = policy if hasattr(policy, "pi") else policy.ac
             module.eval()
@@ -76,10 +86,14 @@ class post_train:
 
         def one_step():
             running = n_done < per_env
-            a_inc = (fn(env.obs, env.count, n_done, ep_len) if info_fn else fn(env.obs, env.count)).to(torch.float32)
-            a_inc = torch.round(a_inc * 100.0) / 100.0                                   # np.round(float32, 2)
-            vel = env.get_state()["vel_pitch"][:, :3]
-            action = ((self.acceler_vel * a_inc).double() + vel.double()).float().contiguous()   # float32(a) promoted, + float64 velocity
+            if fn is None:                                                               # scripted baseline: K7 velocity selection -> env controls
+                _, ctrl = env.rvo_select(self.rvo_vmax, self.rvo_acceler)
+                action = (torch.round(ctrl.double() * 100.0) / 100.0).float().contiguous()
+            else:
+                a_inc = (fn(env.obs, env.count, n_done, ep_len) if info_fn else fn(env.obs, env.count)).to(torch.float32)
+                a_inc = torch.round(a_inc * 100.0) / 100.0                               # np.round(float32, 2)
+                vel = env.get_state()["vel_pitch"][:, :3]
+                action = ((self.acceler_vel * a_inc).double() + vel.double()).float().contiguous()   # float32(a) promoted, + float64 velocity
             env.step(action)
             vel = env.get_state()["vel_pitch"][:, :3].double()
             sp_sum.add_(vel.norm(dim=1).view(E, N).mean(dim=1))

@@ -53,7 +53,8 @@ class PPOConfig:                      # train_process.py:53-63 defaults
     std_factor: float = 1.0
     use_cuda_graph: bool = True       # capture one rollout step (policy + transform + env step + reset policy + stores)
     graph_update: bool = True         # replay the update iterations as CUDA graphs (also with world_size > 1: the all-reduce is captured)
-    use_fused_policy: bool = True     # rollout forward through csrc/uaisa_policy.cu (K6a features + K6b tcgen05 heads, TF32 inputs)
+    use_fused_policy: bool = True     # rollout forward through the fused tcgen05 kernels (TF32 operands, fp32 accumulation)
+    fused_kernel: str = "full"        # "full": csrc/uaisa_policy_fwd.cu (one kernel, in-kernel recurrence); "split": round-1 K6a + K6b pair
     multi_cap_frac: float = 1.0 / 64  # static capacity of the multi-row GRU path in the captured step (fraction of A)
 
 
@@ -150,7 +151,7 @@ class PPOTrainer:
         self.vf_opt = FlatAdam(self.flat.n, self.cfg.vf_lr, self.dev)        # Adam(ac.v.parameters()):  v_net + reader = [0, v_hi)   (multi_ppo.py:115-116)
         self._ctl = torch.zeros(2, dtype=torch.int32, device=self.dev)       # device side of the KL early stop: {stopped latch, iterations applied}
         self._upd = None              # captured update graphs
-        self.policy_path = "fused forward (K6a features + K6b tcgen05 heads, TF32)" if self.cfg.use_fused_policy else "torch module (cuBLAS)"
+        self.policy_path = "not built yet"
         self.update_path = "not run yet"
         T, A, D = self.cfg.steps_per_epoch, env.A, env.obs_dim
         f32 = dict(dtype=torch.float32, device=self.dev)
@@ -167,7 +168,10 @@ class PPOTrainer:
         self.fused = None
         if self.cfg.use_fused_policy:
             from .fused import FusedPolicy
-            self.fused = FusedPolicy(self.ac, self.dev)
+            self.fused = FusedPolicy(self.ac, self.dev, kernel=self.cfg.fused_kernel)
+        self._single_graph = self.fused is not None and self.fused.kernel == "full"     # one captured step, no per-step flag read
+        self.policy_path = ("one fused kernel: masked bi-GRU + LayerNorm + actor/critic MLPs on tcgen05 (TF32), bulk-copied pre-swizzled weight tiles" if self._single_graph
+                            else "split kernels: K6a step-0 features + K6b tcgen05 heads, multi-row agents through torch" if self.fused is not None else "torch module (cuBLAS)")
         self._t = torch.zeros(1, dtype=torch.long, device=self.dev)           # device-side step counter (graph-safe buffer index)
         self._ndone = torch.zeros((), dtype=torch.int64, device=self.dev)
         self._last = torch.zeros((), dtype=torch.int64, device=self.dev)
@@ -188,14 +192,17 @@ class PPOTrainer:
         env.autoreset(max_ep_len=cfg.max_ep_len, epoch_ended=epoch_ended)                                          # :226-281 (+ env_observation)
         b["cut"].index_copy_(0, t, env.path_cut.unsqueeze(0))
         t += 1
-        self._flag_dev.copy_((env.count > 1).any().to(torch.int32).reshape(1))      # does the NEXT step need the multi-row path?
-        self._flag_host.copy_(self._flag_dev, non_blocking=True)
+        if not self._single_graph:
+            self._flag_dev.copy_((env.count > 1).any().to(torch.int32).reshape(1))      # does the NEXT step need the multi-row path?
+            self._flag_host.copy_(self._flag_dev, non_blocking=True)
 
     @torch.no_grad()
     def rollout(self):
-        """steps_per_epoch env steps of every env (multi_ppo.py:183-281).  The T-1 ordinary steps replay one CUDA graph
-        (no host synchronisation inside: the policy's multi-row path runs at a static capacity); the last step of the
-        epoch (full reset, multi_ppo.py:244-264) runs eagerly."""
+        """steps_per_epoch env steps of every env (multi_ppo.py:183-281).  The T-1 ordinary steps replay ONE CUDA graph with no host
+        synchronisation in between (the fused forward handles every neighbour-row count inside the kernel); the last step of the epoch
+        (full reset, multi_ppo.py:244-264) runs eagerly.  With the torch policy / the split kernels (`use_fused_policy=False` or
+        FusedPolicy(kernel="split")) two graphs are kept -- with / without the multi-row GRU path at a static capacity -- and a 4-byte
+        flag read per step picks one."""
         cfg = self.cfg
         T = cfg.steps_per_epoch
         self._t.zero_(); self._ndone.zero_()
@@ -203,7 +210,8 @@ class PPOTrainer:
         if getattr(rd, "overflow", None) is None:
             rd.overflow = torch.zeros((), dtype=torch.int64, device=self.dev)
         rd.overflow.zero_()
-        cap = max(64, int(self.env.A * cfg.multi_cap_frac)) if cfg.use_cuda_graph else 0
+        single = self._single_graph
+        cap = max(64, int(self.env.A * cfg.multi_cap_frac)) if (cfg.use_cuda_graph and not single) else 0
         if cfg.use_cuda_graph and self._graph is None and T > 1:
             s = torch.cuda.Stream(device=self.dev)
             s.wait_stream(torch.cuda.current_stream(self.dev))
@@ -211,23 +219,31 @@ class PPOTrainer:
                 self._one_step(False, cap); self._one_step(False, -1)
             torch.cuda.current_stream(self.dev).wait_stream(s)
             self.env.reset()
-            g, gf = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 self._one_step(False, cap)
-            with torch.cuda.graph(gf, pool=g.pool()):
-                self._one_step(False, -1)
-            self._graph, self._graph_fast = g, gf
+            self._graph = g
+            if not single:
+                gf = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gf, pool=g.pool()):
+                    self._one_step(False, -1)
+                self._graph_fast = gf
             self._t.zero_(); self._ndone.zero_(); rd.overflow.zero_()
             self.env.reset()
-        self._flag_host[0] = int((self.env.count > 1).any())
+        if not single:
+            self._flag_host[0] = int((self.env.count > 1).any())
         for t in range(T - 1):
             if self._graph is not None:
-                torch.cuda.current_stream(self.dev).synchronize()        # the flag of the previous step has landed (one small bubble per step)
-                (self._graph if int(self._flag_host[0]) else self._graph_fast).replay()
+                if single:
+                    self._graph.replay()
+                else:
+                    torch.cuda.current_stream(self.dev).synchronize()        # the flag of the previous step has landed (one small bubble per step)
+                    (self._graph if int(self._flag_host[0]) else self._graph_fast).replay()
             else:
                 self._one_step(False, cap)
-        torch.cuda.current_stream(self.dev).synchronize()
-        self._one_step(True, cap if int(self._flag_host[0]) or not cfg.use_cuda_graph else -1)
+        if not single:
+            torch.cuda.current_stream(self.dev).synchronize()
+        self._one_step(True, cap if (single or int(self._flag_host[0]) or not cfg.use_cuda_graph) else -1)
         self.stats["collisions"] = self._ndone
         if cap and int(rd.overflow) > 0:
             raise RuntimeError("%d agent-steps had >= 2 neighbour rows beyond the static GRU capacity (%d); raise PPOConfig.multi_cap_frac" % (int(rd.overflow), cap))

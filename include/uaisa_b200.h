@@ -130,6 +130,13 @@ int uaisa_get_state(UaisaHandle *h, const UaisaStateView *dst, void *stream);
 int uaisa_set_state(UaisaHandle *h, const UaisaStateView *src, void *stream);
 /* ir_gym.cal_des_list (ir_gym.py:44-46): des[A][3] */
 int uaisa_cal_des(UaisaHandle *h, float *des, void *stream);
+/* K7 -- classic RVO velocity selection, reciprocal_vel_obs.cal_vel (uaisa_env/vel_obs/reciprocal_vel_obs.py:21-31) with vel_candidate :85-107, vo_out2
+ * :109-128, vel_select :131-138, penalty :140-166, on the handle's current state: vel_out[A][3] = the selected velocity of every drone (grid of 0.5
+ * within +-acceler of its velocity, clipped to +-vmax; ir_gym.py:18-29 constructs the class with vmax = 2, acceler = 0.5).  PARITY UNPINNED: the
+ * reference's code for this is dead and raises; the behaviour is the corrected restatement oracle/uaisa_oracle.c:uo_rvo_select (fixes F1-F9 listed
+ * there).  ctrl_out[A][3] (may be NULL) = the same velocity expressed in the controls mdin.drone_step actually applies
+ * ([acc, yaw change / 90, pitch change / 90], drone.py:431-490), i.e. what to feed uaisa_step to fly it. */
+int uaisa_rvo_select(UaisaHandle *h, double vmax, double acceler, float *vel_out, float *ctrl_out, void *stream);
 /* Trainer action transform (multi_ppo.py:197-205): a_inc[A][3] = the policy's float32 sample;
  * a_inc_rounded = np.round(a_inc, 2) (what the buffer stores, may be NULL); action = np.round(acceler * a_inc_rounded +
  * drone.vel, 2) = what uaisa_step consumes. */
@@ -166,6 +173,21 @@ int uaisa_step_host(UaisaHandle *h, const float *action, float *obs, uint8_t *co
 int uaisa_policy_features(const float *obs, int32_t A, int32_t obs_dim, const float *wih_t, const float *bias, const float *ln_w,
                           const float *ln_b, float *feat, void *stream);
 int uaisa_policy_heads(const float *feat, int32_t A, const float *const *weights, float *mu, float *v, void *stream);
+
+/* ---- K6, complete: the whole rollout forward in ONE kernel (csrc/uaisa_policy_fwd.cu) ------------------------------------------------------------
+ * uaisa_policy_pack:    repacks the module's parameters (22 DEVICE pointers, torch layouts: weight_ih_l0, weight_hh_l0, bias_ih_l0, bias_hh_l0, the same
+ *   four with suffix _reverse, ln.weight, ln.bias, actor net_out.{0,2,4}.{weight,bias}, critic v_net.{0,2,4}.{weight,bias}) into `wpack`
+ *   ([uaisa_policy_pack_floats()] floats, 16-byte aligned): every weight tile as the swizzled shared-memory image the tensor cores read, so that the
+ *   forward kernel fetches a tile with ONE bulk copy.  Call it after every optimiser step (in place: `wpack` keeps its address).
+ * uaisa_policy_forward:  obs[A][obs_dim] + count[A] -> mu[A][3] = tanh(actor MLP), v[A] = critic MLP, with the masked bi-GRU recurrence over each
+ *   agent's max(count, 1) neighbour rows (policy_rnn_ac.py:102-168), LayerNorm(268) and both MLPs on the tensor cores (tcgen05.mma kind::tf32,
+ *   fp32 accumulation in TMEM).  feat_out (may be NULL): the LayerNorm output [A][268] in the module's [self | h] order.  scratch: DEVICE buffer of
+ *   ceil(A/128) * 128 * 1024 bytes (forward-direction GRU state of tiles that run the recurrence).  stats (may be NULL): int32[2] {tiles that ran the
+ *   recurrence (+=), max steps (max)}.  Stateless, asynchronous on `stream`, capturable in a CUDA graph. */
+int uaisa_policy_pack_floats(void);
+int uaisa_policy_pack(const float *const *params, float *wpack, void *stream);
+int uaisa_policy_forward(const float *obs, const uint8_t *count, int32_t A, int32_t obs_dim, const float *wpack, float *mu, float *v, float *feat_out,
+                         void *scratch, int32_t *stats, void *stream);
 
 /* ---- optimiser epilogue of the PPO update (train/policy/multi_ppo.py:355-376; SURVEY.md section 5 "fused grad-norm + clip + Adam") -----------
  * Parameters, gradients and Adam moments are FLAT fp32 DEVICE buckets.  One update iteration ends with

@@ -53,6 +53,7 @@ def lib():
         L.uo_cal_des.argtypes = [vp, vp]
         L.uo_get_route_len.argtypes = [vp, vp]
         L.uo_get_counters.argtypes = [vp, vp, vp]
+        L.uo_rvo_select.argtypes = [vp, C.c_double, C.c_double, vp, vp]
         L.uo_pair.restype = C.c_int
         L.uo_pair.argtypes = [C.POINTER(UoConfig)] + [vp] * 6
         L.uo_pyround2.restype = C.c_double
@@ -158,6 +159,12 @@ class OracleBatch:
         d = np.zeros((self.A, 3), np.float64)
         self.L.uo_cal_des(self.h, _p(d))
         return d
+
+    def rvo_select(self, vmax: float = 2.0, acceler: float = 0.5):
+        """K7: classic RVO velocity selection (corrected restatement of reciprocal_vel_obs.cal_vel; PARITY UNPINNED) -> (velocity [A,3], env controls [A,3])."""
+        v, c = np.zeros((self.A, 3), np.float64), np.zeros((self.A, 3), np.float64)
+        self.L.uo_rvo_select(self.h, float(vmax), float(acceler), _p(v), _p(c))
+        return v, c
 
     def route_len(self):
         r = np.zeros((self.scn.S, self.N), np.float64)

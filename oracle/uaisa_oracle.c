@@ -552,3 +552,129 @@ void uo_cal_des(const UoBatch *b, double *des) {
 }
 void uo_get_route_len(const UoBatch *b, double *route_len) { memcpy(route_len, b->route_len, sizeof(double) * (size_t)b->S * b->N); }
 void uo_get_counters(const UoBatch *b, int64_t *r, int64_t *c) { *r = b->cnt_in_range; *c = b->cnt_cone; }
+
+/* =====================================================================================================================
+ * K7 -- classic RVO velocity selection: reciprocal_vel_obs.cal_vel -> vel_candidate -> vo_out2 -> vel_select -> penalty
+ * (uaisa_env/vel_obs/reciprocal_vel_obs.py:21-166).
+ *
+ * PARITY UNPINNED.  The reference's code for this path is dead (no caller, grep cal_vel) and cannot run: it raises on the
+ * first call.  This is therefore a CORRECTED restatement -- it follows the reference statement by statement and fixes only
+ * what stops it from running or makes it meaningless; every fix is listed here and in DESIGN.md:
+ *   F1  config_vo is defined twice (:56, :63) and cal_vel calls it with the list (:26): the per-neighbour form (:63-83) is
+ *       mapped over the neighbour list.
+ *   F2  Pa = state[0:4] / Pb = odro[0:4] (:65, :70) feed 4 values into 3-value unpackings (get_PAA): positions are [0:3].
+ *   F3  get_alpha calls math.asin(R / |rel|), a ValueError for overlapping drones: alpha = round(pi/2, 2) there.
+ *   F4  vo_out2: `arr_AA_Anew.append = ...` (:122) -> append(...);  `odro_rvo[4:6]` (:118, a 2-vector) -> the relative
+ *       position odro_rvo[3:6].
+ *   F5  vel_select returns None when vo_outside is non-empty (:134-138): the selected velocity is returned in both cases.
+ *   F6  penalty (:140-166) evaluates cal_exp_tim with the agent's CURRENT velocity -- a constant that cannot influence the
+ *       arg-min; the candidate velocity is used instead (what the `vel` argument is for).  tc_min = inf gives 1/inf = 0.
+ *   F7  no candidate survives the 0.3 speed floor (:98) -> min() of an empty list raises: the current velocity is kept.
+ *   F8  "self" is not in the list cal_vel receives (the caller passes the OTHER drones): excluded here by index.
+ *   F9  np.arange(lo, hi, 0.5) (:93-96) excludes hi: with acceler = 0.5 the grid would be {v-0.5, v} per axis (never v+0.5), so a drone at
+ *       rest could only pick negative components and -- with the 0.3 speed floor -- never its desired direction.  The grid INCLUDES the
+ *       end point: lo + 0.5 i for every i with lo + 0.5 i <= hi + 1e-9 ("within +-acceler of v").
+ * Kept as they are: the hard-coded neighbour range 10 (:43), buildings filtered but never used (:47-54, config_vo only sees
+ * drones), the 0.5 grid step and the 0.3 speed floor, builtin round for alpha / numpy-style round for beta, the unclamped arccos, first
+ * minimum wins (Python min; candidates in vx-outer, vz-inner order), ir_gym's constructor values vmax = 2, acceler = 0.5, delta_t = 1 (ir_gym.py:18-29).
+ * Arithmetic of the distances is plain IEEE mul/add/sqrt (x*x, not pow): this restatement defines it.
+ * ===================================================================================================================== */
+static double k7_exp_tim(const double *Pa, const double *Pb, const double *Va, const double *Vb, double ra, double rb) { /* vel_obs3D.cal_exp_tim :104-143 */
+    double rx = Pa[0] - Pb[0], ry = Pa[1] - Pb[1], rz = Pa[2] - Pb[2];
+    double vx = Va[0] - Vb[0], vy = Va[1] - Vb[1], vz = Va[2] - Vb[2];
+    double r = ra + rb;
+    double a = vx * vx + vy * vy + vz * vz;
+    double b = 2 * rx * vx + 2 * ry * vy + 2 * rz * vz;
+    double c = rx * rx + ry * ry + rz * rz - r * r;
+    if (c <= 0) return 0;
+    double temp = b * b - 4 * a * c;
+    if (temp <= 0) return INFINITY;
+    double sq = sqrt(temp);
+    double t1 = (-b + sq) / (2 * a), t2 = (-b - sq) / (2 * a);
+    double t3 = t1 >= 0 ? t1 : INFINITY, t4 = t2 >= 0 ? t2 : INFINITY;
+    return t3 < t4 ? t3 : t4;
+}
+static double k7_dist(const double *p, const double *q) { /* reciprocal_vel_obs.distance :169-171 */
+    double dx = q[0] - p[0], dy = q[1] - p[1], dz = q[2] - p[2];
+    return sqrt(dx * dx + dy * dy + dz * dz);
+}
+#define K7_MAXC 5 /* candidates per axis: 2*acceler/0.5 + 1 for acceler <= 1 */
+
+/* ctrl_out (may be NULL): the selected velocity expressed in the env's own controls, because mdin.drone_step re-reads its "action" as
+ * [acceleration, yaw change / 90 deg, pitch change / 90 deg] (drone.py:431-490): acc = |v*| - |v|, yaw / pitch steered onto v*'s heading, each clipped
+ * to [-1, 1].  Not in the reference (its only usage example, uaisa_env/gym_env_test.py:12, feeds the velocity itself and spirals): this is the
+ * adapter that makes the selection usable as a scripted baseline controller (uaisa_ppo.post_train, policy "rvo"). */
+void uo_rvo_select(const UoBatch *b, double vmax, double acceler, double *vel_out /*[A][3]*/, double *ctrl_out /*[A][3] or NULL*/) {
+    const int N = b->N;
+    const double dt = b->cfg.delta_t;
+#pragma omp parallel for schedule(static) num_threads(nthreads())
+    for (int e = 0; e < b->E; e++) {
+        const int s = b->env2scn[e];
+        for (int k = 0; k < N; k++) {
+            const int a = e * N + k;
+            const double *Pa = b->pos + 3 * (size_t)a, *Va = b->vel + 3 * (size_t)a;
+            const double ra = b->radius[(size_t)s * N + k], pra = b->prio[(size_t)s * N + k];
+            double des[3];
+            cal_des_vel(b, Pa, WP(b, s, k, b->wp_idx[a]), des);                 /* agent_state[8:11] */
+            /* vel_candidate :85-96: axis grids */
+            double grid[3][K7_MAXC]; int ng[3];
+            for (int ax = 0; ax < 3; ax++) {
+                double lo = np_clip(Va[ax] - acceler, -vmax, vmax), hi = np_clip(Va[ax] + acceler, -vmax, vmax);
+                int n = 0;                                                       /* F9: end point included */
+                while (n < K7_MAXC && lo + n * 0.5 <= hi + 1e-9) { grid[ax][n] = lo + n * 0.5; n++; }
+                ng[ax] = n;
+            }
+            int have_out = 0, have_in = 0;
+            double best_out = 0, best_in = 0, vout[3] = {0, 0, 0}, vin[3] = {0, 0, 0};
+            for (int ix = 0; ix < ng[0]; ix++) for (int iy = 0; iy < ng[1]; iy++) for (int iz = 0; iz < ng[2]; iz++) {
+                const double v[3] = {grid[0][ix], grid[1][iy], grid[2][iz]};
+                if (sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]) < 0.3) continue;       /* :98 */
+                const double Pn[3] = {Pa[0] + v[0] * dt, Pa[1] + v[1] * dt, Pa[2] + v[2] * dt};   /* vo_out2 :111-114 */
+                int inside = 0; double tc_min = INFINITY;
+                for (int j = 0; j < N; j++) {
+                    if (j == k) continue;                                                    /* F8 */
+                    const int o = e * N + j;
+                    const double *Pb = b->pos + 3 * (size_t)o, *Vb = b->vel + 3 * (size_t)o;
+                    const double dif[3] = {Pa[0] - Pb[0], Pa[1] - Pb[1], Pa[2] - Pb[2]};
+                    if (!(np_norm3(dif) <= 10.0)) continue;                                  /* preprocess :38-44 */
+                    const double rb = b->radius[(size_t)s * N + j], prb = b->prio[(size_t)s * N + j];
+                    const double rel[3] = {Pb[0] - Pa[0], Pb[1] - Pa[1], Pb[2] - Pa[2]};       /* get_rvo_array */
+                    const double nab = np_norm3(rel), R = ra + rb;
+                    const double alpha = (R / nab <= 1.0) ? uo_pyround2(wraptopi(asin(R / nab))) : uo_pyround2(M_PI / 2);   /* get_alpha, F3 */
+                    const double pr = pra / (pra + prb);
+                    const double PAA[3] = {pr * (2 * Pa[0] + (Va[0] + Vb[0]) * 1), pr * (2 * Pa[1] + (Va[1] + Vb[1]) * 1), pr * (2 * Pa[2] + (Va[2] + Vb[2]) * 1)};
+                    const double B[3] = {Pn[0] - PAA[0], Pn[1] - PAA[1], Pn[2] - PAA[2]};
+                    const double AB = nab * np_norm3(B);                                     /* get_beta :44-66 */
+                    const double cosang = (AB != 0) ? np_dot3(rel, B) / AB : 0.0;
+                    const double beta = uo_npround(wraptopi(acos(cosang)), 2);
+                    if (alpha > beta) inside = 1;                                            /* :125-126 (NaN beta -> outside) */
+                    const double tc = k7_exp_tim(Pa, Pb, v, Vb, ra, rb);                     /* penalty :151-153, F6 */
+                    if (tc < tc_min) tc_min = tc;
+                }
+                if (!inside) {                                                               /* vel_select :134-135 */
+                    const double dd = k7_dist(v, des);
+                    if (!have_out || dd < best_out) { have_out = 1; best_out = dd; vout[0] = v[0]; vout[1] = v[1]; vout[2] = v[2]; }
+                } else {                                                                     /* :137, penalty :140-166 with factor 1 */
+                    const double tc_inv = (tc_min == 0) ? INFINITY : 1.0 / tc_min;
+                    const double pen = 1.0 * tc_inv + k7_dist(des, v);
+                    if (!have_in || pen < best_in) { have_in = 1; best_in = pen; vin[0] = v[0]; vin[1] = v[1]; vin[2] = v[2]; }
+                }
+            }
+            double *out = vel_out + 3 * (size_t)a;
+            if (have_out) { out[0] = vout[0]; out[1] = vout[1]; out[2] = vout[2]; }
+            else if (have_in) { out[0] = vin[0]; out[1] = vin[1]; out[2] = vin[2]; }
+            else { out[0] = Va[0]; out[1] = Va[1]; out[2] = Va[2]; }                         /* F7 */
+            if (ctrl_out) {
+                double *c = ctrl_out + 3 * (size_t)a;
+                const double sp_new = sqrt(out[0] * out[0] + out[1] * out[1] + out[2] * out[2]), sp = sqrt(Va[0] * Va[0] + Va[1] * Va[1] + Va[2] * Va[2]);
+                double dyaw = 0, dpitch = 0;
+                if (sp_new > 0) {
+                    const double yaw_t = atan2(out[1], out[0]) * (180.0 / M_PI), pitch_t = atan2(out[2], sqrt(out[0] * out[0] + out[1] * out[1])) * (180.0 / M_PI);
+                    dyaw = py_mod(yaw_t - b->yaw[a] + 180.0, 360.0) - 180.0;
+                    dpitch = pitch_t - b->pitch[a];
+                }
+                c[0] = np_clip(sp_new - sp, -1.0, 1.0); c[1] = np_clip(dyaw / 90.0, -1.0, 1.0); c[2] = np_clip(dpitch / 90.0, -1.0, 1.0);
+            }
+        }
+    }
+}

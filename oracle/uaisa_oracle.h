@@ -82,6 +82,9 @@ void uo_get_counters(const UoBatch *b, int64_t *in_range_pairs, int64_t *cone_ev
  * (rvo_inter.py:116-196). out9 = row, returns bit0 vo_flag, bit1 collision; t, md via pointers. */
 int uo_pair(const UoConfig *cfg, const double *sa8, const double *sb8, const double *act, double *out9,
             double *t, double *md);
+/* K7, classic RVO velocity selection (reciprocal_vel_obs.py:21-166): PARITY UNPINNED -- the reference's code is dead and raises on its
+ * first call; this is the corrected restatement documented at the function (uaisa_oracle.c).  vel_out[A][3]. */
+void uo_rvo_select(const UoBatch *b, double vmax, double acceler, double *vel_out, double *ctrl_out /* [A][3] env controls, may be NULL */);
 double uo_pyround2(double x);          /* builtin round(x, 2) on a Python float */
 double uo_npround(double x, int nd);   /* np.round(x, nd) */
 

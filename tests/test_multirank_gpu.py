@@ -108,15 +108,19 @@ def _worker(rank, world, port, backend, q):
 def test_two_rank_product_sharding_and_ppo_update():
     backend = "nccl" if torch.cuda.device_count() >= 2 else "gloo"
     ctx = mp.get_context("spawn")
-    q = ctx.SimpleQueue()
+    q = ctx.Queue()
     port = _free_port()
     procs = [ctx.Process(target=_worker, args=(r, 2, port, backend, q)) for r in range(2)]
     for p in procs:
         p.start()
-    for p in procs:
-        p.join(300)
-        assert p.exitcode == 0, p.exitcode
-    ok, flat2 = q.get()
+    try:
+        ok, flat2 = q.get(timeout=240)          # (read BEFORE joining: a 2.7 MB payload does not fit the pipe buffer, the writer would block)
+    finally:
+        for p in procs:
+            p.join(60)
+            if p.exitcode is None:
+                p.kill()
+    assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
     assert ok["sharding"] and ok["ranks_identical"] and ok["pi_iters"] == 3, ok
     # the same update in ONE process on the whole buffer (full batch: the mean gradient is the same whatever the split)
     from uaisa_env.scenario import scenario_c1

@@ -84,7 +84,7 @@ def test_fused_features_and_tcgen05_heads_match_torch():
 
     torch.backends.cuda.matmul.allow_tf32 = False
     m = _model("cuda")
-    fp = FusedPolicy(m, "cuda")
+    fp = FusedPolicy(m, "cuda", kernel="split")
     rng = np.random.default_rng(3)
     for A in (96, 128, 1000, 4133):
         obs = np.zeros((A, 102), np.float32)
@@ -122,3 +122,54 @@ def test_eval_parity_policy_forms_agree():
     b = goal_policy_torch(torch.from_numpy(obs.astype(np.float32))).numpy()
     ra, rb = np.round(a, 2), np.round(b, 2)
     assert (ra != rb).mean() == 0 and np.abs(a - b).max() < 1e-6
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("nm", [10, 3, 16])
+def test_full_forward_kernel_matches_torch_for_every_row_count(nm):
+    """K6 complete (csrc/uaisa_policy_fwd.cu): ONE kernel with the masked bi-GRU recurrence, LayerNorm and both tcgen05 heads against the torch module
+    (itself pinned to the reference's rnn_ac by the golden above) for every neighbour-row count 0..nm, tiles with and without multi-row agents, ragged
+    last tile.  TF32 operands (10-bit mantissa), fp32 accumulation."""
+    from uaisa_ppo.fused import FusedPolicy
+
+    torch.backends.cuda.matmul.allow_tf32 = False
+    m = _model("cuda")
+    fp = FusedPolicy(m, "cuda")
+    rng = np.random.default_rng(7)
+    D = 12 + 9 * nm
+    for A, choices in ((128, [0, 1]), (256, [0, 0, 1, 2]), (1000, list(range(nm + 1))), (4133, [0, 0, 0, 1, 1, 2, 3, nm]), (77, [nm])):
+        obs = np.zeros((A, D), np.float32)
+        obs[:, :12] = np.round(rng.normal(0, 5, (A, 12)), 2); obs[:, 0:3] += 20
+        cnt = rng.choice(choices, A).astype(np.uint8)
+        if A == 4133:
+            cnt[:1024] = np.minimum(cnt[:1024], 1)             # the first 8 tiles take the no-recurrence path
+        for b in range(A):
+            obs[b, 12:12 + 9 * cnt[b]] = np.round(rng.normal(0, 2, 9 * int(cnt[b])), 2)
+        o, c = torch.from_numpy(obs).cuda(), torch.from_numpy(cnt).cuda()
+        with torch.no_grad():
+            ref_feat = m.features(o, c)
+            dist, ref_v, _ = m.evaluate(o, c)
+        fp.stats.zero_()
+        mu, v, feat = fp.forward(o, c, want_features=True)
+        torch.cuda.synchronize()
+        err_f = (feat - ref_feat).abs().max().item()
+        assert err_f < 1.5e-2, (A, nm, err_f)                                  # LayerNorm output is O(1); TF32 recurrence over <= nm steps
+        assert (feat - ref_feat).abs().mean().item() < 1e-3
+        assert (mu - dist.mean).abs().max().item() < 1e-2 and (v - ref_v).abs().max().item() < 1e-2 * max(1.0, float(ref_v.abs().max())), ((mu - dist.mean).abs().max(), (v - ref_v).abs().max())
+        st = fp.stats.tolist()
+        tiles_multi = int(sum(int(cnt[t:t + 128].max()) > 1 for t in range(0, A, 128)))
+        assert st[0] == tiles_multi and st[1] == (int(cnt.max()) if tiles_multi else 0), (st, tiles_multi)
+        single = torch.from_numpy(cnt <= 1).cuda()
+        if bool(single.any()):      # no recurrence for these agents: the only TF32 rounding is in the 9-wide input projection
+            assert (feat[single] - ref_feat[single]).abs().max().item() < 4e-3
+    # graph capture + in-place refresh after a weight change
+    a, vv, logp = fp.step(o, c)
+    assert a.shape == (A, 3) and torch.isfinite(logp).all()
+    with torch.no_grad():
+        for p_ in m.parameters():
+            p_.mul_(1.01)
+    fp.refresh()
+    with torch.no_grad():
+        dist2, ref_v2, _ = m.evaluate(o, c)
+    mu2, v2, _ = fp.forward(o, c)
+    assert (mu2 - dist2.mean).abs().max().item() < 1e-2 and (v2 - ref_v2).abs().max().item() < 1e-2 * max(1.0, float(ref_v2.abs().max()))

@@ -20,6 +20,8 @@ KPAD = 288
 class FusedPolicy:
     def __init__(self, ac: rnn_ac, device, kernel: str = "full"):
         self.ac, self.dev = ac, torch.device(device)
+        if self.dev.type == "cuda" and self.dev.index is None:
+            self.dev = torch.device("cuda", torch.cuda.current_device())
         self.L = _capi.lib()
         if kernel not in ("full", "split"):
             raise ValueError("kernel must be 'full' or 'split'")

@@ -44,13 +44,23 @@ CASES = [
     ("swarm12_nm10", swarm(12, 1.0, 1).to_dict(), 10, 250, 5, {"block": 20}),
     ("c3_n12_m3", scenario_c3(seed=1, n_drones=12, n_buildings=3).to_dict(), 10, 300, 6, {}),
     ("world_4_noreset", json.load(open(os.path.join(REF_WORLDS, "world_4", "data_1.json"))), 10, 200, 7, {"reset_on": ()}),
+    # fp32-representable pre-states and actions (the reference is teacher-forced with float64 copies of fp32 values): the CUDA path has to match
+    # these with no input-rounding slack
+    ("f32_world_8", json.load(open(os.path.join(REF_WORLDS, "world_8", "data_1.json"))), 10, 200, 11, {"f32": True}),
+    ("f32_c1_yaml4", scenario_c1().to_dict(), 10, 200, 12, {"f32": True, "full_reset_every": 90}),
+    ("f32_swarm12_nm10", swarm(12, 1.0, 2).to_dict(), 10, 160, 13, {"f32": True, "block": 20}),
+    ("f32_swarm12_nm3", swarm(12, 1.0, 3).to_dict(), 3, 120, 14, {"f32": True, "block": 15}),
+    ("f32_c3_n12_m3", scenario_c3(seed=2, n_drones=12, n_buildings=3).to_dict(), 10, 160, 15, {"f32": True}),
 ]
 
 
 def main():
     out_dir = os.path.join(ROOT, "tests", "golden")
     os.makedirs(out_dir, exist_ok=True)
+    only = sys.argv[1:]
     for name, scn, nm, steps, seed, kw in CASES:
+        if only and not any(name.startswith(o) for o in only):
+            continue
         tr = lockstep.run_reference(scn, nm, steps, seed, **kw)
         tr["scenario_json"] = np.array(json.dumps(scn))
         path = os.path.join(out_dir, name + ".npz")

@@ -40,12 +40,20 @@ def mixed_actions(rng, step, des, st, block=50):
                             noise=0.05 if mode == 2 else 0.2)
 
 
-def run_reference(scenario_dict, nm, steps, seed, reset_on=("done", "finish"), full_reset_every=0, block=50):
+def run_reference(scenario_dict, nm, steps, seed, reset_on=("done", "finish"), full_reset_every=0, block=50, f32=False):
     """Run the reference; return a dict of stacked per-step arrays (a golden trace).
 
     Per step t the trace holds the state BEFORE the step, the action, the step outputs, the state
     AFTER the step, the reset mask applied afterwards and the observation returned by
-    ``env_observation()`` after those resets (only when any reset happened)."""
+    ``env_observation()`` after those resets (only when any reset happened).
+
+    f32 = True: before every step (and before the post-reset observation) the reference is re-loaded with float64 COPIES of the fp32 image of its own
+    state, and it is stepped with the fp32 image of the action -- what a device that stores fp32 state would hand it.  The
+    recorded pre-states / actions are then exactly representable on the device, so the CUDA path must reproduce the recorded outputs with NO
+    input-rounding slack (tests/test_gpu_parity.py::test_against_reference_golden_exact)."""
+
+    def q32(st):
+        return {k: (np.asarray(v, np.float64).astype(np.float32).astype(np.float64) if np.asarray(v).dtype.kind == "f" else v) for k, v in st.items()}
     env = ref_shim.make_reference_env(scenario_dict, nm=nm)
     rng = np.random.default_rng(seed)
     N = len(env.ir_gym.drone_list)
@@ -56,10 +64,15 @@ def run_reference(scenario_dict, nm, steps, seed, reset_on=("done", "finish"), f
     post = {k: [] for k in ref_shim.STATE_FIELDS}
     for t in range(steps):
         st = ref_shim.get_state(env)
+        if f32:
+            st = q32(st)
+            ref_shim.set_state(env, st)
         for k in pre:
             pre[k].append(st[k])
         des = np.array(env.ir_gym.cal_des_list(), dtype=np.float64)
         act = mixed_actions(rng, t, des, st, block)
+        if f32:
+            act = act.astype(np.float32).astype(np.float64)
         o, r, d, i, f = env.drone_step([a for a in act])
         po, pc = ref_shim.pad_obs(o, nm)
         st2 = ref_shim.get_state(env)
@@ -79,6 +92,8 @@ def run_reference(scenario_dict, nm, steps, seed, reset_on=("done", "finish"), f
             mask[:] = 1
             po2, pc2 = ref_shim.pad_obs(env.drone_reset(False), nm)
         elif mask.any():
+            if f32:
+                ref_shim.set_state(env, q32(ref_shim.get_state(env)))      # the device resets / re-observes from its fp32 post-step state
             for k in np.nonzero(mask)[0]:
                 env.drone_reset_one(False, int(k))
             po2, pc2 = ref_shim.pad_obs(env.ir_gym.env_observation(), nm)

@@ -13,6 +13,18 @@ case $what in
     done ;;
   alltests)
     timeout 1500 python -m pytest tests -m gpu -x -q --timeout 400 > gpurun_out/r2/tests.txt 2>&1; echo "tests rc=$?" | tee -a gpurun_out/r2/tests.txt; tail -15 gpurun_out/r2/tests.txt ;;
+  dbg)
+    timeout 200 python profiles/dbg_collinear.py > gpurun_out/r2/dbg_collinear.txt 2>&1; tail -40 gpurun_out/r2/dbg_collinear.txt | cut -c1-400 ;;
+  quick)     # the tests that failed last time
+    timeout 300 python -m pytest tests/test_trainer_trace_gpu.py tests/test_quirks_gpu.py -m gpu -q --timeout 200 > gpurun_out/r2/tests_quick.txt 2>&1; echo "quick rc=$?" | tee -a gpurun_out/r2/tests_quick.txt; tail -30 gpurun_out/r2/tests_quick.txt | cut -c1-300
+    timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -q --timeout 200 -k "golden_exact" > gpurun_out/r2/tests_exact.txt 2>&1; echo "exact rc=$?" | tee -a gpurun_out/r2/tests_exact.txt; tail -30 gpurun_out/r2/tests_exact.txt | cut -c1-400 ;;
+  bench2)    # what the driver runs at N = 2
+    s=$(date +%s); timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 20 --warmup 5 > gpurun_out/r2/bench_n2.json 2> gpurun_out/r2/bench_n2.err; echo "bench2 rc=$? in $(( $(date +%s) - s )) s"
+    tail -5 gpurun_out/r2/bench_n2.err | cut -c1-300; head -c 1500 gpurun_out/r2/bench_n2.json ;;
+  mr2)
+    timeout 400 python -m pytest tests/test_multirank_gpu.py -m gpu -q --timeout 300 > gpurun_out/r2/tests_mr2.txt 2>&1; echo "mr2 rc=$?" | tee -a gpurun_out/r2/tests_mr2.txt; tail -20 gpurun_out/r2/tests_mr2.txt | cut -c1-300 ;;
+  ptime)
+    timeout 300 python profiles/policy_timing.py 262144 > gpurun_out/r2/policy_timing.txt 2>&1; cat gpurun_out/r2/policy_timing.txt | cut -c1-200 ;;
   fma)
     ./profiles/fma_peak > gpurun_out/r2/fma_peak.json 2> gpurun_out/r2/fma_peak.err; cat gpurun_out/r2/fma_peak.json ;;
   bench)

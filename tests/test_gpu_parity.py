@@ -124,6 +124,48 @@ def test_against_reference_golden(path):
     assert rew_bad <= max(1, n // 200), rew_bad
 
 
+F32_GOLDEN = [p for p in GOLDEN if os.path.basename(p).startswith("f32_")]
+
+
+@pytest.mark.parametrize("path", F32_GOLDEN, ids=[os.path.basename(p)[:-4] for p in F32_GOLDEN])
+def test_against_reference_golden_exact(path):
+    """CUDA path vs outputs recorded from the UNMODIFIED reference with fp32-representable pre-states and actions (oracle/gen_golden.py, f32 cases:
+    the reference was teacher-forced with float64 copies of fp32 values).  No input-rounding slack is left, so the contract
+    applies literally: every flag, count and ragged length identical; observations, rewards and post-states within 1e-5 relative of the
+    reference's doubles (in practice: their fp32 images); also the post-reset re-observation."""
+    z = np.load(path)
+    scn = ScenarioSet.from_dict(json.loads(str(z["scenario_json"])))
+    nm = int(z["nm"])
+    env = VecMdin(scn, 1, neighbors_num=nm)
+    T = z["action"].shape[0]
+    st = Stats()
+    n_inexact = 0
+    for t in range(T):
+        pre = {k: z["pre_" + k][t] for k in ("pos", "vel", "yaw", "pitch", "wp_idx", "arrive_flag", "dest_flag", "real_len", "max_dev", "extra_len")}
+        for k in ("pos", "vel", "yaw", "pitch", "real_len", "max_dev", "extra_len"):
+            assert np.array_equal(pre[k].astype(np.float32).astype(np.float64), pre[k]), (t, k)      # the fixture really is fp32-representable
+        assert np.array_equal(z["action"][t].astype(np.float32).astype(np.float64), z["action"][t])
+        env.set_state(pack_state(pre))
+        env.step(torch.from_numpy(z["action"][t].astype(np.float32)).cuda())
+        g = {k: getattr(env, k).cpu().numpy() for k in ("obs", "count", "reward", "done", "info", "finish")}
+        st.flag_mismatch += int((g["done"] != z["done"][t]).sum() + (g["finish"] != z["finish"][t]).sum() + (g["info"] != z["info"][t]).sum())
+        st.count_mismatch += int((g["count"] != z["count"][t]).sum())
+        st.add_obs(g["obs"], z["obs"][t]); st.add_rew(g["reward"], z["reward"][t])
+        post = unpack_state(env.get_state())
+        for k in ("pos", "vel", "yaw", "pitch", "real_len", "max_dev"):
+            st.add_state(post[k].astype(np.float32), z["post_" + k][t])
+        st.flag_mismatch += int((post["wp_idx"] != z["post_wp_idx"][t]).sum() + (post["arrive_flag"] != z["post_arrive_flag"][t]).sum() + (post["dest_flag"] != z["post_dest_flag"][t]).sum())
+        m = z["reset_mask"][t]
+        if m.any():      # reset + env_observation from the device's own fp32 post-state, as recorded
+            env.reset(torch.from_numpy(m.astype(np.uint8)).cuda())
+            st.add_obs(env.obs.cpu().numpy(), z["obs_after_reset"][t])
+            st.count_mismatch += int((env.count.cpu().numpy() != z["count_after_reset"][t]).sum())
+    env.close()
+    st.assert_parity(1e-5)
+    n_inexact = st.obs_inexact + st.rew_inexact
+    assert n_inexact <= 2, st.summary()       # (fp32 images of the reference's doubles, bit for bit, up to a libm ulp at a decimal tie)
+
+
 def test_rollout_equals_repeated_step_and_fused_autoreset():
     scn = swarm(12, 1.2, 9)
     E, nm, T = 40, 10, 30

@@ -58,7 +58,10 @@ def test_oracle_teacher_forced(path):
             assert close(o2, z["obs_after_reset"][t]) and np.array_equal(c2, z["count_after_reset"][t]), (t, "observe")
 
 
-@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
+FREE = [p for p in GOLDEN if not os.path.basename(p).startswith("f32_")]      # (the f32_ traces re-load a rounded state every step: not one free trajectory)
+
+
+@pytest.mark.parametrize("path", FREE, ids=[os.path.basename(p)[:-4] for p in FREE])
 def test_oracle_free_running(path):
     """No teacher forcing: the oracle reproduces the whole recorded trajectory from reset."""
     z, scn, nm = load(path)

@@ -425,6 +425,12 @@ class PPOTrainer:
         self.stats.update(rollout_s=t1 - t0, update_s=t2 - t1)
         return self.stats
 
+    def close(self):
+        """Drop the captured CUDA graphs.  With world_size > 1 the update graphs hold NCCL kernels: release them BEFORE
+        torch.distributed.destroy_process_group(), which otherwise waits on the communicator they still reference."""
+        self._upd = None; self._graph = None; self._graph_fast = None
+        torch.cuda.synchronize(self.dev)
+
     def save_model(self, path):
         """Same container as multi_ppo.save_model (multi_ppo.py:406-420): {'model_state', 'pi_optimizer', 'vf_optimizer'}."""
         F = self.flat

@@ -458,7 +458,6 @@ def measure_ppo(D, args, envs_per_gpu, epochs=1, warm=1):
         tr.train_epoch()
     D.barrier()
     torch.cuda.synchronize()
-    l0 = env.launch_count
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     ro = up = 0.0
@@ -476,8 +475,12 @@ def measure_ppo(D, args, envs_per_gpu, epochs=1, warm=1):
            "passes_per_sample": {"pi": tr.stats.get("pi_iters", 0) * min(cfg.minibatch, n) / n, "v": cfg.train_v_iters * min(cfg.minibatch, n) / n,
                                  "note": "the reference makes 50+50 FULL-BATCH passes over each robot's 300 samples (multi_ppo.py:355-376); here each iteration is one "
                                          "minibatch drawn without replacement from the whole [T x A] buffer -- samples/s is NOT a like-for-like ratio to the reference's"},
-           "policy": tr.policy_path, "update": tr.update_path, "gpu_launches_env": int(env.launch_count - l0),
+           "policy": tr.policy_path, "update": tr.update_path,
+           "gpu_launches_per_epoch": {"env (action transform, step, reset policy) + fused policy forward": 4 * cfg.steps_per_epoch, "gae": 1,
+                                      "clip/Adam (prepare + apply)": 2 * (cfg.train_pi_iters + cfg.train_v_iters), "policy repack": 1,
+                                      "note": "own kernels per epoch (graph replays included); the update's GEMMs are torch / cuBLAS"},
            "stats": {k: (float(v) if not isinstance(v, (int, float, str)) else v) for k, v in tr.stats.items()}}
+    tr.close()
     env.close()
     del tr
     torch.cuda.empty_cache()

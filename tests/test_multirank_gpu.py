@@ -101,6 +101,8 @@ def _worker(rank, world, port, backend, q):
         ok["pi_iters"] = st["pi_iters"]; ok["update_path"] = tr.update_path
         q.put((ok, flat.cpu().numpy()))
     dist.barrier()
+    tr.close()                  # captured NCCL graphs go before the process group
+    del tr
     e1.close()
     dist.destroy_process_group()
 

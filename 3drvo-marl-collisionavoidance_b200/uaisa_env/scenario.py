@@ -197,11 +197,29 @@ def scenario_world3() -> ScenarioSet:
     return ScenarioSet.from_start_end(starts, ends, (10, 10, 5))
 
 
-def scenario_c3(seed: int = 0, n_scenarios: int = 1, n_drones: int = 16, n_buildings: int = 8) -> ScenarioSet:
+def scenario_c3(seed: int = 0, n_scenarios: int = 1, n_drones: int = 16, n_buildings: int = 8, planned: bool = False) -> ScenarioSet:
     """configs[2]: N=16 on a ring of radius 4 about (5,5), z 5 -> antipodal goals at z 2, one or two
-    intermediate waypoints, M cylinders (x,y~U(2,8), h~U(3,5), r~U(0.5,1.0)) clear of every waypoint."""
+    intermediate waypoints, M cylinders (x,y~U(2,8), h~U(3,5), r~U(0.5,1.0)) clear of every waypoint.
+    planned=True: the same starts / goals / cylinder statistics, but the routes come from the offline Theta* planner
+    (uaisa_env.world.plan_scenario): obstacle-aware legs that keep 0.35 from every cylinder."""
     rng = np.random.default_rng(seed)
     out = []
+    if planned:
+        from .world import plan_scenario
+        for _ in range(n_scenarios):
+            ang = 2 * np.pi * (np.arange(n_drones) + rng.uniform(0, 1)) / n_drones
+            starts = np.round(np.stack([5 + 4 * np.cos(ang), 5 + 4 * np.sin(ang), np.full(n_drones, 4.0)], axis=1), 2)
+            ends = np.round(np.stack([5 - 4 * np.cos(ang), 5 - 4 * np.sin(ang), np.full(n_drones, 2.0)], axis=1), 2)
+            ends_all = np.concatenate([starts, ends])
+            bl = []
+            while len(bl) < n_buildings:
+                x, y = rng.uniform(2.5, 7.5, 2)
+                h, r = rng.uniform(3, 5), rng.uniform(0.4, 0.8)
+                if np.min(np.hypot(ends_all[:, 0] - x, ends_all[:, 1] - y)) < r + 0.8:
+                    continue
+                bl.append([round(float(x), 2), round(float(y), 2), round(float(h), 2), round(float(r), 2)])
+            out.append(plan_scenario(starts, ends, (10, 10, 5), buildings=bl))
+        return ScenarioSet.stack(out)
     for _ in range(n_scenarios):
         ang = 2 * np.pi * (np.arange(n_drones) + rng.uniform(0, 1)) / n_drones
         starts = np.stack([5 + 4 * np.cos(ang), 5 + 4 * np.sin(ang), np.full(n_drones, 5.0)], axis=1)

@@ -25,6 +25,12 @@ case $what in
     timeout 400 python -m pytest tests/test_multirank_gpu.py -m gpu -q --timeout 300 > gpurun_out/r2/tests_mr2.txt 2>&1; echo "mr2 rc=$?" | tee -a gpurun_out/r2/tests_mr2.txt; tail -20 gpurun_out/r2/tests_mr2.txt | cut -c1-300 ;;
   ptime)
     timeout 300 python profiles/policy_timing.py 262144 > gpurun_out/r2/policy_timing.txt 2>&1; cat gpurun_out/r2/policy_timing.txt | cut -c1-200 ;;
+  ncu_policy)   # launch list + one full capture of the fused policy forward (sparse and mixed batches)
+    for kind in sparse mixed; do
+      timeout 200 python profiles/prof_policy.py $kind > gpurun_out/r2/prof_policy_$kind.log 2>&1 && \
+      timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 20 --csv --log-file gpurun_out/r2/launches_policy_$kind.csv python profiles/prof_policy.py $kind > /dev/null 2>&1
+      timeout 400 ncu --set full --clock-control none --import-source on -k regex:uaisa_policy_forward -s 2 -c 1 -f -o gpurun_out/r2/prof_policy_$kind python profiles/prof_policy.py $kind > gpurun_out/r2/ncu_policy_$kind.log 2>&1; tail -2 gpurun_out/r2/ncu_policy_$kind.log
+    done ;;
   fma)
     ./profiles/fma_peak > gpurun_out/r2/fma_peak.json 2> gpurun_out/r2/fma_peak.err; cat gpurun_out/r2/fma_peak.json ;;
   bench)

@@ -12,7 +12,8 @@
 //   * weights are PRE-SWIZZLED on the device into the exact shared-memory image of each [rows x 32] tile (uaisa_policy_pack), so a weight tile is ONE
 //     bulk copy (cp.async.bulk global -> shared, the TMA engine; SASS UBLKCP) completing on an mbarrier.  One elected thread is producer and MMA issuer:
 //     a 2-stage ring (full / empty mbarriers, tcgen05.commit releases a stage) keeps the next two tiles in flight, also across the epilogues.
-//   * the 4 epilogue warps own one TMEM lane quarter each.
+//   * 512 threads: 4 threads share an agent row (same TMEM lane quarter, different warps) and split every epilogue by 16-unit blocks, so 16 warps hide
+//     the latency of the element-wise work (gates, LayerNorm, bias + ReLU), which is most of the kernel's instructions.
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -38,7 +39,7 @@ constexpr int FW_PACK_FLOATS = FW_OFF_B3 + 16;
 
 constexpr int FW_A_CHUNK = FW_M * 128;                           // bytes of one A chunk [128 rows x 32 fp32]
 constexpr int FW_STAGE = 256 * 128;                              // bytes of one B stage
-constexpr int FW_SMEM = 1024 + 9 * FW_A_CHUNK + 2 * FW_STAGE + 128;
+constexpr int FW_SMEM = 1024 + 9 * FW_A_CHUNK + 2 * FW_STAGE + 64 + 4 * 128 * 4 * 4;      // + barriers + row-reduction scratch [4][128][4] floats
 
 struct PackSrc {       // raw module parameters (device pointers), torch layouts
     const float *w_ih[2], *w_hh[2], *b_ih[2], *b_hh[2];          // GRU, [768][9] / [768][256] / [768] (gate order r, z, n); [1] = reverse direction
@@ -125,7 +126,12 @@ struct TileIter {
 __device__ __forceinline__ float sigm(float x) { return 1.0f / (1.0f + __expf(-x)); }
 __device__ __forceinline__ float tanh_fast(float x) { return 1.0f - 2.0f / (1.0f + __expf(2.0f * x)); }
 
-__global__ void __launch_bounds__(128, 1) uaisa_policy_forward_kernel(const __grid_constant__ FwdParams P) {
+// FW_S threads share one agent row (thread t, t + 128, ...: same TMEM lane, different warps): the 16-unit blocks of every epilogue are dealt round-robin to
+// them, so a CTA has 4 * FW_S warps to hide the latency of the element-wise work (gates, LayerNorm, bias + ReLU) that dominates the kernel's instruction count.
+constexpr int FW_S = 4;
+constexpr int FW_NT = FW_M * FW_S;
+
+__global__ void __launch_bounds__(FW_NT, 1) uaisa_policy_forward_kernel(const __grid_constant__ FwdParams P) {
     extern __shared__ unsigned char fw_smem_raw[];
     char *base = reinterpret_cast<char *>((reinterpret_cast<uintptr_t>(fw_smem_raw) + 1023) & ~uintptr_t(1023));   // SWIZZLE_128B needs 1024-byte alignment
     char *As = base;                                   // 9 chunks [128 x 32] fp32: chunks 0..7 = GRU state / features h / hidden activations, chunk 8 = x_t / self
@@ -133,8 +139,9 @@ __global__ void __launch_bounds__(128, 1) uaisa_policy_forward_kernel(const __gr
     uint64_t *bars = reinterpret_cast<uint64_t *>(Bs + 2 * FW_STAGE);   // full[2], empty[2], done
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 5);
     int *s_lmax = reinterpret_cast<int *>(tmem_slot + 1);
-    const int tid = threadIdx.x, warp = tid >> 5;
-    const int a0 = blockIdx.x * FW_M, a = a0 + tid;
+    float *s_red = reinterpret_cast<float *>(bars + 8);                 // [FW_S][128][4] partial sums of the row reductions (LayerNorm, output layer)
+    const int tid = threadIdx.x, warp = tid >> 5, row = tid & (FW_M - 1), sub = tid >> 7;
+    const int a0 = blockIdx.x * FW_M, a = a0 + row;
     const bool ok = a < P.A;
     const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[2]), done = smem_u32(&bars[4]);
 
@@ -148,7 +155,7 @@ __global__ void __launch_bounds__(128, 1) uaisa_policy_forward_kernel(const __gr
     int cnt = ok ? (int)P.count[a] : 0;
     cnt = cnt < P.nm ? cnt : P.nm;
     const int c_eff = cnt > 1 ? cnt : 1;               // an agent without neighbours feeds ONE zero row (ir_gym.py:211-212)
-    {
+    if (sub == 0) {
         const int wmax = __reduce_max_sync(0xffffffffu, c_eff);
         if ((tid & 31) == 0) atomicMax(s_lmax, wmax);
     }
@@ -157,7 +164,7 @@ __global__ void __launch_bounds__(128, 1) uaisa_policy_forward_kernel(const __gr
     fence_after_sync();
     const uint32_t tmem = *tmem_slot;
     const int lmax = *s_lmax;
-    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;      // a warp reaches the TMEM lane quarter (warp id % 4)
     const float *orow = P.obs + (size_t)(ok ? a : 0) * P.obs_dim;
     const float *wp = P.wp;
     uint32_t dpar = 0;                                 // parity of the `done` barrier (all threads)
@@ -190,48 +197,75 @@ __global__ void __launch_bounds__(128, 1) uaisa_policy_forward_kernel(const __gr
     auto group_done = [&]() { umma_commit(done); topup(); };               // (thread 0) accumulators ready -> `done`; next tiles stream during the epilogue
     auto wait_done = [&]() { mbar_wait(done, dpar); dpar ^= 1u; __syncwarp(); fence_after_sync(); };   // (warp 0 reconverges after thread 0's issue block: tcgen05.ld / st are .aligned)
     auto sync_smem_to_mma = [&]() { fence_proxy_async(); fence_before_sync(); __syncthreads(); fence_after_sync(); };
+    auto sync_tmem = [&]() { fence_before_sync(); __syncthreads(); fence_after_sync(); };
     constexpr uint32_t ID192 = umma_idesc_tf32(128, 192), ID128 = umma_idesc_tf32(128, 128), ID64 = umma_idesc_tf32(128, 64), ID256 = umma_idesc_tf32(128, 256);
 
-    // x_t of my row into the A tile of chunk 8 (9 values, zero padded to 32)
+    // x_t of my row into the A tile of chunk 8 (9 values, zero padded to 32): sub-thread 0 writes the values, the others the padding
     auto write_x = [&](int idx, bool valid) {
-        float x[12];
-#pragma unroll
-        for (int k = 0; k < 12; k++) x[k] = 0.0f;
-        if (valid && ok && idx < P.nm) {
-#pragma unroll
-            for (int k = 0; k < FW_IN; k++) x[k] = __ldg(orow + FW_SELF + FW_IN * idx + k);
-        }
         char *t8 = As + 8 * FW_A_CHUNK;
-        *swz(t8, tid, 0) = make_float4(x[0], x[1], x[2], x[3]); *swz(t8, tid, 1) = make_float4(x[4], x[5], x[6], x[7]);
-        *swz(t8, tid, 2) = make_float4(x[8], 0.f, 0.f, 0.f);
+        if (sub == 0) {
+            float x[12];
 #pragma unroll
-        for (int k4 = 3; k4 < 8; k4++) *swz(t8, tid, k4) = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int k = 0; k < 12; k++) x[k] = 0.0f;
+            if (valid && ok && idx < P.nm) {
+#pragma unroll
+                for (int k = 0; k < FW_IN; k++) x[k] = __ldg(orow + FW_SELF + FW_IN * idx + k);
+            }
+            *swz(t8, row, 0) = make_float4(x[0], x[1], x[2], x[3]); *swz(t8, row, 1) = make_float4(x[4], x[5], x[6], x[7]);
+            *swz(t8, row, 2) = make_float4(x[8], 0.f, 0.f, 0.f);
+        }
+        for (int k4 = 3 + sub; k4 < 8; k4 += FW_S) *swz(t8, row, k4) = make_float4(0.f, 0.f, 0.f, 0.f);
     };
+    auto ld4 = [&](const float *p, float *o) { const float4 f = __ldg(reinterpret_cast<const float4 *>(p)); o[0] = f.x; o[1] = f.y; o[2] = f.z; o[3] = f.w; };
+    auto ld16 = [&](const float *p, float *o) { ld4(p, o); ld4(p + 4, o + 4); ld4(p + 8, o + 8); ld4(p + 12, o + 12); };
     // gates of 16 hidden units [u0, u0+16) of direction `dir` from the accumulator columns at `dcol`: out = (1 - z) n + z h_old
     auto gates16 = [&](int dir, int u0, uint32_t dcol, int jb, bool has_h, const float *h_old, float *out) {
-        float r[16], z[16], gi[16], gh[16];
-        tmem_ld16(tmem + lane_base + dcol + jb * 16, r);
-        tmem_ld16(tmem + lane_base + dcol + 64 + jb * 16, z);
-        tmem_ld16(tmem + lane_base + dcol + 128 + jb * 16, gi);
-        if (has_h) tmem_ld16(tmem + lane_base + dcol + 192 + jb * 16, gh);
+        float r[16], z[16], gi[16], gh[16], b[16];
         const float *gb = wp + FW_OFF_GB + dir * 1024 + u0;
+        tmem_ld16(tmem + lane_base + dcol + jb * 16, r);
+        ld16(gb, b);
+#pragma unroll
+        for (int q = 0; q < 16; q++) r[q] = sigm(r[q] + b[q]);
+        tmem_ld16(tmem + lane_base + dcol + 64 + jb * 16, z);
+        ld16(gb + 256, b);
+#pragma unroll
+        for (int q = 0; q < 16; q++) z[q] = sigm(z[q] + b[q]);
+        ld16(gb + 768, b);
+        if (has_h) {
+            tmem_ld16(tmem + lane_base + dcol + 192 + jb * 16, gh);
+#pragma unroll
+            for (int q = 0; q < 16; q++) r[q] *= gh[q] + b[q];
+        } else {
+#pragma unroll
+            for (int q = 0; q < 16; q++) r[q] *= b[q];
+        }
+        tmem_ld16(tmem + lane_base + dcol + 128 + jb * 16, gi);
+        ld16(gb + 512, b);
 #pragma unroll
         for (int q = 0; q < 16; q++) {
-            const float rr = sigm(r[q] + __ldg(gb + q)), zz = sigm(z[q] + __ldg(gb + 256 + q));
-            const float hn = (has_h ? gh[q] : 0.0f) + __ldg(gb + 768 + q);
-            const float nn = tanh_fast(gi[q] + __ldg(gb + 512 + q) + rr * hn);
-            out[q] = (1.0f - zz) * nn + zz * (has_h ? h_old[q] : 0.0f);
+            const float nn = tanh_fast(gi[q] + b[q] + r[q]);
+            out[q] = (1.0f - z[q]) * nn + (has_h ? z[q] * h_old[q] : 0.0f);
         }
     };
     auto read_h16 = [&](int u0, float *h) {            // my row's state, units [u0, u0+16), from the swizzled A tile
         char *t = As + (u0 >> 5) * FW_A_CHUNK;
 #pragma unroll
-        for (int q4 = 0; q4 < 4; q4++) { const float4 f = *swz(t, tid, ((u0 & 31) >> 2) + q4); h[4 * q4] = f.x; h[4 * q4 + 1] = f.y; h[4 * q4 + 2] = f.z; h[4 * q4 + 3] = f.w; }
+        for (int q4 = 0; q4 < 4; q4++) { const float4 f = *swz(t, row, ((u0 & 31) >> 2) + q4); h[4 * q4] = f.x; h[4 * q4 + 1] = f.y; h[4 * q4 + 2] = f.z; h[4 * q4 + 3] = f.w; }
     };
     auto write_h16 = [&](int u0, const float *h) {
         char *t = As + (u0 >> 5) * FW_A_CHUNK;
 #pragma unroll
-        for (int q4 = 0; q4 < 4; q4++) *swz(t, tid, ((u0 & 31) >> 2) + q4) = make_float4(h[4 * q4], h[4 * q4 + 1], h[4 * q4 + 2], h[4 * q4 + 3]);
+        for (int q4 = 0; q4 < 4; q4++) *swz(t, row, ((u0 & 31) >> 2) + q4) = make_float4(h[4 * q4], h[4 * q4 + 1], h[4 * q4 + 2], h[4 * q4 + 3]);
+    };
+    // sum over the FW_S sub-threads of a row of up to 4 partial values (through shared memory)
+    auto row_reduce = [&](float *v, int n) {
+        for (int i = 0; i < n; i++) s_red[(sub * FW_M + row) * 4 + i] = v[i];
+        __syncthreads();
+        for (int i = 0; i < n; i++) { float t = 0.0f;
+#pragma unroll
+            for (int q = 0; q < FW_S; q++) t += s_red[(q * FW_M + row) * 4 + i];
+            v[i] = t; }
+        __syncthreads();
     };
 
     // =========================================================================================== bi-GRU reader
@@ -247,7 +281,7 @@ __global__ void __launch_bounds__(128, 1) uaisa_policy_forward_kernel(const __gr
             }
             wait_done();
 #pragma unroll 1
-            for (int jb = 0; jb < 4; jb++) {
+            for (int jb = sub; jb < 4; jb += FW_S) {
                 const int u0 = slice * 64 + jb * 16;
                 float hf[16], hb[16];
                 gates16(0, u0, 0, jb, false, nullptr, hf);
@@ -256,9 +290,7 @@ __global__ void __launch_bounds__(128, 1) uaisa_policy_forward_kernel(const __gr
                 for (int q = 0; q < 16; q++) hf[q] += hb[q];
                 write_h16(u0, hf);
             }
-            fence_before_sync();
-            __syncthreads();                           // the accumulators are free for the next slice
-            fence_after_sync();
+            sync_tmem();                               // the accumulators are free for the next slice
         }
     } else {
         float4 *stash = P.scratch + (size_t)blockIdx.x * 64 * FW_M;
@@ -269,7 +301,7 @@ __global__ void __launch_bounds__(128, 1) uaisa_policy_forward_kernel(const __gr
                 write_x(dir == 0 ? step : c_eff - 1 - step, active);
                 if (step > 0) {
 #pragma unroll 1
-                    for (int ub = 0; ub < 16; ub++) { float h[16]; tmem_ld16(tmem + lane_base + 256 + ub * 16, h); write_h16(ub * 16, h); }
+                    for (int ub = sub; ub < 16; ub += FW_S) { float h[16]; tmem_ld16(tmem + lane_base + 256 + ub * 16, h); write_h16(ub * 16, h); }
                 }
                 sync_smem_to_mma();
                 for (int slice = 0; slice < 4; slice++) {
@@ -288,7 +320,7 @@ __global__ void __launch_bounds__(128, 1) uaisa_policy_forward_kernel(const __gr
                     }
                     wait_done();
 #pragma unroll 1
-                    for (int jb = 0; jb < 4; jb++) {
+                    for (int jb = sub; jb < 4; jb += FW_S) {
                         const int u0 = slice * 64 + jb * 16;
                         float ho[16], hn[16];
                         if (step > 0) read_h16(u0, ho);
@@ -300,31 +332,27 @@ __global__ void __launch_bounds__(128, 1) uaisa_policy_forward_kernel(const __gr
                         tmem_st16(tmem + lane_base + 256 + u0, hn);
                     }
                     tmem_st_wait();
-                    fence_before_sync();
-                    __syncthreads();                   // accumulator columns free; the new state of this slice is in TMEM
-                    fence_after_sync();
+                    sync_tmem();                       // accumulator columns free; the new state of this slice is in TMEM
                 }
             }
             // ---- final state of this direction (TMEM columns 256..511)
             if (dir == 0) {
 #pragma unroll 1
-                for (int ub = 0; ub < 16; ub++) {
+                for (int ub = sub; ub < 16; ub += FW_S) {
                     float h[16]; tmem_ld16(tmem + lane_base + 256 + ub * 16, h);
 #pragma unroll
-                    for (int q4 = 0; q4 < 4; q4++) stash[(size_t)(ub * 4 + q4) * FW_M + tid] = make_float4(h[4 * q4], h[4 * q4 + 1], h[4 * q4 + 2], h[4 * q4 + 3]);
+                    for (int q4 = 0; q4 < 4; q4++) stash[(size_t)(ub * 4 + q4) * FW_M + row] = make_float4(h[4 * q4], h[4 * q4 + 1], h[4 * q4 + 2], h[4 * q4 + 3]);
                 }
             } else {
 #pragma unroll 1
-                for (int ub = 0; ub < 16; ub++) {
+                for (int ub = sub; ub < 16; ub += FW_S) {
                     float h[16]; tmem_ld16(tmem + lane_base + 256 + ub * 16, h);
 #pragma unroll
-                    for (int q4 = 0; q4 < 4; q4++) { const float4 f = stash[(size_t)(ub * 4 + q4) * FW_M + tid]; h[4 * q4] += f.x; h[4 * q4 + 1] += f.y; h[4 * q4 + 2] += f.z; h[4 * q4 + 3] += f.w; }
+                    for (int q4 = 0; q4 < 4; q4++) { const float4 f = stash[(size_t)(ub * 4 + q4) * FW_M + row]; h[4 * q4] += f.x; h[4 * q4 + 1] += f.y; h[4 * q4 + 2] += f.z; h[4 * q4 + 3] += f.w; }
                     write_h16(ub * 16, h);             // h_fwd + h_bwd (policy_rnn_ac.py:122, 163)
                 }
             }
-            fence_before_sync();
-            __syncthreads();
-            fence_after_sync();
+            sync_tmem();
         }
         if (P.stats && tid == 0) { atomicAdd(P.stats, 1); atomicMax(P.stats + 1, lmax); }
     }
@@ -333,44 +361,51 @@ __global__ void __launch_bounds__(128, 1) uaisa_policy_forward_kernel(const __gr
     {
         float self[FW_SELF];
 #pragma unroll
-        for (int k = 0; k < FW_SELF; k++) self[k] = ok ? __ldg(orow + k) : 0.0f;
-        float sum = 0.0f;
+        for (int k = 0; k < FW_SELF; k++) self[k] = (ok && sub == 0) ? __ldg(orow + k) : 0.0f;
+        float red[1] = {0.0f};
+        if (sub == 0) {
 #pragma unroll
-        for (int k = 0; k < FW_SELF; k++) sum += self[k];
+            for (int k = 0; k < FW_SELF; k++) red[0] += self[k];
+        }
 #pragma unroll 1
-        for (int ub = 0; ub < 16; ub++) { float h[16]; read_h16(ub * 16, h);
+        for (int ub = sub; ub < 16; ub += FW_S) { float h[16]; read_h16(ub * 16, h);
 #pragma unroll
-            for (int q = 0; q < 16; q++) sum += h[q]; }
-        const float mean = sum * (1.0f / FW_FEAT);
-        float ss = 0.0f;
+            for (int q = 0; q < 16; q++) red[0] += h[q]; }
+        row_reduce(red, 1);
+        const float mean = red[0] * (1.0f / FW_FEAT);
+        red[0] = 0.0f;
+        if (sub == 0) {
 #pragma unroll
-        for (int k = 0; k < FW_SELF; k++) ss += (self[k] - mean) * (self[k] - mean);
+            for (int k = 0; k < FW_SELF; k++) red[0] += (self[k] - mean) * (self[k] - mean);
+        }
 #pragma unroll 1
-        for (int ub = 0; ub < 16; ub++) { float h[16]; read_h16(ub * 16, h);
+        for (int ub = sub; ub < 16; ub += FW_S) { float h[16]; read_h16(ub * 16, h);
 #pragma unroll
-            for (int q = 0; q < 16; q++) ss += (h[q] - mean) * (h[q] - mean); }
-        const float rstd = rsqrtf(ss * (1.0f / FW_FEAT) + 1e-5f);                  // nn.LayerNorm: biased variance, eps 1e-5
+            for (int q = 0; q < 16; q++) red[0] += (h[q] - mean) * (h[q] - mean); }
+        row_reduce(red, 1);
+        const float rstd = rsqrtf(red[0] * (1.0f / FW_FEAT) + 1e-5f);                  // nn.LayerNorm: biased variance, eps 1e-5
         const float *lw = wp + FW_OFF_LN, *lb = lw + 288;
         float *fo = (P.feat_out && ok) ? P.feat_out + (size_t)a * FW_FEAT : nullptr;
 #pragma unroll 1
-        for (int ub = 0; ub < 16; ub++) {
-            float h[16]; read_h16(ub * 16, h);
+        for (int ub = sub; ub < 16; ub += FW_S) {
+            float h[16], w[16], b[16]; read_h16(ub * 16, h); ld16(lw + ub * 16, w); ld16(lb + ub * 16, b);
 #pragma unroll
-            for (int q = 0; q < 16; q++) h[q] = (h[q] - mean) * rstd * __ldg(lw + ub * 16 + q) + __ldg(lb + ub * 16 + q);
+            for (int q = 0; q < 16; q++) h[q] = (h[q] - mean) * rstd * w[q] + b[q];
             write_h16(ub * 16, h);
             if (fo) {
 #pragma unroll
                 for (int q = 0; q < 16; q++) fo[FW_SELF + ub * 16 + q] = h[q];
             }
         }
-        float sn[FW_SELF];
-#pragma unroll
-        for (int k = 0; k < FW_SELF; k++) { sn[k] = (self[k] - mean) * rstd * __ldg(lw + 256 + k) + __ldg(lb + 256 + k); if (fo) fo[k] = sn[k]; }
         char *t8 = As + 8 * FW_A_CHUNK;
-        *swz(t8, tid, 0) = make_float4(sn[0], sn[1], sn[2], sn[3]); *swz(t8, tid, 1) = make_float4(sn[4], sn[5], sn[6], sn[7]);
-        *swz(t8, tid, 2) = make_float4(sn[8], sn[9], sn[10], sn[11]);
+        if (sub == 0) {
+            float sn[FW_SELF];
 #pragma unroll
-        for (int k4 = 3; k4 < 8; k4++) *swz(t8, tid, k4) = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int k = 0; k < FW_SELF; k++) { sn[k] = (self[k] - mean) * rstd * __ldg(lw + 256 + k) + __ldg(lb + 256 + k); if (fo) fo[k] = sn[k]; }
+            *swz(t8, row, 0) = make_float4(sn[0], sn[1], sn[2], sn[3]); *swz(t8, row, 1) = make_float4(sn[4], sn[5], sn[6], sn[7]);
+            *swz(t8, row, 2) = make_float4(sn[8], sn[9], sn[10], sn[11]);
+        }
+        for (int k4 = 3 + sub; k4 < 8; k4 += FW_S) *swz(t8, row, k4) = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     sync_smem_to_mma();
 
@@ -388,10 +423,10 @@ __global__ void __launch_bounds__(128, 1) uaisa_policy_forward_kernel(const __gr
         // epilogue of layer 1: bias + ReLU -> A chunks 0..7 (the features are no longer needed)
         const float *b1 = wp + FW_OFF_B1 + head * 256;
 #pragma unroll 1
-        for (int ub = 0; ub < 16; ub++) {
-            float h[16]; tmem_ld16(tmem + lane_base + (head ? 256 : 0) + ub * 16, h);
+        for (int ub = sub; ub < 16; ub += FW_S) {
+            float h[16], b[16]; tmem_ld16(tmem + lane_base + (head ? 256 : 0) + ub * 16, h); ld16(b1 + ub * 16, b);
 #pragma unroll
-            for (int q = 0; q < 16; q++) h[q] = fmaxf(h[q] + __ldg(b1 + ub * 16 + q), 0.0f);
+            for (int q = 0; q < 16; q++) h[q] = fmaxf(h[q] + b[q], 0.0f);
             write_h16(ub * 16, h);
         }
         sync_smem_to_mma();
@@ -400,27 +435,34 @@ __global__ void __launch_bounds__(128, 1) uaisa_policy_forward_kernel(const __gr
             group_done();
         }
         wait_done();
-        // epilogue of layer 2: bias + ReLU, then the tiny output layer on the CUDA cores (row = thread)
+        // epilogue of layer 2: bias + ReLU, then the tiny output layer on the CUDA cores (partial dot products per sub-thread, summed through shared memory)
         const float *b2 = wp + FW_OFF_B2 + head * 256, *w3 = wp + FW_OFF_W3 + (head ? 768 : 0);
-        float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f;
+        float acc[3] = {0.f, 0.f, 0.f};
 #pragma unroll 1
-        for (int ub = 0; ub < 16; ub++) {
-            float h[16]; tmem_ld16(tmem + lane_base + ub * 16, h);
+        for (int ub = sub; ub < 16; ub += FW_S) {
+            float h[16], b[16], w[16]; tmem_ld16(tmem + lane_base + ub * 16, h); ld16(b2 + ub * 16, b);
 #pragma unroll
-            for (int q = 0; q < 16; q++) {
-                const float hq = fmaxf(h[q] + __ldg(b2 + ub * 16 + q), 0.0f);
-                acc0 = fmaf(hq, __ldg(w3 + ub * 16 + q), acc0);
-                if (!head) { acc1 = fmaf(hq, __ldg(w3 + 256 + ub * 16 + q), acc1); acc2 = fmaf(hq, __ldg(w3 + 512 + ub * 16 + q), acc2); }
+            for (int q = 0; q < 16; q++) h[q] = fmaxf(h[q] + b[q], 0.0f);
+            ld16(w3 + ub * 16, w);
+#pragma unroll
+            for (int q = 0; q < 16; q++) acc[0] = fmaf(h[q], w[q], acc[0]);
+            if (!head) {
+                ld16(w3 + 256 + ub * 16, w);
+#pragma unroll
+                for (int q = 0; q < 16; q++) acc[1] = fmaf(h[q], w[q], acc[1]);
+                ld16(w3 + 512 + ub * 16, w);
+#pragma unroll
+                for (int q = 0; q < 16; q++) acc[2] = fmaf(h[q], w[q], acc[2]);
             }
         }
-        if (ok) {
-            const float *b3 = wp + FW_OFF_B3;
-            if (!head) { P.mu[(size_t)a * 3] = tanhf(acc0 + __ldg(b3)); P.mu[(size_t)a * 3 + 1] = tanhf(acc1 + __ldg(b3 + 1)); P.mu[(size_t)a * 3 + 2] = tanhf(acc2 + __ldg(b3 + 2)); }
-            else P.v[a] = acc0 + __ldg(b3 + 3);
-        }
         fence_before_sync();
-        __syncthreads();                               // columns 0..255 fully read before the next head's layer 2 overwrites them
+        row_reduce(acc, head ? 1 : 3);                 // (its barriers also order the TMEM reads above before the next head's layer 2 overwrites columns 0..255)
         fence_after_sync();
+        if (ok && sub == 0) {
+            const float *b3 = wp + FW_OFF_B3;
+            if (!head) { P.mu[(size_t)a * 3] = tanhf(acc[0] + __ldg(b3)); P.mu[(size_t)a * 3 + 1] = tanhf(acc[1] + __ldg(b3 + 1)); P.mu[(size_t)a * 3 + 2] = tanhf(acc[2] + __ldg(b3 + 2)); }
+            else P.v[a] = acc[0] + __ldg(b3 + 3);
+        }
     }
     if (warp == 0) tmem_dealloc(tmem, 512u);
 }
@@ -461,7 +503,7 @@ int uaisa_policy_forward(const float *obs, const uint8_t *count, int32_t A, int3
     uaisa::FwdParams P{};
     P.obs = obs; P.count = count; P.A = A; P.obs_dim = obs_dim; P.nm = (obs_dim - uaisa::FW_SELF) / uaisa::FW_IN;
     P.wp = wpack; P.mu = mu; P.v = v; P.feat_out = feat_out; P.scratch = static_cast<float4 *>(scratch); P.stats = stats;
-    uaisa::uaisa_policy_forward_kernel<<<(A + uaisa::FW_M - 1) / uaisa::FW_M, 128, uaisa::FW_SMEM, static_cast<cudaStream_t>(stream)>>>(P);
+    uaisa::uaisa_policy_forward_kernel<<<(A + uaisa::FW_M - 1) / uaisa::FW_M, uaisa::FW_NT, uaisa::FW_SMEM, static_cast<cudaStream_t>(stream)>>>(P);
     return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 

@@ -123,8 +123,11 @@ struct TileIter {
     }
 };
 
-__device__ __forceinline__ float sigm(float x) { return 1.0f / (1.0f + __expf(-x)); }
-__device__ __forceinline__ float tanh_fast(float x) { return 1.0f - 2.0f / (1.0f + __expf(2.0f * x)); }
+// Gate non-linearities on the SFU: tanh.approx.f32 (one MUFU.TANH, max abs error 2^-10.99 ~ 4.9e-4) and sigmoid(x) = 0.5 tanh(x/2) + 0.5 (error 2.4e-4) --
+// the same order as the TF32 rounding of the GEMM operands that feed them (10-bit mantissa).  The exp-and-IEEE-divide forms were 48 % of the kernel's
+// executed instructions (profiles/r2/ncu_policy_forward_sparse.txt).
+__device__ __forceinline__ float tanh_fast(float x) { float y; asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float sigm(float x) { return fmaf(0.5f, tanh_fast(0.5f * x), 0.5f); }
 
 // FW_S threads share one agent row (thread t, t + 128, ...: same TMEM lane, different warps): the 16-unit blocks of every epilogue are dealt round-robin to
 // them, so a CTA has 4 * FW_S warps to hide the latency of the element-wise work (gates, LayerNorm, bias + ReLU) that dominates the kernel's instruction count.

@@ -31,6 +31,11 @@ case $what in
       timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 20 --csv --log-file gpurun_out/r2/launches_policy_$kind.csv python profiles/prof_policy.py $kind > /dev/null 2>&1
       timeout 400 ncu --set full --clock-control none --import-source on -k regex:uaisa_policy_forward -s 2 -c 1 -f -o gpurun_out/r2/prof_policy_$kind python profiles/prof_policy.py $kind > gpurun_out/r2/ncu_policy_$kind.log 2>&1; tail -2 gpurun_out/r2/ncu_policy_$kind.log
     done ;;
+  ncu_env)      # one full capture of a warm 8-step rollout launch of the dense env workloads
+    for w in c3 c4; do
+      timeout 200 python profiles/prof_rollout.py $w 8 > gpurun_out/r2/prof_env_$w.log 2>&1 && \
+      timeout 600 ncu --set full --clock-control none --import-source on -k regex:uaisa_env -s 3 -c 1 -f -o gpurun_out/r2/prof_env_$w python profiles/prof_rollout.py $w 8 > gpurun_out/r2/ncu_env_$w.log 2>&1; tail -2 gpurun_out/r2/ncu_env_$w.log
+    done ;;
   fma)
     ./profiles/fma_peak > gpurun_out/r2/fma_peak.json 2> gpurun_out/r2/fma_peak.err; cat gpurun_out/r2/fma_peak.json ;;
   bench)

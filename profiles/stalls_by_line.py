@@ -39,7 +39,7 @@ for (loc, _), r in zip(seq, data):
         byst[loc][hdr[c][6:]] += int(r[c] or 0)
 tot = sum(by.values()); toti = sum(byi.values())
 root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "3drvo-marl-collisionavoidance_b200", "csrc")
-src = {f: open(os.path.join(root, f)).read().split("\n") for f in ("uaisa_kernels.cu", "uaisa_kernels.cuh")}
+src = {f: open(os.path.join(root, f)).read().split("\n") for f in os.listdir(root) if f.endswith((".cu", ".cuh"))}
 print("kernel %s: %d samples, %d warp-instructions" % (kname, tot, toti))
 for loc, c in by.most_common(topn):
     top = ", ".join("%s %d" % kv for kv in byst[loc].most_common(3))

@@ -13,7 +13,7 @@ SYMBOLS = (
     "uaisa_set_scenarios", "uaisa_step", "uaisa_reset", "uaisa_observe", "uaisa_autoreset", "uaisa_rollout",
     "uaisa_get_state", "uaisa_set_state", "uaisa_cal_des", "uaisa_indicators", "uaisa_get_counters",
     "uaisa_launch_count", "uaisa_step_host", "uaisa_get_region_clocks", "uaisa_action_transform", "uaisa_gae", "uaisa_step_host_sparse", "uaisa_policy_features", "uaisa_policy_heads",
-    "uaisa_opt_partials_len", "uaisa_opt_prepare", "uaisa_clip_adam", "uaisa_rvo_select", "uaisa_policy_pack_floats", "uaisa_policy_pack", "uaisa_policy_forward",
+    "uaisa_opt_partials_len", "uaisa_opt_prepare", "uaisa_clip_adam", "uaisa_rvo_select", "uaisa_reader_fwd", "uaisa_reader_bwd", "uaisa_policy_pack_floats", "uaisa_policy_pack", "uaisa_policy_forward",
 )
 
 
@@ -79,6 +79,8 @@ def lib():
         L.uaisa_gae.argtypes = [vp, vp, vp, i32, i32, C.c_float, C.c_float, vp, vp, vp]
         L.uaisa_step_host.argtypes = [vp] * 9 + [i32, i32]
         L.uaisa_rvo_select.argtypes = [vp, C.c_double, C.c_double, vp, vp, vp]
+        L.uaisa_reader_fwd.argtypes = [vp, vp, i32, i32, vp, vp, vp, vp]
+        L.uaisa_reader_bwd.argtypes = [vp, vp, i32, i32, vp, vp, vp, vp, vp]
         L.uaisa_policy_pack_floats.restype = C.c_int
         L.uaisa_policy_pack.argtypes = [vp, vp, vp]
         L.uaisa_policy_forward.argtypes = [vp, vp, i32, i32, vp, vp, vp, vp, vp, vp, vp]

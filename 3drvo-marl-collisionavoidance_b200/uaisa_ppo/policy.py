@@ -31,6 +31,47 @@ def mlp(sizes, activation, output_activation=nn.Identity):   # policy_rnn_ac.py:
     return nn.Sequential(*layers)
 
 
+class _ReaderStep0(torch.autograd.Function):
+    """The reader for samples that all have <= 1 neighbour row as ONE forward and ONE backward kernel (csrc/uaisa_train.cu: uaisa_reader_fwd /
+    uaisa_reader_bwd): bi-GRU from h0 = 0, direction sum, concat, LayerNorm -- instead of ~60 element-wise / reduction launches over
+    [batch x 768] tensors.  fp32, same values and gradients as the torch ops below (tests/test_ppo_gpu.py).  `index` gathers rows of `obs` on the fly."""
+
+    @staticmethod
+    def forward(ctx, obs, index, *params):
+        import ctypes as C
+        from uaisa_env import _capi
+        L = _capi.lib()
+        B = int(index.shape[0]) if index is not None else int(obs.shape[0])
+        feat = torch.empty((B, 268), dtype=torch.float32, device=obs.device)
+        stats = torch.empty((B, 2), dtype=torch.float32, device=obs.device)
+        ptrs = (C.c_void_p * 8)(*[p.data_ptr() for p in params])
+        s = C.c_void_p(torch.cuda.current_stream(obs.device).cuda_stream)
+        rc = L.uaisa_reader_fwd(C.c_void_p(obs.data_ptr()), None if index is None else C.c_void_p(index.data_ptr()), B, int(obs.shape[1]), ptrs,
+                                C.c_void_p(feat.data_ptr()), C.c_void_p(stats.data_ptr()), s)
+        if rc:
+            raise RuntimeError("uaisa_reader_fwd failed (%d)" % rc)
+        ctx.save_for_backward(obs, index, stats, *params)
+        return feat
+
+    @staticmethod
+    def backward(ctx, dfeat):
+        import ctypes as C
+        from uaisa_env import _capi
+        L = _capi.lib()
+        obs, index, stats, *params = ctx.saved_tensors
+        B = int(stats.shape[0])
+        dfeat = dfeat.contiguous()
+        grads = [torch.zeros_like(p) for p in params]
+        ptrs = (C.c_void_p * 8)(*[p.data_ptr() for p in params])
+        gptrs = (C.c_void_p * 8)(*[g.data_ptr() for g in grads])
+        s = C.c_void_p(torch.cuda.current_stream(obs.device).cuda_stream)
+        rc = L.uaisa_reader_bwd(C.c_void_p(obs.data_ptr()), None if index is None else C.c_void_p(index.data_ptr()), B, int(obs.shape[1]), ptrs,
+                                C.c_void_p(dfeat.data_ptr()), C.c_void_p(stats.data_ptr()), gptrs, s)
+        if rc:
+            raise RuntimeError("uaisa_reader_bwd failed (%d)" % rc)
+        return (None, None, *grads)
+
+
 class rnn_Reader(nn.Module):   # policy_rnn_ac.py:75-168 (mode 'biGRU')
     def __init__(self, state_dim=12, input_dim=9, hidden_dim=256):
         super().__init__()
@@ -58,13 +99,25 @@ class rnn_Reader(nn.Module):   # policy_rnn_ac.py:75-168 (mode 'biGRU')
         r, z = torch.sigmoid(i_r + h_r), torch.sigmoid(i_z + h_z)
         return (1 - z) * torch.tanh(i_n + r * h_n)
 
-    def forward(self, obs: torch.Tensor, count: torch.Tensor, multi_cap: int = 0) -> torch.Tensor:
+    fused_step0 = True       # CUDA + multi_cap < 0: the single-step reader runs as one forward / one backward kernel (_ReaderStep0)
+
+    def _step0_params(self):
+        g = self.rnn_net
+        return (g.weight_ih_l0, g.bias_ih_l0, g.bias_hh_l0, g.weight_ih_l0_reverse, g.bias_ih_l0_reverse, g.bias_hh_l0_reverse, self.ln.weight, self.ln.bias)
+
+    def forward(self, obs: torch.Tensor, count: torch.Tensor, multi_cap: int = 0, index=None) -> torch.Tensor:
         """obs [B, 12+9nm] float32, count [B] (rows valid; 0 means one zero row) -> LayerNorm(cat(self, h_f + h_b)) [B, 268].
+        `index` (int64 [b]): evaluate rows obs[index] / count[index] (the fused single-step path gathers them inside the kernel).
 
         multi_cap = 0: agents with >= 2 rows are compacted with ``nonzero`` (exact for any input, one host sync).
         multi_cap = K > 0: static shapes and no host sync (CUDA-graph capturable): the K agents with the most rows go
         through the sequential part; exact as long as at most K agents have >= 2 rows -- ``self.overflow`` counts the
         agents that did not fit so the caller can check it once per epoch."""
+        if (multi_cap < 0 and self.fused_step0 and obs.is_cuda and obs.dtype == torch.float32 and obs.is_contiguous() and self.hidden_dim == 256
+                and self.state_dim == 12 and self.input_dim == 9 and all(p.is_contiguous() for p in self._step0_params())):
+            return _ReaderStep0.apply(obs, index, *self._step0_params())
+        if index is not None:
+            obs, count = obs[index], count[index]
         B = obs.shape[0]
         nm = (obs.shape[1] - self.state_dim) // self.input_dim
         self_state = obs[:, : self.state_dim]
@@ -125,13 +178,13 @@ class rnn_ac(nn.Module):   # policy_rnn_ac.py:31-72, defaults of train_process.p
         self.pi = GaussianActor(obs_dim, act_dim, hidden_sizes_ac, activation, output_activation, rnn)
         self.v = Critic(obs_dim, hidden_sizes_v, activation, output_activation_v, rnn)     # the reader is SHARED (:46-54)
 
-    def features(self, obs, count, multi_cap=0):
-        return self.pi.rnn_reader(obs, count, multi_cap)
+    def features(self, obs, count, multi_cap=0, index=None):
+        return self.pi.rnn_reader(obs, count, multi_cap, index)
 
-    def evaluate(self, obs, count, act=None, std_factor=1.0, multi_cap=0, heads="both"):
+    def evaluate(self, obs, count, act=None, std_factor=1.0, multi_cap=0, heads="both", index=None):
         """-> (Normal, value[B], logp[B] or None); one reader pass feeds both heads.  `heads` = "pi" / "v" skips the head an update
         iteration does not use (its forward would be thrown away): the skipped entry comes back as None."""
-        feat = self.features(obs, count, multi_cap)
+        feat = self.features(obs, count, multi_cap, index)
         dist = self.pi.distribution_from_features(feat, std_factor) if heads != "v" else None
         v = torch.squeeze(self.v.v_net(feat), -1) if heads != "pi" else None
         logp = dist.log_prob(act).sum(-1) if (act is not None and dist is not None) else None

@@ -265,7 +265,7 @@ class PPOTrainer:
         idx = self._next_idx()
         w = self._ok[idx].float()
         wsum = w.sum().clamp(min=1)
-        _, _, logp = self.ac.evaluate(self._obs[idx], self._cnt[idx], self._act[idx], multi_cap=u["cap"], heads="pi")
+        _, _, logp = self.ac.evaluate(self._obs, self._cnt, self._act[idx], multi_cap=u["cap"], heads="pi", index=idx)
         lo = self._logp_old[idx]
         ratio = torch.exp(logp - lo)
         a_ = torch.nan_to_num(self._adv[idx], 0.0, 0.0, 0.0)
@@ -291,7 +291,7 @@ class PPOTrainer:
         F.g[:F.v_hi].zero_()                                       # vf_optimizer.zero_grad()
         idx = self._next_idx()
         w = self._ok[idx].float()
-        _, v, _ = self.ac.evaluate(self._obs[idx], self._cnt[idx], None, multi_cap=u["cap"], heads="v")
+        _, v, _ = self.ac.evaluate(self._obs, self._cnt, None, multi_cap=u["cap"], heads="v", index=idx)
         loss = (((v - torch.nan_to_num(self._ret[idx], 0.0, 0.0, 0.0)) ** 2) * w).sum() / w.sum().clamp(min=1)
         (loss / W).backward()
         u["loss_v"].copy_(loss.detach())
@@ -368,6 +368,8 @@ class PPOTrainer:
         permutation of the epoch's T x A samples (without replacement).  `PPOConfig.passes` > 0 makes the iteration count cover the
         buffer that many times (ceil(passes * n / minibatch) iterations per head) instead of train_pi_iters / train_v_iters."""
         cfg = self.cfg
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]      # device-side split of the update: prepare | policy iterations | value iterations
+        ev[0].record()
         n, mb = self._begin_update(adv, ret)
         u = self._u
         n_pi = cfg.train_pi_iters if cfg.passes <= 0 else int(-(-cfg.passes * n // mb))
@@ -390,21 +392,27 @@ class PPOTrainer:
             graphed = bool(self._upd)
         else:
             u["cap"] = 0 if multi else -1
+        ev[1].record()
         if graphed:
             g1, g2 = self._upd
             for _ in range(n_pi):
                 g1.replay()
+            ev[2].record()
             for _ in range(n_v):
                 g2.replay()
         else:
             for _ in range(n_pi):
                 self._pi_iter()
+            ev[2].record()
             for _ in range(n_v):
                 self._v_iter()
+        ev[3].record()
         if self.fused is not None:
             self.fused.refresh()          # repack the updated weights in place (addresses stay fixed: the captured rollout step stays valid)
         ctl = self._ctl.tolist()          # the update's only host read: iterations applied / early-stop latch
-        self.update_path = ("CUDA graph per iteration" if graphed else "eager iterations") + "; torch autograd GEMMs (cuBLAS) + flat-bucket all-reduce + fused clip/Adam kernel"
+        self.update_path = (("CUDA graph per iteration" if graphed else "eager iterations") + "; " + ("reader forward/backward kernels (uaisa_reader_fwd/bwd) + " if u["cap"] < 0 and self.ac.pi.rnn_reader.fused_step0 else "")
+                            + "torch autograd GEMMs for the MLPs (cuBLAS) + flat-bucket all-reduce + fused clip/Adam kernel")
+        self.stats.update(update_prepare_ms=ev[0].elapsed_time(ev[1]), update_pi_ms=ev[1].elapsed_time(ev[2]), update_v_ms=ev[2].elapsed_time(ev[3]))
         self.stats.update(pi_iters=int(ctl[1]), early_stop=bool(ctl[0]), loss_v=float(u["loss_v"]), kl=float(self.flat.g[self.flat.n]), loss_pi=float(self.flat.g[self.flat.n + 1]),
                           passes_pi=ctl[1] * mb / n, passes_v=n_v * mb / n, mean_ret=float(torch.nan_to_num(self._ret, 0.0, 0.0, 0.0).mean()))
         return self.stats

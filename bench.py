@@ -461,15 +461,17 @@ def measure_ppo(D, args, envs_per_gpu, epochs=1, warm=1):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     ro = up = 0.0
+    per_epoch = []
     for _ in range(epochs):
         st = tr.train_epoch(); ro += st["rollout_s"]; up += st["update_s"]
+        per_epoch.append({k: round(float(st[k]), 4) for k in ("rollout_s", "update_s", "update_prepare_ms", "update_pi_ms", "update_v_ms") if k in st})
     e1.record(); torch.cuda.synchronize()
     D.barrier()
     ms_max, _ = D.max_min(e0.elapsed_time(e1))
     samples = D.world * env.A * cfg.steps_per_epoch * epochs
     n = env.A * cfg.steps_per_epoch
     out = {"metric": "PPO samples/sec (rollout + GAE + update)", "value": samples / (ms_max * 1e-3), "unit": "samples/s", "epochs_timed": epochs, "epochs_warmup": warm,
-           "ms_per_epoch": ms_max / epochs, "rollout_s_per_epoch": ro / epochs, "update_s_per_epoch": up / epochs, "dtype": "tf32" if args.tf32 else "f32",
+           "ms_per_epoch": ms_max / epochs, "rollout_s_per_epoch": ro / epochs, "update_s_per_epoch": up / epochs, "per_epoch": per_epoch, "dtype": "tf32" if args.tf32 else "f32",
            "workload": "configs[4]: %d envs x 4 drones per GPU x %d GPUs, %d steps/epoch, rnn_ac 680991 params, reference PPO hyper-parameters" % (envs_per_gpu, D.world, cfg.steps_per_epoch),
            "minibatch": cfg.minibatch, "pi_iters": cfg.train_pi_iters, "v_iters": cfg.train_v_iters,
            "passes_per_sample": {"pi": tr.stats.get("pi_iters", 0) * min(cfg.minibatch, n) / n, "v": cfg.train_v_iters * min(cfg.minibatch, n) / n,

@@ -205,6 +205,16 @@ int uaisa_opt_prepare(const float *g, int64_t n, int32_t want_norm, double *part
 int uaisa_clip_adam(float *p, float *g, float *m, float *v, int64_t n_total, int64_t r_off, int64_t r_cnt, const double *partials,
                     float max_norm, float lr, float beta1, float beta2, float eps, const int32_t *step, const int32_t *ctl, void *stream);
 
+/* Reader forward / backward for update minibatches whose samples all have <= 1 neighbour row (rnn_Reader.obs_rnn_list with L = 1, policy_rnn_ac.py:129-168:
+ * the bi-GRU from h0 = 0 -- W_hh never enters --, the sum of both directions, the concat with the 12 self values, LayerNorm(268)) and their gradients, fp32.
+ * params / grads: 8 DEVICE pointers in torch layouts: weight_ih_l0 [768][9], bias_ih_l0 [768], bias_hh_l0 [768], the same three of the reverse direction,
+ * ln.weight [268], ln.bias [268].  obs [*][obs_dim]; idx (may be NULL): int64[B], the row of `obs` each sample reads (the minibatch is never materialised);
+ * feat / dfeat [B][268]; stats [B][2] (LayerNorm mean and rstd, saved by the forward for the backward).  uaisa_reader_bwd ADDS this minibatch's gradients to
+ * `grads`.  Asynchronous on `stream`, capturable in a CUDA graph. */
+int uaisa_reader_fwd(const float *obs, const int64_t *idx, int32_t B, int32_t obs_dim, const float *const *params, float *feat, float *stats, void *stream);
+int uaisa_reader_bwd(const float *obs, const int64_t *idx, int32_t B, int32_t obs_dim, const float *const *params, const float *dfeat, const float *stats,
+                     float *const *grads, void *stream);
+
 /* ---- latency-optimised host round trip ------------------------------------------------------------------------
  * One env step with HOST action in / HOST results out, returned in the reference's own ragged spirit: the 12 self
  * values of every observation plus only the neighbour rows that exist (an observation is 12 + 9*max(k,1) values in

@@ -36,6 +36,9 @@ case $what in
       timeout 200 python profiles/prof_rollout.py $w 8 > gpurun_out/r2/prof_env_$w.log 2>&1 && \
       timeout 600 ncu --set full --clock-control none --import-source on -k regex:uaisa_env -s 3 -c 1 -f -o gpurun_out/r2/prof_env_$w python profiles/prof_rollout.py $w 8 > gpurun_out/r2/ncu_env_$w.log 2>&1; tail -2 gpurun_out/r2/ncu_env_$w.log
     done ;;
+  ppo)
+    timeout 600 python bench.py --workload ppo --ppo-epochs 3 > gpurun_out/r2/bench_ppo.json 2> gpurun_out/r2/bench_ppo.err; tail -3 gpurun_out/r2/bench_ppo.err; python -c "
+import json;d=json.loads([l for l in open('gpurun_out/r2/bench_ppo.json') if l.startswith('{')][-1]);print(d['value']);print(d['ppo']['per_epoch'])" ;;
   fma)
     ./profiles/fma_peak > gpurun_out/r2/fma_peak.json 2> gpurun_out/r2/fma_peak.err; cat gpurun_out/r2/fma_peak.json ;;
   bench)

@@ -229,3 +229,47 @@ def test_fused_forward_logp_and_value_are_close_to_the_update_path():
     assert float((logp - logp_t).abs().max()) < 2e-2 and float((logp - logp_t).abs().mean()) < 3e-3
     assert float((v - v_t).abs().max()) < 2e-2
     env.close()
+
+
+def test_fused_reader_forward_backward_matches_torch_autograd():
+    """uaisa_reader_fwd / uaisa_reader_bwd (the reader of update minibatches without multi-row samples as one forward and one backward kernel, with the
+    minibatch gathered inside the kernel) against the torch ops they replace: features to 1e-5, every parameter gradient to 1e-4 of its scale."""
+    from uaisa_ppo.policy import rnn_ac
+
+    torch.manual_seed(3)
+    ac = rnn_ac().cuda()
+    rd = ac.pi.rnn_reader
+    rng = np.random.default_rng(2)
+    n, B = 5000, 3111
+    obs = np.zeros((n, 102), np.float32)
+    obs[:, :12] = np.round(rng.normal(0, 4, (n, 12)), 2); obs[:, 0:3] += 15
+    cnt = (rng.uniform(0, 1, n) < 0.4).astype(np.uint8)
+    obs[:, 12:21] = np.round(rng.normal(0, 2, (n, 9)), 2) * cnt[:, None]
+    o, c = torch.from_numpy(obs).cuda(), torch.from_numpy(cnt).cuda()
+    idx = torch.from_numpy(rng.integers(0, n, B)).cuda()
+    wgt = torch.from_numpy(rng.normal(0, 1, (B, 268)).astype(np.float32)).cuda()
+    res = {}
+    for fused in (False, True):
+        rd.fused_step0 = fused
+        ac.zero_grad(set_to_none=True)
+        feat = ac.features(o, c, multi_cap=-1, index=idx)
+        assert (feat.grad_fn is not None) and (("ReaderStep0" in type(feat.grad_fn).__name__) == fused)
+        (feat * wgt).sum().backward()
+        res[fused] = (feat.detach().clone(), {k: p.grad.detach().clone() for k, p in rd.named_parameters() if p.grad is not None})
+    rd.fused_step0 = True
+    assert torch.allclose(res[True][0], res[False][0], rtol=1e-5, atol=2e-5), float((res[True][0] - res[False][0]).abs().max())
+    assert set(res[True][1]) >= set(res[False][1])
+    for k, g_ref in res[False][1].items():
+        g = res[True][1][k]
+        scale = float(g_ref.abs().max())
+        assert float((g - g_ref).abs().max()) <= 2e-4 * scale + 1e-6, (k, float((g - g_ref).abs().max()), scale)
+    # weight_hh never enters a single step from h0 = 0: no gradient (torch) / zero gradient (kernel)
+    for k, g in res[True][1].items():
+        if "weight_hh" in k:
+            assert float(g.abs().max()) == 0.0
+    # without an index: all rows
+    f1 = ac.features(o, c, multi_cap=-1)
+    rd.fused_step0 = False
+    f0 = ac.features(o, c, multi_cap=-1)
+    rd.fused_step0 = True
+    assert torch.allclose(f1, f0, rtol=1e-5, atol=2e-5)

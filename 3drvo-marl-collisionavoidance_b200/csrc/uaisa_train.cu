@@ -115,7 +115,7 @@ int uaisa_clip_adam(float *p, float *g, float *m, float *v, int64_t n_total, int
 // Reader forward / backward for update minibatches whose samples all have <= 1 neighbour row (the captured-graph path of the PPO update): the
 // bi-GRU from h0 = 0 (policy_rnn_ac.py:102-127 with L = 1: W_hh never enters), the sum of both directions, the concat with the 12 self values and
 // LayerNorm(268) -- and their gradients -- in two kernels instead of ~60 element-wise / reduction launches over [minibatch x 768] tensors, which were
-// 70 % of an update iteration.  fp32 on the CUDA cores with the accurate expf / tanhf (the update keeps the reference's precision).
+// 70 % of an update iteration.  fp32 on the CUDA cores (the update keeps the reference's precision: 1e-5 on the features against the torch ops, tests/test_ppo_gpu.py).
 // Parameters are read in torch's own layouts (weight_ih [768][9] gate-major r|z|n, bias_ih / bias_hh [768]); gradients are ACCUMULATED (atomicAdd) into
 // caller buffers of the same layouts.  `idx` (optional) gathers rows of `obs` on the fly, so the minibatch is never materialised.
 namespace uaisa {
@@ -129,146 +129,159 @@ struct ReaderG {
     float *w_ih[2], *b_ih[2], *b_hh[2], *ln_w, *ln_b;
 };
 
-__device__ __forceinline__ float rd_sig(float x) { return 1.0f / (1.0f + expf(-x)); }
+// exp on the SFU (2 ulp) + fast division: absolute error ~1e-7 on sigmoid / tanh, far inside fp32 training noise; the IEEE divide and libm expf / tanhf
+// forms were most of these kernels' instructions
+__device__ __forceinline__ float rd_sig(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float rd_tanh(float x) { return 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * x)); }
 
-// one warp per sample: lane l owns hidden units l, l+32, ..., l+224 and (l < 12) self value l
-__global__ void __launch_bounds__(256) uaisa_reader_fwd_kernel(const float *__restrict__ obs, const long long *__restrict__ idx, int B, int obs_dim, ReaderW W,
-                                                                 float *__restrict__ feat, float *__restrict__ stats) {
-    const int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (s >= B) return;
-    const float *o = obs + (size_t)(idx ? idx[s] : s) * obs_dim;
-    float x[RD_IN];
+// Both kernels use the same mapping.  A CTA of 512 threads walks tiles of RB_T samples; thread = (direction d, hidden unit u) keeps ITS 27 input weights
+// and 4 biases in registers, the tile's x rows (9 values each) are broadcast from shared memory:
+//   gates phase   every thread evaluates r, z, n of its unit for each sample of the tile (K = 9) and leaves h = (1 - z) n in shared memory
+//   row phase     one warp per sample: direction sum, concat with the 12 self values, LayerNorm statistics (forward: writes the features; backward: the
+//                 LayerNorm backward -> dh[256], and dfeat * xhat for the LayerNorm weight gradient)
+//   (backward)    gradient phase: thread = (d, u) again, gates recomputed, 27 weight + 4 bias gradients accumulated in registers over ALL the CTA's tiles;
+//                 threads < 268 accumulate the LayerNorm weight / bias gradients; one atomicAdd per value per CTA at the end.
+constexpr int RB_T = 15;      // (the backward kernel fits the 48 KB of static shared memory with 15)
+
+struct ReaderThread {                 // thread (d, u): its weights, biases
+    float wv[3][RD_IN], br, bz, bn, bhn;
+    __device__ __forceinline__ void load(const ReaderW &W, int d, int u) {
 #pragma unroll
-    for (int k = 0; k < RD_IN; k++) x[k] = (obs_dim >= RD_SELF + RD_IN) ? __ldg(o + RD_SELF + k) : 0.0f;
-    float h[8];
+        for (int g = 0; g < 3; g++)
 #pragma unroll
-    for (int i = 0; i < 8; i++) {
-        const int u = lane + 32 * i;
-        float hs = 0.0f;
-#pragma unroll
-        for (int d = 0; d < 2; d++) {
-            float ar = __ldg(W.b_ih[d] + u) + __ldg(W.b_hh[d] + u), az = __ldg(W.b_ih[d] + 256 + u) + __ldg(W.b_hh[d] + 256 + u), an = __ldg(W.b_ih[d] + 512 + u);
-            const float *wr = W.w_ih[d] + (size_t)u * RD_IN, *wz = wr + 256 * RD_IN, *wn = wr + 512 * RD_IN;
-#pragma unroll
-            for (int k = 0; k < RD_IN; k++) { ar = fmaf(x[k], __ldg(wr + k), ar); az = fmaf(x[k], __ldg(wz + k), az); an = fmaf(x[k], __ldg(wn + k), an); }
-            const float r = rd_sig(ar), z = rd_sig(az), n = tanhf(an + r * __ldg(W.b_hh[d] + 512 + u));
-            hs += (1.0f - z) * n;
-        }
-        h[i] = hs;
+            for (int k = 0; k < RD_IN; k++) wv[g][k] = __ldg(W.w_ih[d] + (size_t)(g * 256 + u) * RD_IN + k);
+        br = __ldg(W.b_ih[d] + u) + __ldg(W.b_hh[d] + u); bz = __ldg(W.b_ih[d] + 256 + u) + __ldg(W.b_hh[d] + 256 + u);
+        bn = __ldg(W.b_ih[d] + 512 + u); bhn = __ldg(W.b_hh[d] + 512 + u);
     }
-    const float sv = (lane < RD_SELF) ? __ldg(o + lane) : 0.0f;
-    float sum = sv;
+    __device__ __forceinline__ void gates(const float *x, float &r, float &z, float &n) const {
+        float ar = br, az = bz, an = bn;
 #pragma unroll
-    for (int i = 0; i < 8; i++) sum += h[i];
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
-    const float mean = sum * (1.0f / RD_FEAT);
-    float ss = (lane < RD_SELF) ? (sv - mean) * (sv - mean) : 0.0f;
-#pragma unroll
-    for (int i = 0; i < 8; i++) ss += (h[i] - mean) * (h[i] - mean);
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, off);
-    const float rstd = rsqrtf(ss * (1.0f / RD_FEAT) + 1e-5f);
-    float *f = feat + (size_t)s * RD_FEAT;
-    if (lane < RD_SELF) f[lane] = (sv - mean) * rstd * __ldg(W.ln_w + lane) + __ldg(W.ln_b + lane);
-#pragma unroll
-    for (int i = 0; i < 8; i++) { const int q = RD_SELF + lane + 32 * i; f[q] = (h[i] - mean) * rstd * __ldg(W.ln_w + q) + __ldg(W.ln_b + q); }
-    if (lane == 0) { stats[2 * s] = mean; stats[2 * s + 1] = rstd; }
+        for (int k = 0; k < RD_IN; k++) { ar = fmaf(x[k], wv[0][k], ar); az = fmaf(x[k], wv[1][k], az); an = fmaf(x[k], wv[2][k], an); }
+        r = rd_sig(ar); z = rd_sig(az); n = rd_tanh(an + r * bhn);
+    }
+};
+
+// x rows of a tile -> shared memory (threads 0 .. ns*9-1), zero if the observation has no neighbour slot
+__device__ __forceinline__ void load_x_tile(float (*s_x)[RD_IN + 3], const float *obs, const long long *idx, int obs_dim, int s0, int ns, int tid) {
+    if (tid < ns * RD_IN) {
+        const int j = tid / RD_IN, k = tid - j * RD_IN;
+        const float *o = obs + (size_t)(idx ? idx[s0 + j] : s0 + j) * obs_dim;
+        s_x[j][k] = (obs_dim >= RD_SELF + RD_IN) ? __ldg(o + RD_SELF + k) : 0.0f;
+    }
 }
 
-// Backward.  A CTA (512 threads) walks tiles of RB_T samples:  phase 1, one warp per sample: recompute the pre-LayerNorm vector, LayerNorm backward (two row
-// reductions) -> dh[256] and xhat * dfeat / dfeat contributions, staged in shared memory;  phase 2, thread = (direction, hidden unit): loop over the tile's
-// samples, recompute the three gates from x (K = 9) and accumulate the 27 weight and 4 bias gradients in registers; threads < 268 accumulate the LayerNorm
-// weight / bias gradients.  After its last tile the CTA adds its accumulators to the global gradient buffers (one atomicAdd per value per CTA).
-constexpr int RB_T = 16;
+__global__ void __launch_bounds__(512) uaisa_reader_fwd_kernel(const float *__restrict__ obs, const long long *__restrict__ idx, int B, int obs_dim, ReaderW W,
+                                                                 float *__restrict__ feat, float *__restrict__ stats) {
+    __shared__ float s_x[RB_T][RD_IN + 3];
+    __shared__ float s_h[RB_T][2][RD_H];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, d = tid >> 8, u = tid & 255;
+    ReaderThread T; T.load(W, d, u);
+    const int n_tiles = (B + RB_T - 1) / RB_T;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int s0 = tile * RB_T, ns = min(RB_T, B - s0);
+        load_x_tile(s_x, obs, idx, obs_dim, s0, ns, tid);
+        __syncthreads();
+        for (int j = 0; j < ns; j++) {
+            float x[RD_IN];
+#pragma unroll
+            for (int k = 0; k < RD_IN; k++) x[k] = s_x[j][k];
+            float r, z, n; T.gates(x, r, z, n);
+            s_h[j][d][u] = (1.0f - z) * n;
+        }
+        __syncthreads();
+        if (warp < ns) {                                   // row phase: warp j = sample s0 + j; lane l owns units l, l+32, ... and (l < 12) self value l
+            const int j = warp, s = s0 + j;
+            const float *o = obs + (size_t)(idx ? idx[s] : s) * obs_dim;
+            float h[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) h[i] = s_h[j][0][lane + 32 * i] + s_h[j][1][lane + 32 * i];
+            const float sv = (lane < RD_SELF) ? __ldg(o + lane) : 0.0f;
+            float sum = sv;
+#pragma unroll
+            for (int i = 0; i < 8; i++) sum += h[i];
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+            const float mean = sum * (1.0f / RD_FEAT);
+            float ss = (lane < RD_SELF) ? (sv - mean) * (sv - mean) : 0.0f;
+#pragma unroll
+            for (int i = 0; i < 8; i++) ss += (h[i] - mean) * (h[i] - mean);
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, off);
+            const float rstd = rsqrtf(ss * (1.0f / RD_FEAT) + 1e-5f);          // nn.LayerNorm: biased variance, eps 1e-5
+            float *f = feat + (size_t)s * RD_FEAT;
+            if (lane < RD_SELF) f[lane] = (sv - mean) * rstd * __ldg(W.ln_w + lane) + __ldg(W.ln_b + lane);
+#pragma unroll
+            for (int i = 0; i < 8; i++) { const int q = RD_SELF + lane + 32 * i; f[q] = (h[i] - mean) * rstd * __ldg(W.ln_w + q) + __ldg(W.ln_b + q); }
+            if (lane == 0) { stats[2 * s] = mean; stats[2 * s + 1] = rstd; }
+        }
+        __syncthreads();
+    }
+}
+
 __global__ void __launch_bounds__(512) uaisa_reader_bwd_kernel(const float *__restrict__ obs, const long long *__restrict__ idx, int B, int obs_dim, ReaderW W,
                                                                  const float *__restrict__ dfeat, const float *__restrict__ stats, ReaderG G) {
     __shared__ float s_x[RB_T][RD_IN + 3];           // x of the tile's samples
-    __shared__ float s_dh[RB_T][RD_H];               // d loss / d (h_fwd + h_bwd)
+    __shared__ float s_h[RB_T][2][RD_H];             // gates phase: h per direction; row phase overwrites [j][0][.] with d loss / d (h_fwd + h_bwd)
     __shared__ float s_gw[RB_T][RD_FEAT];            // dfeat * xhat  (LayerNorm weight gradient terms)
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int d = tid >> 8, u = tid & 255;           // phase-2 identity
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, d = tid >> 8, u = tid & 255;
+    ReaderThread T; T.load(W, d, u);
     float aw[3][RD_IN], ab[4], alw = 0.0f, alb = 0.0f;
 #pragma unroll
     for (int g = 0; g < 3; g++)
 #pragma unroll
         for (int k = 0; k < RD_IN; k++) aw[g][k] = 0.0f;
     ab[0] = ab[1] = ab[2] = ab[3] = 0.0f;
-    // this thread's weights (phase 2)
-    float wv[3][RD_IN];
-#pragma unroll
-    for (int g = 0; g < 3; g++)
-#pragma unroll
-        for (int k = 0; k < RD_IN; k++) wv[g][k] = __ldg(W.w_ih[d] + (size_t)(g * 256 + u) * RD_IN + k);
-    const float br = __ldg(W.b_ih[d] + u) + __ldg(W.b_hh[d] + u), bz = __ldg(W.b_ih[d] + 256 + u) + __ldg(W.b_hh[d] + 256 + u), bn = __ldg(W.b_ih[d] + 512 + u),
-                bhn = __ldg(W.b_hh[d] + 512 + u);
     const int n_tiles = (B + RB_T - 1) / RB_T;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int s0 = tile * RB_T, ns = min(RB_T, B - s0);
-        // ---- phase 1: 16 warps, one sample each
-        for (int j = warp; j < ns; j += 16) {
-            const int s = s0 + j;
-            const float *o = obs + (size_t)(idx ? idx[s] : s) * obs_dim;
+        load_x_tile(s_x, obs, idx, obs_dim, s0, ns, tid);
+        __syncthreads();
+        for (int j = 0; j < ns; j++) {                     // gates phase
             float x[RD_IN];
 #pragma unroll
-            for (int k = 0; k < RD_IN; k++) x[k] = (obs_dim >= RD_SELF + RD_IN) ? __ldg(o + RD_SELF + k) : 0.0f;
-            if (lane < RD_IN) s_x[j][lane] = x[lane];
-            float h[8];
-#pragma unroll
-            for (int i = 0; i < 8; i++) {
-                const int uu = lane + 32 * i;
-                float hs = 0.0f;
-#pragma unroll
-                for (int dd = 0; dd < 2; dd++) {
-                    float ar = __ldg(W.b_ih[dd] + uu) + __ldg(W.b_hh[dd] + uu), az = __ldg(W.b_ih[dd] + 256 + uu) + __ldg(W.b_hh[dd] + 256 + uu), an = __ldg(W.b_ih[dd] + 512 + uu);
-                    const float *wr = W.w_ih[dd] + (size_t)uu * RD_IN, *wz = wr + 256 * RD_IN, *wn = wr + 512 * RD_IN;
-#pragma unroll
-                    for (int k = 0; k < RD_IN; k++) { ar = fmaf(x[k], __ldg(wr + k), ar); az = fmaf(x[k], __ldg(wz + k), az); an = fmaf(x[k], __ldg(wn + k), an); }
-                    const float r = rd_sig(ar), z = rd_sig(az), n = tanhf(an + r * __ldg(W.b_hh[dd] + 512 + uu));
-                    hs += (1.0f - z) * n;
-                }
-                h[i] = hs;
-            }
+            for (int k = 0; k < RD_IN; k++) x[k] = s_x[j][k];
+            float r, z, n; T.gates(x, r, z, n);
+            s_h[j][d][u] = (1.0f - z) * n;
+        }
+        __syncthreads();
+        if (warp < ns) {                                   // row phase: LayerNorm backward of sample s0 + warp
+            const int j = warp, s = s0 + j;
+            const float *o = obs + (size_t)(idx ? idx[s] : s) * obs_dim;
             const float mean = stats[2 * s], rstd = stats[2 * s + 1];
             const float sv = (lane < RD_SELF) ? __ldg(o + lane) : 0.0f;
             const float *df = dfeat + (size_t)s * RD_FEAT;
             // g = dfeat * ln_w ; dx = rstd * (g - mean(g) - xhat * mean(g * xhat))
-            float gq[9], xh[9];
-            float sg = 0.0f, sgx = 0.0f;
+            float gq[8], xh[8], sg = 0.0f, sgx = 0.0f;
 #pragma unroll
             for (int i = 0; i < 8; i++) {
                 const int q = RD_SELF + lane + 32 * i;
-                const float dfq = df[q];
-                xh[i] = (h[i] - mean) * rstd; gq[i] = dfq * __ldg(W.ln_w + q);
+                const float dfq = df[q], hq = s_h[j][0][lane + 32 * i] + s_h[j][1][lane + 32 * i];
+                xh[i] = (hq - mean) * rstd; gq[i] = dfq * __ldg(W.ln_w + q);
                 sg += gq[i]; sgx += gq[i] * xh[i];
                 s_gw[j][q] = dfq * xh[i];
             }
             if (lane < RD_SELF) {
-                const float dfq = df[lane];
-                xh[8] = (sv - mean) * rstd; gq[8] = dfq * __ldg(W.ln_w + lane);
-                sg += gq[8]; sgx += gq[8] * xh[8];
-                s_gw[j][lane] = dfq * xh[8];
+                const float dfq = df[lane], xs = (sv - mean) * rstd, gs = dfq * __ldg(W.ln_w + lane);
+                sg += gs; sgx += gs * xs;
+                s_gw[j][lane] = dfq * xs;
             }
 #pragma unroll
             for (int off = 16; off > 0; off >>= 1) { sg += __shfl_xor_sync(0xffffffffu, sg, off); sgx += __shfl_xor_sync(0xffffffffu, sgx, off); }
             const float mg = sg * (1.0f / RD_FEAT), mgx = sgx * (1.0f / RD_FEAT);
+            __syncwarp();
 #pragma unroll
-            for (int i = 0; i < 8; i++) s_dh[j][lane + 32 * i] = rstd * (gq[i] - mg - xh[i] * mgx);      // (no gradient w.r.t. the observation is needed)
+            for (int i = 0; i < 8; i++) s_h[j][0][lane + 32 * i] = rstd * (gq[i] - mg - xh[i] * mgx);      // dh (no gradient w.r.t. the observation is needed)
         }
         __syncthreads();
-        // ---- phase 2: thread = (direction d, unit u)
-        for (int j = 0; j < ns; j++) {
+        for (int j = 0; j < ns; j++) {                     // gradient phase
             float x[RD_IN];
 #pragma unroll
             for (int k = 0; k < RD_IN; k++) x[k] = s_x[j][k];
-            float ar = br, az = bz, an = bn;
-#pragma unroll
-            for (int k = 0; k < RD_IN; k++) { ar = fmaf(x[k], wv[0][k], ar); az = fmaf(x[k], wv[1][k], az); an = fmaf(x[k], wv[2][k], an); }
-            const float r = rd_sig(ar), z = rd_sig(az), n = tanhf(an + r * bhn);
-            const float dh = s_dh[j][u];
+            float r, z, n; T.gates(x, r, z, n);
+            const float dh = s_h[j][0][u];
             const float dpn = dh * (1.0f - z) * (1.0f - n * n);        // d / d (i_n + b_in + r * b_hn)
             const float dpz = -dh * n * z * (1.0f - z);
-            const float dpr = dpn * bhn * r * (1.0f - r);
+            const float dpr = dpn * T.bhn * r * (1.0f - r);
 #pragma unroll
             for (int k = 0; k < RD_IN; k++) { aw[0][k] = fmaf(dpr, x[k], aw[0][k]); aw[1][k] = fmaf(dpz, x[k], aw[1][k]); aw[2][k] = fmaf(dpn, x[k], aw[2][k]); }
             ab[0] += dpr; ab[1] += dpz; ab[2] += dpn; ab[3] += dpn * r;
@@ -297,7 +310,8 @@ int uaisa_reader_fwd(const float *obs, const int64_t *idx, int32_t B, int32_t ob
     uaisa::ReaderW W{};
     for (int d = 0; d < 2; d++) { W.w_ih[d] = params[3 * d]; W.b_ih[d] = params[3 * d + 1]; W.b_hh[d] = params[3 * d + 2]; }
     W.ln_w = params[6]; W.ln_b = params[7];
-    uaisa::uaisa_reader_fwd_kernel<<<(B + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(obs, reinterpret_cast<const long long *>(idx), B, obs_dim, W, feat, stats);
+    const int tiles_f = (B + uaisa::RB_T - 1) / uaisa::RB_T;
+    uaisa::uaisa_reader_fwd_kernel<<<tiles_f < 592 ? tiles_f : 592, 512, 0, static_cast<cudaStream_t>(stream)>>>(obs, reinterpret_cast<const long long *>(idx), B, obs_dim, W, feat, stats);
     return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 
@@ -312,7 +326,7 @@ int uaisa_reader_bwd(const float *obs, const int64_t *idx, int32_t B, int32_t ob
     }
     W.ln_w = params[6]; W.ln_b = params[7]; G.ln_w = grads[6]; G.ln_b = grads[7];
     const int tiles = (B + uaisa::RB_T - 1) / uaisa::RB_T;
-    const int grid = tiles < 296 ? tiles : 296;
+    const int grid = tiles < 444 ? tiles : 444;      // 3 CTAs of 512 threads per SM
     uaisa::uaisa_reader_bwd_kernel<<<grid, 512, 0, static_cast<cudaStream_t>(stream)>>>(obs, reinterpret_cast<const long long *>(idx), B, obs_dim, W, dfeat, stats, G);
     return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }

@@ -193,3 +193,15 @@ def test_reset_starts_a_new_episode_for_the_reset_policy():
             assert bool(a.reset_mask.view(E, 3)[:, 1:].all()) and not bool(a.reset_mask.view(E, 3)[:, 0].any())
     a.close(); b.close()
     del pc
+
+
+@pytest.mark.parametrize("name,E,steps", [("c2", 1024, 12), ("c3", 4096, 5), ("c4", 64, 4), ("c5", 65536, 5)])
+def test_full_size_lockstep_on_diverse_data(name, E, steps):
+    """BASELINE.json's full sizes with DIVERSE data: every env has its own action stream (and, for configs[2] / [3], one of several scenarios); the
+    whole batch is compared with the oracle every step (teacher-forced), not one representative env."""
+    from uaisa_env.scenario import scenario_c4
+    scn = {"c2": scenario_c1, "c5": scenario_c1, "c3": lambda: scenario_c3(seed=0, n_scenarios=8), "c4": lambda: scenario_c4(seed=0, n_scenarios=2)}[name]()
+    st = lockstep(scn, E, 10, steps, seed=31, epoch_len=0, block=2, max_ep_len=3)
+    st.assert_parity()
+    assert st.n_agent_steps == E * scn.N * steps and st.resets > 0
+    assert st.obs_inexact <= 1e-5 * st.obs_vals and st.rew_inexact <= 1e-4 * st.rew_vals, st.summary()

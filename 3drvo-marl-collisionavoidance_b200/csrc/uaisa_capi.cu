@@ -166,7 +166,8 @@ int uaisa_create(const UaisaConfig *cfg, UaisaHandle **out) {
                + (size_t)th * (4 * 8 + 3 * 4) + sizeof(int) * (epc + 2) + 16                         // + re-observe compaction
                + cols * 16 + 16                                                                    // + fp32 position copies
                + (size_t)(s - 1) * th * 12 + (size_t)th * 4 + 16                                     // + helpers' partial results, owners' activity
-               + (size_t)th * 80 + epc * 24 + 16;                                                  // + per-drone route cache, map sizes
+               + (size_t)th * 80 + epc * 24 + 16                                                   // + per-drone route cache, map sizes
+               + (size_t)(P.M <= 16 ? P.M : 0) * 32 * epc;                                         // + cylinders of the CTA's envs (used when a scenario has any)
     };
     const bool auto_threads = threads <= 0;
     if (auto_threads) {
@@ -274,7 +275,9 @@ int uaisa_set_scenarios(UaisaHandle *h, const double *waypoints, const int32_t *
             if (mag != 0.0) { g[0] = dx / mag; g[1] = dy / mag; g[2] = dz / mag; }
         }
     }
-    for (size_t s = 0; s < S; s++) if (n_buildings[s] < 0 || n_buildings[s] > P.M) return fail(UAISA_EINVAL, "n_buildings out of range");
+    int any_bld = 0;
+    for (size_t s = 0; s < S; s++) { if (n_buildings[s] < 0 || n_buildings[s] > P.M) return fail(UAISA_EINVAL, "n_buildings out of range"); any_bld |= n_buildings[s] > 0; }
+    h->P.bld_cache = (any_bld && P.M <= 16) ? 1 : 0;
     for (int e = 0; e < P.E; e++) if (env2scenario[e] < 0 || env2scenario[e] >= (int)S) return fail(UAISA_EINVAL, "env2scenario out of range");
     DeviceGuard g(h->device);
     CK(cudaMemcpy(const_cast<double *>(P.wp), waypoints, sizeof(double) * SN * W * 3, cudaMemcpyHostToDevice));

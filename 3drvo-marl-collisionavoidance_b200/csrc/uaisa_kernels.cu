@@ -92,6 +92,9 @@ enum Region : int { RG_PROLOGUE = 0, RG_FILL, RG_SYNC, RG_DRONESTATE, RG_PAIRS, 
 #ifndef UAISA_LB_THREADS
 #define UAISA_LB_THREADS MAXT   // experiments: smaller CTAs with a different register cap (profiles/variants.sh)
 #endif
+#ifndef UAISA_F32_SMALL
+#define UAISA_F32_SMALL 0   // experiments: fp32 range pre-gate also in the few-neighbour kernels (MAXR <= 4)
+#endif
 #ifndef UAISA_MINB128
 #define UAISA_MINB128 3   // CTAs of 128 threads per SM the register allocator must leave room for
 #endif
@@ -111,6 +114,7 @@ __global__ void __launch_bounds__(UAISA_LB_THREADS, (MAXT <= 128 ? UAISA_MINB128
     // copy of the env's exchange columns in its own shared memory; at each publish point the CTAs write their slice to a
     // double-buffered global (L2) exchange array, meet at the hardware cluster barrier and reload all N columns.
     const bool CLM = !WL && P.cl > 1;
+    constexpr bool F32G = (MAXR > 4) || (UAISA_F32_SMALL != 0);                  // stage 1a runs in fp32 on float copies of the positions
     const int sst = CLM ? P.N : threads;                                         // column stride of the exchange tile
     // Shared memory is carved up by byte offsets from the one __shared__ array, never through integer round trips of a pointer, so
     // that every access below compiles to LDS/STS (a pointer rebuilt from a uintptr_t is generic: LD.E on the long scoreboard).
@@ -141,6 +145,18 @@ __global__ void __launch_bounds__(UAISA_LB_THREADS, (MAXT <= 128 ? UAISA_MINB128
     // long-scoreboard round trip that small batches (one warp per scheduler) cannot hide.  smap: map size of each env of the CTA.
     double *swp = reinterpret_cast<double *>(take(8u * 10u * threads));                              // [10][threads]
     double *smap = reinterpret_cast<double *>(take(8u * 3u * P.envs_per_cta));                       // [3][envs_per_cta]
+    // Cylinders of each env of the CTA ([x, y, h, r] x M, M <= 16): every drone walks them once per step; from L1 each value is a long-scoreboard
+    // round trip (4.4 % of configs[2]'s stall samples sat on these loads, profiles/r2/ncu_env_c3.txt).
+    const int Mc = P.bld_cache ? P.M : 0;          // (host: some scenario has cylinders and M <= 16)
+    double *sbld = reinterpret_cast<double *>(take(8u * 4u * (unsigned)Mc * P.envs_per_cta));        // [envs_per_cta][Mc][4]
+    {
+        const bool clm_ = !WL && P.cl > 1;
+        const int e0_ = clm_ ? (int)(blockIdx.x / P.cl) : blockIdx.x * P.envs_per_cta;
+        for (int i = threadIdx.x; i < P.envs_per_cta * Mc * 4; i += blockDim.x) {
+            const int le_ = i / (Mc * 4), e_ = e0_ + le_;
+            sbld[i] = e_ < P.E ? __ldg(P.bld + (size_t)__ldg(P.env2scn + e_) * P.M * 4 + (i - le_ * Mc * 4)) : 0.0;
+        }
+    }
     if (threadIdx.x == 0) { s_nt[0] = 0; s_nt[1] = 0; }
     const float nbr2_lo_f = (float)(P.nbr_range * P.nbr_range * (1.0 - 1e-4)), nbr2_hi_f = (float)(P.nbr_range * P.nbr_range * (1.0 + 1e-4));
     if (WL) {
@@ -326,7 +342,7 @@ __global__ void __launch_bounds__(UAISA_LB_THREADS, (MAXT <= 128 ? UAISA_MINB128
                         const uint32_t b_ = mapa_shared(sx_a, (uint32_t)r);
                         st_cluster_f64(b_, d.px); st_cluster_f64(b_ + fs, d.py); st_cluster_f64(b_ + 2 * fs, d.pz);
                         st_cluster_f64(b_ + 3 * fs, d.vx); st_cluster_f64(b_ + 4 * fs, d.vy); st_cluster_f64(b_ + 5 * fs, d.vz);
-                        if constexpr (MAXR > 4) st_cluster_v4f32(mapa_shared(sxf_a, (uint32_t)r), (float)d.px, (float)d.py, (float)d.pz, 0.f);
+                        if constexpr (F32G) st_cluster_v4f32(mapa_shared(sxf_a, (uint32_t)r), (float)d.px, (float)d.py, (float)d.pz, 0.f);
                     }
                 }
             } else if (CLM) {
@@ -339,12 +355,12 @@ __global__ void __launch_bounds__(UAISA_LB_THREADS, (MAXT <= 128 ? UAISA_MINB128
                     const double x_ = __ldcg(g), y_ = __ldcg(g + 1), z_ = __ldcg(g + 2);
                     sx[0 * sst + j] = x_; sx[1 * sst + j] = y_; sx[2 * sst + j] = z_;
                     sx[3 * sst + j] = __ldcg(g + 3); sx[4 * sst + j] = __ldcg(g + 4); sx[5 * sst + j] = __ldcg(g + 5);
-                    if constexpr (MAXR > 4) sxf[j] = make_float4((float)x_, (float)y_, (float)z_, 0.f);
+                    if constexpr (F32G) sxf[j] = make_float4((float)x_, (float)y_, (float)z_, 0.f);
                 }
             } else if (valid) {
                 sx[0 * sst + scol] = d.px; sx[1 * sst + scol] = d.py; sx[2 * sst + scol] = d.pz;
                 sx[3 * sst + scol] = d.vx; sx[4 * sst + scol] = d.vy; sx[5 * sst + scol] = d.vz;
-                if constexpr (MAXR > 4) sxf[scol] = make_float4((float)d.px, (float)d.py, (float)d.pz, 0.f);
+                if constexpr (F32G) sxf[scol] = make_float4((float)d.px, (float)d.py, (float)d.pz, 0.f);
             }
             if (ph == PH_OBS && compact) {
                 // Only the envs touched by the reset policy are re-observed (typically a quarter of them, spread over
@@ -408,7 +424,7 @@ __global__ void __launch_bounds__(UAISA_LB_THREADS, (MAXT <= 128 ? UAISA_MINB128
                 for (int jb = jb_lo; jb < jb_hi; jb += 32) {
                     unsigned cand = 0, slow = 0, near = 0;
                     const int jn = min(32, jb_hi - jb);
-                    if constexpr (MAXR > 4) {                     // many neighbours: fp32 pre-gate on float copies of the positions
+                    if constexpr (F32G) {                         // fp32 pre-gate on float copies of the positions
                         const float fx = (float)d.px, fy = (float)d.py, fz = (float)d.pz;
                         if (jn == 32) {                          // full chunk: fixed trip count, fully unrolled -> 32 independent gates in flight
 #pragma unroll
@@ -593,8 +609,11 @@ __global__ void __launch_bounds__(UAISA_LB_THREADS, (MAXT <= 128 ? UAISA_MINB128
                 if (at_dest && !(d.flags & FLAG_DEST)) { d.flags |= FLAG_DEST; dest_now = true; }
             }
             RG_MARK(RG_B_FLAGS);
+            const double *sb_ = sbld + (CLM ? 0 : le) * Mc * 4;
             for (int m = 0; m < nb; m++) {   // rvo_inter.py:99-105 filter, :198-209 check
-                const double bx = __ldg(bld + 4 * m), by = __ldg(bld + 4 * m + 1), bh = __ldg(bld + 4 * m + 2), br = __ldg(bld + 4 * m + 3);
+                double bx, by, bh, br;
+                if (Mc) { bx = sb_[4 * m]; by = sb_[4 * m + 1]; bh = sb_[4 * m + 2]; br = sb_[4 * m + 3]; }
+                else { bx = __ldg(bld + 4 * m); by = __ldg(bld + 4 * m + 1); bh = __ldg(bld + 4 * m + 2); br = __ldg(bld + 4 * m + 3); }
                 if (bh > d.pz - P.bld_zgate && d.pz <= bh) {
                     const double ex = d.px - bx, ey = d.py - by;
                     if (sqrt_le(fma(ey, ey, ex * ex), P.bld_range) && sqrt_le(ex * ex + ey * ey, C.radius + br)) col = true;

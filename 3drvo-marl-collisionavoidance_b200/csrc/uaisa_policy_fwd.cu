@@ -17,6 +17,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <cstdlib>
+
 #include "uaisa_tc.cuh"
 
 namespace uaisa {
@@ -134,6 +136,11 @@ __device__ __forceinline__ float sigm(float x) { return fmaf(0.5f, tanh_fast(0.5
 constexpr int FW_S = 4;
 constexpr int FW_NT = FW_M * FW_S;
 
+// CL = 2 (optional, UAISA_POLICY_CLUSTER=2): the kernel runs as thread-block clusters of two CTAs (two agent tiles on two SMs) that walk the SAME weight-tile
+// sequence; every tile is fetched once per cluster -- each CTA bulk-copies one half and MULTICASTS it into both CTAs' stage (SASS UBLKCP.S.G.MULTICAST) -- which
+// halves the L2 -> SM weight traffic.  A stage is refilled only after BOTH CTAs' MMAs have released it (the `empty` barriers count two multicast tcgen05.commit
+// arrivals, UTCBAR.MULTICAST).  Measured no faster than CL = 1: the weight stream is bound by the latency of the two stages in flight, not by L2 bandwidth.
+template <int CL>
 __global__ void __launch_bounds__(FW_NT, 1) uaisa_policy_forward_kernel(const __grid_constant__ FwdParams P) {
     extern __shared__ unsigned char fw_smem_raw[];
     char *base = reinterpret_cast<char *>((reinterpret_cast<uintptr_t>(fw_smem_raw) + 1023) & ~uintptr_t(1023));   // SWIZZLE_128B needs 1024-byte alignment
@@ -148,9 +155,13 @@ __global__ void __launch_bounds__(FW_NT, 1) uaisa_policy_forward_kernel(const __
     const bool ok = a < P.A;
     const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[2]), done = smem_u32(&bars[4]);
 
+    const uint32_t crank = CL > 1 ? cluster_ctarank() : 0u;
+    constexpr uint16_t CMASK = (uint16_t)((1u << CL) - 1u);
     if (warp == 0) tmem_alloc(smem_u32(tmem_slot), 512u);
     if (tid == 0) {
-        for (int i = 0; i < 5; i++) mbar_init(smem_u32(&bars[i]), 1);
+        mbar_init(smem_u32(&bars[0]), 1); mbar_init(smem_u32(&bars[1]), 1);          // full: my own arrive.expect_tx (+ the tile's bytes)
+        mbar_init(smem_u32(&bars[2]), CL); mbar_init(smem_u32(&bars[3]), CL);        // empty: one tcgen05.commit arrival per CTA of the cluster
+        mbar_init(smem_u32(&bars[4]), 1);                                            // done
         mbar_init_fence();
         *s_lmax = 1;
     }
@@ -158,13 +169,21 @@ __global__ void __launch_bounds__(FW_NT, 1) uaisa_policy_forward_kernel(const __
     int cnt = ok ? (int)P.count[a] : 0;
     cnt = cnt < P.nm ? cnt : P.nm;
     const int c_eff = cnt > 1 ? cnt : 1;               // an agent without neighbours feeds ONE zero row (ir_gym.py:211-212)
-    if (sub == 0) {
-        const int wmax = __reduce_max_sync(0xffffffffu, c_eff);
-        if ((tid & 31) == 0) atomicMax(s_lmax, wmax);
+    {   // number of GRU steps = the largest row count in the CLUSTER's tiles (all its CTAs must walk the same weight-tile sequence)
+        int m = 1;
+        for (int q = tid; q < CL * FW_M; q += FW_NT) {
+            const int aq = (int)(blockIdx.x / CL) * CL * FW_M + q;
+            int c = aq < P.A ? (int)P.count[aq] : 0;
+            c = c < P.nm ? c : P.nm;
+            m = c > m ? c : m;
+        }
+        m = __reduce_max_sync(0xffffffffu, m);
+        if ((tid & 31) == 0) atomicMax(s_lmax, m);
     }
     fence_before_sync();
     __syncthreads();
     fence_after_sync();
+    if (CL > 1) cluster_sync();                        // the peers' barriers are initialised before anything is multicast to them
     const uint32_t tmem = *tmem_slot;
     const int lmax = *s_lmax;
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;      // a warp reaches the TMEM lane quarter (warp id % 4)
@@ -181,7 +200,11 @@ __global__ void __launch_bounds__(FW_NT, 1) uaisa_policy_forward_kernel(const __
             const int s = pf & 1;
             if (pf >= 2) { mbar_wait(empty0 + 8 * s, epar[s]); epar[s] ^= 1u; }      // the MMAs that read this stage have completed
             mbar_expect_tx(full0 + 8 * s, bytes);
-            bulk_g2s(smem_u32(Bs + s * FW_STAGE), addr, bytes, full0 + 8 * s);
+            if (CL == 1) bulk_g2s(smem_u32(Bs + s * FW_STAGE), addr, bytes, full0 + 8 * s);
+            else {                                     // my 1/CL of the tile, into every CTA of the cluster
+                const uint32_t part = bytes / CL;
+                bulk_g2s_multicast(smem_u32(Bs + s * FW_STAGE) + crank * part, reinterpret_cast<const char *>(addr) + crank * part, part, full0 + 8 * s, CMASK);
+            }
             pf++;
         }
     };
@@ -192,7 +215,7 @@ __global__ void __launch_bounds__(FW_NT, 1) uaisa_policy_forward_kernel(const __
         fence_after_sync();
         return s;
     };
-    auto release = [&](int s) { umma_commit(empty0 + 8 * s); cs++; };
+    auto release = [&](int s) { if (CL == 1) umma_commit(empty0 + 8 * s); else umma_commit_multicast(empty0 + 8 * s, CMASK); cs++; };
     auto mma = [&](int a_chunk, uint32_t b_saddr, int ksteps, uint32_t idesc, uint32_t tmem_d, bool acc) {
         const uint32_t sa = smem_u32(As + a_chunk * FW_A_CHUNK);
         for (int k = 0; k < ksteps; k++) umma_tf32(tmem_d, umma_desc(sa + k * 32), umma_desc(b_saddr + k * 32), idesc, (acc || k > 0) ? 1u : 0u);   // UMMA K = 8 tf32 = 32 bytes
@@ -344,20 +367,20 @@ __global__ void __launch_bounds__(FW_NT, 1) uaisa_policy_forward_kernel(const __
                 for (int ub = sub; ub < 16; ub += FW_S) {
                     float h[16]; tmem_ld16(tmem + lane_base + 256 + ub * 16, h);
 #pragma unroll
-                    for (int q4 = 0; q4 < 4; q4++) stash[(size_t)(ub * 4 + q4) * FW_M + row] = make_float4(h[4 * q4], h[4 * q4 + 1], h[4 * q4 + 2], h[4 * q4 + 3]);
+                    for (int q4 = 0; q4 < 4; q4++) if (a0 < P.A) stash[(size_t)(ub * 4 + q4) * FW_M + row] = make_float4(h[4 * q4], h[4 * q4 + 1], h[4 * q4 + 2], h[4 * q4 + 3]);
                 }
             } else {
 #pragma unroll 1
                 for (int ub = sub; ub < 16; ub += FW_S) {
                     float h[16]; tmem_ld16(tmem + lane_base + 256 + ub * 16, h);
 #pragma unroll
-                    for (int q4 = 0; q4 < 4; q4++) { const float4 f = stash[(size_t)(ub * 4 + q4) * FW_M + row]; h[4 * q4] += f.x; h[4 * q4 + 1] += f.y; h[4 * q4 + 2] += f.z; h[4 * q4 + 3] += f.w; }
+                    for (int q4 = 0; q4 < 4; q4++) { const float4 f = a0 < P.A ? stash[(size_t)(ub * 4 + q4) * FW_M + row] : make_float4(0.f, 0.f, 0.f, 0.f); h[4 * q4] += f.x; h[4 * q4 + 1] += f.y; h[4 * q4 + 2] += f.z; h[4 * q4 + 3] += f.w; }
                     write_h16(ub * 16, h);             // h_fwd + h_bwd (policy_rnn_ac.py:122, 163)
                 }
             }
             sync_tmem();
         }
-        if (P.stats && tid == 0) { atomicAdd(P.stats, 1); atomicMax(P.stats + 1, lmax); }
+        if (P.stats && tid == 0 && a0 < P.A) { atomicAdd(P.stats, 1); atomicMax(P.stats + 1, lmax); }
     }
 
     // =========================================================================================== concat + LayerNorm(268), in place in the A tile
@@ -467,8 +490,11 @@ __global__ void __launch_bounds__(FW_NT, 1) uaisa_policy_forward_kernel(const __
             else P.v[a] = acc[0] + __ldg(b3 + 3);
         }
     }
+    if (CL > 1) cluster_sync();                        // no peer may still signal my barriers (or expect my copies) when I leave
     if (warp == 0) tmem_dealloc(tmem, 512u);
 }
+template __global__ void uaisa_policy_forward_kernel<1>(const __grid_constant__ FwdParams);
+template __global__ void uaisa_policy_forward_kernel<2>(const __grid_constant__ FwdParams);
 
 }  // namespace uaisa
 
@@ -497,16 +523,30 @@ int uaisa_policy_forward(const float *obs, const uint8_t *count, int32_t A, int3
                          void *scratch, int32_t *stats, void *stream) {
     if (!obs || !count || !wpack || !mu || !v || !scratch || A < 1 || obs_dim < uaisa::FW_SELF || (obs_dim - uaisa::FW_SELF) % uaisa::FW_IN) return -1;
     static bool attr_set[64] = {};      // per device
+    // UAISA_POLICY_CLUSTER=2: clusters of two CTAs that multicast every weight tile into both (A/B switch).  Measured NO faster (0.72 vs 0.69 ms at 262 144
+    // agents): the stall is the latency of two 32 KB stages in flight per SM, not L2 bandwidth -- see DESIGN.md section 6.  Default: 1.
+    static const int cl = std::getenv("UAISA_POLICY_CLUSTER") ? std::atoi(std::getenv("UAISA_POLICY_CLUSTER")) : 1;
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return -2;
     if (dev < 0 || dev >= 64 || !attr_set[dev]) {
-        if (cudaFuncSetAttribute(uaisa::uaisa_policy_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, uaisa::FW_SMEM) != cudaSuccess) return -2;
+        if (cudaFuncSetAttribute(uaisa::uaisa_policy_forward_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, uaisa::FW_SMEM) != cudaSuccess) return -2;
+        if (cudaFuncSetAttribute(uaisa::uaisa_policy_forward_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, uaisa::FW_SMEM) != cudaSuccess) return -2;
         if (dev >= 0 && dev < 64) attr_set[dev] = true;
     }
     uaisa::FwdParams P{};
     P.obs = obs; P.count = count; P.A = A; P.obs_dim = obs_dim; P.nm = (obs_dim - uaisa::FW_SELF) / uaisa::FW_IN;
     P.wp = wpack; P.mu = mu; P.v = v; P.feat_out = feat_out; P.scratch = static_cast<float4 *>(scratch); P.stats = stats;
-    uaisa::uaisa_policy_forward_kernel<<<(A + uaisa::FW_M - 1) / uaisa::FW_M, uaisa::FW_NT, uaisa::FW_SMEM, static_cast<cudaStream_t>(stream)>>>(P);
+    const int tiles = (A + uaisa::FW_M - 1) / uaisa::FW_M;
+    if (cl == 2) {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(((tiles + 1) / 2) * 2); cfg.blockDim = dim3(uaisa::FW_NT); cfg.dynamicSmemBytes = uaisa::FW_SMEM; cfg.stream = static_cast<cudaStream_t>(stream);
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        if (cudaLaunchKernelEx(&cfg, uaisa::uaisa_policy_forward_kernel<2>, P) != cudaSuccess) return -2;
+    } else {
+        uaisa::uaisa_policy_forward_kernel<1><<<tiles, uaisa::FW_NT, uaisa::FW_SMEM, static_cast<cudaStream_t>(stream)>>>(P);
+    }
     return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 

@@ -49,6 +49,20 @@ __device__ __forceinline__ void bulk_g2s(uint32_t sdst, const void *gsrc, uint32
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sdst), "l"(gsrc), "r"(bytes), "r"(mbar) : "memory");
 }
 
+// The same copy issued by ONE CTA of a cluster, delivered to the CTA-relative address `sdst` (and signalled on the CTA-relative mbarrier `mbar`) of EVERY
+// CTA in `cta_mask`: a weight tile read once from L2 feeds several SMs.
+__device__ __forceinline__ void bulk_g2s_multicast(uint32_t sdst, const void *gsrc, uint32_t bytes, uint32_t mbar, uint16_t cta_mask) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(sdst), "l"(gsrc), "r"(bytes),
+                 "r"(mbar), "h"(cta_mask)
+                 : "memory");
+}
+// tcgen05.commit that arrives on the mbarrier at the same CTA-relative offset in every CTA of `cta_mask`
+__device__ __forceinline__ void umma_commit_multicast(uint32_t mbar, uint16_t cta_mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(mbar), "h"(cta_mask) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync() { asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+
 __device__ __forceinline__ void tmem_alloc(uint32_t smem_slot, uint32_t cols) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_slot), "r"(cols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");

@@ -209,6 +209,7 @@ int uaisa_create(const UaisaConfig *cfg, UaisaHandle **out) {
     h->threads = threads; P.threads = threads; P.slices = slices; P.envs_per_cta = cluster ? 1 : threads / N;
     // CTA-level compaction of the re-observe phase pays only with several warps per CTA and more than a handful of
     // drones per env (measured: N=16 +7 %, N=4 +2 % at 128 threads, -10 % with single-warp CTAs)
+    P.defer_obs = std::getenv("UAISA_NO_DEFER") ? 0 : 1;   // T-step launches: re-observation of step t < T-1 rides on PASS A of step t+1 (A/B switch)
     P.compact = (!cluster && slices == 1 && threads >= 128 && (N > 4 || std::getenv("UAISA_FORCE_COMPACT")) && !std::getenv("UAISA_NO_COMPACT")) ? 1 : 0;
     h->grid = cluster ? E * P.cl : (E + P.envs_per_cta - 1) / P.envs_per_cta;
     h->smem = smem_for(threads, slices);

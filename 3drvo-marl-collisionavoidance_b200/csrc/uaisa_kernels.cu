@@ -216,6 +216,13 @@ __global__ void __launch_bounds__(UAISA_LB_THREADS, (MAXT <= 128 ? UAISA_MINB128
     }
     unsigned n_rng = 0, n_cone = 0, n_bad = 0;
     const int T = is_step ? L.T : 1;
+    // Deferred re-observation (T-step launches): the re-observe phase of step t < T-1 would publish the state, run dronestate and the
+    // stage-1 gates on exactly what PASS A of step t+1 publishes and gates again (same fp32-rounded state, same waypoint).  So the phase
+    // is not run: the reset policy only marks the env (`pend`), and PASS A of the next step also evaluates the cones with action 0, builds
+    // the top-nm list and writes the observation row into the PREVIOUS step's slot.  The last step of a launch re-observes as before.
+    const bool defer_on = is_step && do_auto && P.defer_obs;
+    bool pend = false;                                            // my env's row of the previous step is still to be rewritten
+    int staged = -1;                                              // rows of mine already in HBM this step (-1: none, row not cleared)
     RG_MARK(RG_PROLOGUE);
 
     for (int t = 0; t < T; t++) {
@@ -257,7 +264,8 @@ __global__ void __launch_bounds__(UAISA_LB_THREADS, (MAXT <= 128 ? UAISA_MINB128
 #endif
         RG_MARK(RG_ACT);
         bool st_done = false, st_fin = false;
-        int staged = -1;                                 // rows of mine already in HBM this step (-1: none, row not cleared)
+        const int staged_prev = staged;                  // (what PASS B of the previous step left in ITS slot: a deferred re-observation clears the rest)
+        staged = -1;
         // "working identity": normally the thread's own drone; in a compacted re-observe phase the drone it was handed
         int wk = k, wlbase = lbase, tt = tid, wa = a;
         bool remapped = false, worker = false;
@@ -324,6 +332,8 @@ __global__ void __launch_bounds__(UAISA_LB_THREADS, (MAXT <= 128 ? UAISA_MINB128
                 active = valid && sel && (L.obs || L.count || L.nbr);
                 if (S > 1 && !helper) s_act[tid] = active;             // read by my helpers after the barriers below
                 RG_MARK(RG_AUTORESET);
+                pend = false;
+                if (defer_on && t + 1 < T) { pend = active; continue; }   // (uniform) re-observed inside PASS A of the next step
             }
             // a warp none of whose envs is re-observed has nothing to publish or read (warp-local envs only)
             if (WL && !compact && ph == PH_OBS && !__any_sync(0xffffffffu, active)) continue;      // (the compacted variant meets at CTA barriers)
@@ -416,6 +426,9 @@ __global__ void __launch_bounds__(UAISA_LB_THREADS, (MAXT <= 128 ? UAISA_MINB128
             TopList<MAXR> top; top.init(stop + (unsigned)(slice * TopList<MAXR>::smem_bytes(threads)), threads, tid); top.clear();
             int jb_lo = 0, jb_hi = N;                          // my slice: whole 32-neighbour chunks
             if (S > 1) { const int nch = (N + 31) >> 5; jb_lo = ((slice * nch) / S) << 5; jb_hi = min(N, (((slice + 1) * nch) / S) << 5); }
+            // evaluations of the cones in this pass: ev 1 = the phase's own (the action; 0 when re-observing), ev 0 = the re-observation
+            // deferred from the previous step (action 0, list only) -- both on the same stage-1 masks
+            const bool ev0 = (ph == PH_A) && ((S > 1 && helper) ? (defer_on && t > 0 && s_act[tid] != 0) : pend);
             {
                 double bx = (ph == PH_OBS) ? 0.0 : ax, by = (ph == PH_OBS) ? 0.0 : ay, bz = (ph == PH_OBS) ? 0.0 : az;
                 if (np_dot3(bx, by, bz, bx, by, bz) < 1e-10 * (1.0 - 1e-14)) { bx = by = bz = 0.0; }   // norm(a) < 1e-5, rvo_inter.py:118-119
@@ -468,19 +481,22 @@ __global__ void __launch_bounds__(UAISA_LB_THREADS, (MAXT <= 128 ? UAISA_MINB128
                         col |= (bits & PB_COL) != 0;
                         cand |= (bits & PB_FULL) ? (1u << jj) : 0u;
                     }
+                    if (cand == 0u) continue;
+                    for (int ev = ev0 ? 0 : 1; ev < 2; ev++) {
+                    const double ex_ = ev ? bx : 0.0, ey_ = ev ? by : 0.0, ez_ = ev ? bz : 0.0;
                     n_cone += __popc(cand);
                     // stage 2a: trig-free screen of every candidate (uniform work) -> inside / ambiguous masks
                     unsigned ins = 0, amb = 0;
                     for (unsigned m = cand; m; m &= m - 1) {
                         const int jj = __ffs(m) - 1;
-                        PairGeom g; pair_geom(P, d.px, d.py, d.pz, d.vx, d.vy, d.vz, C.radius, C.prio, sx + wlbase + jb + jj, sst, bx, by, bz, g);
+                        PairGeom g; pair_geom(P, d.px, d.py, d.pz, d.vx, d.vy, d.vz, C.radius, C.prio, sx + wlbase + jb + jj, sst, ex_, ey_, ez_, g);
                         const int c = cone_screen(g);
                         ins |= (c == 1) ? (1u << jj) : 0u; amb |= (c == 2) ? (1u << jj) : 0u;
                     }
                     // stage 2b: the few ambiguous pairs go through asin/acos with the reference's roundings
                     for (unsigned m = amb; m; m &= m - 1) {
                         const int jj = __ffs(m) - 1;
-                        PairGeom g; pair_geom(P, d.px, d.py, d.pz, d.vx, d.vy, d.vz, C.radius, C.prio, sx + wlbase + jb + jj, sst, bx, by, bz, g);
+                        PairGeom g; pair_geom(P, d.px, d.py, d.pz, d.vx, d.vy, d.vz, C.radius, C.prio, sx + wlbase + jb + jj, sst, ex_, ey_, ez_, g);
                         double ah;
                         if (cone_exact(g, ah)) ins |= 1u << jj;
                     }
@@ -488,15 +504,16 @@ __global__ void __launch_bounds__(UAISA_LB_THREADS, (MAXT <= 128 ? UAISA_MINB128
                     for (unsigned m = ins; m; m &= m - 1) {
                         const int jj = __ffs(m) - 1, j = jb + jj;
                         const double *so = sx + wlbase + j;
-                        PairGeom g; pair_geom(P, d.px, d.py, d.pz, d.vx, d.vy, d.vz, C.radius, C.prio, so, sst, bx, by, bz, g);
+                        PairGeom g; pair_geom(P, d.px, d.py, d.pz, d.vx, d.vy, d.vz, C.radius, C.prio, so, sst, ex_, ey_, ez_, g);
                         double tt, md, iet;
-                        if (cone_time(P, d.vx, d.vy, d.vz, C.radius, so, sst, bx, by, bz, g, tt, md, iet)) {
-                            vo_any = true; if (tt < tmin) tmin = tt;
-                            if (ph != PH_A) {
+                        if (cone_time(P, d.vx, d.vy, d.vz, C.radius, so, sst, ex_, ey_, ez_, g, tt, md, iet)) {
+                            if (ev) { vo_any = true; if (tt < tmin) tmin = tt; }
+                            if (ph != PH_A || ev == 0) {
                                 const double ah = py_round2_hundredths(asin(g.R / sqrt(g.s2)));   // get_alpha, vel_obs3D.py:8-17
                                 top.insert(cap, iet, md, j, (int)ah);
                             }
                         }
+                    }
                     }
                 }
             }
@@ -514,41 +531,11 @@ __global__ void __launch_bounds__(UAISA_LB_THREADS, (MAXT <= 128 ? UAISA_MINB128
                     }
                 }
             }
-            if (ph == PH_A) {
-                // ---------------------------------------------------- ir_gym.rvo_reward_cal (ir_gym.py:64-133)
-                const double vnum = 0.2 * fast_sqrt(np_dot3(ax, ay, az, ax, ay, az)), vden = fast_sqrt(np_dot3(d0, d1, d2, d0, d1, d2));
-                const double vel_pen = (vden != 0.0) ? fast_div(vnum, vden) : vnum / vden;   // IEEE inf/nan when des = 0 (ir_gym.py:88)
-                const double ap_ = angle_punish(d0, d1, d2, ax, ay, az);
-                double safety = 0;
-                if (vo_any) { double urg = 0; if (tmin < 2) urg = -8.0 * exp(-tmin / 0.5); safety = -2.5 + urg; }
-                rA = np_round3(ap_ + vel_pen + safety);
-                RG_MARK(RG_REWARD_A);
-                // ---------------------------------------------------- MOVE: drone.move_forward (drone.py:96-129,431-490)
-                const double speed = fast_sqrt(np_dot3(d.vx, d.vy, d.vz, d.vx, d.vy, d.vz));
-                const double acc = np_clip(ax * P.max_acc, -P.max_acc, P.max_acc);
-                const double dyaw = np_clip(ay * P.max_ang, -P.max_ang, P.max_ang), dpitch = np_clip(az * P.max_ang, -P.max_ang, P.max_ang);
-                double nv = speed + acc * 1.0; nv = (0.0 > nv) ? 0.0 : nv;
-                d.yaw = py_mod360(d.yaw + dyaw); d.pitch = np_clip(d.pitch + dpitch, -90.0, 90.0);
-                const double D2R = CUDART_PI / 180.0;
-                double sy, cy, sp, cp; sincos_small(d.yaw * D2R, sy, cy); sincos_small(d.pitch * D2R, sp, cp);
-                double nvx = nv * cp * cy, nvy = nv * cp * sy, nvz = nv * sp;
-                if (d.flags & FLAG_DEST) { nvx = nvy = nvz = 0.0; }   // stop is always on (env_base.py:142)
-                const double nx = d.px + nvx * P.dt, ny = d.py + nvy * P.dt, nz = d.pz + nvz * P.dt;
-                { const double ux = nx - d.px, uy = ny - d.py, uz = nz - d.pz; d.real_len = d.real_len + fast_sqrt(np_dot3(ux, uy, uz, ux, uy, uz)); }
-                d.px = nx; d.py = ny; d.pz = nz; d.vx = nvx; d.vy = nvy; d.vz = nvz;
-                if (within_goal_v(P, d.px, d.py, d.pz, swp[0 * threads + tt], swp[1 * threads + tt], swp[2 * threads + tt])) {           // drone.py:116-129
-                    const bool at_dest = within_goal(P, d.px, d.py, d.pz, C.wp(P) + 3 * (C.n - 1));
-                    if (at_dest) P.extra_len[a] = (float)(d.real_len - C.route_len);      // (stored right away: one live double less)
-                    if (!at_dest && d.i < C.n - 1) { d.i += 1; d.flags &= ~FLAG_ARRIVE; FILL_WP(tt); }
-                }
-                RG_MARK(RG_MOVE);
-                continue;
-            }
-
             // ------------------------------------------------------------ observation row (ir_gym.py:203-229)
-            {
+            if (ph != PH_A || ev0) {    // (PASS A: the re-observation deferred from the previous step, into THAT step's slot)
                 bool bad = false;
-                const size_t wo = OUT_SLOT(wa);
+                const size_t wo = (ph == PH_A) ? OUT_SLOT(wa) - (size_t)A : OUT_SLOT(wa);
+                const int staged_in = (ph == PH_A) ? staged_prev : staged;
                 float *const wobs = L.obs ? L.obs + wo * P.obs_dim : nullptr; int *const wnbr = L.nbr ? L.nbr + wo * P.nm : nullptr;
                 if (wobs) {
                     const double self[OBS_SELF] = {d.px, d.py, d.pz, d.vx, d.vy, d.vz, C.radius, C.prio, d0, d1, d2, dev};
@@ -586,18 +573,49 @@ __global__ void __launch_bounds__(UAISA_LB_THREADS, (MAXT <= 128 ? UAISA_MINB128
                 });
                 // rows beyond cnt: untouched zero fill after a step's clear, stale after a re-observe, or
                 // never cleared in the stand-alone observe/reset/autoreset modes
-                const int stale_end = (staged < 0) ? (is_step ? 0 : P.nm) : staged;
+                const int stale_end = (staged_in < 0) ? (is_step ? 0 : P.nm) : staged_in;
                 for (int r = top.cnt; r < stale_end; r++) {
                     if (wobs) { float *rr = wobs + OBS_SELF + ROW * r;
 #pragma unroll
                         for (int q = 0; q < ROW; q++) rr[q] = 0.0f; }
                     if (wnbr) wnbr[r] = -1;
                 }
-                staged = top.cnt;
+                if (ph != PH_A) staged = top.cnt;
                 n_bad += bad ? 1u : 0u;
                 if (L.count) L.count[wo] = (uint8_t)top.cnt;
             }
             RG_MARK(RG_OBSROW);
+            if (ph == PH_A) {
+                // ---------------------------------------------------- ir_gym.rvo_reward_cal (ir_gym.py:64-133)
+                const double vnum = 0.2 * fast_sqrt(np_dot3(ax, ay, az, ax, ay, az)), vden = fast_sqrt(np_dot3(d0, d1, d2, d0, d1, d2));
+                const double vel_pen = (vden != 0.0) ? fast_div(vnum, vden) : vnum / vden;   // IEEE inf/nan when des = 0 (ir_gym.py:88)
+                const double ap_ = angle_punish(d0, d1, d2, ax, ay, az);
+                double safety = 0;
+                if (vo_any) { double urg = 0; if (tmin < 2) urg = -8.0 * exp(-tmin / 0.5); safety = -2.5 + urg; }
+                rA = np_round3(ap_ + vel_pen + safety);
+                RG_MARK(RG_REWARD_A);
+                // ---------------------------------------------------- MOVE: drone.move_forward (drone.py:96-129,431-490)
+                const double speed = fast_sqrt(np_dot3(d.vx, d.vy, d.vz, d.vx, d.vy, d.vz));
+                const double acc = np_clip(ax * P.max_acc, -P.max_acc, P.max_acc);
+                const double dyaw = np_clip(ay * P.max_ang, -P.max_ang, P.max_ang), dpitch = np_clip(az * P.max_ang, -P.max_ang, P.max_ang);
+                double nv = speed + acc * 1.0; nv = (0.0 > nv) ? 0.0 : nv;
+                d.yaw = py_mod360(d.yaw + dyaw); d.pitch = np_clip(d.pitch + dpitch, -90.0, 90.0);
+                const double D2R = CUDART_PI / 180.0;
+                double sy, cy, sp, cp; sincos_small(d.yaw * D2R, sy, cy); sincos_small(d.pitch * D2R, sp, cp);
+                double nvx = nv * cp * cy, nvy = nv * cp * sy, nvz = nv * sp;
+                if (d.flags & FLAG_DEST) { nvx = nvy = nvz = 0.0; }   // stop is always on (env_base.py:142)
+                const double nx = d.px + nvx * P.dt, ny = d.py + nvy * P.dt, nz = d.pz + nvz * P.dt;
+                { const double ux = nx - d.px, uy = ny - d.py, uz = nz - d.pz; d.real_len = d.real_len + fast_sqrt(np_dot3(ux, uy, uz, ux, uy, uz)); }
+                d.px = nx; d.py = ny; d.pz = nz; d.vx = nvx; d.vy = nvy; d.vz = nvz;
+                if (within_goal_v(P, d.px, d.py, d.pz, swp[0 * threads + tt], swp[1 * threads + tt], swp[2 * threads + tt])) {           // drone.py:116-129
+                    const bool at_dest = within_goal(P, d.px, d.py, d.pz, C.wp(P) + 3 * (C.n - 1));
+                    if (at_dest) P.extra_len[a] = (float)(d.real_len - C.route_len);      // (stored right away: one live double less)
+                    if (!at_dest && d.i < C.n - 1) { d.i += 1; d.flags &= ~FLAG_ARRIVE; FILL_WP(tt); }
+                }
+                RG_MARK(RG_MOVE);
+                continue;
+            }
+
             if (ph == PH_OBS) { d.max_dev = rt(d.max_dev); continue; }
 
             // ------------------------------------------------------------ phase B only: flags, collisions, reward

@@ -37,6 +37,7 @@ struct Params {
     int envs_per_cta, threads;
     int tile0_bytes, tile1_bytes;   // constant smem tiles behind the TMA fills (zeros / 0xFF), multiples of 16
     int env_train, count_pairs, compact;
+    int defer_obs;                   // T-step launches with the reset policy: the re-observation of step t < T-1 is evaluated inside PASS A of step t+1
     int bld_cache;                   // cylinders of the CTA's envs are cached in shared memory (set by uaisa_set_scenarios: some scenario has cylinders, M <= 16)
     int slices;                      // neighbour slices per ego (helper threads; 1 = off).  blockDim.x = threads * slices
     int dsmem;                       // cluster mode: exchange the columns through distributed shared memory (1) or through L2 (0)

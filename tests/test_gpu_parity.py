@@ -166,27 +166,51 @@ def test_against_reference_golden_exact(path):
     assert n_inexact <= 2, st.summary()       # (fp32 images of the reference's doubles, bit for bit, up to a libm ulp at a decimal tie)
 
 
-def test_rollout_equals_repeated_step_and_fused_autoreset():
-    scn = swarm(12, 1.2, 9)
-    E, nm, T = 40, 10, 30
+@pytest.mark.parametrize("geom", ["swarm12", "wl4", "wl4_small", "c3_16", "swarm20_nm16", "cluster200", "sliced256", "sliced64"])
+def test_rollout_equals_repeated_step_and_fused_autoreset(geom):
+    """A T-step uaisa_rollout with the fused reset policy == T x (uaisa_step + uaisa_autoreset), bit for bit, in every geometry of the kernel
+    (warp-local, CTA + re-observe compaction, thread-block cluster, neighbour slices).  The launch is cut into uneven chunks so that both the
+    deferred re-observation (steps t < T-1 of a launch: evaluated inside PASS A of step t+1) and the in-step one (last step) are compared."""
+    scn, E, nm, T, kw = {
+        "swarm12": (lambda: swarm(12, 1.2, 9), 40, 10, 30, {}),
+        "wl4": (scenario_c1, 75, 10, 40, {}),
+        "wl4_small": (lambda: swarm(4, 0.8, 2), 33, 3, 40, {}),
+        "c3_16": (lambda: scenario_c3(seed=5, n_scenarios=3, n_drones=16, n_buildings=6), 24, 10, 30, {}),
+        "swarm20_nm16": (lambda: swarm(20, 1.3, 4), 13, 16, 30, {}),
+        "cluster200": (lambda: scenario_c4(seed=2, n_scenarios=1, n_drones=200), 3, 10, 14, {"threads_per_block": 64}),
+        "sliced256": (lambda: scenario_c4(seed=3, n_scenarios=2, n_drones=256), 3, 10, 14, {"threads_per_block": 64, "neighbor_slices": 2}),
+        "sliced64": (lambda: scenario_c4(seed=4, n_scenarios=1, n_drones=64), 5, 10, 20, {"threads_per_block": 64, "neighbor_slices": 2}),
+    }[geom]
+    scn = scn()
     rng = np.random.default_rng(0)
     A = E * scn.N
     acts = torch.from_numpy(np.round(rng.uniform(-1, 1, (T, A, 3)), 2).astype(np.float32)).cuda()
-    a = VecMdin(scn, E, neighbors_num=nm); b = VecMdin(scn, E, neighbors_num=nm)
+    e2s = (np.arange(E) % scn.S).astype(np.int32) if getattr(scn, "S", 1) > 1 else None
+    a = VecMdin(scn, E, env2scenario=e2s, neighbors_num=nm, **kw); b = VecMdin(scn, E, env2scenario=e2s, neighbors_num=nm, **kw)
     a.reset(); b.reset()
-    names = ("obs", "count", "nbr", "reward", "done", "info", "finish")
     out = {"obs": torch.zeros((T, A, a.obs_dim), device="cuda"), "count": torch.zeros((T, A), dtype=torch.uint8, device="cuda"),
            "nbr": torch.zeros((T, A, nm), dtype=torch.int32, device="cuda"), "reward": torch.zeros((T, A), device="cuda"),
            "done": torch.zeros((T, A), dtype=torch.uint8, device="cuda"), "info": torch.zeros((T, A), dtype=torch.uint8, device="cuda"),
            "finish": torch.zeros((T, A), dtype=torch.uint8, device="cuda")}
-    a.rollout(acts, out, auto_reset=True, max_ep_len=12)
+    s = 0
+    for chunk in (7, 1, 2, T):                       # launches of 7, 1, 2 and the remaining steps
+        n = min(chunk, T - s)
+        if n <= 0:
+            break
+        a.rollout(acts[s:s + n], {k: v[s:s + n] for k, v in out.items()}, auto_reset=True, max_ep_len=12)
+        s += n
+    resets = rows = 0
     for t in range(T):
         b.step(acts[t])
         for k in ("reward", "done", "info", "finish"):
             assert torch.equal(getattr(b, k).view(-1), out[k][t].view(-1)) or (k == "reward" and torch.equal(torch.nan_to_num(b.reward, 7.0), torch.nan_to_num(out[k][t], 7.0))), (t, k)
         b.autoreset(max_ep_len=12)
+        resets += int(b.reset_mask.sum()); rows += int(b.count.sum())
         for k in ("obs", "count", "nbr"):
-            assert torch.equal(getattr(b, k), out[k][t]), (t, k)
+            assert torch.equal(getattr(b, k), out[k][t]), (geom, t, k)
+    assert resets > 0, "the reset policy never fired: the test compares nothing"
+    if geom in ("swarm12", "swarm20_nm16", "c3_16", "cluster200", "sliced256"):
+        assert rows > 0, "no neighbour row in any re-observed env"
     sa, sb = a.get_state(), b.get_state()
     for k in sa:
         assert torch.equal(sa[k], sb[k]), k

@@ -509,7 +509,7 @@ __global__ void __launch_bounds__(UAISA_LB_THREADS, (MAXT <= 128 ? UAISA_MINB128
                         if (cone_time(P, d.vx, d.vy, d.vz, C.radius, so, sst, ex_, ey_, ez_, g, tt, md, iet)) {
                             if (ev) { vo_any = true; if (tt < tmin) tmin = tt; }
                             if (ph != PH_A || ev == 0) {
-                                const double ah = py_round2_hundredths(asin(g.R / sqrt(g.s2)));   // get_alpha, vel_obs3D.py:8-17
+                                const double ah = py_round2_hundredths(rare_asin(g.R / sqrt(g.s2)));   // get_alpha, vel_obs3D.py:8-17
                                 top.insert(cap, iet, md, j, (int)ah);
                             }
                         }
@@ -542,10 +542,10 @@ __global__ void __launch_bounds__(UAISA_LB_THREADS, (MAXT <= 128 ? UAISA_MINB128
                     float fs[OBS_SELF];
 #pragma unroll
                     for (int q = 0; q < OBS_SELF; q++) fs[q] = np_round2_f32(self[q]);
-                    float chk = 0.f;
+                    float chk = fs[0];
 #pragma unroll
-                    for (int q = 0; q < OBS_SELF; q++) chk += fs[q] * 0.f;      // NaN iff some value is NaN/Inf
-                    bad |= (chk != chk);
+                    for (int q = 1; q < OBS_SELF; q++) chk += fs[q];            // NaN or Inf iff some value is (finite values of this size cannot overflow)
+                    bad |= (chk * 0.f != 0.f);
                     if ((P.obs_dim & 1) == 0) {
 #pragma unroll
                         for (int q = 0; q < OBS_SELF; q += 2) reinterpret_cast<float2 *>(wobs)[q >> 1] = make_float2(fs[q], fs[q + 1]);
@@ -591,7 +591,7 @@ __global__ void __launch_bounds__(UAISA_LB_THREADS, (MAXT <= 128 ? UAISA_MINB128
                 const double vel_pen = (vden != 0.0) ? fast_div(vnum, vden) : vnum / vden;   // IEEE inf/nan when des = 0 (ir_gym.py:88)
                 const double ap_ = angle_punish(d0, d1, d2, ax, ay, az);
                 double safety = 0;
-                if (vo_any) { double urg = 0; if (tmin < 2) urg = -8.0 * exp(-tmin / 0.5); safety = -2.5 + urg; }
+                if (vo_any) { double urg = 0; if (tmin < 2) urg = -8.0 * rare_exp(-tmin / 0.5); safety = -2.5 + urg; }
                 rA = np_round3(ap_ + vel_pen + safety);
                 RG_MARK(RG_REWARD_A);
                 // ---------------------------------------------------- MOVE: drone.move_forward (drone.py:96-129,431-490)
@@ -646,12 +646,12 @@ __global__ void __launch_bounds__(UAISA_LB_THREADS, (MAXT <= 128 ? UAISA_MINB128
             if (col) rB = -50.0;
             else {
                 double rew = 0;
-                if (arr_now) rew += 3.0 * pow(0.95, (double)((C.n - 1) - d.i));
+                if (arr_now) rew += 3.0 * rare_pow(0.95, (double)((C.n - 1) - d.i));
                 if (dest_now) rew += 20.0;
                 const double dev_pen = -1.5 * fast_div(2.0, 1.0 + exp(-(dev * 10.0 - 5.0) / 0.3));
                 double ex_pen = 0;
                 const double exlen = d.real_len - C.route_len + 4.0;
-                if (exlen > 0) { ex_pen = -0.3 * log(exlen + 1.0 + 1e-6); if (ex_pen < -6.0 || ex_pen != ex_pen) ex_pen = -6.0; }
+                if (exlen > 0) { ex_pen = -0.3 * rare_log(exlen + 1.0 + 1e-6); if (ex_pen < -6.0 || ex_pen != ex_pen) ex_pen = -6.0; }
                 rB = np_round3(rew + dev_pen + ex_pen);
             }
             RG_MARK(RG_B_REWARD);

@@ -123,6 +123,20 @@ __device__ __forceinline__ double np_round3(double x) { double k = rint(x * 1000
 // (float)np.round(x, 2): the fp32 image of rint(x*100)/100 equals the fp32 image of rint(x*100)*0.01
 // (k/100 is never within 2^-30 of an fp32 rounding tie unless it is exact; checked exhaustively, ibid.)
 __device__ __forceinline__ float np_round2_f32(double x) { return (float)(rint(x * 100.0) * 0.01); }
+// Rare libm paths.  Inlined, each is 60-170 instructions in the middle of the hot instruction stream that every warp has to branch over (the
+// kernel's second largest stall reason is `no_instruction`); moving them out of line (-DUAISA_RARE_NOINLINE) was MEASURED 3-4 % slower on the
+// sparse workloads (call ABI: more spills around the call sites) and 1 % faster on configs[2] -- so they stay inline.
+#ifdef UAISA_RARE_NOINLINE
+#define UAISA_RARE_ATTR __noinline__
+#else
+#define UAISA_RARE_ATTR __forceinline__
+#endif
+static __device__ UAISA_RARE_ATTR double rare_exp(double x) { return exp(x); }
+static __device__ UAISA_RARE_ATTR double rare_log(double x) { return log(x); }
+static __device__ UAISA_RARE_ATTR double rare_pow(double x, double y) { return pow(x, y); }
+static __device__ UAISA_RARE_ATTR double rare_fmod(double x, double y) { return fmod(x, y); }
+static __device__ UAISA_RARE_ATTR double rare_asin(double x) { return asin(x); }
+static __device__ UAISA_RARE_ATTR double rare_acos(double x) { return acos(x); }
 // sqrt(x) <= T without the square root unless x is within 1e-14 of T^2 (NaN -> false)
 static __device__ __noinline__ bool sqrt_le_exact(double x, double T) { return sqrt(x) <= T; }   // rare: kept out of line (i-cache)
 __device__ __forceinline__ bool sqrt_le_band(double x, double T, double lo, double hi) {
@@ -168,7 +182,7 @@ __device__ __forceinline__ double py_mod360(double x) {  // drone.py:457, Python
         const double m = (x >= 360.0) ? x - 360.0 : x;     // fmod(x, 360), sign of x
         return (m < 0.0) ? m + 360.0 : m + 0.0;            // (-0.0 + 0.0 = +0.0; a tiny negative m rounds up to 360.0 exactly like CPython)
     }
-    double m = fmod(x, 360.0);
+    double m = rare_fmod(x, 360.0);
     if (m != 0.0) { if (m < 0.0) m += 360.0; } else m = 0.0;
     return m;
 }
@@ -357,10 +371,10 @@ __device__ __forceinline__ int cone_screen(const PairGeom &g) {
 }
 __device__ __forceinline__ bool cone_exact(const PairGeom &g, double &alpha_h) {
     const double nab = sqrt(g.s2);
-    alpha_h = py_round2_hundredths(asin(g.R / nab));       // get_alpha, vel_obs3D.py:8-17 (IEEE ops: rare path)
+    alpha_h = py_round2_hundredths(rare_asin(g.R / nab));       // get_alpha, vel_obs3D.py:8-17 (IEEE ops: rare path)
     const double AB = nab * sqrt(g.b2);
     const double cosang = (AB != 0.0) ? g.dab / AB : 0.0;
-    const double beta_h = rint(acos(cosang) * 100.0);      // get_beta: unclamped arccos, numpy rounding
+    const double beta_h = rint(rare_acos(cosang) * 100.0); // get_beta: unclamped arccos, numpy rounding
     return alpha_h > beta_h;                               // NaN beta -> outside, as in the reference
 }
 // Returns true when the expected collision time is below the threshold (vo_flag); then t_out, md, iet are valid.

@@ -12,7 +12,8 @@ the env kernel writes them.  A drone without neighbours feeds ONE all-zero row (
 what the zero padding already is, so step 0 of the GRU runs densely for everybody and only the (few) agents
 with two or more rows go through the sequential part.
 
-The GEMMs are library calls (cuBLAS through torch); the fused tcgen05 forward is the next step.
+The rollout forward is the fused tcgen05 kernel (uaisa_ppo/fused.py); in the update the two MLPs run through _MlpTc (csrc/uaisa_mlp.cu, tcgen05)
+when `tc_mlp` is set, through torch (cuBLAS) otherwise.
 """
 from __future__ import annotations
 
@@ -70,6 +71,83 @@ class _ReaderStep0(torch.autograd.Function):
         if rc:
             raise RuntimeError("uaisa_reader_bwd failed (%d)" % rc)
         return (None, None, *grads)
+
+
+class _MlpTc(torch.autograd.Function):
+    """One 268-256-256-nout MLP head (ReLU, ReLU, linear output; the actor's Tanh stays outside) on the tcgen05 tensor cores: forward, input
+    gradient and weight gradients are launches of ONE GEMM kernel (csrc/uaisa_mlp.cu: TF32 operands, fp32 accumulation in TMEM, fused bias /
+    ReLU / output-layer / ReLU-mask epilogues, split-K vector atomics for the weight gradients) plus two small CUDA-core kernels -- instead of
+    torch autograd's cuBLAS SIMT fp32 GEMMs (policy_rnn_ac.py:206-257 forward, multi_ppo.py:379-404 backward through autograd)."""
+
+    SPLITS = 74     # split-K CTAs per 128-row tile of a weight gradient (x 2 tiles = 148 CTAs)
+
+    @staticmethod
+    def _lib():
+        import ctypes as C
+        from uaisa_env import _capi
+        return C, _capi.lib()
+
+    @staticmethod
+    def _gemm(L, C, s, A, lda, a_mn, Bm, ldb, b_mn, Cm, ldc, M, N, K, splits, epi, bias=None, mask=None, ldm=0, W3=None, b3=None, Y=None, nout=0):
+        p = lambda t: None if t is None else C.c_void_p(t.data_ptr())  # noqa: E731
+        rc = L.uaisa_mlp_gemm(p(A), lda, a_mn, p(Bm), ldb, b_mn, p(Cm), ldc, M, N, K, splits, epi, p(bias), p(mask), ldm, p(W3), p(b3), p(Y), nout, s)
+        if rc:
+            raise RuntimeError("uaisa_mlp_gemm failed (%d)" % rc)
+
+    @staticmethod
+    def forward(ctx, feat, W1, b1, W2, b2, W3, b3):
+        C, L = _MlpTc._lib()
+        B, nout, dev = int(feat.shape[0]), int(W3.shape[0]), feat.device
+        s = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        H1 = torch.empty((B, 256), dtype=torch.float32, device=dev)
+        H2 = torch.empty((B, 256), dtype=torch.float32, device=dev)
+        y = torch.empty((B, nout), dtype=torch.float32, device=dev)
+        _MlpTc._gemm(L, C, s, feat, 268, 0, W1, 268, 0, H1, 256, B, 256, 268, 1, 1, bias=b1)                                  # H1 = relu(feat W1^T + b1)
+        _MlpTc._gemm(L, C, s, H1, 256, 0, W2, 256, 0, H2, 256, B, 256, 256, 1, 2, bias=b2, W3=W3, b3=b3, Y=y, nout=nout)      # H2 = relu(H1 W2^T + b2), y = H2 W3^T + b3
+        ctx.save_for_backward(feat, W1, W2, W3, H1, H2)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        C, L = _MlpTc._lib()
+        feat, W1, W2, W3, H1, H2 = ctx.saved_tensors
+        B, nout, dev = int(feat.shape[0]), int(W3.shape[0]), feat.device
+        s = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        p = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
+        dy = dy.contiguous()
+        z = lambda *shape: torch.zeros(shape, dtype=torch.float32, device=dev)  # noqa: E731
+        dW1, db1, dW2, db2, dW3, db3 = z(256, 268), z(256), z(256, 256), z(256), z(nout, 256), z(nout)
+        dZ2 = torch.empty((B, 256), dtype=torch.float32, device=dev)
+        dZ1 = torch.empty((B, 256), dtype=torch.float32, device=dev)
+        if L.uaisa_mlp_out_bwd(p(dy), p(H2), p(W3), B, nout, p(dZ2), p(dW3), p(db3), p(db2), s):                              # dZ2, db2, dW3, db3
+            raise RuntimeError("uaisa_mlp_out_bwd failed")
+        sp = max(1, min(_MlpTc.SPLITS, (B + 31) // 32))
+        _MlpTc._gemm(L, C, s, dZ2, 256, 1, H1, 256, 1, dW2, 256, 256, 256, B, sp, 4)                                          # dW2 = dZ2^T H1       (K = batch)
+        _MlpTc._gemm(L, C, s, dZ2, 256, 0, W2, 256, 1, dZ1, 256, B, 256, 256, 1, 3, mask=H1, ldm=256)                         # dZ1 = (dZ2 W2) * (H1 > 0)
+        if L.uaisa_colsum(p(dZ1), B, 256, p(db1), s):                                                                         # db1
+            raise RuntimeError("uaisa_colsum failed")
+        _MlpTc._gemm(L, C, s, dZ1, 256, 1, feat, 268, 1, dW1, 268, 256, 268, B, sp, 4)                                        # dW1 = dZ1^T feat
+        dfeat = None
+        if ctx.needs_input_grad[0]:
+            dfeat = torch.empty((B, 268), dtype=torch.float32, device=dev)
+            _MlpTc._gemm(L, C, s, dZ1, 256, 0, W1, 268, 1, dfeat, 268, B, 268, 256, 1, 0)                                     # dfeat = dZ1 W1
+        return dfeat, dW1, db1, dW2, db2, dW3, db3
+
+
+def _tc_mlp_ok(net, feat):
+    """The tcgen05 MLP path applies to the reference architecture only: Linear(268,256) ReLU Linear(256,256) ReLU Linear(256,nout<=3) + output activation."""
+    lin = [m for m in net if isinstance(m, nn.Linear)]
+    return (feat.is_cuda and feat.dtype == torch.float32 and feat.is_contiguous() and feat.shape[1] == 268 and len(lin) == 3 and len(net) == 6
+            and isinstance(net[1], nn.ReLU) and isinstance(net[3], nn.ReLU)
+            and tuple(lin[0].weight.shape) == (256, 268) and tuple(lin[1].weight.shape) == (256, 256) and lin[2].weight.shape[1] == 256 and lin[2].weight.shape[0] <= 3
+            and all(q.is_contiguous() for l in lin for q in (l.weight, l.bias)))
+
+
+def _run_mlp(net, feat, tc: bool):
+    if tc and _tc_mlp_ok(net, feat):
+        l0, l1, l2 = net[0], net[2], net[4]
+        return net[5](_MlpTc.apply(feat, l0.weight, l0.bias, l1.weight, l1.bias, l2.weight, l2.bias))
+    return net(feat)
 
 
 class rnn_Reader(nn.Module):   # policy_rnn_ac.py:75-168 (mode 'biGRU')
@@ -156,8 +234,10 @@ class GaussianActor(nn.Module):   # policy_rnn_ac.py:191-235
         self.net_out = mlp([obs_dim] + list(hidden_sizes) + [act_dim], activation, output_activation)
         self.log_std = nn.Parameter(torch.as_tensor(-1 * np.ones(act_dim, dtype=np.float32)))
 
+    tc_mlp = False      # MLP forward / backward through csrc/uaisa_mlp.cu (tcgen05, TF32 operands); set by PPOTrainer for the update
+
     def distribution_from_features(self, feat, std_factor=1.0):
-        mu = self.net_out(feat)
+        mu = _run_mlp(self.net_out, feat, self.tc_mlp)
         std = torch.clamp(std_factor * torch.exp(self.log_std) + 1e-6, min=1e-4, max=10.0)
         return Normal(mu, std, validate_args=False)   # validation would synchronise (and break graph capture)
 
@@ -167,6 +247,8 @@ class Critic(nn.Module):   # policy_rnn_ac.py:238-257
         super().__init__()
         self.v_net = mlp([obs_dim] + list(hidden_sizes) + [1], activation, output_activation)
         self.rnn_reader = rnn_reader
+
+    tc_mlp = False
 
 
 class rnn_ac(nn.Module):   # policy_rnn_ac.py:31-72, defaults of train_process.py:37-48
@@ -186,7 +268,7 @@ class rnn_ac(nn.Module):   # policy_rnn_ac.py:31-72, defaults of train_process.p
         iteration does not use (its forward would be thrown away): the skipped entry comes back as None."""
         feat = self.features(obs, count, multi_cap, index)
         dist = self.pi.distribution_from_features(feat, std_factor) if heads != "v" else None
-        v = torch.squeeze(self.v.v_net(feat), -1) if heads != "pi" else None
+        v = torch.squeeze(_run_mlp(self.v.v_net, feat, self.v.tc_mlp), -1) if heads != "pi" else None
         logp = dist.log_prob(act).sum(-1) if (act is not None and dist is not None) else None
         return dist, v, logp
 

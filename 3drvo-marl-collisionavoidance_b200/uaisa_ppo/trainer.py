@@ -56,6 +56,7 @@ class PPOConfig:                      # train_process.py:53-63 defaults
     use_fused_policy: bool = True     # rollout forward through the fused tcgen05 kernels (TF32 operands, fp32 accumulation)
     fused_kernel: str = "full"        # "full": csrc/uaisa_policy_fwd.cu (one kernel, in-kernel recurrence); "split": round-1 K6a + K6b pair
     multi_cap_frac: float = 1.0 / 64  # static capacity of the multi-row GRU path in the captured step (fraction of A)
+    tc_mlp: bool = True               # update: actor / critic MLP forward + backward on tcgen05 (csrc/uaisa_mlp.cu, TF32 operands) instead of torch autograd / cuBLAS fp32
 
 
 def gae(rew, val, cut, gamma, lam):
@@ -146,6 +147,7 @@ class PPOTrainer:
             for p in self.ac.parameters():
                 dist.broadcast(p.data, 0)
             torch.manual_seed(seed + 1000 * dist.get_rank())   # same weights, different exploration noise per shard
+        self.ac.pi.tc_mlp = self.ac.v.tc_mlp = bool(self.cfg.tc_mlp)
         self.flat = FlatParams(self.ac, self.dev)
         self.pi_opt = FlatAdam(self.flat.n, self.cfg.pi_lr, self.dev)        # Adam(ac.pi.parameters()): reader + net_out + log_std = [pi_lo, n)
         self.vf_opt = FlatAdam(self.flat.n, self.cfg.vf_lr, self.dev)        # Adam(ac.v.parameters()):  v_net + reader = [0, v_hi)   (multi_ppo.py:115-116)
@@ -411,7 +413,8 @@ class PPOTrainer:
             self.fused.refresh()          # repack the updated weights in place (addresses stay fixed: the captured rollout step stays valid)
         ctl = self._ctl.tolist()          # the update's only host read: iterations applied / early-stop latch
         self.update_path = (("CUDA graph per iteration" if graphed else "eager iterations") + "; " + ("reader forward/backward kernels (uaisa_reader_fwd/bwd) + " if u["cap"] < 0 and self.ac.pi.rnn_reader.fused_step0 else "")
-                            + "torch autograd GEMMs for the MLPs (cuBLAS) + flat-bucket all-reduce + fused clip/Adam kernel")
+                            + ("MLP forward / dgrad / wgrad on tcgen05 (uaisa_mlp_gemm, TF32 operands)" if cfg.tc_mlp else "torch autograd GEMMs for the MLPs (cuBLAS fp32)")
+                            + " + flat-bucket all-reduce + fused clip/Adam kernel")
         self.stats.update(update_prepare_ms=ev[0].elapsed_time(ev[1]), update_pi_ms=ev[1].elapsed_time(ev[2]), update_v_ms=ev[2].elapsed_time(ev[3]))
         self.stats.update(pi_iters=int(ctl[1]), early_stop=bool(ctl[0]), loss_v=float(u["loss_v"]), kl=float(self.flat.g[self.flat.n]), loss_pi=float(self.flat.g[self.flat.n + 1]),
                           passes_pi=ctl[1] * mb / n, passes_v=n_v * mb / n, mean_ret=float(torch.nan_to_num(self._ret, 0.0, 0.0, 0.0).mean()))

@@ -215,6 +215,21 @@ int uaisa_reader_fwd(const float *obs, const int64_t *idx, int32_t B, int32_t ob
 int uaisa_reader_bwd(const float *obs, const int64_t *idx, int32_t B, int32_t obs_dim, const float *const *params, const float *dfeat, const float *stats,
                      float *const *grads, void *stream);
 
+/* ---- actor / critic MLP forward and backward of the PPO update on the tensor cores (csrc/uaisa_mlp.cu) -----------------------------------------
+ * Replaces torch autograd's GEMMs for GaussianActor.net_out / Critic.v_net (policy_rnn_ac.py:206-257; backward through multi_ppo.py:379-404).
+ * uaisa_mlp_gemm:  C[M][N] (+)= A * B^T, tcgen05.mma kind::tf32 (fp32 storage, TF32 operand precision, fp32 accumulation), N <= 288.
+ *   a_mn = 0: A is stored [M][lda] (K contiguous); a_mn = 1: A is stored [K][lda] (M contiguous) -- likewise b_mn for B ([N][ldb] / [K][ldb]).
+ *   splits > 1 cuts K over that many CTAs per row tile; it requires epi = 4 and a C the caller has zeroed (or wants added to).
+ *   epi: 0 store | 1 relu(acc + bias[n]) | 2 = 1 plus Y[m][o] = sum_n C[m][n] W3[o][n] + b3[o] (o < nout <= 3; C may be NULL) |
+ *        3 acc where mask[m][n] > 0 else 0 (mask [M][ldm]) | 4 atomic add into C.
+ * uaisa_mlp_out_bwd: dZ2[b][j] = H2[b][j] > 0 ? sum_o dy[b][o] W3[o][j] : 0; ADDS db2[j], dW3[o][j], db3[o] (hidden width 256, nout <= 3).
+ * uaisa_colsum: out[j] += sum_r X[r][j].   All asynchronous on `stream`, capturable in a CUDA graph; 0 ok, -1 bad arguments, -2 launch failure. */
+int uaisa_mlp_gemm(const float *A, int32_t lda, int32_t a_mn, const float *B, int32_t ldb, int32_t b_mn, float *C, int32_t ldc, int32_t M, int32_t N, int32_t K,
+                    int32_t splits, int32_t epi, const float *bias, const float *mask, int32_t ldm, const float *W3, const float *b3, float *Y, int32_t nout,
+                    void *stream);
+int uaisa_mlp_out_bwd(const float *dy, const float *H2, const float *W3, int32_t B, int32_t nout, float *dZ2, float *dW3, float *db3, float *db2, void *stream);
+int uaisa_colsum(const float *X, int32_t rows, int32_t cols, float *out, void *stream);
+
 /* ---- latency-optimised host round trip ------------------------------------------------------------------------
  * One env step with HOST action in / HOST results out, returned in the reference's own ragged spirit: the 12 self
  * values of every observation plus only the neighbour rows that exist (an observation is 12 + 9*max(k,1) values in

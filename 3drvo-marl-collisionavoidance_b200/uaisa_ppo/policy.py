@@ -45,13 +45,14 @@ class _ReaderStep0(torch.autograd.Function):
         B = int(index.shape[0]) if index is not None else int(obs.shape[0])
         feat = torch.empty((B, 268), dtype=torch.float32, device=obs.device)
         stats = torch.empty((B, 2), dtype=torch.float32, device=obs.device)
+        hsum = torch.empty((B, 256), dtype=torch.float32, device=obs.device)      # h_fwd + h_bwd before the LayerNorm: spares the backward one gate evaluation
         ptrs = (C.c_void_p * 8)(*[p.data_ptr() for p in params])
         s = C.c_void_p(torch.cuda.current_stream(obs.device).cuda_stream)
         rc = L.uaisa_reader_fwd(C.c_void_p(obs.data_ptr()), None if index is None else C.c_void_p(index.data_ptr()), B, int(obs.shape[1]), ptrs,
-                                C.c_void_p(feat.data_ptr()), C.c_void_p(stats.data_ptr()), s)
+                                C.c_void_p(feat.data_ptr()), C.c_void_p(stats.data_ptr()), C.c_void_p(hsum.data_ptr()), s)
         if rc:
             raise RuntimeError("uaisa_reader_fwd failed (%d)" % rc)
-        ctx.save_for_backward(obs, index, stats, *params)
+        ctx.save_for_backward(obs, index, stats, hsum, *params)
         return feat
 
     @staticmethod
@@ -59,7 +60,7 @@ class _ReaderStep0(torch.autograd.Function):
         import ctypes as C
         from uaisa_env import _capi
         L = _capi.lib()
-        obs, index, stats, *params = ctx.saved_tensors
+        obs, index, stats, hsum, *params = ctx.saved_tensors
         B = int(stats.shape[0])
         dfeat = dfeat.contiguous()
         grads = [torch.zeros_like(p) for p in params]
@@ -67,7 +68,7 @@ class _ReaderStep0(torch.autograd.Function):
         gptrs = (C.c_void_p * 8)(*[g.data_ptr() for g in grads])
         s = C.c_void_p(torch.cuda.current_stream(obs.device).cuda_stream)
         rc = L.uaisa_reader_bwd(C.c_void_p(obs.data_ptr()), None if index is None else C.c_void_p(index.data_ptr()), B, int(obs.shape[1]), ptrs,
-                                C.c_void_p(dfeat.data_ptr()), C.c_void_p(stats.data_ptr()), gptrs, s)
+                                C.c_void_p(dfeat.data_ptr()), C.c_void_p(stats.data_ptr()), C.c_void_p(hsum.data_ptr()), gptrs, s)
         if rc:
             raise RuntimeError("uaisa_reader_bwd failed (%d)" % rc)
         return (None, None, *grads)

@@ -452,7 +452,7 @@ def measure_ppo(D, args, envs_per_gpu, epochs=1, warm=1):
         torch.backends.cuda.matmul.allow_tf32 = True
     scn = scenario_c1()
     env = VecMdin(scn, envs_per_gpu, neighbors_num=NM, device=D.dev)
-    cfg = PPOConfig(steps_per_epoch=args.ppo_steps)
+    cfg = PPOConfig(steps_per_epoch=args.ppo_steps, tc_mlp=not args.no_tc_mlp)
     tr = PPOTrainer(env, cfg=cfg)
     for _ in range(warm):
         tr.train_epoch()
@@ -471,16 +471,18 @@ def measure_ppo(D, args, envs_per_gpu, epochs=1, warm=1):
     samples = D.world * env.A * cfg.steps_per_epoch * epochs
     n = env.A * cfg.steps_per_epoch
     out = {"metric": "PPO samples/sec (rollout + GAE + update)", "value": samples / (ms_max * 1e-3), "unit": "samples/s", "epochs_timed": epochs, "epochs_warmup": warm,
-           "ms_per_epoch": ms_max / epochs, "rollout_s_per_epoch": ro / epochs, "update_s_per_epoch": up / epochs, "per_epoch": per_epoch, "dtype": "tf32" if args.tf32 else "f32",
+           "ms_per_epoch": ms_max / epochs, "rollout_s_per_epoch": ro / epochs, "update_s_per_epoch": up / epochs, "per_epoch": per_epoch, "dtype": "tf32" if (args.tf32 or cfg.tc_mlp) else "f32",
            "workload": "configs[4]: %d envs x 4 drones per GPU x %d GPUs, %d steps/epoch, rnn_ac 680991 params, reference PPO hyper-parameters" % (envs_per_gpu, D.world, cfg.steps_per_epoch),
            "minibatch": cfg.minibatch, "pi_iters": cfg.train_pi_iters, "v_iters": cfg.train_v_iters,
-           "passes_per_sample": {"pi": tr.stats.get("pi_iters", 0) * min(cfg.minibatch, n) / n, "v": cfg.train_v_iters * min(cfg.minibatch, n) / n,
+           "minibatch_per_rank": int(tr._u["mb"]),
+           "passes_per_sample": {"pi": tr.stats.get("pi_iters", 0) * int(tr._u["mb"]) / n, "v": cfg.train_v_iters * int(tr._u["mb"]) / n,
                                  "note": "the reference makes 50+50 FULL-BATCH passes over each robot's 300 samples (multi_ppo.py:355-376); here each iteration is one "
                                          "minibatch drawn without replacement from the whole [T x A] buffer -- samples/s is NOT a like-for-like ratio to the reference's"},
            "policy": tr.policy_path, "update": tr.update_path,
            "gpu_launches_per_epoch": {"env (action transform, step, reset policy) + fused policy forward": 4 * cfg.steps_per_epoch, "gae": 1,
                                       "clip/Adam (prepare + apply)": 2 * (cfg.train_pi_iters + cfg.train_v_iters), "policy repack": 1,
-                                      "note": "own kernels per epoch (graph replays included); the update's GEMMs are torch / cuBLAS"},
+                                      "update forward/backward (reader fwd + bwd, 6 x uaisa_mlp_gemm, out_bwd, colsum)": 10 * (cfg.train_pi_iters + cfg.train_v_iters) if cfg.tc_mlp else 2 * (cfg.train_pi_iters + cfg.train_v_iters),
+                                      "note": "own kernels per epoch (graph replays included)" + ("" if cfg.tc_mlp else "; the update's MLP GEMMs are torch / cuBLAS")},
            "stats": {k: (float(v) if not isinstance(v, (int, float, str)) else v) for k, v in tr.stats.items()}}
     tr.close()
     env.close()
@@ -505,6 +507,7 @@ def main():
     ap.add_argument("--threads-per-block", type=int, default=0)
     ap.add_argument("--slices", type=int, default=0, help="neighbour slices per drone (0 = auto)")
     ap.add_argument("--tf32", action="store_true")
+    ap.add_argument("--no-tc-mlp", action="store_true", help="PPO update MLPs through torch autograd / cuBLAS fp32 instead of the tcgen05 kernels (A/B)")
     ap.add_argument("--ppo-envs", type=int, default=0, help="envs per GPU for PPO (0 = 65536 / world size)")
     ap.add_argument("--ppo-steps", type=int, default=300)
     ap.add_argument("--ppo-epochs", type=int, default=1)

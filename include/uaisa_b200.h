@@ -210,10 +210,11 @@ int uaisa_clip_adam(float *p, float *g, float *m, float *v, int64_t n_total, int
  * params / grads: 8 DEVICE pointers in torch layouts: weight_ih_l0 [768][9], bias_ih_l0 [768], bias_hh_l0 [768], the same three of the reverse direction,
  * ln.weight [268], ln.bias [268].  obs [*][obs_dim]; idx (may be NULL): int64[B], the row of `obs` each sample reads (the minibatch is never materialised);
  * feat / dfeat [B][268]; stats [B][2] (LayerNorm mean and rstd, saved by the forward for the backward).  uaisa_reader_bwd ADDS this minibatch's gradients to
- * `grads`.  Asynchronous on `stream`, capturable in a CUDA graph. */
-int uaisa_reader_fwd(const float *obs, const int64_t *idx, int32_t B, int32_t obs_dim, const float *const *params, float *feat, float *stats, void *stream);
+ * `grads`.  hsum (may be NULL in both): [B][256], the pre-LayerNorm sum of the two directions' states -- saved by the forward, it spares the backward a second
+ * evaluation of the gates.  Asynchronous on `stream`, capturable in a CUDA graph. */
+int uaisa_reader_fwd(const float *obs, const int64_t *idx, int32_t B, int32_t obs_dim, const float *const *params, float *feat, float *stats, float *hsum, void *stream);
 int uaisa_reader_bwd(const float *obs, const int64_t *idx, int32_t B, int32_t obs_dim, const float *const *params, const float *dfeat, const float *stats,
-                     float *const *grads, void *stream);
+                     const float *hsum, float *const *grads, void *stream);
 
 /* ---- actor / critic MLP forward and backward of the PPO update on the tensor cores (csrc/uaisa_mlp.cu) -----------------------------------------
  * Replaces torch autograd's GEMMs for GaussianActor.net_out / Critic.v_net (policy_rnn_ac.py:206-257; backward through multi_ppo.py:379-404).

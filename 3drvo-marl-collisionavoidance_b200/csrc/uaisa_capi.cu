@@ -158,12 +158,21 @@ int uaisa_create(const UaisaConfig *cfg, UaisaHandle **out) {
     const int minthreads = cluster ? 32 : ((N + 31) / 32) * 32;
     const int nch = (N + 31) / 32;                // 32-neighbour chunks of the pair loop
     P.tile0_bytes = ((32 * P.obs_dim * 4) + 15) & ~15; P.tile1_bytes = ((32 * (P.nm ? P.nm : 1) * 4) + 15) & ~15;
+    if (maxr > 4 && P.tile0_bytes > 2048) P.tile0_bytes = 2048;     // many-neighbour kernels: shared memory decides the resident CTAs; the fill is then a few bulk stores instead of one
+    const bool force_compact = std::getenv("UAISA_FORCE_COMPACT") != nullptr, no_compact = std::getenv("UAISA_NO_COMPACT") != nullptr;
+    // CTA-level compaction of the re-observe phase pays only with several warps per CTA and more than a handful of
+    // drones per env (measured: N=16 +7 %, N=4 +2 % at 128 threads, -10 % with single-warp CTAs)
+    auto compact_for = [&](int th, int s) { return !cluster && s == 1 && th >= 128 && (N > 4 || force_compact) && !no_compact; };
+#ifndef UAISA_REGS_DENSE
+#define UAISA_REGS_DENSE 128
+#endif
+    auto regs_for = [&](int s) { return (maxr > 4 && s == 1) ? UAISA_REGS_DENSE : 168; };   // register caps of the instantiations (uaisa_kernels.cu, Makefile)
     auto grid_for = [&](int th) { return cluster ? (long long)E * ((N + th - 1) / th) : (long long)(E + (th / N) - 1) / (th / N); };
     auto smem_for = [&](int th, int s) {
         const size_t epc = cluster ? 1 : th / N, cols = cluster ? N : th;
         return sizeof(double) * 8 * cols + sizeof(int) * 2 * epc + 16 + P.tile0_bytes + P.tile1_bytes   // exchange tile, env bits, TMA fill tiles
                + (maxr > 4 ? (size_t)th * s * maxr * 24 : 0)                                       // + shared top-nm lists (one set per slice)
-               + (size_t)th * (4 * 8 + 3 * 4) + sizeof(int) * (epc + 2) + 16                         // + re-observe compaction
+               + (compact_for(th, s) ? (size_t)th * (4 * 8 + 3 * 4) + sizeof(int) * epc : 0) + sizeof(int) * 2 + 32   // + re-observe compaction
                + cols * 16 + 16                                                                    // + fp32 position copies
                + (size_t)(s - 1) * th * 12 + (size_t)th * 4 + 16                                     // + helpers' partial results, owners' activity
                + (size_t)th * 80 + epc * 24 + 16                                                   // + per-drone route cache, map sizes
@@ -175,21 +184,34 @@ int uaisa_create(const UaisaConfig *cfg, UaisaHandle **out) {
         while (threads / 2 >= minthreads && threads / 2 >= 32 && (!cluster || (N + threads / 2 - 1) / (threads / 2) <= 8) &&
                grid_for(threads) < 2 * prop.multiProcessorCount) threads /= 2;
     }
+    // Cost model per (egos per CTA, slices): waves of the grid over the resident CTA slots x (32-neighbour chunks per slice + 1 chunk-equivalent
+    // of per-ego work), stretched by the warps sharing an SM.
+    auto est_for = [&](int th, int s) -> double {
+        const int block = th * s;
+        long long per_sm = 4 * (16384 / ((long long)regs_for(s) * 32)) / (block / 32), by_smem = (long long)prop.sharedMemPerMultiprocessor / (long long)(smem_for(th, s) + 1024);
+        if (by_smem < per_sm) per_sm = by_smem;
+        if (per_sm > 32) per_sm = 32;
+        if (per_sm < 1) return 1e300;
+        const long long cap = per_sm * prop.multiProcessorCount, g = grid_for(th), waves = (g + cap - 1) / cap;
+        const double wpsm = (double)(g < cap ? g : cap) * (block / 32) / prop.multiProcessorCount;
+        return (double)waves * ((nch + s - 1) / s + 1.0) * (1.0 + 0.04 * wpsm);
+    };
+    if (auto_threads && !cluster && grid_for(threads) >= 2 * prop.multiProcessorCount) {
+        // Wave quantisation: a T-step launch keeps every CTA resident for all T steps, so a grid of 1.15 waves costs 2 (configs[2]: 2048 warps on
+        // 1776 warp slots ran at 1.24e9 agent-steps/s, the 1776 warps of 3552 envs at 1.79e9, profiles/wave_quant.py).  Smaller CTAs pack more
+        // warps next to the shared-memory limit; take them when the model predicts >= 3 % less time.
+        double best = est_for(threads, 1); int bt = threads;
+        for (int th = threads - 32; th >= 32; th -= 32) {
+            if (th < minthreads || th / N < 1) continue;
+            const double e_ = est_for(th, 1);
+            if (e_ < 0.97 * best) { best = e_; bt = th; }
+        }
+        threads = bt;
+    }
     if (auto_threads && !wl && maxr > 4 && nch > 1) {
         // Many neighbours per ego and few egos (dense airspace): add neighbour slices -- helper threads that walk a share of each
-        // ego's neighbours and hand partial results to the owner through shared memory.  Cost model per (egos per CTA, slices):
-        // waves of the grid over the resident CTA slots x (32-neighbour chunks per slice + 1 chunk-equivalent of per-ego work),
-        // stretched by the warps sharing an SM.  The unsliced geometry stays unless slicing is predicted >= 10 % faster.
-        auto est_for = [&](int th, int s) -> double {
-            const int block = th * s;
-            long long per_sm = 65536 / (168LL * block), by_smem = (long long)prop.sharedMemPerMultiprocessor / (long long)(smem_for(th, s) + 1024);
-            if (by_smem < per_sm) per_sm = by_smem;
-            if (per_sm > 32) per_sm = 32;
-            if (per_sm < 1) return 1e300;
-            const long long cap = per_sm * prop.multiProcessorCount, g = grid_for(th), waves = (g + cap - 1) / cap;
-            const double wpsm = (double)(g < cap ? g : cap) * (block / 32) / prop.multiProcessorCount;
-            return (double)waves * ((nch + s - 1) / s + 1.0) * (1.0 + 0.04 * wpsm);
-        };
+        // ego's neighbours and hand partial results to the owner through shared memory.  The unsliced geometry stays unless slicing is
+        // predicted >= 10 % faster.
         double best = 0.9 * est_for(threads, 1); int bt = threads, bs = 1;
         for (int th = threads; th >= 32; th -= 32) {
             if (th < minthreads || (cluster && (N + th - 1) / th > 8)) continue;
@@ -207,16 +229,14 @@ int uaisa_create(const UaisaConfig *cfg, UaisaHandle **out) {
     } else if (threads < N || threads > 128 || threads % 32) { delete h; return fail(UAISA_EINVAL, "threads_per_block must be a multiple of 32 in [n_drones, 128]"); }
     P.dsmem = (cluster && !std::getenv("UAISA_CLUSTER_L2")) ? 1 : 0;   // exchange through distributed shared memory unless asked for the L2 path
     h->threads = threads; P.threads = threads; P.slices = slices; P.envs_per_cta = cluster ? 1 : threads / N;
-    // CTA-level compaction of the re-observe phase pays only with several warps per CTA and more than a handful of
-    // drones per env (measured: N=16 +7 %, N=4 +2 % at 128 threads, -10 % with single-warp CTAs)
     P.defer_obs = std::getenv("UAISA_NO_DEFER") ? 0 : 1;   // T-step launches: re-observation of step t < T-1 rides on PASS A of step t+1 (A/B switch)
-    P.compact = (!cluster && slices == 1 && threads >= 128 && (N > 4 || std::getenv("UAISA_FORCE_COMPACT")) && !std::getenv("UAISA_NO_COMPACT")) ? 1 : 0;
+    P.compact = compact_for(threads, slices) ? 1 : 0;
     h->grid = cluster ? E * P.cl : (E + P.envs_per_cta - 1) / P.envs_per_cta;
     h->smem = smem_for(threads, slices);
     if (std::getenv("UAISA_VERBOSE")) std::fprintf(stderr, "[uaisa] E=%d N=%d: %s, %d egos x %d slices per CTA, %d CTAs%s, %zu B smem\n", E, N, wl ? "warp-local" : "CTA", threads, slices, h->grid, cluster ? " (clustered)" : "", h->smem);
-    if (wl) h->kernel = need <= 4 ? uaisa_env_kernel<4, 128, true, false> : need <= 10 ? uaisa_env_kernel<10, 128, true, false> : uaisa_env_kernel<16, 128, true, false>;
+    if (wl) h->kernel = need <= 4 ? uaisa_env_kernel<4, 128, true, false> : need <= 10 ? uaisa_env_kernel_d<10, 128, true, false> : uaisa_env_kernel_d<16, 128, true, false>;
     else if (slices > 1 || (maxr > 4 && std::getenv("UAISA_FORCE_SL"))) h->kernel = need <= 10 ? uaisa_env_kernel<10, 128, false, true> : uaisa_env_kernel<16, 128, false, true>;
-    else h->kernel = need <= 4 ? uaisa_env_kernel<4, 128, false, false> : need <= 10 ? uaisa_env_kernel<10, 128, false, false> : uaisa_env_kernel<16, 128, false, false>;
+    else h->kernel = need <= 4 ? uaisa_env_kernel<4, 128, false, false> : need <= 10 ? uaisa_env_kernel_d<10, 128, false, false> : uaisa_env_kernel_d<16, 128, false, false>;
     if (h->smem > (size_t)prop.sharedMemPerBlockOptin) { delete h; return fail(UAISA_EINVAL, "shared memory per CTA exceeds the device limit; lower threads_per_block"); }
     cudaError_t e = cudaFuncSetAttribute(reinterpret_cast<const void *>(h->kernel), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem);
     if (e != cudaSuccess) { delete h; return cuda_fail(e, "cudaFuncSetAttribute"); }

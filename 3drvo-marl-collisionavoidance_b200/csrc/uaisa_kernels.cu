@@ -96,12 +96,21 @@ enum Region : int { RG_PROLOGUE = 0, RG_FILL, RG_SYNC, RG_DRONESTATE, RG_PAIRS, 
 #define UAISA_F32_SMALL 0   // experiments: fp32 range pre-gate also in the few-neighbour kernels (MAXR <= 4)
 #endif
 #ifndef UAISA_MINB128
-#define UAISA_MINB128 3   // CTAs of 128 threads per SM the register allocator must leave room for
+#define UAISA_MINB128 3   // CTAs of 128 threads per SM the register allocator must leave room for (few-neighbour kernels, MAXR <= 4: 168 registers)
 #endif
+// The many-neighbour instantiations without helper slices (MAXR > 4: top-nm lists in shared memory) are compiled in a translation unit of their own
+// (-DUAISA_TU_DENSE -maxrregcount=128, see the Makefile).  The register file is split over the four schedulers of an SM (16384 each), so a warp of
+// 168-register threads leaves room for 3 warps per scheduler = 12 per SM -- and so does any count down to 129; 128 registers make it 16.  For these
+// kernels 128 registers cost ~50 bytes of spills (12 % per warp at equal occupancy) but let configs[2]'s 2048 warps run as ONE wave of 64-thread
+// CTAs instead of 1.15 waves that cost 2: 1.24e9 -> 1.58e9 agent-steps/s (profiles/wave_quant.py, profiles/variants.sh).  The sliced instantiations
+// (configs[3]) measured 4 % slower at 128 and keep 168, like the few-neighbour kernels (200+ bytes of spills at any lower cap).
+// (The cap has to come from -maxrregcount ALONE: next to a __launch_bounds__ the same cap spills 190 bytes instead of 16, __maxnreg__ 240.)
 // WL ("warp local"): N divides 32, so every env lives inside one warp -- all CTA barriers become __syncwarp(),
 // the per-env reductions of the reset policy become ballots, and each warp clears its own 32 output rows.
 template <int MAXR, int MAXT, bool WL, bool SL>
-#ifdef UAISA_NO_LB   // experiments: register cap from -maxrregcount instead
+#if defined(UAISA_TU_DENSE)   // register cap from -maxrregcount alone (with a __launch_bounds__ next to it the same cap spills 190 bytes instead of 16)
+__global__ void uaisa_env_kernel_d(
+#elif defined(UAISA_NO_LB)
 __global__ void uaisa_env_kernel(
 #else
 __global__ void __launch_bounds__(UAISA_LB_THREADS, (MAXT <= 128 ? UAISA_MINB128 : 1)) uaisa_env_kernel(
@@ -129,11 +138,7 @@ __global__ void __launch_bounds__(UAISA_LB_THREADS, (MAXT <= 128 ? UAISA_MINB128
     uint4 *tile0 = reinterpret_cast<uint4 *>(take(P.tile0_bytes));                                   // one warp's 32 observation rows of zeros
     uint4 *tile1 = reinterpret_cast<uint4 *>(take(P.tile1_bytes));                                   // 32 rows of nbr = -1
     unsigned char *stop = take((unsigned)(S * TopList<MAXR>::smem_bytes(threads)));                  // top-nm lists of the MAXR > 4 instantiations, one set per slice
-    // CTA-level compaction of the re-observe phase: parked owner state + list of touched envs
-    double *spk_d = reinterpret_cast<double *>(take(8u * 4u * threads));                             // [4][threads] yaw pitch real_len max_dev
-    int *spk_i = reinterpret_cast<int *>(take(4u * 3u * threads));                                   // [3][threads] wp index, flags, staged
-    int *s_list = reinterpret_cast<int *>(take(4u * P.envs_per_cta));                                // [envs_per_cta]
-    int *s_nt = reinterpret_cast<int *>(take(8u));                                                   // [2] (double-buffered counter)
+    int *s_nt = reinterpret_cast<int *>(take(8u));                                                   // [2] (double-buffered counter of the re-observe compaction)
     align16();
     float4 *sxf = reinterpret_cast<float4 *>(take(16u * sst));                                       // [sst] fp32 copies of the positions
     double *spart_t = reinterpret_cast<double *>(take(8u * (S - 1) * threads));                      // [S-1][threads] helpers' partial tmin
@@ -149,6 +154,12 @@ __global__ void __launch_bounds__(UAISA_LB_THREADS, (MAXT <= 128 ? UAISA_MINB128
     // round trip (4.4 % of configs[2]'s stall samples sat on these loads, profiles/r2/ncu_env_c3.txt).
     const int Mc = P.bld_cache ? P.M : 0;          // (host: some scenario has cylinders and M <= 16)
     double *sbld = reinterpret_cast<double *>(take(8u * 4u * (unsigned)Mc * P.envs_per_cta));        // [envs_per_cta][Mc][4]
+    // CTA-level compaction of the re-observe phase: parked owner state + list of touched envs.  Reserved only when the geometry can compact, and
+    // LAST in the carve-up: with the conditional size in the middle of it the few-neighbour kernels measured 5 % slower (same work, different
+    // register allocation around the offsets that follow).
+    double *spk_d = reinterpret_cast<double *>(take(0u));                                            // [4][threads] yaw pitch real_len max_dev
+    int *spk_i = reinterpret_cast<int *>(spk_d + 4 * threads);                                       // [3][threads] wp index, flags, staged
+    int *s_list = spk_i + 3 * threads;                                                               // [envs_per_cta]
     {
         const bool clm_ = !WL && P.cl > 1;
         const int e0_ = clm_ ? (int)(blockIdx.x / P.cl) : blockIdx.x * P.envs_per_cta;
@@ -771,6 +782,7 @@ __global__ void __launch_bounds__(UAISA_LB_THREADS, (MAXT <= 128 ? UAISA_MINB128
     }
 }
 
+#ifndef UAISA_TU_DENSE   // (the small kernels live in the default translation unit only)
 // cal_des_list (ir_gym.py:44-46)
 __global__ void uaisa_cal_des_kernel(const __grid_constant__ Params P, float *des) {
     const int a = blockIdx.x * blockDim.x + threadIdx.x;
@@ -950,10 +962,20 @@ __global__ void uaisa_pack_kernel(int A, int obs_dim, int nm, const float *obs, 
     }
 }
 
+#endif  // !UAISA_TU_DENSE
+
 #define UAISA_INST(R, T, W, S) template __global__ void uaisa_env_kernel<R, T, W, S>(const __grid_constant__ Params, const __grid_constant__ Launch);
+#ifdef UAISA_TU_DENSE
+#define UAISA_INST_D(R, T, W, S) template __global__ void uaisa_env_kernel_d<R, T, W, S>(const __grid_constant__ Params, const __grid_constant__ Launch);
+UAISA_INST_D(10, 128, true, false) UAISA_INST_D(16, 128, true, false)
+UAISA_INST_D(10, 128, false, false) UAISA_INST_D(16, 128, false, false)
+#undef UAISA_INST_D
+#else
+// (The default translation unit keeps ALL instantiations, also the ones whose 128-register twins in the other unit are the ones launched.)
 UAISA_INST(4, 128, true, false) UAISA_INST(10, 128, true, false) UAISA_INST(16, 128, true, false)
 UAISA_INST(4, 128, false, false) UAISA_INST(10, 128, false, false) UAISA_INST(16, 128, false, false)
 UAISA_INST(10, 128, false, true) UAISA_INST(16, 128, false, true)      // with neighbour slices (helper threads)
+#endif
 #undef UAISA_INST
 
 }  // namespace uaisa

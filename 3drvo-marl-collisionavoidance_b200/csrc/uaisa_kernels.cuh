@@ -479,6 +479,8 @@ __device__ __forceinline__ double angle_punish(double A0, double A1, double A2, 
 
 template <int MAXR, int MAXT, bool WL, bool SL>
 __global__ void uaisa_env_kernel(const __grid_constant__ Params P, const __grid_constant__ Launch L);
+template <int MAXR, int MAXT, bool WL, bool SL>      // the same kernel compiled under a 128-register cap (many-neighbour instantiations without slices)
+__global__ void uaisa_env_kernel_d(const __grid_constant__ Params P, const __grid_constant__ Launch L);
 __global__ void uaisa_cal_des_kernel(const __grid_constant__ Params P, float *des);
 __global__ void uaisa_rvo_select_kernel(const __grid_constant__ Params P, double vmax, double acceler, float *vel_out, float *ctrl_out);
 __global__ void uaisa_action_transform_kernel(const __grid_constant__ Params P, const float *a_inc, float acceler, float *a_inc_rounded, float *action);

@@ -156,6 +156,18 @@ __global__ void __launch_bounds__(GM_T, NT <= 256 ? 2 : 1) uaisa_mlp_gemm_kernel
     const bool vecC = ((reinterpret_cast<uintptr_t>(P.C) & 15) == 0) && (P.ldc & 3) == 0;
     const bool vecM = P.mask && ((reinterpret_cast<uintptr_t>(P.mask) & 15) == 0) && (P.ldm & 3) == 0;
     float yacc[3] = {0.f, 0.f, 0.f};
+    // EPI_MASK: the saved activations of the NEXT 16 columns are fetched while the current ones are processed (23 % of the kernel's stall samples
+    // sat on these loads when they were issued at their use, profiles/r2/ncu_mlp_gemm.txt)
+    float4 hm[4];
+    const bool mvec = P.epi == EPI_MASK && mok && vecM;
+    auto fetch_mask = [&](int n0_) {
+        if (mvec && n0_ + 15 < P.N) {
+            const float4 *mp4 = reinterpret_cast<const float4 *>(P.mask + (size_t)m * P.ldm + n0_);
+#pragma unroll
+            for (int i4 = 0; i4 < 4; i4++) hm[i4] = __ldg(mp4 + i4);
+        }
+    };
+    fetch_mask(half * HC);
 #pragma unroll 1
     for (int cb = 0; cb < HC; cb += 16) {
         const int n0 = half * HC + cb;
@@ -179,9 +191,13 @@ __global__ void __launch_bounds__(GM_T, NT <= 256 ? 2 : 1) uaisa_mlp_gemm_kernel
             if (mok) {
                 const float *mp = P.mask + (size_t)m * P.ldm + n0;
                 if (vecM && n0 + 15 < P.N) {
+                    float4 hc[4];
+#pragma unroll
+                    for (int i4 = 0; i4 < 4; i4++) hc[i4] = hm[i4];
+                    if (cb + 16 < HC) fetch_mask(n0 + 16);
 #pragma unroll
                     for (int i4 = 0; i4 < 4; i4++) {
-                        const float4 h = __ldg(reinterpret_cast<const float4 *>(mp) + i4);
+                        const float4 h = hc[i4];
                         v[4 * i4] = h.x > 0.f ? v[4 * i4] : 0.f; v[4 * i4 + 1] = h.y > 0.f ? v[4 * i4 + 1] : 0.f;
                         v[4 * i4 + 2] = h.z > 0.f ? v[4 * i4 + 2] : 0.f; v[4 * i4 + 3] = h.w > 0.f ? v[4 * i4 + 3] : 0.f;
                     }

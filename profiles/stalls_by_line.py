@@ -29,6 +29,8 @@ for r in csv.reader(io.StringIO(out)):
         hdr = r; continue
     if hdr and r and len(r) == len(hdr):
         data.append(r)
+if len(data) > len(seq) and len(data) % len(seq) == 0:      # several launches of the kernel in one report: take the last one
+    data = data[-len(seq):]
 assert len(seq) == len(data), (len(seq), len(data), "the report and the library are different builds")
 ss = hdr.index("# Samples"); ie = hdr.index("Instructions Executed")
 cols = [i for i, h in enumerate(hdr) if h.startswith("stall_") and "Not Issued" not in h]

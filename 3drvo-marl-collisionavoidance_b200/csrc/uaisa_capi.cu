@@ -176,7 +176,8 @@ int uaisa_create(const UaisaConfig *cfg, UaisaHandle **out) {
                + cols * 16 + 16                                                                    // + fp32 position copies
                + (size_t)(s - 1) * th * 12 + (size_t)th * 4 + 16                                     // + helpers' partial results, owners' activity
                + (size_t)th * 80 + epc * 24 + 16                                                   // + per-drone route cache, map sizes
-               + (size_t)(P.M <= 16 ? P.M : 0) * 32 * epc;                                         // + cylinders of the CTA's envs (used when a scenario has any)
+               + (size_t)(P.M <= 16 ? P.M : 0) * 32 * epc                                          // + cylinders of the CTA's envs (used when a scenario has any)
+               + ((wl && maxr <= 4 && s == 2) ? (size_t)th * (64 + 80 + 16 + 8) + 16 : 0);          // + owner / helper split: pre-move tile, helpers' route cache, mailboxes
     };
     const bool auto_threads = threads <= 0;
     if (auto_threads) {
@@ -219,9 +220,16 @@ int uaisa_create(const UaisaConfig *cfg, UaisaHandle **out) {
         }
         threads = bt; slices = bs;
     }
+    // Owner / helper split of the few-neighbour warp-local kernels (slices = 2 there): a helper warp per owner warp runs PASS A while the owner moves and
+    // runs PASS B.  It shortens the dependent chain of a step, which is all a small batch is bound by; a batch that fills the machine would only pay
+    // for the extra warps.  Taken when owners + helpers fit the resident warp slots of that instantiation (compiled without a register cap: 8 per SM).
+    const bool can_split = wl && maxr <= 4;
+    if (can_split && auto_threads && cfg->neighbor_slices == 0 && !std::getenv("UAISA_NO_SPLIT") &&
+        (long long)E * N <= 4LL * 32 * prop.multiProcessorCount) { slices = 2; if (threads > 64) threads = 64; }
     if (cfg->neighbor_slices > 0) {
         slices = cfg->neighbor_slices;
-        if (slices > 1 && (wl || maxr <= 4 || slices * threads > 128 || slices > nch)) { delete h; return fail(UAISA_EINVAL, "neighbor_slices > 1 needs n_drones > 32, nm > 4 and slices * threads_per_block <= 128"); }
+        if (can_split && slices == 2) { if (threads > 64) { if (!auto_threads) { delete h; return fail(UAISA_EINVAL, "the owner / helper split needs threads_per_block <= 64"); } threads = 64; } }
+        else if (slices > 1 && (wl || maxr <= 4 || slices * threads > 128 || slices > nch)) { delete h; return fail(UAISA_EINVAL, "neighbor_slices > 1 needs n_drones > 32, nm > 4 and slices * threads_per_block <= 128 (or = 2 for the owner / helper split of warp-local envs with nm <= 4 rows)"); }
     }
     if (cluster) {
         if (threads > 128 || threads % 32 || (N + threads - 1) / threads > 8) { delete h; return fail(UAISA_EINVAL, "n_drones > 128 needs threads_per_block in {32,64,96,128} with at most 8 CTAs per env"); }
@@ -234,7 +242,8 @@ int uaisa_create(const UaisaConfig *cfg, UaisaHandle **out) {
     h->grid = cluster ? E * P.cl : (E + P.envs_per_cta - 1) / P.envs_per_cta;
     h->smem = smem_for(threads, slices);
     if (std::getenv("UAISA_VERBOSE")) std::fprintf(stderr, "[uaisa] E=%d N=%d: %s, %d egos x %d slices per CTA, %d CTAs%s, %zu B smem\n", E, N, wl ? "warp-local" : "CTA", threads, slices, h->grid, cluster ? " (clustered)" : "", h->smem);
-    if (wl) h->kernel = need <= 4 ? uaisa_env_kernel<4, 128, true, false> : need <= 10 ? uaisa_env_kernel_d<10, 128, true, false> : uaisa_env_kernel_d<16, 128, true, false>;
+    if (wl && slices == 2) h->kernel = uaisa_env_kernel<4, 128, true, true>;
+    else if (wl) h->kernel = need <= 4 ? uaisa_env_kernel<4, 128, true, false> : need <= 10 ? uaisa_env_kernel_d<10, 128, true, false> : uaisa_env_kernel_d<16, 128, true, false>;
     else if (slices > 1 || (maxr > 4 && std::getenv("UAISA_FORCE_SL"))) h->kernel = need <= 10 ? uaisa_env_kernel<10, 128, false, true> : uaisa_env_kernel<16, 128, false, true>;
     else h->kernel = need <= 4 ? uaisa_env_kernel<4, 128, false, false> : need <= 10 ? uaisa_env_kernel_d<10, 128, false, false> : uaisa_env_kernel_d<16, 128, false, false>;
     if (h->smem > (size_t)prop.sharedMemPerBlockOptin) { delete h; return fail(UAISA_EINVAL, "shared memory per CTA exceeds the device limit; lower threads_per_block"); }

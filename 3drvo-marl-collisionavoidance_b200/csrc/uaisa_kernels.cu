@@ -123,6 +123,11 @@ __global__ void __launch_bounds__(UAISA_LB_THREADS, (MAXT <= 128 ? UAISA_MINB128
     // copy of the env's exchange columns in its own shared memory; at each publish point the CTAs write their slice to a
     // double-buffered global (L2) exchange array, meet at the hardware cluster barrier and reload all N columns.
     const bool CLM = !WL && P.cl > 1;
+    // SPLIT (WL && SL, few-neighbour kernels, small batches): the CTA carries a HELPER warp per owner warp.  PASS A (pre-move dronestate, pair pass,
+    // rvo reward, and the deferred re-observation row) does not feed the move -- only the reward -- so the helper runs it on the pre-move state the
+    // owner publishes while the owner moves and runs PASS B: the dependent chain of a step shrinks from A + MOVE + B to max(A, MOVE + B).  What a
+    // latency-bound batch (one warp per scheduler or less) gains is exactly that; a saturating batch would only pay for the second warp.
+    constexpr bool SPLIT = WL && SL;
     constexpr bool F32G = (MAXR > 4) || (UAISA_F32_SMALL != 0);                  // stage 1a runs in fp32 on float copies of the positions
     const int sst = CLM ? P.N : threads;                                         // column stride of the exchange tile
     // Shared memory is carved up by byte offsets from the one __shared__ array, never through integer round trips of a pointer, so
@@ -160,6 +165,14 @@ __global__ void __launch_bounds__(UAISA_LB_THREADS, (MAXT <= 128 ? UAISA_MINB128
     double *spk_d = reinterpret_cast<double *>(take(0u));                                            // [4][threads] yaw pitch real_len max_dev
     int *spk_i = reinterpret_cast<int *>(spk_d + 4 * threads);                                       // [3][threads] wp index, flags, staged
     int *s_list = spk_i + 3 * threads;                                                               // [envs_per_cta]
+    // SPLIT (never together with the compaction): the pre-move exchange tile the helpers read while the owners republish `sx`, the helpers' own
+    // route cache, and the owner <-> helper mailboxes (rvo reward and deviation of PASS A; waypoint index and rows staged by the previous PASS B)
+    double *sxA = sx, *swp_h = swp, *s_rA = nullptr, *s_dvA = nullptr; int *s_wpi = nullptr, *s_stg = nullptr;
+    if constexpr (SPLIT) {
+        sxA = reinterpret_cast<double *>(take(8u * 8u * threads)); swp_h = reinterpret_cast<double *>(take(8u * 10u * threads));
+        s_rA = reinterpret_cast<double *>(take(8u * threads)); s_dvA = reinterpret_cast<double *>(take(8u * threads));
+        s_wpi = reinterpret_cast<int *>(take(4u * threads)); s_stg = reinterpret_cast<int *>(take(4u * threads));
+    }
     {
         const bool clm_ = !WL && P.cl > 1;
         const int e0_ = clm_ ? (int)(blockIdx.x / P.cl) : blockIdx.x * P.envs_per_cta;
@@ -220,7 +233,10 @@ __global__ void __launch_bounds__(UAISA_LB_THREADS, (MAXT <= 128 ? UAISA_MINB128
         FILL_WP(tid);
         if (k == 0 || CLM) { const int le_ = CLM ? 0 : le; smap[0 * P.envs_per_cta + le_] = __ldg(P.map + 3 * scn); smap[1 * P.envs_per_cta + le_] = __ldg(P.map + 3 * scn + 1); smap[2 * P.envs_per_cta + le_] = __ldg(P.map + 3 * scn + 2); }
         if (!CLM) { sx[6 * sst + scol] = C.radius; sx[7 * sst + scol] = C.prio; }      // constant over the launch
+        if constexpr (SPLIT) { sxA[6 * sst + scol] = C.radius; sxA[7 * sst + scol] = C.prio; }
     }
+    int h_i = -1;                                      // SPLIT helper: waypoint index its route cache holds
+    if (SPLIT && helper && evalid) { scn = __ldg(P.env2scn + env); C.set(P, scn * N + k); }
     if (CLM) {   // every CTA of the cluster needs the constants of ALL drones of the env
         const int s_ = __ldg(P.env2scn + env0);
         for (int j = tix; j < N; j += blockDim.x) { sx[6 * sst + j] = __ldg(P.radius + s_ * N + j); sx[7 * sst + j] = __ldg(P.prio + s_ * N + j); }
@@ -247,7 +263,7 @@ __global__ void __launch_bounds__(UAISA_LB_THREADS, (MAXT <= 128 ? UAISA_MINB128
         const bool clear_rows = is_step && !L.hp_self;   // (the host round trip reads back only the rows that exist: its staging buffers are not cleared)
         if (clear_rows) {   // every row is written this step: clear the output region once, coalesced 16-byte stores
             if (WL) {    // my warp's 32 rows
-                const int w0 = tid - lane, nw = min(32, nag_here - w0);
+                const int w0 = tid - lane, nw = (SPLIT ? !helper : helper) ? 0 : min(32, nag_here - w0);      // (SPLIT: the helper warp clears its owner's rows)
                 if (nw > 0) {
                     const size_t abase = (size_t)t * A + (size_t)env0 * N + w0;
                     if (L.obs) {
@@ -261,6 +277,7 @@ __global__ void __launch_bounds__(UAISA_LB_THREADS, (MAXT <= 128 ? UAISA_MINB128
                         else fill_out(reinterpret_cast<uint32_t *>(dst), bytes >> 2, ~0u, lane, 32);
                     }
                     if (lane == 0) bulk_commit();
+                    if constexpr (SPLIT) __syncwarp();       // (fallback stores of the other lanes are ordered before lane 0 raises the flag)
                 }
             } else {
                 const size_t abase = (size_t)t * A + (size_t)ag0;
@@ -282,6 +299,7 @@ __global__ void __launch_bounds__(UAISA_LB_THREADS, (MAXT <= 128 ? UAISA_MINB128
         bool remapped = false, worker = false;
 
         for (int ph = is_step ? PH_A : PH_OBS; ph <= PH_OBS; ph++) {
+            if (SPLIT && helper && ph != PH_A) break;      // a helper only runs PASS A
             bool active = valid;
             RG_MARK(RG_TAIL_B);
             if (ph == PH_OBS) {
@@ -349,7 +367,7 @@ __global__ void __launch_bounds__(UAISA_LB_THREADS, (MAXT <= 128 ? UAISA_MINB128
             // a warp none of whose envs is re-observed has nothing to publish or read (warp-local envs only)
             if (WL && !compact && ph == PH_OBS && !__any_sync(0xffffffffu, active)) continue;      // (the compacted variant meets at CTA barriers)
             // -------------------------------------------------------- publish my state, then read the others'
-            if (WL && clear_rows && ph == PH_B && lane == 0) bulk_wait_all();   // my warp's cleared rows have landed: rows may now be scattered
+            if (WL && !SPLIT && clear_rows && ph == PH_B && lane == 0) bulk_wait_all();   // my warp's cleared rows have landed: rows may now be scattered
             const bool DSM = CLM && P.dsmem;
             if (DSM) cluster_sync_all(); else ENV_SYNC();   // everybody (of the cluster / the CTA) is done reading the previous phase's columns
             if (DSM) {
@@ -379,9 +397,11 @@ __global__ void __launch_bounds__(UAISA_LB_THREADS, (MAXT <= 128 ? UAISA_MINB128
                     if constexpr (F32G) sxf[j] = make_float4((float)x_, (float)y_, (float)z_, 0.f);
                 }
             } else if (valid) {
-                sx[0 * sst + scol] = d.px; sx[1 * sst + scol] = d.py; sx[2 * sst + scol] = d.pz;
-                sx[3 * sst + scol] = d.vx; sx[4 * sst + scol] = d.vy; sx[5 * sst + scol] = d.vz;
+                double *sxw = (SPLIT && ph == PH_A) ? sxA : sx;
+                sxw[0 * sst + scol] = d.px; sxw[1 * sst + scol] = d.py; sxw[2 * sst + scol] = d.pz;
+                sxw[3 * sst + scol] = d.vx; sxw[4 * sst + scol] = d.vy; sxw[5 * sst + scol] = d.vz;
                 if constexpr (F32G) sxf[scol] = make_float4((float)d.px, (float)d.py, (float)d.pz, 0.f);
+                if constexpr (SPLIT) { if (ph == PH_A) { s_wpi[tid] = d.i; s_stg[tid] = staged_prev; } }
             }
             if (ph == PH_OBS && compact) {
                 // Only the envs touched by the reset policy are re-observed (typically a quarter of them, spread over
@@ -409,6 +429,8 @@ __global__ void __launch_bounds__(UAISA_LB_THREADS, (MAXT <= 128 ? UAISA_MINB128
                     C.radius = sx[6 * threads + tt]; C.prio = sx[7 * threads + tt];
                     wa = env_t * N + wk;
                 }
+            } else if (SPLIT && ph == PH_A) {
+                asm volatile("barrier.sync 0;" ::: "memory");    // SPLIT sync #1: the pre-move tile is complete, the helpers start PASS A on it
             } else {
                 if (DSM) cluster_sync_all(); else ENV_SYNC();   // all columns are in place
             }
@@ -417,11 +439,35 @@ __global__ void __launch_bounds__(UAISA_LB_THREADS, (MAXT <= 128 ? UAISA_MINB128
             const bool hact = S > 1 && helper && evalid && (ph != PH_OBS || s_act[tid] != 0);
             // (threads with nothing to do still meet the others at the merge barrier below: barrier.sync without .aligned
             // counts thread arrivals on barrier 0 wherever the instruction sits)
-            if (!active && !hact) { if (S > 1) asm volatile("barrier.sync 0;" ::: "memory"); continue; }
+            if (!active && !hact) {
+                if (S > 1 && !SPLIT) asm volatile("barrier.sync 0;" ::: "memory");
+                if (SPLIT && ((helper && ph == PH_A) || (!helper && ph == PH_B))) asm volatile("barrier.sync 0;" ::: "memory");      // idle lanes still arrive at SPLIT sync #2
+                continue;
+            }
+            const double *sxr = (SPLIT && ph == PH_A) ? sxA : sx;       // the tile this pass reads
+            const bool own_a_skip = SPLIT && !helper && ph == PH_A;    // SPLIT owner in PASS A: publish, then straight to the move
 
             // drone.dronestate (drone.py:254-263): desired velocity + deviation, side effect on max_deviation
             double d0 = 0, d1 = 0, d2 = 0, dev = 0;
-            if (!SL || !helper) {
+            int staged_a = staged_prev;                        // rows PASS B of the previous step left in its slot (SPLIT helper: from the owner's mailbox)
+            if (own_a_skip) {
+            } else if (SPLIT && helper) {   // the ego as its owner just published it; my own route cache follows the published waypoint index
+                d.px = sxA[0 * sst + scol]; d.py = sxA[1 * sst + scol]; d.pz = sxA[2 * sst + scol];
+                d.vx = sxA[3 * sst + scol]; d.vy = sxA[4 * sst + scol]; d.vz = sxA[5 * sst + scol];
+                C.radius = sxA[6 * sst + scol]; C.prio = sxA[7 * sst + scol];
+                staged_a = s_stg[tid];
+                const int wi = s_wpi[tid];
+                if (wi != h_i) {
+                    h_i = wi;
+                    const double *w_ = C.wp(P) + 3 * wi, *wp_ = C.wp(P) + 3 * max(wi - 1, 0), *sg_ = C.seg(P) + 4 * wi;
+                    swp_h[0 * threads + tid] = __ldg(w_); swp_h[1 * threads + tid] = __ldg(w_ + 1); swp_h[2 * threads + tid] = __ldg(w_ + 2);
+                    swp_h[3 * threads + tid] = __ldg(wp_); swp_h[4 * threads + tid] = __ldg(wp_ + 1); swp_h[5 * threads + tid] = __ldg(wp_ + 2);
+                    swp_h[6 * threads + tid] = __ldg(sg_); swp_h[7 * threads + tid] = __ldg(sg_ + 1); swp_h[8 * threads + tid] = __ldg(sg_ + 2); swp_h[9 * threads + tid] = __ldg(sg_ + 3);
+                }
+                cal_des_vel_v(P, d.px, d.py, d.pz, swp_h[0 * threads + tid], swp_h[1 * threads + tid], swp_h[2 * threads + tid], d0, d1, d2);
+                dev = deviation(swp_h[3 * threads + tid], swp_h[4 * threads + tid], swp_h[5 * threads + tid], swp_h[6 * threads + tid], swp_h[7 * threads + tid],
+                                swp_h[8 * threads + tid], swp_h[9 * threads + tid], d.px, d.py, d.pz);
+            } else if (!SL || !helper) {
                 cal_des_vel_v(P, d.px, d.py, d.pz, swp[0 * threads + tt], swp[1 * threads + tt], swp[2 * threads + tt], d0, d1, d2);
                 dev = deviation(swp[3 * threads + tt], swp[4 * threads + tt], swp[5 * threads + tt], swp[6 * threads + tt], swp[7 * threads + tt],
                                 swp[8 * threads + tt], swp[9 * threads + tt], d.px, d.py, d.pz);
@@ -436,10 +482,11 @@ __global__ void __launch_bounds__(UAISA_LB_THREADS, (MAXT <= 128 ? UAISA_MINB128
             bool vo_any = false, col = false; double tmin = CUDART_INF;
             TopList<MAXR> top; top.init(stop + (unsigned)(slice * TopList<MAXR>::smem_bytes(threads)), threads, tid); top.clear();
             int jb_lo = 0, jb_hi = N;                          // my slice: whole 32-neighbour chunks
-            if (S > 1) { const int nch = (N + 31) >> 5; jb_lo = ((slice * nch) / S) << 5; jb_hi = min(N, (((slice + 1) * nch) / S) << 5); }
+            if (S > 1 && !SPLIT) { const int nch = (N + 31) >> 5; jb_lo = ((slice * nch) / S) << 5; jb_hi = min(N, (((slice + 1) * nch) / S) << 5); }
+            if (own_a_skip) jb_hi = jb_lo;                     // (the helper walks the neighbours of PASS A)
             // evaluations of the cones in this pass: ev 1 = the phase's own (the action; 0 when re-observing), ev 0 = the re-observation
             // deferred from the previous step (action 0, list only) -- both on the same stage-1 masks
-            const bool ev0 = (ph == PH_A) && ((S > 1 && helper) ? (defer_on && t > 0 && s_act[tid] != 0) : pend);
+            const bool ev0 = (ph == PH_A) && !own_a_skip && ((S > 1 && helper) ? (defer_on && t > 0 && s_act[tid] != 0) : pend);
             {
                 double bx = (ph == PH_OBS) ? 0.0 : ax, by = (ph == PH_OBS) ? 0.0 : ay, bz = (ph == PH_OBS) ? 0.0 : az;
                 if (np_dot3(bx, by, bz, bx, by, bz) < 1e-10 * (1.0 - 1e-14)) { bx = by = bz = 0.0; }   // norm(a) < 1e-5, rvo_inter.py:118-119
@@ -470,7 +517,7 @@ __global__ void __launch_bounds__(UAISA_LB_THREADS, (MAXT <= 128 ? UAISA_MINB128
                     } else {                                      // a handful of neighbours: the fp64 gate directly
 #pragma unroll 4
                         for (int jj = 0; jj < jn; jj++) {        // straight-line like the fp32 gates: +1 gate (self), no branch (+6..9 % per step)
-                            const int bits = pair_range_fast(P, d.px, d.py, d.pz, sx + wlbase + jb + jj, sst);
+                            const int bits = pair_range_fast(P, d.px, d.py, d.pz, sxr + wlbase + jb + jj, sst);
                             near |= (bits & PB_EVAL) ? (1u << jj) : 0u;
                             slow |= (bits & PB_SLOW) ? (1u << jj) : 0u;
                         }
@@ -479,7 +526,7 @@ __global__ void __launch_bounds__(UAISA_LB_THREADS, (MAXT <= 128 ? UAISA_MINB128
                     if ((near | slow) == 0u) continue;          // nobody in range in this chunk (the common case in sparse airspace): one branch instead of five empty loops
                     for (unsigned m = near; m; m &= m - 1) {     // stage 1b: collision / moving-away gates of the near ones (fp64)
                         const int jj = __ffs(m) - 1;
-                        const int bits = pair_near_fast(P, d.px, d.py, d.pz, d.vx, d.vy, d.vz, C.radius, sx + wlbase + jb + jj, sst);
+                        const int bits = pair_near_fast(P, d.px, d.py, d.pz, d.vx, d.vy, d.vz, C.radius, sxr + wlbase + jb + jj, sst);
                         n_rng += (bits & PB_SAME) ? 0u : 1u;
                         col |= (bits & PB_COL) != 0;
                         cand |= (bits & PB_FULL) ? (1u << jj) : 0u;
@@ -487,7 +534,7 @@ __global__ void __launch_bounds__(UAISA_LB_THREADS, (MAXT <= 128 ? UAISA_MINB128
                     }
                     for (unsigned m = slow; m; m &= m - 1) {     // a squared distance inside a guard band: exact comparisons
                         const int jj = __ffs(m) - 1;
-                        const int bits = pair_gate(P, d.px, d.py, d.pz, d.vx, d.vy, d.vz, C.radius, sx + wlbase + jb + jj, sst);
+                        const int bits = pair_gate(P, d.px, d.py, d.pz, d.vx, d.vy, d.vz, C.radius, sxr + wlbase + jb + jj, sst);
                         n_rng += ((bits & PB_EVAL) && !((near >> jj) & 1u)) ? 1u : 0u;   // (pairs already counted in stage 1b are not counted twice)
                         col |= (bits & PB_COL) != 0;
                         cand |= (bits & PB_FULL) ? (1u << jj) : 0u;
@@ -500,21 +547,21 @@ __global__ void __launch_bounds__(UAISA_LB_THREADS, (MAXT <= 128 ? UAISA_MINB128
                     unsigned ins = 0, amb = 0;
                     for (unsigned m = cand; m; m &= m - 1) {
                         const int jj = __ffs(m) - 1;
-                        PairGeom g; pair_geom(P, d.px, d.py, d.pz, d.vx, d.vy, d.vz, C.radius, C.prio, sx + wlbase + jb + jj, sst, ex_, ey_, ez_, g);
+                        PairGeom g; pair_geom(P, d.px, d.py, d.pz, d.vx, d.vy, d.vz, C.radius, C.prio, sxr + wlbase + jb + jj, sst, ex_, ey_, ez_, g);
                         const int c = cone_screen(g);
                         ins |= (c == 1) ? (1u << jj) : 0u; amb |= (c == 2) ? (1u << jj) : 0u;
                     }
                     // stage 2b: the few ambiguous pairs go through asin/acos with the reference's roundings
                     for (unsigned m = amb; m; m &= m - 1) {
                         const int jj = __ffs(m) - 1;
-                        PairGeom g; pair_geom(P, d.px, d.py, d.pz, d.vx, d.vy, d.vz, C.radius, C.prio, sx + wlbase + jb + jj, sst, ex_, ey_, ez_, g);
+                        PairGeom g; pair_geom(P, d.px, d.py, d.pz, d.vx, d.vy, d.vz, C.radius, C.prio, sxr + wlbase + jb + jj, sst, ex_, ey_, ez_, g);
                         double ah;
                         if (cone_exact(g, ah)) ins |= 1u << jj;
                     }
                     // stage 2c: pairs inside the cone -> expected collision time, vo_flag, row keys
                     for (unsigned m = ins; m; m &= m - 1) {
                         const int jj = __ffs(m) - 1, j = jb + jj;
-                        const double *so = sx + wlbase + j;
+                        const double *so = sxr + wlbase + j;
                         PairGeom g; pair_geom(P, d.px, d.py, d.pz, d.vx, d.vy, d.vz, C.radius, C.prio, so, sst, ex_, ey_, ez_, g);
                         double tt, md, iet;
                         if (cone_time(P, d.vx, d.vy, d.vz, C.radius, so, sst, ex_, ey_, ez_, g, tt, md, iet)) {
@@ -529,6 +576,19 @@ __global__ void __launch_bounds__(UAISA_LB_THREADS, (MAXT <= 128 ? UAISA_MINB128
                 }
             }
             RG_MARK(RG_PAIRS);
+            if constexpr (SPLIT) {
+                // The rows the helper warp cleared at the top of the step must have landed before its owner warp scatters into them: lane 0 of the
+                // helper (the lane that issued the bulk stores) raises a per-warp-pair flag in shared memory, the owner's lanes poll it.  (A named
+                // barrier with arrive / sync would do, but a NON-ALIGNED barrier.arrive executed by a diverged warp -- a partly filled last warp --
+                // faulted with "illegal instruction" on sm_100a.)
+                volatile int *fd = s_nt + (tid >> 5);
+                if (clear_rows && helper) {
+                    if (lane == 0) { bulk_wait_all(); __threadfence_block(); *fd = t + 1; }
+                } else if (clear_rows && ph == PH_B) {
+                    while (*fd < t + 1) { }
+                    __threadfence_block();
+                }
+            }
             if (S > 1) {       // helpers hand their partial results to the owner: flags, earliest collision time, their top-nm lists
                 if constexpr (MAXR > 4) {
                     if (helper) { spart_t[(slice - 1) * threads + tid] = tmin; spart_f[(slice - 1) * threads + tid] = (vo_any ? 1 : 0) | (col ? 2 : 0) | (top.cnt << 2); }
@@ -546,7 +606,7 @@ __global__ void __launch_bounds__(UAISA_LB_THREADS, (MAXT <= 128 ? UAISA_MINB128
             if (ph != PH_A || ev0) {    // (PASS A: the re-observation deferred from the previous step, into THAT step's slot)
                 bool bad = false;
                 const size_t wo = (ph == PH_A) ? OUT_SLOT(wa) - (size_t)A : OUT_SLOT(wa);
-                const int staged_in = (ph == PH_A) ? staged_prev : staged;
+                const int staged_in = (ph == PH_A) ? staged_a : staged;
                 float *const wobs = L.obs ? L.obs + wo * P.obs_dim : nullptr; int *const wnbr = L.nbr ? L.nbr + wo * P.nm : nullptr;
                 if (wobs) {
                     const double self[OBS_SELF] = {d.px, d.py, d.pz, d.vx, d.vy, d.vz, C.radius, C.prio, d0, d1, d2, dev};
@@ -568,7 +628,7 @@ __global__ void __launch_bounds__(UAISA_LB_THREADS, (MAXT <= 128 ? UAISA_MINB128
                 // slot r (least urgent first, most urgent last) = top[cnt-1-r]
                 top.for_each([&](int sl, double t_iet, double t_md, int t_j, int t_ah) {
                     const int r = top.cnt - 1 - sl;
-                    const double *so = sx + wlbase + t_j;
+                    const double *so = sxr + wlbase + t_j;
                     if (wobs) {
                         const double mx = so[0], my = so[sst], mz = so[2 * sst];
                         const double mvx = so[3 * sst], mvy = so[4 * sst], mvz = so[5 * sst], prb = so[7 * sst];
@@ -597,6 +657,7 @@ __global__ void __launch_bounds__(UAISA_LB_THREADS, (MAXT <= 128 ? UAISA_MINB128
             }
             RG_MARK(RG_OBSROW);
             if (ph == PH_A) {
+                if (!own_a_skip) {
                 // ---------------------------------------------------- ir_gym.rvo_reward_cal (ir_gym.py:64-133)
                 const double vnum = 0.2 * fast_sqrt(np_dot3(ax, ay, az, ax, ay, az)), vden = fast_sqrt(np_dot3(d0, d1, d2, d0, d1, d2));
                 const double vel_pen = (vden != 0.0) ? fast_div(vnum, vden) : vnum / vden;   // IEEE inf/nan when des = 0 (ir_gym.py:88)
@@ -604,7 +665,13 @@ __global__ void __launch_bounds__(UAISA_LB_THREADS, (MAXT <= 128 ? UAISA_MINB128
                 double safety = 0;
                 if (vo_any) { double urg = 0; if (tmin < 2) urg = -8.0 * rare_exp(-tmin / 0.5); safety = -2.5 + urg; }
                 rA = np_round3(ap_ + vel_pen + safety);
+                }
                 RG_MARK(RG_REWARD_A);
+                if (SPLIT && helper) {      // hand the reward and the deviation of PASS A to the owner (SPLIT sync #2) and wait for the next step
+                    s_rA[tid] = rA; s_dvA[tid] = dev;
+                    asm volatile("barrier.sync 0;" ::: "memory");
+                    break;
+                }
                 // ---------------------------------------------------- MOVE: drone.move_forward (drone.py:96-129,431-490)
                 const double speed = fast_sqrt(np_dot3(d.vx, d.vy, d.vz, d.vx, d.vy, d.vz));
                 const double acc = np_clip(ax * P.max_acc, -P.max_acc, P.max_acc);
@@ -667,6 +734,12 @@ __global__ void __launch_bounds__(UAISA_LB_THREADS, (MAXT <= 128 ? UAISA_MINB128
             }
             RG_MARK(RG_B_REWARD);
             st_done = col; st_fin = (d.flags & FLAG_DEST) != 0;
+            if constexpr (SPLIT) {          // SPLIT sync #2: the helper's PASS A results (max() commutes: the deviation of PASS A folds in here)
+                asm volatile("barrier.sync 0;" ::: "memory");
+                rA = s_rA[tid];
+                const double dva = s_dvA[tid];
+                if (dva > d.max_dev) d.max_dev = dva;
+            }
             { const size_t o = OUT_SLOT(a);
               if (L.reward) L.reward[o] = (float)(rA + rB);
               if (L.done) L.done[o] = col;
@@ -782,7 +855,7 @@ __global__ void __launch_bounds__(UAISA_LB_THREADS, (MAXT <= 128 ? UAISA_MINB128
     }
 }
 
-#ifndef UAISA_TU_DENSE   // (the small kernels live in the default translation unit only)
+#if !defined(UAISA_TU_DENSE) && !defined(UAISA_TU_SPLIT)   // (the small kernels live in the default translation unit only)
 // cal_des_list (ir_gym.py:44-46)
 __global__ void uaisa_cal_des_kernel(const __grid_constant__ Params P, float *des) {
     const int a = blockIdx.x * blockDim.x + threadIdx.x;
@@ -962,10 +1035,12 @@ __global__ void uaisa_pack_kernel(int A, int obs_dim, int nm, const float *obs, 
     }
 }
 
-#endif  // !UAISA_TU_DENSE
+#endif  // default translation unit
 
 #define UAISA_INST(R, T, W, S) template __global__ void uaisa_env_kernel<R, T, W, S>(const __grid_constant__ Params, const __grid_constant__ Launch);
-#ifdef UAISA_TU_DENSE
+#if defined(UAISA_TU_SPLIT)
+UAISA_INST(4, 128, true, true)          // SPLIT: owner + helper warps (small batches of few-neighbour envs)
+#elif defined(UAISA_TU_DENSE)
 #define UAISA_INST_D(R, T, W, S) template __global__ void uaisa_env_kernel_d<R, T, W, S>(const __grid_constant__ Params, const __grid_constant__ Launch);
 UAISA_INST_D(10, 128, true, false) UAISA_INST_D(16, 128, true, false)
 UAISA_INST_D(10, 128, false, false) UAISA_INST_D(16, 128, false, false)

@@ -90,6 +90,8 @@ def test_edge_shapes():
     lockstep(scenario_world3(), 50, 10, 40, seed=3, threads_per_block=32).assert_parity()
     lockstep(swarm(12, 1.0, 7), 30, 10, 40, seed=4, threads_per_block=64).assert_parity()
     lockstep(scenario_c1(), 9, 10, 40, seed=5, env_train=0).assert_parity()
+    lockstep(scenario_c1(), 37, 10, 60, seed=6, threads_per_block=64, neighbor_slices=2).assert_parity()      # owner / helper split, two warp pairs per CTA
+    lockstep(scenario_c1(), 37, 10, 60, seed=6, neighbor_slices=1).assert_parity()                            # ... and the same batch unsplit
 
 
 @pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
@@ -166,14 +168,16 @@ def test_against_reference_golden_exact(path):
     assert n_inexact <= 2, st.summary()       # (fp32 images of the reference's doubles, bit for bit, up to a libm ulp at a decimal tie)
 
 
-@pytest.mark.parametrize("geom", ["swarm12", "wl4", "wl4_small", "c3_16", "swarm20_nm16", "cluster200", "sliced256", "sliced64"])
+@pytest.mark.parametrize("geom", ["swarm12", "wl4", "wl4_nosplit", "wl4_split64", "wl4_small", "c3_16", "swarm20_nm16", "cluster200", "sliced256", "sliced64"])
 def test_rollout_equals_repeated_step_and_fused_autoreset(geom):
     """A T-step uaisa_rollout with the fused reset policy == T x (uaisa_step + uaisa_autoreset), bit for bit, in every geometry of the kernel
     (warp-local, CTA + re-observe compaction, thread-block cluster, neighbour slices).  The launch is cut into uneven chunks so that both the
     deferred re-observation (steps t < T-1 of a launch: evaluated inside PASS A of step t+1) and the in-step one (last step) are compared."""
     scn, E, nm, T, kw = {
         "swarm12": (lambda: swarm(12, 1.2, 9), 40, 10, 30, {}),
-        "wl4": (scenario_c1, 75, 10, 40, {}),
+        "wl4": (scenario_c1, 75, 10, 40, {}),                                                        # small batch: owner / helper split chosen automatically
+        "wl4_nosplit": (scenario_c1, 75, 10, 40, {"neighbor_slices": 1}),                            # the same through the unsplit warp-local kernel
+        "wl4_split64": (scenario_c1, 203, 10, 40, {"neighbor_slices": 2, "threads_per_block": 64}),   # two owner / helper warp pairs per CTA, ragged last CTA
         "wl4_small": (lambda: swarm(4, 0.8, 2), 33, 3, 40, {}),
         "c3_16": (lambda: scenario_c3(seed=5, n_scenarios=3, n_drones=16, n_buildings=6), 24, 10, 30, {}),
         "swarm20_nm16": (lambda: swarm(20, 1.3, 4), 13, 16, 30, {}),

@@ -346,6 +346,18 @@ int uaisa_rollout(UaisaHandle *h, int32_t T, const float *action, float *obs, ui
     return launch(h, L, stream);
 }
 
+// One env step + the trainer reset policy + the re-observation of the touched envs in ONE launch (what uaisa_step followed by uaisa_autoreset
+// computes, bit for bit): the step of multi_ppo.training_loop (multi_ppo.py:210-281) as the PPO rollout issues it.
+int uaisa_step_autoreset(UaisaHandle *h, const float *action, float *obs, uint8_t *count, int32_t *nbr, float *reward, uint8_t *done, uint8_t *info,
+                         uint8_t *finish, int32_t max_ep_len, int32_t epoch_ended, uint8_t *reset_mask, uint8_t *path_cut, void *stream) {
+    if (!h || !action) return fail(UAISA_EINVAL, "NULL handle or action");
+    Launch L{};
+    L.mode = MODE_STEP; L.T = 1; L.auto_reset = 1; L.max_ep_len = max_ep_len; L.epoch_ended = epoch_ended ? 1 : 0;
+    L.action = action; L.obs = obs; L.count = count; L.nbr = nbr; L.reward = reward; L.done = done; L.info = info; L.finish = finish;
+    L.reset_mask = reset_mask; L.path_cut = path_cut;
+    return launch(h, L, stream);
+}
+
 int uaisa_reset(UaisaHandle *h, const uint8_t *agent_mask, float *obs, uint8_t *count, int32_t *nbr, void *stream) {
     if (!h) return fail(UAISA_EINVAL, "NULL handle");
     Launch L{};

@@ -102,6 +102,16 @@ class VecMdin:
                                          g("info"), g("finish"), int(auto_reset), int(max_ep_len), self._stream()))
         return out
 
+    def step_autoreset(self, action: torch.Tensor, max_ep_len: int = 300, epoch_ended: bool = False):
+        """step() followed by autoreset() in one launch (same outputs, bit for bit): the env part of one trainer iteration (multi_ppo.py:210-281).
+        -> (obs of the next step, reward, done, info, finish, reset_mask, path_cut)."""
+        if action.dtype != torch.float32 or not action.is_cuda or not action.is_contiguous() or action.numel() != self.A * 3:
+            raise ValueError("action must be a contiguous float32 CUDA tensor [E*N, 3]")
+        _capi.check(self.L.uaisa_step_autoreset(self.h, _ptr(action), _ptr(self.obs), _ptr(self.count), _ptr(self.nbr), _ptr(self.reward), _ptr(self.done),
+                                                _ptr(self.info), _ptr(self.finish), int(max_ep_len), int(bool(epoch_ended)), _ptr(self.reset_mask),
+                                                _ptr(self.path_cut), self._stream()))
+        return self.obs, self.reward, self.done, self.info, self.finish, self.reset_mask, self.path_cut
+
     def reset(self, agent_mask: Optional[torch.Tensor] = None, observe: bool = True):
         """mdin.drone_reset (agent_mask None) / drone_reset_one + env_observation (mdin.py:38-46)."""
         if agent_mask is not None and (agent_mask.dtype != torch.uint8 or agent_mask.numel() != self.A or not agent_mask.is_cuda):

@@ -188,11 +188,10 @@ class PPOTrainer:
         stepper = self.fused if self.fused is not None else self.ac
         a_inc, v, logp = stepper.step(env.obs, env.count, cfg.std_factor, multi_cap=cap)                          # :196
         _, a_r = env.action_transform(a_inc, self.action)                                                          # :197-208
-        env.step(self.action)                                                                                      # :210
+        env.step_autoreset(self.action, max_ep_len=cfg.max_ep_len, epoch_ended=epoch_ended)                        # :210 + :226-281 (+ env_observation): one launch
         b["act"].index_copy_(0, t, a_r.unsqueeze(0)); b["rew"].index_copy_(0, t, env.reward.unsqueeze(0))
         b["val"].index_copy_(0, t, v.unsqueeze(0)); b["logp"].index_copy_(0, t, logp.unsqueeze(0))
         self._ndone += env.done.sum()
-        env.autoreset(max_ep_len=cfg.max_ep_len, epoch_ended=epoch_ended)                                          # :226-281 (+ env_observation)
         b["cut"].index_copy_(0, t, env.path_cut.unsqueeze(0))
         t += 1
         if not self._single_graph:

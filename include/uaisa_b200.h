@@ -125,6 +125,11 @@ int uaisa_rollout(UaisaHandle *h, int32_t T, const float *action, float *obs, ui
                   float *reward, uint8_t *done, uint8_t *info, uint8_t *finish, int32_t auto_reset,
                   int32_t max_ep_len, void *stream);
 
+/* uaisa_step followed by uaisa_autoreset in ONE launch (same outputs, bit for bit): the env part of one iteration of multi_ppo.training_loop
+ * (multi_ppo.py:210-281).  reset_mask / path_cut [A] may be NULL. */
+int uaisa_step_autoreset(UaisaHandle *h, const float *action, float *obs, uint8_t *count, int32_t *nbr, float *reward, uint8_t *done,
+                         uint8_t *info, uint8_t *finish, int32_t max_ep_len, int32_t epoch_ended, uint8_t *reset_mask, uint8_t *path_cut, void *stream);
+
 /* state access (teacher forcing, drone_list[i].vel): copies between the handle and caller buffers */
 int uaisa_get_state(UaisaHandle *h, const UaisaStateView *dst, void *stream);
 int uaisa_set_state(UaisaHandle *h, const UaisaStateView *src, void *stream);

@@ -221,6 +221,32 @@ def test_rollout_equals_repeated_step_and_fused_autoreset(geom):
     a.close(); b.close()
 
 
+@pytest.mark.parametrize("geom", ["wl4", "c3_16", "swarm12"])
+def test_step_autoreset_is_step_then_autoreset(geom):
+    """uaisa_step_autoreset (one launch: what the PPO rollout issues per step) == uaisa_step + uaisa_autoreset, every output incl. reset_mask / path_cut."""
+    scn = {"wl4": scenario_c1, "c3_16": lambda: scenario_c3(seed=5, n_scenarios=3, n_drones=16, n_buildings=6), "swarm12": lambda: swarm(12, 1.2, 9)}[geom]()
+    E, T = 60, 45
+    a = VecMdin(scn, E, neighbors_num=10); b = VecMdin(scn, E, neighbors_num=10)
+    a.reset(); b.reset()
+    rng = np.random.default_rng(3)
+    n_reset = n_cut = 0
+    for t in range(T):
+        act = torch.from_numpy(np.round(rng.uniform(-1, 1, (a.A, 3)), 2).astype(np.float32)).cuda()
+        ended = (t % 20 == 19)
+        a.step_autoreset(act, max_ep_len=9, epoch_ended=ended)
+        b.step(act)
+        rew, done, info, fin = (x.clone() for x in (b.reward, b.done, b.info, b.finish))
+        b.autoreset(max_ep_len=9, epoch_ended=ended)
+        for k, ref in (("reward", rew), ("done", done), ("info", info), ("finish", fin), ("obs", b.obs), ("count", b.count), ("nbr", b.nbr),
+                       ("reset_mask", b.reset_mask), ("path_cut", b.path_cut)):
+            assert torch.equal(torch.nan_to_num(getattr(a, k).float(), 7.0), torch.nan_to_num(ref.float(), 7.0)), (geom, t, k)
+        n_reset += int(b.reset_mask.sum()); n_cut += int(b.path_cut.sum())
+    assert n_reset > 0 and n_cut > 0
+    sa, sb = a.get_state(), b.get_state()
+    assert all(torch.equal(sa[k], sb[k]) for k in sa)
+    a.close(); b.close()
+
+
 def test_env_sharding_is_bitwise_deterministic():
     """a shard of envs computes exactly what the same env ids compute in the full batch."""
     scn = scenario_c3(seed=3, n_scenarios=3, n_drones=8, n_buildings=4)

@@ -36,6 +36,15 @@ case $what in
       timeout 200 python profiles/prof_rollout.py $w 8 > gpurun_out/r2/prof_env_$w.log 2>&1 && \
       timeout 600 ncu --set full --clock-control none --import-source on -k regex:uaisa_env -s 3 -c 1 -f -o gpurun_out/r2/prof_env_$w python profiles/prof_rollout.py $w 8 > gpurun_out/r2/ncu_env_$w.log 2>&1; tail -2 gpurun_out/r2/ncu_env_$w.log
     done ;;
+  ncu_env_all)  # one full capture of a warm 8-step rollout launch per env workload (sat = few-neighbour warp-local kernel, c2 = owner / helper split, c3 / c4 dense)
+    for w in sat c2 c3 c4; do
+      timeout 200 python profiles/prof_rollout.py $w 8 > gpurun_out/r2/prof_env_$w.log 2>&1 && \
+      timeout 600 ncu --set full --clock-control none --import-source on -k regex:uaisa_env -s 3 -c 1 -f -o gpurun_out/r2/prof_env_$w python profiles/prof_rollout.py $w 8 > gpurun_out/r2/ncu_env_$w.log 2>&1; tail -1 gpurun_out/r2/ncu_env_$w.log
+    done ;;
+  launches)     # launch list of the default bench command (per-launch durations are cold-cache and serialised under ncu: shares, not absolutes)
+    timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:uaisa_ -c 400 --csv --log-file gpurun_out/r2/launches_bench_default.csv python bench.py --steps 20 --warmup 5 --no-cpu > gpurun_out/r2/ncu_bench.log 2>&1; tail -2 gpurun_out/r2/ncu_bench.log | cut -c1-200; wc -l gpurun_out/r2/launches_bench_default.csv ;;
+  ncu_mlp)
+    timeout 200 python profiles/prof_mlp.py > /dev/null 2>&1 && timeout 400 ncu --set full --clock-control none --import-source on -k regex:uaisa_mlp_gemm -s 8 -c 2 -f -o gpurun_out/r2/prof_mlp_gemm python profiles/prof_mlp.py > gpurun_out/r2/ncu_mlp.log 2>&1; tail -1 gpurun_out/r2/ncu_mlp.log ;;
   ppo)
     timeout 600 python bench.py --workload ppo --ppo-epochs 3 > gpurun_out/r2/bench_ppo.json 2> gpurun_out/r2/bench_ppo.err; tail -3 gpurun_out/r2/bench_ppo.err; python -c "
 import json;d=json.loads([l for l in open('gpurun_out/r2/bench_ppo.json') if l.startswith('{')][-1]);print(d['value']);print(d['ppo']['per_epoch'])" ;;

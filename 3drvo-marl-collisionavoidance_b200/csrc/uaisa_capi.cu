@@ -518,7 +518,7 @@ static int sparse_setup(UaisaHandle *h) {
     const size_t max_rows = A * (size_t)(P.nm ? P.nm : 1);
     h->sp_cap = (int)(max_rows * sizeof(UaisaRowRec) <= (size_t(256) << 20) ? max_rows : (size_t(256) << 20) / sizeof(UaisaRowRec));
     h->sp_r0 = (int)(A / 8 > 256 ? A / 8 : 256); if (h->sp_r0 > h->sp_cap) h->sp_r0 = h->sp_cap;
-    h->sp_off_reward = 32;      // header: ready word, two profiling timestamps
+    h->sp_off_reward = 64;      // header: ready word, seven profiling timestamps (GPU %globaltimer: first CTA start, publication, CTA 0 after its prologue / step / result writes / fence)
     h->sp_off_self = up16(h->sp_off_reward + 4 * A);
     h->sp_off_flags = up16(h->sp_off_self + 4 * A * UAISA_OBS_SELF);      // done | info | finish | count
     h->sp_off_rows = up16(h->sp_off_flags + 4 * A);
@@ -565,6 +565,7 @@ int uaisa_step_host_sparse(UaisaHandle *h, const float *action, int32_t auto_res
             L.hp_self = reinterpret_cast<float *>(h->sp_host_dev + h->sp_off_self); L.hp_count = hfl + 3 * A;
             L.hp_rows = h->sp_host_dev + h->sp_off_rows; L.hp_cap = h->sp_cap;
             L.hp_ctr = reinterpret_cast<unsigned long long *>(h->sp_dev); L.hp_hdr = reinterpret_cast<unsigned long long *>(h->sp_host_dev);
+            L.hp_sysfence = std::getenv("UAISA_HOST_FENCE_SYS") ? 1 : 0;
         } else {
             cudaMemcpyAsync(h->h_action, h->sp_hact, sizeof(float) * A * 3, cudaMemcpyHostToDevice, s);
             cudaMemsetAsync(h->sp_dev, 0, 16, s);
@@ -623,7 +624,10 @@ int uaisa_step_host_sparse(UaisaHandle *h, const float *action, int32_t auto_res
         const double t3 = now();
         acc[0] += t1 - t0; acc[1] += t2 - t1; acc[2] += t3 - t2;
         static double kacc = 0;
-        if (h->sp_zero_copy) { const unsigned long long *hd = reinterpret_cast<const unsigned long long *>(h->sp_host); kacc += (double)(hd[2] - hd[1]) * 1e-3; }
+        static double sacc[4] = {0, 0, 0, 0};
+        if (h->sp_zero_copy) { const unsigned long long *hd = reinterpret_cast<const unsigned long long *>(h->sp_host); kacc += (double)(hd[2] - hd[1]) * 1e-3;
+            for (int q = 0; q < 4; q++) sacc[q] += (double)((long long)hd[3 + q] - (long long)hd[1]) * 1e-3; }
+        if (nprof % 200 == 199 && h->sp_zero_copy) { std::fprintf(stderr, "[uaisa host step] CTA 0 after first CTA start: prologue done %.1f us, step done %.1f us, results written %.1f us, fence done %.1f us\n", sacc[0] / 200, sacc[1] / 200, sacc[2] / 200, sacc[3] / 200); sacc[0] = sacc[1] = sacc[2] = sacc[3] = 0; }
         if (++nprof % 200 == 0) { std::fprintf(stderr, "[uaisa host step] memcpy %.1f us, graph launch %.1f us, wait %.1f us of which first CTA start -> publication %.1f us (avg of 200)\n", acc[0] / 200, acc[1] / 200, acc[2] / 200, kacc / 200); acc[0] = acc[1] = acc[2] = 0; kacc = 0; }
     }
     if (n_rows > h->sp_cap) return fail(UAISA_EINVAL, "neighbour-row capacity of the host block exceeded");

@@ -202,6 +202,10 @@ __global__ void __launch_bounds__(UAISA_LB_THREADS, (MAXT <= 128 ? UAISA_MINB128
     const int lbase = le * N;
     const int A = P.E * N;
     const int a = evalid ? env * N + k : 0;
+    // The first step's action is requested before anything else: in the host round trip it comes over PCIe (mapped pinned memory, ~3 us) and that
+    // latency then overlaps the prologue's dependent loads (scenario constants, state, route cache) instead of following them.
+    float p32x = 0.f, p32y = 0.f, p32z = 0.f;
+    if (L.mode == MODE_STEP && evalid) { const float *ap = L.action + (size_t)a * 3; p32x = ap[0]; p32y = ap[1]; p32z = ap[2]; }
     const int scol = CLM ? k : tid;                               // my column in the exchange tile
     const int ag0 = CLM ? env0 * N + crank * threads : env0 * N;  // first agent of this CTA (its agents are contiguous)
     const int nag_here = CLM ? max(0, min(threads, N - crank * threads)) : min(P.envs_per_cta, P.E - env0) * N;
@@ -243,6 +247,8 @@ __global__ void __launch_bounds__(UAISA_LB_THREADS, (MAXT <= 128 ? UAISA_MINB128
     }
     unsigned n_rng = 0, n_cone = 0, n_bad = 0;
     const int T = is_step ? L.T : 1;
+#define HP_STAMP(slot) do { if (L.hp_self && blockIdx.x == 0 && threadIdx.x == 0) { unsigned long long g_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_)); L.hp_hdr[slot] = g_; } } while (0)
+    HP_STAMP(3);   // host-step profiling: CTA 0's prologue done
     // Deferred re-observation (T-step launches): the re-observe phase of step t < T-1 would publish the state, run dronestate and the
     // stage-1 gates on exactly what PASS A of step t+1 publishes and gates again (same fp32-rounded state, same waypoint).  So the phase
     // is not run: the reset policy only marks the env (`pend`), and PASS A of the next step also evaluates the cones with action 0, builds
@@ -255,8 +261,10 @@ __global__ void __launch_bounds__(UAISA_LB_THREADS, (MAXT <= 128 ? UAISA_MINB128
     for (int t = 0; t < T; t++) {
 #define OUT_SLOT(agent) ((size_t)t * A + (size_t)(agent))   // slot in the [T][A] outputs (recomputed at the use sites: no live 64-bit pointers)
         float a32x = 0.f, a32y = 0.f, a32z = 0.f;        // issue the action loads ahead of the burst of clearing stores
+        if (t == 0) { a32x = p32x; a32y = p32y; a32z = p32z; }
         if (is_step && evalid) {
-            const float *ap = L.action + OUT_SLOT(a) * 3; a32x = ap[0]; a32y = ap[1]; a32z = ap[2];
+            const float *ap = L.action + OUT_SLOT(a) * 3;
+            if (t > 0) { a32x = ap[0]; a32y = ap[1]; a32z = ap[2]; }
             if (t + 1 < T) asm volatile("prefetch.global.L2 [%0];" ::"l"(ap + (size_t)A * 3));   // next step's action
         }
         if (!WL && tix < P.envs_per_cta) { senv[tix] = 0; ssel[tix] = 0; }
@@ -775,6 +783,7 @@ __global__ void __launch_bounds__(UAISA_LB_THREADS, (MAXT <= 128 ? UAISA_MINB128
         P.wpf[a] = d.i | d.flags;
         if (do_auto) P.ep_len[a] = ep_len;
     }
+    HP_STAMP(4);       // (host-step profiling: CTA 0's step done)
     if (L.hp_self) {   // ---- host-pack tail: self part + existing rows of my agent -> mapped host memory, then the completion protocol
         // Writes over PCIe want full 128-byte lines, so every warp stages its 32 agents' data in a 2 KB slice of the (now idle)
         // exchange tile and streams it out with consecutive lanes on consecutive 16-byte words.
@@ -824,12 +833,17 @@ __global__ void __launch_bounds__(UAISA_LB_THREADS, (MAXT <= 128 ? UAISA_MINB128
             __syncwarp();
             base += n;
         }
-        // Completion (the pattern of a cooperative-groups grid barrier, at system scope): the CTA barrier orders every thread's host
-        // writes -- these and the step's reward / flags -- before thread 0's fence; the fence is cumulative, so they are performed
-        // system-wide before the CTA's arrival; the CTA that sees all others arrived fences once more and raises the ready word.
+        // Completion (the pattern of a cooperative-groups grid barrier): the CTA barrier orders every thread's host writes -- these and the step's
+        // reward / flags -- before thread 0's fence.  That fence only needs DEVICE scope: it makes the CTA's writes performed with respect to the
+        // GPU before the CTA's arrival on the counter; the one CTA that observes all the others arrived then issues the SYSTEM fence, which is
+        // cumulative over everything that happened before the arrivals it observed, and only then raises the ready word.  (A system fence per
+        // CTA, as before, cost 4.6 us each on the critical path -- it waits for the PCIe writes -- i.e. two of them in series: 17.4 -> 13 us
+        // from the first CTA's start to the publication.  UAISA_HOST_FENCE_SYS=1 restores it.)
         __syncthreads();
+        HP_STAMP(5);
         if (tix == 0) {
-            __threadfence_system();
+            if (L.hp_sysfence) __threadfence_system(); else __threadfence();
+            HP_STAMP(6);
             const unsigned long long old_ = atomicAdd(L.hp_ctr, 1ull << 32);      // high word: CTAs finished (their reservations precede their arrival)
             if ((unsigned)(old_ >> 32) == gridDim.x - 1) {
                 __threadfence_system();

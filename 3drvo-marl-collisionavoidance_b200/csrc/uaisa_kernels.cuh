@@ -69,6 +69,7 @@ struct Launch {
     int hp_cap;
     unsigned long long *hp_ctr;  // DEVICE: low word rows reserved, high word CTAs finished (left at 0 by the last CTA)
     unsigned long long *hp_hdr;  // HOST: low word = ready flag, high word = n_rows
+    int hp_sysfence;             // 1: every CTA issues a system-scope fence before its arrival (the older completion protocol, A/B switch)
 };
 
 // ---- numpy / python arithmetic primitives (see oracle/uaisa_oracle.c for the derivation) ----------

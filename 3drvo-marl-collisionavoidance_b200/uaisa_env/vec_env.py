@@ -222,26 +222,30 @@ class VecMdin:
 
     def step_host_sparse(self, action: np.ndarray, auto_reset: bool = False, max_ep_len: int = 300) -> dict:
         """Latency-optimised host round trip (uaisa_step_host_sparse): float32 [A,3] numpy action in; a dict of numpy
-        VIEWS into library-owned pinned memory out (valid until the next call): reward[A], self_obs[A,12], done/info/
-        finish/count[A], rows[n_rows] (structured: v[9], agent, slot, nbr)."""
+        VIEWS into library-owned pinned memory out (the SAME dict and views every call, valid until the next call): reward[A],
+        self_obs[A,12], done/info/finish/count[A], rows[n_rows] (structured: v[9], agent, slot, nbr)."""
         if action.dtype != np.float32 or action.size != self.A * 3 or not action.flags.c_contiguous:
             raise ValueError("action must be a C-contiguous float32 array with E*N*3 elements")
-        hs = self._hs if hasattr(self, "_hs") else _capi.UaisaHostStep()
+        hv = self.__dict__.get("_hv")
+        if hv is None:               # first call: one result struct, views into the library's pinned block and ONE result dict, reused by every call
+            self._hs = _capi.UaisaHostStep()
+            self._hs_ref = C.byref(self._hs)
+            self._hss = self.L.uaisa_step_host_sparse
+        hs = self._hs
         # no torch device context here: the library selects (and restores) the handle's device itself
-        rc = self.L.uaisa_step_host_sparse(self.h, action.ctypes.data, int(auto_reset), int(max_ep_len), C.byref(hs))
+        rc = self._hss(self.h, action.__array_interface__["data"][0], 1 if auto_reset else 0, int(max_ep_len), self._hs_ref)
         if rc:
             _capi.check(rc)
-        if not hasattr(self, "_hs"):
-            self._hs = hs
+        if hv is None:
             A = self.A
             view = lambda p, n, dt: np.frombuffer((C.c_char * (n * np.dtype(dt).itemsize)).from_address(p), dtype=dt, count=n)  # noqa: E731
             rows_cap = max(1, A * max(self.nm, 1))
-            self._hv = {"reward": view(hs.reward, A, np.float32), "self_obs": view(hs.self_obs, A * 12, np.float32).reshape(A, 12),
-                        "done": view(hs.done, A, np.uint8), "info": view(hs.info, A, np.uint8), "finish": view(hs.finish, A, np.uint8),
-                        "count": view(hs.count, A, np.uint8), "_rows_all": view(hs.rows, min(rows_cap, (256 << 20) // 48), self.ROW_DTYPE)}
-        out = dict(self._hv)
-        out["rows"] = out.pop("_rows_all")[: hs.n_rows]
-        return out
+            self._rows_all = view(hs.rows, min(rows_cap, (256 << 20) // 48), self.ROW_DTYPE)
+            hv = self._hv = {"reward": view(hs.reward, A, np.float32), "self_obs": view(hs.self_obs, A * 12, np.float32).reshape(A, 12),
+                             "done": view(hs.done, A, np.uint8), "info": view(hs.info, A, np.uint8), "finish": view(hs.finish, A, np.uint8),
+                             "count": view(hs.count, A, np.uint8), "rows": None}
+        hv["rows"] = self._rows_all[: hs.n_rows]
+        return hv
 
     @staticmethod
     def ragged_from_sparse(out: dict, nm: int):

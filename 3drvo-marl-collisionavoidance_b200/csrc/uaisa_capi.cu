@@ -195,7 +195,8 @@ int uaisa_create(const UaisaConfig *cfg, UaisaHandle **out) {
         if (per_sm < 1) return 1e300;
         const long long cap = per_sm * prop.multiProcessorCount, g = grid_for(th), waves = (g + cap - 1) / cap;
         const double wpsm = (double)(g < cap ? g : cap) * (block / 32) / prop.multiProcessorCount;
-        return (double)waves * ((nch + s - 1) / s + 1.0) * (1.0 + 0.04 * wpsm);
+        const int csz = cluster ? (N + th - 1) / th : 1;      // CTAs per env: every publish stores into, and waits for, all of them (64 x 3 measured 3 % ahead of 32 x 3 on configs[3])
+        return (double)waves * ((nch + s - 1) / s + 1.0) * (1.0 + 0.04 * wpsm) * (1.0 + 0.01 * csz);
     };
     if (auto_threads && !cluster && grid_for(threads) >= 2 * prop.multiProcessorCount) {
         // Wave quantisation: a T-step launch keeps every CTA resident for all T steps, so a grid of 1.15 waves costs 2 (configs[2]: 2048 warps on
@@ -214,9 +215,9 @@ int uaisa_create(const UaisaConfig *cfg, UaisaHandle **out) {
         // ego's neighbours and hand partial results to the owner through shared memory.  The unsliced geometry stays unless slicing is
         // predicted >= 10 % faster.
         double best = 0.9 * est_for(threads, 1); int bt = threads, bs = 1;
-        for (int th = threads; th >= 32; th -= 32) {
+        for (int th = 96; th >= 32; th -= 32) {       // (egos per CTA; 96 x 2 = 192 threads is the largest sliced CTA)
             if (th < minthreads || (cluster && (N + th - 1) / th > 8)) continue;
-            for (int s = 2; s * th <= 128 && s <= nch; s++) { const double e_ = est_for(th, s); if (e_ < best) { best = e_; bt = th; bs = s; } }
+            for (int s = 2; s * th <= 192 && s <= nch; s++) { const double e_ = est_for(th, s); if (e_ < best) { best = e_; bt = th; bs = s; } }
         }
         threads = bt; slices = bs;
     }
@@ -229,7 +230,7 @@ int uaisa_create(const UaisaConfig *cfg, UaisaHandle **out) {
     if (cfg->neighbor_slices > 0) {
         slices = cfg->neighbor_slices;
         if (can_split && slices == 2) { if (threads > 64) { if (!auto_threads) { delete h; return fail(UAISA_EINVAL, "the owner / helper split needs threads_per_block <= 64"); } threads = 64; } }
-        else if (slices > 1 && (wl || maxr <= 4 || slices * threads > 128 || slices > nch)) { delete h; return fail(UAISA_EINVAL, "neighbor_slices > 1 needs n_drones > 32, nm > 4 and slices * threads_per_block <= 128 (or = 2 for the owner / helper split of warp-local envs with nm <= 4 rows)"); }
+        else if (slices > 1 && (wl || maxr <= 4 || slices * threads > 192 || slices > nch)) { delete h; return fail(UAISA_EINVAL, "neighbor_slices > 1 needs n_drones > 32, nm > 4 and slices * threads_per_block <= 192 (or = 2 for the owner / helper split of warp-local envs with nm <= 4 rows)"); }
     }
     if (cluster) {
         if (threads > 128 || threads % 32 || (N + threads - 1) / threads > 8) { delete h; return fail(UAISA_EINVAL, "n_drones > 128 needs threads_per_block in {32,64,96,128} with at most 8 CTAs per env"); }
@@ -244,6 +245,7 @@ int uaisa_create(const UaisaConfig *cfg, UaisaHandle **out) {
     if (std::getenv("UAISA_VERBOSE")) std::fprintf(stderr, "[uaisa] E=%d N=%d: %s, %d egos x %d slices per CTA, %d CTAs%s, %zu B smem\n", E, N, wl ? "warp-local" : "CTA", threads, slices, h->grid, cluster ? " (clustered)" : "", h->smem);
     if (wl && slices == 2) h->kernel = uaisa_env_kernel<4, 128, true, true>;
     else if (wl) h->kernel = need <= 4 ? uaisa_env_kernel<4, 128, true, false> : need <= 10 ? uaisa_env_kernel_d<10, 128, true, false> : uaisa_env_kernel_d<16, 128, true, false>;
+    else if (slices * threads > 128) h->kernel = need <= 10 ? uaisa_env_kernel<10, 192, false, true> : uaisa_env_kernel<16, 192, false, true>;
     else if (slices > 1 || (maxr > 4 && std::getenv("UAISA_FORCE_SL"))) h->kernel = need <= 10 ? uaisa_env_kernel<10, 128, false, true> : uaisa_env_kernel<16, 128, false, true>;
     else h->kernel = need <= 4 ? uaisa_env_kernel<4, 128, false, false> : need <= 10 ? uaisa_env_kernel_d<10, 128, false, false> : uaisa_env_kernel_d<16, 128, false, false>;
     if (h->smem > (size_t)prop.sharedMemPerBlockOptin) { delete h; return fail(UAISA_EINVAL, "shared memory per CTA exceeds the device limit; lower threads_per_block"); }

@@ -113,7 +113,7 @@ __global__ void uaisa_env_kernel_d(
 #elif defined(UAISA_NO_LB)
 __global__ void uaisa_env_kernel(
 #else
-__global__ void __launch_bounds__(UAISA_LB_THREADS, (MAXT <= 128 ? UAISA_MINB128 : 1)) uaisa_env_kernel(
+__global__ void __launch_bounds__(UAISA_LB_THREADS, (MAXT <= 128 ? UAISA_MINB128 : (MAXT <= 192 ? 2 : 1))) uaisa_env_kernel(
 #endif
     const __grid_constant__ Params P, const __grid_constant__ Launch L) {
 #define ENV_SYNC() do { if (WL) __syncwarp(); else __syncthreads(); } while (0)
@@ -869,7 +869,7 @@ __global__ void __launch_bounds__(UAISA_LB_THREADS, (MAXT <= 128 ? UAISA_MINB128
     }
 }
 
-#if !defined(UAISA_TU_DENSE) && !defined(UAISA_TU_SPLIT)   // (the small kernels live in the default translation unit only)
+#if !defined(UAISA_TU_DENSE) && !defined(UAISA_TU_SPLIT) && !defined(UAISA_TU_WIDE)   // (the small kernels live in the default translation unit only)
 // cal_des_list (ir_gym.py:44-46)
 __global__ void uaisa_cal_des_kernel(const __grid_constant__ Params P, float *des) {
     const int a = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1054,6 +1054,8 @@ __global__ void uaisa_pack_kernel(int A, int obs_dim, int nm, const float *obs, 
 #define UAISA_INST(R, T, W, S) template __global__ void uaisa_env_kernel<R, T, W, S>(const __grid_constant__ Params, const __grid_constant__ Launch);
 #if defined(UAISA_TU_SPLIT)
 UAISA_INST(4, 128, true, true)          // SPLIT: owner + helper warps (small batches of few-neighbour envs)
+#elif defined(UAISA_TU_WIDE)
+UAISA_INST(10, 192, false, true) UAISA_INST(16, 192, false, true)      // neighbour slices in CTAs of up to 192 threads
 #elif defined(UAISA_TU_DENSE)
 #define UAISA_INST_D(R, T, W, S) template __global__ void uaisa_env_kernel_d<R, T, W, S>(const __grid_constant__ Params, const __grid_constant__ Launch);
 UAISA_INST_D(10, 128, true, false) UAISA_INST_D(16, 128, true, false)

@@ -102,15 +102,21 @@ class VecMdin:
                                          g("info"), g("finish"), int(auto_reset), int(max_ep_len), self._stream()))
         return out
 
-    def step_autoreset(self, action: torch.Tensor, max_ep_len: int = 300, epoch_ended: bool = False):
+    def step_autoreset(self, action: torch.Tensor, max_ep_len: int = 300, epoch_ended: bool = False, out: Optional[dict] = None):
         """step() followed by autoreset() in one launch (same outputs, bit for bit): the env part of one trainer iteration (multi_ppo.py:210-281).
+        `out` may redirect any of obs / count / reward / path_cut to caller tensors of the same shapes (e.g. slices of a rollout buffer: no copy).
         -> (obs of the next step, reward, done, info, finish, reset_mask, path_cut)."""
         if action.dtype != torch.float32 or not action.is_cuda or not action.is_contiguous() or action.numel() != self.A * 3:
             raise ValueError("action must be a contiguous float32 CUDA tensor [E*N, 3]")
-        _capi.check(self.L.uaisa_step_autoreset(self.h, _ptr(action), _ptr(self.obs), _ptr(self.count), _ptr(self.nbr), _ptr(self.reward), _ptr(self.done),
+        o = {"obs": self.obs, "count": self.count, "reward": self.reward, "path_cut": self.path_cut}
+        for k, t in (out or {}).items():
+            if k not in o or t.dtype != o[k].dtype or t.numel() != o[k].numel() or not t.is_cuda or not t.is_contiguous():
+                raise ValueError("out[%r] must be a contiguous CUDA tensor with the dtype and size of the env's own %s buffer" % (k, k))
+            o[k] = t
+        _capi.check(self.L.uaisa_step_autoreset(self.h, _ptr(action), _ptr(o["obs"]), _ptr(o["count"]), _ptr(self.nbr), _ptr(o["reward"]), _ptr(self.done),
                                                 _ptr(self.info), _ptr(self.finish), int(max_ep_len), int(bool(epoch_ended)), _ptr(self.reset_mask),
-                                                _ptr(self.path_cut), self._stream()))
-        return self.obs, self.reward, self.done, self.info, self.finish, self.reset_mask, self.path_cut
+                                                _ptr(o["path_cut"]), self._stream()))
+        return o["obs"], o["reward"], self.done, self.info, self.finish, self.reset_mask, o["path_cut"]
 
     def reset(self, agent_mask: Optional[torch.Tensor] = None, observe: bool = True):
         """mdin.drone_reset (agent_mask None) / drone_reset_one + env_observation (mdin.py:38-46)."""

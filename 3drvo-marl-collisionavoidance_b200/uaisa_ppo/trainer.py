@@ -57,6 +57,7 @@ class PPOConfig:                      # train_process.py:53-63 defaults
     use_fused_policy: bool = True     # rollout forward through the fused tcgen05 kernels (TF32 operands, fp32 accumulation)
     fused_kernel: str = "full"        # "full": csrc/uaisa_policy_fwd.cu (one kernel, in-kernel recurrence); "split": round-1 K6a + K6b pair
     multi_cap_frac: float = 1.0 / 64  # static capacity of the multi-row GRU path in the captured step (fraction of A)
+    unroll_rollout: bool = True       # capture ALL steps of an epoch as one graph whose kernels write straight into the epoch buffers (no per-step copies of obs / count / reward / cut)
     tc_mlp: bool = True               # update: actor / critic MLP forward + backward on tcgen05 (csrc/uaisa_mlp.cu, TF32 operands) instead of torch autograd / cuBLAS fp32
 
 
@@ -165,6 +166,7 @@ class PPOTrainer:
         self.env.reset()
         self.stats = {}
         self._graph = None
+        self._graph_unrolled = None   # the whole epoch as one graph (unroll_rollout)
         self._graph_fast = None       # same step without the multi-row GRU path (taken when no agent has >= 2 neighbour rows)
         self._flag_dev = torch.zeros(1, dtype=torch.int32, device=self.dev)
         self._flag_host = torch.zeros(1, dtype=torch.int32).pin_memory()
@@ -199,6 +201,47 @@ class PPOTrainer:
             self._flag_host.copy_(self._flag_dev, non_blocking=True)
 
     @torch.no_grad()
+    def _one_step_direct(self, t: int, last: bool):
+        """Step t of an epoch with a STATIC buffer index (unrolled capture): the policy reads the observation where the previous step's env kernel
+        wrote it (buf[obs][t]), the env kernel writes reward / path cut into buf[..][t] and the next observation into buf[obs][t+1] -- no copies
+        of the big tensors.  The last step (full reset, multi_ppo.py:244-264) leaves the next epoch's first observation in the env's own buffers."""
+        env, cfg, b = self.env, self.cfg, self.buf
+        a_inc, v, logp = self.fused.step(b["obs"][t], b["count"][t], cfg.std_factor)                                # :196
+        env.action_transform(a_inc, self.action, b["act"][t])                                                      # :197-208
+        out = {"reward": b["rew"][t], "path_cut": b["cut"][t]}
+        if not last:
+            out["obs"] = b["obs"][t + 1]; out["count"] = b["count"][t + 1]
+        env.step_autoreset(self.action, max_ep_len=cfg.max_ep_len, epoch_ended=last, out=out)                      # :210 + :226-281
+        b["val"][t].copy_(v); b["logp"][t].copy_(logp)
+        self._ndone += env.done.sum()
+
+    @torch.no_grad()
+    def _rollout_unrolled(self):
+        """The whole epoch as ONE CUDA graph of T unrolled steps (captured once; replay = one launch per epoch)."""
+        T = self.cfg.steps_per_epoch
+        self._ndone.zero_()
+        if self._graph_unrolled is None:
+            s = torch.cuda.Stream(device=self.dev)
+            s.wait_stream(torch.cuda.current_stream(self.dev))
+            with torch.cuda.stream(s):            # warm-up on a side stream, then start again from a reset
+                self.buf["obs"][0].copy_(self.env.obs); self.buf["count"][0].copy_(self.env.count)
+                self._one_step_direct(0, False); self._one_step_direct(T - 1, True)
+            torch.cuda.current_stream(self.dev).wait_stream(s)
+            self.env.reset()
+            self._ndone.zero_()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self.buf["obs"][0].copy_(self.env.obs); self.buf["count"][0].copy_(self.env.count)
+                for t in range(T):
+                    self._one_step_direct(t, t == T - 1)
+            self._graph_unrolled = g
+            self._ndone.zero_()
+            self.env.reset()
+        self._graph_unrolled.replay()
+        self.stats["collisions"] = self._ndone
+        return self.buf
+
+    @torch.no_grad()
     def rollout(self):
         """steps_per_epoch env steps of every env (multi_ppo.py:183-281).  The T-1 ordinary steps replay ONE CUDA graph with no host
         synchronisation in between (the fused forward handles every neighbour-row count inside the kernel); the last step of the epoch
@@ -207,6 +250,8 @@ class PPOTrainer:
         flag read per step picks one."""
         cfg = self.cfg
         T = cfg.steps_per_epoch
+        if cfg.use_cuda_graph and cfg.unroll_rollout and self._single_graph and 1 < T <= 2048:
+            return self._rollout_unrolled()
         self._t.zero_(); self._ndone.zero_()
         rd = self.ac.pi.rnn_reader
         if getattr(rd, "overflow", None) is None:
@@ -447,7 +492,7 @@ class PPOTrainer:
     def close(self):
         """Drop the captured CUDA graphs.  With world_size > 1 the update graphs hold NCCL kernels: release them BEFORE
         torch.distributed.destroy_process_group(), which otherwise waits on the communicator they still reference."""
-        self._upd = None; self._graph = None; self._graph_fast = None
+        self._upd = None; self._graph = None; self._graph_fast = None; self._graph_unrolled = None
         torch.cuda.synchronize(self.dev)
 
     def save_model(self, path):

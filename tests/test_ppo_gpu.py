@@ -274,3 +274,29 @@ def test_fused_reader_forward_backward_matches_torch_autograd():
     f0 = ac.features(o, c, multi_cap=-1)
     rd.fused_step0 = True
     assert torch.allclose(f1, f0, rtol=1e-5, atol=2e-5)
+
+
+def test_unrolled_rollout_fills_the_buffers_like_the_per_step_rollout():
+    """PPOConfig.unroll_rollout (the whole epoch as one graph, env / policy kernels writing straight into the epoch buffers) against the per-step graph
+    with its buffer copies: same seeds -> identical observations, counts, actions, rewards, values, log-probs and path cuts."""
+    from uaisa_env.scenario import scenario_c1
+    from uaisa_env.vec_env import VecMdin
+    from uaisa_ppo.trainer import PPOConfig, PPOTrainer
+    bufs = []
+    for unroll in (True, False):
+        env = VecMdin(scenario_c1(), 48, neighbors_num=10)
+        tr = PPOTrainer(env, cfg=PPOConfig(steps_per_epoch=21, max_ep_len=9, unroll_rollout=unroll), seed=11)
+        assert (tr._single_graph and unroll) == unroll
+        torch.manual_seed(5)
+        tr.rollout()
+        first = {k: v.clone() for k, v in tr.buf.items()}
+        tr.rollout()                                    # a second epoch continues from the first one's final observation
+        bufs.append((first, {k: v.clone() for k, v in tr.buf.items()}, int(tr.stats["collisions"])))
+        assert (tr._graph_unrolled is not None) == unroll
+        tr.close(); env.close()
+    for ep in (0, 1):
+        for k in bufs[0][ep]:
+            a, b = bufs[0][ep][k], bufs[1][ep][k]
+            assert torch.equal(torch.nan_to_num(a.float(), 7.0), torch.nan_to_num(b.float(), 7.0)), (ep, k)
+    assert bufs[0][2] == bufs[1][2] and bufs[0][2] > 0
+    assert int(bufs[0][0]["cut"].sum()) > 0

@@ -305,6 +305,97 @@ __global__ void __launch_bounds__(512) uaisa_reader_bwd_kernel(const float *__re
     if (tid < RD_FEAT) { atomicAdd(G.ln_w + tid, alw); atomicAdd(G.ln_b + tid, alb); }
 }
 
+// ---- PPO losses and their gradients with respect to the heads' outputs (multi_ppo.py:379-404), one thread per minibatch sample --------------------
+// scal[0] <- max(1, number of usable samples): samples whose advantage / return is not finite are masked out (ok[i] == 0)
+__global__ void __launch_bounds__(1024) uaisa_ppo_wsum_kernel(const uint8_t *__restrict__ ok, const long long *__restrict__ idx, int B, float *__restrict__ scal) {
+    __shared__ int red[32];
+    int c = 0;
+    for (int s = threadIdx.x; s < B; s += 1024) c += ok[idx ? idx[s] : s] ? 1 : 0;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) c += __shfl_xor_sync(0xffffffffu, c, off);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) { int t = 0; for (int w = 0; w < 32; w++) t += red[w]; scal[0] = (float)(t > 1 ? t : 1); }
+}
+
+__device__ __forceinline__ float nan_to_zero(float x) { return (x == x && fabsf(x) <= 3.402823466e38f) ? x : 0.0f; }   // torch.nan_to_num(x, 0, 0, 0)
+
+// compute_loss_pi (multi_ppo.py:385-404): y [B][3] = the actor's pre-tanh output.  dy [B][3] = d(loss / W) / dy; dlogstd[3], slots[0] (approx-KL / W) and
+// slots[1] (loss / W) are ADDED to (the caller zeroes them with the gradient bucket).  inv = 1 / (wsum * W).
+__global__ void __launch_bounds__(256) uaisa_ppo_pi_loss_kernel(const float *__restrict__ y, const float *__restrict__ log_std, float std_factor,
+                                                               const float *__restrict__ act, const float *__restrict__ logp_old, const float *__restrict__ adv,
+                                                               const uint8_t *__restrict__ ok, const long long *__restrict__ idx, int B, float clip, float inv_world,
+                                                               const float *__restrict__ scal, float *__restrict__ dy, float *__restrict__ dlogstd, float *__restrict__ slots) {
+    __shared__ float red[8][5];
+    const int s = blockIdx.x * 256 + threadIdx.x;
+    float part[5] = {0.f, 0.f, 0.f, 0.f, 0.f};       // loss, kl, dlogstd[0..2]
+    if (s < B) {
+        const long long i = idx ? idx[s] : s;
+        const float inv = inv_world / scal[0], w = ok[i] ? 1.0f : 0.0f;
+        float mu[3], st[3], e[3], a[3], logp = 0.f;
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+            mu[j] = tanhf(y[(size_t)s * 3 + j]);
+            e[j] = std_factor * expf(__ldg(log_std + j)) + 1e-6f;
+            st[j] = fminf(fmaxf(e[j], 1e-4f), 10.0f);
+            a[j] = act[i * 3 + j];
+            const float d = a[j] - mu[j];
+            logp += -(d * d) / (2.0f * st[j] * st[j]) - logf(st[j]) - 0.9189385332046727f;
+        }
+        const float lo = logp_old[i], ratio = expf(logp - lo), av = nan_to_zero(adv[i]);
+        const float ra = ratio * av, cl = fminf(fmaxf(ratio, 1.0f - clip), 1.0f + clip) * av;
+        part[0] = -fminf(ra, cl) * w;
+        part[1] = (lo - logp) * w;
+        const float dterm = -w * inv;
+        const bool inside = ratio >= 1.0f - clip && ratio <= 1.0f + clip;
+        const float g_ra = av * dterm, g_cl = inside ? av * dterm : 0.0f;           // d term / d ratio through either argument of min()
+        const float dratio = ra < cl ? g_ra : (ra > cl ? g_cl : 0.5f * (g_ra + g_cl));   // torch.min splits the gradient at ties
+        const float dlogp = ratio * dratio;
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+            const float d = a[j] - mu[j], is2 = 1.0f / (st[j] * st[j]);
+            dy[(size_t)s * 3 + j] = dlogp * d * is2 * (1.0f - mu[j] * mu[j]);
+            const float dstd = dlogp * (d * d * is2 / st[j] - 1.0f / st[j]);
+            part[2 + j] = (e[j] >= 1e-4f && e[j] <= 10.0f) ? dstd * (e[j] - 1e-6f) : 0.0f;    // d std / d log_std = std_factor * exp(log_std) inside the clamp
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < 5; q++) {
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) part[q] += __shfl_xor_sync(0xffffffffu, part[q], off);
+    }
+    if ((threadIdx.x & 31) == 0) for (int q = 0; q < 5; q++) red[threadIdx.x >> 5][q] = part[q];
+    __syncthreads();
+    if (threadIdx.x < 5) {
+        float t = 0.f;
+        for (int w = 0; w < 8; w++) t += red[w][threadIdx.x];
+        const float inv = inv_world / scal[0];
+        if (threadIdx.x == 0) atomicAdd(slots + 1, t * inv);            // loss / W
+        else if (threadIdx.x == 1) atomicAdd(slots + 0, t * inv);       // approx-KL / W
+        else atomicAdd(dlogstd + (threadIdx.x - 2), t);
+    }
+}
+
+// compute_loss_v (multi_ppo.py:379-383): y [B] = the critic's output.  dy [B] = d(loss / W) / dy; loss_out[0] += sum((v - ret)^2 w) / wsum
+__global__ void __launch_bounds__(256) uaisa_ppo_v_loss_kernel(const float *__restrict__ y, const float *__restrict__ ret, const uint8_t *__restrict__ ok,
+                                                              const long long *__restrict__ idx, int B, float inv_world, const float *__restrict__ scal,
+                                                              float *__restrict__ dy, float *__restrict__ loss_out) {
+    __shared__ float red[8];
+    const int s = blockIdx.x * 256 + threadIdx.x;
+    float part = 0.f;
+    if (s < B) {
+        const long long i = idx ? idx[s] : s;
+        const float w = ok[i] ? 1.0f : 0.0f, d = y[s] - nan_to_zero(ret[i]);
+        part = d * d * w;
+        dy[s] = 2.0f * d * w * (inv_world / scal[0]);
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) part += __shfl_xor_sync(0xffffffffu, part, off);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = part;
+    __syncthreads();
+    if (threadIdx.x == 0) { float t = 0.f; for (int w = 0; w < 8; w++) t += red[w]; atomicAdd(loss_out, t / scal[0]); }
+}
+
 }  // namespace uaisa
 
 extern "C" {
@@ -334,6 +425,28 @@ int uaisa_reader_bwd(const float *obs, const int64_t *idx, int32_t B, int32_t ob
     const int tiles = (B + uaisa::RB_T - 1) / uaisa::RB_T;
     const int grid = tiles < 444 ? tiles : 444;      // 3 CTAs of 512 threads per SM
     uaisa::uaisa_reader_bwd_kernel<<<grid, 512, 0, static_cast<cudaStream_t>(stream)>>>(obs, reinterpret_cast<const long long *>(idx), B, obs_dim, W, dfeat, stats, hsum, G);
+    return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+
+// PPO losses of one update iteration and their gradients with respect to the heads' outputs (multi_ppo.py:379-404), minibatch gathered through idx
+// (may be NULL).  scal: float[1] workspace (the usable-sample count, written by uaisa_ppo_wsum).  See the kernels above for the outputs.
+int uaisa_ppo_wsum(const uint8_t *ok, const int64_t *idx, int32_t B, float *scal, void *stream) {
+    if (!ok || !scal || B < 1) return -1;
+    uaisa::uaisa_ppo_wsum_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(ok, reinterpret_cast<const long long *>(idx), B, scal);
+    return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+int uaisa_ppo_pi_loss(const float *y, const float *log_std, float std_factor, const float *act, const float *logp_old, const float *adv, const uint8_t *ok,
+                      const int64_t *idx, int32_t B, float clip_ratio, float inv_world, const float *scal, float *dy, float *dlogstd, float *slots, void *stream) {
+    if (!y || !log_std || !act || !logp_old || !adv || !ok || !scal || !dy || !dlogstd || !slots || B < 1) return -1;
+    uaisa::uaisa_ppo_pi_loss_kernel<<<(B + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(y, log_std, std_factor, act, logp_old, adv, ok,
+        reinterpret_cast<const long long *>(idx), B, clip_ratio, inv_world, scal, dy, dlogstd, slots);
+    return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+int uaisa_ppo_v_loss(const float *y, const float *ret, const uint8_t *ok, const int64_t *idx, int32_t B, float inv_world, const float *scal, float *dy,
+                     float *loss_out, void *stream) {
+    if (!y || !ret || !ok || !scal || !dy || !loss_out || B < 1) return -1;
+    uaisa::uaisa_ppo_v_loss_kernel<<<(B + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(y, ret, ok, reinterpret_cast<const long long *>(idx), B, inv_world,
+                                                                                                  scal, dy, loss_out);
     return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 

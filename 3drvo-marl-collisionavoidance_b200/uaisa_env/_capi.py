@@ -15,6 +15,7 @@ SYMBOLS = (
     "uaisa_launch_count", "uaisa_step_host", "uaisa_get_region_clocks", "uaisa_action_transform", "uaisa_gae", "uaisa_step_host_sparse", "uaisa_policy_features", "uaisa_policy_heads",
     "uaisa_opt_partials_len", "uaisa_opt_prepare", "uaisa_clip_adam", "uaisa_rvo_select", "uaisa_reader_fwd", "uaisa_reader_bwd", "uaisa_policy_pack_floats", "uaisa_policy_pack", "uaisa_policy_forward",
     "uaisa_mlp_gemm", "uaisa_mlp_out_bwd", "uaisa_colsum", "uaisa_step_autoreset",
+    "uaisa_ppo_wsum", "uaisa_ppo_pi_loss", "uaisa_ppo_v_loss",
 )
 
 
@@ -87,6 +88,10 @@ def lib():
         L.uaisa_policy_forward.argtypes = [vp, vp, i32, i32, vp, vp, vp, vp, vp, vp, vp]
         L.uaisa_mlp_gemm.argtypes = [vp, i32, i32, vp, i32, i32, vp, i32, i32, i32, i32, i32, i32, vp, vp, i32, vp, vp, vp, i32, vp]
         L.uaisa_step_autoreset.argtypes = [vp] * 9 + [i32, i32, vp, vp, vp]
+        f32 = C.c_float
+        L.uaisa_ppo_wsum.argtypes = [vp, vp, i32, vp, vp]
+        L.uaisa_ppo_pi_loss.argtypes = [vp, vp, f32, vp, vp, vp, vp, vp, i32, f32, f32, vp, vp, vp, vp, vp]
+        L.uaisa_ppo_v_loss.argtypes = [vp, vp, vp, vp, i32, f32, vp, vp, vp, vp]
         L.uaisa_mlp_out_bwd.argtypes = [vp, vp, vp, i32, i32, vp, vp, vp, vp, vp]
         L.uaisa_colsum.argtypes = [vp, i32, i32, vp, vp]
         L.uaisa_opt_partials_len.restype = C.c_int

@@ -58,6 +58,8 @@ class PPOConfig:                      # train_process.py:53-63 defaults
     fused_kernel: str = "full"        # "full": csrc/uaisa_policy_fwd.cu (one kernel, in-kernel recurrence); "split": round-1 K6a + K6b pair
     multi_cap_frac: float = 1.0 / 64  # static capacity of the multi-row GRU path in the captured step (fraction of A)
     unroll_rollout: bool = True       # capture ALL steps of an epoch as one graph whose kernels write straight into the epoch buffers (no per-step copies of obs / count / reward / cut)
+    native_update: bool = True        # update iterations without torch autograd: reader / MLP / loss forward and backward as a fixed sequence of our own kernels writing
+                                      # straight into the flat gradient bucket (needs tc_mlp and minibatches without multi-row samples; otherwise the autograd path)
     tc_mlp: bool = True               # update: actor / critic MLP forward + backward on tcgen05 (csrc/uaisa_mlp.cu, TF32 operands) instead of torch autograd / cuBLAS fp32
 
 
@@ -307,11 +309,66 @@ class PPOTrainer:
         u["off"] += u["mb"]
         return idx
 
+    # ---- native iterations: no autograd tape, ~20 launches of our own kernels instead of ~75 (most of them element-wise torch kernels) ----------
+    def _native(self):
+        u, rd = self._u, self.ac.pi.rnn_reader
+        return bool(self.cfg.native_update and self.cfg.tc_mlp and u["cap"] < 0 and rd.fused_step0 and self._obs.is_cuda)
+
+    def _head_fb(self, head: str):
+        """One head's forward, loss and backward on minibatch idx as a fixed kernel sequence (csrc/uaisa_train.cu, uaisa_mlp.cu): reader forward ->
+        H1 -> H2, y -> loss + d loss / dy -> output layer backward -> dW2, dZ1, db1, dW1, dfeat -> reader backward.  Every gradient lands in the
+        parameter's view of the flat bucket (zeroed by the caller); same arithmetic as the autograd path (tests/test_ppo_gpu.py)."""
+        from .policy import _MlpTc
+        cfg, F, u, W, L, dev = self.cfg, self.flat, self._u, self.world, self.flat.L, self.dev
+        B, nout = u["mb"], (3 if head == "pi" else 1)
+        ws = u.get("ws")
+        if ws is None:
+            e = lambda *sh: torch.empty(sh, dtype=torch.float32, device=dev)  # noqa: E731
+            ws = u["ws"] = {"feat": e(B, 268), "stats": e(B, 2), "hsum": e(B, 256), "H1": e(B, 256), "H2": e(B, 256), "y": e(B, 3), "dy": e(B, 3),
+                            "dZ2": e(B, 256), "dZ1": e(B, 256), "dfeat": e(B, 268), "scal": e(4)}
+        p = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
+        s = F._s()
+        rd = self.ac.pi.rnn_reader
+        net = self.ac.pi.net_out if head == "pi" else self.ac.v.v_net
+        (W1, b1), (W2, b2), (W3, b3) = ((net[i].weight, net[i].bias) for i in (0, 2, 4))
+        idx = self._next_idx()
+        rparams = rd._step0_params()
+        pptr = (C.c_void_p * 8)(*[q.data_ptr() for q in rparams]); gptr = (C.c_void_p * 8)(*[q.grad.data_ptr() for q in rparams])
+
+        def chk(rc, what):
+            if rc:
+                raise _capi.UaisaError("%s failed (%d)" % (what, rc))
+
+        chk(L.uaisa_ppo_wsum(p(self._ok), p(idx), B, p(ws["scal"]), s), "uaisa_ppo_wsum")
+        chk(L.uaisa_reader_fwd(p(self._obs), p(idx), B, int(self._obs.shape[1]), pptr, p(ws["feat"]), p(ws["stats"]), p(ws["hsum"]), s), "uaisa_reader_fwd")
+        g = lambda *a, **k: _MlpTc._gemm(L, C, s, *a, **k)  # noqa: E731
+        g(ws["feat"], 268, 0, W1, 268, 0, ws["H1"], 256, B, 256, 268, 1, 1, bias=b1)
+        g(ws["H1"], 256, 0, W2, 256, 0, ws["H2"], 256, B, 256, 256, 1, 2, bias=b2, W3=W3, b3=b3, Y=ws["y"], nout=nout)
+        if head == "pi":
+            chk(L.uaisa_ppo_pi_loss(p(ws["y"]), p(self.ac.pi.log_std), float(cfg.std_factor), p(self._act), p(self._logp_old), p(self._adv), p(self._ok), p(idx), B,
+                                    float(cfg.clip_ratio), 1.0 / W, p(ws["scal"]), p(ws["dy"]), p(self.ac.pi.log_std.grad), p(F.g[F.n:]), s), "uaisa_ppo_pi_loss")
+        else:
+            u["loss_v"].zero_()
+            chk(L.uaisa_ppo_v_loss(p(ws["y"]), p(self._ret), p(self._ok), p(idx), B, 1.0 / W, p(ws["scal"]), p(ws["dy"]), p(u["loss_v"]), s), "uaisa_ppo_v_loss")
+        chk(L.uaisa_mlp_out_bwd(p(ws["dy"]), p(ws["H2"]), p(W3), B, nout, p(ws["dZ2"]), p(W3.grad), p(b3.grad), p(b2.grad), s), "uaisa_mlp_out_bwd")
+        sp = max(1, min(_MlpTc.SPLITS, (B + 31) // 32))
+        g(ws["dZ2"], 256, 1, ws["H1"], 256, 1, W2.grad, 256, 256, 256, B, sp, 4)
+        g(ws["dZ2"], 256, 0, W2, 256, 1, ws["dZ1"], 256, B, 256, 256, 1, 3, mask=ws["H1"], ldm=256)
+        chk(L.uaisa_colsum(p(ws["dZ1"]), B, 256, p(b1.grad), s), "uaisa_colsum")
+        g(ws["dZ1"], 256, 1, ws["feat"], 268, 1, W1.grad, 268, 256, 268, B, sp, 4)
+        g(ws["dZ1"], 256, 0, W1, 268, 1, ws["dfeat"], 268, B, 268, 256, 1, 0)
+        chk(L.uaisa_reader_bwd(p(self._obs), p(idx), B, int(self._obs.shape[1]), pptr, p(ws["dfeat"]), p(ws["stats"]), p(ws["hsum"]), gptr, s), "uaisa_reader_bwd")
+
     def _pi_fb(self):
         """Forward + PPO-clip loss + approx-KL + backward of one policy iteration (multi_ppo.py:385-404) into the flat gradient bucket, then
         ONE all-reduce of [reader | pi-only | kl, loss] across ranks.  No host round trip."""
         cfg, F, u, W = self.cfg, self.flat, self._u, self.world
         F.g[F.pi_lo:].zero_()                                      # pi_optimizer.zero_grad() (+ the kl / loss slots)
+        if self._native():
+            self._head_fb("pi")
+            if W > 1:
+                dist.all_reduce(F.g[F.pi_lo:])
+            return
         idx = self._next_idx()
         w = self._ok[idx].float()
         wsum = w.sum().clamp(min=1)
@@ -339,6 +396,11 @@ class PPOTrainer:
         """Forward + MSE loss + backward of one value iteration (multi_ppo.py:379-383), all-reduce of [v_net | reader]."""
         F, u, W = self.flat, self._u, self.world
         F.g[:F.v_hi].zero_()                                       # vf_optimizer.zero_grad()
+        if self._native():
+            self._head_fb("v")
+            if W > 1:
+                dist.all_reduce(F.g[:F.v_hi])
+            return
         idx = self._next_idx()
         w = self._ok[idx].float()
         _, v, _ = self.ac.evaluate(self._obs, self._cnt, None, multi_cap=u["cap"], heads="v", index=idx)
@@ -467,6 +529,7 @@ class PPOTrainer:
         ctl = self._ctl.tolist()          # the update's only host read: iterations applied / early-stop latch
         self.update_path = (("CUDA graph per iteration" if graphed else "eager iterations") + "; " + ("reader forward/backward kernels (uaisa_reader_fwd/bwd) + " if u["cap"] < 0 and self.ac.pi.rnn_reader.fused_step0 else "")
                             + ("MLP forward / dgrad / wgrad on tcgen05 (uaisa_mlp_gemm, TF32 operands)" if cfg.tc_mlp else "torch autograd GEMMs for the MLPs (cuBLAS fp32)")
+                            + (" + loss kernels, no autograd tape" if self._native() else " + torch loss algebra / autograd")
                             + " + flat-bucket all-reduce + fused clip/Adam kernel")
         self.stats.update(update_prepare_ms=ev[0].elapsed_time(ev[1]), update_pi_ms=ev[1].elapsed_time(ev[2]), update_v_ms=ev[2].elapsed_time(ev[3]))
         self.stats.update(pi_iters=int(ctl[1]), early_stop=bool(ctl[0]), loss_v=float(u["loss_v"]), kl=float(self.flat.g[self.flat.n]), loss_pi=float(self.flat.g[self.flat.n + 1]),

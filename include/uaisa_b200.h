@@ -236,6 +236,17 @@ int uaisa_mlp_gemm(const float *A, int32_t lda, int32_t a_mn, const float *B, in
 int uaisa_mlp_out_bwd(const float *dy, const float *H2, const float *W3, int32_t B, int32_t nout, float *dZ2, float *dW3, float *db3, float *db2, void *stream);
 int uaisa_colsum(const float *X, int32_t rows, int32_t cols, float *out, void *stream);
 
+/* PPO losses of one update iteration and their gradients with respect to the heads' outputs (multi_ppo.compute_loss_pi / compute_loss_v, multi_ppo.py:379-404),
+ * one thread per minibatch sample; idx (may be NULL): int64[B], the buffer row of each sample; ok: uint8 per buffer row (0 = advantage / return not finite:
+ * masked out).  uaisa_ppo_wsum writes scal[0] = max(1, usable samples).  uaisa_ppo_pi_loss: y [B][3] = the actor's pre-tanh output -> dy [B][3] =
+ * d(loss / W) / dy with inv_world = 1 / W; ADDS d/dlog_std to dlogstd[3], approx-KL / W to slots[0] and loss / W to slots[1].  uaisa_ppo_v_loss: y [B] =
+ * the critic's output -> dy [B]; ADDS the loss to loss_out[0].  Asynchronous on `stream`, capturable in a CUDA graph. */
+int uaisa_ppo_wsum(const uint8_t *ok, const int64_t *idx, int32_t B, float *scal, void *stream);
+int uaisa_ppo_pi_loss(const float *y, const float *log_std, float std_factor, const float *act, const float *logp_old, const float *adv, const uint8_t *ok,
+                      const int64_t *idx, int32_t B, float clip_ratio, float inv_world, const float *scal, float *dy, float *dlogstd, float *slots, void *stream);
+int uaisa_ppo_v_loss(const float *y, const float *ret, const uint8_t *ok, const int64_t *idx, int32_t B, float inv_world, const float *scal, float *dy,
+                     float *loss_out, void *stream);
+
 /* ---- latency-optimised host round trip ------------------------------------------------------------------------
  * One env step with HOST action in / HOST results out, returned in the reference's own ragged spirit: the 12 self
  * values of every observation plus only the neighbour rows that exist (an observation is 12 + 9*max(k,1) values in

@@ -300,3 +300,39 @@ def test_unrolled_rollout_fills_the_buffers_like_the_per_step_rollout():
             assert torch.equal(torch.nan_to_num(a.float(), 7.0), torch.nan_to_num(b.float(), 7.0)), (ep, k)
     assert bufs[0][2] == bufs[1][2] and bufs[0][2] > 0
     assert int(bufs[0][0]["cut"].sum()) > 0
+
+
+@pytest.mark.parametrize("mask_some", [False, True])
+def test_native_update_iteration_matches_the_autograd_iteration(mask_some):
+    """PPOConfig.native_update (reader / MLP / loss forward and backward as a fixed sequence of our own kernels, no autograd tape) against the same
+    iteration through torch autograd over the same kernels: the whole gradient bucket, the approx-KL, both losses; then parameters after an update."""
+    from uaisa_env.scenario import scenario_c1
+    from uaisa_env.vec_env import VecMdin
+    from uaisa_ppo.trainer import PPOConfig, PPOTrainer
+    res = []
+    for native in (True, False):
+        env = VecMdin(scenario_c1(), 40, neighbors_num=10)
+        tr = PPOTrainer(env, cfg=PPOConfig(steps_per_epoch=20, max_ep_len=9, train_pi_iters=3, train_v_iters=3, minibatch=1000, pi_lr=1e-3, vf_lr=1e-3, target_kl=10.0,
+                                           native_update=native, graph_update=False), seed=5)
+        torch.manual_seed(17)
+        tr.rollout()
+        if mask_some:                                      # inf / nan rewards of the reference (ir_gym.py:88): masked samples
+            tr.buf["rew"][3, 5] = float("inf"); tr.buf["rew"][7, 11] = float("nan")
+        tr._begin_update(); tr._u["cap"] = -1
+        assert tr._native() == native
+        F = tr.flat
+        F.g.zero_(); tr._pi_fb(); g_pi = F.g.clone()
+        tr._u["off"].zero_()
+        F.g.zero_(); tr._v_fb(); g_v = F.g.clone(); lv = float(tr._u["loss_v"])
+        torch.manual_seed(23)
+        p0 = F.p.clone()
+        st = tr.update()
+        res.append((g_pi, g_v, lv, F.p.clone() - p0, st["pi_iters"]))
+        tr.close(); env.close()
+    (gp1, gv1, lv1, d1, it1), (gp0, gv0, lv0, d0, it0) = res
+    for a, b, name in ((gp1, gp0, "pi gradients + kl + loss"), (gv1, gv0, "v gradients")):
+        assert float(b.abs().max()) > 0
+        assert float((a - b).abs().max()) <= 2e-5 * float(b.abs().max()) + 1e-9, (name, float((a - b).abs().max()), float(b.abs().max()))
+    assert abs(lv1 - lv0) <= 1e-5 * max(1.0, abs(lv0)) and it1 == it0 == 3
+    cos = float((d1 * d0).sum() / (d1.norm() * d0.norm()))
+    assert cos > 0.999, cos

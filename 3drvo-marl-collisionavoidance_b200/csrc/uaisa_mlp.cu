@@ -49,43 +49,65 @@ constexpr int GM_A_STAGE = GM_M * 128;  // bytes of one A chunk [128 rows x 32 f
 
 template <int NT> constexpr int gemm_smem() { return 1024 + 2 * (GM_A_STAGE + NT * 128) + 128 * 4 * 4 + 64; }
 
-// ---- operand chunk loaders: [ROWS x 32 floats] of chunk k0, rows row0.., into registers (zero beyond the matrix) -------------------------
+// ---- operand chunk loader: [ROWS x 32 floats] of one K chunk into registers (zero beyond the matrix), then into the swizzled stage -----------------
+// Everything that does not depend on the chunk -- the item's element offset in global memory, its swizzled byte offset in the stage, whether its row
+// exists -- is computed ONCE per thread; a full chunk then costs one load and one store per item (the first version recomputed indices and bounds for
+// every item of every chunk: 600 instructions per thread and chunk, the kernel was issue-bound on them).
 template <int ROWS>
-__device__ __forceinline__ void load_chunk(float4 (&r)[ROWS * 8 / GM_T], const float *__restrict__ X, int ld, int mn, int row0, int R, int k0, int Kend,
-                                           bool vec, int tid) {
+struct Loader {
+    static constexpr int NI = ROWS * 8 / GM_T;
+    uint32_t goff[NI], soff[NI], ok;
+    int ld, mn, step;
+    bool vec;
+    const float *X;
+    __device__ __forceinline__ void init(const float *X_, int ld_, int mn_, int row0, int R, int kb, bool vec_, int tid) {
+        X = X_; ld = ld_; mn = mn_; vec = vec_; ok = 0u; step = mn_ ? 32 * ld_ : 32;
 #pragma unroll
-    for (int i = 0; i < ROWS * 8 / GM_T; i++) {
-        const int item = tid + i * GM_T;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (!mn) {                                        // X[row][k]: 8 consecutive threads read one 128-byte row piece
-            const int row = item >> 3, k = k0 + ((item & 7) << 2), g = row0 + row;
-            if (g < R && k < Kend) {
-                const float *p = X + (size_t)g * ld + k;
-                if (vec && k + 3 < Kend) v = __ldg(reinterpret_cast<const float4 *>(p));
-                else { v.x = __ldg(p); if (k + 1 < Kend) v.y = __ldg(p + 1); if (k + 2 < Kend) v.z = __ldg(p + 2); if (k + 3 < Kend) v.w = __ldg(p + 3); }
+        for (int i = 0; i < NI; i++) {
+            const int item = tid + i * GM_T;
+            const int row = mn_ ? item % ROWS : item >> 3, k4 = mn_ ? item / ROWS : item & 7, g = row0 + row;
+            if (g < R) ok |= 1u << i;
+            goff[i] = mn_ ? (uint32_t)(kb + 4 * k4) * (uint32_t)ld_ + (uint32_t)g : (uint32_t)g * (uint32_t)ld_ + (uint32_t)(kb + 4 * k4);
+            soff[i] = (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((k4 ^ (row & 7)) << 4));
+        }
+    }
+    // chunk c of this CTA's K range; krem = K elements left from the chunk's first one (>= 32: a full chunk)
+    __device__ __forceinline__ void load(float4 (&r)[NI], int c, int krem, int tid) const {
+        const float *base = X + (size_t)c * step;
+        if (krem >= 32) {
+#pragma unroll
+            for (int i = 0; i < NI; i++) {
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if ((ok >> i) & 1u) {
+                    const float *p = base + goff[i];
+                    if (!mn) {
+                        if (vec) v = __ldg(reinterpret_cast<const float4 *>(p));
+                        else { v.x = __ldg(p); v.y = __ldg(p + 1); v.z = __ldg(p + 2); v.w = __ldg(p + 3); }
+                    } else { v.x = __ldg(p); v.y = __ldg(p + ld); v.z = __ldg(p + 2 * ld); v.w = __ldg(p + 3 * ld); }
+                }
+                r[i] = v;
             }
-        } else {                                          // X[k][row]: consecutive threads read consecutive rows of four k
-            const int row = item % ROWS, k = k0 + ((item / ROWS) << 2), g = row0 + row;
-            if (g < R) {
-                const float *p = X + (size_t)k * ld + g;
-                if (k < Kend) v.x = __ldg(p);
-                if (k + 1 < Kend) v.y = __ldg(p + ld);
-                if (k + 2 < Kend) v.z = __ldg(p + 2 * (size_t)ld);
-                if (k + 3 < Kend) v.w = __ldg(p + 3 * (size_t)ld);
+        } else {                      // the ragged last chunk: per-element bounds
+#pragma unroll
+            for (int i = 0; i < NI; i++) {
+                const int item = tid + i * GM_T, k = (mn ? item / ROWS : item & 7) << 2, st = mn ? ld : 1;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if ((ok >> i) & 1u) {
+                    const float *p = base + goff[i];
+                    if (k < krem) v.x = __ldg(p);
+                    if (k + 1 < krem) v.y = __ldg(p + st);
+                    if (k + 2 < krem) v.z = __ldg(p + 2 * st);
+                    if (k + 3 < krem) v.w = __ldg(p + 3 * st);
+                }
+                r[i] = v;
             }
         }
-        r[i] = v;
     }
-}
-template <int ROWS>
-__device__ __forceinline__ void store_chunk(const float4 (&r)[ROWS * 8 / GM_T], char *tile, int mn, int tid) {
+    __device__ __forceinline__ void store(const float4 (&r)[NI], char *tile) const {
 #pragma unroll
-    for (int i = 0; i < ROWS * 8 / GM_T; i++) {
-        const int item = tid + i * GM_T;
-        const int row = mn ? item % ROWS : item >> 3, k4 = mn ? item / ROWS : item & 7;
-        *swz(tile, row, k4) = r[i];
+        for (int i = 0; i < NI; i++) *reinterpret_cast<float4 *>(tile + soff[i]) = r[i];
     }
-}
+};
 
 template <int NT>
 __global__ void __launch_bounds__(GM_T, NT <= 256 ? 2 : 1) uaisa_mlp_gemm_kernel(const __grid_constant__ GemmParams P) {
@@ -115,17 +137,17 @@ __global__ void __launch_bounds__(GM_T, NT <= 256 ? 2 : 1) uaisa_mlp_gemm_kernel
     constexpr uint32_t IDESC_MAIN = umma_idesc_tf32(GM_M, NT <= 256 ? NT : 256), IDESC_TAIL = umma_idesc_tf32(GM_M, NT > 256 ? NT - 256 : 8);
 
     float4 ra[GM_M * 8 / GM_T], rb[NT * 8 / GM_T];
-    load_chunk<GM_M>(ra, P.A, P.lda, P.a_mn, m0, P.M, kb, Kend, vecA, tid);
-    load_chunk<NT>(rb, P.B, P.ldb, P.b_mn, 0, P.N, kb, Kend, vecB, tid);
+    Loader<GM_M> la; la.init(P.A, P.lda, P.a_mn, m0, P.M, kb, vecA, tid);
+    Loader<NT> lb; lb.init(P.B, P.ldb, P.b_mn, 0, P.N, kb, vecB, tid);
+    la.load(ra, 0, Kend - kb, tid); lb.load(rb, 0, Kend - kb, tid);
     uint32_t par[2] = {0u, 0u};
     for (int c = 0; c < nch; c++) {
         const int s = c & 1;
         if (c >= 2) { mbar_wait(empty0 + 8 * s, par[s]); par[s] ^= 1u; }       // the MMAs that read this stage have completed
-        store_chunk<GM_M>(ra, As + s * GM_A_STAGE, P.a_mn, tid);
-        store_chunk<NT>(rb, Bs + s * B_STAGE, P.b_mn, tid);
+        la.store(ra, As + s * GM_A_STAGE);
+        lb.store(rb, Bs + s * B_STAGE);
         if (c + 1 < nch) {                                                     // next chunk's loads fly while this one is multiplied
-            load_chunk<GM_M>(ra, P.A, P.lda, P.a_mn, m0, P.M, kb + 32 * (c + 1), Kend, vecA, tid);
-            load_chunk<NT>(rb, P.B, P.ldb, P.b_mn, 0, P.N, kb + 32 * (c + 1), Kend, vecB, tid);
+            la.load(ra, c + 1, Kend - kb - 32 * (c + 1), tid); lb.load(rb, c + 1, Kend - kb - 32 * (c + 1), tid);
         }
         fence_proxy_async();
         fence_before_sync();

@@ -306,16 +306,27 @@ __global__ void __launch_bounds__(512) uaisa_reader_bwd_kernel(const float *__re
 }
 
 // ---- PPO losses and their gradients with respect to the heads' outputs (multi_ppo.py:379-404), one thread per minibatch sample --------------------
-// scal[0] <- max(1, number of usable samples): samples whose advantage / return is not finite are masked out (ok[i] == 0)
-__global__ void __launch_bounds__(1024) uaisa_ppo_wsum_kernel(const uint8_t *__restrict__ ok, const long long *__restrict__ idx, int B, float *__restrict__ scal) {
-    __shared__ int red[32];
+// scal[0] <- max(1, number of usable samples): samples whose advantage / return is not finite are masked out (ok[i] == 0).  scal[1], scal[2] are an
+// integer counter and an arrival ticket (zero between launches: the last CTA to arrive publishes the count and re-arms them).
+__global__ void __launch_bounds__(256) uaisa_ppo_wsum_kernel(const uint8_t *__restrict__ ok, const long long *__restrict__ idx, int B, float *__restrict__ scal) {
+    __shared__ int red[8];
     int c = 0;
-    for (int s = threadIdx.x; s < B; s += 1024) c += ok[idx ? idx[s] : s] ? 1 : 0;
+    for (int s = blockIdx.x * 256 + threadIdx.x; s < B; s += gridDim.x * 256) c += ok[idx ? idx[s] : s] ? 1 : 0;
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) c += __shfl_xor_sync(0xffffffffu, c, off);
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = c;
     __syncthreads();
-    if (threadIdx.x == 0) { int t = 0; for (int w = 0; w < 32; w++) t += red[w]; scal[0] = (float)(t > 1 ? t : 1); }
+    if (threadIdx.x == 0) {
+        int t = 0; for (int w = 0; w < 8; w++) t += red[w];
+        int *cnt = reinterpret_cast<int *>(scal + 1), *ticket = reinterpret_cast<int *>(scal + 2);
+        atomicAdd(cnt, t);
+        __threadfence();
+        if (atomicAdd(ticket, 1) == (int)gridDim.x - 1) {
+            const int tot = atomicAdd(cnt, 0);
+            scal[0] = (float)(tot > 1 ? tot : 1);
+            *cnt = 0; *ticket = 0;
+        }
+    }
 }
 
 __device__ __forceinline__ float nan_to_zero(float x) { return (x == x && fabsf(x) <= 3.402823466e38f) ? x : 0.0f; }   // torch.nan_to_num(x, 0, 0, 0)
@@ -429,10 +440,11 @@ int uaisa_reader_bwd(const float *obs, const int64_t *idx, int32_t B, int32_t ob
 }
 
 // PPO losses of one update iteration and their gradients with respect to the heads' outputs (multi_ppo.py:379-404), minibatch gathered through idx
-// (may be NULL).  scal: float[1] workspace (the usable-sample count, written by uaisa_ppo_wsum).  See the kernels above for the outputs.
+// (may be NULL).  scal: float[4] workspace, ZEROED once by the caller ([0] = the usable-sample count written by uaisa_ppo_wsum, [1..2] its counters).  See the kernels above for the outputs.
 int uaisa_ppo_wsum(const uint8_t *ok, const int64_t *idx, int32_t B, float *scal, void *stream) {
     if (!ok || !scal || B < 1) return -1;
-    uaisa::uaisa_ppo_wsum_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(ok, reinterpret_cast<const long long *>(idx), B, scal);
+    const int grid = (B + 1023) / 1024 < 148 ? (B + 1023) / 1024 : 148;
+    uaisa::uaisa_ppo_wsum_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(ok, reinterpret_cast<const long long *>(idx), B, scal);
     return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 int uaisa_ppo_pi_loss(const float *y, const float *log_std, float std_factor, const float *act, const float *logp_old, const float *adv, const uint8_t *ok,

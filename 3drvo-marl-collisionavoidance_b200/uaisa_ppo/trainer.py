@@ -325,7 +325,7 @@ class PPOTrainer:
         if ws is None:
             e = lambda *sh: torch.empty(sh, dtype=torch.float32, device=dev)  # noqa: E731
             ws = u["ws"] = {"feat": e(B, 268), "stats": e(B, 2), "hsum": e(B, 256), "H1": e(B, 256), "H2": e(B, 256), "y": e(B, 3), "dy": e(B, 3),
-                            "dZ2": e(B, 256), "dZ1": e(B, 256), "dfeat": e(B, 268), "scal": e(4)}
+                            "dZ2": e(B, 256), "dZ1": e(B, 256), "dfeat": e(B, 268), "scal": torch.zeros(4, dtype=torch.float32, device=dev)}
         p = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
         s = F._s()
         rd = self.ac.pi.rnn_reader

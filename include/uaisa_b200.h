@@ -238,7 +238,7 @@ int uaisa_colsum(const float *X, int32_t rows, int32_t cols, float *out, void *s
 
 /* PPO losses of one update iteration and their gradients with respect to the heads' outputs (multi_ppo.compute_loss_pi / compute_loss_v, multi_ppo.py:379-404),
  * one thread per minibatch sample; idx (may be NULL): int64[B], the buffer row of each sample; ok: uint8 per buffer row (0 = advantage / return not finite:
- * masked out).  uaisa_ppo_wsum writes scal[0] = max(1, usable samples).  uaisa_ppo_pi_loss: y [B][3] = the actor's pre-tanh output -> dy [B][3] =
+ * masked out).  uaisa_ppo_wsum writes scal[0] = max(1, usable samples); scal is float[4], zeroed ONCE by the caller ([1..2] are the kernel's counters, re-armed by itself).  uaisa_ppo_pi_loss: y [B][3] = the actor's pre-tanh output -> dy [B][3] =
  * d(loss / W) / dy with inv_world = 1 / W; ADDS d/dlog_std to dlogstd[3], approx-KL / W to slots[0] and loss / W to slots[1].  uaisa_ppo_v_loss: y [B] =
  * the critic's output -> dy [B]; ADDS the loss to loss_out[0].  Asynchronous on `stream`, capturable in a CUDA graph. */
 int uaisa_ppo_wsum(const uint8_t *ok, const int64_t *idx, int32_t B, float *scal, void *stream);

@@ -89,6 +89,13 @@ enum Region : int { RG_PROLOGUE = 0, RG_FILL, RG_SYNC, RG_DRONESTATE, RG_PAIRS, 
 #define RG_FLUSH() do { } while (0)
 #endif
 
+#define UAISA_PRAGMA_(x) _Pragma(#x)
+#define UAISA_PRAGMA(x) UAISA_PRAGMA_(x)
+#ifdef UAISA_PAIR_UNROLL        // experiments: unroll factor of the stage-1b / stage-2a mask loops (profiles/variants.sh)
+#define UAISA_PAIR_UNROLL_PRAGMA UAISA_PRAGMA(unroll UAISA_PAIR_UNROLL)
+#else
+#define UAISA_PAIR_UNROLL_PRAGMA
+#endif
 #ifndef UAISA_LB_THREADS
 #define UAISA_LB_THREADS MAXT   // experiments: smaller CTAs with a different register cap (profiles/variants.sh)
 #endif
@@ -532,6 +539,7 @@ __global__ void __launch_bounds__(UAISA_LB_THREADS, (MAXT <= 128 ? UAISA_MINB128
                         { const unsigned notself = ((unsigned)(wk - jb) < 32u) ? ~(1u << (wk - jb)) : ~0u; near &= notself; slow &= notself; }
                     }
                     if ((near | slow) == 0u) continue;          // nobody in range in this chunk (the common case in sparse airspace): one branch instead of five empty loops
+                    UAISA_PAIR_UNROLL_PRAGMA
                     for (unsigned m = near; m; m &= m - 1) {     // stage 1b: collision / moving-away gates of the near ones (fp64)
                         const int jj = __ffs(m) - 1;
                         const int bits = pair_near_fast(P, d.px, d.py, d.pz, d.vx, d.vy, d.vz, C.radius, sxr + wlbase + jb + jj, sst);
@@ -553,6 +561,7 @@ __global__ void __launch_bounds__(UAISA_LB_THREADS, (MAXT <= 128 ? UAISA_MINB128
                     n_cone += __popc(cand);
                     // stage 2a: trig-free screen of every candidate (uniform work) -> inside / ambiguous masks
                     unsigned ins = 0, amb = 0;
+                    UAISA_PAIR_UNROLL_PRAGMA
                     for (unsigned m = cand; m; m &= m - 1) {
                         const int jj = __ffs(m) - 1;
                         PairGeom g; pair_geom(P, d.px, d.py, d.pz, d.vx, d.vy, d.vz, C.radius, C.prio, sxr + wlbase + jb + jj, sst, ex_, ey_, ez_, g);

@@ -80,7 +80,8 @@ class _MlpTc(torch.autograd.Function):
     ReLU / output-layer / ReLU-mask epilogues, split-K vector atomics for the weight gradients) plus two small CUDA-core kernels -- instead of
     torch autograd's cuBLAS SIMT fp32 GEMMs (policy_rnn_ac.py:206-257 forward, multi_ppo.py:379-404 backward through autograd)."""
 
-    SPLITS = 74     # split-K CTAs per 128-row tile of a weight gradient (x 2 tiles = 148 CTAs)
+    SPLITS = 74     # split-K CTAs per 128-row tile of a weight gradient whose CTA tile is 288 wide (one CTA per SM: x 2 row tiles = 148 CTAs)
+    SPLITS_256 = 148   # ... whose CTA tile is 256 wide (two CTAs per SM); measured at K = 65 536: 55.8 us instead of 62.0 (profiles/gemm_splits.py)
 
     @staticmethod
     def _lib():
@@ -122,8 +123,8 @@ class _MlpTc(torch.autograd.Function):
         dZ1 = torch.empty((B, 256), dtype=torch.float32, device=dev)
         if L.uaisa_mlp_out_bwd(p(dy), p(H2), p(W3), B, nout, p(dZ2), p(dW3), p(db3), p(db2), s):                              # dZ2, db2, dW3, db3
             raise RuntimeError("uaisa_mlp_out_bwd failed")
-        sp = max(1, min(_MlpTc.SPLITS, (B + 31) // 32))
-        _MlpTc._gemm(L, C, s, dZ2, 256, 1, H1, 256, 1, dW2, 256, 256, 256, B, sp, 4)                                          # dW2 = dZ2^T H1       (K = batch)
+        sp, sp2 = max(1, min(_MlpTc.SPLITS, (B + 31) // 32)), max(1, min(_MlpTc.SPLITS_256, (B + 31) // 32))
+        _MlpTc._gemm(L, C, s, dZ2, 256, 1, H1, 256, 1, dW2, 256, 256, 256, B, sp2, 4)                                          # dW2 = dZ2^T H1       (K = batch)
         _MlpTc._gemm(L, C, s, dZ2, 256, 0, W2, 256, 1, dZ1, 256, B, 256, 256, 1, 3, mask=H1, ldm=256)                         # dZ1 = (dZ2 W2) * (H1 > 0)
         if L.uaisa_colsum(p(dZ1), B, 256, p(db1), s):                                                                         # db1
             raise RuntimeError("uaisa_colsum failed")

@@ -351,8 +351,8 @@ class PPOTrainer:
             u["loss_v"].zero_()
             chk(L.uaisa_ppo_v_loss(p(ws["y"]), p(self._ret), p(self._ok), p(idx), B, 1.0 / W, p(ws["scal"]), p(ws["dy"]), p(u["loss_v"]), s), "uaisa_ppo_v_loss")
         chk(L.uaisa_mlp_out_bwd(p(ws["dy"]), p(ws["H2"]), p(W3), B, nout, p(ws["dZ2"]), p(W3.grad), p(b3.grad), p(b2.grad), s), "uaisa_mlp_out_bwd")
-        sp = max(1, min(_MlpTc.SPLITS, (B + 31) // 32))
-        g(ws["dZ2"], 256, 1, ws["H1"], 256, 1, W2.grad, 256, 256, 256, B, sp, 4)
+        sp, sp2 = max(1, min(_MlpTc.SPLITS, (B + 31) // 32)), max(1, min(_MlpTc.SPLITS_256, (B + 31) // 32))
+        g(ws["dZ2"], 256, 1, ws["H1"], 256, 1, W2.grad, 256, 256, 256, B, sp2, 4)
         g(ws["dZ2"], 256, 0, W2, 256, 1, ws["dZ1"], 256, B, 256, 256, 1, 3, mask=ws["H1"], ldm=256)
         chk(L.uaisa_colsum(p(ws["dZ1"]), B, 256, p(b1.grad), s), "uaisa_colsum")
         g(ws["dZ1"], 256, 1, ws["feat"], 268, 1, W1.grad, 268, 256, 268, B, sp, 4)

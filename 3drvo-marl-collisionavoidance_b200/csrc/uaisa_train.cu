@@ -141,7 +141,12 @@ __device__ __forceinline__ float rd_tanh(float x) { return 1.0f - __fdividef(2.0
 //                 LayerNorm backward -> dh[256], and dfeat * xhat for the LayerNorm weight gradient)
 //   (backward)    gradient phase: thread = (d, u) again, gates recomputed, 27 weight + 4 bias gradients accumulated in registers over ALL the CTA's tiles;
 //                 threads < 268 accumulate the LayerNorm weight / bias gradients; one atomicAdd per value per CTA at the end.
-constexpr int RB_T = 15;      // (the backward kernel fits the 48 KB of static shared memory with 15)
+#ifndef UAISA_RB_T
+#define UAISA_RB_T 32
+#endif
+constexpr int RB_T = UAISA_RB_T;   // samples per tile: three CTA barriers are paid per tile (15, what 48 KB of static shared memory held, measured 126 / 337 us
+                                   // per 65 536 samples forward / backward); the arrays now live in dynamic shared memory (101 KB for the backward)
+constexpr int RB_SMEM_FWD = (RB_T * (RD_IN + 3) + RB_T * 2 * RD_H) * 4, RB_SMEM_BWD = RB_SMEM_FWD + RB_T * RD_FEAT * 4;
 
 struct ReaderThread {                 // thread (d, u): its weights, biases
     float wv[3][RD_IN], br, bz, bn, bhn;
@@ -172,8 +177,9 @@ __device__ __forceinline__ void load_x_tile(float (*s_x)[RD_IN + 3], const float
 
 __global__ void __launch_bounds__(512) uaisa_reader_fwd_kernel(const float *__restrict__ obs, const long long *__restrict__ idx, int B, int obs_dim, ReaderW W,
                                                                  float *__restrict__ feat, float *__restrict__ stats, float *__restrict__ hsum) {
-    __shared__ float s_x[RB_T][RD_IN + 3];
-    __shared__ float s_h[RB_T][2][RD_H];
+    extern __shared__ __align__(16) float rd_smem[];
+    float (*s_x)[RD_IN + 3] = reinterpret_cast<float (*)[RD_IN + 3]>(rd_smem);
+    float (*s_h)[2][RD_H] = reinterpret_cast<float (*)[2][RD_H]>(rd_smem + RB_T * (RD_IN + 3));
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, d = tid >> 8, u = tid & 255;
     ReaderThread T; T.load(W, d, u);
     const int n_tiles = (B + RB_T - 1) / RB_T;
@@ -189,8 +195,8 @@ __global__ void __launch_bounds__(512) uaisa_reader_fwd_kernel(const float *__re
             s_h[j][d][u] = (1.0f - z) * n;
         }
         __syncthreads();
-        if (warp < ns) {                                   // row phase: warp j = sample s0 + j; lane l owns units l, l+32, ... and (l < 12) self value l
-            const int j = warp, s = s0 + j;
+        for (int j = warp; j < ns; j += 16) {              // row phase: a warp per sample; lane l owns units l, l+32, ... and (l < 12) self value l
+            const int s = s0 + j;
             const float *o = obs + (size_t)(idx ? idx[s] : s) * obs_dim;
             float h[8];
 #pragma unroll
@@ -224,9 +230,10 @@ __global__ void __launch_bounds__(512) uaisa_reader_fwd_kernel(const float *__re
 
 __global__ void __launch_bounds__(512) uaisa_reader_bwd_kernel(const float *__restrict__ obs, const long long *__restrict__ idx, int B, int obs_dim, ReaderW W,
                                                                  const float *__restrict__ dfeat, const float *__restrict__ stats, const float *__restrict__ hsum, ReaderG G) {
-    __shared__ float s_x[RB_T][RD_IN + 3];           // x of the tile's samples
-    __shared__ float s_h[RB_T][2][RD_H];             // gates phase: h per direction; row phase overwrites [j][0][.] with d loss / d (h_fwd + h_bwd)
-    __shared__ float s_gw[RB_T][RD_FEAT];            // dfeat * xhat  (LayerNorm weight gradient terms)
+    extern __shared__ __align__(16) float rd_smem[];
+    float (*s_x)[RD_IN + 3] = reinterpret_cast<float (*)[RD_IN + 3]>(rd_smem);                               // x of the tile's samples
+    float (*s_h)[2][RD_H] = reinterpret_cast<float (*)[2][RD_H]>(rd_smem + RB_T * (RD_IN + 3));              // gates phase: h per direction; row phase overwrites [j][0][.] with d loss / d (h_fwd + h_bwd)
+    float (*s_gw)[RD_FEAT] = reinterpret_cast<float (*)[RD_FEAT]>(rd_smem + RB_T * (RD_IN + 3) + RB_T * 2 * RD_H);   // dfeat * xhat  (LayerNorm weight gradient terms)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, d = tid >> 8, u = tid & 255;
     ReaderThread T; T.load(W, d, u);
     float aw[3][RD_IN], ab[4], alw = 0.0f, alb = 0.0f;
@@ -250,8 +257,8 @@ __global__ void __launch_bounds__(512) uaisa_reader_bwd_kernel(const float *__re
             }
             __syncthreads();
         }
-        if (warp < ns) {                                   // row phase: LayerNorm backward of sample s0 + warp
-            const int j = warp, s = s0 + j;
+        for (int j = warp; j < ns; j += 16) {              // row phase: LayerNorm backward, a warp per sample
+            const int s = s0 + j;
             const float *o = obs + (size_t)(idx ? idx[s] : s) * obs_dim;
             const float mean = stats[2 * s], rstd = stats[2 * s + 1];
             const float sv = (lane < RD_SELF) ? __ldg(o + lane) : 0.0f;
@@ -411,6 +418,18 @@ __global__ void __launch_bounds__(256) uaisa_ppo_v_loss_kernel(const float *__re
 
 extern "C" {
 
+static int reader_attrs() {      // dynamic shared memory above 48 KB is an opt-in, per device
+    static bool set[64] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return -2;
+    if (dev < 0 || dev >= 64 || !set[dev]) {
+        if (cudaFuncSetAttribute(uaisa::uaisa_reader_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, uaisa::RB_SMEM_FWD) != cudaSuccess) return -2;
+        if (cudaFuncSetAttribute(uaisa::uaisa_reader_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, uaisa::RB_SMEM_BWD) != cudaSuccess) return -2;
+        if (dev >= 0 && dev < 64) set[dev] = true;
+    }
+    return 0;
+}
+
 // params: 8 DEVICE pointers weight_ih_l0, bias_ih_l0, bias_hh_l0, weight_ih_l0_reverse, bias_ih_l0_reverse, bias_hh_l0_reverse, ln.weight, ln.bias (torch layouts).
 // obs [*, obs_dim]; idx (may be NULL): int64[B] row of `obs` each sample reads; feat [B][268]; stats [B][2] = LayerNorm mean, rstd (saved for the backward).
 int uaisa_reader_fwd(const float *obs, const int64_t *idx, int32_t B, int32_t obs_dim, const float *const *params, float *feat, float *stats, float *hsum, void *stream) {
@@ -419,7 +438,8 @@ int uaisa_reader_fwd(const float *obs, const int64_t *idx, int32_t B, int32_t ob
     for (int d = 0; d < 2; d++) { W.w_ih[d] = params[3 * d]; W.b_ih[d] = params[3 * d + 1]; W.b_hh[d] = params[3 * d + 2]; }
     W.ln_w = params[6]; W.ln_b = params[7];
     const int tiles_f = (B + uaisa::RB_T - 1) / uaisa::RB_T;
-    uaisa::uaisa_reader_fwd_kernel<<<tiles_f < 592 ? tiles_f : 592, 512, 0, static_cast<cudaStream_t>(stream)>>>(obs, reinterpret_cast<const long long *>(idx), B, obs_dim, W, feat, stats, hsum);
+    if (reader_attrs()) return -2;
+    uaisa::uaisa_reader_fwd_kernel<<<tiles_f < 592 ? tiles_f : 592, 512, uaisa::RB_SMEM_FWD, static_cast<cudaStream_t>(stream)>>>(obs, reinterpret_cast<const long long *>(idx), B, obs_dim, W, feat, stats, hsum);
     return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 
@@ -435,7 +455,8 @@ int uaisa_reader_bwd(const float *obs, const int64_t *idx, int32_t B, int32_t ob
     W.ln_w = params[6]; W.ln_b = params[7]; G.ln_w = grads[6]; G.ln_b = grads[7];
     const int tiles = (B + uaisa::RB_T - 1) / uaisa::RB_T;
     const int grid = tiles < 444 ? tiles : 444;      // 3 CTAs of 512 threads per SM
-    uaisa::uaisa_reader_bwd_kernel<<<grid, 512, 0, static_cast<cudaStream_t>(stream)>>>(obs, reinterpret_cast<const long long *>(idx), B, obs_dim, W, dfeat, stats, hsum, G);
+    if (reader_attrs()) return -2;
+    uaisa::uaisa_reader_bwd_kernel<<<grid, 512, uaisa::RB_SMEM_BWD, static_cast<cudaStream_t>(stream)>>>(obs, reinterpret_cast<const long long *>(idx), B, obs_dim, W, dfeat, stats, hsum, G);
     return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 

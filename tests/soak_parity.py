@@ -34,4 +34,39 @@ for name, mk, E, T, kw in CASES:
           % ("OK " if ok else "BAD", name, s["n_agent_steps"], s["rows"], s["dones"], s["resets"], s["flag_mismatch"], s["count_mismatch"], s["nbr_mismatch"],
              s["obs_inexact"], s["obs_vals"], s["rew_inexact"], s["rew_vals"], s["state_inexact"], s["state_vals"],
              max(s["obs_maxrel"], s["rew_maxrel"], s["state_maxrel"]), time.time() - t0), flush=True)
+
+# ---- T-step launches (deferred re-observation, owner / helper split, 128-register dense kernels, clusters + slices) against single steps, every output bit for bit
+import torch
+from uaisa_env.vec_env import VecMdin
+ROLL = [("configs[1] 1024x4 (owner / helper split)", scenario_c1, 1024, 120, 20), ("configs[1] scenario 16384x4", scenario_c1, 16384, 60, 20),
+        ("configs[2] 4 scenarios x16 drones, 1024 envs", lambda: scenario_c3(seed=5, n_scenarios=4), 1024, 60, 20),
+        ("swarm of 20, 256 envs", lambda: swarm(20, 1.3, 9), 256, 80, 16), ("configs[3] 256 drones, 6 envs", lambda: scenario_c4(seed=2, n_scenarios=2), 6, 40, 8),
+        ("100 drones dense, 6 envs", lambda: scenario_c4(seed=6, n_scenarios=1, n_drones=100), 6, 40, 8)]
+for name, mk, E, T, chunk in ROLL:
+    t0 = time.time()
+    scn = mk()
+    a = VecMdin(scn, E, neighbors_num=10); b = VecMdin(scn, E, neighbors_num=10)
+    a.reset(); b.reset()
+    A = a.A
+    acts = torch.from_numpy(np.round(np.random.default_rng(3).uniform(-1, 1, (T, A, 3)), 2).astype(np.float32)).cuda()
+    out = {"obs": torch.zeros((T, A, a.obs_dim), device="cuda"), "count": torch.zeros((T, A), dtype=torch.uint8, device="cuda"),
+           "nbr": torch.zeros((T, A, 10), dtype=torch.int32, device="cuda"), "reward": torch.zeros((T, A), device="cuda"),
+           "done": torch.zeros((T, A), dtype=torch.uint8, device="cuda"), "info": torch.zeros((T, A), dtype=torch.uint8, device="cuda"),
+           "finish": torch.zeros((T, A), dtype=torch.uint8, device="cuda")}
+    for s0 in range(0, T, chunk):
+        a.rollout(acts[s0:s0 + chunk], {k: v[s0:s0 + chunk] for k, v in out.items()}, auto_reset=True, max_ep_len=25)
+    mism = resets = rows = 0
+    for t in range(T):
+        b.step(acts[t])
+        for k in ("reward", "done", "info", "finish"):
+            mism += int((torch.nan_to_num(getattr(b, k).float(), 7.0).view(-1) != torch.nan_to_num(out[k][t].float(), 7.0).view(-1)).sum())
+        b.autoreset(max_ep_len=25)
+        resets += int(b.reset_mask.sum()); rows += int(b.count.sum())
+        for k in ("obs", "count", "nbr"):
+            mism += int((getattr(b, k) != out[k][t]).sum())
+    sa, sb = a.get_state(), b.get_state()
+    mism += sum(int((sa[k] != sb[k]).sum()) for k in sa)
+    bad += mism != 0
+    print("%s | rollout == steps | %s | agent-steps %d rows %d resets %d | mismatching values %d | %.0f s" % ("OK " if mism == 0 else "BAD", name, A * T, rows, resets, mism, time.time() - t0), flush=True)
+    a.close(); b.close()
 sys.exit(1 if bad else 0)

@@ -41,7 +41,10 @@ from uaisa_env.vec_env import VecMdin
 ROLL = [("configs[1] 1024x4 (owner / helper split)", scenario_c1, 1024, 120, 20), ("configs[1] scenario 16384x4", scenario_c1, 16384, 60, 20),
         ("configs[2] 4 scenarios x16 drones, 1024 envs", lambda: scenario_c3(seed=5, n_scenarios=4), 1024, 60, 20),
         ("swarm of 20, 256 envs", lambda: swarm(20, 1.3, 9), 256, 80, 16), ("configs[3] 256 drones, 6 envs", lambda: scenario_c4(seed=2, n_scenarios=2), 6, 40, 8),
-        ("100 drones dense, 6 envs", lambda: scenario_c4(seed=6, n_scenarios=1, n_drones=100), 6, 40, 8)]
+        ("100 drones dense, 6 envs", lambda: scenario_c4(seed=6, n_scenarios=1, n_drones=100), 6, 40, 8),
+        # BASELINE.json's full sizes
+        ("configs[4] env part 65536x4", scenario_c1, 65536, 40, 20), ("configs[2] 4096x16 + cylinders", lambda: scenario_c3(seed=0, n_scenarios=8), 4096, 20, 10),
+        ("configs[3] 64x256", lambda: scenario_c4(seed=0, n_scenarios=2), 64, 20, 10)]
 for name, mk, E, T, chunk in ROLL:
     t0 = time.time()
     scn = mk()

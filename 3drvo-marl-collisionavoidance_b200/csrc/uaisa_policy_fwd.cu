@@ -496,6 +496,29 @@ __global__ void __launch_bounds__(FW_NT, 1) uaisa_policy_forward_kernel(const __
 template __global__ void uaisa_policy_forward_kernel<1>(const __grid_constant__ FwdParams);
 template __global__ void uaisa_policy_forward_kernel<2>(const __grid_constant__ FwdParams);
 
+
+// rnn_ac.step's sampling (policy_rnn_ac.py:57-69 with GaussianActor._distribution :206-228 and _log_prob_from_distribution): std = clamp(std_factor exp(log_std) + 1e-6,
+// 1e-4, 10), a = mu + std eps, logp = sum_q( -(a - mu)^2 / (2 std^2) - log std - log sqrt(2 pi) ) -- the dozen element-wise torch kernels of one rollout step
+// in ONE launch; every operation in the order (and rounding) of the torch expression it replaces.  eps comes from the caller (torch's generator).
+__global__ void uaisa_policy_sample_kernel(const float *__restrict__ mu, const float *__restrict__ eps, const float *__restrict__ log_std, float std_factor, int A,
+                                           float *__restrict__ a_out, float *__restrict__ logp) {
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= A) return;
+    float lp = 0.0f;
+#pragma unroll
+    for (int q = 0; q < 3; q++) {
+        const float sd = fminf(fmaxf(__fadd_rn(__fmul_rn(std_factor, expf(__ldg(log_std + q))), 1e-6f), 1e-4f), 10.0f);
+        const float m = mu[3 * a + q];
+        const float x = __fadd_rn(m, __fmul_rn(sd, eps[3 * a + q]));
+        const float d = __fsub_rn(x, m);
+        float t = __fdiv_rn(-__fmul_rn(d, d), __fmul_rn(__fmul_rn(2.0f, sd), sd));
+        t = __fsub_rn(__fsub_rn(t, logf(sd)), 0.9189385332046727f);
+        lp = q == 0 ? t : __fadd_rn(lp, t);
+        a_out[3 * a + q] = x;
+    }
+    logp[a] = lp;
+}
+
 }  // namespace uaisa
 
 // ---- C ABI -----------------------------------------------------------------------------------------------------------
@@ -547,6 +570,12 @@ int uaisa_policy_forward(const float *obs, const uint8_t *count, int32_t A, int3
     } else {
         uaisa::uaisa_policy_forward_kernel<1><<<tiles, uaisa::FW_NT, uaisa::FW_SMEM, static_cast<cudaStream_t>(stream)>>>(P);
     }
+    return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+
+int uaisa_policy_sample(const float *mu, const float *eps, const float *log_std, float std_factor, int32_t A, float *a_out, float *logp, void *stream) {
+    if (!mu || !eps || !log_std || !a_out || !logp || A < 1) return -1;
+    uaisa::uaisa_policy_sample_kernel<<<(A + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(mu, eps, log_std, std_factor, A, a_out, logp);
     return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 

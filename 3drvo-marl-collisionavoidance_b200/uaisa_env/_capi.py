@@ -13,7 +13,7 @@ SYMBOLS = (
     "uaisa_set_scenarios", "uaisa_step", "uaisa_reset", "uaisa_observe", "uaisa_autoreset", "uaisa_rollout",
     "uaisa_get_state", "uaisa_set_state", "uaisa_cal_des", "uaisa_indicators", "uaisa_get_counters",
     "uaisa_launch_count", "uaisa_step_host", "uaisa_get_region_clocks", "uaisa_action_transform", "uaisa_gae", "uaisa_step_host_sparse", "uaisa_policy_features", "uaisa_policy_heads",
-    "uaisa_opt_partials_len", "uaisa_opt_prepare", "uaisa_clip_adam", "uaisa_rvo_select", "uaisa_reader_fwd", "uaisa_reader_bwd", "uaisa_policy_pack_floats", "uaisa_policy_pack", "uaisa_policy_forward",
+    "uaisa_opt_partials_len", "uaisa_opt_prepare", "uaisa_clip_adam", "uaisa_rvo_select", "uaisa_reader_fwd", "uaisa_reader_bwd", "uaisa_policy_pack_floats", "uaisa_policy_pack", "uaisa_policy_forward", "uaisa_policy_sample",
     "uaisa_mlp_gemm", "uaisa_mlp_out_bwd", "uaisa_colsum", "uaisa_step_autoreset",
     "uaisa_ppo_wsum", "uaisa_ppo_pi_loss", "uaisa_ppo_v_loss",
 )
@@ -86,6 +86,7 @@ def lib():
         L.uaisa_policy_pack_floats.restype = C.c_int
         L.uaisa_policy_pack.argtypes = [vp, vp, vp]
         L.uaisa_policy_forward.argtypes = [vp, vp, i32, i32, vp, vp, vp, vp, vp, vp, vp]
+        L.uaisa_policy_sample.argtypes = [vp, vp, vp, C.c_float, i32, vp, vp, vp]
         L.uaisa_mlp_gemm.argtypes = [vp, i32, i32, vp, i32, i32, vp, i32, i32, i32, i32, i32, i32, vp, vp, i32, vp, vp, vp, i32, vp]
         L.uaisa_step_autoreset.argtypes = [vp] * 9 + [i32, i32, vp, vp, vp]
         f32 = C.c_float

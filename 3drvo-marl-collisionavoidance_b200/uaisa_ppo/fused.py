@@ -84,8 +84,8 @@ class FusedPolicy:
 
     # ---- kernel = "full" ---------------------------------------------------------------------------------------------------------------
     @torch.no_grad()
-    def forward(self, obs: torch.Tensor, count: torch.Tensor, want_features: bool = False):
-        """-> (mu [A,3], v [A], LayerNorm features [A,268] or None)"""
+    def forward(self, obs: torch.Tensor, count: torch.Tensor, want_features: bool = False, out_v: torch.Tensor = None):
+        """-> (mu [A,3], v [A], LayerNorm features [A,268] or None); `out_v` (contiguous fp32 [A]): where the critic's values are written."""
         A = obs.shape[0]
         if obs.dtype != torch.float32 or not obs.is_contiguous() or count.dtype != torch.uint8 or count.numel() != A:
             raise ValueError("obs must be contiguous float32 [A, 12+9nm] and count uint8 [A]")
@@ -93,13 +93,35 @@ class FusedPolicy:
         if self._scratch is None or self._scratch.numel() < tiles * 128 * 256:
             self._scratch = torch.empty(tiles * 128 * 256, dtype=torch.float32, device=self.dev)
         mu = torch.empty((A, 3), dtype=torch.float32, device=self.dev)
-        v = torch.empty(A, dtype=torch.float32, device=self.dev)
+        v = self._out(out_v, (A,)) if out_v is not None else torch.empty(A, dtype=torch.float32, device=self.dev)
         feat = torch.empty((A, 268), dtype=torch.float32, device=self.dev) if want_features else None
         p = lambda t: None if t is None else C.c_void_p(t.data_ptr())  # noqa: E731
         rc = self.L.uaisa_policy_forward(p(obs), p(count), A, obs.shape[1], p(self.wpack), p(mu), p(v), p(feat), p(self._scratch), p(self.stats), self._stream())
         if rc:
             raise _capi.UaisaError("uaisa_policy_forward failed (%d)" % rc)
         return mu, v, feat
+
+    def _out(self, t, shape):
+        if t.dtype != torch.float32 or not t.is_contiguous() or tuple(t.shape) != tuple(shape) or t.device != self.dev:
+            raise ValueError("output buffer must be contiguous float32 %r on %s" % (tuple(shape), self.dev))
+        return t
+
+    @torch.no_grad()
+    def sample(self, mu: torch.Tensor, std_factor: float = 1.0, out_logp: torch.Tensor = None, eps: torch.Tensor = None):
+        """a = mu + std eps and its log-probability (policy_rnn_ac.py:57-69) in one launch (uaisa_policy_sample) -> (a [A,3], logp [A])."""
+        A = mu.shape[0]
+        if eps is None:
+            eps = torch.randn_like(mu)
+        a = torch.empty_like(mu)
+        logp = self._out(out_logp, (A,)) if out_logp is not None else torch.empty(A, dtype=torch.float32, device=self.dev)
+        p = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
+        ls = self.ac.pi.log_std
+        if ls.dtype != torch.float32 or not ls.is_contiguous() or ls.numel() != 3:
+            raise ValueError("log_std must be contiguous float32 [3]")
+        rc = self.L.uaisa_policy_sample(p(mu), p(eps), p(ls), float(std_factor), A, p(a), p(logp), self._stream())
+        if rc:
+            raise _capi.UaisaError("uaisa_policy_sample failed (%d)" % rc)
+        return a, logp
 
     # ---- kernel = "split" --------------------------------------------------------------------------------------------------------------
     @torch.no_grad()
@@ -144,13 +166,19 @@ class FusedPolicy:
 
     # -----------------------------------------------------------------------------------------------------------------------------------
     @torch.no_grad()
-    def step(self, obs, count, std_factor=1.0, multi_cap=0):
-        """Drop-in for rnn_ac.step: (a, v, logp).  (`multi_cap` only matters for kernel = "split".)"""
+    def step(self, obs, count, std_factor=1.0, multi_cap=0, out_v=None, out_logp=None):
+        """Drop-in for rnn_ac.step: (a, v, logp).  (`multi_cap` only matters for kernel = "split"; `out_v` / `out_logp`: rollout-buffer rows the values and
+        log-probabilities are written into directly.)"""
         if self.kernel == "full":
-            mu, v, _ = self.forward(obs, count)
-        else:
-            mu, v = self._split_mu_v(obs, count, multi_cap)
+            mu, v, _ = self.forward(obs, count, out_v=out_v)
+            a, logp = self.sample(mu, std_factor, out_logp=out_logp)
+            return a, v, logp
+        mu, v = self._split_mu_v(obs, count, multi_cap)
         std = torch.clamp(std_factor * torch.exp(self.ac.pi.log_std) + 1e-6, min=1e-4, max=10.0)
         a = mu + std * torch.randn_like(mu)
         logp = (-((a - mu) ** 2) / (2 * std * std) - torch.log(std) - 0.9189385332046727).sum(-1)
+        if out_v is not None:
+            out_v.copy_(v); v = out_v
+        if out_logp is not None:
+            out_logp.copy_(logp); logp = out_logp
         return a, v, logp

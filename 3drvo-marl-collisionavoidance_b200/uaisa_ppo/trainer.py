@@ -208,13 +208,12 @@ class PPOTrainer:
         wrote it (buf[obs][t]), the env kernel writes reward / path cut into buf[..][t] and the next observation into buf[obs][t+1] -- no copies
         of the big tensors.  The last step (full reset, multi_ppo.py:244-264) leaves the next epoch's first observation in the env's own buffers."""
         env, cfg, b = self.env, self.cfg, self.buf
-        a_inc, v, logp = self.fused.step(b["obs"][t], b["count"][t], cfg.std_factor)                                # :196
+        a_inc, _, _ = self.fused.step(b["obs"][t], b["count"][t], cfg.std_factor, out_v=b["val"][t], out_logp=b["logp"][t])   # :196; values and log-probabilities land in the buffer
         env.action_transform(a_inc, self.action, b["act"][t])                                                      # :197-208
         out = {"reward": b["rew"][t], "path_cut": b["cut"][t]}
         if not last:
             out["obs"] = b["obs"][t + 1]; out["count"] = b["count"][t + 1]
         env.step_autoreset(self.action, max_ep_len=cfg.max_ep_len, epoch_ended=last, out=out)                      # :210 + :226-281
-        b["val"][t].copy_(v); b["logp"][t].copy_(logp)
         self._ndone += env.done.sum()
 
     @torch.no_grad()

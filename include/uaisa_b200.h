@@ -193,6 +193,10 @@ int uaisa_policy_pack_floats(void);
 int uaisa_policy_pack(const float *const *params, float *wpack, void *stream);
 int uaisa_policy_forward(const float *obs, const uint8_t *count, int32_t A, int32_t obs_dim, const float *wpack, float *mu, float *v, float *feat_out,
                          void *scratch, int32_t *stats, void *stream);
+/* uaisa_policy_sample: the sampling half of rnn_ac.step (train/policy/policy_rnn_ac.py:57-69; GaussianActor._distribution :206-228): std = clamp(std_factor
+ *   exp(log_std[3]) + 1e-6, 1e-4, 10), a_out[A][3] = mu + std eps, logp[A] = sum_q(-(a - mu)^2 / (2 std^2) - log std - log sqrt(2 pi)), in one launch and in
+ *   the operation order of the torch expression.  eps[A][3]: standard normal draws from the caller's generator.  All DEVICE pointers. */
+int uaisa_policy_sample(const float *mu, const float *eps, const float *log_std, float std_factor, int32_t A, float *a_out, float *logp, void *stream);
 
 /* ---- optimiser epilogue of the PPO update (train/policy/multi_ppo.py:355-376; SURVEY.md section 5 "fused grad-norm + clip + Adam") -----------
  * Parameters, gradients and Adam moments are FLAT fp32 DEVICE buckets.  One update iteration ends with

@@ -31,13 +31,14 @@ def batch(kind):
     obs[:, 12:] = (rows * mask).reshape(A, 90)
     return obs, cnt
 with torch.no_grad():
-    for kind in ("sparse", "mixed", "dense"):
+    for kind in os.environ.get("KINDS", "sparse,mixed,dense").split(","):
         obs, cnt = batch(kind)
         mean_rows = float(cnt.float().clamp(min=1).mean()); lmax_tile = float(cnt.view(-1, 128).max(dim=1).values.float().clamp(min=1).mean())
         print("---- %s: A=%d, mean steps per agent %.2f, mean steps per 128-agent tile %.2f" % (kind, A, mean_rows, lmax_tile))
         torch.backends.cuda.matmul.allow_tf32 = False
-        print("torch module step (fp32 cuBLAS):          %.3f ms" % timeit(lambda: m.step(obs, cnt, 1.0, multi_cap=0), 5))
-        if kind == "sparse":
+        if not os.environ.get("FUSED_ONLY"):
+            print("torch module step (fp32 cuBLAS):          %.3f ms" % timeit(lambda: m.step(obs, cnt, 1.0, multi_cap=0), 5))
+        if kind == "sparse" and not os.environ.get("FUSED_ONLY"):
             print("split kernels K6a + K6b + torch patch:    %.3f ms" % timeit(lambda: fs.step(obs, cnt, 1.0, multi_cap=0), 10))
         t = timeit(lambda: ff.forward(obs, cnt))
         # tensor-core flops actually issued: per tile, GRU x-part 2 dirs x L x 4 slices x (128x192x16), h-part (L-1) x 2 x 4 x (128x192x256), heads 128 x (2 x 272 x 256 + 2 x 256 x 256)

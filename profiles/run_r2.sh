@@ -25,6 +25,8 @@ case $what in
     timeout 400 python -m pytest tests/test_multirank_gpu.py -m gpu -q --timeout 300 > gpurun_out/r2/tests_mr2.txt 2>&1; echo "mr2 rc=$?" | tee -a gpurun_out/r2/tests_mr2.txt; tail -20 gpurun_out/r2/tests_mr2.txt | cut -c1-300 ;;
   ptime)
     timeout 300 python profiles/policy_timing.py 262144 > gpurun_out/r2/policy_timing.txt 2>&1; cat gpurun_out/r2/policy_timing.txt | cut -c1-200 ;;
+  ptime_ab)  # serial (UAISA_POLICY_PIPE=0) against pipelined forward
+    for pp in ${PIPES:-0 7}; do echo "== UAISA_POLICY_PIPE=$pp"; FUSED_ONLY=1 UAISA_POLICY_PIPE=$pp timeout 200 python profiles/policy_timing.py 262144 2>&1 | grep -E "^----|fused" | cut -c1-200; done | tee gpurun_out/r2/policy_timing_ab.txt ;;
   ncu_policy)   # launch list + one full capture of the fused policy forward (sparse and mixed batches)
     for kind in sparse mixed; do
       timeout 200 python profiles/prof_policy.py $kind > gpurun_out/r2/prof_policy_$kind.log 2>&1 && \

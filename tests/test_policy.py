@@ -176,3 +176,37 @@ def test_full_forward_kernel_matches_torch_for_every_row_count(nm):
         dist2, ref_v2, _ = m.evaluate(o, c)
     mu2, v2, _ = fp.forward(o, c)
     assert (mu2 - dist2.mean).abs().max().item() < 1e-2 and (v2 - ref_v2).abs().max().item() < 1e-2 * max(1.0, float(ref_v2.abs().max()))
+
+
+@pytest.mark.gpu
+def test_sample_kernel_equals_the_torch_expression():
+    """uaisa_policy_sample (one launch) against the element-wise torch expression of rnn_ac.step it replaces (policy_rnn_ac.py:57-69): the same
+    draws give the same actions bit for bit and log-probabilities within one fp32 rounding of the 3-term sum; values / log-probabilities land in
+    the caller's buffers."""
+    from uaisa_ppo.fused import FusedPolicy
+
+    m = _model("cuda")
+    fp = FusedPolicy(m, "cuda")
+    g = torch.Generator(device="cuda"); g.manual_seed(5)
+    for A, sf, ls in ((1, 1.0, (-1.0, -1.0, -1.0)), (1000, 0.7, (-1.0, 0.3, -2.5)), (70001, 1.0, (-30.0, 5.0, 0.0))):     # the last one hits both clamps
+        with torch.no_grad():
+            m.pi.log_std.copy_(torch.tensor(ls, device="cuda"))
+        mu = torch.tanh(torch.randn((A, 3), device="cuda", generator=g))
+        eps = torch.randn((A, 3), device="cuda", generator=g)
+        out_lp = torch.full((A,), 7.0, device="cuda")
+        a, logp = fp.sample(mu, sf, out_logp=out_lp, eps=eps)
+        std = torch.clamp(sf * torch.exp(m.pi.log_std) + 1e-6, min=1e-4, max=10.0)
+        a_ref = mu + std * eps
+        lp_ref = (-((a_ref - mu) ** 2) / (2 * std * std) - torch.log(std) - 0.9189385332046727).sum(-1)
+        assert logp.data_ptr() == out_lp.data_ptr()
+        assert torch.equal(a, a_ref), (A, (a - a_ref).abs().max())
+        assert (logp - lp_ref).abs().max().item() <= 2e-6 * max(1.0, float(lp_ref.abs().max())), (A, (logp - lp_ref).abs().max())
+    # step(): values and log-probabilities written straight into rollout-buffer rows
+    D = 12 + 9 * 3
+    obs = torch.zeros((300, D), device="cuda"); obs[:, :12] = torch.randn((300, 12), device="cuda", generator=g)
+    cnt = torch.zeros(300, dtype=torch.uint8, device="cuda")
+    buf_v, buf_lp = torch.zeros((2, 300), device="cuda"), torch.zeros((2, 300), device="cuda")
+    a, v, logp = fp.step(obs, cnt, 1.0, out_v=buf_v[1], out_logp=buf_lp[1])
+    mu, v_ref, _ = fp.forward(obs, cnt)
+    assert v.data_ptr() == buf_v[1].data_ptr() and torch.equal(buf_v[1], v_ref) and float(buf_v[0].abs().max()) == 0.0
+    assert torch.isfinite(buf_lp[1]).all() and float(buf_lp[1].abs().max()) > 0 and float(buf_lp[0].abs().max()) == 0.0

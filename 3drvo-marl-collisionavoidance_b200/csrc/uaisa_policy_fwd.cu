@@ -100,6 +100,9 @@ struct FwdParams {
     float *feat_out;              // optional [A][268] LayerNorm output in the module's [self | h] order (tests)
     float4 *scratch;              // [ceil(A/128)][64][128] float4: forward-direction state of CTAs that run the recurrence
     int *stats;                   // optional: [0] += CTAs that ran the recurrence, [1] = max steps seen
+#ifdef UAISA_FWD_DBG
+    int dbg;                      // timing experiments (results are WRONG): 1 = no weight copies after the first two, 2 = no MMAs, 4 = no element-wise epilogue math
+#endif
 };
 
 // order in which the weight tiles are consumed (thread 0's prefetcher walks it independently of the consumer)
@@ -150,7 +153,8 @@ __global__ void __launch_bounds__(FW_NT, 1) uaisa_policy_forward_kernel(const __
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 5);
     int *s_lmax = reinterpret_cast<int *>(tmem_slot + 1);
     float *s_red = reinterpret_cast<float *>(bars + 8);                 // [FW_S][128][4] partial sums of the row reductions (LayerNorm, output layer)
-    const int tid = threadIdx.x, warp = tid >> 5, row = tid & (FW_M - 1), sub = tid >> 7;
+    const int tid = threadIdx.x, lane = tid & 31, row = tid & (FW_M - 1), sub = tid >> 7;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);            // (provably warp-uniform: the issuer block below stays on the uniform datapath)
     const int a0 = blockIdx.x * FW_M, a = a0 + row;
     const bool ok = a < P.A;
     const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[2]), done = smem_u32(&bars[4]);
@@ -184,26 +188,34 @@ __global__ void __launch_bounds__(FW_NT, 1) uaisa_policy_forward_kernel(const __
     __syncthreads();
     fence_after_sync();
     if (CL > 1) cluster_sync();                        // the peers' barriers are initialised before anything is multicast to them
-    const uint32_t tmem = *tmem_slot;
-    const int lmax = *s_lmax;
+    const uint32_t tmem = __shfl_sync(0xffffffffu, *tmem_slot, 0);      // (warp-uniform values, provably)
+    const int lmax = __shfl_sync(0xffffffffu, *s_lmax, 0);
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;      // a warp reaches the TMEM lane quarter (warp id % 4)
     const float *orow = P.obs + (size_t)(ok ? a : 0) * P.obs_dim;
     const float *wp = P.wp;
     uint32_t dpar = 0;                                 // parity of the `done` barrier (all threads)
-    // ---- thread 0: weight-tile ring
+    // ---- warp 0: weight-tile ring and MMA issue.  The WHOLE warp runs this code (warp-uniform control flow and state, so ring indices, parities and the
+    // matrix descriptors live on the uniform datapath); lane 0 alone executes the instructions with side effects (expect_tx, bulk copy, tcgen05.mma / commit).
+    // With `if (tid == 0)` around everything the compiler kept the state in vector registers and local memory and moved five registers into uniform ones for
+    // every MMA: 6 800 single-thread instructions per tile, half of warp 0's time -- and every other warp waits for it (profiles/r2/policy_dbg.txt).
     TileIter it; it.init(lmax);
-    int pf = 0, cs = 0; uint32_t fpar[2] = {0u, 0u}, epar[2] = {0u, 0u};
+    int pf = 0, cs = 0; uint32_t fmask = 0u, emask = 0u;               // tiles requested / consumed; parity bit per stage of the full / empty barriers
     auto topup = [&]() {
         while (pf < cs + 2) {
             const float *addr; uint32_t bytes;
             if (!it.next(wp, addr, bytes)) break;
             const int s = pf & 1;
-            if (pf >= 2) { mbar_wait(empty0 + 8 * s, epar[s]); epar[s] ^= 1u; }      // the MMAs that read this stage have completed
-            mbar_expect_tx(full0 + 8 * s, bytes);
-            if (CL == 1) bulk_g2s(smem_u32(Bs + s * FW_STAGE), addr, bytes, full0 + 8 * s);
-            else {                                     // my 1/CL of the tile, into every CTA of the cluster
-                const uint32_t part = bytes / CL;
-                bulk_g2s_multicast(smem_u32(Bs + s * FW_STAGE) + crank * part, reinterpret_cast<const char *>(addr) + crank * part, part, full0 + 8 * s, CMASK);
+            if (pf >= 2) { mbar_wait(empty0 + 8 * s, (emask >> s) & 1u); emask ^= 1u << s; }      // the MMAs that read this stage have completed
+#ifdef UAISA_FWD_DBG
+            if ((P.dbg & 1) && pf >= 2) { pf++; continue; }
+#endif
+            if (lane == 0) {
+                mbar_expect_tx(full0 + 8 * s, bytes);
+                if (CL == 1) bulk_g2s(smem_u32(Bs + s * FW_STAGE), addr, bytes, full0 + 8 * s);
+                else {                                 // my 1/CL of the tile, into every CTA of the cluster
+                    const uint32_t part = bytes / CL;
+                    bulk_g2s_multicast(smem_u32(Bs + s * FW_STAGE) + crank * part, reinterpret_cast<const char *>(addr) + crank * part, part, full0 + 8 * s, CMASK);
+                }
             }
             pf++;
         }
@@ -211,17 +223,30 @@ __global__ void __launch_bounds__(FW_NT, 1) uaisa_policy_forward_kernel(const __
     auto acquire = [&]() -> int {
         topup();
         const int s = cs & 1;
-        mbar_wait(full0 + 8 * s, fpar[s]); fpar[s] ^= 1u;
+#ifdef UAISA_FWD_DBG
+        if ((P.dbg & 1) && cs >= 2) return s;
+#endif
+        mbar_wait(full0 + 8 * s, (fmask >> s) & 1u); fmask ^= 1u << s;
         fence_after_sync();
         return s;
     };
-    auto release = [&](int s) { if (CL == 1) umma_commit(empty0 + 8 * s); else umma_commit_multicast(empty0 + 8 * s, CMASK); cs++; };
-    auto mma = [&](int a_chunk, uint32_t b_saddr, int ksteps, uint32_t idesc, uint32_t tmem_d, bool acc) {
-        const uint32_t sa = smem_u32(As + a_chunk * FW_A_CHUNK);
-        for (int k = 0; k < ksteps; k++) umma_tf32(tmem_d, umma_desc(sa + k * 32), umma_desc(b_saddr + k * 32), idesc, (acc || k > 0) ? 1u : 0u);   // UMMA K = 8 tf32 = 32 bytes
+    auto release = [&](int s) {
+        if (lane == 0) { if (CL == 1) umma_commit(empty0 + 8 * s); else umma_commit_multicast(empty0 + 8 * s, CMASK); }
+        cs++;
     };
-    auto group_done = [&]() { umma_commit(done); topup(); };               // (thread 0) accumulators ready -> `done`; next tiles stream during the epilogue
-    auto wait_done = [&]() { mbar_wait(done, dpar); dpar ^= 1u; __syncwarp(); fence_after_sync(); };   // (warp 0 reconverges after thread 0's issue block: tcgen05.ld / st are .aligned)
+    auto mma = [&](int a_chunk, uint32_t b_saddr, int ksteps, uint32_t idesc, uint32_t tmem_d, bool acc) {
+        const uint64_t da = umma_desc(smem_u32(As + a_chunk * FW_A_CHUNK)), db = umma_desc(b_saddr);
+#ifdef UAISA_FWD_DBG
+        if (P.dbg & 2) return;
+#endif
+        if (lane == 0) {                               // UMMA K = 8 tf32 = 32 bytes: + 2 in the descriptor's (address >> 4) field per step
+            umma_tf32(tmem_d, da, db, idesc, acc ? 1u : 0u);
+            umma_tf32(tmem_d, da + 2, db + 2, idesc, 1u);
+            if (ksteps == 4) { umma_tf32(tmem_d, da + 4, db + 4, idesc, 1u); umma_tf32(tmem_d, da + 6, db + 6, idesc, 1u); }
+        }
+    };
+    auto group_done = [&]() { if (lane == 0) umma_commit(done); topup(); };   // (warp 0) accumulators ready -> `done`; next tiles stream during the epilogue
+    auto wait_done = [&]() { mbar_wait(done, dpar); dpar ^= 1u; __syncwarp(); fence_after_sync(); };   // (warp 0 reconverges after lane 0's instructions: tcgen05.ld / st are .aligned)
     auto sync_smem_to_mma = [&]() { fence_proxy_async(); fence_before_sync(); __syncthreads(); fence_after_sync(); };
     auto sync_tmem = [&]() { fence_before_sync(); __syncthreads(); fence_after_sync(); };
     constexpr uint32_t ID192 = umma_idesc_tf32(128, 192), ID128 = umma_idesc_tf32(128, 128), ID64 = umma_idesc_tf32(128, 64), ID256 = umma_idesc_tf32(128, 256);
@@ -247,6 +272,9 @@ __global__ void __launch_bounds__(FW_NT, 1) uaisa_policy_forward_kernel(const __
     // gates of 16 hidden units [u0, u0+16) of direction `dir` from the accumulator columns at `dcol`: out = (1 - z) n + z h_old
     auto gates16 = [&](int dir, int u0, uint32_t dcol, int jb, bool has_h, const float *h_old, float *out) {
         float r[16], z[16], gi[16], gh[16], b[16];
+#ifdef UAISA_FWD_DBG
+        if (P.dbg & 4) { for (int q = 0; q < 16; q++) out[q] = 0.25f; return; }
+#endif
         const float *gb = wp + FW_OFF_GB + dir * 1024 + u0;
         tmem_ld16(tmem + lane_base + dcol + jb * 16, r);
         ld16(gb, b);
@@ -300,7 +328,7 @@ __global__ void __launch_bounds__(FW_NT, 1) uaisa_policy_forward_kernel(const __
         write_x(0, true);
         sync_smem_to_mma();
         for (int slice = 0; slice < 4; slice++) {
-            if (tid == 0) {
+            if (warp == 0) {
                 int s = acquire(); mma(8, smem_u32(Bs + s * FW_STAGE), 2, ID192, tmem + 0, false); release(s);
                 s = acquire(); mma(8, smem_u32(Bs + s * FW_STAGE), 2, ID192, tmem + 256, false); release(s);
                 group_done();
@@ -331,7 +359,7 @@ __global__ void __launch_bounds__(FW_NT, 1) uaisa_policy_forward_kernel(const __
                 }
                 sync_smem_to_mma();
                 for (int slice = 0; slice < 4; slice++) {
-                    if (tid == 0) {
+                    if (warp == 0) {
                         int s = acquire(); mma(8, smem_u32(Bs + s * FW_STAGE), 2, ID192, tmem + 0, false); release(s);           // x_t W_i^T -> [r | z | i_n]
                         if (step > 0) {
                             for (int c = 0; c < 8; c++) {                                                                         // h W_h^T
@@ -384,6 +412,9 @@ __global__ void __launch_bounds__(FW_NT, 1) uaisa_policy_forward_kernel(const __
     }
 
     // =========================================================================================== concat + LayerNorm(268), in place in the A tile
+#ifdef UAISA_FWD_DBG
+    if (!(P.dbg & 8))
+#endif
     {
         float self[FW_SELF];
 #pragma unroll
@@ -436,7 +467,7 @@ __global__ void __launch_bounds__(FW_NT, 1) uaisa_policy_forward_kernel(const __
     sync_smem_to_mma();
 
     // =========================================================================================== actor / critic heads
-    if (tid == 0) {                                    // layer 1 of both heads from the same A (features): columns 0..255 actor, 256..511 critic
+    if (warp == 0) {                                   // layer 1 of both heads from the same A (features): columns 0..255 actor, 256..511 critic
         for (int c = 0; c < 9; c++) {
             const int ks = c < 8 ? 4 : 2;              // chunk 8 holds the 12 self values: K = 16 covers them
             int s = acquire(); mma(c, smem_u32(Bs + s * FW_STAGE), ks, ID256, tmem + 0, c > 0); release(s);
@@ -450,13 +481,16 @@ __global__ void __launch_bounds__(FW_NT, 1) uaisa_policy_forward_kernel(const __
         const float *b1 = wp + FW_OFF_B1 + head * 256;
 #pragma unroll 1
         for (int ub = sub; ub < 16; ub += FW_S) {
+#ifdef UAISA_FWD_DBG
+            if (P.dbg & 16) break;
+#endif
             float h[16], b[16]; tmem_ld16(tmem + lane_base + (head ? 256 : 0) + ub * 16, h); ld16(b1 + ub * 16, b);
 #pragma unroll
             for (int q = 0; q < 16; q++) h[q] = fmaxf(h[q] + b[q], 0.0f);
             write_h16(ub * 16, h);
         }
         sync_smem_to_mma();
-        if (tid == 0) {                                // layer 2 -> columns 0..255 (the critic's layer-1 accumulator still sits in 256..511)
+        if (warp == 0) {                               // layer 2 -> columns 0..255 (the critic's layer-1 accumulator still sits in 256..511)
             for (int c = 0; c < 8; c++) { const int s = acquire(); mma(c, smem_u32(Bs + s * FW_STAGE), 4, ID256, tmem + 0, c > 0); release(s); }
             group_done();
         }
@@ -466,6 +500,9 @@ __global__ void __launch_bounds__(FW_NT, 1) uaisa_policy_forward_kernel(const __
         float acc[3] = {0.f, 0.f, 0.f};
 #pragma unroll 1
         for (int ub = sub; ub < 16; ub += FW_S) {
+#ifdef UAISA_FWD_DBG
+            if (P.dbg & 16) break;
+#endif
             float h[16], b[16], w[16]; tmem_ld16(tmem + lane_base + ub * 16, h); ld16(b2 + ub * 16, b);
 #pragma unroll
             for (int q = 0; q < 16; q++) h[q] = fmaxf(h[q] + b[q], 0.0f);
@@ -558,6 +595,9 @@ int uaisa_policy_forward(const float *obs, const uint8_t *count, int32_t A, int3
     }
     uaisa::FwdParams P{};
     P.obs = obs; P.count = count; P.A = A; P.obs_dim = obs_dim; P.nm = (obs_dim - uaisa::FW_SELF) / uaisa::FW_IN;
+#ifdef UAISA_FWD_DBG
+    P.dbg = std::getenv("UAISA_FWD_DBG") ? std::atoi(std::getenv("UAISA_FWD_DBG")) : 0;
+#endif
     P.wp = wpack; P.mu = mu; P.v = v; P.feat_out = feat_out; P.scratch = static_cast<float4 *>(scratch); P.stats = stats;
     const int tiles = (A + uaisa::FW_M - 1) / uaisa::FW_M;
     if (cl == 2) {

@@ -119,7 +119,8 @@ __global__ void __launch_bounds__(GM_T, NT <= 256 ? 2 : 1) uaisa_mlp_gemm_kernel
     float *s_y = reinterpret_cast<float *>(Bs + 2 * B_STAGE);                  // [128][4] partial output-layer sums of the upper column half
     uint64_t *bars = reinterpret_cast<uint64_t *>(s_y + 128 * 4);
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);                   // (provably warp-uniform: the MMA issue below stays on the uniform datapath)
     const int m0 = blockIdx.x * GM_M;
     const int kb = blockIdx.y * P.k_per_split, Kend = min(P.K, kb + P.k_per_split);
     const int nch = (Kend - kb + 31) >> 5;
@@ -132,7 +133,7 @@ __global__ void __launch_bounds__(GM_T, NT <= 256 ? 2 : 1) uaisa_mlp_gemm_kernel
     fence_before_sync();
     __syncthreads();
     fence_after_sync();
-    const uint32_t tmem = *tmem_slot;
+    const uint32_t tmem = __shfl_sync(0xffffffffu, *tmem_slot, 0);
     const uint32_t empty0 = smem_u32(&bars[0]);
     constexpr uint32_t IDESC_MAIN = umma_idesc_tf32(GM_M, NT <= 256 ? NT : 256), IDESC_TAIL = umma_idesc_tf32(GM_M, NT > 256 ? NT - 256 : 8);
 
@@ -152,15 +153,18 @@ __global__ void __launch_bounds__(GM_T, NT <= 256 ? 2 : 1) uaisa_mlp_gemm_kernel
         fence_proxy_async();
         fence_before_sync();
         __syncthreads();
-        if (tid == 0) {
+        if (warp == 0) {                                                       // warp-uniform descriptors; lane 0 issues (uaisa_policy_fwd.cu: the same change there was 14-19 %)
             fence_after_sync();
-            const uint32_t sa = smem_u32(As + s * GM_A_STAGE), sb = smem_u32(Bs + s * B_STAGE);
+            const uint32_t sa = __shfl_sync(0xffffffffu, smem_u32(As + s * GM_A_STAGE), 0), sb = __shfl_sync(0xffffffffu, smem_u32(Bs + s * B_STAGE), 0);
+            const uint64_t da = umma_desc(sa), db = umma_desc(sb), dt = umma_desc(sb + 256 * 128);
+            if (lane == 0) {
 #pragma unroll
-            for (int k = 0; k < 4; k++) {                                      // UMMA K = 8 tf32 = 32 bytes inside the swizzle row
-                umma_tf32(tmem, umma_desc(sa + k * 32), umma_desc(sb + k * 32), IDESC_MAIN, (c > 0 || k > 0) ? 1u : 0u);
-                if (NT > 256) umma_tf32(tmem + 256, umma_desc(sa + k * 32), umma_desc(sb + 256 * 128 + k * 32), IDESC_TAIL, (c > 0 || k > 0) ? 1u : 0u);
+                for (int k = 0; k < 4; k++) {                                  // UMMA K = 8 tf32 = 32 bytes inside the swizzle row: + 2 in the (address >> 4) field
+                    umma_tf32(tmem, da + 2 * k, db + 2 * k, IDESC_MAIN, (c > 0 || k > 0) ? 1u : 0u);
+                    if (NT > 256) umma_tf32(tmem + 256, da + 2 * k, dt + 2 * k, IDESC_TAIL, (c > 0 || k > 0) ? 1u : 0u);
+                }
+                umma_commit(empty0 + 8 * s);
             }
-            umma_commit(empty0 + 8 * s);
         }
     }
     {   // drain: every issued MMA has completed

@@ -24,6 +24,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <cstdlib>
+
 #include "uaisa_tc.cuh"
 
 namespace uaisa {
@@ -41,6 +43,9 @@ struct GemmParams {
     const float *bias;                  // [N]
     const float *mask; int ldm;         // [M][N]
     const float *W3, *b3; float *Y; int nout;   // EPI_BIAS_RELU_OUT: W3 [nout][N], b3 [nout], Y [M][nout]
+#ifdef UAISA_GEMM_DBG
+    int dbg;                            // timing experiments (results are WRONG): 1 = no operand loads after chunk 0, 2 = no MMAs, 4 = no epilogue loads / stores
+#endif
 };
 
 constexpr int GM_M = 128;               // rows of the CTA tile = TMEM lanes
@@ -147,6 +152,9 @@ __global__ void __launch_bounds__(GM_T, NT <= 256 ? 2 : 1) uaisa_mlp_gemm_kernel
         if (c >= 2) { mbar_wait(empty0 + 8 * s, par[s]); par[s] ^= 1u; }       // the MMAs that read this stage have completed
         la.store(ra, As + s * GM_A_STAGE);
         lb.store(rb, Bs + s * B_STAGE);
+#ifdef UAISA_GEMM_DBG
+        if (!(P.dbg & 1))
+#endif
         if (c + 1 < nch) {                                                     // next chunk's loads fly while this one is multiplied
             la.load(ra, c + 1, Kend - kb - 32 * (c + 1), tid); lb.load(rb, c + 1, Kend - kb - 32 * (c + 1), tid);
         }
@@ -158,6 +166,9 @@ __global__ void __launch_bounds__(GM_T, NT <= 256 ? 2 : 1) uaisa_mlp_gemm_kernel
             const uint32_t sa = __shfl_sync(0xffffffffu, smem_u32(As + s * GM_A_STAGE), 0), sb = __shfl_sync(0xffffffffu, smem_u32(Bs + s * B_STAGE), 0);
             const uint64_t da = umma_desc(sa), db = umma_desc(sb), dt = umma_desc(sb + 256 * 128);
             if (lane == 0) {
+#ifdef UAISA_GEMM_DBG
+                if (!(P.dbg & 2))
+#endif
 #pragma unroll
                 for (int k = 0; k < 4; k++) {                                  // UMMA K = 8 tf32 = 32 bytes inside the swizzle row: + 2 in the (address >> 4) field
                     umma_tf32(tmem, da + 2 * k, db + 2 * k, IDESC_MAIN, (c > 0 || k > 0) ? 1u : 0u);
@@ -177,65 +188,20 @@ __global__ void __launch_bounds__(GM_T, NT <= 256 ? 2 : 1) uaisa_mlp_gemm_kernel
     // ---- epilogue: warp w reads TMEM lanes 32 (w % 4) .. +31; warps w and w + 4 split the columns ---------------------------------------
     const int q = warp & 3, half = warp >> 2, row = q * 32 + lane, m = m0 + row;
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
-    constexpr int HC = NT / 2;                                                 // columns per half: 128 or 144 (multiples of 16)
     const bool mok = m < P.M;
     const bool vecC = ((reinterpret_cast<uintptr_t>(P.C) & 15) == 0) && (P.ldc & 3) == 0;
     const bool vecM = P.mask && ((reinterpret_cast<uintptr_t>(P.mask) & 15) == 0) && (P.ldm & 3) == 0;
     float yacc[3] = {0.f, 0.f, 0.f};
-    // EPI_MASK: the saved activations of the NEXT 16 columns are fetched while the current ones are processed (23 % of the kernel's stall samples
-    // sat on these loads when they were issued at their use, profiles/r2/ncu_mlp_gemm.txt)
-    float4 hm[4];
-    const bool mvec = P.epi == EPI_MASK && mok && vecM;
-    auto fetch_mask = [&](int n0_) {
-        if (mvec && n0_ + 15 < P.N) {
-            const float4 *mp4 = reinterpret_cast<const float4 *>(P.mask + (size_t)m * P.ldm + n0_);
-#pragma unroll
-            for (int i4 = 0; i4 < 4; i4++) hm[i4] = __ldg(mp4 + i4);
-        }
-    };
-    fetch_mask(half * HC);
+    if (P.epi == EPI_ATOMIC) {                 // split-K: the partial tile is added straight from the registers (small outputs: the weight gradients)
+        constexpr int HC = NT / 2;             // columns per half: 128 or 144 (multiples of 16)
 #pragma unroll 1
-    for (int cb = 0; cb < HC; cb += 16) {
-        const int n0 = half * HC + cb;
-        float v[16];
-        __syncwarp();                                                          // tcgen05.ld is warp-collective: reconverge after the per-row branches below
-        tmem_ld16(tmem + lane_base + n0, v);                                   // (all lanes of the warp take part, also rows beyond M)
-        if (n0 >= P.N) continue;                                               // (warp-uniform)
-        if (P.epi == EPI_BIAS_RELU || P.epi == EPI_BIAS_RELU_OUT) {
-#pragma unroll
-            for (int i = 0; i < 16; i++) v[i] = (n0 + i < P.N) ? fmaxf(v[i] + __ldg(P.bias + n0 + i), 0.f) : 0.f;
-            if (P.epi == EPI_BIAS_RELU_OUT) {
-#pragma unroll
-                for (int i = 0; i < 16; i++) {
-                    if (n0 + i < P.N) {
-#pragma unroll
-                        for (int o = 0; o < 3; o++) if (o < P.nout) yacc[o] = fmaf(v[i], __ldg(P.W3 + (size_t)o * P.N + n0 + i), yacc[o]);
-                    }
-                }
-            }
-        } else if (P.epi == EPI_MASK) {
-            if (mok) {
-                const float *mp = P.mask + (size_t)m * P.ldm + n0;
-                if (vecM && n0 + 15 < P.N) {
-                    float4 hc[4];
-#pragma unroll
-                    for (int i4 = 0; i4 < 4; i4++) hc[i4] = hm[i4];
-                    if (cb + 16 < HC) fetch_mask(n0 + 16);
-#pragma unroll
-                    for (int i4 = 0; i4 < 4; i4++) {
-                        const float4 h = hc[i4];
-                        v[4 * i4] = h.x > 0.f ? v[4 * i4] : 0.f; v[4 * i4 + 1] = h.y > 0.f ? v[4 * i4 + 1] : 0.f;
-                        v[4 * i4 + 2] = h.z > 0.f ? v[4 * i4 + 2] : 0.f; v[4 * i4 + 3] = h.w > 0.f ? v[4 * i4 + 3] : 0.f;
-                    }
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 16; i++) if (n0 + i < P.N) v[i] = __ldg(mp + i) > 0.f ? v[i] : 0.f;
-                }
-            }
-        }
-        float *cp = P.C + (size_t)m * P.ldc + n0;
-        if (!mok) {
-        } else if (P.epi == EPI_ATOMIC) {
+        for (int cb = 0; cb < HC; cb += 16) {
+            const int n0 = half * HC + cb;
+            float v[16];
+            __syncwarp();                      // tcgen05.ld is warp-collective: reconverge after the per-row branches below
+            tmem_ld16(tmem + lane_base + n0, v);
+            if (n0 >= P.N || !mok) continue;
+            float *cp = P.C + (size_t)m * P.ldc + n0;
             if (vecC && n0 + 15 < P.N) {
 #pragma unroll
                 for (int i4 = 0; i4 < 4; i4++)
@@ -244,14 +210,72 @@ __global__ void __launch_bounds__(GM_T, NT <= 256 ? 2 : 1) uaisa_mlp_gemm_kernel
 #pragma unroll
                 for (int i = 0; i < 16; i++) if (n0 + i < P.N) atomicAdd(cp + i, v[i]);
             }
-        } else if (P.C) {
-            if (vecC && n0 + 15 < P.N) {
+        }
+    } else {
+        // The tile leaves through shared memory (the operand stages are free once the MMAs have drained), 128 columns per pass: a thread owns one accumulator
+        // ROW, so direct stores put the 32 lanes of a warp on 32 different rows -- 16 useful bytes per 32-byte sector and request; timing experiments put the
+        // epilogue's global traffic at 31 of 68 us (51 of 92 us with the mask loads, profiles/r2/gemm_dbg.txt).  Pass: TMEM -> registers -> (bias, ReLU, output
+        // layer partials) -> staging tile [128][132]; then each warp streams 16 rows out, 512 contiguous bytes per instruction, the ReLU mask read the same way.
+        constexpr int PITCH = 132;             // floats: consecutive rows start 4 banks apart -> conflict-free float4 column writes and row reads
+        float *stg = reinterpret_cast<float *>(base);
+        static_assert(GM_M * PITCH * 4 <= 2 * (GM_A_STAGE + NT * 128), "the staging tile reuses the operand stages");
+#pragma unroll 1
+        for (int pass = 0; pass * 128 < NT; pass++) {
+            const int cbase = pass * 128;
+#pragma unroll 1
+            for (int b = 0; b < 4; b++) {
+                const int n0 = cbase + half * 64 + b * 16;         // (warp-uniform)
+                if (n0 >= NT) break;
+                float v[16];
+                tmem_ld16(tmem + lane_base + n0, v);
+                if (n0 >= P.N) continue;
+                if (P.epi == EPI_BIAS_RELU || P.epi == EPI_BIAS_RELU_OUT) {
 #pragma unroll
-                for (int i4 = 0; i4 < 4; i4++) reinterpret_cast<float4 *>(cp)[i4] = make_float4(v[4 * i4], v[4 * i4 + 1], v[4 * i4 + 2], v[4 * i4 + 3]);
-            } else {
+                    for (int i = 0; i < 16; i++) v[i] = (n0 + i < P.N) ? fmaxf(v[i] + __ldg(P.bias + n0 + i), 0.f) : 0.f;
+                    if (P.epi == EPI_BIAS_RELU_OUT) {
 #pragma unroll
-                for (int i = 0; i < 16; i++) if (n0 + i < P.N) cp[i] = v[i];
+                        for (int i = 0; i < 16; i++) {
+                            if (n0 + i < P.N) {
+#pragma unroll
+                                for (int o = 0; o < 3; o++) if (o < P.nout) yacc[o] = fmaf(v[i], __ldg(P.W3 + (size_t)o * P.N + n0 + i), yacc[o]);
+                            }
+                        }
+                    }
+                }
+                float4 *sp = reinterpret_cast<float4 *>(stg + row * PITCH + (n0 - cbase));
+#pragma unroll
+                for (int i4 = 0; i4 < 4; i4++) sp[i4] = make_float4(v[4 * i4], v[4 * i4 + 1], v[4 * i4 + 2], v[4 * i4 + 3]);
             }
+            __syncthreads();
+#ifdef UAISA_GEMM_DBG
+            if (!(P.dbg & 4))
+#endif
+            if (P.C) {
+                const int n = cbase + 4 * lane;
+#pragma unroll 4
+                for (int r = warp; r < GM_M; r += GM_T / 32) {
+                    const int mr = m0 + r;
+                    if (mr >= P.M || n >= P.N) continue;
+                    float4 o = *reinterpret_cast<const float4 *>(stg + r * PITCH + 4 * lane);
+                    float *cp = P.C + (size_t)mr * P.ldc + n;
+                    const bool full = n + 3 < P.N;
+                    if (P.epi == EPI_MASK) {
+                        const float *mp = P.mask + (size_t)mr * P.ldm + n;
+                        if (vecM && full) {
+                            const float4 h = __ldg(reinterpret_cast<const float4 *>(mp));
+                            o.x = h.x > 0.f ? o.x : 0.f; o.y = h.y > 0.f ? o.y : 0.f; o.z = h.z > 0.f ? o.z : 0.f; o.w = h.w > 0.f ? o.w : 0.f;
+                        } else {
+                            o.x = __ldg(mp) > 0.f ? o.x : 0.f;
+                            if (n + 1 < P.N) o.y = __ldg(mp + 1) > 0.f ? o.y : 0.f;
+                            if (n + 2 < P.N) o.z = __ldg(mp + 2) > 0.f ? o.z : 0.f;
+                            if (n + 3 < P.N) o.w = __ldg(mp + 3) > 0.f ? o.w : 0.f;
+                        }
+                    }
+                    if (vecC && full) *reinterpret_cast<float4 *>(cp) = o;
+                    else { cp[0] = o.x; if (n + 1 < P.N) cp[1] = o.y; if (n + 2 < P.N) cp[2] = o.z; if (n + 3 < P.N) cp[3] = o.w; }
+                }
+            }
+            __syncthreads();                   // the staging tile is rewritten by the next pass
         }
     }
     if (P.epi == EPI_BIAS_RELU_OUT) {          // the two column halves of a row meet in shared memory
@@ -341,6 +365,9 @@ int uaisa_mlp_gemm(const float *A, int32_t lda, int32_t a_mn, const float *B, in
     GemmParams P{};
     P.A = A; P.lda = lda; P.a_mn = a_mn; P.B = B; P.ldb = ldb; P.b_mn = b_mn; P.C = C; P.ldc = ldc; P.M = M; P.N = N; P.K = K;
     P.k_per_split = (((K + splits - 1) / splits) + 31) / 32 * 32;
+#ifdef UAISA_GEMM_DBG
+    P.dbg = std::getenv("UAISA_GEMM_DBG") ? std::atoi(std::getenv("UAISA_GEMM_DBG")) : 0;
+#endif
     P.epi = epi; P.bias = bias; P.mask = mask; P.ldm = ldm; P.W3 = W3; P.b3 = b3; P.Y = Y; P.nout = nout;
     const dim3 grid((M + GM_M - 1) / GM_M, (K + P.k_per_split - 1) / P.k_per_split);
     if (N <= 256) uaisa_mlp_gemm_kernel<256><<<grid, GM_T, gemm_smem<256>(), static_cast<cudaStream_t>(stream)>>>(P);

@@ -161,6 +161,15 @@ __global__ void __launch_bounds__(FW_NT, 1) uaisa_policy_forward_kernel(const __
 
     const uint32_t crank = CL > 1 ? cluster_ctarank() : 0u;
     constexpr uint16_t CMASK = (uint16_t)((1u << CL) - 1u);
+    // every global input of the tile's first phases is requested BEFORE the set-up barriers -- the row count, the 12 self values and neighbour row 0 (21
+    // consecutive floats of the agent's observation) -- so the tile pays one exposed memory latency instead of three (count -> x tile -> self at the LayerNorm)
+    const float *orow = P.obs + (size_t)(ok ? a : 0) * P.obs_dim;
+    int cnt = ok ? (int)P.count[a] : 0;
+    float in0[FW_SELF + FW_IN];
+    if (sub == 0) {
+#pragma unroll
+        for (int k = 0; k < FW_SELF + FW_IN; k++) in0[k] = (ok && (k < FW_SELF || P.nm > 0)) ? __ldg(orow + k) : 0.0f;
+    }
     if (warp == 0) tmem_alloc(smem_u32(tmem_slot), 512u);
     if (tid == 0) {
         mbar_init(smem_u32(&bars[0]), 1); mbar_init(smem_u32(&bars[1]), 1);          // full: my own arrive.expect_tx (+ the tile's bytes)
@@ -170,20 +179,32 @@ __global__ void __launch_bounds__(FW_NT, 1) uaisa_policy_forward_kernel(const __
         *s_lmax = 1;
     }
     __syncthreads();
-    int cnt = ok ? (int)P.count[a] : 0;
     cnt = cnt < P.nm ? cnt : P.nm;
     const int c_eff = cnt > 1 ? cnt : 1;               // an agent without neighbours feeds ONE zero row (ir_gym.py:211-212)
     {   // number of GRU steps = the largest row count in the CLUSTER's tiles (all its CTAs must walk the same weight-tile sequence)
-        int m = 1;
-        for (int q = tid; q < CL * FW_M; q += FW_NT) {
-            const int aq = (int)(blockIdx.x / CL) * CL * FW_M + q;
-            int c = aq < P.A ? (int)P.count[aq] : 0;
-            c = c < P.nm ? c : P.nm;
-            m = c > m ? c : m;
+        int m = cnt > 1 ? cnt : 1;
+        if (CL > 1) {
+            for (int q = tid; q < CL * FW_M; q += FW_NT) {
+                const int aq = (int)(blockIdx.x / CL) * CL * FW_M + q;
+                int c = aq < P.A ? (int)P.count[aq] : 0;
+                c = c < P.nm ? c : P.nm;
+                m = c > m ? c : m;
+            }
         }
         m = __reduce_max_sync(0xffffffffu, m);
         if ((tid & 31) == 0) atomicMax(s_lmax, m);
     }
+    {   // A chunk 8, my row: neighbour row 0 in K columns 0..8 (zero up to 15: the chunk is multiplied with K = 16), the self values parked in columns 16..27
+        // (never read by an MMA) until the LayerNorm
+        char *t8 = As + 8 * FW_A_CHUNK;
+        if (sub == 0) {
+            *swz(t8, row, 0) = make_float4(in0[12], in0[13], in0[14], in0[15]); *swz(t8, row, 1) = make_float4(in0[16], in0[17], in0[18], in0[19]);
+            *swz(t8, row, 2) = make_float4(in0[20], 0.f, 0.f, 0.f); *swz(t8, row, 3) = make_float4(0.f, 0.f, 0.f, 0.f);
+            *swz(t8, row, 4) = make_float4(in0[0], in0[1], in0[2], in0[3]); *swz(t8, row, 5) = make_float4(in0[4], in0[5], in0[6], in0[7]);
+            *swz(t8, row, 6) = make_float4(in0[8], in0[9], in0[10], in0[11]);
+        }
+    }
+    fence_proxy_async();
     fence_before_sync();
     __syncthreads();
     fence_after_sync();
@@ -191,7 +212,6 @@ __global__ void __launch_bounds__(FW_NT, 1) uaisa_policy_forward_kernel(const __
     const uint32_t tmem = __shfl_sync(0xffffffffu, *tmem_slot, 0);      // (warp-uniform values, provably)
     const int lmax = __shfl_sync(0xffffffffu, *s_lmax, 0);
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;      // a warp reaches the TMEM lane quarter (warp id % 4)
-    const float *orow = P.obs + (size_t)(ok ? a : 0) * P.obs_dim;
     const float *wp = P.wp;
     uint32_t dpar = 0;                                 // parity of the `done` barrier (all threads)
     // ---- warp 0: weight-tile ring and MMA issue.  The WHOLE warp runs this code (warp-uniform control flow and state, so ring indices, parities and the
@@ -251,7 +271,7 @@ __global__ void __launch_bounds__(FW_NT, 1) uaisa_policy_forward_kernel(const __
     auto sync_tmem = [&]() { fence_before_sync(); __syncthreads(); fence_after_sync(); };
     constexpr uint32_t ID192 = umma_idesc_tf32(128, 192), ID128 = umma_idesc_tf32(128, 128), ID64 = umma_idesc_tf32(128, 64), ID256 = umma_idesc_tf32(128, 256);
 
-    // x_t of my row into the A tile of chunk 8 (9 values, zero padded to 32): sub-thread 0 writes the values, the others the padding
+    // x_t of my row into the A tile of chunk 8 (9 values, zero padded to 16 = the K the chunk is multiplied with)
     auto write_x = [&](int idx, bool valid) {
         char *t8 = As + 8 * FW_A_CHUNK;
         if (sub == 0) {
@@ -264,8 +284,7 @@ __global__ void __launch_bounds__(FW_NT, 1) uaisa_policy_forward_kernel(const __
             }
             *swz(t8, row, 0) = make_float4(x[0], x[1], x[2], x[3]); *swz(t8, row, 1) = make_float4(x[4], x[5], x[6], x[7]);
             *swz(t8, row, 2) = make_float4(x[8], 0.f, 0.f, 0.f);
-        }
-        for (int k4 = 3 + sub; k4 < 8; k4 += FW_S) *swz(t8, row, k4) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }                                              // (K columns 12..15 stay zero from the set-up, 16..31 are never multiplied)
     };
     auto ld4 = [&](const float *p, float *o) { const float4 f = __ldg(reinterpret_cast<const float4 *>(p)); o[0] = f.x; o[1] = f.y; o[2] = f.z; o[3] = f.w; };
     auto ld16 = [&](const float *p, float *o) { ld4(p, o); ld4(p + 4, o + 4); ld4(p + 8, o + 8); ld4(p + 12, o + 12); };
@@ -325,9 +344,7 @@ __global__ void __launch_bounds__(FW_NT, 1) uaisa_policy_forward_kernel(const __
     // =========================================================================================== bi-GRU reader
     if (lmax == 1) {
         // every agent of the tile has <= 1 row: one step from h = 0 in both directions (no recurrent GEMM); both directions' accumulators side by side
-        write_x(0, true);
-        sync_smem_to_mma();
-        for (int slice = 0; slice < 4; slice++) {
+        for (int slice = 0; slice < 4; slice++) {          // (row 0 is in the A tile since the set-up)
             if (warp == 0) {
                 int s = acquire(); mma(8, smem_u32(Bs + s * FW_STAGE), 2, ID192, tmem + 0, false); release(s);
                 s = acquire(); mma(8, smem_u32(Bs + s * FW_STAGE), 2, ID192, tmem + 256, false); release(s);
@@ -352,7 +369,7 @@ __global__ void __launch_bounds__(FW_NT, 1) uaisa_policy_forward_kernel(const __
             for (int step = 0; step < lmax; step++) {
                 const bool active = step < c_eff;
                 // ---- this step's x tile; (from step 1 on) the previous step's new state, TMEM -> A tile
-                write_x(dir == 0 ? step : c_eff - 1 - step, active);
+                if (dir | step) write_x(dir == 0 ? step : c_eff - 1 - step, active);       // (row 0 of the first step is in the A tile since the set-up)
                 if (step > 0) {
 #pragma unroll 1
                     for (int ub = sub; ub < 16; ub += FW_S) { float h[16]; tmem_ld16(tmem + lane_base + 256 + ub * 16, h); write_h16(ub * 16, h); }
@@ -416,9 +433,13 @@ __global__ void __launch_bounds__(FW_NT, 1) uaisa_policy_forward_kernel(const __
     if (!(P.dbg & 8))
 #endif
     {
-        float self[FW_SELF];
+        float self[FW_SELF];                           // parked in K columns 16..27 of A chunk 8 by the set-up
 #pragma unroll
-        for (int k = 0; k < FW_SELF; k++) self[k] = (ok && sub == 0) ? __ldg(orow + k) : 0.0f;
+        for (int k = 0; k < FW_SELF; k++) self[k] = 0.0f;
+        if (sub == 0) {
+#pragma unroll
+            for (int j = 0; j < 3; j++) { const float4 f = *swz(As + 8 * FW_A_CHUNK, row, 4 + j); self[4 * j] = f.x; self[4 * j + 1] = f.y; self[4 * j + 2] = f.z; self[4 * j + 3] = f.w; }
+        }
         float red[1] = {0.0f};
         if (sub == 0) {
 #pragma unroll

@@ -252,27 +252,36 @@ __global__ void __launch_bounds__(GM_T, NT <= 256 ? 2 : 1) uaisa_mlp_gemm_kernel
 #endif
             if (P.C) {
                 const int n = cbase + 4 * lane;
-#pragma unroll 4
-                for (int r = warp; r < GM_M; r += GM_T / 32) {
-                    const int mr = m0 + r;
-                    if (mr >= P.M || n >= P.N) continue;
-                    float4 o = *reinterpret_cast<const float4 *>(stg + r * PITCH + 4 * lane);
-                    float *cp = P.C + (size_t)mr * P.ldc + n;
-                    const bool full = n + 3 < P.N;
-                    if (P.epi == EPI_MASK) {
-                        const float *mp = P.mask + (size_t)mr * P.ldm + n;
-                        if (vecM && full) {
-                            const float4 h = __ldg(reinterpret_cast<const float4 *>(mp));
-                            o.x = h.x > 0.f ? o.x : 0.f; o.y = h.y > 0.f ? o.y : 0.f; o.z = h.z > 0.f ? o.z : 0.f; o.w = h.w > 0.f ? o.w : 0.f;
-                        } else {
-                            o.x = __ldg(mp) > 0.f ? o.x : 0.f;
-                            if (n + 1 < P.N) o.y = __ldg(mp + 1) > 0.f ? o.y : 0.f;
-                            if (n + 2 < P.N) o.z = __ldg(mp + 2) > 0.f ? o.z : 0.f;
-                            if (n + 3 < P.N) o.w = __ldg(mp + 3) > 0.f ? o.w : 0.f;
-                        }
+                const bool full = n + 3 < P.N, mv = P.epi == EPI_MASK && vecM && full;
+                constexpr int RG = 8;                              // rows per group: the group's mask loads are all in flight before the first is used
+#pragma unroll 1
+                for (int r0 = warp; r0 < GM_M; r0 += RG * (GM_T / 32)) {
+                    float4 h[RG];
+#pragma unroll
+                    for (int u = 0; u < RG; u++) {
+                        const int mr = m0 + r0 + u * (GM_T / 32);
+                        if (mv && mr < P.M) h[u] = __ldg(reinterpret_cast<const float4 *>(P.mask + (size_t)mr * P.ldm + n));
                     }
-                    if (vecC && full) *reinterpret_cast<float4 *>(cp) = o;
-                    else { cp[0] = o.x; if (n + 1 < P.N) cp[1] = o.y; if (n + 2 < P.N) cp[2] = o.z; if (n + 3 < P.N) cp[3] = o.w; }
+#pragma unroll
+                    for (int u = 0; u < RG; u++) {
+                        const int r = r0 + u * (GM_T / 32), mr = m0 + r;
+                        if (mr >= P.M || n >= P.N) continue;
+                        float4 o = *reinterpret_cast<const float4 *>(stg + r * PITCH + 4 * lane);
+                        float *cp = P.C + (size_t)mr * P.ldc + n;
+                        if (P.epi == EPI_MASK) {
+                            if (mv) {
+                                o.x = h[u].x > 0.f ? o.x : 0.f; o.y = h[u].y > 0.f ? o.y : 0.f; o.z = h[u].z > 0.f ? o.z : 0.f; o.w = h[u].w > 0.f ? o.w : 0.f;
+                            } else {
+                                const float *mp = P.mask + (size_t)mr * P.ldm + n;
+                                o.x = __ldg(mp) > 0.f ? o.x : 0.f;
+                                if (n + 1 < P.N) o.y = __ldg(mp + 1) > 0.f ? o.y : 0.f;
+                                if (n + 2 < P.N) o.z = __ldg(mp + 2) > 0.f ? o.z : 0.f;
+                                if (n + 3 < P.N) o.w = __ldg(mp + 3) > 0.f ? o.w : 0.f;
+                            }
+                        }
+                        if (vecC && full) *reinterpret_cast<float4 *>(cp) = o;
+                        else { cp[0] = o.x; if (n + 1 < P.N) cp[1] = o.y; if (n + 2 < P.N) cp[2] = o.z; if (n + 3 < P.N) cp[3] = o.w; }
+                    }
                 }
             }
             __syncthreads();                   // the staging tile is rewritten by the next pass

@@ -47,6 +47,9 @@ case $what in
     timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:uaisa_ -c 400 --csv --log-file gpurun_out/r2/launches_bench_default.csv python bench.py --steps 20 --warmup 5 --no-cpu > gpurun_out/r2/ncu_bench.log 2>&1; tail -2 gpurun_out/r2/ncu_bench.log | cut -c1-200; wc -l gpurun_out/r2/launches_bench_default.csv ;;
   ncu_mlp)
     timeout 200 python profiles/prof_mlp.py > /dev/null 2>&1 && timeout 400 ncu --set full --clock-control none --import-source on -k regex:uaisa_mlp_gemm -s 8 -c 2 -f -o gpurun_out/r2/prof_mlp_gemm python profiles/prof_mlp.py > gpurun_out/r2/ncu_mlp.log 2>&1; tail -1 gpurun_out/r2/ncu_mlp.log ;;
+  ppoprof)   # torch.profiler kernel tables of one update iteration and one rollout step
+    timeout 300 python profiles/ppo_update_profile.py 65536 > gpurun_out/r2/ppo_update_profile_tc.txt 2>&1; head -16 gpurun_out/r2/ppo_update_profile_tc.txt | cut -c1-150
+    timeout 300 python profiles/ppo_rollout_profile.py > gpurun_out/r2/ppo_rollout_profile.txt 2>&1; head -12 gpurun_out/r2/ppo_rollout_profile.txt | cut -c1-150 ;;
   ppo)
     timeout 600 python bench.py --workload ppo --ppo-epochs 3 > gpurun_out/r2/bench_ppo.json 2> gpurun_out/r2/bench_ppo.err; tail -3 gpurun_out/r2/bench_ppo.err; python -c "
 import json;d=json.loads([l for l in open('gpurun_out/r2/bench_ppo.json') if l.startswith('{')][-1]);print(d['value']);print(d['ppo']['per_epoch'])" ;;

@@ -37,7 +37,8 @@ constexpr int FW_OFF_B1 = FW_OFF_LN + 2 * 288;                   // [2 head][256
 constexpr int FW_OFF_B2 = FW_OFF_B1 + 512;                       // [2 head][256]
 constexpr int FW_OFF_W3 = FW_OFF_B2 + 512;                       // [4][256]: actor rows 0..2, critic row 3
 constexpr int FW_OFF_B3 = FW_OFF_W3 + 1024;                      // [4]
-constexpr int FW_PACK_FLOATS = FW_OFF_B3 + 16;
+constexpr int FW_OFF_H0 = FW_OFF_B3 + 16;                        // [256]: the reader's output for an agent WITHOUT neighbour rows (one zero row, h0 = 0): a constant of the weights
+constexpr int FW_PACK_FLOATS = FW_OFF_H0 + 256;
 
 constexpr int FW_A_CHUNK = FW_M * 128;                           // bytes of one A chunk [128 rows x 32 fp32]
 constexpr int FW_STAGE = 256 * 128;                              // bytes of one B stage
@@ -48,6 +49,12 @@ struct PackSrc {       // raw module parameters (device pointers), torch layouts
     const float *ln_w, *ln_b;                                    // [268] in [self | h] order
     const float *W1[2], *b1[2], *W2[2], *b2[2], *W3[2], *b3[2];  // [0] actor, [1] critic; W1 [256][268], W2 [256][256], W3 [3 | 1][256]
 };
+
+// Gate non-linearities on the SFU: tanh.approx.f32 (one MUFU.TANH, max abs error 2^-10.99 ~ 4.9e-4) and sigmoid(x) = 0.5 tanh(x/2) + 0.5 (error 2.4e-4) --
+// the same order as the TF32 rounding of the GEMM operands that feed them (10-bit mantissa).  The exp-and-IEEE-divide forms were 48 % of the kernel's
+// executed instructions (profiles/r2/ncu_policy_forward_sparse.txt).
+__device__ __forceinline__ float tanh_fast(float x) { float y; asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float sigm(float x) { return fmaf(0.5f, tanh_fast(0.5f * x), 0.5f); }
 
 // (row, k) of float index w inside a swizzled tile image (inverse of tc::swz_float_index)
 __device__ __forceinline__ void unswz(int w, int &row, int &k) {
@@ -89,7 +96,20 @@ __global__ void uaisa_policy_pack_kernel(const __grid_constant__ PackSrc S, floa
     } else if (i < FW_OFF_B2) { const int j = i - FW_OFF_B1; val = S.b1[j >> 8][j & 255]; }
     else if (i < FW_OFF_W3) { const int j = i - FW_OFF_B2; val = S.b2[j >> 8][j & 255]; }
     else if (i < FW_OFF_B3) { const int j = i - FW_OFF_W3, r = j >> 8; val = r < 3 ? S.W3[0][r * 256 + (j & 255)] : S.W3[1][j & 255]; }
-    else { const int j = i - FW_OFF_B3; if (j < 3) val = S.b3[0][j]; else if (j == 3) val = S.b3[1][0]; }
+    else if (i < FW_OFF_H0) { const int j = i - FW_OFF_B3; if (j < 3) val = S.b3[0][j]; else if (j == 3) val = S.b3[1][0]; }
+    else {                                                         // one GRU step from h = 0 on a zero row, both directions summed: the operations (and their order) of
+        const int u = i - FW_OFF_H0;                               // gates16() in the forward kernel on accumulators that are exactly 0
+        float hd[2];
+        for (int dir = 0; dir < 2; dir++) {
+            const float br = S.b_ih[dir][u] + S.b_hh[dir][u], bz = S.b_ih[dir][256 + u] + S.b_hh[dir][256 + u], bin = S.b_ih[dir][512 + u], bhn = S.b_hh[dir][512 + u];
+            float r = sigm(0.0f + br);
+            const float z = sigm(0.0f + bz);
+            r *= bhn;
+            const float nn = tanh_fast(0.0f + bin + r);
+            hd[dir] = (1.0f - z) * nn + 0.0f;
+        }
+        val = hd[0] + hd[1];
+    }
     wp[i] = val;
 }
 
@@ -108,7 +128,7 @@ struct FwdParams {
 // order in which the weight tiles are consumed (thread 0's prefetcher walks it independently of the consumer)
 struct TileIter {
     int lmax, phase, dir, step, slice, sub, lin;
-    __device__ __forceinline__ void init(int lmax_) { lmax = lmax_; phase = 0; dir = step = slice = sub = lin = 0; }
+    __device__ __forceinline__ void init(int lmax_) { lmax = lmax_; phase = lmax_ == 0 ? 1 : 0; dir = step = slice = sub = lin = 0; }   // (no GRU tiles for a tile without neighbour rows)
     __device__ __forceinline__ bool next(const float *wp, const float *&addr, uint32_t &bytes) {
         if (phase == 0) {
             bytes = FW_TILE_G * 4;
@@ -127,12 +147,6 @@ struct TileIter {
         return false;
     }
 };
-
-// Gate non-linearities on the SFU: tanh.approx.f32 (one MUFU.TANH, max abs error 2^-10.99 ~ 4.9e-4) and sigmoid(x) = 0.5 tanh(x/2) + 0.5 (error 2.4e-4) --
-// the same order as the TF32 rounding of the GEMM operands that feed them (10-bit mantissa).  The exp-and-IEEE-divide forms were 48 % of the kernel's
-// executed instructions (profiles/r2/ncu_policy_forward_sparse.txt).
-__device__ __forceinline__ float tanh_fast(float x) { float y; asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-__device__ __forceinline__ float sigm(float x) { return fmaf(0.5f, tanh_fast(0.5f * x), 0.5f); }
 
 // FW_S threads share one agent row (thread t, t + 128, ...: same TMEM lane, different warps): the 16-unit blocks of every epilogue are dealt round-robin to
 // them, so a CTA has 4 * FW_S warps to hide the latency of the element-wise work (gates, LayerNorm, bias + ReLU) that dominates the kernel's instruction count.
@@ -176,13 +190,13 @@ __global__ void __launch_bounds__(FW_NT, 1) uaisa_policy_forward_kernel(const __
         mbar_init(smem_u32(&bars[2]), CL); mbar_init(smem_u32(&bars[3]), CL);        // empty: one tcgen05.commit arrival per CTA of the cluster
         mbar_init(smem_u32(&bars[4]), 1);                                            // done
         mbar_init_fence();
-        *s_lmax = 1;
+        *s_lmax = 0;
     }
     __syncthreads();
     cnt = cnt < P.nm ? cnt : P.nm;
     const int c_eff = cnt > 1 ? cnt : 1;               // an agent without neighbours feeds ONE zero row (ir_gym.py:211-212)
     {   // number of GRU steps = the largest row count in the CLUSTER's tiles (all its CTAs must walk the same weight-tile sequence)
-        int m = cnt > 1 ? cnt : 1;
+        int m = cnt;
         if (CL > 1) {
             for (int q = tid; q < CL * FW_M; q += FW_NT) {
                 const int aq = (int)(blockIdx.x / CL) * CL * FW_M + q;
@@ -198,6 +212,10 @@ __global__ void __launch_bounds__(FW_NT, 1) uaisa_policy_forward_kernel(const __
         // (never read by an MMA) until the LayerNorm
         char *t8 = As + 8 * FW_A_CHUNK;
         if (sub == 0) {
+            if (cnt == 0) {                            // no neighbours: the reader is fed ONE ZERO row whatever the observation holds there (ir_gym.py:211-212)
+#pragma unroll
+                for (int k = 0; k < FW_IN; k++) in0[FW_SELF + k] = 0.0f;
+            }
             *swz(t8, row, 0) = make_float4(in0[12], in0[13], in0[14], in0[15]); *swz(t8, row, 1) = make_float4(in0[16], in0[17], in0[18], in0[19]);
             *swz(t8, row, 2) = make_float4(in0[20], 0.f, 0.f, 0.f); *swz(t8, row, 3) = make_float4(0.f, 0.f, 0.f, 0.f);
             *swz(t8, row, 4) = make_float4(in0[0], in0[1], in0[2], in0[3]); *swz(t8, row, 5) = make_float4(in0[4], in0[5], in0[6], in0[7]);
@@ -342,7 +360,13 @@ __global__ void __launch_bounds__(FW_NT, 1) uaisa_policy_forward_kernel(const __
     };
 
     // =========================================================================================== bi-GRU reader
-    if (lmax == 1) {
+    if (lmax == 0) {
+        // no agent of the tile has a neighbour row: the reader's output is the same vector for every agent, h0 (packed with the weights) -- no GRU tile is fetched,
+        // no MMA issued, no gate evaluated.  Bit-identical to the general path, whose accumulators are exactly 0 for a zero row
+        // (tests/test_policy.py::test_tiles_without_neighbour_rows_take_the_constant_reader_output).  Sparse airspace: the whole rollout of configs[1] / [4].
+#pragma unroll 1
+        for (int ub = sub; ub < 16; ub += FW_S) { float h[16]; ld16(wp + FW_OFF_H0 + ub * 16, h); write_h16(ub * 16, h); }
+    } else if (lmax == 1) {
         // every agent of the tile has <= 1 row: one step from h = 0 in both directions (no recurrent GEMM); both directions' accumulators side by side
         for (int slice = 0; slice < 4; slice++) {          // (row 0 is in the A tile since the set-up)
             if (warp == 0) {

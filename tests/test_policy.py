@@ -210,3 +210,40 @@ def test_sample_kernel_equals_the_torch_expression():
     mu, v_ref, _ = fp.forward(obs, cnt)
     assert v.data_ptr() == buf_v[1].data_ptr() and torch.equal(buf_v[1], v_ref) and float(buf_v[0].abs().max()) == 0.0
     assert torch.isfinite(buf_lp[1]).all() and float(buf_lp[1].abs().max()) > 0 and float(buf_lp[0].abs().max()) == 0.0
+
+
+@pytest.mark.gpu
+def test_tiles_without_neighbour_rows_take_the_constant_reader_output():
+    """A 128-agent tile in which NO agent has a neighbour row skips the GRU (no weight tile, no MMA, no gate): the reader's output is the constant h0 packed with
+    the weights.  Same values BIT FOR BIT as the general path (an agent without neighbours feeds one zero row, ir_gym.py:211-212, so its accumulators are
+    exactly 0 there), whatever the observation holds in the unused row slots; and equal to the torch module within the TF32 bound."""
+    from uaisa_ppo.fused import FusedPolicy
+
+    torch.backends.cuda.matmul.allow_tf32 = False
+    m = _model("cuda")
+    fp = FusedPolicy(m, "cuda")
+    g = torch.Generator(device="cuda"); g.manual_seed(11)
+    A, D = 300, 12 + 9 * 3                                            # tiles 0, 1 full, tile 2 ragged
+    obs = torch.zeros((A, D), device="cuda"); obs[:, :12] = torch.randn((A, 12), device="cuda", generator=g) * 4
+    cnt0 = torch.zeros(A, dtype=torch.uint8, device="cuda")
+    fp.stats.zero_()
+    mu0, v0, f0 = fp.forward(obs, cnt0, want_features=True)           # every tile takes the constant path
+    assert fp.stats.tolist() == [0, 0]
+    with torch.no_grad():
+        ref_f = m.features(obs, cnt0); dist, ref_v, _ = m.evaluate(obs, cnt0)
+    assert (f0 - ref_f).abs().max().item() < 1e-3 and (mu0 - dist.mean).abs().max().item() < 1e-2 and (v0 - ref_v).abs().max().item() < 1e-2 * max(1.0, float(ref_v.abs().max()))
+    # one agent with a row in every tile: the tiles run the GRU step now; the agents without rows must not change by a bit
+    obs1, cnt1 = obs.clone(), cnt0.clone()
+    for a in (127, 128, 299):
+        cnt1[a] = 1; obs1[a, 12:21] = torch.randn(9, device="cuda", generator=g)
+    mu1, v1, f1 = fp.forward(obs1, cnt1, want_features=True)
+    keep = cnt1 == 0
+    assert torch.equal(mu0[keep], mu1[keep]) and torch.equal(v0[keep], v1[keep]) and torch.equal(f0[keep], f1[keep])
+    assert not torch.equal(f0[127], f1[127])
+    # stale data in the row slots of agents without neighbours is never read -- in either path
+    obs2 = obs.clone(); obs2[:, 12:] = torch.randn((A, D - 12), device="cuda", generator=g) * 3
+    mu2, v2, f2 = fp.forward(obs2, cnt0, want_features=True)
+    assert torch.equal(mu0, mu2) and torch.equal(v0, v2) and torch.equal(f0, f2)
+    obs3 = obs1.clone(); obs3[keep, 12:] = obs2[keep, 12:]
+    mu3, v3, f3 = fp.forward(obs3, cnt1, want_features=True)
+    assert torch.equal(mu1, mu3) and torch.equal(v1, v3) and torch.equal(f1, f3)

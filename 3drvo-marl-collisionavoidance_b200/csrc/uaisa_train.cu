@@ -166,6 +166,13 @@ struct ReaderThread {                 // thread (d, u): its weights, biases
     }
 };
 
+__device__ __forceinline__ bool rd_all_zero(const float *x) {
+    bool z = true;
+#pragma unroll
+    for (int k = 0; k < RD_IN; k++) z = z && (x[k] == 0.0f);
+    return z;
+}
+
 // x rows of a tile -> shared memory (threads 0 .. ns*9-1), zero if the observation has no neighbour slot
 __device__ __forceinline__ void load_x_tile(float (*s_x)[RD_IN + 3], const float *obs, const long long *idx, int obs_dim, int s0, int ns, int tid) {
     if (tid < ns * RD_IN) {
@@ -182,6 +189,14 @@ __global__ void __launch_bounds__(512) uaisa_reader_fwd_kernel(const float *__re
     float (*s_h)[2][RD_H] = reinterpret_cast<float (*)[2][RD_H]>(rd_smem + RB_T * (RD_IN + 3));
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, d = tid >> 8, u = tid & 255;
     ReaderThread T; T.load(W, d, u);
+    // A sample without neighbour rows feeds a ZERO row (ir_gym.py:211-212): its gates are constants of the biases -- fmaf(0, w, b) = b exactly, so evaluating them
+    // once per thread gives the very bits of the general path.  Sparse airspace: almost every sample of a configs[1] / configs[4] epoch.
+    float r0, z0, n0;
+    { float xz[RD_IN];
+#pragma unroll
+      for (int k = 0; k < RD_IN; k++) xz[k] = 0.0f;
+      T.gates(xz, r0, z0, n0); }
+    const float h0 = (1.0f - z0) * n0;
     const int n_tiles = (B + RB_T - 1) / RB_T;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int s0 = tile * RB_T, ns = min(RB_T, B - s0);
@@ -191,6 +206,7 @@ __global__ void __launch_bounds__(512) uaisa_reader_fwd_kernel(const float *__re
             float x[RD_IN];
 #pragma unroll
             for (int k = 0; k < RD_IN; k++) x[k] = s_x[j][k];
+            if (rd_all_zero(x)) { s_h[j][d][u] = h0; continue; }       // (uniform over the CTA)
             float r, z, n; T.gates(x, r, z, n);
             s_h[j][d][u] = (1.0f - z) * n;
         }
@@ -236,6 +252,11 @@ __global__ void __launch_bounds__(512) uaisa_reader_bwd_kernel(const float *__re
     float (*s_gw)[RD_FEAT] = reinterpret_cast<float (*)[RD_FEAT]>(rd_smem + RB_T * (RD_IN + 3) + RB_T * 2 * RD_H);   // dfeat * xhat  (LayerNorm weight gradient terms)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, d = tid >> 8, u = tid & 255;
     ReaderThread T; T.load(W, d, u);
+    float r0, z0, n0;                                      // gates of a zero row (see the forward kernel)
+    { float xz[RD_IN];
+#pragma unroll
+      for (int k = 0; k < RD_IN; k++) xz[k] = 0.0f;
+      T.gates(xz, r0, z0, n0); }
     float aw[3][RD_IN], ab[4], alw = 0.0f, alb = 0.0f;
 #pragma unroll
     for (int g = 0; g < 3; g++)
@@ -252,6 +273,7 @@ __global__ void __launch_bounds__(512) uaisa_reader_bwd_kernel(const float *__re
                 float x[RD_IN];
 #pragma unroll
                 for (int k = 0; k < RD_IN; k++) x[k] = s_x[j][k];
+                if (rd_all_zero(x)) { s_h[j][d][u] = (1.0f - z0) * n0; continue; }
                 float r, z, n; T.gates(x, r, z, n);
                 s_h[j][d][u] = (1.0f - z) * n;
             }
@@ -290,13 +312,17 @@ __global__ void __launch_bounds__(512) uaisa_reader_bwd_kernel(const float *__re
             float x[RD_IN];
 #pragma unroll
             for (int k = 0; k < RD_IN; k++) x[k] = s_x[j][k];
-            float r, z, n; T.gates(x, r, z, n);
+            const bool zero = rd_all_zero(x);                          // (uniform over the CTA) a zero row: constant gates, no weight gradient -- the same expressions, so the same bits
+            float r = r0, z = z0, n = n0;
+            if (!zero) T.gates(x, r, z, n);
             const float dh = s_h[j][0][u];
             const float dpn = dh * (1.0f - z) * (1.0f - n * n);        // d / d (i_n + b_in + r * b_hn)
             const float dpz = -dh * n * z * (1.0f - z);
             const float dpr = dpn * T.bhn * r * (1.0f - r);
+            if (!zero) {
 #pragma unroll
-            for (int k = 0; k < RD_IN; k++) { aw[0][k] = fmaf(dpr, x[k], aw[0][k]); aw[1][k] = fmaf(dpz, x[k], aw[1][k]); aw[2][k] = fmaf(dpn, x[k], aw[2][k]); }
+                for (int k = 0; k < RD_IN; k++) { aw[0][k] = fmaf(dpr, x[k], aw[0][k]); aw[1][k] = fmaf(dpz, x[k], aw[1][k]); aw[2][k] = fmaf(dpn, x[k], aw[2][k]); }
+            }
             ab[0] += dpr; ab[1] += dpz; ab[2] += dpn; ab[3] += dpn * r;
             if (tid < RD_FEAT) { alw += s_gw[j][tid]; alb += dfeat[(size_t)(s0 + j) * RD_FEAT + tid]; }
         }

@@ -39,6 +39,8 @@ struct GemmParams {
     float *C; int ldc;
     int M, N, K;
     int k_per_split;                    // K range of one blockIdx.y, a multiple of 32
+    int tile_m;                         // output rows one CTA owns (<= 128 = the MMA's M; the rows above it are zero operand rows nobody stores): chosen by the
+                                        // launcher so that the row tiles fill whole waves of resident CTAs
     int epi;
     const float *bias;                  // [N]
     const float *mask; int ldm;         // [M][N]
@@ -126,7 +128,7 @@ __global__ void __launch_bounds__(GM_T, NT <= 256 ? 2 : 1) uaisa_mlp_gemm_kernel
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2);
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);                   // (provably warp-uniform: the MMA issue below stays on the uniform datapath)
-    const int m0 = blockIdx.x * GM_M;
+    const int m0 = blockIdx.x * P.tile_m, m_end = min(P.M, m0 + P.tile_m);
     const int kb = blockIdx.y * P.k_per_split, Kend = min(P.K, kb + P.k_per_split);
     const int nch = (Kend - kb + 31) >> 5;
     if (nch <= 0) return;                                 // (uniform) an empty split adds nothing
@@ -143,7 +145,7 @@ __global__ void __launch_bounds__(GM_T, NT <= 256 ? 2 : 1) uaisa_mlp_gemm_kernel
     constexpr uint32_t IDESC_MAIN = umma_idesc_tf32(GM_M, NT <= 256 ? NT : 256), IDESC_TAIL = umma_idesc_tf32(GM_M, NT > 256 ? NT - 256 : 8);
 
     float4 ra[GM_M * 8 / GM_T], rb[NT * 8 / GM_T];
-    Loader<GM_M> la; la.init(P.A, P.lda, P.a_mn, m0, P.M, kb, vecA, tid);
+    Loader<GM_M> la; la.init(P.A, P.lda, P.a_mn, m0, m_end, kb, vecA, tid);
     Loader<NT> lb; lb.init(P.B, P.ldb, P.b_mn, 0, P.N, kb, vecB, tid);
     la.load(ra, 0, Kend - kb, tid); lb.load(rb, 0, Kend - kb, tid);
     uint32_t par[2] = {0u, 0u};
@@ -188,7 +190,7 @@ __global__ void __launch_bounds__(GM_T, NT <= 256 ? 2 : 1) uaisa_mlp_gemm_kernel
     // ---- epilogue: warp w reads TMEM lanes 32 (w % 4) .. +31; warps w and w + 4 split the columns ---------------------------------------
     const int q = warp & 3, half = warp >> 2, row = q * 32 + lane, m = m0 + row;
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
-    const bool mok = m < P.M;
+    const bool mok = m < m_end;
     const bool vecC = ((reinterpret_cast<uintptr_t>(P.C) & 15) == 0) && (P.ldc & 3) == 0;
     const bool vecM = P.mask && ((reinterpret_cast<uintptr_t>(P.mask) & 15) == 0) && (P.ldm & 3) == 0;
     float yacc[3] = {0.f, 0.f, 0.f};
@@ -260,12 +262,12 @@ __global__ void __launch_bounds__(GM_T, NT <= 256 ? 2 : 1) uaisa_mlp_gemm_kernel
 #pragma unroll
                     for (int u = 0; u < RG; u++) {
                         const int mr = m0 + r0 + u * (GM_T / 32);
-                        if (mv && mr < P.M) h[u] = __ldg(reinterpret_cast<const float4 *>(P.mask + (size_t)mr * P.ldm + n));
+                        if (mv && mr < m_end) h[u] = __ldg(reinterpret_cast<const float4 *>(P.mask + (size_t)mr * P.ldm + n));
                     }
 #pragma unroll
                     for (int u = 0; u < RG; u++) {
                         const int r = r0 + u * (GM_T / 32), mr = m0 + r;
-                        if (mr >= P.M || n >= P.N) continue;
+                        if (mr >= m_end || n >= P.N) continue;
                         float4 o = *reinterpret_cast<const float4 *>(stg + r * PITCH + 4 * lane);
                         float *cp = P.C + (size_t)mr * P.ldc + n;
                         if (P.epi == EPI_MASK) {
@@ -378,7 +380,26 @@ int uaisa_mlp_gemm(const float *A, int32_t lda, int32_t a_mn, const float *B, in
     P.dbg = std::getenv("UAISA_GEMM_DBG") ? std::atoi(std::getenv("UAISA_GEMM_DBG")) : 0;
 #endif
     P.epi = epi; P.bias = bias; P.mask = mask; P.ldm = ldm; P.W3 = W3; P.b3 = b3; P.Y = Y; P.nout = nout;
-    const dim3 grid((M + GM_M - 1) / GM_M, (K + P.k_per_split - 1) / P.k_per_split);
+    // Wave quantisation: 65 536 rows are 512 tiles of 128 on 296 resident CTAs (2 per SM; 148 for the 288-column kernel) = 1.73 waves that cost 2.  The kernel is
+    // bound by its loads and stores, not by the MMAs, so a tile may own FEWER than the MMA's 128 rows: pick the height (multiple of 8, >= 64) that minimises
+    // waves x height -- 112 rows -> 586 tiles = 1.98 waves of 0.875 the work each.
+    int tile_m = GM_M;
+    if (splits == 1) {
+        int dev = 0, sms = 148;
+        static int sm_count[64] = {};
+        if (cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < 64) {
+            if (!sm_count[dev]) { int v = 0; if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0) sm_count[dev] = v; }
+            if (sm_count[dev]) sms = sm_count[dev];
+        }
+        const long long slots = (long long)sms * (N <= 256 ? 2 : 1);
+        long long best = -1;
+        for (int t = GM_M; t >= 64; t -= 8) {
+            const long long tiles = (M + t - 1) / t, waves = (tiles + slots - 1) / slots, cost = waves * t;
+            if (best < 0 || cost < best) { best = cost; tile_m = t; }
+        }
+    }
+    P.tile_m = tile_m;
+    const dim3 grid((M + tile_m - 1) / tile_m, (K + P.k_per_split - 1) / P.k_per_split);
     if (N <= 256) uaisa_mlp_gemm_kernel<256><<<grid, GM_T, gemm_smem<256>(), static_cast<cudaStream_t>(stream)>>>(P);
     else uaisa_mlp_gemm_kernel<288><<<grid, GM_T, gemm_smem<288>(), static_cast<cudaStream_t>(stream)>>>(P);
     return cudaGetLastError() == cudaSuccess ? 0 : -2;

@@ -479,7 +479,7 @@ def measure_ppo(D, args, envs_per_gpu, epochs=1, warm=1):
                                  "note": "the reference makes 50+50 FULL-BATCH passes over each robot's 300 samples (multi_ppo.py:355-376); here each iteration is one "
                                          "minibatch drawn without replacement from the whole [T x A] buffer -- samples/s is NOT a like-for-like ratio to the reference's"},
            "policy": tr.policy_path, "update": tr.update_path,
-           "gpu_launches_per_epoch": {"env (action transform, step + reset policy in one launch) + fused policy forward": 3 * cfg.steps_per_epoch, "gae": 1,
+           "gpu_launches_per_epoch": {"env (action transform, step + reset policy in one launch) + fused policy forward + sampling (uaisa_policy_sample)": 4 * cfg.steps_per_epoch, "gae": 1,
                                       "clip/Adam (prepare + apply)": 2 * (cfg.train_pi_iters + cfg.train_v_iters), "policy repack": 1,
                                       "update forward/backward (reader fwd + bwd, 6 x uaisa_mlp_gemm, out_bwd, colsum)": 10 * (cfg.train_pi_iters + cfg.train_v_iters) if cfg.tc_mlp else 2 * (cfg.train_pi_iters + cfg.train_v_iters),
                                       "note": "own kernels per epoch (graph replays included)" + ("" if cfg.tc_mlp else "; the update's MLP GEMMs are torch / cuBLAS")},

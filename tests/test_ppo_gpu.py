@@ -174,3 +174,173 @@ def test_graphed_update_equals_eager_update():
     lr_max = max(float(z["hyper"][0]), float(z["hyper"][1]))
     frac = float((d <= 2e-6).float().mean())
     assert frac >= 0.998 and float(d.max()) <= 6.5 * lr_max, (float(d.max()), frac, int((d > 2e-6).sum()), torch.nonzero(d > 2e-6).flatten()[:8].tolist())
+
+
+def test_clip_adam_kernel_matches_torch_and_early_stop_latches():
+    """uaisa_opt_prepare + uaisa_clip_adam against clip_grad_norm_ + torch.optim.Adam on a flat bucket; the KL latch stops later iterations."""
+    import ctypes as C
+    from uaisa_env import _capi
+    L = _capi.lib()
+    dev = torch.device("cuda")
+    g0 = torch.Generator(device="cpu").manual_seed(3)
+    n, lo, cnt = 100003, 1000, 90000
+    p = torch.randn(n, generator=g0).to(dev); ref_p = p.clone().requires_grad_(True)
+    m, v = torch.zeros(n, device=dev), torch.zeros(n, device=dev)
+    step = torch.zeros(1, dtype=torch.int32, device=dev); ctl = torch.zeros(2, dtype=torch.int32, device=dev)
+    partials = torch.zeros(L.uaisa_opt_partials_len(), dtype=torch.float64, device=dev)
+    kl = torch.zeros(1, device=dev)
+    opt = torch.optim.Adam([ref_p], lr=1e-2)
+    P = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
+    s = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    for it in range(5):
+        g = (torch.randn(n, generator=g0) * (0.02 if it % 2 else 0.001)).to(dev)     # norm 6.3 (clipped) / 0.3 (not clipped)
+        ref_p.grad = g.clone(); ref_p.grad[:lo] = 0; ref_p.grad[lo + cnt:] = 0        # the reference optimiser only sees its own range ...
+        total = torch.linalg.vector_norm(g)                                            # ... but the clip norm covers the whole bucket
+        coef = torch.clamp(2.0 / (total + 1e-6), max=1.0)
+        ref_p.grad.mul_(coef)
+        before = ref_p.detach().clone()
+        opt.step()
+        ref_p.data[:lo] = before[:lo]; ref_p.data[lo + cnt:] = before[lo + cnt:]
+        assert L.uaisa_opt_prepare(P(g), n, 1, P(partials), P(kl), 0.05, P(ctl), P(step), s) == 0
+        assert L.uaisa_clip_adam(P(p), P(g), P(m), P(v), n, lo, cnt, P(partials), 2.0, 1e-2, 0.9, 0.999, 1e-8, P(step), P(ctl), s) == 0
+        assert torch.allclose(p, ref_p.detach(), rtol=1e-5, atol=2e-6), (it, float((p - ref_p.detach()).abs().max()))
+    assert step.item() == 5 and ctl.tolist() == [0, 5]
+    kl.fill_(0.06)                                   # KL above the target: latch, nothing is applied any more (multi_ppo.py:362-364)
+    snap = p.clone()
+    for it in range(2):
+        if it == 1:
+            kl.fill_(0.0)                            # the latch holds for the rest of the update
+        g = torch.randn(n, generator=g0).to(dev)
+        assert L.uaisa_opt_prepare(P(g), n, 1, P(partials), P(kl), 0.05, P(ctl), P(step), s) == 0
+        assert L.uaisa_clip_adam(P(p), P(g), P(m), P(v), n, lo, cnt, P(partials), 2.0, 1e-2, 0.9, 0.999, 1e-8, P(step), P(ctl), s) == 0
+    assert torch.equal(p, snap) and step.item() == 5 and ctl.tolist() == [1, 5]
+
+
+def test_fused_forward_logp_and_value_are_close_to_the_update_path():
+    """The rollout's logp_old / value come from the fused forward (TF32 tcgen05 heads), the update evaluates with torch in fp32: bound the
+    mismatch that feeds the PPO ratio and the approx-KL early stop (target_kl 0.05)."""
+    from uaisa_env.scenario import scenario_c3
+    from uaisa_env.vec_env import VecMdin
+    from uaisa_ppo.fused import FusedPolicy
+    from uaisa_ppo.policy import rnn_ac
+
+    env = VecMdin(scenario_c3(seed=3, n_drones=8, n_buildings=2), 256); env.reset()
+    rng = np.random.default_rng(0)
+    for _ in range(12):
+        env.step(torch.from_numpy(np.round(rng.uniform(-1, 1, (env.A, 3)), 2).astype(np.float32)).cuda())
+    torch.manual_seed(5)
+    ac = rnn_ac().cuda()
+    fp = FusedPolicy(ac, env.device)
+    torch.manual_seed(11)
+    a, v, logp = fp.step(env.obs, env.count)
+    with torch.no_grad():
+        _, v_t, logp_t = ac.evaluate(env.obs, env.count, a)
+    assert float((logp - logp_t).abs().max()) < 2e-2 and float((logp - logp_t).abs().mean()) < 3e-3
+    assert float((v - v_t).abs().max()) < 2e-2
+    env.close()
+
+
+def test_fused_reader_forward_backward_matches_torch_autograd():
+    """uaisa_reader_fwd / uaisa_reader_bwd (the reader of update minibatches without multi-row samples as one forward and one backward kernel, with the
+    minibatch gathered inside the kernel) against the torch ops they replace: features to 1e-5, every parameter gradient to 1e-4 of its scale."""
+    from uaisa_ppo.policy import rnn_ac
+
+    torch.manual_seed(3)
+    ac = rnn_ac().cuda()
+    rd = ac.pi.rnn_reader
+    rng = np.random.default_rng(2)
+    n, B = 5000, 3111
+    obs = np.zeros((n, 102), np.float32)
+    obs[:, :12] = np.round(rng.normal(0, 4, (n, 12)), 2); obs[:, 0:3] += 15
+    cnt = (rng.uniform(0, 1, n) < 0.4).astype(np.uint8)
+    obs[:, 12:21] = np.round(rng.normal(0, 2, (n, 9)), 2) * cnt[:, None]
+    o, c = torch.from_numpy(obs).cuda(), torch.from_numpy(cnt).cuda()
+    idx = torch.from_numpy(rng.integers(0, n, B)).cuda()
+    wgt = torch.from_numpy(rng.normal(0, 1, (B, 268)).astype(np.float32)).cuda()
+    res = {}
+    for fused in (False, True):
+        rd.fused_step0 = fused
+        ac.zero_grad(set_to_none=True)
+        feat = ac.features(o, c, multi_cap=-1, index=idx)
+        assert (feat.grad_fn is not None) and (("ReaderStep0" in type(feat.grad_fn).__name__) == fused)
+        (feat * wgt).sum().backward()
+        res[fused] = (feat.detach().clone(), {k: p.grad.detach().clone() for k, p in rd.named_parameters() if p.grad is not None})
+    rd.fused_step0 = True
+    assert torch.allclose(res[True][0], res[False][0], rtol=1e-5, atol=2e-5), float((res[True][0] - res[False][0]).abs().max())
+    assert set(res[True][1]) >= set(res[False][1])
+    for k, g_ref in res[False][1].items():
+        g = res[True][1][k]
+        scale = float(g_ref.abs().max())
+        assert float((g - g_ref).abs().max()) <= 2e-4 * scale + 1e-6, (k, float((g - g_ref).abs().max()), scale)
+    # weight_hh never enters a single step from h0 = 0: no gradient (torch) / zero gradient (kernel)
+    for k, g in res[True][1].items():
+        if "weight_hh" in k:
+            assert float(g.abs().max()) == 0.0
+    # without an index: all rows
+    f1 = ac.features(o, c, multi_cap=-1)
+    rd.fused_step0 = False
+    f0 = ac.features(o, c, multi_cap=-1)
+    rd.fused_step0 = True
+    assert torch.allclose(f1, f0, rtol=1e-5, atol=2e-5)
+
+
+def test_unrolled_rollout_fills_the_buffers_like_the_per_step_rollout():
+    """PPOConfig.unroll_rollout (the whole epoch as one graph, env / policy kernels writing straight into the epoch buffers) against the per-step graph
+    with its buffer copies: same seeds -> identical observations, counts, actions, rewards, values, log-probs and path cuts."""
+    from uaisa_env.scenario import scenario_c1
+    from uaisa_env.vec_env import VecMdin
+    from uaisa_ppo.trainer import PPOConfig, PPOTrainer
+    bufs = []
+    for unroll in (True, False):
+        env = VecMdin(scenario_c1(), 48, neighbors_num=10)
+        tr = PPOTrainer(env, cfg=PPOConfig(steps_per_epoch=21, max_ep_len=9, unroll_rollout=unroll), seed=11)
+        assert (tr._single_graph and unroll) == unroll
+        torch.manual_seed(5)
+        tr.rollout()
+        first = {k: v.clone() for k, v in tr.buf.items()}
+        tr.rollout()                                    # a second epoch continues from the first one's final observation
+        bufs.append((first, {k: v.clone() for k, v in tr.buf.items()}, int(tr.stats["collisions"])))
+        assert (tr._graph_unrolled is not None) == unroll
+        tr.close(); env.close()
+    for ep in (0, 1):
+        for k in bufs[0][ep]:
+            a, b = bufs[0][ep][k], bufs[1][ep][k]
+            assert torch.equal(torch.nan_to_num(a.float(), 7.0), torch.nan_to_num(b.float(), 7.0)), (ep, k)
+    assert bufs[0][2] == bufs[1][2] and bufs[0][2] > 0
+    assert int(bufs[0][0]["cut"].sum()) > 0
+
+
+@pytest.mark.parametrize("mask_some", [False, True])
+def test_native_update_iteration_matches_the_autograd_iteration(mask_some):
+    """PPOConfig.native_update (reader / MLP / loss forward and backward as a fixed sequence of our own kernels, no autograd tape) against the same
+    iteration through torch autograd over the same kernels: the whole gradient bucket, the approx-KL, both losses; then parameters after an update."""
+    from uaisa_env.scenario import scenario_c1
+    from uaisa_env.vec_env import VecMdin
+    from uaisa_ppo.trainer import PPOConfig, PPOTrainer
+    res = []
+    for native in (True, False):
+        env = VecMdin(scenario_c1(), 40, neighbors_num=10)
+        tr = PPOTrainer(env, cfg=PPOConfig(steps_per_epoch=20, max_ep_len=9, train_pi_iters=3, train_v_iters=3, minibatch=1000, pi_lr=1e-3, vf_lr=1e-3, target_kl=10.0,
+                                           native_update=native, graph_update=False), seed=5)
+        torch.manual_seed(17)
+        tr.rollout()
+        if mask_some:                                      # inf / nan rewards of the reference (ir_gym.py:88): masked samples
+            tr.buf["rew"][3, 5] = float("inf"); tr.buf["rew"][7, 11] = float("nan")
+        tr._begin_update(); tr._u["cap"] = -1
+        assert tr._native() == native
+        F = tr.flat
+        F.g.zero_(); tr._pi_fb(); g_pi = F.g.clone()
+        tr._u["off"].zero_()
+        F.g.zero_(); tr._v_fb(); g_v = F.g.clone(); lv = float(tr._u["loss_v"])
+        torch.manual_seed(23)
+        p0 = F.p.clone()
+        st = tr.update()
+        res.append((g_pi, g_v, lv, F.p.clone() - p0, st["pi_iters"]))
+        tr.close(); env.close()
+    (gp1, gv1, lv1, d1, it1), (gp0, gv0, lv0, d0, it0) = res
+    for a, b, name in ((gp1, gp0, "pi gradients + kl + loss"), (gv1, gv0, "v gradients")):
+        assert float(b.abs().max()) > 0
+        assert float((a - b).abs().max()) <= 2e-5 * float(b.abs().max()) + 1e-9, (name, float((a - b).abs().max()), float(b.abs().max()))
+    assert abs(lv1 - lv0) <= 1e-5 * max(1.0, abs(lv0)) and it1 == it0 == 3
+    cos = float((d1 * d0).sum() / (d1.norm() * d0.norm()))
+    assert cos > 0.999, cos

@@ -10,8 +10,10 @@
 //     a second TMEM region (tcgen05.st) because the old state is still the A operand of the other slices; after the 4 slices the new state is copied
 //     back into the swizzled A tile.  Steps beyond an agent's own row count leave its state untouched (mask), a CTA runs max(count) steps.
 //   * weights are PRE-SWIZZLED on the device into the exact shared-memory image of each [rows x 32] tile (uaisa_policy_pack), so a weight tile is ONE
-//     bulk copy (cp.async.bulk global -> shared, the TMA engine; SASS UBLKCP) completing on an mbarrier.  One elected thread is producer and MMA issuer:
-//     a 2-stage ring (full / empty mbarriers, tcgen05.commit releases a stage) keeps the next two tiles in flight, also across the epilogues.
+//     bulk copy (cp.async.bulk global -> shared, the TMA engine; SASS UBLKCP) completing on an mbarrier.  Warp 0 is producer and MMA issuer -- the whole
+//     warp runs the ring / issue code with warp-uniform state (uniform datapath), lane 0 executes the instructions with side effects: a 2-stage ring
+//     (full / empty mbarriers, tcgen05.commit releases a stage) keeps the next two tiles in flight, also across the epilogues.
+//   * a tile without any neighbour row takes the reader's constant output h0 (packed behind the weights by uaisa_policy_pack) and skips the GRU.
 //   * 512 threads: 4 threads share an agent row (same TMEM lane quarter, different warps) and split every epilogue by 16-unit blocks, so 16 warps hide
 //     the latency of the element-wise work (gates, LayerNorm, bias + ReLU), which is most of the kernel's instructions.
 #include <cuda_runtime.h>

@@ -298,7 +298,7 @@ __global__ void __launch_bounds__(FW_NT, 1) uaisa_policy_forward_kernel(const __
             float x[12];
 #pragma unroll
             for (int k = 0; k < 12; k++) x[k] = 0.0f;
-            if (valid && ok && idx < P.nm) {
+            if (valid && ok && idx < P.nm && cnt > 0) {         // (cnt == 0: the one row the reader is fed is a zero row, whatever the observation holds)
 #pragma unroll
                 for (int k = 0; k < FW_IN; k++) x[k] = __ldg(orow + FW_SELF + FW_IN * idx + k);
             }

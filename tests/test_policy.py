@@ -247,3 +247,16 @@ def test_tiles_without_neighbour_rows_take_the_constant_reader_output():
     obs3 = obs1.clone(); obs3[keep, 12:] = obs2[keep, 12:]
     mu3, v3, f3 = fp.forward(obs3, cnt1, want_features=True)
     assert torch.equal(mu1, mu3) and torch.equal(v1, v3) and torch.equal(f1, f3)
+    # ... nor in a tile that runs the recurrence (an agent with 3 rows next to agents without any): both directions feed the zero row
+    obs4, cnt4 = obs1.clone(), cnt1.clone()
+    cnt4[5] = 3; obs4[5, 12:] = torch.randn(D - 12, device="cuda", generator=g)
+    fp.stats.zero_()
+    mu4, v4, f4 = fp.forward(obs4, cnt4, want_features=True)
+    assert fp.stats.tolist() == [1, 3]
+    keep4 = cnt4 == 0
+    obs5 = obs4.clone(); obs5[keep4, 12:] = obs2[keep4, 12:]
+    mu5, v5, f5 = fp.forward(obs5, cnt4, want_features=True)
+    assert torch.equal(mu4, mu5) and torch.equal(v4, v5) and torch.equal(f4, f5)
+    with torch.no_grad():
+        ref4 = m.features(obs4, cnt4)
+    assert (f4 - ref4).abs().max().item() < 1.5e-2 and (f4[keep4] - ref4[keep4]).abs().max().item() < 4e-3
